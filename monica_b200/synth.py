@@ -1,0 +1,157 @@
+"""Seeded synthetic inputs of the shapes BASELINE.json names (NCBI fetches are unavailable offline).
+
+Genomes are uniform-random ACGT; a fraction are mutated "strain" copies of earlier genomes so that
+repeat filtering (mid_occ > 2), MAPQ < 60 and monica's best_hit ties are exercised.
+Contig names follow the database builder's wire format ``Species:accession``
+(/root/reference/monica/genomes/database.py:59-64), which the aligner parses at
+/root/reference/monica/genomes/aligner.py:234,240.
+
+Reads are ONT-like: log-normal lengths, substitution / insertion / deletion errors at a stated mix,
+random strand.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+_ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+_COMP = np.zeros(256, dtype=np.uint8)
+for _a, _b in zip(b"ACGTNacgtn", b"TGCANtgcan"):
+    _COMP[_a] = _b
+
+
+def revcomp(seq: np.ndarray) -> np.ndarray:
+    return _COMP[seq[::-1]]
+
+
+def random_genome(rng: np.random.Generator, length: int) -> np.ndarray:
+    return _ACGT[rng.integers(0, 4, size=length, dtype=np.uint8)]
+
+
+def mutate(rng: np.random.Generator, seq: np.ndarray, sub: float, ins: float, dele: float) -> np.ndarray:
+    """Apply i.i.d. substitutions / insertions / deletions (rates per base)."""
+    n = len(seq)
+    r = rng.random(n)
+    out = seq.copy()
+    is_sub = r < sub
+    # substitution: shift to a different base
+    if is_sub.any():
+        codes = np.searchsorted(_ACGT, out[is_sub])
+        out[is_sub] = _ACGT[(codes + rng.integers(1, 4, size=int(is_sub.sum()))) % 4]
+    is_del = (r >= sub) & (r < sub + dele)
+    is_ins = (r >= sub + dele) & (r < sub + dele + ins)
+    keep = ~is_del
+    if not is_ins.any():
+        return out[keep]
+    # insertion of one random base after the position
+    reps = keep.astype(np.int64) + is_ins.astype(np.int64)
+    idx = np.repeat(np.arange(n), reps)
+    res = out[idx]
+    # positions that are the inserted copy: second occurrence for kept+ins, only occurrence for del+ins
+    first = np.ones(len(idx), dtype=bool)
+    first[1:] = idx[1:] != idx[:-1]
+    inserted = (~first) | (first & is_del[idx] & is_ins[idx])
+    res[inserted] = _ACGT[rng.integers(0, 4, size=int(inserted.sum()))]
+    return res
+
+
+def make_genomes(seed: int, n_genomes: int, genome_len: int, strain_frac: float = 0.2,
+                 strain_div: tuple[float, float] = (0.01, 0.05), contigs_per_genome: int = 1):
+    """Return (names, seqs) where names are 'Species_i:ACC_i' and seqs are uint8 ASCII arrays.
+
+    Every contig of one genome carries the same name, as monica's database builder does.
+    """
+    rng = np.random.default_rng(seed)
+    names, seqs, base = [], [], []
+    n_strain = int(round(n_genomes * strain_frac)) if n_genomes > 1 else 0
+    for g in range(n_genomes):
+        if g >= n_genomes - n_strain and base:
+            src = base[int(rng.integers(0, len(base)))]
+            d = float(rng.uniform(*strain_div))
+            s = mutate(rng, src, d * 0.8, d * 0.1, d * 0.1)
+        else:
+            s = random_genome(rng, genome_len)
+            base.append(s)
+        name = f"Species_{g}:ACC{g:05d}.1"
+        if contigs_per_genome <= 1:
+            names.append(name)
+            seqs.append(s)
+        else:
+            cuts = np.linspace(0, len(s), contigs_per_genome + 1).astype(np.int64)
+            for c in range(contigs_per_genome):
+                names.append(name)
+                seqs.append(s[cuts[c]:cuts[c + 1]])
+    return names, seqs
+
+
+def lognormal_lengths(rng: np.random.Generator, n: int, mean: float, sigma: float = 0.6,
+                      min_len: int = 200, max_len: int | None = None) -> np.ndarray:
+    mu = np.log(mean) - 0.5 * sigma * sigma
+    L = rng.lognormal(mu, sigma, size=n).astype(np.int64)
+    L = np.maximum(L, min_len)
+    if max_len is not None:
+        L = np.minimum(L, max_len)
+    return L
+
+
+def simulate_reads(seed: int, seqs: list[np.ndarray], n_reads: int, mean_len: float, error: float = 0.10,
+                   mix: tuple[float, float, float] = (0.4, 0.3, 0.3), sigma: float = 0.6,
+                   junk_frac: float = 0.0, fixed_len: int | None = None):
+    """Simulate ONT-like reads.
+
+    error is the total per-base error rate, split into (substitution, insertion, deletion) by ``mix``
+    (default 4% / 3% / 3% at error = 10%).  Returns (reads, truth) with reads a list of uint8 ASCII
+    arrays and truth a list of (contig_idx, start, end, strand) (contig_idx = -1 for junk reads).
+    """
+    rng = np.random.default_rng(seed)
+    lens = np.array([len(s) for s in seqs], dtype=np.int64)
+    prob = lens / lens.sum()
+    if fixed_len is not None:
+        L = np.full(n_reads, fixed_len, dtype=np.int64)
+    else:
+        L = lognormal_lengths(rng, n_reads, mean_len, sigma)
+    reads, truth = [], []
+    sub, ins, dele = (error * m for m in mix)
+    for i in range(n_reads):
+        if junk_frac > 0 and rng.random() < junk_frac:
+            reads.append(random_genome(rng, int(L[i])))
+            truth.append((-1, 0, 0, 0))
+            continue
+        c = int(rng.choice(len(seqs), p=prob))
+        ln = int(min(L[i], lens[c]))
+        st = int(rng.integers(0, lens[c] - ln + 1))
+        frag = seqs[c][st:st + ln]
+        strand = int(rng.integers(0, 2))
+        if strand:
+            frag = revcomp(frag)
+        reads.append(mutate(rng, frag, sub, ins, dele))
+        truth.append((c, st, st + ln, strand))
+    return reads, truth
+
+
+def concat_reads(reads: list[np.ndarray]):
+    """Concatenate reads into one uint8 buffer + int64 offsets[n+1] (the C-ABI's batch layout)."""
+    off = np.zeros(len(reads) + 1, dtype=np.int64)
+    if reads:
+        off[1:] = np.cumsum([len(r) for r in reads])
+        cat = np.concatenate(reads).astype(np.uint8, copy=False)
+    else:
+        cat = np.zeros(0, dtype=np.uint8)
+    return np.ascontiguousarray(cat), off
+
+
+def write_fastq(path: str, reads: list[np.ndarray], prefix: str = "read"):
+    with open(path, "wb") as fh:
+        for i, r in enumerate(reads):
+            fh.write(b"@" + f"{prefix}{i}".encode() + b"\n")
+            fh.write(r.tobytes() + b"\n+\n")
+            fh.write(b"I" * len(r) + b"\n")
+
+
+def write_fasta_gz(path: str, names: list[str], seqs: list[np.ndarray]):
+    import gzip
+    with gzip.open(path, "wb", compresslevel=1) as fh:
+        for n, s in zip(names, seqs):
+            fh.write(b">" + n.encode() + b"\n")
+            b = s.tobytes()
+            for i in range(0, len(b), 80):
+                fh.write(b[i:i + 80] + b"\n")
