@@ -1,0 +1,140 @@
+/*
+ * monica_b200.h -- C ABI of the B200-native mapper that replaces mappy==2.17 under monica's aligner.
+ *
+ * Loaded with ctypes (monica_b200/_lib.py).  Plain pointers and sizes only; no torch types.
+ * Every function returns 0 on success or a negative error code; mb_last_error() returns the
+ * thread-local message.  There is NO CPU fallback: every compute entry point needs a CUDA device
+ * and fails with MB_ERR_CUDA otherwise.
+ *
+ * What each entry point replaces in the reference (paths relative to /root/reference):
+ *   mb_index_build / mb_index_build_fasta / mb_index_save
+ *        mappy.Aligner(fn_idx_in=<fna.gz>, preset='map-ont', best_n=15, fn_idx_out=<mmi>)
+ *        monica/genomes/aligner.py:45-46 (indexer, :31-53)
+ *   mb_index_load
+ *        mappy.Aligner(fn_idx_in=<mmi>)            monica/genomes/aligner.py:59 (index_loader, :56-62)
+ *   mb_map_batch (+ mb_hits_*)
+ *        for hit in index.map(str(seq_record.seq)) monica/genomes/aligner.py:193,215
+ *        fields hit.is_primary .mapq .ctg .NM .mlen monica/genomes/aligner.py:194-195,216-217
+ *   mb_count
+ *        best_hit + taxon/accession Counter update monica/genomes/aligner.py:225-263,328-339
+ *   mb_sketch / mb_seed / mb_chain / mb_dp_batch
+ *        per-stage entry points for parity tests (no reference counterpart; stages of mm_map_frag)
+ */
+#ifndef MONICA_B200_H
+#define MONICA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB_OK            0
+#define MB_ERR_ARG      -1
+#define MB_ERR_CUDA     -2
+#define MB_ERR_IO       -3
+#define MB_ERR_OVERFLOW -4
+#define MB_ERR_NOMEM    -5
+
+typedef struct mb_index mb_index_t;   /* opaque: host metadata + HBM-resident index */
+typedef struct mb_hits  mb_hits_t;    /* opaque: library-owned result of one mb_map_batch call */
+
+/* Mapping options; mb_opt_init() sets minimap2-2.17 mm_mapopt_init() defaults (== map-ont apart from k). */
+typedef struct {
+	int32_t seed;
+	float   mid_occ_frac;
+	int32_t min_cnt, min_chain_score, bw, max_gap, max_gap_ref, max_chain_skip, max_chain_iter;
+	float   mask_level, pri_ratio;
+	int32_t best_n;
+	int32_t max_join_long, max_join_short, min_join_flank_sc;
+	float   min_join_flank_ratio;
+	int32_t a, b, q, e, q2, e2, sc_ambi, zdrop, zdrop_inv, end_bonus, min_dp_max, min_ksw_len;
+	float   max_clip_ratio;
+	int64_t max_sw_mat;
+	int32_t mid_occ;          /* <=0: derive from the index (mm_mapopt_update) */
+} mb_opt_t;
+
+/* Work counters of one batch (the algorithmic units bench.py's roofline uses). */
+typedef struct {
+	int64_t n_reads, n_bases, n_mini, n_anchor, n_regs, n_dp_tasks, n_dp_pass2, dp_cells, n_hits, n_rounds;
+	float   ms_sketch, ms_seed, ms_sort, ms_chain, ms_glue, ms_dp, ms_post, ms_total, ms_h2d, ms_d2h;
+	int64_t n_launches;       /* kernels launched for this batch */
+} mb_stats_t;
+
+const char *mb_last_error(void);
+int  mb_device_count(void);
+int  mb_opt_init(mb_opt_t *opt);
+
+/* ---- index ---- */
+int  mb_index_build(int device, int n_seq, const char *const *names, const uint8_t *const *seqs, const int64_t *lens,
+                    int w, int k, mb_index_t **out);
+int  mb_index_build_fasta(int device, const char *fasta_gz_path, int w, int k, mb_index_t **out);
+int  mb_index_save(const mb_index_t *idx, const char *mmi_path);
+int  mb_index_load(int device, const char *mmi_path, mb_index_t **out);
+void mb_index_free(mb_index_t *idx);
+int  mb_index_n_seq(const mb_index_t *idx);
+const char *mb_index_seq_name(const mb_index_t *idx, int rid);
+int64_t mb_index_seq_len(const mb_index_t *idx, int rid);
+int  mb_index_mid_occ(const mb_index_t *idx);
+int  mb_index_kw(const mb_index_t *idx, int *k, int *w);
+int64_t mb_index_n_minimizers(const mb_index_t *idx);
+int64_t mb_index_hbm_bytes(const mb_index_t *idx);
+
+/* ---- batch mapping: host buffers in, library-owned host hits out ----
+ * cat: concatenated ASCII reads; off[n_reads+1]: byte offsets.  Thread-safe per (index, calling thread):
+ * each calling thread gets its own CUDA stream + scratch. */
+int  mb_map_batch(mb_index_t *idx, const mb_opt_t *opt, const uint8_t *cat, const int64_t *off, int32_t n_reads,
+                  mb_hits_t **out, mb_stats_t *stats);
+/* device-resident variant used by bench.py's `value` leg: reads must already be uploaded with mb_reads_upload */
+typedef struct mb_reads mb_reads_t;
+int  mb_reads_upload(mb_index_t *idx, const uint8_t *cat, const int64_t *off, int32_t n_reads, mb_reads_t **out);
+void mb_reads_free(mb_reads_t *r);
+int  mb_map_resident(mb_index_t *idx, const mb_opt_t *opt, mb_reads_t *reads, int want_hits, mb_hits_t **out, mb_stats_t *stats);
+
+/* hits: struct-of-arrays, n = mb_hits_n(); arrays stay valid until mb_hits_free */
+int64_t mb_hits_n(const mb_hits_t *h);
+const int32_t *mb_hits_field(const mb_hits_t *h, const char *name);
+/* names: read_idx rid rev qs qe rs re mapq mlen blen nm dp_max dp_max2 score score0 cnt subsc n_sub
+ *        id parent is_primary sam_pri n_cigar */
+const int64_t *mb_hits_cigar_off(const mb_hits_t *h);   /* [n] offsets into the cigar pool */
+const uint32_t *mb_hits_cigar_pool(const mb_hits_t *h, int64_t *n);
+const int32_t *mb_hits_rep_len(const mb_hits_t *h, int64_t *n_reads); /* per read */
+void mb_hits_free(mb_hits_t *h);
+
+/* ---- counting: monica's hit filter + best_hit + per-target sum, on the device ----
+ * mode: 0 basic (+1), 1 query_length (+len(read)), 2 matching (+mlen)   (aligner.py:247-263)
+ * counts[n_seq] int64, indexed by rid (contigs of one genome share a name; the host folds by name).
+ * n_class[3] = {mapped, unmapped, ambiguous} reads.  read_class[n_reads]: 0 unmapped, 1 mapped, 2 ambiguous;
+ * read_best[n_reads]: hit index chosen or -1.  Any pointer may be NULL. */
+int  mb_count(mb_index_t *idx, const mb_hits_t *h, int32_t mapq_min, int mode, int64_t *counts, int64_t *n_class,
+              int8_t *read_class, int64_t *read_best);
+/* device pointer to the int64[n_seq] count vector of the LAST mb_count on this thread (for the NCCL allreduce) */
+void *mb_count_device_ptr(mb_index_t *idx);
+int  mb_count_fetch(mb_index_t *idx, int64_t *counts);
+
+/* ---- per-stage entry points (parity tests) ---- */
+/* minimizers of each read: out_xy[2*cap], out_off[n_reads+1]; y carries the read index in its high 32 bits */
+int  mb_sketch(int device, const uint8_t *cat, const int64_t *off, int32_t n_reads, int w, int k,
+               uint64_t *out_xy, int64_t cap, int64_t *out_off);
+/* sorted anchors of each read */
+int  mb_seed(mb_index_t *idx, const mb_opt_t *opt, const uint8_t *cat, const int64_t *off, int32_t n_reads,
+             uint64_t *out_xy, int64_t cap, int64_t *out_off, int32_t *rep_len);
+/* chaining DP arrays f,p,v for caller-provided sorted anchors (per read), plus chains */
+int  mb_chain(int device, const mb_opt_t *opt, const uint64_t *anchors_xy, const int64_t *off, int32_t n_reads,
+              int32_t *f, int32_t *p, int32_t *v,
+              uint64_t *chained_xy, int64_t *chained_off, uint64_t *u, int64_t *u_off);
+/* batch of stand-alone ksw_extd2 problems on nt4-coded sequences */
+typedef struct {
+	int32_t qlen, tlen, w, zdrop, end_bonus, flag;
+	int64_t q_off, t_off;        /* into seqpool */
+	/* outputs */
+	int32_t score, max, max_q, max_t, mqe, mqe_t, zdropped, reach_end, n_cigar;
+	int64_t cigar_off;           /* into cigar_pool; capacity qlen+tlen+1 per task, set by caller */
+} mb_dp_task_t;
+int  mb_dp_batch(int device, const mb_opt_t *opt, mb_dp_task_t *tasks, int64_t n_tasks, const uint8_t *seqpool, int64_t n_seqpool,
+                 uint32_t *cigar_pool, int64_t n_cigar_pool);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,452 @@
+// align2.cuh -- the bookkeeping kernels around k_dp: mm_test_zdrop, CIGAR stitching / Z-drop splitting,
+// mm_update_extra (mlen, blen, NM, dp_max), and the per-read finalisation (mm_filter_regs, mm_hit_sort, mm_set_parent,
+// mm_select_sub, mm_set_sam_pri, mm_set_mapq) plus hit emission in mappy's field layout (python/cmappy.h mm_reg2hitpy).
+// Reference call sites: /root/reference/monica/genomes/aligner.py:193-195,215-217.
+#pragma once
+#include "align.cuh"
+
+#define INV_SLOTS 2048
+#define INV_STRIDE (2 * 5002)
+
+MB_D void mb_update_max_zdrop(int32_t score, int i, int j, int32_t *mx, int *max_i, int *max_j, int e, int *max_zdrop, int pos[2][2])
+{
+	if (score < *mx) {
+		int li = i - *max_i, lj = j - *max_j;
+		int diff = li > lj ? li - lj : lj - li;
+		int z = *mx - score - diff * e;
+		if (z > *max_zdrop) {
+			*max_zdrop = z;
+			pos[0][0] = *max_i, pos[0][1] = *max_j;
+			pos[1][0] = i, pos[1][1] = j;
+		}
+	} else *mx = score, *max_i = i, *max_j = j;
+}
+
+MB_D int mb_mat(int ct, int cq, const mb_opt_t &o)
+{
+	if (ct > 3 || cq > 3) return -(o.sc_ambi > 0 ? o.sc_ambi : -o.sc_ambi);
+	return ct == cq ? (o.a < 0 ? -o.a : o.a) : (o.b > 0 ? -o.b : o.b);
+}
+
+// ksw2_ll_sse.c ksw_ll_i16: local single-affine score between qseq2 (reverse complement of q[qe-1..qs]) and t[ts..te)
+MB_D int mb_ll_score(const QView &qv, int q_end, int q_len, const TView &tv, int t_st, int t_len, const mb_opt_t &o, int *H, int *E)
+{
+	int gmax = 0;
+	for (int j = 0; j <= q_len; ++j) H[j] = E[j] = 0;
+	for (int i = 0; i < t_len; ++i) {
+		int f = 0, h_diag = 0;
+		const int ct = tv.at(t_st + i);
+		for (int j = 0; j < q_len; ++j) {
+			int c = qv.at(q_end - j - 1);
+			c = c >= 4 ? 4 : 3 - c;
+			int h = h_diag + mb_mat(ct, c, o);
+			int e = E[j + 1];
+			h_diag = H[j + 1];
+			h = h > e ? h : e;
+			h = h > f ? h : f;
+			h = h > 0 ? h : 0;
+			H[j + 1] = h;
+			gmax = gmax > h ? gmax : h;
+			h -= o.q + o.e; if (h < 0) h = 0;
+			e -= o.e; e = e > h ? e : h; E[j + 1] = e;
+			f -= o.e; f = f > h ? f : h;
+		}
+	}
+	return gmax;
+}
+
+// one thread per task of this round; gap fills only
+__global__ void k_ztest(AlignCtx c, DpTask *__restrict__ tasks, int64_t n_tasks, const uint32_t *__restrict__ cigar_pool,
+                        int32_t *__restrict__ pass2_list, int32_t *__restrict__ n_pass2, int *__restrict__ inv_pool, int32_t *__restrict__ inv_ctr, int *__restrict__ err)
+{
+	int64_t ti = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (ti >= n_tasks) return;
+	DpTask &T = tasks[ti];
+	if (T.kind != 1) return;
+	const mb_opt_t &opt = c.opt;
+	QView qv; qv.codes = c.codes; qv.idx0 = T.q_idx0; qv.step = T.q_step; qv.comp = T.q_comp == 1;
+	TView tv; tv.S = c.ix.S; tv.bytes = nullptr; tv.idx0 = T.t_idx0; tv.step = T.t_step; tv.packed = 1;
+	const uint32_t *cigar = cigar_pool + T.cigar_off;
+	const int n_cigar = T.n_cigar;
+	int32_t score = 0, mx = INT32_MIN, max_i = -1, max_j = -1, i = 0, j = 0, max_zdrop = 0;
+	int pos[2][2] = {{-1, -1}, {-1, -1}};
+	for (int k = 0; k < n_cigar; ++k) {
+		const uint32_t op = cigar[k] & 0xf, len = cigar[k] >> 4;
+		if (op == 0) {
+			for (uint32_t l = 0; l < len; ++l) {
+				score += mb_mat(tv.at(i + l), qv.at(j + l), opt);
+				mb_update_max_zdrop(score, i + l, j + l, &mx, &max_i, &max_j, opt.e, &max_zdrop, pos);
+			}
+			i += len, j += len;
+		} else if (op == 1 || op == 2 || op == 3) {
+			score -= opt.q + opt.e * (int)len;
+			if (op == 1) j += len; else i += len;
+			mb_update_max_zdrop(score, i, j, &mx, &max_i, &max_j, opt.e, &max_zdrop, pos);
+		}
+	}
+	int code = 0;
+	const int q_len = pos[1][1] - pos[0][1], t_len = pos[1][0] - pos[0][0];
+	if (max_zdrop > opt.zdrop_inv && q_len < opt.max_gap && t_len < opt.max_gap) {
+		int slot = atomicAdd(inv_ctr, 1);
+		if (slot >= INV_SLOTS || q_len + 1 > INV_STRIDE / 2) { *err = 3; }
+		else {
+			int *H = inv_pool + (size_t)slot * INV_STRIDE, *E = H + INV_STRIDE / 2;
+			int sc = q_len > 0 && t_len > 0 ? mb_ll_score(qv, pos[1][1], q_len, tv, pos[0][0], t_len, opt, H, E) : 0;
+			if (sc >= opt.min_chain_score * opt.a && sc >= opt.min_dp_max) code = 2;
+		}
+	}
+	if (code == 0) code = max_zdrop > opt.zdrop ? 1 : 0;
+	T.zdrop_code = code;
+	if (code) {
+		T.flag = 0; // second pass: exact max, real Z-drop
+		T.zdrop = code == 2 ? opt.zdrop_inv : opt.zdrop;
+		pass2_list[atomicAdd(n_pass2, 1)] = (int32_t)ti;
+	}
+}
+
+// ---- region CIGAR assembled in place at the first task's slot ----
+MB_D void mb_append_cigar(uint32_t *dst, int &n_dst, const uint32_t *src, int n_src)
+{
+	if (n_src == 0) return;
+	int k = 0;
+	if (n_dst > 0 && (dst[n_dst - 1] & 0xf) == (src[0] & 0xf)) { dst[n_dst - 1] += (src[0] >> 4) << 4; k = 1; }
+	for (; k < n_src; ++k) dst[n_dst++] = src[k];
+}
+
+MB_D void mb_fix_cigar(Reg *r, uint32_t *cigar, const QView &qv, const TView &tv, int *qshift, int *tshift)
+{
+	int32_t toff = 0, qoff = 0, to_shrink = 0;
+	int n_cigar = r->n_cigar;
+	*qshift = *tshift = 0;
+	if (n_cigar <= 1) return;
+	for (int k = 0; k < n_cigar; ++k) {
+		const uint32_t op = cigar[k] & 0xf, len = cigar[k] >> 4;
+		if (len == 0) to_shrink = 1;
+		if (op == 0) {
+			toff += len, qoff += len;
+		} else if (op == 1 || op == 2) {
+			if (k > 0 && k < n_cigar - 1 && (cigar[k - 1] & 0xf) == 0 && (cigar[k + 1] & 0xf) == 0) {
+				int l, prev_len = (int)(cigar[k - 1] >> 4);
+				if (op == 1) {
+					for (l = 0; l < prev_len; ++l)
+						if (qv.at(qoff - 1 - l) != qv.at(qoff + (int)len - 1 - l)) break;
+				} else {
+					for (l = 0; l < prev_len; ++l)
+						if (tv.at(toff - 1 - l) != tv.at(toff + (int)len - 1 - l)) break;
+				}
+				if (l > 0) cigar[k - 1] -= (uint32_t)l << 4, cigar[k + 1] += (uint32_t)l << 4, qoff -= l, toff -= l;
+				if (l == prev_len) to_shrink = 1;
+			}
+			if (op == 1) qoff += len; else toff += len;
+		} else if (op == 3) toff += len;
+	}
+	if (to_shrink) {
+		int l = 0;
+		for (int k = 0; k < n_cigar; ++k)
+			if (cigar[k] >> 4 != 0) cigar[l++] = cigar[k];
+		n_cigar = l;
+		l = 0;
+		for (int k = 0; k < n_cigar; ++k)
+			if (k == n_cigar - 1 || (cigar[k] & 0xf) != (cigar[k + 1] & 0xf)) cigar[l++] = cigar[k];
+			else cigar[k + 1] += cigar[k] >> 4 << 4;
+		n_cigar = l;
+	}
+	if ((cigar[0] & 0xf) == 1 || (cigar[0] & 0xf) == 2) {
+		const int32_t l = (int32_t)(cigar[0] >> 4);
+		if ((cigar[0] & 0xf) == 1) {
+			if (r->rev) r->qe -= l; else r->qs += l;
+			*qshift = l;
+		} else r->rs += l, *tshift = l;
+		--n_cigar;
+		for (int k = 0; k < n_cigar; ++k) cigar[k] = cigar[k + 1];
+	}
+	r->n_cigar = n_cigar;
+}
+
+MB_D void mb_update_extra(Reg *r, uint32_t *cigar, QView qv, TView tv, const mb_opt_t &opt)
+{
+	int32_t s = 0, mx = 0, qshift, tshift, toff = 0, qoff = 0;
+	if (!r->has_p) return;
+	mb_fix_cigar(r, cigar, qv, tv, &qshift, &tshift);
+	qv.idx0 += (int64_t)qshift * qv.step, tv.idx0 += (int64_t)tshift * tv.step;
+	r->blen = r->mlen = 0;
+	for (int k = 0; k < r->n_cigar; ++k) {
+		const uint32_t op = cigar[k] & 0xf, len = cigar[k] >> 4;
+		if (op == 0) {
+			int n_ambi = 0, n_diff = 0;
+			for (uint32_t l = 0; l < len; ++l) {
+				const int cq = qv.at(qoff + l), ct = tv.at(toff + l);
+				if (ct > 3 || cq > 3) ++n_ambi;
+				else if (ct != cq) ++n_diff;
+				s += mb_mat(ct, cq, opt);
+				if (s < 0) s = 0;
+				else mx = mx > s ? mx : s;
+			}
+			r->blen += len - n_ambi, r->mlen += len - (n_ambi + n_diff), r->n_ambi += n_ambi;
+			toff += len, qoff += len;
+		} else if (op == 1) {
+			int n_ambi = 0;
+			for (uint32_t l = 0; l < len; ++l) if (qv.at(qoff + l) > 3) ++n_ambi;
+			r->blen += len - n_ambi, r->n_ambi += n_ambi;
+			s -= opt.q + opt.e * (int)len;
+			if (s < 0) s = 0;
+			qoff += len;
+		} else if (op == 2) {
+			int n_ambi = 0;
+			for (uint32_t l = 0; l < len; ++l) if (tv.at(toff + l) > 3) ++n_ambi;
+			r->blen += len - n_ambi, r->n_ambi += n_ambi;
+			s -= opt.q + opt.e * (int)len;
+			if (s < 0) s = 0;
+			toff += len;
+		} else if (op == 3) toff += len;
+	}
+	r->dp_max = mx;
+}
+
+// one thread per region of this round: the part of mm_align1 after each mm_align_pair
+__global__ void k_stitch(AlignCtx c, ReadArrays ra, const int2 *__restrict__ work, int n_work, const RegPlan *__restrict__ plans,
+                         DpTask *__restrict__ tasks, uint32_t *__restrict__ cigar_pool,
+                         int2 *__restrict__ next_work, int32_t *__restrict__ n_next, int *__restrict__ err)
+{
+	int wi = blockIdx.x * blockDim.x + threadIdx.x;
+	if (wi >= n_work) return;
+	const int read = work[wi].x, slot = work[wi].y;
+	Reg *regs = ra.regs + ra.reg_off[read];
+	Reg *r = regs + slot;
+	const mb128 *a = ra.a + ra.a_roff[read];
+	const RegPlan pl = plans[wi];
+	const mb_opt_t &opt = c.opt;
+	const int64_t roff = c.read_off[read];
+	const int qlen = (int)(c.read_off[read + 1] - roff);
+	r->aligned = 1;
+	if (r->cnt == 0) return;
+	const int rev = r->rev, rid = r->rid;
+	const int k2 = c.ix.k >> 1;
+	DpTask *T = tasks + pl.task0;
+	int ti = 0, n_cig = 0, dropped = 0;
+	uint32_t *cig = pl.n_tasks > 0 ? cigar_pool + T[0].cigar_off : nullptr;
+	int32_t rs = pl.rs, qs = pl.qs, re = pl.re, qe = pl.qe, rs1, qs1, re1, qe1;
+	int32_t dp_score = 0;
+	if (pl.has_left) {
+		const DpTask &t = T[ti++];
+		if (t.n_cigar > 0) { mb_append_cigar(cig, n_cig, cigar_pool + t.cigar_off, t.n_cigar); dp_score += t.max; }
+		rs1 = rs - (t.reach_end ? t.mqe_t + 1 : t.max_t + 1);
+		qs1 = qs - (t.reach_end ? qs - pl.qs0 : t.max_q + 1);
+	} else rs1 = rs, qs1 = qs;
+	re1 = rs, qe1 = qs;
+	for (int i = 1; i < pl.cnt1; ++i) {
+		const mb128 ai = a[pl.as1 + i];
+		if ((ai.y & (MB_SEED_IGNORE | MB_SEED_TANDEM)) && i != pl.cnt1 - 1) continue;
+		re = (int32_t)ai.x - k2, qe = (int32_t)ai.y - k2;
+		re1 = re, qe1 = qe;
+		if (i == pl.cnt1 - 1 || (ai.y & MB_SEED_LONG_JOIN) || (qe - qs >= opt.min_ksw_len && re - rs >= opt.min_ksw_len)) {
+			const DpTask &t = T[ti++];
+			if (t.n_cigar > 0) mb_append_cigar(cig, n_cig, cigar_pool + t.cigar_off, t.n_cigar);
+			if (t.zdropped) {
+				int j;
+				for (j = i - 1; j >= 0; --j)
+					if ((int32_t)a[pl.as1 + j].x <= rs + t.max_t) break;
+				dropped = 1;
+				if (j < 0) j = 0;
+				dp_score += t.max;
+				re1 = rs + (t.max_t + 1);
+				qe1 = qs + (t.max_q + 1);
+				if (pl.cnt1 - (j + 1) >= opt.min_cnt) {
+					const int n_split = pl.as1 + j + 1 - r->as;
+					if (n_split > 0 && n_split < r->cnt) {
+						const int ns = atomicAdd(&ra.n_regs[read], 1);
+						if (ns >= (int)(ra.reg_off[read + 1] - ra.reg_off[read])) { *err = 2; atomicSub(&ra.n_regs[read], 1); }
+						else {
+							Reg *r2 = regs + ns;
+							mb_split_reg(r, r2, n_split, qlen, a);
+							r2->slot = ns;
+							if (t.zdrop_code == 2) r2->split_inv = 1;
+							r->next_split = ns;
+							next_work[atomicAdd(n_next, 1)] = make_int2(read, ns);
+						}
+					}
+				}
+				break;
+			} else dp_score += t.score;
+			rs = re, qs = qe;
+		}
+	}
+	if (!dropped && pl.has_right) {
+		const DpTask &t = T[pl.n_tasks - 1];
+		if (t.n_cigar > 0) { mb_append_cigar(cig, n_cig, cigar_pool + t.cigar_off, t.n_cigar); dp_score += t.max; }
+		re1 = re + (t.reach_end ? t.mqe_t + 1 : t.max_t + 1);
+		qe1 = qe + (t.reach_end ? pl.qe0 - qe : t.max_q + 1);
+	}
+	r->rs = rs1, r->re = re1;
+	if (rev) r->qs = qlen - qe1, r->qe = qlen - qs1;
+	else r->qs = qs1, r->qe = qe1;
+	if (n_cig > 0) {
+		r->has_p = 1, r->n_cigar = n_cig, r->cigar_off = T[0].cigar_off, r->dp_score = dp_score;
+		QView qv; qv.codes = c.codes;
+		if (!rev) qv.idx0 = roff + qs1, qv.step = 1, qv.comp = 0;
+		else qv.idx0 = roff + qlen - 1 - qs1, qv.step = -1, qv.comp = 1;
+		TView tv; tv.S = c.ix.S; tv.bytes = nullptr; tv.idx0 = (int64_t)c.ix.seq_off[rid] + rs1; tv.step = 1; tv.packed = 1;
+		mb_update_extra(r, cig, qv, tv, opt);
+	}
+}
+
+// ---- per-read kernels before / after the alignment rounds ----
+struct ReadScratch {
+	mb128 *b;          // mb128[n_a]  (same offsets as anchors)
+	uint64_t *u;       // u64[n_a]
+	uint64_t *scr;     // u64[3*n_a + 3*n_reads]: offset 3*a_roff[r] + 3*r
+	int32_t *f, *p, *v, *t;
+	Reg *regs_tmp;     // same offsets as regs
+};
+
+// G1a: chain backtrack; writes n_u per read
+__global__ void k_chain_bt(ReadArrays ra, ReadScratch rs, int n_reads, int min_cnt, int min_sc, int32_t *__restrict__ n_u, int *__restrict__ err)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	const int64_t base = ra.a_roff[r];
+	const int n = (int)(ra.a_roff[r + 1] - base);
+	int e = 0;
+	n_u[r] = mb_chain_backtrack(n, ra.a + base, rs.f + base, rs.p + base, rs.v + base, rs.t + base, rs.b + base, rs.u + base,
+	                            rs.scr + 3 * base + 3 * r, min_cnt, min_sc, &e);
+	if (e) *err = 1;
+}
+
+__global__ void k_reg_cap(const int32_t *__restrict__ n_u, const int64_t *__restrict__ a_roff, int n_reads, int32_t *__restrict__ cap)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	int n_a = (int)(a_roff[r + 1] - a_roff[r]);
+	int extra = n_a / 3; if (extra > 32) extra = 32;
+	cap[r] = n_u[r] ? n_u[r] + extra + 2 : 0;
+}
+
+// G1b: mm_gen_regs + chain_post (mm_set_parent, mm_select_sub, mm_join_long) + mm_squeeze_a of mm_align_skeleton
+__global__ void k_gen_regs(AlignCtx c, ReadArrays ra, ReadScratch rs, int n_reads, const int32_t *__restrict__ n_u, int32_t *__restrict__ n_a_sq,
+                           int2 *__restrict__ work, int32_t *__restrict__ n_work, int *__restrict__ err)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	const mb_opt_t &opt = c.opt;
+	const int64_t base = ra.a_roff[r];
+	const int qlen = (int)(c.read_off[r + 1] - c.read_off[r]);
+	int n = n_u[r];
+	ra.n_regs[r] = 0;
+	n_a_sq[r] = 0;
+	if (n == 0) return;
+	mb128 *a = ra.a + base;
+	Reg *regs = ra.regs + ra.reg_off[r];
+	uint64_t *scr = rs.scr + 3 * base + 3 * r;
+	int *iscr = ra.iscr + base;
+	int e = 0;
+	uint32_t hash = 0;
+	hash ^= mb_wang32((uint32_t)qlen) + mb_wang32((uint32_t)opt.seed);
+	hash = mb_wang32(hash);
+	mb_gen_regs(hash, qlen, n, rs.u + base, a, regs, (mb128*)scr, &e);
+	mb_set_parent(opt.mask_level, n, regs, opt.a * 2 + opt.b, scr, iscr, &e);
+	mb_select_sub(opt.pri_ratio, c.ix.k * 2, opt.best_n, &n, regs, iscr);
+	mb_join_long(&opt, qlen, &n, regs, a, scr, iscr, &e);
+	// mm_align_skeleton: n_a = mm_squeeze_a(...)
+	n_a_sq[r] = mb_squeeze_a(n, regs, a, scr, &e);
+	for (int i = 0; i < n; ++i) regs[i].slot = i, regs[i].next_split = -1, regs[i].aligned = 0;
+	ra.n_regs[r] = n;
+	if (n > 0) {
+		int w0 = atomicAdd(n_work, n);
+		for (int i = 0; i < n; ++i) work[w0 + i] = make_int2(r, i);
+	}
+	if (e) *err = 1;
+}
+
+// after the alignment rounds: restore upstream's region order (a split-off region sits right after its source), then
+// mm_filter_regs, mm_hit_sort, mm_set_parent, mm_select_sub, mm_set_sam_pri, mm_set_mapq
+__global__ void k_finish(AlignCtx c, ReadArrays ra, ReadScratch rs, int n_reads, const int32_t *__restrict__ n0_regs, const int32_t *__restrict__ rep_len,
+                         int32_t *__restrict__ n_hits, int32_t *__restrict__ n_hit_cigar, int *__restrict__ err)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	const mb_opt_t &opt = c.opt;
+	const int64_t base = ra.a_roff[r];
+	const int qlen = (int)(c.read_off[r + 1] - c.read_off[r]);
+	Reg *regs = ra.regs + ra.reg_off[r], *tmp = rs.regs_tmp + ra.reg_off[r];
+	uint64_t *scr = rs.scr + 3 * base + 3 * r;
+	int *iscr = ra.iscr + base;
+	int n_all = ra.n_regs[r], n0 = n0_regs[r], n = 0, e = 0;
+	n_hits[r] = 0, n_hit_cigar[r] = 0;
+	if (n_all == 0) return;
+	for (int i = 0; i < n0; ++i) {
+		int s = i;
+		while (s >= 0) { tmp[n++] = regs[s]; s = regs[s].next_split; }
+	}
+	for (int i = 0; i < n; ++i) regs[i] = tmp[i];
+	mb_filter_regs(&opt, qlen, &n, regs);
+	mb_hit_sort(&n, regs, (mb128*)scr, tmp, &e);
+	mb_set_parent(opt.mask_level, n, regs, opt.a * 2 + opt.b, scr, iscr, &e);
+	mb_select_sub(opt.pri_ratio, c.ix.k * 2, opt.best_n, &n, regs, iscr);
+	mb_set_sam_pri(n, regs);
+	mb_set_mapq(n, regs, opt.min_chain_score, opt.a, rep_len[r]);
+	ra.n_regs[r] = n;
+	n_hits[r] = n;
+	int nc = 0;
+	for (int i = 0; i < n; ++i) nc += regs[i].has_p ? regs[i].n_cigar : 0;
+	n_hit_cigar[r] = nc;
+	if (e) *err = 1;
+}
+
+#define HIT_NF 23
+// field order: read_idx rid rev qs qe rs re mapq mlen blen nm dp_max dp_max2 score score0 cnt subsc n_sub id parent is_primary sam_pri n_cigar
+__global__ void k_write_hits(ReadArrays ra, int n_reads, const int64_t *__restrict__ hit_off, const int64_t *__restrict__ cig_off, int64_t n_hits_total,
+                             int32_t *__restrict__ fields, int64_t *__restrict__ hit_cig_off, const uint32_t *__restrict__ cigar_pool, uint32_t *__restrict__ out_cigar)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	const Reg *regs = ra.regs + ra.reg_off[r];
+	const int n = ra.n_regs[r];
+	int64_t h = hit_off[r], co = cig_off[r];
+	for (int i = 0; i < n; ++i, ++h) {
+		const Reg &g = regs[i];
+		const int32_t vals[HIT_NF] = { r, g.rid, g.rev, g.qs, g.qe, g.rs, g.re, g.mapq, g.mlen, g.blen,
+			g.blen - g.mlen + (g.has_p ? g.n_ambi : 0), g.has_p ? g.dp_max : 0, g.has_p ? g.dp_max2 : 0, g.score, g.score0, g.cnt, g.subsc, g.n_sub,
+			g.id, g.parent, g.id == g.parent, g.sam_pri, g.has_p ? g.n_cigar : 0 };
+		#pragma unroll
+		for (int f = 0; f < HIT_NF; ++f) fields[(int64_t)f * n_hits_total + h] = vals[f];
+		hit_cig_off[h] = co;
+		if (g.has_p) {
+			const uint32_t *src = cigar_pool + g.cigar_off;
+			for (int k = 0; k < g.n_cigar; ++k) out_cigar[co + k] = src[k];
+			co += g.n_cigar;
+		}
+	}
+}
+
+// ---- monica's hit filter + best_hit + per-target sum (aligner.py:193-195,225-263,328-339) ----
+// best_hit scans hits left to right with `<=` on NM/mlen and returns 0 (ambiguous) iff the minimum occurs twice or more.
+// float(NM)/mlen comparisons are done exactly by cross-multiplication (NM, mlen < 2^31).
+__global__ void k_count(int n_reads, const int64_t *__restrict__ hit_off, int64_t n_hits_total, const int32_t *__restrict__ fields,
+                        const int64_t *__restrict__ read_off, int mapq_min, int mode,
+                        unsigned long long *__restrict__ counts, unsigned long long *__restrict__ n_class, int8_t *__restrict__ read_class, int64_t *__restrict__ read_best)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	const int32_t *F_rid = fields + 1 * n_hits_total, *F_mapq = fields + 7 * n_hits_total, *F_mlen = fields + 8 * n_hits_total;
+	const int32_t *F_nm = fields + 10 * n_hits_total, *F_pri = fields + 20 * n_hits_total;
+	int64_t best = -1; int n_kept = 0; bool tie = false;
+	for (int64_t h = hit_off[r]; h < hit_off[r + 1]; ++h) {
+		if (!(F_pri[h] && F_mapq[h] >= mapq_min)) continue;
+		++n_kept;
+		if (best < 0) { best = h; tie = false; continue; }
+		// inverse_identity(h) <= inverse_identity(best)  <=>  nm_h * mlen_b <= nm_b * mlen_h
+		const long long lhs = (long long)F_nm[h] * F_mlen[best], rhs = (long long)F_nm[best] * F_mlen[h];
+		if (lhs <= rhs) { tie = (lhs == rhs); best = h; }
+	}
+	int cls = 0;
+	if (n_kept == 0) cls = 0;
+	else if (n_kept >= 2 && tie) cls = 2, best = -1;
+	else cls = 1;
+	if (read_class) read_class[r] = (int8_t)cls;
+	if (read_best) read_best[r] = best;
+	atomicAdd(&n_class[cls == 1 ? 0 : cls == 0 ? 1 : 2], 1ULL);
+	if (cls == 1 && counts) {
+		unsigned long long inc = mode == 0 ? 1ULL : mode == 1 ? (unsigned long long)(read_off[r + 1] - read_off[r]) : mode == 2 ? (unsigned long long)F_mlen[best] : 0ULL;
+		if (inc) atomicAdd(&counts[F_rid[best]], inc);
+	}
+}

@@ -1,0 +1,1002 @@
+// monica_b200.cu -- C-ABI implementation (include/monica_b200.h) and the per-batch device pipeline.
+//
+// Pipeline of one batch (all on the calling thread's stream; the host only learns array sizes between stages):
+//   H2D reads -> k_encode_nt4 -> K1 k_sketch -> K2 k_seed_lookup/k_seed_fill -> K2b k_sort_anchors
+//   -> K3 k_chain_dp -> k_chain_bt / k_gen_regs (region logic) -> rounds of { k_plan1, k_plan2, K4 k_dp, k_ztest, k_dp, k_stitch }
+//   -> k_finish -> k_write_hits -> D2H hits.
+// There is no CPU fallback anywhere in this file: every compute entry point throws MB_ERR_CUDA without a device.
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <zlib.h>
+#include "common.cuh"
+#include "sketch.cuh"
+#include "seed.cuh"
+#include "chain.cuh"
+#include "glue.cuh"
+#include "align.cuh"
+#include "align2.cuh"
+
+thread_local std::string g_mb_err;
+
+extern "C" const char *mb_last_error(void) { return g_mb_err.c_str(); }
+
+#define API_BEGIN try {
+#define API_END   } catch (const mb_error &e) { g_mb_err = e.what(); return e.code; } \
+                    catch (const std::exception &e) { g_mb_err = e.what(); return MB_ERR_ARG; } \
+                    return MB_OK;
+
+extern "C" int mb_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+
+extern "C" int mb_opt_init(mb_opt_t *opt)
+{
+	if (!opt) return MB_ERR_ARG;
+	memset(opt, 0, sizeof(*opt));
+	opt->seed = 11;
+	opt->mid_occ_frac = 2e-4f;
+	opt->min_cnt = 3, opt->min_chain_score = 40, opt->bw = 500, opt->max_gap = 5000, opt->max_gap_ref = -1;
+	opt->max_chain_skip = 25, opt->max_chain_iter = 5000;
+	opt->mask_level = 0.5f, opt->pri_ratio = 0.8f, opt->best_n = 5;
+	opt->max_join_long = 20000, opt->max_join_short = 2000, opt->min_join_flank_sc = 1000, opt->min_join_flank_ratio = 0.5f;
+	opt->a = 2, opt->b = 4, opt->q = 4, opt->e = 2, opt->q2 = 24, opt->e2 = 1, opt->sc_ambi = 1;
+	opt->zdrop = 400, opt->zdrop_inv = 200, opt->end_bonus = -1;
+	opt->min_dp_max = opt->min_chain_score * opt->a;
+	opt->min_ksw_len = 200;
+	opt->max_clip_ratio = 1.0f;
+	opt->max_sw_mat = 100000000;
+	opt->mid_occ = 0;
+	return MB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-thread device context
+// ---------------------------------------------------------------------------------------------
+struct ThreadCtx {
+	int device = -1;
+	cudaStream_t st = nullptr;
+	Arena ar;
+	int num_sms = 148;
+	uint8_t *h_pin = nullptr; size_t h_pin_cap = 0;   // pinned staging for reads
+	unsigned long long *d_counts = nullptr; int n_counts = 0; // last mb_count vector
+	~ThreadCtx() {
+		if (device >= 0) {
+			cudaSetDevice(device);
+			ar.release();
+			if (h_pin) cudaFreeHost(h_pin);
+			if (d_counts) cudaFree(d_counts);
+			if (st) cudaStreamDestroy(st);
+		}
+	}
+};
+static thread_local std::map<int, ThreadCtx*> t_ctx;
+
+static void ensure_device(int device)
+{
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0) { cudaGetLastError(); throw mb_error(MB_ERR_CUDA, "no CUDA device available: monica_b200 has no CPU fallback"); }
+	if (device < 0 || device >= n) throw mb_error(MB_ERR_ARG, "bad device ordinal");
+	CK(cudaSetDevice(device));
+}
+
+static std::once_flag g_const_once[16];
+
+static ThreadCtx &get_ctx(int device)
+{
+	ensure_device(device);
+	auto it = t_ctx.find(device);
+	if (it != t_ctx.end()) return *it->second;
+	ThreadCtx *c = new ThreadCtx();
+	c->device = device;
+	CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+	cudaDeviceProp prop;
+	CK(cudaGetDeviceProperties(&prop, device));
+	c->num_sms = prop.multiProcessorCount;
+	std::call_once(g_const_once[device & 15], [&]() {
+		CK(cudaMemcpyToSymbol(c_nt4, h_nt4, 256));
+		CK(cudaFuncSetAttribute(k_dp, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_WARPS * DP_SMEM_PER_WARP));
+	});
+	t_ctx[device] = c;
+	return *c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// index
+// ---------------------------------------------------------------------------------------------
+struct mb_index {
+	int device = 0;
+	int k = 15, w = 10, b = 14;
+	std::vector<std::string> names;
+	std::vector<uint32_t> lens;
+	std::vector<uint64_t> offs;
+	uint64_t sum_len = 0;
+	int64_t n_mini = 0, n_keys = 0;
+	int mid_occ = 0;
+	// host copies (kept for save)
+	std::vector<uint64_t> h_hkey, h_hval, h_pos;
+	std::vector<uint32_t> h_S;
+	DevIndex d;
+	int64_t hbm_bytes = 0;
+};
+
+__global__ void k_pack4(const uint8_t *__restrict__ codes, uint32_t *__restrict__ S, int64_t n)
+{
+	int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (w * 8 >= n) return;
+	uint32_t v = 0;
+	#pragma unroll
+	for (int j = 0; j < 8; ++j) {
+		int64_t i = w * 8 + j;
+		uint32_t c = i < n ? codes[i] : 0;
+		v |= c << (j << 2);
+	}
+	S[w] = v;
+}
+
+static void index_upload(mb_index *ix)
+{
+	DevIndex &d = ix->d;
+	size_t cap = ix->h_hkey.size();
+	CK(cudaMalloc(&d.hkey, cap * 8)); CK(cudaMalloc(&d.hval, cap * 8));
+	CK(cudaMalloc(&d.pos, (ix->h_pos.size() + 1) * 8));
+	CK(cudaMalloc(&d.S, (ix->h_S.size() + 1) * 4));
+	CK(cudaMalloc(&d.seq_off, (ix->offs.size() + 1) * 8));
+	CK(cudaMalloc(&d.seq_len, (ix->lens.size() + 1) * 4));
+	CK(cudaMemcpy(d.hkey, ix->h_hkey.data(), cap * 8, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(d.hval, ix->h_hval.data(), cap * 8, cudaMemcpyHostToDevice));
+	if (!ix->h_pos.empty()) CK(cudaMemcpy(d.pos, ix->h_pos.data(), ix->h_pos.size() * 8, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(d.S, ix->h_S.data(), ix->h_S.size() * 4, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(d.seq_off, ix->offs.data(), ix->offs.size() * 8, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(d.seq_len, ix->lens.data(), ix->lens.size() * 4, cudaMemcpyHostToDevice));
+	d.hmask = cap - 1;
+	int bits = 0; while (((size_t)1 << bits) < cap) ++bits;
+	d.hshift = 64 - bits;
+	d.n_seq = (int)ix->names.size(); d.k = ix->k; d.w = ix->w; d.mid_occ = ix->mid_occ;
+	ix->hbm_bytes = (int64_t)(cap * 16 + ix->h_pos.size() * 8 + ix->h_S.size() * 4 + ix->offs.size() * 12);
+}
+
+// build the hash table from minimizers sorted by (hash, y): index.c worker_post() semantics
+static void index_build_table(mb_index *ix, std::vector<mb128> &m)
+{
+	std::sort(m.begin(), m.end(), [](const mb128 &a, const mb128 &b) {
+		uint64_t ha = a.x >> 8, hb = b.x >> 8;
+		return ha != hb ? ha < hb : a.y < b.y;
+	});
+	ix->n_mini = (int64_t)m.size();
+	size_t n_keys = 0;
+	for (size_t i = 0; i < m.size(); ++i) if (i == 0 || (m[i].x >> 8) != (m[i - 1].x >> 8)) ++n_keys;
+	ix->n_keys = (int64_t)n_keys;
+	size_t cap = 1024; while (cap < n_keys * 2 + 2) cap <<= 1;
+	int bits = 0; while (((size_t)1 << bits) < cap) ++bits;
+	ix->h_hkey.assign(cap, ~0ULL); ix->h_hval.assign(cap, 0);
+	ix->h_pos.clear();
+	std::vector<uint32_t> occ; occ.reserve(n_keys);
+	for (size_t i = 0; i < m.size();) {
+		size_t j = i; uint64_t h = m[i].x >> 8;
+		while (j < m.size() && (m[j].x >> 8) == h) ++j;
+		size_t n = j - i;
+		occ.push_back((uint32_t)n);
+		uint64_t slot = mb_slot_hash(h, 64 - bits) & (cap - 1);
+		while (ix->h_hkey[slot] != ~0ULL) slot = (slot + 1) & (cap - 1);
+		if (n == 1) { ix->h_hkey[slot] = h << 1 | 1; ix->h_hval[slot] = m[i].y; }
+		else {
+			ix->h_hkey[slot] = h << 1;
+			ix->h_hval[slot] = (uint64_t)ix->h_pos.size() << 32 | (uint32_t)n;
+			for (size_t k = i; k < j; ++k) ix->h_pos.push_back(m[k].y);
+		}
+		i = j;
+	}
+	// index.c mm_idx_cal_max_occ(mi, 2e-4): ks_ksmall(counts, (1-f)*n) + 1
+	if (!occ.empty()) {
+		size_t kth = (size_t)(uint32_t)((1. - (double)2e-4f) * occ.size());
+		if (kth >= occ.size()) kth = occ.size() - 1;
+		std::nth_element(occ.begin(), occ.begin() + kth, occ.end());
+		ix->mid_occ = (int)occ[kth] + 1;
+	} else ix->mid_occ = 1;
+}
+
+static mb_index *index_build_impl(int device, int n_seq, const char *const *names, const uint8_t *const *seqs, const int64_t *lens, int w, int k)
+{
+	ThreadCtx &c = get_ctx(device);
+	std::unique_ptr<mb_index> ix(new mb_index());
+	ix->device = device, ix->k = k, ix->w = w;
+	uint64_t sum = 0;
+	for (int i = 0; i < n_seq; ++i) {
+		if (lens[i] < 0 || lens[i] > 0x7fffffffLL) throw mb_error(MB_ERR_ARG, "contig longer than 2^31");
+		ix->names.push_back(names[i]); ix->lens.push_back((uint32_t)lens[i]); ix->offs.push_back(sum); sum += (uint64_t)lens[i];
+	}
+	ix->sum_len = sum;
+	c.ar.reset();
+	cudaStream_t st = c.st;
+	// upload contigs as one "read batch": the sketch kernel stores the sequence index in y>>32, which is mm_idx's rid
+	std::vector<int64_t> off(n_seq + 1, 0);
+	for (int i = 0; i < n_seq; ++i) off[i + 1] = off[i] + lens[i];
+	uint8_t *d_ascii = c.ar.get<uint8_t>(sum + 16), *d_codes = c.ar.get<uint8_t>(sum + 16);
+	int64_t *d_off = c.ar.get<int64_t>(n_seq + 1);
+	for (int i = 0; i < n_seq; ++i) if (lens[i]) CK(cudaMemcpyAsync(d_ascii + off[i], seqs[i], lens[i], cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(d_off, off.data(), (n_seq + 1) * 8, cudaMemcpyHostToDevice, st));
+	int64_t nl = 0;
+	if (sum) k_encode_nt4<<<(unsigned)cdiv(cdiv((int64_t)sum, 16), 256), 256, 0, st>>>(d_ascii, d_codes, (int64_t)sum);
+	SketchOut so;
+	run_sketch(c.ar, st, d_codes, d_off, n_seq, (int64_t)sum, w, k, so, &nl);
+	std::vector<mb128> m(so.n_mini);
+	if (so.n_mini) CK(cudaMemcpyAsync(m.data(), so.mini, so.n_mini * sizeof(mb128), cudaMemcpyDeviceToHost, st));
+	uint32_t *d_S = c.ar.get<uint32_t>(sum / 8 + 2);
+	if (sum) k_pack4<<<(unsigned)cdiv(cdiv((int64_t)sum, 8), 256), 256, 0, st>>>(d_codes, d_S, (int64_t)sum);
+	ix->h_S.assign((sum + 7) / 8, 0);
+	if (sum) CK(cudaMemcpyAsync(ix->h_S.data(), d_S, ix->h_S.size() * 4, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	CK(cudaGetLastError());
+	index_build_table(ix.get(), m);
+	index_upload(ix.get());
+	c.ar.reset();
+	return ix.release();
+}
+
+extern "C" int mb_index_build(int device, int n_seq, const char *const *names, const uint8_t *const *seqs, const int64_t *lens, int w, int k, mb_index_t **out)
+{
+	API_BEGIN
+	if (!out || n_seq < 0) throw mb_error(MB_ERR_ARG, "bad arguments");
+	*out = index_build_impl(device, n_seq, names, seqs, lens, w, k);
+	API_END
+}
+
+extern "C" int mb_index_build_fasta(int device, const char *path, int w, int k, mb_index_t **out)
+{
+	API_BEGIN
+	gzFile fp = gzopen(path, "rb");
+	if (!fp) throw mb_error(MB_ERR_IO, std::string("cannot open ") + path);
+	std::vector<std::string> names; std::vector<std::string> seqs;
+	std::vector<char> buf(1 << 20);
+	std::string line;
+	bool in_name = false;
+	int n;
+	auto flush_line = [&](const std::string &l) {
+		if (l.empty()) return;
+		if (l[0] == '>') {
+			size_t e = l.find_first_of(" \t", 1);
+			names.push_back(l.substr(1, e == std::string::npos ? std::string::npos : e - 1));
+			seqs.emplace_back();
+		} else if (!seqs.empty()) seqs.back() += l;
+	};
+	(void)in_name;
+	while ((n = gzread(fp, buf.data(), (unsigned)buf.size())) > 0) {
+		for (int i = 0; i < n; ++i) {
+			char ch = buf[i];
+			if (ch == '\n') { flush_line(line); line.clear(); }
+			else if (ch != '\r') line.push_back(ch);
+		}
+	}
+	flush_line(line);
+	gzclose(fp);
+	if (names.empty()) throw mb_error(MB_ERR_IO, std::string("no sequences in ") + path);
+	std::vector<const char*> np; std::vector<const uint8_t*> sp; std::vector<int64_t> lp;
+	for (size_t i = 0; i < names.size(); ++i) { np.push_back(names[i].c_str()); sp.push_back((const uint8_t*)seqs[i].data()); lp.push_back((int64_t)seqs[i].size()); }
+	*out = index_build_impl(device, (int)names.size(), np.data(), sp.data(), lp.data(), w, k);
+	API_END
+}
+
+// ---- on-disk format ----
+// Written in minimap2's .mmi layout (index.c mm_idx_dump): "MMI\2", u32 w,k,b,n_seq,flag; per sequence u8 name_len, name,
+// u32 len; per bucket (2^b of them) i32 n, u64 p[n], u32 size, (u64 key, u64 val)[size]; then the 4-bit packed sequence.
+// Bucket = hash & (2^b-1); key = hash>>b<<1 | singleton; val = position or offset<<32|n into the bucket's p[].
+extern "C" int mb_index_save(const mb_index_t *ix, const char *path)
+{
+	API_BEGIN
+	if (!ix || !path) throw mb_error(MB_ERR_ARG, "bad arguments");
+	FILE *fp = fopen(path, "wb");
+	if (!fp) throw mb_error(MB_ERR_IO, std::string("cannot write ") + path);
+	const int b = ix->b;
+	uint32_t x[5] = { (uint32_t)ix->w, (uint32_t)ix->k, (uint32_t)b, (uint32_t)ix->names.size(), 0 };
+	fwrite("MMI\2", 1, 4, fp);
+	fwrite(x, 4, 5, fp);
+	for (size_t i = 0; i < ix->names.size(); ++i) {
+		if (ix->names[i].size() > 255) { fclose(fp); throw mb_error(MB_ERR_ARG, "contig name longer than 255 bytes cannot be stored in .mmi"); }
+		uint8_t l = (uint8_t)ix->names[i].size();
+		fwrite(&l, 1, 1, fp);
+		fwrite(ix->names[i].data(), 1, l, fp);
+		fwrite(&ix->lens[i], 4, 1, fp);
+	}
+	// regroup the table by bucket
+	struct Ent { uint64_t h, key_val; bool single; uint32_t n; uint64_t start; };
+	std::vector<std::vector<Ent>> B((size_t)1 << b);
+	for (size_t s = 0; s < ix->h_hkey.size(); ++s) {
+		uint64_t kk = ix->h_hkey[s];
+		if (kk == ~0ULL) continue;
+		Ent e; e.h = kk >> 1; e.single = kk & 1;
+		if (e.single) e.key_val = ix->h_hval[s], e.n = 1, e.start = 0;
+		else e.key_val = 0, e.n = (uint32_t)ix->h_hval[s], e.start = ix->h_hval[s] >> 32;
+		B[e.h & (((uint64_t)1 << b) - 1)].push_back(e);
+	}
+	for (auto &bk : B) {
+		std::sort(bk.begin(), bk.end(), [](const Ent &a, const Ent &c) { return a.h < c.h; });
+		std::vector<uint64_t> p;
+		std::vector<uint64_t> kv;
+		for (auto &e : bk) {
+			uint64_t key = e.h >> b << 1 | (e.single ? 1 : 0), val;
+			if (e.single) val = e.key_val;
+			else {
+				val = (uint64_t)p.size() << 32 | e.n;
+				for (uint32_t k2 = 0; k2 < e.n; ++k2) p.push_back(ix->h_pos[e.start + k2]);
+			}
+			kv.push_back(key); kv.push_back(val);
+		}
+		int32_t n = (int32_t)p.size();
+		uint32_t size = (uint32_t)bk.size();
+		fwrite(&n, 4, 1, fp);
+		if (n) fwrite(p.data(), 8, p.size(), fp);
+		fwrite(&size, 4, 1, fp);
+		if (size) fwrite(kv.data(), 8, kv.size(), fp);
+	}
+	fwrite(ix->h_S.data(), 4, (ix->sum_len + 7) / 8, fp);
+	if (fclose(fp) != 0) throw mb_error(MB_ERR_IO, "write failed");
+	API_END
+}
+
+extern "C" int mb_index_load(int device, const char *path, mb_index_t **out)
+{
+	API_BEGIN
+	get_ctx(device);
+	FILE *fp = fopen(path, "rb");
+	if (!fp) throw mb_error(MB_ERR_IO, std::string("cannot open ") + path);
+	std::unique_ptr<mb_index> ix(new mb_index());
+	auto fail = [&](const char *m) { fclose(fp); throw mb_error(MB_ERR_IO, std::string(m) + ": " + path); };
+	char magic[4]; uint32_t x[5];
+	if (fread(magic, 1, 4, fp) != 4 || memcmp(magic, "MMI\2", 4) != 0) fail("damaged or empty index (bad magic)");
+	if (fread(x, 4, 5, fp) != 5) fail("damaged index header");
+	ix->device = device, ix->w = (int)x[0], ix->k = (int)x[1], ix->b = (int)x[2];
+	if (x[4] & 3) fail("HPC / no-sequence .mmi flags are not supported");
+	uint64_t sum = 0;
+	for (uint32_t i = 0; i < x[3]; ++i) {
+		uint8_t l; char nm[256]; uint32_t len;
+		if (fread(&l, 1, 1, fp) != 1) fail("damaged index (names)");
+		if (l && fread(nm, 1, l, fp) != l) fail("damaged index (names)");
+		if (fread(&len, 4, 1, fp) != 1) fail("damaged index (names)");
+		ix->names.emplace_back(nm, l); ix->lens.push_back(len); ix->offs.push_back(sum); sum += len;
+	}
+	ix->sum_len = sum;
+	std::vector<mb128> m;
+	const int b = ix->b;
+	for (uint64_t bi = 0; bi < ((uint64_t)1 << b); ++bi) {
+		int32_t n; uint32_t size;
+		if (fread(&n, 4, 1, fp) != 1) fail("damaged index (bucket)");
+		std::vector<uint64_t> p(n);
+		if (n && fread(p.data(), 8, n, fp) != (size_t)n) fail("damaged index (bucket)");
+		if (fread(&size, 4, 1, fp) != 1) fail("damaged index (bucket)");
+		for (uint32_t s = 0; s < size; ++s) {
+			uint64_t kv[2];
+			if (fread(kv, 8, 2, fp) != 2) fail("damaged index (hash)");
+			uint64_t h = (kv[0] >> 1) << b | bi;
+			if (kv[0] & 1) m.push_back(mb128{ h << 8 | (uint64_t)ix->k, kv[1] });
+			else {
+				uint64_t st = kv[1] >> 32; uint32_t cnt = (uint32_t)kv[1];
+				if (st + cnt > (uint64_t)n) fail("damaged index (offsets)");
+				for (uint32_t c2 = 0; c2 < cnt; ++c2) m.push_back(mb128{ h << 8 | (uint64_t)ix->k, p[st + c2] });
+			}
+		}
+	}
+	ix->h_S.assign((sum + 7) / 8, 0);
+	if (!ix->h_S.empty() && fread(ix->h_S.data(), 4, ix->h_S.size(), fp) != ix->h_S.size()) fail("damaged index (sequence)");
+	fclose(fp);
+	index_build_table(ix.get(), m);
+	index_upload(ix.get());
+	*out = ix.release();
+	API_END
+}
+
+extern "C" void mb_index_free(mb_index_t *ix)
+{
+	if (!ix) return;
+	cudaSetDevice(ix->device);
+	DevIndex &d = ix->d;
+	cudaFree(d.hkey); cudaFree(d.hval); cudaFree(d.pos); cudaFree(d.S); cudaFree(d.seq_off); cudaFree(d.seq_len);
+	delete ix;
+}
+extern "C" int mb_index_n_seq(const mb_index_t *ix) { return ix ? (int)ix->names.size() : 0; }
+extern "C" const char *mb_index_seq_name(const mb_index_t *ix, int rid) { return (ix && rid >= 0 && rid < (int)ix->names.size()) ? ix->names[rid].c_str() : nullptr; }
+extern "C" int64_t mb_index_seq_len(const mb_index_t *ix, int rid) { return (ix && rid >= 0 && rid < (int)ix->lens.size()) ? ix->lens[rid] : -1; }
+extern "C" int mb_index_mid_occ(const mb_index_t *ix) { return ix ? ix->mid_occ : 0; }
+extern "C" int mb_index_kw(const mb_index_t *ix, int *k, int *w) { if (!ix) return MB_ERR_ARG; if (k) *k = ix->k; if (w) *w = ix->w; return MB_OK; }
+extern "C" int64_t mb_index_n_minimizers(const mb_index_t *ix) { return ix ? ix->n_mini : 0; }
+extern "C" int64_t mb_index_hbm_bytes(const mb_index_t *ix) { return ix ? ix->hbm_bytes : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// reads / hits containers
+// ---------------------------------------------------------------------------------------------
+struct mb_reads {
+	int device = 0; int32_t n_reads = 0; int64_t total = 0;
+	uint8_t *d_codes = nullptr; int64_t *d_off = nullptr;
+};
+
+struct mb_hits {
+	int64_t n = 0; int32_t n_reads = 0;
+	std::vector<int32_t> fields;        // HIT_NF * n
+	std::vector<int64_t> cigar_off;
+	std::vector<uint32_t> cigar;
+	std::vector<int32_t> rep_len;
+	std::vector<int64_t> hit_off;       // [n_reads+1]
+	std::vector<int64_t> read_off;      // [n_reads+1] (for mb_count's query_length mode)
+};
+
+static const char *HIT_NAMES[HIT_NF] = { "read_idx", "rid", "rev", "qs", "qe", "rs", "re", "mapq", "mlen", "blen", "nm", "dp_max", "dp_max2",
+	"score", "score0", "cnt", "subsc", "n_sub", "id", "parent", "is_primary", "sam_pri", "n_cigar" };
+
+extern "C" int64_t mb_hits_n(const mb_hits_t *h) { return h ? h->n : 0; }
+extern "C" const int32_t *mb_hits_field(const mb_hits_t *h, const char *name)
+{
+	if (!h || !name) return nullptr;
+	for (int f = 0; f < HIT_NF; ++f) if (strcmp(name, HIT_NAMES[f]) == 0) return h->fields.data() + (size_t)f * h->n;
+	return nullptr;
+}
+extern "C" const int64_t *mb_hits_cigar_off(const mb_hits_t *h) { return h ? h->cigar_off.data() : nullptr; }
+extern "C" const uint32_t *mb_hits_cigar_pool(const mb_hits_t *h, int64_t *n) { if (!h) return nullptr; if (n) *n = (int64_t)h->cigar.size(); return h->cigar.data(); }
+extern "C" const int32_t *mb_hits_rep_len(const mb_hits_t *h, int64_t *n_reads) { if (!h) return nullptr; if (n_reads) *n_reads = h->n_reads; return h->rep_len.data(); }
+extern "C" void mb_hits_free(mb_hits_t *h) { delete h; }
+
+// ---------------------------------------------------------------------------------------------
+// the pipeline
+// ---------------------------------------------------------------------------------------------
+struct Timer {
+	cudaEvent_t e[2]; cudaStream_t st;
+	Timer(cudaStream_t s) : st(s) { cudaEventCreate(&e[0]); cudaEventCreate(&e[1]); }
+	~Timer() { cudaEventDestroy(e[0]); cudaEventDestroy(e[1]); }
+	void start() { cudaEventRecord(e[0], st); }
+	float stop() { cudaEventRecord(e[1], st); cudaEventSynchronize(e[1]); float ms = 0; cudaEventElapsedTime(&ms, e[0], e[1]); return ms; }
+};
+
+template <typename T> static T d2h_scalar(const T *d, cudaStream_t st)
+{
+	T v; CK(cudaMemcpyAsync(&v, d, sizeof(T), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); return v;
+}
+
+static DpScoring make_scoring(const mb_opt_t &o)
+{
+	DpScoring s;
+	s.q = (int8_t)o.q, s.e = (int8_t)o.e, s.q2 = (int8_t)o.q2, s.e2 = (int8_t)o.e2;
+	s.sc_mch = (int8_t)(o.a < 0 ? -o.a : o.a);
+	s.sc_mis = (int8_t)(o.b > 0 ? -o.b : o.b);
+	int amb = o.sc_ambi > 0 ? -o.sc_ambi : o.sc_ambi;
+	s.sc_N = (int8_t)(amb == 0 ? -o.e2 : amb);
+	s.pad = 0;
+	return s;
+}
+
+// scratch geometry of one DP task
+struct DpGeom { size_t p_bytes, ws_bytes, h_ints; };
+static __host__ __device__ inline DpGeom dp_geom(int qlen, int tlen, int w)
+{
+	DpGeom g; g.p_bytes = g.ws_bytes = g.h_ints = 0;
+	if (qlen <= 0 || tlen <= 0) return g;
+	if (w < 0) w = tlen > qlen ? tlen : qlen;
+	int tlen_ = (tlen + 15) / 16, qlen_ = (qlen + 15) / 16;
+	int n_col_ = qlen < tlen ? qlen : tlen;
+	n_col_ = ((n_col_ < w + 1 ? n_col_ : w + 1) + 15) / 16 + 1;
+	g.p_bytes = ((size_t)(qlen + tlen - 1) * n_col_ + 1) * 16;
+	g.ws_bytes = (size_t)tlen_ * 16 * 8 + (size_t)qlen_ * 16 + 16;
+	g.h_ints = (size_t)tlen_ * 16;
+	return g;
+}
+
+#define DP_SMALL_P (1u << 20)
+
+// classify tasks into small / big scratch classes; record maxima
+__global__ void k_dp_classify(const DpTask *__restrict__ tasks, const int32_t *__restrict__ ids, int64_t n, int use_ids,
+                              int32_t *__restrict__ small_list, int32_t *__restrict__ big_list, int32_t *__restrict__ ctr /* n_small, n_big */,
+                              unsigned long long *__restrict__ maxima /* small: p, ws, h ; big: p, ws, h */)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	int id = use_ids ? ids[i] : (int)i;
+	const DpTask &t = tasks[id];
+	DpGeom g = dp_geom(t.qlen, t.tlen, t.w);
+	if (t.skip) g.p_bytes = g.ws_bytes = g.h_ints = 0;
+	int big = g.p_bytes > DP_SMALL_P;
+	if (big) big_list[atomicAdd(&ctr[1], 1)] = id; else small_list[atomicAdd(&ctr[0], 1)] = id;
+	atomicMax(&maxima[big * 3 + 0], (unsigned long long)g.p_bytes);
+	atomicMax(&maxima[big * 3 + 1], (unsigned long long)g.ws_bytes);
+	atomicMax(&maxima[big * 3 + 2], (unsigned long long)g.h_ints);
+}
+
+struct DpRunner {
+	ThreadCtx &c; cudaStream_t st; int64_t *nl;
+	DpRunner(ThreadCtx &c_, int64_t *nl_) : c(c_), st(c_.st), nl(nl_) {}
+	// run k_dp over `n` tasks (ids[] if use_ids else 0..n-1)
+	void run(DpTask *tasks, const int32_t *ids, int64_t n, bool use_ids, const uint8_t *codes, const uint32_t *S, const uint8_t *pool,
+	         uint32_t *cigar_pool, const DpScoring &sc, unsigned long long *d_cells)
+	{
+		if (n <= 0) return;
+		Arena &ar = c.ar;
+		int32_t *small_list = ar.get<int32_t>(n), *big_list = ar.get<int32_t>(n);
+		int32_t *ctr = ar.get<int32_t>(4);
+		unsigned long long *maxima = ar.get<unsigned long long>(6);
+		CK(cudaMemsetAsync(ctr, 0, 4 * sizeof(int32_t), st));
+		CK(cudaMemsetAsync(maxima, 0, 6 * sizeof(unsigned long long), st));
+		k_dp_classify<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(tasks, ids, n, use_ids ? 1 : 0, small_list, big_list, ctr, maxima); ++*nl;
+		int32_t h_ctr[4]; unsigned long long h_max[6];
+		CK(cudaMemcpyAsync(h_ctr, ctr, sizeof(h_ctr), cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(h_max, maxima, sizeof(h_max), cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		for (int cls = 0; cls < 2; ++cls) {
+			int64_t cnt = h_ctr[cls];
+			if (cnt == 0) continue;
+			size_t p_stride = ((size_t)h_max[cls * 3 + 0] + 255) & ~(size_t)255;
+			size_t g_stride = ((size_t)h_max[cls * 3 + 1] + 255) & ~(size_t)255;
+			size_t h_stride = ((size_t)h_max[cls * 3 + 2] + 63) & ~(size_t)63;
+			if (p_stride == 0) p_stride = 256;
+			if (h_stride == 0) h_stride = 64;
+			int max_cta = c.num_sms * 6;
+			int64_t want_cta = cdiv(cnt, DP_WARPS);
+			int n_cta = (int)(want_cta < max_cta ? want_cta : max_cta);
+			// bound total scratch to ~24 GB
+			size_t per_warp = p_stride + (g_stride > DP_SMEM_PER_WARP ? g_stride : 0) + h_stride * 4;
+			size_t budget = (size_t)24 << 30;
+			while (n_cta > 1 && (size_t)n_cta * DP_WARPS * per_warp > budget) n_cta = (n_cta + 1) / 2;
+			size_t n_warps = (size_t)n_cta * DP_WARPS;
+			uint8_t *p_scr = ar.get<uint8_t>(n_warps * p_stride);
+			int8_t *g_ws = g_stride > DP_SMEM_PER_WARP ? ar.get<int8_t>(n_warps * g_stride) : ar.get<int8_t>(16);
+			int32_t *h_scr = ar.get<int32_t>(n_warps * h_stride);
+			int32_t *wc = ar.get<int32_t>(1);
+			CK(cudaMemsetAsync(wc, 0, sizeof(int32_t), st));
+			k_dp<<<n_cta, DP_WARPS * 32, DP_WARPS * DP_SMEM_PER_WARP, st>>>(tasks, cls ? big_list : small_list, ctr + cls, wc, codes, S, pool,
+				p_scr, p_stride, g_ws, g_stride, h_scr, h_stride, cigar_pool, sc, d_cells);
+			++*nl;
+		}
+	}
+};
+
+__global__ void k_copy_i32(const int32_t *__restrict__ src, int32_t *__restrict__ dst, int n)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) dst[i] = src[i];
+}
+
+__global__ void k_task_cap(const DpTask *__restrict__ tasks, int64_t n, int32_t *__restrict__ cap)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) cap[i] = tasks[i].qlen + tasks[i].tlen + 1;
+}
+
+static void check_err(int *d_err, cudaStream_t st, const char *where)
+{
+	int e = d2h_scalar(d_err, st);
+	if (e == 1) throw mb_error(MB_ERR_OVERFLOW, std::string(where) + ": tie between sort keys in a >64-element region sort (exact upstream order not reproduced)");
+	if (e == 2) throw mb_error(MB_ERR_OVERFLOW, std::string(where) + ": region pool overflow");
+	if (e == 3) throw mb_error(MB_ERR_OVERFLOW, std::string(where) + ": inversion-test scratch overflow");
+	if (e) throw mb_error(MB_ERR_OVERFLOW, std::string(where) + ": device error flag");
+}
+
+static mb_hits *map_device(mb_index *ix, const mb_opt_t &opt_in, ThreadCtx &c, const uint8_t *d_codes, const int64_t *d_off, const int64_t *h_off,
+                           int32_t n_reads, int64_t total, bool want_hits, mb_stats_t *stats)
+{
+	cudaStream_t st = c.st;
+	Arena &ar = c.ar;
+	mb_opt_t opt = opt_in;
+	if (opt.mid_occ <= 0) opt.mid_occ = ix->mid_occ;
+	if (opt.q + opt.e >= 127 || opt.q2 + opt.e2 >= 127) throw mb_error(MB_ERR_ARG, "gap costs too large for int8 DP");
+	mb_stats_t S; memset(&S, 0, sizeof(S));
+	S.n_reads = n_reads, S.n_bases = total;
+	int64_t nl = 0;
+	Timer tm(st), tall(st);
+	tall.start();
+	std::unique_ptr<mb_hits> H(new mb_hits());
+	H->n_reads = n_reads;
+	H->read_off.assign(h_off, h_off + n_reads + 1);
+	H->hit_off.assign(n_reads + 1, 0);
+	H->rep_len.assign(n_reads, 0);
+	if (n_reads == 0) { if (stats) *stats = S; return H.release(); }
+
+	// K1
+	tm.start();
+	SketchOut so;
+	run_sketch(ar, st, d_codes, d_off, n_reads, total, ix->w, ix->k, so, &nl);
+	S.ms_sketch = tm.stop(); S.n_mini = so.n_mini;
+	// K2 + K2b
+	tm.start();
+	SeedOut sd;
+	run_seed(ar, st, ix->d, opt.mid_occ, so.mini, so.mini_off, so.n_mini, d_off, n_reads, sd, &nl, c.num_sms);
+	S.ms_seed = tm.stop(); S.n_anchor = sd.n_a;
+	const int64_t n_a = sd.n_a;
+	// K3
+	tm.start();
+	ReadScratch rs;
+	rs.f = ar.get<int32_t>(n_a + 1), rs.p = ar.get<int32_t>(n_a + 1), rs.v = ar.get<int32_t>(n_a + 1), rs.t = ar.get<int32_t>(n_a + 1);
+	rs.b = ar.get<mb128>(n_a + 1); rs.u = ar.get<uint64_t>(n_a + 1); rs.scr = ar.get<uint64_t>(3 * n_a + 3 * (int64_t)n_reads + 3);
+	int32_t *wc = ar.get<int32_t>(4);
+	unsigned long long *d_cells = ar.get<unsigned long long>(2);
+	int *d_err = ar.get<int>(1);
+	CK(cudaMemsetAsync(wc, 0, 4 * sizeof(int32_t), st));
+	CK(cudaMemsetAsync(d_cells, 0, 2 * sizeof(unsigned long long), st));
+	CK(cudaMemsetAsync(d_err, 0, sizeof(int), st));
+	const int max_chain_gap_ref = opt.max_gap_ref > 0 ? opt.max_gap_ref : opt.max_gap, max_chain_gap_qry = opt.max_gap;
+	if (n_a > 0) {
+		int grid = c.num_sms * 8;
+		k_chain_dp<<<grid, CH_WARPS * 32, 0, st>>>(sd.a, sd.a_roff, n_reads, max_chain_gap_ref, max_chain_gap_qry, opt.bw, opt.max_chain_skip, opt.max_chain_iter,
+			rs.f, rs.p, rs.v, rs.t, wc, d_cells); ++nl;
+	}
+	S.ms_chain = tm.stop();
+	// region logic
+	tm.start();
+	ReadArrays ra;
+	ra.a = sd.a; ra.a_roff = sd.a_roff;
+	int32_t *n_u = ar.get<int32_t>(n_reads), *cap = ar.get<int32_t>(n_reads), *n_a_sq = ar.get<int32_t>(n_reads), *n0_regs = ar.get<int32_t>(n_reads);
+	ra.n_a_sq = n_a_sq;
+	ra.n_regs = ar.get<int32_t>(n_reads);
+	ra.iscr = ar.get<int32_t>(n_a + 1);
+	int64_t *reg_off = ar.get<int64_t>(n_reads + 1);
+	ra.reg_off = reg_off;
+	const unsigned rb = (unsigned)cdiv(n_reads, 128);
+	k_chain_bt<<<rb, 128, 0, st>>>(ra, rs, n_reads, opt.min_cnt, opt.min_chain_score, n_u, d_err); ++nl;
+	k_reg_cap<<<rb, 128, 0, st>>>(n_u, sd.a_roff, n_reads, cap); ++nl;
+	exclusive_scan<int32_t>(ar, st, cap, reg_off, n_reads, &nl);
+	const int64_t reg_total = d2h_scalar(reg_off + n_reads, st);
+	ra.regs = ar.get<Reg>(reg_total + 1);
+	rs.regs_tmp = ar.get<Reg>(reg_total + 1);
+	int2 *work = ar.get<int2>(reg_total + 1), *work2 = ar.get<int2>(reg_total + 1);
+	int32_t *n_work = ar.get<int32_t>(2);
+	CK(cudaMemsetAsync(n_work, 0, 2 * sizeof(int32_t), st));
+	AlignCtx ac; ac.codes = d_codes; ac.read_off = d_off; ac.ix = ix->d; ac.opt = opt;
+	k_gen_regs<<<rb, 128, 0, st>>>(ac, ra, rs, n_reads, n_u, n_a_sq, work, n_work, d_err); ++nl;
+	k_copy_i32<<<rb, 128, 0, st>>>(ra.n_regs, n0_regs, n_reads); ++nl;
+	int32_t h_n_work = d2h_scalar(n_work, st);
+	check_err(d_err, st, "region generation");
+	S.ms_glue = tm.stop(); S.n_regs = h_n_work;
+	// alignment rounds
+	tm.start();
+	const DpScoring scoring = make_scoring(opt);
+	int *inv_pool = nullptr; int32_t *inv_ctr = ar.get<int32_t>(1);
+	CK(cudaMemsetAsync(inv_ctr, 0, sizeof(int32_t), st));
+	DpRunner runner(c, &nl);
+	int round = 0;
+	while (h_n_work > 0) {
+		++round;
+		const unsigned wb = (unsigned)cdiv(h_n_work, 128);
+		RegPlan *plans = ar.get<RegPlan>(h_n_work);
+		int32_t *nt = ar.get<int32_t>(h_n_work);
+		int64_t *task_off = ar.get<int64_t>(h_n_work + 1);
+		k_plan1<<<wb, 128, 0, st>>>(ac, ra, work, h_n_work, plans); ++nl;
+		k_plan_ntasks<<<wb, 128, 0, st>>>(plans, h_n_work, nt); ++nl;
+		exclusive_scan<int32_t>(ar, st, nt, task_off, h_n_work, &nl);
+		const int64_t n_tasks = d2h_scalar(task_off + h_n_work, st);
+		DpTask *tasks = ar.get<DpTask>(n_tasks + 1);
+		int32_t *cig_cap = ar.get<int32_t>(n_tasks + 1);
+		int64_t *cig_off = ar.get<int64_t>(n_tasks + 2);
+		k_plan2<<<wb, 128, 0, st>>>(ac, ra, work, h_n_work, plans, task_off, tasks, cig_cap); ++nl;
+		int64_t cig_total = 0;
+		uint32_t *cigar_pool = nullptr;
+		if (n_tasks > 0) {
+			exclusive_scan<int32_t>(ar, st, cig_cap, cig_off, n_tasks, &nl);
+			cig_total = d2h_scalar(cig_off + n_tasks, st);
+			cigar_pool = ar.get<uint32_t>(cig_total + 1);
+			k_set_cigar_off<<<(unsigned)cdiv(n_tasks, 256), 256, 0, st>>>(tasks, cig_off, n_tasks, (int64_t)((uintptr_t)cigar_pool / 4)); ++nl;
+			cigar_pool = nullptr; // offsets are now absolute word addresses (pools of different rounds coexist)
+			runner.run(tasks, nullptr, n_tasks, false, d_codes, ix->d.S, nullptr, cigar_pool, scoring, d_cells + 1);
+			// Z-drop test and second pass
+			int32_t *pass2 = ar.get<int32_t>(n_tasks), *n_pass2 = ar.get<int32_t>(1);
+			CK(cudaMemsetAsync(n_pass2, 0, sizeof(int32_t), st));
+			if (!inv_pool) inv_pool = ar.get<int>((size_t)INV_SLOTS * INV_STRIDE);
+			k_ztest<<<(unsigned)cdiv(n_tasks, 128), 128, 0, st>>>(ac, tasks, n_tasks, cigar_pool, pass2, n_pass2, inv_pool, inv_ctr, d_err); ++nl;
+			const int32_t h_pass2 = d2h_scalar(n_pass2, st);
+			S.n_dp_pass2 += h_pass2;
+			if (h_pass2 > 0) runner.run(tasks, pass2, h_pass2, true, d_codes, ix->d.S, nullptr, cigar_pool, scoring, d_cells + 1);
+		}
+		S.n_dp_tasks += n_tasks;
+		CK(cudaMemsetAsync(n_work + 1, 0, sizeof(int32_t), st));
+		k_stitch<<<wb, 128, 0, st>>>(ac, ra, work, h_n_work, plans, tasks, cigar_pool, work2, n_work + 1, d_err); ++nl;
+		h_n_work = d2h_scalar(n_work + 1, st);
+		check_err(d_err, st, "alignment round");
+		std::swap(work, work2);
+		if (round > 64) throw mb_error(MB_ERR_OVERFLOW, "alignment did not converge in 64 split rounds");
+	}
+	S.n_rounds = round;
+	S.ms_dp = tm.stop();
+	// finish
+	tm.start();
+	int32_t *n_hits = ar.get<int32_t>(n_reads), *n_hit_cig = ar.get<int32_t>(n_reads);
+	int64_t *hit_off = ar.get<int64_t>(n_reads + 1), *hcig_off = ar.get<int64_t>(n_reads + 1);
+	k_finish<<<rb, 128, 0, st>>>(ac, ra, rs, n_reads, n0_regs, sd.rep_len, n_hits, n_hit_cig, d_err); ++nl;
+	exclusive_scan<int32_t>(ar, st, n_hits, hit_off, n_reads, &nl);
+	exclusive_scan<int32_t>(ar, st, n_hit_cig, hcig_off, n_reads, &nl);
+	const int64_t n_h = d2h_scalar(hit_off + n_reads, st);
+	const int64_t n_c = d2h_scalar(hcig_off + n_reads, st);
+	check_err(d_err, st, "finalisation");
+	int32_t *d_fields = ar.get<int32_t>((size_t)HIT_NF * n_h + 1);
+	int64_t *d_hcoff = ar.get<int64_t>(n_h + 1);
+	uint32_t *d_hcig = ar.get<uint32_t>(n_c + 1);
+	// cigars of surviving regions live in per-round pools that are all still allocated in the arena
+	k_write_hits<<<rb, 128, 0, st>>>(ra, n_reads, hit_off, hcig_off, n_h, d_fields, d_hcoff, (const uint32_t*)nullptr, d_hcig); ++nl;
+	S.ms_post = tm.stop();
+	S.n_hits = n_h;
+	unsigned long long h_cells[2];
+	CK(cudaMemcpyAsync(h_cells, d_cells, sizeof(h_cells), cudaMemcpyDeviceToHost, st));
+	tm.start();
+	H->n = n_h;
+	if (want_hits) {
+		H->fields.resize((size_t)HIT_NF * n_h); H->cigar_off.resize(n_h); H->cigar.resize(n_c);
+		if (n_h) {
+			CK(cudaMemcpyAsync(H->fields.data(), d_fields, (size_t)HIT_NF * n_h * 4, cudaMemcpyDeviceToHost, st));
+			CK(cudaMemcpyAsync(H->cigar_off.data(), d_hcoff, n_h * 8, cudaMemcpyDeviceToHost, st));
+		}
+		if (n_c) CK(cudaMemcpyAsync(H->cigar.data(), d_hcig, n_c * 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(H->rep_len.data(), sd.rep_len, n_reads * 4, cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(H->hit_off.data(), hit_off, (n_reads + 1) * 8, cudaMemcpyDeviceToHost, st));
+	}
+	CK(cudaStreamSynchronize(st));
+	CK(cudaGetLastError());
+	S.ms_d2h = tm.stop();
+	S.dp_cells = (int64_t)h_cells[1];
+	S.n_launches = nl;
+	S.ms_total = tall.stop();
+	if (stats) { float h2d = stats->ms_h2d; *stats = S; stats->ms_h2d = h2d; }
+	return H.release();
+}
+
+static void upload_reads(ThreadCtx &c, const uint8_t *cat, const int64_t *off, int32_t n_reads, uint8_t **d_codes, int64_t **d_off, int64_t *total, bool persistent)
+{
+	cudaStream_t st = c.st;
+	*total = n_reads > 0 ? off[n_reads] : 0;
+	if (n_reads < 0 || (n_reads > 0 && off[0] != 0)) throw mb_error(MB_ERR_ARG, "offsets must start at 0");
+	for (int i = 0; i < n_reads; ++i) {
+		if (off[i + 1] < off[i]) throw mb_error(MB_ERR_ARG, "offsets must be non-decreasing");
+		if (off[i + 1] - off[i] > 0x3fffffff) throw mb_error(MB_ERR_ARG, "read longer than 2^30");
+	}
+	uint8_t *d_ascii = c.ar.get<uint8_t>(*total + 32);
+	if (persistent) { CK(cudaMalloc(d_codes, *total + 32)); CK(cudaMalloc(d_off, (n_reads + 1) * 8)); }
+	else { *d_codes = c.ar.get<uint8_t>(*total + 32); *d_off = c.ar.get<int64_t>(n_reads + 1); }
+	if (*total) CK(cudaMemcpyAsync(d_ascii, cat, *total, cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(*d_off, off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+	if (*total) k_encode_nt4<<<(unsigned)cdiv(cdiv(*total, 16), 256), 256, 0, st>>>(d_ascii, *d_codes, *total);
+}
+
+extern "C" int mb_map_batch(mb_index_t *ix, const mb_opt_t *opt, const uint8_t *cat, const int64_t *off, int32_t n_reads, mb_hits_t **out, mb_stats_t *stats)
+{
+	API_BEGIN
+	if (!ix || !opt || !off || !out || (n_reads > 0 && !cat && off[n_reads] > 0)) throw mb_error(MB_ERR_ARG, "bad arguments");
+	ThreadCtx &c = get_ctx(ix->device);
+	c.ar.reset();
+	uint8_t *d_codes; int64_t *d_off; int64_t total;
+	Timer tm(c.st); tm.start();
+	upload_reads(c, cat, off, n_reads, &d_codes, &d_off, &total, false);
+	float ms_h2d = tm.stop();
+	if (stats) stats->ms_h2d = ms_h2d;
+	*out = map_device(ix, *opt, c, d_codes, d_off, off, n_reads, total, true, stats);
+	if (stats) { stats->ms_h2d = ms_h2d; stats->n_launches += 1; }
+	API_END
+}
+
+extern "C" int mb_reads_upload(mb_index_t *ix, const uint8_t *cat, const int64_t *off, int32_t n_reads, mb_reads_t **out)
+{
+	API_BEGIN
+	if (!ix || !off || !out) throw mb_error(MB_ERR_ARG, "bad arguments");
+	ThreadCtx &c = get_ctx(ix->device);
+	c.ar.reset();
+	std::unique_ptr<mb_reads> r(new mb_reads());
+	r->device = ix->device; r->n_reads = n_reads;
+	upload_reads(c, cat, off, n_reads, &r->d_codes, &r->d_off, &r->total, true);
+	CK(cudaStreamSynchronize(c.st));
+	c.ar.reset();
+	*out = r.release();
+	API_END
+}
+
+extern "C" void mb_reads_free(mb_reads_t *r)
+{
+	if (!r) return;
+	cudaSetDevice(r->device);
+	cudaFree(r->d_codes); cudaFree(r->d_off);
+	delete r;
+}
+
+extern "C" int mb_map_resident(mb_index_t *ix, const mb_opt_t *opt, mb_reads_t *reads, int want_hits, mb_hits_t **out, mb_stats_t *stats)
+{
+	API_BEGIN
+	if (!ix || !opt || !reads || !out) throw mb_error(MB_ERR_ARG, "bad arguments");
+	ThreadCtx &c = get_ctx(ix->device);
+	c.ar.reset();
+	std::vector<int64_t> h_off(reads->n_reads + 1);
+	CK(cudaMemcpyAsync(h_off.data(), reads->d_off, (reads->n_reads + 1) * 8, cudaMemcpyDeviceToHost, c.st));
+	CK(cudaStreamSynchronize(c.st));
+	if (stats) stats->ms_h2d = 0;
+	*out = map_device(ix, *opt, c, reads->d_codes, reads->d_off, h_off.data(), reads->n_reads, reads->total, want_hits != 0, stats);
+	API_END
+}
+
+// ---------------------------------------------------------------------------------------------
+// counting
+// ---------------------------------------------------------------------------------------------
+extern "C" int mb_count(mb_index_t *ix, const mb_hits_t *h, int32_t mapq_min, int mode, int64_t *counts, int64_t *n_class, int8_t *read_class, int64_t *read_best)
+{
+	API_BEGIN
+	if (!ix || !h) throw mb_error(MB_ERR_ARG, "bad arguments");
+	if ((int64_t)h->fields.size() != (int64_t)HIT_NF * h->n) throw mb_error(MB_ERR_ARG, "hits were produced with want_hits=0");
+	ThreadCtx &c = get_ctx(ix->device);
+	cudaStream_t st = c.st;
+	c.ar.reset();
+	const int n_seq = (int)ix->names.size(), n_reads = h->n_reads;
+	if (c.n_counts < n_seq + 4) {
+		if (c.d_counts) cudaFree(c.d_counts);
+		CK(cudaMalloc(&c.d_counts, (size_t)(n_seq + 4) * 8));
+		c.n_counts = n_seq + 4;
+	}
+	CK(cudaMemsetAsync(c.d_counts, 0, (size_t)(n_seq + 4) * 8, st));
+	int32_t *d_fields = c.ar.get<int32_t>((size_t)HIT_NF * h->n + 1);
+	int64_t *d_hit_off = c.ar.get<int64_t>(n_reads + 1), *d_read_off = c.ar.get<int64_t>(n_reads + 1);
+	int8_t *d_cls = c.ar.get<int8_t>(n_reads + 1);
+	int64_t *d_best = c.ar.get<int64_t>(n_reads + 1);
+	if (h->n) CK(cudaMemcpyAsync(d_fields, h->fields.data(), (size_t)HIT_NF * h->n * 4, cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(d_hit_off, h->hit_off.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(d_read_off, h->read_off.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+	if (n_reads) k_count<<<(unsigned)cdiv(n_reads, 128), 128, 0, st>>>(n_reads, d_hit_off, h->n, d_fields, d_read_off, mapq_min, mode,
+		c.d_counts, c.d_counts + n_seq, d_cls, d_best);
+	if (counts) CK(cudaMemcpyAsync(counts, c.d_counts, (size_t)n_seq * 8, cudaMemcpyDeviceToHost, st));
+	if (n_class) CK(cudaMemcpyAsync(n_class, c.d_counts + n_seq, 3 * 8, cudaMemcpyDeviceToHost, st));
+	if (read_class && n_reads) CK(cudaMemcpyAsync(read_class, d_cls, n_reads, cudaMemcpyDeviceToHost, st));
+	if (read_best && n_reads) CK(cudaMemcpyAsync(read_best, d_best, (size_t)n_reads * 8, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	CK(cudaGetLastError());
+	API_END
+}
+
+extern "C" void *mb_count_device_ptr(mb_index_t *ix)
+{
+	if (!ix) return nullptr;
+	auto it = t_ctx.find(ix->device);
+	return it == t_ctx.end() ? nullptr : (void*)it->second->d_counts;
+}
+
+extern "C" int mb_count_fetch(mb_index_t *ix, int64_t *counts)
+{
+	API_BEGIN
+	if (!ix || !counts) throw mb_error(MB_ERR_ARG, "bad arguments");
+	ThreadCtx &c = get_ctx(ix->device);
+	if (!c.d_counts) throw mb_error(MB_ERR_ARG, "no count vector on this thread");
+	CK(cudaMemcpy(counts, c.d_counts, ix->names.size() * 8, cudaMemcpyDeviceToHost));
+	API_END
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-stage entry points (parity tests)
+// ---------------------------------------------------------------------------------------------
+extern "C" int mb_sketch(int device, const uint8_t *cat, const int64_t *off, int32_t n_reads, int w, int k, uint64_t *out_xy, int64_t cap, int64_t *out_off)
+{
+	API_BEGIN
+	ThreadCtx &c = get_ctx(device);
+	c.ar.reset();
+	uint8_t *d_codes; int64_t *d_off; int64_t total; int64_t nl = 0;
+	upload_reads(c, cat, off, n_reads, &d_codes, &d_off, &total, false);
+	SketchOut so;
+	run_sketch(c.ar, c.st, d_codes, d_off, n_reads, total, w, k, so, &nl);
+	if (so.n_mini > cap) throw mb_error(MB_ERR_OVERFLOW, "output capacity too small");
+	if (so.n_mini) CK(cudaMemcpyAsync(out_xy, so.mini, so.n_mini * 16, cudaMemcpyDeviceToHost, c.st));
+	CK(cudaMemcpyAsync(out_off, so.mini_off, (n_reads + 1) * 8, cudaMemcpyDeviceToHost, c.st));
+	CK(cudaStreamSynchronize(c.st));
+	CK(cudaGetLastError());
+	API_END
+}
+
+extern "C" int mb_seed(mb_index_t *ix, const mb_opt_t *opt, const uint8_t *cat, const int64_t *off, int32_t n_reads,
+                       uint64_t *out_xy, int64_t cap, int64_t *out_off, int32_t *rep_len)
+{
+	API_BEGIN
+	if (!ix || !opt) throw mb_error(MB_ERR_ARG, "bad arguments");
+	ThreadCtx &c = get_ctx(ix->device);
+	c.ar.reset();
+	uint8_t *d_codes; int64_t *d_off; int64_t total; int64_t nl = 0;
+	upload_reads(c, cat, off, n_reads, &d_codes, &d_off, &total, false);
+	SketchOut so;
+	run_sketch(c.ar, c.st, d_codes, d_off, n_reads, total, ix->w, ix->k, so, &nl);
+	SeedOut sd;
+	run_seed(c.ar, c.st, ix->d, opt->mid_occ > 0 ? opt->mid_occ : ix->mid_occ, so.mini, so.mini_off, so.n_mini, d_off, n_reads, sd, &nl, c.num_sms);
+	if (sd.n_a > cap) throw mb_error(MB_ERR_OVERFLOW, "output capacity too small");
+	if (sd.n_a) CK(cudaMemcpyAsync(out_xy, sd.a, sd.n_a * 16, cudaMemcpyDeviceToHost, c.st));
+	CK(cudaMemcpyAsync(out_off, sd.a_roff, (n_reads + 1) * 8, cudaMemcpyDeviceToHost, c.st));
+	if (rep_len && n_reads) CK(cudaMemcpyAsync(rep_len, sd.rep_len, n_reads * 4, cudaMemcpyDeviceToHost, c.st));
+	CK(cudaStreamSynchronize(c.st));
+	CK(cudaGetLastError());
+	API_END
+}
+
+extern "C" int mb_chain(int device, const mb_opt_t *opt, const uint64_t *anchors_xy, const int64_t *off, int32_t n_reads,
+                        int32_t *f, int32_t *p, int32_t *v, uint64_t *chained_xy, int64_t *chained_off, uint64_t *u, int64_t *u_off)
+{
+	API_BEGIN
+	if (!opt || !off) throw mb_error(MB_ERR_ARG, "bad arguments");
+	ThreadCtx &c = get_ctx(device);
+	c.ar.reset();
+	cudaStream_t st = c.st;
+	Arena &ar = c.ar;
+	const int64_t n_a = off[n_reads];
+	mb128 *d_a = ar.get<mb128>(n_a + 1);
+	int64_t *d_roff = ar.get<int64_t>(n_reads + 1);
+	if (n_a) CK(cudaMemcpyAsync(d_a, anchors_xy, n_a * 16, cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(d_roff, off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+	ReadScratch rs;
+	rs.f = ar.get<int32_t>(n_a + 1), rs.p = ar.get<int32_t>(n_a + 1), rs.v = ar.get<int32_t>(n_a + 1), rs.t = ar.get<int32_t>(n_a + 1);
+	rs.b = ar.get<mb128>(n_a + 1); rs.u = ar.get<uint64_t>(n_a + 1); rs.scr = ar.get<uint64_t>(3 * n_a + 3 * (int64_t)n_reads + 3);
+	rs.regs_tmp = nullptr;
+	int32_t *wc = ar.get<int32_t>(1); int *d_err = ar.get<int>(1);
+	CK(cudaMemsetAsync(wc, 0, sizeof(int32_t), st)); CK(cudaMemsetAsync(d_err, 0, sizeof(int), st));
+	const int max_chain_gap_ref = opt->max_gap_ref > 0 ? opt->max_gap_ref : opt->max_gap;
+	if (n_a) k_chain_dp<<<c.num_sms * 8, CH_WARPS * 32, 0, st>>>(d_a, d_roff, n_reads, max_chain_gap_ref, opt->max_gap, opt->bw, opt->max_chain_skip, opt->max_chain_iter,
+		rs.f, rs.p, rs.v, rs.t, wc, nullptr);
+	if (f && n_a) CK(cudaMemcpyAsync(f, rs.f, n_a * 4, cudaMemcpyDeviceToHost, st));
+	if (p && n_a) CK(cudaMemcpyAsync(p, rs.p, n_a * 4, cudaMemcpyDeviceToHost, st));
+	if (v && n_a) CK(cudaMemcpyAsync(v, rs.v, n_a * 4, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	if (chained_xy) {
+		ReadArrays ra; memset(&ra, 0, sizeof(ra));
+		ra.a = d_a; ra.a_roff = d_roff;
+		int32_t *n_u = ar.get<int32_t>(n_reads + 1);
+		if (n_reads) k_chain_bt<<<(unsigned)cdiv(n_reads, 128), 128, 0, st>>>(ra, rs, n_reads, opt->min_cnt, opt->min_chain_score, n_u, d_err);
+		std::vector<int32_t> h_nu(n_reads);
+		std::vector<mb128> h_a(n_a); std::vector<uint64_t> h_u(n_a);
+		if (n_reads) CK(cudaMemcpyAsync(h_nu.data(), n_u, n_reads * 4, cudaMemcpyDeviceToHost, st));
+		if (n_a) { CK(cudaMemcpyAsync(h_a.data(), d_a, n_a * 16, cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(h_u.data(), rs.u, n_a * 8, cudaMemcpyDeviceToHost, st)); }
+		CK(cudaStreamSynchronize(st));
+		check_err(d_err, st, "chain backtrack");
+		int64_t co = 0, uo = 0;
+		for (int r = 0; r < n_reads; ++r) {
+			chained_off[r] = co, u_off[r] = uo;
+			int64_t k2 = 0;
+			for (int i = 0; i < h_nu[r]; ++i) { u[uo++] = h_u[off[r] + i]; k2 += (int32_t)h_u[off[r] + i]; }
+			for (int64_t i = 0; i < k2; ++i) { chained_xy[2 * co] = h_a[off[r] + i].x; chained_xy[2 * co + 1] = h_a[off[r] + i].y; ++co; }
+		}
+		chained_off[n_reads] = co, u_off[n_reads] = uo;
+	}
+	CK(cudaGetLastError());
+	API_END
+}
+
+__global__ void k_tasks_from_api(const mb_dp_task_t *__restrict__ in, DpTask *__restrict__ out, int64_t n, int64_t cig_base)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	DpTask t; memset(&t, 0, sizeof(t));
+	t.reg = -1, t.kind = (in[i].flag & MB_EZ_EXTZ_ONLY) ? 2 : 1;
+	t.qlen = in[i].qlen, t.tlen = in[i].tlen, t.w = in[i].w, t.zdrop = in[i].zdrop, t.end_bonus = in[i].end_bonus, t.flag = in[i].flag;
+	t.q_idx0 = in[i].q_off, t.q_step = 1, t.q_comp = 2;
+	t.t_idx0 = in[i].t_off, t.t_step = 1, t.t_packed = 0;
+	t.cigar_off = cig_base + in[i].cigar_off;
+	t.skip = 0;
+	out[i] = t;
+}
+
+__global__ void k_tasks_to_api(const DpTask *__restrict__ in, mb_dp_task_t *__restrict__ out, int64_t n)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	out[i].score = in[i].score, out[i].max = in[i].max, out[i].max_q = in[i].max_q, out[i].max_t = in[i].max_t;
+	out[i].mqe = in[i].mqe, out[i].mqe_t = in[i].mqe_t, out[i].zdropped = in[i].zdropped, out[i].reach_end = in[i].reach_end, out[i].n_cigar = in[i].n_cigar;
+}
+
+extern "C" int mb_dp_batch(int device, const mb_opt_t *opt, mb_dp_task_t *tasks, int64_t n_tasks, const uint8_t *seqpool, int64_t n_seqpool,
+                           uint32_t *cigar_pool, int64_t n_cigar_pool)
+{
+	API_BEGIN
+	if (!opt || !tasks || n_tasks < 0) throw mb_error(MB_ERR_ARG, "bad arguments");
+	ThreadCtx &c = get_ctx(device);
+	c.ar.reset();
+	cudaStream_t st = c.st; Arena &ar = c.ar;
+	int64_t nl = 0;
+	mb_dp_task_t *d_in = ar.get<mb_dp_task_t>(n_tasks + 1);
+	DpTask *d_t = ar.get<DpTask>(n_tasks + 1);
+	uint8_t *d_pool = ar.get<uint8_t>(n_seqpool + 16);
+	uint32_t *d_cig = ar.get<uint32_t>(n_cigar_pool + 1);
+	if (n_tasks) CK(cudaMemcpyAsync(d_in, tasks, n_tasks * sizeof(mb_dp_task_t), cudaMemcpyHostToDevice, st));
+	if (n_seqpool) CK(cudaMemcpyAsync(d_pool, seqpool, n_seqpool, cudaMemcpyHostToDevice, st));
+	if (n_tasks) k_tasks_from_api<<<(unsigned)cdiv(n_tasks, 256), 256, 0, st>>>(d_in, d_t, n_tasks, (int64_t)((uintptr_t)d_cig / 4));
+	DpRunner runner(c, &nl);
+	runner.run(d_t, nullptr, n_tasks, false, nullptr, nullptr, d_pool, nullptr, make_scoring(*opt), nullptr);
+	if (n_tasks) k_tasks_to_api<<<(unsigned)cdiv(n_tasks, 256), 256, 0, st>>>(d_t, d_in, n_tasks);
+	if (n_tasks) CK(cudaMemcpyAsync(tasks, d_in, n_tasks * sizeof(mb_dp_task_t), cudaMemcpyDeviceToHost, st));
+	if (n_cigar_pool) CK(cudaMemcpyAsync(cigar_pool, d_cig, n_cigar_pool * 4, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	CK(cudaGetLastError());
+	API_END
+}

@@ -1,0 +1,251 @@
+// seed.cuh -- K2 hash-index seed lookup, anchor emission, K2b per-read anchor sort.
+//
+// Replaces minimap2-2.17 index.c mm_idx_get() and map.c collect_matches()/collect_seed_hits()
+// (+ ksort.h radix_sort_128x) as reached from mappy's Aligner.map
+// (/root/reference/monica/genomes/aligner.py:193,215).
+//
+// HBM layout of the index (one replica per GPU):
+//   hkey[cap], hval[cap]  open-addressing table, linear probing, load <= 0.5.
+//                         hkey = hash<<1 | singleton, ~0 = empty; hval = position (singleton) or start<<32|n
+//   pos[n_multi]          position lists of multi-occurrence minimizers, each list ascending (index.c worker_post)
+//   S[sum_len/8]          4-bit packed reference, 8 bases per word (mm_idx_t::S), seq_off[], seq_len[]
+// A probe touches one 16-byte slot pair (two 8-byte loads from two arrays -> 2 sectors); singletons need no
+// second dependent access.
+#pragma once
+#include "common.cuh"
+#include "radix_emul.cuh"
+
+struct DevIndex {
+	uint64_t *hkey = nullptr, *hval = nullptr;
+	uint64_t hmask = 0;
+	int hshift = 0;
+	uint64_t *pos = nullptr;
+	uint32_t *S = nullptr;
+	uint64_t *seq_off = nullptr;
+	uint32_t *seq_len = nullptr;
+	int n_seq = 0, k = 15, w = 10, mid_occ = 0;
+};
+
+MB_HD uint64_t mb_slot_hash(uint64_t h, int shift) { return (h * 0x9E3779B97F4A7C15ULL) >> shift; }
+
+// one thread per query minimizer: probe, record occurrence count and value
+__global__ void k_seed_lookup(DevIndex ix, const mb128 *__restrict__ mini, int64_t n_mini, int mid_occ,
+                              int32_t *__restrict__ occ, uint64_t *__restrict__ val, int32_t *__restrict__ cnt)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_mini) return;
+	uint64_t h = mini[i].x >> 8;
+	uint64_t slot = mb_slot_hash(h, ix.hshift) & ix.hmask;
+	int n = 0; uint64_t v = 0;
+	for (;;) {
+		uint64_t kk = __ldg(ix.hkey + slot);
+		if (kk == ~0ULL) break;
+		if ((kk >> 1) == h) {
+			v = __ldg(ix.hval + slot);
+			n = (kk & 1) ? 1 : (int)(uint32_t)v;
+			if (kk & 1) v = v; // singleton: v is the position itself
+			else v = (v >> 32) | (1ULL << 63); // multi: start index into pos[], tagged
+			break;
+		}
+		slot = (slot + 1) & ix.hmask;
+	}
+	occ[i] = n;
+	val[i] = v;
+	cnt[i] = n < mid_occ ? n : 0;
+}
+
+// one thread per read: rep_len (collect_matches) -- union length of repetitive-minimizer intervals
+__global__ void k_rep_len(const mb128 *__restrict__ mini, const int64_t *__restrict__ mini_off, const int32_t *__restrict__ occ,
+                          int n_reads, int mid_occ, int32_t *__restrict__ rep_len)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	int rep_st = 0, rep_en = 0, rl = 0;
+	for (int64_t i = mini_off[r]; i < mini_off[r + 1]; ++i) {
+		if (occ[i] >= mid_occ) {
+			uint32_t q_pos = (uint32_t)mini[i].y, q_span = (uint32_t)(mini[i].x & 0xff);
+			int en = (int)(q_pos >> 1) + 1, st = en - (int)q_span;
+			if (st > rep_en) { rl += rep_en - rep_st; rep_st = st, rep_en = en; }
+			else rep_en = en;
+		}
+	}
+	rl += rep_en - rep_st;
+	rep_len[r] = rl;
+}
+
+// one thread per query minimizer: emit its anchors (collect_seed_hits) in upstream emission order
+__global__ void k_seed_fill(DevIndex ix, const mb128 *__restrict__ mini, const int64_t *__restrict__ mini_off, int64_t n_mini,
+                            const int64_t *__restrict__ read_off, const int32_t *__restrict__ cnt, const uint64_t *__restrict__ val,
+                            const int64_t *__restrict__ a_off, mb128 *__restrict__ a)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_mini) return;
+	int n = cnt[i];
+	if (n == 0) return;
+	mb128 m = mini[i];
+	int r = (int)(m.y >> 32);
+	uint32_t q_pos = (uint32_t)m.y, q_span = (uint32_t)(m.x & 0xff);
+	int qlen = (int)(read_off[r + 1] - read_off[r]);
+	bool tandem = false;
+	if (i > mini_off[r] && (mini[i - 1].x >> 8) == (m.x >> 8)) tandem = true;
+	if (i + 1 < mini_off[r + 1] && (mini[i + 1].x >> 8) == (m.x >> 8)) tandem = true;
+	uint64_t v = val[i];
+	const uint64_t *cr = (v >> 63) ? ix.pos + (v & 0x7fffffffffffffffULL) : nullptr;
+	int64_t o = a_off[i];
+	for (int kk = 0; kk < n; ++kk) {
+		uint64_t rr = cr ? __ldg(cr + kk) : v;
+		uint32_t rpos = (uint32_t)rr >> 1;
+		mb128 p;
+		if ((rr & 1) == (q_pos & 1)) { // forward strand
+			p.x = (rr & 0xffffffff00000000ULL) | rpos;
+			p.y = (uint64_t)q_span << 32 | q_pos >> 1;
+		} else { // reverse strand
+			p.x = 1ULL << 63 | (rr & 0xffffffff00000000ULL) | rpos;
+			p.y = (uint64_t)q_span << 32 | (uint32_t)(qlen - (int)((q_pos >> 1) + 1 - q_span) - 1);
+		}
+		if (tandem) p.y |= MB_SEED_TANDEM;
+		a[o + kk] = p;
+	}
+}
+
+// per-read anchor offsets: a_roff[r] = a_off[mini_off[r]]
+__global__ void k_read_anchor_off(const int64_t *__restrict__ mini_off, const int64_t *__restrict__ a_off, int n_reads, int64_t *__restrict__ a_roff)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r > n_reads) return;
+	a_roff[r] = a_off[mini_off[r]];
+}
+
+// ---- K2b: one CTA per read; bitonic sort of (x, original index) in shared memory, global scratch beyond ----
+#define SORT_TPB 256
+#define SORT_SMEM_N 2048   // 2048 * (8+4) = 24 KB static shared memory
+
+__global__ void __launch_bounds__(SORT_TPB)
+k_sort_anchors(const mb128 *__restrict__ in, mb128 *__restrict__ out, const int64_t *__restrict__ a_roff, int n_reads,
+               uint64_t *__restrict__ gkey, uint32_t *__restrict__ gidx, const int64_t *__restrict__ g_roff,
+               int32_t *__restrict__ tie_list, int32_t *__restrict__ n_tie)
+{
+	__shared__ uint64_t skey[SORT_SMEM_N];
+	__shared__ uint32_t sidx[SORT_SMEM_N];
+	__shared__ int s_tie;
+	for (int r = blockIdx.x; r < n_reads; r += gridDim.x) {
+		const int64_t base = a_roff[r];
+		const int n = (int)(a_roff[r + 1] - base);
+		if (n == 0) continue;
+		if (n == 1) { if (threadIdx.x == 0) out[base] = in[base]; continue; }
+		int np = 1; while (np < n) np <<= 1;
+		uint64_t *key; uint32_t *idx;
+		if (np <= SORT_SMEM_N) key = skey, idx = sidx;
+		else key = gkey + g_roff[r], idx = gidx + g_roff[r];
+		if (threadIdx.x == 0) s_tie = 0;
+		for (int i = threadIdx.x; i < np; i += SORT_TPB) {
+			key[i] = i < n ? in[base + i].x : ~0ULL;
+			idx[i] = i;
+		}
+		__syncthreads();
+		for (int k2 = 2; k2 <= np; k2 <<= 1) {
+			for (int j = k2 >> 1; j > 0; j >>= 1) {
+				for (int i = threadIdx.x; i < np; i += SORT_TPB) {
+					int l = i ^ j;
+					if (l > i) {
+						uint64_t ka = key[i], kb = key[l];
+						uint32_t ia = idx[i], ib = idx[l];
+						bool gt = ka > kb || (ka == kb && ia > ib);
+						bool up = (i & k2) == 0;
+						if (gt == up) { key[i] = kb, key[l] = ka, idx[i] = ib, idx[l] = ia; }
+					}
+				}
+				__syncthreads();
+			}
+		}
+		for (int i = threadIdx.x; i < n; i += SORT_TPB) {
+			out[base + i] = in[base + idx[i]];
+			if (i > 0 && key[i] == key[i - 1]) s_tie = 1;
+		}
+		__syncthreads();
+		if (threadIdx.x == 0 && s_tie) tie_list[atomicAdd(n_tie, 1)] = r;
+		__syncthreads();
+	}
+}
+
+// reads whose anchors tie on x: reproduce upstream's unstable radix permutation exactly, one thread per read
+#define SORT_EMUL_WORKERS 64
+__global__ void k_sort_emul(const mb128 *__restrict__ in, mb128 *__restrict__ out, const int64_t *__restrict__ a_roff,
+                            const int32_t *__restrict__ tie_list, const int32_t *__restrict__ n_tie, int32_t *__restrict__ cursor,
+                            int *__restrict__ ws_pool)
+{
+	int wid = blockIdx.x * blockDim.x + threadIdx.x;
+	if (wid >= SORT_EMUL_WORKERS) return;
+	int *ws = ws_pool + (size_t)wid * MB_RS_WS_INTS;
+	for (;;) {
+		int t = atomicAdd(cursor, 1);
+		if (t >= *n_tie) break;
+		int r = tie_list[t];
+		int64_t base = a_roff[r];
+		int n = (int)(a_roff[r + 1] - base);
+		for (int i = 0; i < n; ++i) out[base + i] = in[base + i];
+		mb_radix_sort_emul(out + base, n, ws, KeyX());
+	}
+}
+
+struct SeedOut {
+	mb128 *a = nullptr;            // sorted anchors, per read contiguous
+	mb128 *a_unsorted = nullptr;
+	int64_t *a_roff = nullptr;     // [n_reads+1]
+	int32_t *rep_len = nullptr;    // [n_reads]
+	int64_t n_a = 0;
+};
+
+__global__ void k_big_sort_sizes(const int64_t *__restrict__ a_roff, int n_reads, int32_t *__restrict__ sz)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	int64_t n = a_roff[r + 1] - a_roff[r];
+	int np = 1; while (np < n) np <<= 1;
+	sz[r] = np > SORT_SMEM_N ? np : 0;
+}
+
+static void run_seed(Arena &ar, cudaStream_t st, const DevIndex &ix, int mid_occ, const mb128 *mini, const int64_t *mini_off, int64_t n_mini,
+                     const int64_t *d_read_off, int n_reads, SeedOut &o, int64_t *n_launch, int num_sms)
+{
+	o.a_roff = ar.get<int64_t>(n_reads + 1);
+	o.rep_len = ar.get<int32_t>(n_reads);
+	if (n_mini == 0) {
+		CK(cudaMemsetAsync(o.a_roff, 0, (n_reads + 1) * sizeof(int64_t), st));
+		CK(cudaMemsetAsync(o.rep_len, 0, (n_reads ? n_reads : 1) * sizeof(int32_t), st));
+		o.a = o.a_unsorted = ar.get<mb128>(1); o.n_a = 0;
+		return;
+	}
+	int32_t *occ = ar.get<int32_t>(n_mini), *cnt = ar.get<int32_t>(n_mini);
+	uint64_t *val = ar.get<uint64_t>(n_mini);
+	int64_t *a_off = ar.get<int64_t>(n_mini + 1);
+	k_seed_lookup<<<(unsigned)cdiv(n_mini, 256), 256, 0, st>>>(ix, mini, n_mini, mid_occ, occ, val, cnt); ++*n_launch;
+	k_rep_len<<<(unsigned)cdiv(n_reads, 128), 128, 0, st>>>(mini, mini_off, occ, n_reads, mid_occ, o.rep_len); ++*n_launch;
+	exclusive_scan<int32_t>(ar, st, cnt, a_off, n_mini, n_launch);
+	k_read_anchor_off<<<(unsigned)cdiv(n_reads + 1, 128), 128, 0, st>>>(mini_off, a_off, n_reads, o.a_roff); ++*n_launch;
+	int64_t n_a = 0;
+	CK(cudaMemcpyAsync(&n_a, a_off + n_mini, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	o.n_a = n_a;
+	o.a_unsorted = ar.get<mb128>(n_a + 1);
+	o.a = ar.get<mb128>(n_a + 1);
+	if (n_a == 0) return;
+	k_seed_fill<<<(unsigned)cdiv(n_mini, 256), 256, 0, st>>>(ix, mini, mini_off, n_mini, d_read_off, cnt, val, a_off, o.a_unsorted); ++*n_launch;
+	// scratch for reads too large for the shared-memory sort
+	int32_t *big_sz = ar.get<int32_t>(n_reads);
+	int64_t *big_off = ar.get<int64_t>(n_reads + 1);
+	k_big_sort_sizes<<<(unsigned)cdiv(n_reads, 128), 128, 0, st>>>(o.a_roff, n_reads, big_sz); ++*n_launch;
+	exclusive_scan<int32_t>(ar, st, big_sz, big_off, n_reads, n_launch);
+	int64_t big_total = 0;
+	CK(cudaMemcpyAsync(&big_total, big_off + n_reads, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	uint64_t *gkey = ar.get<uint64_t>(big_total + 1);
+	uint32_t *gidx = ar.get<uint32_t>(big_total + 1);
+	int32_t *tie_list = ar.get<int32_t>(n_reads);
+	int32_t *ctr = ar.get<int32_t>(2);
+	CK(cudaMemsetAsync(ctr, 0, 2 * sizeof(int32_t), st));
+	int grid = n_reads < num_sms * 8 ? n_reads : num_sms * 8;
+	k_sort_anchors<<<grid, SORT_TPB, 0, st>>>(o.a_unsorted, o.a, o.a_roff, n_reads, gkey, gidx, big_off, tie_list, ctr); ++*n_launch;
+	int *ws_pool = ar.get<int>((size_t)SORT_EMUL_WORKERS * MB_RS_WS_INTS);
+	k_sort_emul<<<1, SORT_EMUL_WORKERS, 0, st>>>(o.a_unsorted, o.a, o.a_roff, tie_list, ctr, ctr + 1, ws_pool); ++*n_launch;
+}

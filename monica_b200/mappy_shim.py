@@ -1,0 +1,221 @@
+"""A `mappy`-shaped module surface backed by the sm_100a library.
+
+monica's aligner helper touches mappy in exactly four places (/root/reference/monica/genomes/aligner.py):
+  * :45-46  mappy.Aligner(fn_idx_in=<fna.gz>, preset='map-ont', best_n=15, fn_idx_out=<mmi>)  (index build + dump)
+  * :59     mappy.Aligner(fn_idx_in=<mmi>)                                                     (index load)
+  * :47,60  truthiness of the Aligner (falsy on failure)
+  * :193,215 `for hit in index.map(str(seq))` reading hit.is_primary .mapq .ctg .NM .mlen      (:194-195,216-217)
+This module keeps those names, argument meanings and failure behaviour.  `Aligner.map` exists for drop-in use and
+for tests; the product path batches whole FASTQ files through `Aligner.map_batch` (monica_b200/aligner.py).
+
+Like mappy 2.17, the loading constructor ignores preset/best_n recorded at build time: k and w come from the index
+file, every other mapping option is mm_mapopt_init()'s default (best_n = 5).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+from . import _lib
+from ._lib import Hits, Stats, check, lib
+
+__version__ = "2.17-b200"
+
+
+class Alignment:
+    """Field-for-field the object mappy yields (python/mappy.pyx Alignment)."""
+    __slots__ = ("ctg", "ctg_len", "r_st", "r_en", "strand", "q_st", "q_en", "mapq", "is_primary", "mlen", "blen", "NM",
+                 "trans_strand", "read_num", "cigar", "score", "rid")
+
+    def __init__(self, ctg, ctg_len, r_st, r_en, strand, q_st, q_en, mapq, is_primary, mlen, blen, NM, cigar, score, rid):
+        self.ctg, self.ctg_len, self.r_st, self.r_en = ctg, ctg_len, r_st, r_en
+        self.strand, self.q_st, self.q_en, self.mapq = strand, q_st, q_en, mapq
+        self.is_primary, self.mlen, self.blen, self.NM = is_primary, mlen, blen, NM
+        self.trans_strand, self.read_num = 0, 1
+        self.cigar = cigar
+        self.score = score   # dp_max: not a mappy 2.17 field; exposed for parity tests
+        self.rid = rid
+
+    @property
+    def cigar_str(self):
+        return "".join(f"{l}{'MIDNSH'[op]}" for l, op in self.cigar)
+
+    def __str__(self):
+        strand = "+" if self.strand > 0 else "-" if self.strand < 0 else "?"
+        tp = "tp:A:P" if self.is_primary else "tp:A:S"
+        return "\t".join(map(str, [self.q_st, self.q_en, strand, self.ctg, self.ctg_len, self.r_st, self.r_en, self.mlen,
+                                   self.blen, self.mapq, tp, "ts:A:.", "cg:Z:" + self.cigar_str]))
+
+
+class Aligner:
+    """mappy.Aligner(fn_idx_in=None, preset=None, k=None, w=None, best_n=None, n_threads=3, fn_idx_out=None, seq=None)."""
+
+    def __init__(self, fn_idx_in=None, preset=None, k=None, w=None, min_cnt=None, min_chain_score=None, min_dp_score=None,
+                 bw=None, best_n=None, n_threads=3, fn_idx_out=None, max_frag_len=None, extra_flags=None, seq=None,
+                 scoring=None, device=None, names=None, seqs=None):
+        self._idx = None
+        self._lock = threading.Lock()
+        L = lib()
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0")) if L.mb_device_count() > 1 else 0
+            device %= max(1, L.mb_device_count())
+        self.device = device
+        if preset not in (None, "map-ont"):
+            raise ValueError("only the map-ont preset is implemented (it is the one monica uses)")
+        kk = 15 if k is None else int(k)
+        ww = 10 if w is None else int(w)
+        self.opt = _lib.default_opt()
+        if best_n is not None:
+            self.opt.best_n = int(best_n)
+        if min_cnt is not None:
+            self.opt.min_cnt = int(min_cnt)
+        if min_chain_score is not None:
+            self.opt.min_chain_score = int(min_chain_score)
+        if min_dp_score is not None:
+            self.opt.min_dp_max = int(min_dp_score)
+        if bw is not None:
+            self.opt.bw = int(bw)
+        h = C.c_void_p()
+        try:
+            if seqs is not None:
+                n = len(seqs)
+                bufs = [np.ascontiguousarray(np.frombuffer(s, dtype=np.uint8) if isinstance(s, (bytes, bytearray)) else
+                                             np.frombuffer(s.encode(), dtype=np.uint8) if isinstance(s, str) else
+                                             np.asarray(s, dtype=np.uint8)) for s in seqs]
+                nm = (C.c_char_p * n)(*[x.encode() if isinstance(x, str) else x for x in names])
+                sp = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+                lens = np.array([len(b) for b in bufs], dtype=np.int64)
+                check(L.mb_index_build(device, n, nm, sp, lens.ctypes.data_as(C.c_void_p), ww, kk, C.byref(h)))
+            elif seq is not None:
+                b = np.frombuffer(seq.encode() if isinstance(seq, str) else seq, dtype=np.uint8)
+                nm = (C.c_char_p * 1)(b"N/A")
+                sp = (C.c_void_p * 1)(b.ctypes.data)
+                lens = np.array([len(b)], dtype=np.int64)
+                check(L.mb_index_build(device, 1, nm, sp, lens.ctypes.data_as(C.c_void_p), ww, kk, C.byref(h)))
+            elif fn_idx_in is not None:
+                path = os.fspath(fn_idx_in)
+                with open(path, "rb") as fh:
+                    magic = fh.read(4)
+                if magic == b"MMI\x02":
+                    check(L.mb_index_load(device, path.encode(), C.byref(h)))
+                else:
+                    check(L.mb_index_build_fasta(device, path.encode(), ww, kk, C.byref(h)))
+                    if fn_idx_out is not None:
+                        check(L.mb_index_save(h, os.fspath(fn_idx_out).encode()))
+            else:
+                return
+        except _lib.MonicaB200Error as e:
+            if e.code == -2:   # no device / CUDA failure is not "bad index": never mask it as falsy
+                raise
+            self._idx = None   # mappy: failure to open/build leaves a falsy Aligner (aligner.py:47-48,60-61)
+            self._error = str(e)
+            return
+        except OSError as e:
+            self._idx = None
+            self._error = str(e)
+            return
+        self._idx = h
+        self._names = [L.mb_index_seq_name(h, i).decode() for i in range(L.mb_index_n_seq(h))]
+        self._lens = [int(L.mb_index_seq_len(h, i)) for i in range(len(self._names))]
+        k_, w_ = C.c_int(0), C.c_int(0)
+        L.mb_index_kw(h, C.byref(k_), C.byref(w_))
+        self.k, self.w = k_.value, w_.value
+        self.last_stats = None
+
+    def __bool__(self):
+        return self._idx is not None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_idx", None):
+                lib().mb_index_free(self._idx)
+                self._idx = None
+        except Exception:
+            pass
+
+    # ---- mappy surface ----
+    @property
+    def seq_names(self):
+        return list(self._names)
+
+    @property
+    def n_seq(self):
+        return len(self._names)
+
+    @property
+    def mid_occ(self):
+        return lib().mb_index_mid_occ(self._idx)
+
+    def handle(self):
+        return self._idx
+
+    def map(self, seq, seq2=None, buf=None, cs=False, MD=False, max_frag_len=None, extra_flags=None):
+        if self._idx is None:
+            return
+        if seq2 is not None:
+            raise NotImplementedError("paired mapping is not on monica's path")
+        b = seq.encode() if isinstance(seq, str) else bytes(seq)
+        hits = self.map_batch([b])
+        for i in range(hits.n):
+            yield self._alignment(hits, i)
+
+    def _alignment(self, hits: Hits, i: int) -> Alignment:
+        rid = int(hits.rid[i])
+        cg = hits.cigar(i)
+        cigar = [[int(c >> 4), int(c & 0xf)] for c in cg]
+        return Alignment(self._names[rid], self._lens[rid], int(hits.rs[i]), int(hits.re[i]), -1 if hits.rev[i] else 1,
+                         int(hits.qs[i]), int(hits.qe[i]), int(hits.mapq[i]), bool(hits.is_primary[i]), int(hits.mlen[i]),
+                         int(hits.blen[i]), int(hits.nm[i]), cigar, int(hits.dp_max[i]), rid)
+
+    # ---- batched entry (the product path) ----
+    def map_batch(self, seqs=None, cat: np.ndarray | None = None, off: np.ndarray | None = None) -> Hits:
+        """Map many reads in one device pipeline.  Either `seqs` (list of bytes/str/uint8 arrays) or a
+        pre-concatenated (cat uint8[total], off int64[n+1]) pair.  Thread-safe."""
+        if self._idx is None:
+            raise _lib.MonicaB200Error(-1, "empty index")
+        if cat is None:
+            arrs = [np.frombuffer(s.encode() if isinstance(s, str) else s, dtype=np.uint8) if not isinstance(s, np.ndarray)
+                    else s.astype(np.uint8, copy=False) for s in seqs]
+            off = np.zeros(len(arrs) + 1, dtype=np.int64)
+            if arrs:
+                off[1:] = np.cumsum([len(a) for a in arrs])
+            cat = np.concatenate(arrs) if arrs else np.zeros(0, np.uint8)
+        cat = np.ascontiguousarray(cat, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        n = len(off) - 1
+        h = C.c_void_p()
+        st = Stats()
+        check(lib().mb_map_batch(self._idx, C.byref(self.opt), cat.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p),
+                                 n, C.byref(h), C.byref(st)))
+        self.last_stats = st.as_dict()
+        return Hits(h, n)
+
+    def count(self, hits: Hits, mapq_min: int = 60, mode: str | None = "basic"):
+        """monica's hit filter + best_hit + per-target sum on the device (aligner.py:193-195,225-263,328-339).
+        Returns (counts int64[n_seq], n_class [mapped, unmapped, ambiguous], read_class int8[n_reads], read_best int64[n_reads])."""
+        m = {"basic": 0, "query_length": 1, "matching": 2}.get(mode, 3)
+        counts = np.zeros(self.n_seq, dtype=np.int64)
+        ncls = np.zeros(3, dtype=np.int64)
+        rcls = np.zeros(max(1, hits.n_reads), dtype=np.int8)
+        rbest = np.zeros(max(1, hits.n_reads), dtype=np.int64)
+        check(lib().mb_count(self._idx, hits.handle(), mapq_min, m, counts.ctypes.data_as(C.c_void_p),
+                             ncls.ctypes.data_as(C.c_void_p), rcls.ctypes.data_as(C.c_void_p), rbest.ctypes.data_as(C.c_void_p)))
+        return counts, ncls, rcls[:hits.n_reads], rbest[:hits.n_reads]
+
+
+def fastx_read(fn, read_comment=False):
+    """mappy.fastx_read: yields (name, seq, qual[, comment])."""
+    from .fastx import parse_fastx
+    for name, comment, seq, qual in parse_fastx(fn):
+        if read_comment:
+            yield name, seq, qual, comment
+        else:
+            yield name, seq, qual
+
+
+def revcomp(seq):
+    tab = str.maketrans("ACGTUNacgtun", "TGCAANtgcaan")
+    return seq.translate(tab)[::-1]
