@@ -155,3 +155,41 @@ def write_fasta_gz(path: str, names: list[str], seqs: list[np.ndarray]):
             b = s.tobytes()
             for i in range(0, len(b), 80):
                 fh.write(b[i:i + 80] + b"\n")
+
+
+def edge_reads(seed: int, seqs: list[np.ndarray]):
+    """Hand-shaped reads that reach the rarely-taken paths: empty / shorter than k / N-containing reads, chimeras
+    (two loci in one read), a long junk insertion (band-limited DP, Z-drop split), a long deletion, a read overhanging a
+    contig end, an exact (error-free) read and a reverse-complement one, and a tandem-repeat read (anchor ties)."""
+    rng = np.random.default_rng(seed)
+    g = seqs[0]
+    G = len(g)
+    out = []
+    out.append(np.zeros(0, dtype=np.uint8))                                   # empty
+    out.append(g[100:110].copy())                                             # shorter than k
+    out.append(g[200:240].copy())                                             # a few minimizers only
+    r = mutate(rng, g[1000:4000], 0.03, 0.02, 0.02); r[500:520] = ord("N"); r[1500] = ord("n"); out.append(r)  # Ns
+    a = mutate(rng, g[5000:8000], 0.04, 0.03, 0.03)
+    b = mutate(rng, revcomp(g[min(G - 3500, 20000):min(G - 500, 23000)]), 0.04, 0.03, 0.03)
+    out.append(np.concatenate([a, b]))                                        # chimera, different strands
+    out.append(np.concatenate([mutate(rng, g[9000:11500], 0.04, 0.03, 0.03), random_genome(rng, 2000),
+                               mutate(rng, g[11500:14000], 0.04, 0.03, 0.03)]))  # 2 kb junk insertion
+    out.append(np.concatenate([mutate(rng, g[15000:17000], 0.04, 0.03, 0.03),
+                               mutate(rng, g[18200:20500], 0.04, 0.03, 0.03)]))  # 1.2 kb deletion
+    out.append(np.concatenate([random_genome(rng, 900), mutate(rng, g[0:2500], 0.04, 0.03, 0.03)]))  # overhang at contig start
+    out.append(np.concatenate([mutate(rng, g[G - 2500:G], 0.04, 0.03, 0.03), random_genome(rng, 1200)]))  # overhang at end
+    out.append(g[30000:33000].copy())                                         # exact
+    out.append(revcomp(g[33000:36000]))                                       # exact, reverse strand
+    unit = random_genome(rng, 37)
+    out.append(np.concatenate([g[40000:41000], np.tile(unit, 40), g[41000:42000]]))  # tandem repeat inside the read
+    out.append(np.tile(g[42000:42600], 4))                                    # the read repeats a reference segment 4x
+    out.append(random_genome(rng, 5000))                                      # unmappable
+    blk = mutate(rng, g[46000:52000], 0.03, 0.02, 0.02); blk[2500:3400] = random_genome(rng, 900)
+    out.append(blk)                                                           # divergent block: Z-drop test -> 2nd pass -> split
+    inv = g[52000:58000].copy(); inv[2000:3200] = revcomp(inv[2000:3200])
+    out.append(mutate(rng, inv, 0.03, 0.02, 0.02))                            # internal inversion: zdrop_code 2, split_inv
+    blk2 = mutate(rng, g[2000:9000], 0.05, 0.04, 0.04); blk2[1500:2100] = random_genome(rng, 600); blk2[4000:4700] = random_genome(rng, 700)
+    out.append(blk2)                                                          # two divergent blocks: repeated splitting
+    lower = np.char.lower(g[44000:46000].tobytes().decode()).encode() if False else bytes(g[44000:46000]).lower()
+    out.append(np.frombuffer(lower, dtype=np.uint8).copy())                   # lower-case bases
+    return out

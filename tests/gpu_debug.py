@@ -23,9 +23,12 @@ CMP_FIELDS = ["rid", "rev", "qs", "qe", "rs", "re", "mapq", "mlen", "blen", "nm"
               "subsc", "n_sub", "id", "parent", "is_primary", "sam_pri", "n_cigar"]
 
 
-def make_case(seed=1, n_genomes=3, glen=60000, n_reads=60, mean_len=3000, error=0.10, strain_frac=0.34, junk=0.05):
+def make_case(seed=1, n_genomes=3, glen=int(os.environ.get('GLEN', 60000)), n_reads=60, mean_len=3000, error=0.10, strain_frac=0.34, junk=0.05):
     names, seqs = synth.make_genomes(seed, n_genomes, glen, strain_frac=strain_frac)
     reads, truth = synth.simulate_reads(seed + 1, seqs, n_reads, mean_len, error, junk_frac=junk)
+    edge = synth.edge_reads(seed + 2, seqs)
+    reads = edge + reads
+    truth = [(-2, 0, 0, 0)] * len(edge) + truth
     return names, seqs, reads, truth
 
 
