@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- mapped Gbases/s of the map-ont -> per-taxon-count hot path on N B200s (one process per GPU).
+
+A step = one pass of the hot path (sketch -> seed lookup -> chaining -> extension -> count) over this rank's batch of
+synthetic reads.  Workload at N=1 = BASELINE.json configs[1] (10 synthetic 5 Mb genomes, 100k simulated ONT reads, N50 8 kb,
+10 % error); at N>1 every rank maps its own 100k reads against its own index replica (weak scaling) and the per-target
+count vectors are combined with one NCCL all-reduce per step.
+
+  value  whole-job Gbases/s with the reads already resident in HBM (mb_map_resident + mb_count_last)
+  e2e    the same through the C-ABI call a user makes with HOST buffers (mb_map_batch from pinned memory, hits copied back)
+  roofline   the dominant kernel (k_dp, integer pipe): DP cells/s from its own CUDA-event time vs the measured INT32 rate
+  cpu_baseline  the CPU oracle (a restatement of minimap2-2.17, NOT mappy) on the host cores, bounded sample
+
+`--impl reference` times that CPU restatement as the reference arm (mappy itself is not installable offline).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+OPS_PER_CELL = 40   # integer ops per DP cell of the two-piece affine recurrence with direction flags
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--genomes", type=int, default=10)
+    ap.add_argument("--genome-len", type=int, default=5_000_000)
+    ap.add_argument("--reads", type=int, default=100_000, help="reads per GPU")
+    ap.add_argument("--n50", type=float, default=8000.0)
+    ap.add_argument("--error", type=float, default=0.10)
+    ap.add_argument("--cpu-sample", type=int, default=1500, help="reads in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed", type=int, default=20251018)
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"{a.genomes} synthetic {a.genome_len / 1e6:g} Mb genomes (20% strain copies), {a.reads} simulated ONT reads per GPU, "
+            f"N50 {a.n50 / 1e3:g} kb, {a.error * 100:g}% error, map-ont")
+
+
+def make_genomes(a):
+    from monica_b200 import synth
+    return synth.make_genomes(a.seed, a.genomes, a.genome_len, strain_frac=0.2)
+
+
+def _sim_block(args):
+    from monica_b200 import synth
+    seed, seqs, n, n50, err = args
+    return synth.simulate_reads_bulk(seed, seqs, n, n50, err)
+
+
+def make_reads(a, seqs, n_reads, seed):
+    """Simulate in parallel worker processes (the generator is numpy-bound)."""
+    from concurrent.futures import ProcessPoolExecutor
+    block = 5000
+    jobs = [(seed * 1000 + i, seqs, min(block, n_reads - s), a.n50, a.error) for i, s in enumerate(range(0, n_reads, block))]
+    nproc = max(1, min(len(jobs), (os.cpu_count() or 4) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+    if nproc > 1:
+        with ProcessPoolExecutor(nproc) as ex:
+            parts = list(ex.map(_sim_block, jobs))
+    else:
+        parts = [_sim_block(j) for j in jobs]
+    cat = np.concatenate([p[0] for p in parts])
+    lens = np.concatenate([np.diff(p[1]) for p in parts])
+    off = np.zeros(len(lens) + 1, dtype=np.int64)
+    off[1:] = np.cumsum(lens)
+    return cat, off
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def mapped_bases_from_oracle_hits(per_read_hits, lens, mapq_min=60):
+    """monica's filter + best_hit on oracle hits (for the CPU arms): bases of reads assigned to a target."""
+    tot = 0
+    for hits, L in zip(per_read_hits, lens):
+        kept = [(h["nm"], h["mlen"]) for h in hits if h["is_primary"] and h["mapq"] >= mapq_min]
+        if not kept:
+            continue
+        if len(kept) > 1:
+            best, margin = float("inf"), 0
+            for nm, ml in kept:
+                r = nm / ml
+                if r <= best:
+                    margin, best = best - r, r
+            if not margin:
+                continue
+        tot += int(L)
+    return tot
+
+
+def cpu_arm(a, names, seqs, n_sample, steps, warmup):
+    """Time the CPU restatement on a bounded sample with all host threads; returns (Gbases/s mapped, info)."""
+    from oracle import oracle as O
+    O.build()
+    cat, off = make_reads(a, seqs, n_sample, a.seed + 777)
+    oidx = O.Index(names, seqs)
+    cores = os.cpu_count() or 1
+    lens = np.diff(off)
+    hits, _ = oidx.map_batch(cat, off, n_threads=cores)   # one untimed pass also yields the mapped-base count
+    mapped = mapped_bases_from_oracle_hits(hits, lens)
+    for _ in range(max(0, warmup - 1)):
+        oidx.map_batch_raw(cat, off, n_threads=cores)
+    times, cells = [], 0
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        tot = oidx.map_batch_raw(cat, off, n_threads=cores)
+        times.append(time.perf_counter() - t0)
+        cells = tot["dp_cells"]
+    dt = float(np.mean(times))
+    return mapped / dt / 1e9, dict(cores=cores, sample=f"{n_sample} reads / {int(off[-1])} bases of the same workload per step",
+                                   seconds_per_step=dt, total_gbases_per_s=float(off[-1]) / dt / 1e9, gcups=cells / dt / 1e9)
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    names, seqs = make_genomes(a)
+    v, info = cpu_arm(a, names, seqs, a.cpu_sample, a.steps, a.warmup)
+    out = {
+        "impl": "reference", "metric": "mapped Gbases/s", "value": v, "unit": "Gbases/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": info["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int8 DP / uint64 hashing", "data": "synthetic",
+        "config": {"workload": workload_name(a), "note": "CPU restatement of minimap2-2.17 map-ont (oracle/), NOT mappy: mappy is not installable offline"},
+        "cpu_baseline": {"value": v, "unit": "Gbases/s", "cores": info["cores"], "kind": "port", "sample": info["sample"],
+                         "total_gbases_per_s": info["total_gbases_per_s"], "gcups": info["gcups"]},
+        "e2e": {"value": v, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+    return 0
+
+
+class CudaArray:
+    """zero-copy torch view of a raw device pointer (__cuda_array_interface__)."""
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        return run_reference(a)
+    import torch
+    import torch.distributed as dist
+    from monica_b200 import _lib
+    from monica_b200.mappy_shim import Aligner
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    L = _lib.lib()
+
+    names, seqs = make_genomes(a)
+    t0 = time.perf_counter()
+    al = Aligner(names=names, seqs=seqs, device=local)
+    t_index = time.perf_counter() - t0
+    cat_np, off = make_reads(a, seqs, a.reads, a.seed + 1 + rank)
+    n_reads, total_bases = len(off) - 1, int(off[-1])
+    # pinned host copy of the reads for the e2e leg
+    pinned = torch.empty(total_bases, dtype=torch.uint8, pin_memory=True)
+    pinned.numpy()[:] = cat_np
+    cat = pinned.numpy()
+    del cat_np
+    n_seq = al.n_seq
+    opt = al.opt
+    counts = np.zeros(n_seq, dtype=np.int64)
+    ncls = np.zeros(3, dtype=np.int64)
+
+    reads_dev = C.c_void_p()
+    _lib.check(L.mb_reads_upload(al.handle(), _lib._ptr(cat), _lib._ptr(off), n_reads, C.byref(reads_dev)))
+
+    def allreduce_counts():
+        if world == 1:
+            return counts.copy()
+        t = torch.as_tensor(CudaArray(L.mb_count_device_ptr(al.handle()), n_seq), device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)     # one NCCL all-reduce of the int64[n_targets] vector
+        return t.cpu().numpy()
+
+    def step_value():
+        h = C.c_void_p(); st = _lib.Stats()
+        _lib.check(L.mb_map_resident(al.handle(), C.byref(opt), reads_dev, 0, C.byref(h), C.byref(st)))
+        _lib.check(L.mb_count_last(al.handle(), 60, 1, _lib._ptr(counts), _lib._ptr(ncls)))
+        L.mb_hits_free(h)
+        tot = allreduce_counts()
+        return st, tot
+
+    def step_e2e():
+        h = C.c_void_p(); st = _lib.Stats()
+        _lib.check(L.mb_map_batch(al.handle(), C.byref(opt), _lib._ptr(cat), _lib._ptr(off), n_reads, C.byref(h), C.byref(st)))
+        _lib.check(L.mb_count_last(al.handle(), 60, 1, _lib._ptr(counts), _lib._ptr(ncls)))
+        nh = L.mb_hits_n(h)
+        nc = C.c_int64(0); L.mb_hits_cigar_pool(h, C.byref(nc))
+        d2h = nh * 4 * len(_lib.HIT_FIELDS) + nh * 8 + nc.value * 4 + n_reads * 4 + (n_reads + 1) * 8 + n_seq * 8 + 24
+        L.mb_hits_free(h)
+        tot = allreduce_counts()
+        return st, tot, d2h
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- value leg: resident inputs ----
+    for _ in range(a.warmup):
+        step_value()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    stats = []
+    for _ in range(a.steps):
+        st, tot_counts = step_value()
+        stats.append(st.as_dict())
+    barrier()
+    dt_value = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop()
+    mapped_bases_rank = float(counts.sum())            # this rank's bases assigned to a target (query_length mode)
+    mapped_bases_all = float(tot_counts.sum()) if world > 1 else mapped_bases_rank
+    total_bases_all = sum_over_ranks(float(total_bases))
+    value = mapped_bases_all * a.steps / dt_value / 1e9
+
+    # ---- e2e leg: host buffers through the C ABI ----
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(a.steps):
+        st_e, tot_counts_e, d2h = step_e2e()
+    barrier()
+    dt_e2e = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = float(tot_counts_e.sum() if world > 1 else counts.sum()) * a.steps / dt_e2e / 1e9
+
+    # ---- roofline of the dominant kernel (k_dp) ----
+    last = stats[-1]
+    ms_kdp = float(np.mean([s["ms_kdp"] for s in stats]))
+    cells = float(np.mean([s["dp_cells"] for s in stats]))
+    tiops = C.c_double(0)
+    _lib.check(L.mb_int_peak(local, C.byref(tiops)))
+    peak_gcups = tiops.value * 1e3 / OPS_PER_CELL
+    gcups = cells / (ms_kdp * 1e-3) / 1e9 if ms_kdp > 0 else 0.0
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    sketch_bytes = (last["n_bases"] + 16 * last["n_mini"]) * 2   # count + write passes, 1 B/base nt4 in, 16 B/minimizer out
+    seed_bytes = 32 * last["n_mini"] + 24 * last["n_anchor"] + 32 * last["n_anchor"]
+    stage_ms = {k: float(np.mean([s[k] for s in stats])) for k in ("ms_sketch", "ms_seed", "ms_chain", "ms_glue", "ms_dp", "ms_post", "ms_total", "ms_kdp")}
+    roofline = {
+        "kernel": "k_dp (two-piece affine banded DP + traceback, ksw_extd2 equivalent)", "bound": "int", "achieved": gcups, "peak": peak_gcups, "unit": "GCUPS",
+        "frac": gcups / peak_gcups if peak_gcups else None, "traffic": None,
+        "peak_source": f"measured INT32 add/max issue rate {tiops.value:.1f} Tops/s on this GPU (mb_int_peak) / {OPS_PER_CELL} int ops per cell",
+        "share_of_step": ms_kdp / stage_ms["ms_total"] if stage_ms["ms_total"] else None,
+        "hbm_kernels": {
+            "k_sketch": {"bound": "hbm", "achieved": sketch_bytes / (stage_ms["ms_sketch"] * 1e-3) / 1e9 if stage_ms["ms_sketch"] else None,
+                         "peak": hbm_peak, "unit": "GB/s", "note": "stage time includes two scans and a host sync"},
+            "k_seed_lookup+fill+sort": {"bound": "hbm", "achieved": seed_bytes / (stage_ms["ms_seed"] * 1e-3) / 1e9 if stage_ms["ms_seed"] else None,
+                                        "peak": hbm_peak, "unit": "GB/s"},
+        },
+    }
+
+    out = None
+    if rank == 0:
+        cpu = None
+        if world == 1 and not a.no_cpu_baseline:
+            try:
+                v, info = cpu_arm(a, names, seqs, a.cpu_sample, 1, 1)
+                cpu = {"value": v, "unit": "Gbases/s", "cores": info["cores"], "kind": "port", "sample": info["sample"],
+                       "total_gbases_per_s": info["total_gbases_per_s"], "gcups": info["gcups"],
+                       "note": "CPU restatement of minimap2-2.17 (scalar int8 DP), not mappy"}
+            except Exception as e:  # the baseline must never sink the bench line
+                cpu = {"value": None, "unit": "Gbases/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+        out = {
+            "metric": "mapped Gbases/s", "value": value, "unit": "Gbases/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": dt_value / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int8 DP / int32 chaining / uint64 hashing", "data": "synthetic",
+            "config": {"workload": workload_name(a), "reads_per_gpu": n_reads, "bases_per_gpu": total_bases, "l2": "inputs larger than L2 (no flush needed)",
+                       "index_hbm_bytes": int(L.mb_index_hbm_bytes(al.handle())), "index_build_s": t_index, "parallelism": f"reads sharded over {world} GPU(s), index replicated, 1 NCCL all-reduce of int64[{n_seq}] per step"},
+            "total_gbases_per_s": total_bases_all * a.steps / dt_value / 1e9,
+            "mapped_fraction": mapped_bases_all / total_bases_all if total_bases_all else None,
+            "e2e": {"value": e2e_value, "unit": "Gbases/s", "h2d_bytes_per_step": int(total_bases + 8 * (n_reads + 1)), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": dt_e2e / a.steps * 1e3},
+            "gpu_launches": int(sum(s["n_launches"] for s in stats)) + a.steps,
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "stage_ms": stage_ms,
+            "work_per_step": {k: last[k] for k in ("n_reads", "n_bases", "n_mini", "n_anchor", "n_regs", "n_dp_tasks", "n_dp_pass2", "dp_cells", "n_hits", "n_rounds")},
+            "read_classes": {"mapped": int(ncls[0]), "unmapped": int(ncls[1]), "ambiguous": int(ncls[2])},
+        }
+        print(json.dumps(out))
+    L.mb_reads_free(reads_dev)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

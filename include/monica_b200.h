@@ -59,6 +59,8 @@ typedef struct {
 	int64_t n_reads, n_bases, n_mini, n_anchor, n_regs, n_dp_tasks, n_dp_pass2, dp_cells, n_hits, n_rounds;
 	float   ms_sketch, ms_seed, ms_sort, ms_chain, ms_glue, ms_dp, ms_post, ms_total, ms_h2d, ms_d2h;
 	int64_t n_launches;       /* kernels launched for this batch */
+	float   ms_kdp;           /* CUDA-event time of the k_dp launches alone (the roofline kernel) */
+	int32_t n_kdp;            /* number of k_dp launches */
 } mb_stats_t;
 
 const char *mb_last_error(void);
@@ -108,6 +110,9 @@ void mb_hits_free(mb_hits_t *h);
  * read_best[n_reads]: hit index chosen or -1.  Any pointer may be NULL. */
 int  mb_count(mb_index_t *idx, const mb_hits_t *h, int32_t mapq_min, int mode, int64_t *counts, int64_t *n_class,
               int8_t *read_class, int64_t *read_best);
+/* same, on the device-resident hits of the calling thread's LAST mb_map_batch / mb_map_resident on this index (no host
+ * round trip of the hit arrays; valid until that thread's next mapping call) */
+int  mb_count_last(mb_index_t *idx, int32_t mapq_min, int mode, int64_t *counts, int64_t *n_class);
 /* device pointer to the int64[n_seq] count vector of the LAST mb_count on this thread (for the NCCL allreduce) */
 void *mb_count_device_ptr(mb_index_t *idx);
 int  mb_count_fetch(mb_index_t *idx, int64_t *counts);
@@ -133,6 +138,9 @@ typedef struct {
 } mb_dp_task_t;
 int  mb_dp_batch(int device, const mb_opt_t *opt, mb_dp_task_t *tasks, int64_t n_tasks, const uint8_t *seqpool, int64_t n_seqpool,
                  uint32_t *cigar_pool, int64_t n_cigar_pool);
+
+/* ---- measurement helper: sustained INT32 add/max issue rate of the device (roofline denominator for K3/K4) ---- */
+int  mb_int_peak(int device, double *tera_int_ops_per_s);
 
 #ifdef __cplusplus
 }

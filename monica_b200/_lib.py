@@ -38,7 +38,7 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("n_reads", "n_bases", "n_mini", "n_anchor", "n_regs", "n_dp_tasks", "n_dp_pass2",
                                          "dp_cells", "n_hits", "n_rounds")] + \
                [(n, C.c_float) for n in ("ms_sketch", "ms_seed", "ms_sort", "ms_chain", "ms_glue", "ms_dp", "ms_post",
-                                         "ms_total", "ms_h2d", "ms_d2h")] + [("n_launches", C.c_int64)]
+                                         "ms_total", "ms_h2d", "ms_d2h")] + [("n_launches", C.c_int64), ("ms_kdp", C.c_float), ("n_kdp", C.c_int32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -64,8 +64,8 @@ SYMBOLS = [
     "mb_index_seq_name", "mb_index_seq_len", "mb_index_mid_occ", "mb_index_kw", "mb_index_n_minimizers", "mb_index_hbm_bytes",
     "mb_map_batch", "mb_reads_upload", "mb_reads_free", "mb_map_resident",
     "mb_hits_n", "mb_hits_field", "mb_hits_cigar_off", "mb_hits_cigar_pool", "mb_hits_rep_len", "mb_hits_free",
-    "mb_count", "mb_count_device_ptr", "mb_count_fetch",
-    "mb_sketch", "mb_seed", "mb_chain", "mb_dp_batch",
+    "mb_count", "mb_count_last", "mb_count_device_ptr", "mb_count_fetch",
+    "mb_sketch", "mb_seed", "mb_chain", "mb_dp_batch", "mb_int_peak",
 ]
 
 _lib = None
@@ -119,6 +119,8 @@ def lib():
     L.mb_hits_free.argtypes = [vp]
     L.mb_hits_free.restype = None
     L.mb_count.argtypes = [vp, vp, i32, C.c_int, vp, vp, vp, vp]
+    L.mb_count_last.argtypes = [vp, i32, C.c_int, vp, vp]
+    L.mb_int_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.mb_count_device_ptr.argtypes = [vp]
     L.mb_count_device_ptr.restype = vp
     L.mb_count_fetch.argtypes = [vp, vp]

@@ -65,6 +65,9 @@ struct ThreadCtx {
 	int num_sms = 148;
 	uint8_t *h_pin = nullptr; size_t h_pin_cap = 0;   // pinned staging for reads
 	unsigned long long *d_counts = nullptr; int n_counts = 0; // last mb_count vector
+	// device-resident result of the last mapping call (lives in the arena until the next reset)
+	const int32_t *last_fields = nullptr; const int64_t *last_hit_off = nullptr, *last_read_off = nullptr;
+	int64_t last_n_hits = 0; int32_t last_n_reads = -1; const void *last_index = nullptr;
 	~ThreadCtx() {
 		if (device >= 0) {
 			cudaSetDevice(device);
@@ -506,7 +509,10 @@ __global__ void k_dp_classify(const DpTask *__restrict__ tasks, const int32_t *_
 
 struct DpRunner {
 	ThreadCtx &c; cudaStream_t st; int64_t *nl;
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evs; // one pair per k_dp launch, read back after the batch
 	DpRunner(ThreadCtx &c_, int64_t *nl_) : c(c_), st(c_.st), nl(nl_) {}
+	~DpRunner() { for (auto &e : evs) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); } }
+	float total_ms() { float t = 0; for (auto &e : evs) { float ms = 0; if (cudaEventElapsedTime(&ms, e.first, e.second) == cudaSuccess) t += ms; } return t; }
 	// run k_dp over `n` tasks (ids[] if use_ids else 0..n-1)
 	void run(DpTask *tasks, const int32_t *ids, int64_t n, bool use_ids, const uint8_t *codes, const uint32_t *S, const uint8_t *pool,
 	         uint32_t *cigar_pool, const DpScoring &sc, unsigned long long *d_cells)
@@ -544,8 +550,12 @@ struct DpRunner {
 			int32_t *h_scr = ar.get<int32_t>(n_warps * h_stride);
 			int32_t *wc = ar.get<int32_t>(1);
 			CK(cudaMemsetAsync(wc, 0, sizeof(int32_t), st));
+			cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+			cudaEventRecord(e0, st);
 			k_dp<<<n_cta, DP_WARPS * 32, DP_WARPS * DP_SMEM_PER_WARP, st>>>(tasks, cls ? big_list : small_list, ctr + cls, wc, codes, S, pool,
 				p_scr, p_stride, g_ws, g_stride, h_scr, h_stride, cigar_pool, sc, d_cells);
+			cudaEventRecord(e1, st);
+			evs.emplace_back(e0, e1);
 			++*nl;
 		}
 	}
@@ -713,6 +723,7 @@ static mb_hits *map_device(mb_index *ix, const mb_opt_t &opt_in, ThreadCtx &c, c
 	k_write_hits<<<rb, 128, 0, st>>>(ra, n_reads, hit_off, hcig_off, n_h, d_fields, d_hcoff, (const uint32_t*)nullptr, d_hcig); ++nl;
 	S.ms_post = tm.stop();
 	S.n_hits = n_h;
+	c.last_fields = d_fields, c.last_hit_off = hit_off, c.last_read_off = d_off, c.last_n_hits = n_h, c.last_n_reads = n_reads, c.last_index = ix;
 	unsigned long long h_cells[2];
 	CK(cudaMemcpyAsync(h_cells, d_cells, sizeof(h_cells), cudaMemcpyDeviceToHost, st));
 	tm.start();
@@ -732,6 +743,7 @@ static mb_hits *map_device(mb_index *ix, const mb_opt_t &opt_in, ThreadCtx &c, c
 	S.ms_d2h = tm.stop();
 	S.dp_cells = (int64_t)h_cells[1];
 	S.n_launches = nl;
+	S.ms_kdp = runner.total_ms(); S.n_kdp = (int32_t)runner.evs.size();
 	S.ms_total = tall.stop();
 	if (stats) { float h2d = stats->ms_h2d; *stats = S; stats->ms_h2d = h2d; }
 	return H.release();
@@ -840,6 +852,68 @@ extern "C" int mb_count(mb_index_t *ix, const mb_hits_t *h, int32_t mapq_min, in
 	if (read_best && n_reads) CK(cudaMemcpyAsync(read_best, d_best, (size_t)n_reads * 8, cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));
 	CK(cudaGetLastError());
+	API_END
+}
+
+extern "C" int mb_count_last(mb_index_t *ix, int32_t mapq_min, int mode, int64_t *counts, int64_t *n_class)
+{
+	API_BEGIN
+	if (!ix) throw mb_error(MB_ERR_ARG, "bad arguments");
+	ThreadCtx &c = get_ctx(ix->device);
+	if (c.last_index != ix || c.last_n_reads < 0) throw mb_error(MB_ERR_ARG, "no mapped batch of this index on this thread");
+	cudaStream_t st = c.st;
+	const int n_seq = (int)ix->names.size(), n_reads = c.last_n_reads;
+	if (c.n_counts < n_seq + 4) {
+		if (c.d_counts) cudaFree(c.d_counts);
+		CK(cudaMalloc(&c.d_counts, (size_t)(n_seq + 4) * 8));
+		c.n_counts = n_seq + 4;
+	}
+	CK(cudaMemsetAsync(c.d_counts, 0, (size_t)(n_seq + 4) * 8, st));
+	if (n_reads) k_count<<<(unsigned)cdiv(n_reads, 128), 128, 0, st>>>(n_reads, c.last_hit_off, c.last_n_hits, c.last_fields, c.last_read_off, mapq_min, mode,
+		c.d_counts, c.d_counts + n_seq, nullptr, nullptr);
+	if (counts) CK(cudaMemcpyAsync(counts, c.d_counts, (size_t)n_seq * 8, cudaMemcpyDeviceToHost, st));
+	if (n_class) CK(cudaMemcpyAsync(n_class, c.d_counts + n_seq, 3 * 8, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	CK(cudaGetLastError());
+	API_END
+}
+
+// sustained INT32 issue rate: 8 independent add/max chains per thread (IADD3 + IMNMX alternate), all SMs busy
+__global__ void k_int_peak(int *out, int iters, int seed)
+{
+	int a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+	const int b = seed | 1, m = seed + 12345;
+	#pragma unroll 1
+	for (int i = 0; i < iters; ++i) {
+		#pragma unroll
+		for (int k = 0; k < 8; ++k) {
+			a0 = max(a0 + b, m); a1 = max(a1 + b, m); a2 = max(a2 + b, m); a3 = max(a3 + b, m);
+			a4 = max(a4 + b, m); a5 = max(a5 + b, m); a6 = max(a6 + b, m); a7 = max(a7 + b, m);
+		}
+	}
+	if ((a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7) == 0x7fffffff) out[0] = a0;
+}
+
+extern "C" int mb_int_peak(int device, double *tops)
+{
+	API_BEGIN
+	ThreadCtx &c = get_ctx(device);
+	int *d; CK(cudaMalloc(&d, 64));
+	const int iters = 4096, grid = c.num_sms * 8, tpb = 256;
+	k_int_peak<<<grid, tpb, 0, c.st>>>(d, 64, 1);
+	Timer tm(c.st);
+	float best = 1e30f;
+	for (int rep = 0; rep < 5; ++rep) {
+		tm.start();
+		k_int_peak<<<grid, tpb, 0, c.st>>>(d, iters, rep + 2);
+		float ms = tm.stop();
+		if (ms < best) best = ms;
+	}
+	CK(cudaGetLastError());
+	cudaFree(d);
+	// 2 integer ops (add, max) x 8 chains x 8 unrolled x iters per thread
+	double ops = 2.0 * 8 * 8 * iters * (double)grid * tpb;
+	if (tops) *tops = ops / (best * 1e-3) / 1e12;
 	API_END
 }
 

@@ -193,3 +193,62 @@ def edge_reads(seed: int, seqs: list[np.ndarray]):
     lower = np.char.lower(g[44000:46000].tobytes().decode()).encode() if False else bytes(g[44000:46000]).lower()
     out.append(np.frombuffer(lower, dtype=np.uint8).copy())                   # lower-case bases
     return out
+
+
+def simulate_reads_bulk(seed: int, seqs: list[np.ndarray], n_reads: int, n50: float, error: float = 0.10,
+                        mix: tuple[float, float, float] = (0.4, 0.3, 0.3), sigma: float = 0.6, block: int = 2000,
+                        min_len: int = 500, max_len: int | None = None):
+    """Vectorised simulator for bench-sized workloads: returns (cat uint8[total], off int64[n+1]).
+
+    Read lengths are log-normal with length-weighted median (N50) = n50: mu = ln(n50) - sigma^2.  Errors are i.i.d.
+    substitution / insertion / deletion at `error` x mix (default 4% / 3% / 3% at 10%), strands are random."""
+    rng = np.random.default_rng(seed)
+    glens = np.array([len(s) for s in seqs], dtype=np.int64)
+    gcat = np.concatenate(seqs)
+    goff = np.zeros(len(seqs) + 1, dtype=np.int64)
+    goff[1:] = np.cumsum(glens)
+    prob = glens / glens.sum()
+    mu = np.log(n50) - sigma * sigma
+    sub, ins, dele = (error * m for m in mix)
+    chunks, lens_out = [], []
+    done = 0
+    while done < n_reads:
+        nb = min(block, n_reads - done)
+        L = np.maximum(rng.lognormal(mu, sigma, size=nb).astype(np.int64), min_len)
+        if max_len is not None:
+            L = np.minimum(L, max_len)
+        c = rng.choice(len(seqs), size=nb, p=prob)
+        L = np.minimum(L, glens[c])
+        st = (rng.random(nb) * (glens[c] - L + 1)).astype(np.int64)
+        strand = rng.integers(0, 2, size=nb).astype(bool)
+        # gather all fragments of the block with one index array; reverse strands read backwards and complemented
+        roff = np.zeros(nb + 1, dtype=np.int64)
+        roff[1:] = np.cumsum(L)
+        within = np.arange(roff[-1], dtype=np.int64) - np.repeat(roff[:-1], L)
+        rid = np.repeat(np.arange(nb), L)
+        pos = np.where(strand[rid], (st + L - 1)[rid] - within, st[rid] + within) + goff[c][rid]
+        frag = gcat[pos]
+        rs = strand[rid]
+        frag[rs] = _COMP[frag[rs]]
+        # errors over the whole block at once
+        r = rng.random(len(frag), dtype=np.float32)
+        is_sub = r < sub
+        if is_sub.any():
+            codes = np.searchsorted(_ACGT, frag[is_sub])
+            frag[is_sub] = _ACGT[(codes + rng.integers(1, 4, size=int(is_sub.sum()))) % 4]
+        is_del = (r >= sub) & (r < sub + dele)
+        is_ins = (r >= sub + dele) & (r < sub + dele + ins)
+        reps = (~is_del).astype(np.int8) + is_ins.astype(np.int8)
+        idx = np.repeat(np.arange(len(frag), dtype=np.int64), reps)
+        out = frag[idx]
+        dup = np.zeros(len(idx), dtype=bool)
+        dup[1:] = idx[1:] == idx[:-1]
+        out[dup] = _ACGT[rng.integers(0, 4, size=int(dup.sum()))]
+        newlen = np.bincount(rid, weights=reps, minlength=nb).astype(np.int64)
+        chunks.append(out)
+        lens_out.append(newlen)
+        done += nb
+    lens_all = np.concatenate(lens_out)
+    off = np.zeros(n_reads + 1, dtype=np.int64)
+    off[1:] = np.cumsum(lens_all)
+    return np.ascontiguousarray(np.concatenate(chunks)), off

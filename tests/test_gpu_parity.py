@@ -1,0 +1,364 @@
+"""GPU parity tests (run on the B200 box: python -m pytest tests -m gpu).  Every check goes through the C ABI
+(include/monica_b200.h) and compares bit-exactly with the CPU oracle on the same seeded inputs, and with the committed
+golden vectors (tests/golden/: oracle hits; outputs of the unmodified reference aligner.py).  /root/reference is not read.
+"""
+import ctypes as C
+import json
+import os
+import shutil
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CMP_FIELDS = ["rid", "rev", "qs", "qe", "rs", "re", "mapq", "mlen", "blen", "nm", "dp_max", "dp_max2", "score", "score0", "cnt",
+              "subsc", "n_sub", "id", "parent", "is_primary", "sam_pri", "n_cigar"]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from monica_b200 import _lib
+    L = _lib.lib()
+    assert L.mb_device_count() > 0, "no CUDA device: these tests must run on the GPU box"
+    return L
+
+
+@pytest.fixture(scope="module")
+def case(small_case, oracle, lib):
+    from monica_b200.mappy_shim import Aligner
+    names, seqs, reads = small_case
+    al = Aligner(names=names, seqs=seqs, device=0)
+    oidx = oracle.Index(names, seqs)
+    traces = [oidx.map(r, trace=True) for r in reads]
+    return al, oidx, reads, traces
+
+
+def test_native_library_is_the_one_loaded(lib):
+    from monica_b200 import _lib
+    assert os.path.samefile(_lib.SO_PATH, os.path.join(ROOT, "monica_b200", "lib", "libmonica_b200.so"))
+    with open("/proc/self/maps") as fh:
+        assert "libmonica_b200.so" in fh.read()
+
+
+def test_index_metadata(case):
+    al, oidx, reads, _ = case
+    assert al.mid_occ == oidx.mid_occ
+    assert al.k == 15 and al.w == 10 and al.n_seq == 3
+
+
+def test_sketch_bit_exact(case, oracle, lib):
+    from monica_b200 import _lib, synth
+    al, oidx, reads, _ = case
+    cat, off = synth.concat_reads(reads)
+    cap = len(cat) + 64
+    out = np.zeros((cap, 2), dtype=np.uint64)
+    ooff = np.zeros(len(reads) + 1, dtype=np.int64)
+    _lib.check(lib.mb_sketch(0, _lib._ptr(cat), _lib._ptr(off), len(reads), 10, 15, _lib._ptr(out), cap, _lib._ptr(ooff)))
+    for i, r in enumerate(reads):
+        got = out[ooff[i]:ooff[i + 1]].copy()
+        assert np.all((got[:, 1] >> np.uint64(32)) == i)
+        got[:, 1] &= np.uint64(0xffffffff)
+        assert np.array_equal(oracle.sketch(r), got), f"read {i}"
+
+
+def test_sketch_chunk_boundaries_and_long_sequence(oracle, lib):
+    """Reads whose lengths straddle the 256-base chunk and 32768-base CTA spans, N runs at chunk edges, and one long contig."""
+    from monica_b200 import _lib, synth
+    rng = np.random.default_rng(17)
+    reads = [synth.random_genome(rng, n) for n in (1, 14, 15, 24, 25, 255, 256, 257, 511, 513, 32767, 32768, 32769, 70001)]
+    r = synth.random_genome(rng, 3000); r[250:262] = ord("N"); reads.append(r)
+    r = synth.random_genome(rng, 3000); r[300:340] = ord("N"); r[511] = ord("N"); r[512] = ord("N"); reads.append(r)
+    reads.append(np.tile(synth.random_genome(rng, 7), 300))            # low complexity: ties
+    reads.append(synth.random_genome(rng, 400000))                     # contig-sized
+    cat, off = synth.concat_reads(reads)
+    cap = len(cat) + 64
+    out = np.zeros((cap, 2), dtype=np.uint64)
+    ooff = np.zeros(len(reads) + 1, dtype=np.int64)
+    _lib.check(lib.mb_sketch(0, _lib._ptr(cat), _lib._ptr(off), len(reads), 10, 15, _lib._ptr(out), cap, _lib._ptr(ooff)))
+    for i, r in enumerate(reads):
+        got = out[ooff[i]:ooff[i + 1]].copy()
+        got[:, 1] &= np.uint64(0xffffffff)
+        assert np.array_equal(oracle.sketch(r), got), f"read {i} len {len(r)}"
+
+
+def test_seed_lookup_and_sort_bit_exact(case, lib):
+    from monica_b200 import _lib, synth
+    al, oidx, reads, traces = case
+    cat, off = synth.concat_reads(reads)
+    cap = len(cat) * 4 + 1024
+    out = np.zeros((cap, 2), dtype=np.uint64)
+    ooff = np.zeros(len(reads) + 1, dtype=np.int64)
+    rep = np.zeros(len(reads), dtype=np.int32)
+    _lib.check(lib.mb_seed(al.handle(), C.byref(al.opt), _lib._ptr(cat), _lib._ptr(off), len(reads), _lib._ptr(out), cap, _lib._ptr(ooff), _lib._ptr(rep)))
+    n_tie_reads = 0
+    for i, (hits, stats, tr) in enumerate(traces):
+        got = out[ooff[i]:ooff[i + 1]]
+        assert np.array_equal(tr["anchors"], got), f"read {i}"
+        assert stats["rep_len"] == rep[i]
+        if len(got) > 1 and np.any(got[1:, 0] == got[:-1, 0]):
+            n_tie_reads += 1
+    assert n_tie_reads > 0, "the case must contain anchors that tie on x (exercises the exact radix emulation)"
+
+
+def test_chain_bit_exact(case, lib):
+    from monica_b200 import _lib
+    al, oidx, reads, traces = case
+    anchors = [t[2]["anchors"] for t in traces]
+    off = np.zeros(len(anchors) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(x) for x in anchors])
+    n_a = int(off[-1])
+    cat = np.ascontiguousarray(np.concatenate(anchors), dtype=np.uint64)
+    f = np.zeros(n_a + 1, np.int32); p = np.zeros(n_a + 1, np.int32); v = np.zeros(n_a + 1, np.int32)
+    ch = np.zeros((n_a + 1, 2), np.uint64); choff = np.zeros(len(anchors) + 1, np.int64)
+    u = np.zeros(n_a + 1, np.uint64); uoff = np.zeros(len(anchors) + 1, np.int64)
+    _lib.check(lib.mb_chain(0, C.byref(al.opt), _lib._ptr(cat), _lib._ptr(off), len(anchors), _lib._ptr(f), _lib._ptr(p), _lib._ptr(v),
+                            _lib._ptr(ch), _lib._ptr(choff), _lib._ptr(u), _lib._ptr(uoff)))
+    for i, (_, _, tr) in enumerate(traces):
+        s, e = off[i], off[i + 1]
+        if e > s:
+            assert np.array_equal(tr["f"], f[s:e]) and np.array_equal(tr["p"], p[s:e]) and np.array_equal(tr["v"], v[s:e]), f"read {i}"
+        assert np.array_equal(tr["u"], u[uoff[i]:uoff[i + 1]]), f"read {i}"
+        assert np.array_equal(tr["chained"], ch[choff[i]:choff[i + 1]]), f"read {i}"
+
+
+def _run_dp(lib, opt, recs):
+    from monica_b200 import _lib
+    n = len(recs)
+    tasks = (_lib.DpTask * n)()
+    pool, po, co = [], 0, 0
+    for i, r in enumerate(recs):
+        tk = tasks[i]
+        tk.qlen, tk.tlen, tk.w, tk.zdrop, tk.end_bonus, tk.flag = r["qlen"], r["tlen"], r["w"], r["zdrop"], r["end_bonus"], r["flag"]
+        tk.q_off = po; pool.append(r["q"]); po += r["qlen"]
+        tk.t_off = po; pool.append(r["t"]); po += r["tlen"]
+        tk.cigar_off = co; co += r["qlen"] + r["tlen"] + 1
+    pool = np.ascontiguousarray(np.concatenate(pool), dtype=np.uint8)
+    cig = np.zeros(co + 1, dtype=np.uint32)
+    _lib.check(lib.mb_dp_batch(0, C.byref(opt), tasks, n, _lib._ptr(pool), len(pool), _lib._ptr(cig), len(cig)))
+    return tasks, cig
+
+
+def _check_dp(tasks, cig, recs):
+    for i, r in enumerate(recs):
+        tk = tasks[i]
+        keys = ["zdropped", "reach_end", "n_cigar", "score"]
+        if not (r["flag"] & 0x08):
+            keys += ["max", "max_q", "max_t", "mqe", "mqe_t"]
+        for k in keys:
+            assert getattr(tk, k) == r[k], (i, k, getattr(tk, k), r[k], r["qlen"], r["tlen"], hex(r["flag"]))
+        assert np.array_equal(cig[tk.cigar_off:tk.cigar_off + tk.n_cigar], r["cigar"]), (i, r["qlen"], r["tlen"])
+
+
+def test_dp_tasks_of_the_pipeline_bit_exact(case, lib):
+    al, oidx, reads, traces = case
+    recs = [d for t in traces for d in t[2]["dp"]]
+    assert any(not (r["flag"] & 0x08) and (r["flag"] & 0x40) == 0 for r in recs), "needs second-pass (exact, Z-drop) gap fills"
+    assert any(r["zdropped"] for r in recs)
+    tasks, cig = _run_dp(lib, al.opt, recs)
+    _check_dp(tasks, cig, recs)
+
+
+def test_dp_random_and_band_limited(oracle, lib):
+    """Stand-alone ksw_extd2 problems: tiny, ragged, N-containing, one-sided, and larger than the band (w=751 limits the
+    matrix, so the 16-lane block semantics outside the band matter), in all four flag combinations the aligner uses."""
+    from monica_b200 import _lib
+    rng = np.random.default_rng(23)
+    opt = _lib.default_opt()
+    recs = []
+    shapes = [(1, 1), (1, 40), (40, 1), (15, 17), (16, 16), (33, 200), (200, 33), (257, 255), (900, 1000), (1700, 1500), (2500, 300), (300, 2500)]
+    for (ql, tl) in shapes:
+        t = rng.integers(0, 4, tl).astype(np.uint8)
+        q = t[:ql].copy() if ql <= tl else np.concatenate([t, rng.integers(0, 4, ql - tl).astype(np.uint8)])
+        mut = rng.random(len(q)) < 0.12
+        q[mut] = rng.integers(0, 4, int(mut.sum()))
+        if ql > 20:
+            q[7] = 4
+        for flag, zdrop, eb in ((0x08, 400, -1), (0x00, 400, -1), (0x40, 400, -1), (0x40 | 0x02 | 0x80, 200, 10)):
+            for w in (751, 100 if max(ql, tl) > 300 else 751):
+                ez = oracle.ksw_extd2(q, t, w=w, zdrop=zdrop, end_bonus=eb, flag=flag)
+                recs.append(dict(qlen=ql, tlen=tl, w=w, zdrop=zdrop, end_bonus=eb, flag=flag, q=q, t=t, score=ez["score"], max=ez["max"],
+                                 max_q=ez["max_q"], max_t=ez["max_t"], mqe=ez["mqe"], mqe_t=ez["mqe_t"], zdropped=ez["zdropped"],
+                                 reach_end=ez["reach_end"], n_cigar=len(ez["cigar"]), cigar=ez["cigar"]))
+    tasks, cig = _run_dp(lib, opt, recs)
+    _check_dp(tasks, cig, recs)
+
+
+def _compare_hits(hits, per, i, want):
+    got = per[i]
+    assert len(want) == len(got), f"read {i}: oracle {len(want)} hits, GPU {len(got)}"
+    for w, g in zip(want, got):
+        for f in CMP_FIELDS:
+            assert int(getattr(hits, f)[g]) == int(w[f]), f"read {i} field {f}: GPU {int(getattr(hits, f)[g])} oracle {w[f]}"
+        assert np.array_equal(hits.cigar(g), w["cigar"]), f"read {i}: CIGAR"
+
+
+def test_full_pipeline_bit_exact_vs_oracle(case):
+    al, oidx, reads, traces = case
+    hits = al.map_batch(reads)
+    per = hits.per_read()
+    for i in range(len(reads)):
+        _compare_hits(hits, per, i, traces[i][0])
+    assert al.last_stats["n_rounds"] >= 2 and al.last_stats["n_dp_pass2"] > 0     # Z-drop splits were exercised
+    assert np.array_equal(hits.rep_len, np.array([t[1]["rep_len"] for t in traces], dtype=np.int32))
+    # one read at a time gives the same answer as the batch (the mappy-shaped .map())
+    for i in (3, 4, 15, 20):
+        one = list(al.map(reads[i].tobytes()))
+        assert [(a.rid, a.r_st, a.r_en, a.q_st, a.q_en, a.strand, a.mapq, a.mlen, a.NM, a.is_primary) for a in one] == \
+               [(w["rid"], w["rs"], w["re"], w["qs"], w["qe"], -1 if w["rev"] else 1, w["mapq"], w["mlen"], w["nm"], bool(w["is_primary"])) for w in traces[i][0]]
+
+
+def test_full_pipeline_equals_golden_vectors(lib):
+    from monica_b200.mappy_shim import Aligner
+    g = np.load(os.path.join(GOLDEN, "small_case.npz"), allow_pickle=False)
+    names = g["names"].tolist()
+    seqs = [g["genome_cat"][g["genome_off"][i]:g["genome_off"][i + 1]] for i in range(len(names))]
+    al = Aligner(names=names, seqs=seqs, device=0)
+    assert al.mid_occ == int(g["mid_occ"])
+    hits = al.map_batch(cat=g["read_cat"], off=g["read_off"])
+    fields = g["hit_fields"].tolist()
+    assert hits.n == len(g["hits"])
+    assert np.array_equal(np.bincount(hits.read_idx, minlength=len(g["read_off"]) - 1), np.diff(g["hit_off"]))
+    for j, f in enumerate(fields):
+        assert np.array_equal(getattr(hits, f), g["hits"][:, j]), f
+    assert np.array_equal(hits.cigar_pool, g["cigar"])
+
+
+def test_batch_order_invariance_and_threads(case):
+    """Results do not depend on batch composition, and concurrent callers (monica's ThreadPool) get the same answers."""
+    from multiprocessing.dummy import Pool
+    al, oidx, reads, traces = case
+    order = np.random.default_rng(1).permutation(len(reads))
+
+    def run(idx):
+        h = al.map_batch([reads[i] for i in idx])
+        per = h.per_read()
+        for k, i in enumerate(idx):
+            _compare_hits(h, per, k, traces[i][0])
+        return True
+    assert run(order)
+    with Pool(3) as pool:
+        assert all(pool.map(run, [order[:20], order[20:35], order[35:]]))
+
+
+def test_count_modes_equal_python_best_hit(case):
+    from monica_b200 import aligner as mine
+    al, oidx, reads, traces = case
+    hits = al.map_batch(reads)
+    names = al.seq_names
+    for mode in ("basic", "query_length", "matching", None):
+        counts, ncls, rcls, rbest = al.count(hits, 60, mode)
+        want = np.zeros(al.n_seq, dtype=np.int64)
+        cls = []
+        for i, r in enumerate(reads):
+            kept = [(h["rid"], h["nm"], h["mlen"]) for h in traces[i][0] if h["is_primary"] and h["mapq"] >= 60]
+            if not kept:
+                cls.append(0); continue
+            best = kept[0] if len(kept) == 1 else mine.best_hit(kept)
+            if not best:
+                cls.append(2); continue
+            cls.append(1)
+            want[best[0]] += {"basic": 1, "query_length": len(r), "matching": best[2]}.get(mode, 0)
+        assert np.array_equal(counts, want), mode
+        assert rcls.tolist() == cls
+        assert ncls.tolist() == [cls.count(1), cls.count(0), cls.count(2)]
+
+
+def test_index_save_load_roundtrip(case, tmp_path):
+    from monica_b200.mappy_shim import Aligner
+    from monica_b200 import synth
+    al, oidx, reads, traces = case
+    names, seqs = al.seq_names, None
+    fa = str(tmp_path / "database1.fna.gz")
+    g = np.load(os.path.join(GOLDEN, "small_case.npz"), allow_pickle=False)
+    gseqs = [g["genome_cat"][g["genome_off"][i]:g["genome_off"][i + 1]] for i in range(len(names))]
+    synth.write_fasta_gz(fa, g["names"].tolist(), gseqs)
+    mmi = str(tmp_path / "index1.mmi")
+    a1 = Aligner(fn_idx_in=fa, preset="map-ont", best_n=15, fn_idx_out=mmi)
+    assert a1 and os.path.getsize(mmi) > 0
+    a2 = Aligner(fn_idx_in=mmi)
+    assert a2 and a2.seq_names == a1.seq_names and a2.mid_occ == a1.mid_occ == int(g["mid_occ"])
+    h1 = a1.map_batch(cat=g["read_cat"], off=g["read_off"])
+    h2 = a2.map_batch(cat=g["read_cat"], off=g["read_off"])
+    for f in CMP_FIELDS:
+        assert np.array_equal(getattr(h1, f), getattr(h2, f))
+        assert np.array_equal(getattr(h1, f), g["hits"][:, g["hit_fields"].tolist().index(f)])
+    assert not Aligner(fn_idx_in=str(tmp_path / "missing.mmi"))                 # falsy, like mappy
+    bad = tmp_path / "bad.mmi"; bad.write_bytes(b"MMI\x02" + b"\x00" * 7)
+    assert not Aligner(fn_idx_in=str(bad))
+
+
+@pytest.mark.parametrize("key", ["mode=basic,two_indexes=False", "mode=query_length,two_indexes=True", "mode=matching,two_indexes=True", "mode=None,two_indexes=False"])
+def test_aligner_end_to_end_equals_reference_golden(small_case, key):
+    """monica_b200.aligner on the GPU == the UNMODIFIED reference aligner.py over the oracle (tests/golden/ref_aligner.json):
+    same alignment dict, same routed FASTQ bytes, inputs consumed, hits pickles removed."""
+    sys.path.insert(0, GOLDEN)
+    import make_golden
+    from monica_b200 import aligner as mine
+    names, seqs, reads = small_case
+    want = json.load(open(os.path.join(GOLDEN, "ref_aligner.json")))[key]
+    mode = key.split(",")[0].split("=")[1]
+    mode = None if mode == "None" else mode
+    two = key.endswith("True")
+    wd = tempfile.mkdtemp(prefix="gpu_e2e_")
+    try:
+        got = make_golden.run_aligner(mine, wd, names, seqs, reads, mode, two, ["Species_1"] if two else [],
+                                      {"indexer": {"genomes_path": os.path.join(wd, "markers")}})
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)
+    assert json.loads(json.dumps(got)) == want
+
+
+def test_larger_random_batch_bit_exact(oracle, lib):
+    """400 reads (2 kb - 30 kb, 10-15 % error, both strands, junk) against 4 genomes incl. a strain copy."""
+    from monica_b200 import synth
+    from monica_b200.mappy_shim import Aligner
+    names, seqs = synth.make_genomes(31, 4, 150000, strain_frac=0.25)
+    r1, _ = synth.simulate_reads(32, seqs, 250, 5000, 0.10, junk_frac=0.03)
+    r2, _ = synth.simulate_reads(33, seqs, 150, 9000, 0.15, sigma=0.8)
+    reads = r1 + r2
+    al = Aligner(names=names, seqs=seqs, device=0)
+    oidx = oracle.Index(names, seqs)
+    cat, off = synth.concat_reads(reads)
+    want, _ = oidx.map_batch(cat, off, n_threads=os.cpu_count() or 4)
+    hits = al.map_batch(cat=cat, off=off)
+    per = hits.per_read()
+    for i in range(len(reads)):
+        _compare_hits(hits, per, i, want[i])
+
+
+def test_round_trip_properties_at_scale(lib):
+    """Size-independent properties on a bench-shaped batch (20k reads): every CIGAR consumes exactly its query / reference
+    interval, NM = blen - mlen, mapped reads land on their source contig, counts sum to the mapped reads' bases, and a
+    second run of the same batch is identical."""
+    from monica_b200 import synth
+    from monica_b200.mappy_shim import Aligner
+    names, seqs = synth.make_genomes(41, 4, 1_000_000, strain_frac=0.0)
+    cat, off = synth.simulate_reads_bulk(42, seqs, 20000, 8000, 0.10)
+    al = Aligner(names=names, seqs=seqs, device=0)
+    hits = al.map_batch(cat=cat, off=off)
+    assert hits.n > 0.98 * (len(off) - 1)
+    ops = hits.cigar_pool & np.uint32(0xf)
+    lens = (hits.cigar_pool >> np.uint32(4)).astype(np.int64)
+    owner = np.repeat(np.arange(hits.n), hits.n_cigar)
+    qlen = np.bincount(owner, weights=lens * np.isin(ops, (0, 1)), minlength=hits.n).astype(np.int64)
+    tlen = np.bincount(owner, weights=lens * np.isin(ops, (0, 2)), minlength=hits.n).astype(np.int64)
+    assert np.array_equal(qlen, (hits.qe - hits.qs).astype(np.int64))
+    assert np.array_equal(tlen, (hits.re - hits.rs).astype(np.int64))
+    assert np.array_equal(hits.nm, hits.blen - hits.mlen)
+    assert np.all((hits.mapq >= 0) & (hits.mapq <= 60)) and np.all(hits.mlen <= hits.blen)
+    rl = np.diff(off)
+    assert np.all(hits.qe <= rl[hits.read_idx]) and np.all(hits.qs >= 0)
+    counts, ncls, rcls, rbest = al.count(hits, 60, "query_length")
+    assert counts.sum() == rl[rcls == 1].sum()
+    assert ncls.sum() == len(rl) and ncls[0] > 0.97 * len(rl)
+    again = al.map_batch(cat=cat, off=off)
+    for f in CMP_FIELDS:
+        assert np.array_equal(getattr(hits, f), getattr(again, f)), f
+    assert np.array_equal(hits.cigar_pool, again.cigar_pool)

@@ -1,0 +1,297 @@
+"""CPU tests of the oracle (oracle/): known-answer checks against independent Python restatements of the published
+definitions, internal consistency, and the committed golden vectors.
+
+The reference's own tests hold no vectors for this path, and mappy is not installable here, so these
+pin the oracle against (a) definitions that can be re-derived by hand (Wang hash, window minimizers, two-piece affine
+global alignment score) and (b) its own previous outputs (tests/golden/, regression).
+"""
+import os
+
+import numpy as np
+import pytest
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+M30 = (1 << 30) - 1
+
+
+def py_hash64(key, mask=M30):
+    key = (~key + (key << 21)) & mask
+    key = key ^ key >> 24
+    key = ((key + (key << 3)) + (key << 8)) & mask
+    key = key ^ key >> 14
+    key = ((key + (key << 2)) + (key << 4)) & mask
+    key = key ^ key >> 28
+    key = (key + (key << 31)) & mask
+    return key
+
+
+def test_hash64_known_answers(oracle):
+    # hand-evaluated: hash64(0) with a 30-bit mask
+    assert py_hash64(0) == oracle.hash64(0, M30)
+    rng = np.random.default_rng(0)
+    keys = rng.integers(0, 1 << 30, size=2000)
+    got = [oracle.hash64(int(k), M30) for k in keys]
+    assert got == [py_hash64(int(k)) for k in keys]
+    # the hash is a bijection on 30-bit keys: no collisions in a sample
+    assert len(set(got)) == len(set(int(k) for k in keys))
+
+
+def brute_minimizers(seq: bytes, w=10, k=15):
+    code = {65: 0, 67: 1, 71: 2, 84: 3}
+    c = [code[b] for b in seq]
+    km = []
+    for i in range(k - 1, len(c)):
+        f = r = 0
+        for j in range(k):
+            f = f << 2 | c[i - k + 1 + j]
+            r = r << 2 | (3 - c[i - j])
+        z = 0 if f < r else 1
+        km.append((py_hash64(r if z else f), i, z))
+    out = set()
+    for s in range(0, len(km) - w + 1):
+        win = km[s:s + w]
+        m = min(x[0] for x in win)
+        out.update(x for x in win if x[0] == m)
+    return out
+
+
+def test_sketch_equals_window_minimum_definition(oracle):
+    rng = np.random.default_rng(5)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    for t in range(60):
+        n = int(rng.integers(30, 500))
+        seq = acgt[rng.integers(0, 4, n)]
+        got = oracle.sketch(seq)
+        G = {(int(x) >> 8, (int(y) & 0xffffffff) >> 1, int(y) & 1) for x, y in got}
+        assert len(G) == len(got)
+        assert all(int(x) & 0xff == 15 for x, _ in got)
+        assert G == brute_minimizers(seq.tobytes())
+        pos = [(int(y) & 0xffffffff) >> 1 for _, y in got]
+        assert pos == sorted(pos)
+
+
+def test_sketch_ties_first_window_quirk(oracle):
+    """Low-complexity input: every emitted record is a true window minimum; mm_sketch may drop one tied record of the
+    very first window (old minimum replaced while l == w+k-1), never more."""
+    rng = np.random.default_rng(6)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    for t in range(40):
+        n = int(rng.integers(60, 400))
+        unit = acgt[rng.integers(0, 4, int(rng.integers(2, 9)))]
+        seq = np.tile(unit, n // len(unit) + 1)[:n]
+        got = oracle.sketch(seq)
+        G = {(int(x) >> 8, (int(y) & 0xffffffff) >> 1, int(y) & 1) for x, y in got}
+        B = brute_minimizers(seq.tobytes())
+        assert G <= B
+        missing = B - G
+        assert len(missing) <= 1
+        assert all(p < 15 + 10 for _, p, _ in missing)
+
+
+def test_sketch_edge_inputs(oracle):
+    assert len(oracle.sketch(b"")) == 0
+    assert len(oracle.sketch(b"ACGTACGTAC")) == 0           # shorter than k
+    assert len(oracle.sketch(b"N" * 100)) == 0
+    s = b"ACGTTGCAAGCTTGACCTGAAGTCCATGCAAGT"
+    a, b = oracle.sketch(s), oracle.sketch(s.lower())
+    assert np.array_equal(a, b)                              # case-insensitive
+    # an N resets the k-mer run: no minimizer may span it
+    seq = bytearray(np.frombuffer(b"ACGT", dtype=np.uint8)[np.random.default_rng(1).integers(0, 4, 300)].tobytes())
+    seq[150] = ord("N")
+    for x, y in oracle.sketch(bytes(seq)):
+        p = (int(y) & 0xffffffff) >> 1
+        assert not (p - 14 <= 150 <= p)
+
+
+def py_global_2piece(q, t, a=2, b=4, o1=4, e1=2, o2=24, e2=1, amb=1):
+    """Gotoh with two affine pieces; global alignment score (plain O(nm) Python)."""
+    NEG = -10 ** 9
+    n, m = len(t), len(q)
+
+    def gap(l):
+        return -min(o1 + l * e1, o2 + l * e2)
+    H = [[NEG] * (m + 1) for _ in range(n + 1)]
+    E1 = [[NEG] * (m + 1) for _ in range(n + 1)]
+    E2 = [[NEG] * (m + 1) for _ in range(n + 1)]
+    F1 = [[NEG] * (m + 1) for _ in range(n + 1)]
+    F2 = [[NEG] * (m + 1) for _ in range(n + 1)]
+    H[0][0] = 0
+    for i in range(1, n + 1):
+        H[i][0] = gap(i)
+    for j in range(1, m + 1):
+        H[0][j] = gap(j)
+    for i in range(1, n + 1):
+        for j in range(1, m + 1):
+            E1[i][j] = max(E1[i - 1][j] - e1, H[i - 1][j] - o1 - e1)
+            E2[i][j] = max(E2[i - 1][j] - e2, H[i - 1][j] - o2 - e2)
+            F1[i][j] = max(F1[i][j - 1] - e1, H[i][j - 1] - o1 - e1)
+            F2[i][j] = max(F2[i][j - 1] - e2, H[i][j - 1] - o2 - e2)
+            s = -amb if (t[i - 1] > 3 or q[j - 1] > 3) else (a if t[i - 1] == q[j - 1] else -b)
+            H[i][j] = max(H[i - 1][j - 1] + s, E1[i][j], E2[i][j], F1[i][j], F2[i][j])
+    return H[n][m]
+
+
+def cigar_score(cig, q, t, a=2, b=4, o1=4, e1=2, o2=24, e2=1, amb=1):
+    i = j = s = 0
+    for c in cig:
+        op, l = int(c) & 0xf, int(c) >> 4
+        if op == 0:
+            for k in range(l):
+                s += -amb if (t[i + k] > 3 or q[j + k] > 3) else (a if t[i + k] == q[j + k] else -b)
+            i += l; j += l
+        elif op == 1:
+            s -= min(o1 + l * e1, o2 + l * e2); j += l
+        else:
+            s -= min(o1 + l * e1, o2 + l * e2); i += l
+    return s, i, j
+
+
+def test_extd2_global_score_matches_definition(oracle):
+    rng = np.random.default_rng(3)
+    from monica_b200 import synth
+    for trial in range(25):
+        n = int(rng.integers(5, 90))
+        t = rng.integers(0, 4, n).astype(np.uint8)
+        # query = mutated copy, sometimes with a long gap (exercises the second affine piece)
+        q = list(t)
+        for _ in range(int(rng.integers(0, 8))):
+            p = int(rng.integers(0, max(1, len(q))))
+            r = rng.random()
+            if r < 0.4 and q:
+                q[p % len(q)] = int(rng.integers(0, 4))
+            elif r < 0.7:
+                q[p:p] = list(rng.integers(0, 4, int(rng.integers(1, 40))))
+            elif q:
+                del q[p:p + int(rng.integers(1, 30))]
+        if not q:
+            q = [0]
+        if trial % 7 == 0:
+            q[0] = 4                                         # an N
+        q = np.array(q, dtype=np.uint8)
+        for flag in (0x08, 0x08 | 0x02):                     # approx-max global; + right-aligned gaps
+            ez = oracle.ksw_extd2(q, t, w=-1, zdrop=-1, end_bonus=-1, flag=flag)
+            want = py_global_2piece(list(q), list(t))
+            assert ez["score"] == want, (trial, flag, len(q), len(t))
+            s, ti, qi = cigar_score(ez["cigar"], list(q), list(t))
+            assert (ti, qi) == (len(t), len(q))
+            assert s == want
+        # exact-max mode reports the same end score and a max >= score
+        ez2 = oracle.ksw_extd2(q, t, w=-1, zdrop=-1, end_bonus=-1, flag=0)
+        assert ez2["score"] == want and ez2["max"] >= max(0, want)
+
+
+def test_extd2_extension_semantics(oracle):
+    """Extension mode on a perfect match followed by junk: max sits at the end of the matching prefix; the backtrack starts
+    there (no reach_end); with a generous end bonus on a full match it reaches the query end."""
+    rng = np.random.default_rng(4)
+    core = rng.integers(0, 4, 120).astype(np.uint8)
+    q = np.concatenate([core, rng.integers(0, 4, 80).astype(np.uint8)])
+    t = np.concatenate([core, rng.integers(0, 4, 80).astype(np.uint8)])
+    ez = oracle.ksw_extd2(q, t, w=751, zdrop=400, end_bonus=-1, flag=0x40)
+    assert ez["max"] >= 240 and ez["max_q"] >= 119 and ez["max_t"] >= 119
+    assert not ez["reach_end"]
+    s, ti, qi = cigar_score(ez["cigar"], list(q), list(t))
+    assert (ti, qi) == (ez["max_t"] + 1, ez["max_q"] + 1) and s == ez["max"]
+    ez = oracle.ksw_extd2(core, core, w=751, zdrop=400, end_bonus=5, flag=0x40)
+    assert ez["reach_end"] and ez["mqe"] == 240 and ez["mqe_t"] == 119
+    # Z-drop: a long run of mismatches after the match stops the extension early
+    q2 = np.concatenate([core, (core[::-1] ^ 1)[:0], np.full(400, 0, np.uint8)])
+    t2 = np.concatenate([core, np.full(400, 3, np.uint8)])
+    ez = oracle.ksw_extd2(q2, t2, w=751, zdrop=100, end_bonus=-1, flag=0x40)
+    assert ez["zdropped"] and ez["max"] == 240
+
+
+def test_radix_sorts(oracle):
+    rng = np.random.default_rng(7)
+    for n in (0, 1, 2, 63, 64, 65, 200, 5000):
+        k = rng.integers(0, 1 << 62, size=n, dtype=np.uint64)
+        assert np.array_equal(oracle.radix_sort_64(k), np.sort(k))
+        a = np.stack([k, np.arange(n, dtype=np.uint64)], axis=1)
+        s = oracle.radix_sort_128x(a)
+        assert np.array_equal(s[:, 0], np.sort(k))
+        assert sorted(s[:, 1].tolist()) == list(range(n))
+    # ties: still sorted and a permutation, but NOT necessarily stable for n > 64 (upstream's MSD radix is unstable)
+    k = rng.integers(0, 8, size=500, dtype=np.uint64) << np.uint64(40)
+    a = np.stack([k, np.arange(500, dtype=np.uint64)], axis=1)
+    s = oracle.radix_sort_128x(a)
+    assert np.array_equal(s[:, 0], np.sort(k)) and sorted(s[:, 1].tolist()) == list(range(500))
+    small = np.stack([np.array([3, 1, 3, 1, 2], np.uint64), np.arange(5, dtype=np.uint64)], axis=1)
+    assert oracle.radix_sort_128x(small)[:, 1].tolist() == [1, 3, 4, 0, 2]   # <= 64 elements: insertion sort, stable
+
+
+def test_index_and_mid_occ(oracle):
+    from monica_b200 import synth
+    names, seqs = synth.make_genomes(1, 1, 50000)
+    idx = oracle.Index(names, seqs)
+    assert idx.mid_occ == 2                                  # all minimizers unique -> quantile 1, +1
+    names, seqs = synth.make_genomes(1, 3, 50000, strain_frac=0.34)
+    idx = oracle.Index(names, seqs)
+    assert idx.mid_occ == 3
+    # every reference minimizer is found at its own position
+    m = oracle.sketch(seqs[1], rid=1)
+    for x, y in m[::97]:
+        assert int(y) in idx.get(int(x) >> 8).tolist()
+
+
+def test_reads_map_back_to_origin(oracle):
+    from monica_b200 import synth
+    names, seqs = synth.make_genomes(21, 2, 80000, strain_frac=0.0)
+    idx = oracle.Index(names, seqs)
+    reads, truth = synth.simulate_reads(22, seqs, 25, 3000, 0.10)
+    for r, (c, st, en, strand) in zip(reads, truth):
+        hits, stats = idx.map(r)
+        assert hits, "read did not map"
+        h = hits[0]
+        assert h["rid"] == c and h["rev"] == strand and h["mapq"] == 60 and h["is_primary"]
+        assert abs(h["rs"] - st) < 60 and abs(h["re"] - en) < 60
+        assert 0.80 < h["mlen"] / h["blen"] < 0.97
+        assert h["nm"] == h["blen"] - h["mlen"]
+        # the CIGAR consumes exactly the reported intervals
+        ql = sum(int(c_) >> 4 for c_ in h["cigar"] if int(c_) & 0xf in (0, 1))
+        tl = sum(int(c_) >> 4 for c_ in h["cigar"] if int(c_) & 0xf in (0, 2))
+        assert ql == h["qe"] - h["qs"] and tl == h["re"] - h["rs"]
+
+
+def test_empty_and_unmappable(oracle, small_case):
+    names, seqs, reads = small_case
+    idx = oracle.Index(names, seqs)
+    assert idx.map(b"")[0] == []
+    assert idx.map(b"ACGT")[0] == []
+    rng = np.random.default_rng(9)
+    junk = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 4000)]
+    assert idx.map(junk)[0] == []
+
+
+def test_batch_threads_equal_serial(oracle, small_case):
+    from monica_b200 import synth
+    names, seqs, reads = small_case
+    idx = oracle.Index(names, seqs)
+    cat, off = synth.concat_reads(reads)
+    a, _ = idx.map_batch(cat, off, n_threads=1)
+    b, _ = idx.map_batch(cat, off, n_threads=4)
+    assert len(a) == len(b) == len(reads)
+    for x, y in zip(a, b):
+        assert [{k: v for k, v in h.items() if k != "cigar"} for h in x] == [{k: v for k, v in h.items() if k != "cigar"} for h in y]
+
+
+def test_golden_vectors(oracle):
+    """Regression: the oracle reproduces the committed vectors (tests/golden/make_golden.py wrote them from this oracle)."""
+    path = os.path.join(GOLDEN, "small_case.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden vectors not generated")
+    g = np.load(path, allow_pickle=False)
+    names = [n for n in g["names"].tolist()]
+    seqs = [g["genome_cat"][g["genome_off"][i]:g["genome_off"][i + 1]] for i in range(len(names))]
+    idx = oracle.Index(names, seqs)
+    assert idx.mid_occ == int(g["mid_occ"])
+    hit_off = g["hit_off"]
+    fields = [f for f in g["hit_fields"].tolist()]
+    for i in range(len(g["read_off"]) - 1):
+        r = g["read_cat"][g["read_off"][i]:g["read_off"][i + 1]]
+        hits, _ = idx.map(r)
+        want = g["hits"][hit_off[i]:hit_off[i + 1]]
+        assert len(hits) == len(want)
+        for h, w in zip(hits, want):
+            assert [h[f] for f in fields] == w.tolist()
+    m = oracle.sketch(g["read_cat"][g["read_off"][3]:g["read_off"][4]])
+    assert np.array_equal(m, g["sketch_read3"])
