@@ -327,7 +327,7 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     sketch_bytes = (last["n_bases"] + 16 * last["n_mini"]) * 2   # count + write passes, 1 B/base nt4 in, 16 B/minimizer out
     seed_bytes = 32 * last["n_mini"] + 24 * last["n_anchor"] + 32 * last["n_anchor"]
-    stage_ms = {k: float(np.mean([s[k] for s in stats])) for k in ("ms_sketch", "ms_seed", "ms_chain", "ms_glue", "ms_dp", "ms_post", "ms_total", "ms_kdp")}
+    stage_ms = {k: float(np.mean([s[k] for s in stats])) for k in ("ms_sketch", "ms_seed", "ms_chain", "ms_glue", "ms_dp", "ms_post", "ms_total", "ms_kdp", "ms_kdp_fast", "ms_kdp_exact", "ms_d2h")}
     roofline = {
         "kernel": "k_dp (two-piece affine banded DP + traceback, ksw_extd2 equivalent)", "bound": "int", "achieved": gcups, "peak": peak_gcups, "unit": "GCUPS",
         "frac": gcups / peak_gcups if peak_gcups else None, "traffic": None,
@@ -367,7 +367,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu,
             "stage_ms": stage_ms,
-            "work_per_step": {k: last[k] for k in ("n_reads", "n_bases", "n_mini", "n_anchor", "n_regs", "n_dp_tasks", "n_dp_pass2", "dp_cells", "n_hits", "n_rounds")},
+            "work_per_step": {k: last[k] for k in ("n_reads", "n_bases", "n_mini", "n_anchor", "n_regs", "n_dp_tasks", "n_dp_pass2", "dp_cells", "n_hits", "n_rounds", "n_fast_tasks", "n_exact_tasks")},
             "read_classes": {"mapped": int(ncls[0]), "unmapped": int(ncls[1]), "ambiguous": int(ncls[2])},
         }
         print(json.dumps(out))

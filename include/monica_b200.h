@@ -60,7 +60,10 @@ typedef struct {
 	float   ms_sketch, ms_seed, ms_sort, ms_chain, ms_glue, ms_dp, ms_post, ms_total, ms_h2d, ms_d2h;
 	int64_t n_launches;       /* kernels launched for this batch */
 	float   ms_kdp;           /* CUDA-event time of the k_dp launches alone (the roofline kernel) */
-	int32_t n_kdp;            /* number of k_dp launches */
+	int32_t n_kdp;            /* number of DP kernel launches */
+	float   ms_kdp_fast;      /* ... of which the register-resident fast path (k_dp_fast) */
+	float   ms_kdp_exact;     /* ... and the exact ksw_extd2 block emulation (k_dp) */
+	int64_t n_fast_tasks, n_exact_tasks;
 } mb_stats_t;
 
 const char *mb_last_error(void);

@@ -18,6 +18,7 @@
 #include "glue.cuh"
 #include "align.cuh"
 #include "align2.cuh"
+#include "dp_fast.cuh"
 
 thread_local std::string g_mb_err;
 
@@ -488,48 +489,99 @@ static __host__ __device__ inline DpGeom dp_geom(int qlen, int tlen, int w)
 }
 
 #define DP_SMALL_P (1u << 20)
+#define DP_NCLS (DPF_NCLASS + 2)   // fast classes, then exact-emulation small / big scratch classes
 
-// classify tasks into small / big scratch classes; record maxima
+// classify tasks: fast path by columns-per-lane class, the rest into small / big scratch classes; record maxima
 __global__ void k_dp_classify(const DpTask *__restrict__ tasks, const int32_t *__restrict__ ids, int64_t n, int use_ids,
-                              int32_t *__restrict__ small_list, int32_t *__restrict__ big_list, int32_t *__restrict__ ctr /* n_small, n_big */,
-                              unsigned long long *__restrict__ maxima /* small: p, ws, h ; big: p, ws, h */)
+                              int32_t *__restrict__ lists /* DP_NCLS x n */, int32_t *__restrict__ ctr /* DP_NCLS */,
+                              unsigned long long *__restrict__ maxima /* DP_NCLS x 3 */)
 {
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	int id = use_ids ? ids[i] : (int)i;
 	const DpTask &t = tasks[id];
+	int cls = dpf_class(t.qlen, t.tlen, t.w, t.flag, t.skip);
+	if (cls >= 0) {
+		lists[(int64_t)cls * n + atomicAdd(&ctr[cls], 1)] = id;
+		atomicMax(&maxima[cls * 3 + 0], (unsigned long long)t.qlen);
+		return;
+	}
 	DpGeom g = dp_geom(t.qlen, t.tlen, t.w);
 	if (t.skip) g.p_bytes = g.ws_bytes = g.h_ints = 0;
-	int big = g.p_bytes > DP_SMALL_P;
-	if (big) big_list[atomicAdd(&ctr[1], 1)] = id; else small_list[atomicAdd(&ctr[0], 1)] = id;
-	atomicMax(&maxima[big * 3 + 0], (unsigned long long)g.p_bytes);
-	atomicMax(&maxima[big * 3 + 1], (unsigned long long)g.ws_bytes);
-	atomicMax(&maxima[big * 3 + 2], (unsigned long long)g.h_ints);
+	cls = DPF_NCLASS + (g.p_bytes > DP_SMALL_P ? 1 : 0);
+	lists[(int64_t)cls * n + atomicAdd(&ctr[cls], 1)] = id;
+	atomicMax(&maxima[cls * 3 + 0], (unsigned long long)g.p_bytes);
+	atomicMax(&maxima[cls * 3 + 1], (unsigned long long)g.ws_bytes);
+	atomicMax(&maxima[cls * 3 + 2], (unsigned long long)g.h_ints);
 }
 
 struct DpRunner {
 	ThreadCtx &c; cudaStream_t st; int64_t *nl;
-	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evs; // one pair per k_dp launch, read back after the batch
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evs; // one pair per DP launch, read back after the batch
+	std::vector<int> ev_fast; int64_t n_fast = 0, n_exact = 0;
 	DpRunner(ThreadCtx &c_, int64_t *nl_) : c(c_), st(c_.st), nl(nl_) {}
 	~DpRunner() { for (auto &e : evs) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); } }
-	float total_ms() { float t = 0; for (auto &e : evs) { float ms = 0; if (cudaEventElapsedTime(&ms, e.first, e.second) == cudaSuccess) t += ms; } return t; }
-	// run k_dp over `n` tasks (ids[] if use_ids else 0..n-1)
+	float total_ms(int which = -1) { float t = 0; for (size_t i = 0; i < evs.size(); ++i) { if (which >= 0 && ev_fast[i] != which) continue; float ms = 0; if (cudaEventElapsedTime(&ms, evs[i].first, evs[i].second) == cudaSuccess) t += ms; } return t; }
+
+	template <int C>
+	void launch_fast(DpTask *tasks, const int32_t *list, const int32_t *d_cnt, int64_t cnt, int max_q, const uint8_t *codes, const uint32_t *S, const uint8_t *pool,
+	                 uint32_t *cigar_pool, const DpScoring &sc, unsigned long long *d_cells)
+	{
+		Arena &ar = c.ar;
+		constexpr int CW = (C + 3) / 4;
+		static int occ = 0; // resident CTAs per SM for this instantiation
+		if (occ == 0) {
+			CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_dp_fast<C>, DPF_WARPS * 32, 0));
+			if (occ < 1) occ = 1;
+		}
+		const size_t stride_words = ((size_t)32 * (size_t)(max_q + 31) * CW + 63) & ~(size_t)63;
+		int max_cta = c.num_sms * occ;
+		int64_t want = cdiv(cnt, DPF_WARPS);
+		int n_cta = (int)(want < max_cta ? want : max_cta);
+		uint32_t *p_scr = ar.get<uint32_t>((size_t)n_cta * DPF_WARPS * stride_words);
+		int32_t *wc = ar.get<int32_t>(1);
+		CK(cudaMemsetAsync(wc, 0, sizeof(int32_t), st));
+		cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+		cudaEventRecord(e0, st);
+		k_dp_fast<C><<<n_cta, DPF_WARPS * 32, 0, st>>>(tasks, list, d_cnt, wc, codes, S, pool, p_scr, stride_words, cigar_pool, sc, d_cells);
+		cudaEventRecord(e1, st);
+		evs.emplace_back(e0, e1); ev_fast.push_back(1); n_fast += cnt;
+		++*nl;
+	}
+
+	// run the DP kernels over `n` tasks (ids[] if use_ids else 0..n-1)
 	void run(DpTask *tasks, const int32_t *ids, int64_t n, bool use_ids, const uint8_t *codes, const uint32_t *S, const uint8_t *pool,
 	         uint32_t *cigar_pool, const DpScoring &sc, unsigned long long *d_cells)
 	{
 		if (n <= 0) return;
 		Arena &ar = c.ar;
-		int32_t *small_list = ar.get<int32_t>(n), *big_list = ar.get<int32_t>(n);
-		int32_t *ctr = ar.get<int32_t>(4);
-		unsigned long long *maxima = ar.get<unsigned long long>(6);
-		CK(cudaMemsetAsync(ctr, 0, 4 * sizeof(int32_t), st));
-		CK(cudaMemsetAsync(maxima, 0, 6 * sizeof(unsigned long long), st));
-		k_dp_classify<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(tasks, ids, n, use_ids ? 1 : 0, small_list, big_list, ctr, maxima); ++*nl;
-		int32_t h_ctr[4]; unsigned long long h_max[6];
+		int32_t *lists = ar.get<int32_t>((size_t)DP_NCLS * n);
+		int32_t *ctr = ar.get<int32_t>(DP_NCLS);
+		unsigned long long *maxima = ar.get<unsigned long long>(DP_NCLS * 3);
+		CK(cudaMemsetAsync(ctr, 0, DP_NCLS * sizeof(int32_t), st));
+		CK(cudaMemsetAsync(maxima, 0, DP_NCLS * 3 * sizeof(unsigned long long), st));
+		k_dp_classify<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(tasks, ids, n, use_ids ? 1 : 0, lists, ctr, maxima); ++*nl;
+		int32_t h_ctr[DP_NCLS]; unsigned long long h_max[DP_NCLS * 3];
 		CK(cudaMemcpyAsync(h_ctr, ctr, sizeof(h_ctr), cudaMemcpyDeviceToHost, st));
 		CK(cudaMemcpyAsync(h_max, maxima, sizeof(h_max), cudaMemcpyDeviceToHost, st));
 		CK(cudaStreamSynchronize(st));
-		for (int cls = 0; cls < 2; ++cls) {
+		for (int k = 0; k < DPF_NCLASS; ++k) {
+			const int64_t cnt = h_ctr[k];
+			if (cnt == 0) continue;
+			const int32_t *list = lists + (int64_t)k * n;
+			const int mq = (int)h_max[k * 3];
+			switch (DPF_C[k]) {
+			case 4:  launch_fast<4>(tasks, list, ctr + k, cnt, mq, codes, S, pool, cigar_pool, sc, d_cells); break;
+			case 6:  launch_fast<6>(tasks, list, ctr + k, cnt, mq, codes, S, pool, cigar_pool, sc, d_cells); break;
+			case 8:  launch_fast<8>(tasks, list, ctr + k, cnt, mq, codes, S, pool, cigar_pool, sc, d_cells); break;
+			case 10: launch_fast<10>(tasks, list, ctr + k, cnt, mq, codes, S, pool, cigar_pool, sc, d_cells); break;
+			case 12: launch_fast<12>(tasks, list, ctr + k, cnt, mq, codes, S, pool, cigar_pool, sc, d_cells); break;
+			case 16: launch_fast<16>(tasks, list, ctr + k, cnt, mq, codes, S, pool, cigar_pool, sc, d_cells); break;
+			default: launch_fast<24>(tasks, list, ctr + k, cnt, mq, codes, S, pool, cigar_pool, sc, d_cells); break;
+			}
+		}
+		for (int b = 0; b < 2; ++b) {
+			const int cls = DPF_NCLASS + b;
 			int64_t cnt = h_ctr[cls];
 			if (cnt == 0) continue;
 			size_t p_stride = ((size_t)h_max[cls * 3 + 0] + 255) & ~(size_t)255;
@@ -552,10 +604,10 @@ struct DpRunner {
 			CK(cudaMemsetAsync(wc, 0, sizeof(int32_t), st));
 			cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
 			cudaEventRecord(e0, st);
-			k_dp<<<n_cta, DP_WARPS * 32, DP_WARPS * DP_SMEM_PER_WARP, st>>>(tasks, cls ? big_list : small_list, ctr + cls, wc, codes, S, pool,
+			k_dp<<<n_cta, DP_WARPS * 32, DP_WARPS * DP_SMEM_PER_WARP, st>>>(tasks, lists + (int64_t)cls * n, ctr + cls, wc, codes, S, pool,
 				p_scr, p_stride, g_ws, g_stride, h_scr, h_stride, cigar_pool, sc, d_cells);
 			cudaEventRecord(e1, st);
-			evs.emplace_back(e0, e1);
+			evs.emplace_back(e0, e1); ev_fast.push_back(0); n_exact += cnt;
 			++*nl;
 		}
 	}
@@ -744,6 +796,7 @@ static mb_hits *map_device(mb_index *ix, const mb_opt_t &opt_in, ThreadCtx &c, c
 	S.dp_cells = (int64_t)h_cells[1];
 	S.n_launches = nl;
 	S.ms_kdp = runner.total_ms(); S.n_kdp = (int32_t)runner.evs.size();
+	S.ms_kdp_fast = runner.total_ms(1); S.ms_kdp_exact = runner.total_ms(0); S.n_fast_tasks = runner.n_fast; S.n_exact_tasks = runner.n_exact;
 	S.ms_total = tall.stop();
 	if (stats) { float h2d = stats->ms_h2d; *stats = S; stats->ms_h2d = h2d; }
 	return H.release();
