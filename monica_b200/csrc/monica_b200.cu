@@ -493,6 +493,7 @@ static __host__ __device__ inline DpGeom dp_geom(int qlen, int tlen, int w)
 
 // classify tasks: fast path by columns-per-lane class, the rest into small / big scratch classes; record maxima
 __global__ void k_dp_classify(const DpTask *__restrict__ tasks, const int32_t *__restrict__ ids, int64_t n, int use_ids,
+                              const uint8_t *__restrict__ codes, const uint32_t *__restrict__ S, const uint8_t *__restrict__ pool, int fast_ok,
                               int32_t *__restrict__ lists /* DP_NCLS x n */, int32_t *__restrict__ ctr /* DP_NCLS */,
                               unsigned long long *__restrict__ maxima /* DP_NCLS x 3 */)
 {
@@ -500,7 +501,8 @@ __global__ void k_dp_classify(const DpTask *__restrict__ tasks, const int32_t *_
 	if (i >= n) return;
 	int id = use_ids ? ids[i] : (int)i;
 	const DpTask &t = tasks[id];
-	int cls = dpf_class(t.qlen, t.tlen, t.w, t.flag, t.skip);
+	int cls = fast_ok ? dpf_class(t.qlen, t.tlen, t.w, t.flag, t.skip) : -1;
+	if (cls >= 0 && dpf_task_ambig(t, codes, S, pool)) cls = -1; // ambiguous bases: exact kernel
 	if (cls >= 0) {
 		lists[(int64_t)cls * n + atomicAdd(&ctr[cls], 1)] = id;
 		atomicMax(&maxima[cls * 3 + 0], (unsigned long long)t.qlen);
@@ -528,7 +530,7 @@ struct DpRunner {
 	                 uint32_t *cigar_pool, const DpScoring &sc, unsigned long long *d_cells)
 	{
 		Arena &ar = c.ar;
-		constexpr int CW = (C + 3) / 4;
+		constexpr int CW = (C + 1) / 2;
 		static int occ = 0; // resident CTAs per SM for this instantiation
 		if (occ == 0) {
 			CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_dp_fast<C>, DPF_WARPS * 32, 0));
@@ -536,7 +538,7 @@ struct DpRunner {
 		}
 		const size_t stride_words = ((size_t)32 * (size_t)(max_q + 31) * CW + 63) & ~(size_t)63;
 		int max_cta = c.num_sms * occ;
-		int64_t want = cdiv(cnt, DPF_WARPS);
+		int64_t want = cdiv(cdiv(cnt, 2), DPF_WARPS); // two tasks per warp
 		int n_cta = (int)(want < max_cta ? want : max_cta);
 		uint32_t *p_scr = ar.get<uint32_t>((size_t)n_cta * DPF_WARPS * stride_words);
 		int32_t *wc = ar.get<int32_t>(1);
@@ -560,7 +562,7 @@ struct DpRunner {
 		unsigned long long *maxima = ar.get<unsigned long long>(DP_NCLS * 3);
 		CK(cudaMemsetAsync(ctr, 0, DP_NCLS * sizeof(int32_t), st));
 		CK(cudaMemsetAsync(maxima, 0, DP_NCLS * 3 * sizeof(unsigned long long), st));
-		k_dp_classify<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(tasks, ids, n, use_ids ? 1 : 0, lists, ctr, maxima); ++*nl;
+		k_dp_classify<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(tasks, ids, n, use_ids ? 1 : 0, codes, S, pool, dpf_scoring_ok(sc) ? 1 : 0, lists, ctr, maxima); ++*nl;
 		int32_t h_ctr[DP_NCLS]; unsigned long long h_max[DP_NCLS * 3];
 		CK(cudaMemcpyAsync(h_ctr, ctr, sizeof(h_ctr), cudaMemcpyDeviceToHost, st));
 		CK(cudaMemcpyAsync(h_max, maxima, sizeof(h_max), cudaMemcpyDeviceToHost, st));
@@ -572,11 +574,17 @@ struct DpRunner {
 			const int mq = (int)h_max[k * 3];
 			switch (DPF_C[k]) {
 			case 4:  launch_fast<4>(tasks, list, ctr + k, cnt, mq, codes, S, pool, cigar_pool, sc, d_cells); break;
+			case 5:  launch_fast<5>(tasks, list, ctr + k, cnt, mq, codes, S, pool, cigar_pool, sc, d_cells); break;
 			case 6:  launch_fast<6>(tasks, list, ctr + k, cnt, mq, codes, S, pool, cigar_pool, sc, d_cells); break;
+			case 7:  launch_fast<7>(tasks, list, ctr + k, cnt, mq, codes, S, pool, cigar_pool, sc, d_cells); break;
 			case 8:  launch_fast<8>(tasks, list, ctr + k, cnt, mq, codes, S, pool, cigar_pool, sc, d_cells); break;
+			case 9:  launch_fast<9>(tasks, list, ctr + k, cnt, mq, codes, S, pool, cigar_pool, sc, d_cells); break;
 			case 10: launch_fast<10>(tasks, list, ctr + k, cnt, mq, codes, S, pool, cigar_pool, sc, d_cells); break;
+			case 11: launch_fast<11>(tasks, list, ctr + k, cnt, mq, codes, S, pool, cigar_pool, sc, d_cells); break;
 			case 12: launch_fast<12>(tasks, list, ctr + k, cnt, mq, codes, S, pool, cigar_pool, sc, d_cells); break;
+			case 14: launch_fast<14>(tasks, list, ctr + k, cnt, mq, codes, S, pool, cigar_pool, sc, d_cells); break;
 			case 16: launch_fast<16>(tasks, list, ctr + k, cnt, mq, codes, S, pool, cigar_pool, sc, d_cells); break;
+			case 20: launch_fast<20>(tasks, list, ctr + k, cnt, mq, codes, S, pool, cigar_pool, sc, d_cells); break;
 			default: launch_fast<24>(tasks, list, ctr + k, cnt, mq, codes, S, pool, cigar_pool, sc, d_cells); break;
 			}
 		}

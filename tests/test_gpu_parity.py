@@ -190,6 +190,56 @@ def test_dp_random_and_band_limited(oracle, lib):
     _check_dp(tasks, cig, recs)
 
 
+def test_dp_fast_path_pairs(oracle, lib):
+    """First-pass gap fills (flag KSW_EZ_APPROX_MAX, band not limiting) go through the packed two-tasks-per-warp kernel:
+    every column class, ragged pairs (neighbouring tasks of different size share a warp), indel-rich, repeat-rich
+    (tie-breaking) and N-containing sequences (which must fall back to the exact kernel), an odd task count."""
+    from monica_b200 import _lib
+    rng = np.random.default_rng(77)
+    opt = _lib.default_opt()
+    recs = []
+
+    def mutate(t, err):
+        out = []
+        for b in t:
+            r = rng.random()
+            if r < err * 0.4:
+                out.append(int(rng.integers(0, 4)))
+            elif r < err * 0.7:
+                continue
+            elif r < err:
+                out.extend([int(b), int(rng.integers(0, 4))])
+            else:
+                out.append(int(b))
+        return np.array(out if out else [0], dtype=np.uint8)
+
+    tlens = [1, 2, 31, 33, 97, 128, 129, 160, 161, 200, 224, 225, 230, 256, 257, 288, 300, 320, 352, 353, 384, 400, 448, 449, 512, 600, 640, 641, 700, 768]
+    for rep in range(3):
+        for tl in tlens:
+            kind = rng.integers(0, 4)
+            if kind == 3:   # low-complexity: many ties
+                t = np.tile(rng.integers(0, 4, 3).astype(np.uint8), tl // 3 + 1)[:tl]
+            else:
+                t = rng.integers(0, 4, tl).astype(np.uint8)
+            q = mutate(t, (0.05, 0.12, 0.3, 0.15)[kind])
+            if rep == 2 and tl % 7 == 0 and len(q) > 9:
+                q[len(q) // 2] = 4
+            if rep == 1 and tl % 11 == 0:
+                t = t.copy(); t[tl // 3] = 4
+            if len(q) > 1000 or max(len(q), tl) > 752:
+                q = q[:750]
+            if max(len(q), tl) > 752:
+                continue
+            ez = oracle.ksw_extd2(q, t, w=751, zdrop=400, end_bonus=-1, flag=0x08)
+            recs.append(dict(qlen=len(q), tlen=tl, w=751, zdrop=400, end_bonus=-1, flag=0x08, q=q, t=t, score=ez["score"], max=ez["max"],
+                             max_q=ez["max_q"], max_t=ez["max_t"], mqe=ez["mqe"], mqe_t=ez["mqe_t"], zdropped=ez["zdropped"],
+                             reach_end=ez["reach_end"], n_cigar=len(ez["cigar"]), cigar=ez["cigar"]))
+    if len(recs) % 2 == 0:
+        recs.pop()
+    tasks, cig = _run_dp(lib, opt, recs)
+    _check_dp(tasks, cig, recs)
+
+
 def _compare_hits(hits, per, i, want):
     got = per[i]
     assert len(want) == len(got), f"read {i}: oracle {len(want)} hits, GPU {len(got)}"
