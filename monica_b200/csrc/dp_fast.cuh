@@ -51,6 +51,7 @@ static __host__ __device__ inline bool dpf_scoring_ok(const DpScoring &sc)
 	if (sc.sc_mch <= 0 || sc.sc_mis >= 0 || q < 0 || e <= 0 || q2 < 0 || e2 <= 0) return false;
 	if (8 * (sc.sc_mch + 2 * B) + 7 >= 128) return false;      // substitution bytes must stay below 128 (PRMT sign replicate)
 	if (sc.sc_mis + 2 * B <= 0 || sc.sc_N + 2 * B <= 0) return false; // z > 0
+	if (sc.sc_mis + 2 * B <= B - e || sc.sc_N + 2 * B <= B - e || sc.sc_mis + 2 * B <= B - e2 || sc.sc_N + 2 * B <= B - e2) return false; // z > D: K - z always borrows
 	if (q2 + e2 + sc.sc_mch + 2 * B > 2000) return false;
 	return true;
 }
@@ -110,7 +111,7 @@ k_dp_fast(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 	const uint32_t FL1 = X_INIT, FL2 = Y_INIT, FL3 = X2_INIT, FL4 = Y2_INIT;            // floors: opening a new gap
 	const uint32_t NFL1 = dpf_pack2(-(8 * (-q - e + B) + 3)), NFL2 = dpf_pack2(-(8 * (-q - e + B) + 2));
 	const uint32_t NFL3 = dpf_pack2(-(8 * (-q2 - e2 + B) + 1)), NFL4 = dpf_pack2(-(8 * (-q2 - e2 + B) + 0));
-	const uint32_t D1 = dpf_pack2(8 * (B - e)), D2 = dpf_pack2(8 * (B - e2));
+	const uint32_t K1 = 0x00010000u + dpf_pack2(8 * (B - e)), K2 = 0x00010000u + dpf_pack2(8 * (B - e2));
 	const uint32_t EIGHT = 0x00080008u;
 	const uint32_t MCHB = (uint32_t)(8 * (sc.sc_mch + 2 * B) + 4), MISB = (uint32_t)(8 * (sc.sc_mis + 2 * B) + 4), NB = (uint32_t)(8 * (sc.sc_N + 2 * B) + 4);
 	const uint32_t MIS4 = MISB * 0x01010101u, N4 = NB * 0x01010101u, MDIFF = MCHB - MISB;
@@ -142,20 +143,33 @@ k_dp_fast(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 		uint32_t XLo = 0, VLo = 0, X2Lo = 0;
 		const int n_steps = Qm + 31;
 		const bool lane_live = t0 < TLm;
-		// query bases are fetched one step ahead so the load latency hides behind a whole step of arithmetic
-		int qnA = 0, qnB = 0;
-		if (lane == 0) qnA = qvA.at(0), qnB = qvB.at(0);
-		for (int s = 0; s < n_steps; ++s) {
+		// Substitution tables of the query rows: every 32 steps the warp loads the next 32 rows (lane k -> row s+32+k, one
+		// coalesced access per task) and turns them into the PRMT tables LA|LB; each step lane 0 picks its row's tables by
+		// a broadcast shuffle and the tables then travel down the lanes with the systolic skew (shfl_up), like XL/VL/X2L.
+		auto row_tables = [&](int r, uint32_t &la, uint32_t &lb) {
+			const int a = r < QA ? qvA.at(r) : 0, b = r < QB ? qvB.at(r) : 0;
+			la = a < 4 ? MIS4 + (MDIFF << (a * 8)) : N4, lb = b < 4 ? MIS4 + (MDIFF << (b * 8)) : N4;
+		};
+		uint32_t LAc, LBc, LAn = 0, LBn = 0, LAo = 0, LBo = 0;
+		row_tables(lane, LAc, LBc);
+		const uint32_t VB0 = dpf_pack2(8 * (dpf_bnd(0, q, e, e2, long_thres, long_diff) + B)), VB1 = dpf_pack2(8 * (-e + B));
+		const uint32_t VB2 = dpf_pack2(8 * (long_diff + B)), VB3 = dpf_pack2(8 * (-e2 + B));
+		uint32_t *dst = P + (size_t)lane * CW;
+		for (int s = 0; s < n_steps; ++s, dst += 32 * CW) {
 			const int j = s - lane;
-			const int qbA = qnA, qbB = qnB;
-			if (j + 1 >= 0) {
-				qnA = j + 1 < QA ? qvA.at(j + 1) : 0;
-				qnB = j + 1 < QB ? qvB.at(j + 1) : 0;
+			if ((s & 31) == 0) {
+				if (s) LAc = LAn, LBc = LBn;
+				if (s + 32 < Qm) row_tables(s + 32 + lane, LAn, LBn);
 			}
+			const uint32_t LA0 = __shfl_sync(FULL, LAc, s & 31), LB0 = __shfl_sync(FULL, LBc, s & 31);
+			uint32_t LA = __shfl_up_sync(FULL, LAo, 1), LB = __shfl_up_sync(FULL, LBo, 1);
 			uint32_t XL = __shfl_up_sync(FULL, XLo, 1), VL = __shfl_up_sync(FULL, VLo, 1), X2L = __shfl_up_sync(FULL, X2Lo, 1);
+			if (lane == 0) {
+				LA = LA0, LB = LB0, XL = X_INIT, X2L = X2_INIT;
+				VL = s == 0 ? VB0 : s < long_thres ? VB1 : s == long_thres ? VB2 : VB3;
+			}
+			LAo = LA, LBo = LB;
 			if (lane_live && j >= 0 && j < Qm) {
-				if (lane == 0) XL = X_INIT, X2L = X2_INIT, VL = dpf_pack2(8 * (dpf_bnd(j, q, e, e2, long_thres, long_diff) + B));
-				const uint32_t LA = qbA < 4 ? MIS4 + (MDIFF << (qbA * 8)) : N4, LB = qbB < 4 ? MIS4 + (MDIFF << (qbB * 8)) : N4;
 				uint32_t wv[CW];
 				uint32_t wprev = 0;
 				#pragma unroll
@@ -165,8 +179,8 @@ k_dp_fast(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 					const uint32_t zt = __vimax3_s16x2(__vimax3_s16x2(z0, a, b), a2, b2);
 					const uint32_t zc = zt & 0xfff8fff8u;
 					const uint32_t un = zc - VL, vn = zc - U[c];          // halves are non-negative: no borrow
-					const uint32_t nz = 0x00010000u - zc;                  // per-half negation (low half of zc is never 0)
-					const uint32_t nz1 = __vadd2(nz, D1), nz2 = __vadd2(nz, D2);
+					// per-half D - zc: the low half always borrows (zc > D, checked on the host), which the 0x10000 pays back
+					const uint32_t nz1 = K1 - zc, nz2 = K2 - zc;
 					const uint32_t r1 = __viaddmax_s16x2(a, nz1, FL1), r2 = __viaddmax_s16x2(b, nz1, FL2);
 					const uint32_t r3 = __viaddmax_s16x2(a2, nz2, FL3), r4 = __viaddmax_s16x2(b2, nz2, FL4);
 					const uint32_t g1 = __viaddmin_s16x2(r1, NFL1, EIGHT), g2 = __viaddmin_s16x2(r2, NFL2, EIGHT);
@@ -179,7 +193,6 @@ k_dp_fast(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 				}
 				XLo = XL, VLo = VL, X2Lo = X2L;
 				// [step][lane][CW]: the 32 lanes of a step write one contiguous run
-				uint32_t *dst = P + ((size_t)s * 32 + lane) * CW;
 				if (CW % 4 == 0) {
 					#pragma unroll
 					for (int k = 0; k < CW / 4; ++k) reinterpret_cast<uint4*>(dst)[k] = make_uint4(wv[4 * k], wv[4 * k + 1], wv[4 * k + 2], wv[4 * k + 3]);
