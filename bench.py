@@ -367,7 +367,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu,
             "stage_ms": stage_ms,
-            "work_per_step": {k: last[k] for k in ("n_reads", "n_bases", "n_mini", "n_anchor", "n_regs", "n_dp_tasks", "n_dp_pass2", "dp_cells", "n_hits", "n_rounds", "n_fast_tasks", "n_exact_tasks")},
+            "work_per_step": {k: last[k] for k in ("n_reads", "n_bases", "n_mini", "n_anchor", "n_regs", "n_dp_tasks", "n_dp_pass2", "dp_cells", "n_hits", "n_rounds", "n_fast_tasks", "n_exact_tasks", "dp_cells_exact", "chain_cells")},
             "read_classes": {"mapped": int(ncls[0]), "unmapped": int(ncls[1]), "ambiguous": int(ncls[2])},
         }
         print(json.dumps(out))

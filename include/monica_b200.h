@@ -64,6 +64,8 @@ typedef struct {
 	float   ms_kdp_fast;      /* ... of which the register-resident fast path (k_dp_fast) */
 	float   ms_kdp_exact;     /* ... and the exact ksw_extd2 block emulation (k_dp) */
 	int64_t n_fast_tasks, n_exact_tasks;
+	int64_t chain_cells;      /* predecessors visited by the chaining DP (the oracle counts the same loop) */
+	int64_t dp_cells_exact;   /* DP cells evaluated by k_dp (the rest of dp_cells went through k_dp_fast) */
 } mb_stats_t;
 
 const char *mb_last_error(void);

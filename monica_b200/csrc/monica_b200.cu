@@ -62,6 +62,8 @@ extern "C" int mb_opt_init(mb_opt_t *opt)
 struct ThreadCtx {
 	int device = -1;
 	cudaStream_t st = nullptr;
+	cudaStream_t st2[8] = {};     // high-priority side streams: the long-tailed exact DP launches overlap the fast DP kernels
+	cudaEvent_t ev_join[8] = {};
 	Arena ar;
 	int num_sms = 148;
 	uint8_t *h_pin = nullptr; size_t h_pin_cap = 0;   // pinned staging for reads
@@ -76,6 +78,7 @@ struct ThreadCtx {
 			if (h_pin) cudaFreeHost(h_pin);
 			if (d_counts) cudaFree(d_counts);
 			if (st) cudaStreamDestroy(st);
+			for (int i = 0; i < 8; ++i) { if (st2[i]) cudaStreamDestroy(st2[i]); if (ev_join[i]) cudaEventDestroy(ev_join[i]); }
 		}
 	}
 };
@@ -100,6 +103,14 @@ static ThreadCtx &get_ctx(int device)
 	ThreadCtx *c = new ThreadCtx();
 	c->device = device;
 	CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+	{
+		int lo = 0, hi = 0;
+		CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+		for (int i = 0; i < 8; ++i) {
+			CK(cudaStreamCreateWithPriority(&c->st2[i], cudaStreamNonBlocking, hi));
+			CK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+		}
+	}
 	cudaDeviceProp prop;
 	CK(cudaGetDeviceProperties(&prop, device));
 	c->num_sms = prop.multiProcessorCount;
@@ -488,8 +499,14 @@ static __host__ __device__ inline DpGeom dp_geom(int qlen, int tlen, int w)
 	return g;
 }
 
-#define DP_SMALL_P (1u << 20)
-#define DP_NCLS (DPF_NCLASS + 2)   // fast classes, then exact-emulation small / big scratch classes
+#define DP_NEXACT 6                 // exact-kernel classes by direction-matrix size: <=64K, <=256K, <=1M, <=4M, <=16M, larger
+#define DP_NCLS (DPF_NCLASS + DP_NEXACT)
+static __host__ __device__ inline int dp_exact_class(size_t p_bytes)
+{
+	int k = 0;
+	for (size_t lim = (size_t)64 << 10; k < DP_NEXACT - 1 && p_bytes > lim; lim <<= 2) ++k;
+	return k;
+}
 
 // classify tasks: fast path by columns-per-lane class, the rest into small / big scratch classes; record maxima
 __global__ void k_dp_classify(const DpTask *__restrict__ tasks, const int32_t *__restrict__ ids, int64_t n, int use_ids,
@@ -510,7 +527,7 @@ __global__ void k_dp_classify(const DpTask *__restrict__ tasks, const int32_t *_
 	}
 	DpGeom g = dp_geom(t.qlen, t.tlen, t.w);
 	if (t.skip) g.p_bytes = g.ws_bytes = g.h_ints = 0;
-	cls = DPF_NCLASS + (g.p_bytes > DP_SMALL_P ? 1 : 0);
+	cls = DPF_NCLASS + dp_exact_class(g.p_bytes);
 	lists[(int64_t)cls * n + atomicAdd(&ctr[cls], 1)] = id;
 	atomicMax(&maxima[cls * 3 + 0], (unsigned long long)g.p_bytes);
 	atomicMax(&maxima[cls * 3 + 1], (unsigned long long)g.ws_bytes);
@@ -567,6 +584,41 @@ struct DpRunner {
 		CK(cudaMemcpyAsync(h_ctr, ctr, sizeof(h_ctr), cudaMemcpyDeviceToHost, st));
 		CK(cudaMemcpyAsync(h_max, maxima, sizeof(h_max), cudaMemcpyDeviceToHost, st));
 		CK(cudaStreamSynchronize(st));
+		// the exact kernel goes first, on the high-priority side stream (the host synchronised `st` above, so its inputs are
+		// complete), largest class first: a handful of long band-limited tasks give each launch a long tail of a few busy
+		// warps, which the fast kernels on `st` fill
+		bool side[DP_NEXACT] = {};
+		for (int b = DP_NEXACT - 1; b >= 0; --b) {
+			const int cls = DPF_NCLASS + b;
+			cudaStream_t st2 = c.st2[b];
+			int64_t cnt = h_ctr[cls];
+			if (cnt == 0) continue;
+			size_t p_stride = ((size_t)h_max[cls * 3 + 0] + 255) & ~(size_t)255;
+			size_t g_stride = ((size_t)h_max[cls * 3 + 1] + 255) & ~(size_t)255;
+			size_t h_stride = ((size_t)h_max[cls * 3 + 2] + 63) & ~(size_t)63;
+			if (p_stride == 0) p_stride = 256;
+			if (h_stride == 0) h_stride = 64;
+			int max_cta = c.num_sms * 6;
+			int64_t want_cta = cdiv(cnt, DP_WARPS);
+			int n_cta = (int)(want_cta < max_cta ? want_cta : max_cta);
+			// bound total scratch to ~24 GB
+			size_t per_warp = p_stride + (g_stride > DP_SMEM_PER_WARP ? g_stride : 0) + h_stride * 4;
+			size_t budget = (size_t)24 << 30;
+			while (n_cta > 1 && (size_t)n_cta * DP_WARPS * per_warp > budget) n_cta = (n_cta + 1) / 2;
+			size_t n_warps = (size_t)n_cta * DP_WARPS;
+			uint8_t *p_scr = ar.get<uint8_t>(n_warps * p_stride);
+			int8_t *g_ws = g_stride > DP_SMEM_PER_WARP ? ar.get<int8_t>(n_warps * g_stride) : ar.get<int8_t>(16);
+			int32_t *h_scr = ar.get<int32_t>(n_warps * h_stride);
+			int32_t *wc = ar.get<int32_t>(1);
+			CK(cudaMemsetAsync(wc, 0, sizeof(int32_t), st2));
+			cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+			cudaEventRecord(e0, st2);
+			k_dp<<<n_cta, DP_WARPS * 32, DP_WARPS * DP_SMEM_PER_WARP, st2>>>(tasks, lists + (int64_t)cls * n, ctr + cls, wc, codes, S, pool,
+				p_scr, p_stride, g_ws, g_stride, h_scr, h_stride, cigar_pool, sc, d_cells ? d_cells + 1 : nullptr);
+			cudaEventRecord(e1, st2);
+			evs.emplace_back(e0, e1); ev_fast.push_back(0); n_exact += cnt;
+			++*nl; side[b] = true;
+		}
 		for (int k = 0; k < DPF_NCLASS; ++k) {
 			const int64_t cnt = h_ctr[k];
 			if (cnt == 0) continue;
@@ -588,36 +640,8 @@ struct DpRunner {
 			default: launch_fast<24>(tasks, list, ctr + k, cnt, mq, codes, S, pool, cigar_pool, sc, d_cells); break;
 			}
 		}
-		for (int b = 0; b < 2; ++b) {
-			const int cls = DPF_NCLASS + b;
-			int64_t cnt = h_ctr[cls];
-			if (cnt == 0) continue;
-			size_t p_stride = ((size_t)h_max[cls * 3 + 0] + 255) & ~(size_t)255;
-			size_t g_stride = ((size_t)h_max[cls * 3 + 1] + 255) & ~(size_t)255;
-			size_t h_stride = ((size_t)h_max[cls * 3 + 2] + 63) & ~(size_t)63;
-			if (p_stride == 0) p_stride = 256;
-			if (h_stride == 0) h_stride = 64;
-			int max_cta = c.num_sms * 6;
-			int64_t want_cta = cdiv(cnt, DP_WARPS);
-			int n_cta = (int)(want_cta < max_cta ? want_cta : max_cta);
-			// bound total scratch to ~24 GB
-			size_t per_warp = p_stride + (g_stride > DP_SMEM_PER_WARP ? g_stride : 0) + h_stride * 4;
-			size_t budget = (size_t)24 << 30;
-			while (n_cta > 1 && (size_t)n_cta * DP_WARPS * per_warp > budget) n_cta = (n_cta + 1) / 2;
-			size_t n_warps = (size_t)n_cta * DP_WARPS;
-			uint8_t *p_scr = ar.get<uint8_t>(n_warps * p_stride);
-			int8_t *g_ws = g_stride > DP_SMEM_PER_WARP ? ar.get<int8_t>(n_warps * g_stride) : ar.get<int8_t>(16);
-			int32_t *h_scr = ar.get<int32_t>(n_warps * h_stride);
-			int32_t *wc = ar.get<int32_t>(1);
-			CK(cudaMemsetAsync(wc, 0, sizeof(int32_t), st));
-			cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-			cudaEventRecord(e0, st);
-			k_dp<<<n_cta, DP_WARPS * 32, DP_WARPS * DP_SMEM_PER_WARP, st>>>(tasks, lists + (int64_t)cls * n, ctr + cls, wc, codes, S, pool,
-				p_scr, p_stride, g_ws, g_stride, h_scr, h_stride, cigar_pool, sc, d_cells);
-			cudaEventRecord(e1, st);
-			evs.emplace_back(e0, e1); ev_fast.push_back(0); n_exact += cnt;
-			++*nl;
-		}
+		for (int b = 0; b < DP_NEXACT; ++b)
+			if (side[b]) { CK(cudaEventRecord(c.ev_join[b], c.st2[b])); CK(cudaStreamWaitEvent(st, c.ev_join[b], 0)); }
 	}
 };
 
@@ -679,10 +703,10 @@ static mb_hits *map_device(mb_index *ix, const mb_opt_t &opt_in, ThreadCtx &c, c
 	rs.f = ar.get<int32_t>(n_a + 1), rs.p = ar.get<int32_t>(n_a + 1), rs.v = ar.get<int32_t>(n_a + 1), rs.t = ar.get<int32_t>(n_a + 1);
 	rs.b = ar.get<mb128>(n_a + 1); rs.u = ar.get<uint64_t>(n_a + 1); rs.scr = ar.get<uint64_t>(3 * n_a + 3 * (int64_t)n_reads + 3);
 	int32_t *wc = ar.get<int32_t>(4);
-	unsigned long long *d_cells = ar.get<unsigned long long>(2);
+	unsigned long long *d_cells = ar.get<unsigned long long>(3); // chain, DP total, DP exact kernel
 	int *d_err = ar.get<int>(1);
 	CK(cudaMemsetAsync(wc, 0, 4 * sizeof(int32_t), st));
-	CK(cudaMemsetAsync(d_cells, 0, 2 * sizeof(unsigned long long), st));
+	CK(cudaMemsetAsync(d_cells, 0, 3 * sizeof(unsigned long long), st));
 	CK(cudaMemsetAsync(d_err, 0, sizeof(int), st));
 	const int max_chain_gap_ref = opt.max_gap_ref > 0 ? opt.max_gap_ref : opt.max_gap, max_chain_gap_qry = opt.max_gap;
 	if (n_a > 0) {
@@ -784,7 +808,7 @@ static mb_hits *map_device(mb_index *ix, const mb_opt_t &opt_in, ThreadCtx &c, c
 	S.ms_post = tm.stop();
 	S.n_hits = n_h;
 	c.last_fields = d_fields, c.last_hit_off = hit_off, c.last_read_off = d_off, c.last_n_hits = n_h, c.last_n_reads = n_reads, c.last_index = ix;
-	unsigned long long h_cells[2];
+	unsigned long long h_cells[3];
 	CK(cudaMemcpyAsync(h_cells, d_cells, sizeof(h_cells), cudaMemcpyDeviceToHost, st));
 	tm.start();
 	H->n = n_h;
@@ -801,7 +825,7 @@ static mb_hits *map_device(mb_index *ix, const mb_opt_t &opt_in, ThreadCtx &c, c
 	CK(cudaStreamSynchronize(st));
 	CK(cudaGetLastError());
 	S.ms_d2h = tm.stop();
-	S.dp_cells = (int64_t)h_cells[1];
+	S.dp_cells = (int64_t)(h_cells[1] + h_cells[2]); S.dp_cells_exact = (int64_t)h_cells[2]; S.chain_cells = (int64_t)h_cells[0];
 	S.n_launches = nl;
 	S.ms_kdp = runner.total_ms(); S.n_kdp = (int32_t)runner.evs.size();
 	S.ms_kdp_fast = runner.total_ms(1); S.ms_kdp_exact = runner.total_ms(0); S.n_fast_tasks = runner.n_fast; S.n_exact_tasks = runner.n_exact;
