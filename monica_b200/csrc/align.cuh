@@ -62,6 +62,28 @@ struct TView {
 	}
 };
 
+// Sequential readers for the per-thread CIGAR walks (k_ztest, k_stitch): cache the aligned 32-bit word that holds the
+// current base, so a run of consecutive positions costs one load per 4 query bytes / 8 packed reference bases.
+struct QCur {
+	const uint8_t *codes; int64_t idx0; int step, comp; int64_t wi; uint32_t w;
+	MB_D void init(const QView &v) { codes = v.codes, idx0 = v.idx0, step = v.step, comp = v.comp, wi = -1, w = 0; }
+	MB_D int at(int j) {
+		const int64_t p = idx0 + (int64_t)j * step, k = p >> 2;
+		if (k != wi) { wi = k; w = *reinterpret_cast<const uint32_t*>(codes + (k << 2)); }
+		const int c = (int)(w >> ((p & 3) << 3) & 0xff);
+		return comp ? (c < 4 ? 3 - c : 4) : c;
+	}
+};
+struct TCur {
+	const uint32_t *S; int64_t idx0; int step; int64_t wi; uint32_t w;
+	MB_D void init(const TView &v) { S = v.S, idx0 = v.idx0, step = v.step, wi = -1, w = 0; } // packed views only
+	MB_D int at(int i) {
+		const int64_t p = idx0 + (int64_t)i * step, k = p >> 3;
+		if (k != wi) { wi = k; w = S[k]; }
+		return (int)(w >> ((p & 7) << 2) & 0xf);
+	}
+};
+
 struct AlignCtx {
 	const uint8_t *codes;         // nt4 read codes
 	const int64_t *read_off;

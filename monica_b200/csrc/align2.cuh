@@ -163,44 +163,101 @@ MB_D void mb_fix_cigar(Reg *r, uint32_t *cigar, const QView &qv, const TView &tv
 	r->n_cigar = n_cigar;
 }
 
-MB_D void mb_update_extra(Reg *r, uint32_t *cigar, QView qv, TView tv, const mb_opt_t &opt)
+// mm_update_extra for the regions stitched in this round, one WARP per region.  mm_fix_cigar (a sequential pass over the
+// CIGAR ops) is done by lane 0; the base-level scan that yields blen / mlen / n_ambi / dp_max is split over the lanes by
+// blocks of CIGAR ops.  dp_max is the maximum of the running score s <- max(s + d, 0): a lane summarises its block as the
+// pair of max-plus maps  s_out = max(s_in + A, B)  and  block_max = max(s_in + C, D), which compose associatively, so one
+// pass per lane plus a 32-step combine gives the exact sequential result.
+#define UE_NEG (-(1 << 29))
+__global__ void __launch_bounds__(128)
+k_update_extra(AlignCtx c, ReadArrays ra, const int2 *__restrict__ work, int n_work, uint32_t *__restrict__ cigar_pool)
 {
-	int32_t s = 0, mx = 0, qshift, tshift, toff = 0, qoff = 0;
-	if (!r->has_p) return;
-	mb_fix_cigar(r, cigar, qv, tv, &qshift, &tshift);
+	const unsigned FULL = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
+	const int wi = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+	if (wi >= n_work) return;
+	const int read = work[wi].x, slot = work[wi].y;
+	Reg *r = ra.regs + ra.reg_off[read] + slot;
+	if (r->cnt == 0 || !r->has_p) return;
+	const mb_opt_t &opt = c.opt;
+	const int64_t roff = c.read_off[read];
+	const int qlen = (int)(c.read_off[read + 1] - roff);
+	const int rev = r->rev;
+	uint32_t *cigar = cigar_pool + r->cigar_off;
+	const int qs1 = rev ? qlen - r->qe : r->qs, rs1 = r->rs;
+	QView qv; qv.codes = c.codes;
+	if (!rev) qv.idx0 = roff + qs1, qv.step = 1, qv.comp = 0;
+	else qv.idx0 = roff + qlen - 1 - qs1, qv.step = -1, qv.comp = 1;
+	TView tv; tv.S = c.ix.S; tv.bytes = nullptr; tv.idx0 = (int64_t)c.ix.seq_off[r->rid] + rs1; tv.step = 1; tv.packed = 1;
+	int qshift = 0, tshift = 0;
+	__syncwarp();
+	if (lane == 0) mb_fix_cigar(r, cigar, qv, tv, &qshift, &tshift);
+	__syncwarp();
+	qshift = __shfl_sync(FULL, qshift, 0), tshift = __shfl_sync(FULL, tshift, 0);
 	qv.idx0 += (int64_t)qshift * qv.step, tv.idx0 += (int64_t)tshift * tv.step;
-	r->blen = r->mlen = 0;
-	for (int k = 0; k < r->n_cigar; ++k) {
-		const uint32_t op = cigar[k] & 0xf, len = cigar[k] >> 4;
+	const int n_cigar = *reinterpret_cast<volatile int32_t*>(&r->n_cigar);
+	const volatile uint32_t *cg = cigar;
+	// block of ops of this lane, and the query / reference offsets at which it starts
+	const int per = (n_cigar + 31) / 32;
+	const int lo = min(lane * per, n_cigar), hi = min(lo + per, n_cigar);
+	int qsum = 0, tsum = 0;
+	for (int k = lo; k < hi; ++k) {
+		const uint32_t op = cg[k] & 0xf, len = cg[k] >> 4;
+		if (op == 0) qsum += len, tsum += len;
+		else if (op == 1) qsum += len;
+		else if (op == 2 || op == 3) tsum += len;
+	}
+	int qoff = qsum, toff = tsum;
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const int oq = __shfl_up_sync(FULL, qoff, d), ot = __shfl_up_sync(FULL, toff, d);
+		if (lane >= d) qoff += oq, toff += ot;
+	}
+	qoff -= qsum, toff -= tsum;
+	const int sc_a = opt.a < 0 ? -opt.a : opt.a, sc_b = opt.b > 0 ? -opt.b : opt.b, sc_n = -(opt.sc_ambi > 0 ? opt.sc_ambi : -opt.sc_ambi);
+	int blen = 0, mlen = 0, n_ambi_t = 0;
+	int A = 0, B = UE_NEG, Cm = UE_NEG, D = UE_NEG;
+	auto apply = [&](int d) { A += d; B = max(B + d, 0); Cm = max(Cm, A); D = max(D, B); };
+	for (int k = lo; k < hi; ++k) {
+		const uint32_t op = cg[k] & 0xf, len = cg[k] >> 4;
 		if (op == 0) {
 			int n_ambi = 0, n_diff = 0;
 			for (uint32_t l = 0; l < len; ++l) {
 				const int cq = qv.at(qoff + l), ct = tv.at(toff + l);
-				if (ct > 3 || cq > 3) ++n_ambi;
-				else if (ct != cq) ++n_diff;
-				s += mb_mat(ct, cq, opt);
-				if (s < 0) s = 0;
-				else mx = mx > s ? mx : s;
+				int d;
+				if (ct > 3 || cq > 3) ++n_ambi, d = sc_n;
+				else if (ct != cq) ++n_diff, d = sc_b;
+				else d = sc_a;
+				apply(d);
 			}
-			r->blen += len - n_ambi, r->mlen += len - (n_ambi + n_diff), r->n_ambi += n_ambi;
+			blen += len - n_ambi, mlen += len - (n_ambi + n_diff), n_ambi_t += n_ambi;
 			toff += len, qoff += len;
 		} else if (op == 1) {
 			int n_ambi = 0;
 			for (uint32_t l = 0; l < len; ++l) if (qv.at(qoff + l) > 3) ++n_ambi;
-			r->blen += len - n_ambi, r->n_ambi += n_ambi;
-			s -= opt.q + opt.e * (int)len;
-			if (s < 0) s = 0;
+			blen += len - n_ambi, n_ambi_t += n_ambi;
+			apply(-(opt.q + opt.e * (int)len));
 			qoff += len;
 		} else if (op == 2) {
 			int n_ambi = 0;
 			for (uint32_t l = 0; l < len; ++l) if (tv.at(toff + l) > 3) ++n_ambi;
-			r->blen += len - n_ambi, r->n_ambi += n_ambi;
-			s -= opt.q + opt.e * (int)len;
-			if (s < 0) s = 0;
+			blen += len - n_ambi, n_ambi_t += n_ambi;
+			apply(-(opt.q + opt.e * (int)len));
 			toff += len;
 		} else if (op == 3) toff += len;
 	}
-	r->dp_max = mx;
+	// combine the blocks in lane order
+	int s_run = 0, mx = 0;
+	for (int L = 0; L < 32; ++L) {
+		const int a = __shfl_sync(FULL, A, L), b = __shfl_sync(FULL, B, L), cm = __shfl_sync(FULL, Cm, L), dm = __shfl_sync(FULL, D, L);
+		mx = max(mx, max(s_run + cm, dm));
+		s_run = max(s_run + a, b);
+	}
+	#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) {
+		blen += __shfl_xor_sync(FULL, blen, d), mlen += __shfl_xor_sync(FULL, mlen, d), n_ambi_t += __shfl_xor_sync(FULL, n_ambi_t, d);
+	}
+	if (lane == 0) r->blen = blen, r->mlen = mlen, r->n_ambi += n_ambi_t, r->dp_max = mx;
 }
 
 // one thread per region of this round: the part of mm_align1 after each mm_align_pair
@@ -281,12 +338,7 @@ __global__ void k_stitch(AlignCtx c, ReadArrays ra, const int2 *__restrict__ wor
 	if (rev) r->qs = qlen - qe1, r->qe = qlen - qs1;
 	else r->qs = qs1, r->qe = qe1;
 	if (n_cig > 0) {
-		r->has_p = 1, r->n_cigar = n_cig, r->cigar_off = T[0].cigar_off, r->dp_score = dp_score;
-		QView qv; qv.codes = c.codes;
-		if (!rev) qv.idx0 = roff + qs1, qv.step = 1, qv.comp = 0;
-		else qv.idx0 = roff + qlen - 1 - qs1, qv.step = -1, qv.comp = 1;
-		TView tv; tv.S = c.ix.S; tv.bytes = nullptr; tv.idx0 = (int64_t)c.ix.seq_off[rid] + rs1; tv.step = 1; tv.packed = 1;
-		mb_update_extra(r, cig, qv, tv, opt);
+		r->has_p = 1, r->n_cigar = n_cig, r->cigar_off = T[0].cigar_off, r->dp_score = dp_score; // mm_update_extra: k_update_extra
 	}
 }
 

@@ -168,23 +168,76 @@ k_sort_anchors(const mb128 *__restrict__ in, mb128 *__restrict__ out, const int6
 	}
 }
 
-// reads whose anchors tie on x: reproduce upstream's unstable radix permutation exactly, one thread per read
-#define SORT_EMUL_WORKERS 64
-__global__ void k_sort_emul(const mb128 *__restrict__ in, mb128 *__restrict__ out, const int64_t *__restrict__ a_roff,
-                            const int32_t *__restrict__ tie_list, const int32_t *__restrict__ n_tie, int32_t *__restrict__ cursor,
-                            int *__restrict__ ws_pool)
+// reads whose anchors tie on x: reproduce upstream's unstable radix permutation exactly.  One warp per read, spread over
+// the whole GPU: the anchors are staged in shared memory (global scratch beyond SE_SMEM_N), lane 0 replays the sequential
+// cycle-leader passes there (byte levels on which the whole range agrees are no-ops and are skipped), and the <= 64-element
+// leaves are insertion-sorted by one lane each.
+#define SE_SMEM_N 2560             // 2560 * 16 B = 40 KB of anchors per warp
+#define SE_STACK  2304
+#define SE_SMEM_BYTES (SE_SMEM_N * 16 + 512 * 4 + 64)
+
+__global__ void __launch_bounds__(32)
+k_sort_emul(const mb128 *__restrict__ in, mb128 *__restrict__ out, const int64_t *__restrict__ a_roff,
+            const int32_t *__restrict__ tie_list, const int32_t *__restrict__ n_tie, int32_t *__restrict__ cursor,
+            int *__restrict__ ws_pool /* per CTA: 3*SE_STACK ints of range stack + leaf list */)
 {
-	int wid = blockIdx.x * blockDim.x + threadIdx.x;
-	if (wid >= SORT_EMUL_WORKERS) return;
-	int *ws = ws_pool + (size_t)wid * MB_RS_WS_INTS;
+	extern __shared__ __align__(16) uint8_t se_smem[];
+	mb128 *sa = reinterpret_cast<mb128*>(se_smem);
+	int *bb = reinterpret_cast<int*>(se_smem + SE_SMEM_N * 16), *be = bb + 256;
+	int *sh = be + 256; // [0] = n_leaf, [1] = work item
+	int *stk = ws_pool + (size_t)blockIdx.x * (6 * SE_STACK);
+	int *leaf = stk + 3 * SE_STACK; // (beg, end) pairs
+	const int lane = threadIdx.x;
+	const unsigned FULL = 0xffffffffu;
 	for (;;) {
-		int t = atomicAdd(cursor, 1);
+		if (lane == 0) sh[1] = atomicAdd(cursor, 1);
+		__syncwarp();
+		const int t = sh[1];
+		__syncwarp();
 		if (t >= *n_tie) break;
-		int r = tie_list[t];
-		int64_t base = a_roff[r];
-		int n = (int)(a_roff[r + 1] - base);
-		for (int i = 0; i < n; ++i) out[base + i] = in[base + i];
-		mb_radix_sort_emul(out + base, n, ws, KeyX());
+		const int r = tie_list[t];
+		const int64_t base = a_roff[r];
+		const int n = (int)(a_roff[r + 1] - base);
+		mb128 *a = n <= SE_SMEM_N ? sa : out + base;
+		for (int i = lane; i < n; i += 32) a[i] = in[base + i];
+		__syncwarp();
+		KeyX key;
+		if (n <= MB_RS_MIN_SIZE) {
+			if (lane == 0) mb_insertsort(a, a + n, key);
+		} else {
+			if (lane == 0) {
+				int sp = 1, n_leaf = 0;
+				stk[0] = 0, stk[1] = n, stk[2] = 56;
+				while (sp > 0) {
+					--sp;
+					const int beg = stk[3 * sp], end = stk[3 * sp + 1];
+					int s = stk[3 * sp + 2];
+					// skip byte levels on which every key of the range agrees: such a pass moves nothing
+					uint64_t diff = 0; const uint64_t k0 = a[beg].x;
+					for (int i = beg + 1; i < end; ++i) diff |= a[i].x ^ k0;
+					while (s > 0 && !(diff >> s & 255)) s -= 8;
+					mb_rs_partition(a, beg, end, s, bb, be, key);
+					if (s) {
+						const int s2 = s > 8 ? s - 8 : 0;
+						for (int k = 0; k < 256; ++k) {
+							const int len = be[k] - bb[k];
+							if (len > MB_RS_MIN_SIZE) { stk[3 * sp] = bb[k], stk[3 * sp + 1] = be[k], stk[3 * sp + 2] = s2; ++sp; } // depth <= 8 levels x 255 siblings < SE_STACK
+							else if (len > 1) {
+								if (2 * n_leaf + 2 <= 3 * SE_STACK) { leaf[2 * n_leaf] = bb[k], leaf[2 * n_leaf + 1] = be[k]; ++n_leaf; }
+								else mb_insertsort(a + bb[k], a + be[k], key);
+							}
+						}
+					}
+				}
+				sh[0] = n_leaf;
+			}
+			__syncwarp();
+			const int n_leaf = sh[0];
+			for (int l = lane; l < n_leaf; l += 32) mb_insertsort(a + leaf[2 * l], a + leaf[2 * l + 1], key);
+		}
+		__syncwarp();
+		if (a == sa) for (int i = lane; i < n; i += 32) out[base + i] = sa[i];
+		__syncwarp();
 	}
 }
 
@@ -246,6 +299,9 @@ static void run_seed(Arena &ar, cudaStream_t st, const DevIndex &ix, int mid_occ
 	CK(cudaMemsetAsync(ctr, 0, 2 * sizeof(int32_t), st));
 	int grid = n_reads < num_sms * 8 ? n_reads : num_sms * 8;
 	k_sort_anchors<<<grid, SORT_TPB, 0, st>>>(o.a_unsorted, o.a, o.a_roff, n_reads, gkey, gidx, big_off, tie_list, ctr); ++*n_launch;
-	int *ws_pool = ar.get<int>((size_t)SORT_EMUL_WORKERS * MB_RS_WS_INTS);
-	k_sort_emul<<<1, SORT_EMUL_WORKERS, 0, st>>>(o.a_unsorted, o.a, o.a_roff, tie_list, ctr, ctr + 1, ws_pool); ++*n_launch;
+	static bool se_attr = false;
+	if (!se_attr) { CK(cudaFuncSetAttribute(k_sort_emul, cudaFuncAttributeMaxDynamicSharedMemorySize, SE_SMEM_BYTES)); se_attr = true; }
+	const int se_grid = num_sms * 4;
+	int *ws_pool = ar.get<int>((size_t)se_grid * 6 * SE_STACK);
+	k_sort_emul<<<se_grid, 32, SE_SMEM_BYTES, st>>>(o.a_unsorted, o.a, o.a_roff, tie_list, ctr, ctr + 1, ws_pool); ++*n_launch;
 }
