@@ -29,7 +29,11 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-OPS_PER_CELL = 40   # integer ops per DP cell of the two-piece affine recurrence with direction flags
+OPS_PER_CELL = 40   # algorithmic integer ops per DP cell of the two-piece affine recurrence with direction flags
+SIMD_WIDTH = 2      # 16x2 packed integer SIMD lanes per 32-bit lane-op (VIADD.16x2 / VIMNMX3.S16x2 / VIADDMNMX.S16x2)
+# DRAM traffic of the dominant kernel per DP cell, from the committed `ncu --set full` capture (profiles/r01_summary_b.md):
+# (dram__bytes_read.sum + dram__bytes_write.sum) / cells of that launch.  Algorithmic bytes: 1 direction byte per cell.
+NCU_TRAFFIC_BYTES_PER_CELL = 1.12
 
 
 def parse_args():
@@ -281,59 +285,79 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    # Device timing: CUDA events recorded on the library's own stream (the one every kernel of the step is launched on),
+    # bracketing exactly K steps; wall clock is kept beside it as a cross-check.
+    lib_stream = torch.cuda.ExternalStream(L.mb_stream(al.handle()), device=torch.device("cuda", local))
+
+    def timed(step_fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(lib_stream)
+        outs = [step_fn() for _ in range(k)]
+        e1.record(lib_stream)
+        e1.synchronize()
+        barrier()
+        wall = time.perf_counter() - t0
+        dev = e0.elapsed_time(e1) * 1e-3
+        return max_over_ranks(dev), max_over_ranks(wall), outs
+
     # ---- value leg: resident inputs ----
     for _ in range(a.warmup):
         step_value()
     sampler = ClockSampler(local)
-    barrier()
     sampler.start()
-    t0 = time.perf_counter()
-    stats = []
-    for _ in range(a.steps):
-        st, tot_counts = step_value()
-        stats.append(st.as_dict())
-    barrier()
-    dt_value = max_over_ranks(time.perf_counter() - t0)
+    dt_value, wall_value, outs = timed(step_value, a.steps)
     clocks = sampler.stop()
+    stats = [o[0].as_dict() for o in outs]
+    tot_counts = outs[-1][1]
     mapped_bases_rank = float(counts.sum())            # this rank's bases assigned to a target (query_length mode)
     mapped_bases_all = float(tot_counts.sum()) if world > 1 else mapped_bases_rank
     total_bases_all = sum_over_ranks(float(total_bases))
     value = mapped_bases_all * a.steps / dt_value / 1e9
 
     # ---- e2e leg: host buffers through the C ABI ----
-    step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    d2h = 0
-    for _ in range(a.steps):
-        st_e, tot_counts_e, d2h = step_e2e()
-    barrier()
-    dt_e2e = max_over_ranks(time.perf_counter() - t0)
+    for _ in range(max(1, min(a.warmup, 2))):
+        step_e2e()
+    dt_e2e, wall_e2e, outs_e = timed(step_e2e, a.steps)
+    dt_e2e = max(dt_e2e, wall_e2e)                     # host copies of the result happen after the last event: take the wall clock
+    tot_counts_e, d2h = outs_e[-1][1], outs_e[-1][2]
     e2e_value = float(tot_counts_e.sum() if world > 1 else counts.sum()) * a.steps / dt_e2e / 1e9
 
-    # ---- roofline of the dominant kernel (k_dp) ----
+    # ---- roofline of the dominant kernel (k_dp_fast: packed two-piece affine DP + traceback) ----
     last = stats[-1]
-    ms_kdp = float(np.mean([s["ms_kdp"] for s in stats]))
-    cells = float(np.mean([s["dp_cells"] for s in stats]))
+    ms_fast = float(np.mean([s["ms_kdp_fast"] for s in stats]))
+    cells_fast = float(np.mean([s["dp_cells"] - s["dp_cells_exact"] for s in stats]))
     tiops = C.c_double(0)
     _lib.check(L.mb_int_peak(local, C.byref(tiops)))
-    peak_gcups = tiops.value * 1e3 / OPS_PER_CELL
-    gcups = cells / (ms_kdp * 1e-3) / 1e9 if ms_kdp > 0 else 0.0
+    peak_gcups = tiops.value * 1e3 * SIMD_WIDTH / OPS_PER_CELL
+    gcups = cells_fast / (ms_fast * 1e-3) / 1e9 if ms_fast > 0 else 0.0
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"
     sketch_bytes = (last["n_bases"] + 16 * last["n_mini"]) * 2   # count + write passes, 1 B/base nt4 in, 16 B/minimizer out
     seed_bytes = 32 * last["n_mini"] + 24 * last["n_anchor"] + 32 * last["n_anchor"]
-    stage_ms = {k: float(np.mean([s[k] for s in stats])) for k in ("ms_sketch", "ms_seed", "ms_chain", "ms_glue", "ms_dp", "ms_post", "ms_total", "ms_kdp", "ms_kdp_fast", "ms_kdp_exact", "ms_d2h")}
+    stage_keys = ("ms_sketch", "ms_seed", "ms_chain", "ms_glue", "ms_dp", "ms_post", "ms_total", "ms_kdp", "ms_kdp_fast", "ms_kdp_exact", "ms_d2h")
+    stage_ms = {k: float(np.mean([s[k] for s in stats])) for k in stage_keys}
+    n_fast_launches = max(1, int(last["n_kdp_fast"]))
     roofline = {
-        "kernel": "k_dp (two-piece affine banded DP + traceback, ksw_extd2 equivalent)", "bound": "int", "achieved": gcups, "peak": peak_gcups, "unit": "GCUPS",
-        "frac": gcups / peak_gcups if peak_gcups else None, "traffic": None,
-        "peak_source": f"measured INT32 add/max issue rate {tiops.value:.1f} Tops/s on this GPU (mb_int_peak) / {OPS_PER_CELL} int ops per cell",
-        "share_of_step": ms_kdp / stage_ms["ms_total"] if stage_ms["ms_total"] else None,
-        "hbm_kernels": {
+        "kernel": "k_dp_fast<C> (two-piece affine gap-fill DP + traceback, ksw_extd2 equivalent, 2 tasks/warp in 16x2 SIMD)",
+        "bound": "int", "achieved": gcups, "peak": peak_gcups, "unit": "GCUPS",
+        "frac": gcups / peak_gcups if peak_gcups else None,
+        "traffic": NCU_TRAFFIC_BYTES_PER_CELL * cells_fast / n_fast_launches,
+        "traffic_note": "bytes per launch = ncu dram bytes/cell of the committed capture x cells per launch; algorithmic = 1 B/cell",
+        "peak_source": f"measured INT32 add/max issue rate {tiops.value:.1f} Tlane-op/s on this GPU (mb_int_peak) x {SIMD_WIDTH} (16x2 SIMD) / {OPS_PER_CELL} int ops per cell",
+        "cells_per_step": cells_fast, "ms_per_step": ms_fast, "launches_per_step": n_fast_launches,
+        "share_of_step": ms_fast / stage_ms["ms_total"] if stage_ms["ms_total"] else None,
+        "hbm_view": {"bound": "hbm", "achieved": cells_fast / (ms_fast * 1e-3) / 1e9 if ms_fast else None, "peak": hbm_peak, "unit": "GB/s",
+                     "note": f"1 direction byte per cell streamed to HBM; peak {hbm_src}"},
+        "other_kernels": {
+            "k_dp (exact ksw_extd2 emulation, overlapped on side streams)": {"bound": "int", "achieved": (float(np.mean([s["dp_cells_exact"] for s in stats])) / (stage_ms["ms_kdp_exact"] * 1e-3) / 1e9) if stage_ms["ms_kdp_exact"] else None, "unit": "GCUPS"},
+            "k_chain_dp": {"bound": "int", "achieved": (float(last["chain_cells"]) / (stage_ms["ms_chain"] * 1e-3) / 1e9) if stage_ms["ms_chain"] else None, "unit": "G predecessor evaluations/s"},
             "k_sketch": {"bound": "hbm", "achieved": sketch_bytes / (stage_ms["ms_sketch"] * 1e-3) / 1e9 if stage_ms["ms_sketch"] else None,
                          "peak": hbm_peak, "unit": "GB/s", "note": "stage time includes two scans and a host sync"},
             "k_seed_lookup+fill+sort": {"bound": "hbm", "achieved": seed_bytes / (stage_ms["ms_seed"] * 1e-3) / 1e9 if stage_ms["ms_seed"] else None,
@@ -354,8 +378,8 @@ def main():
                 cpu = {"value": None, "unit": "Gbases/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
         out = {
             "metric": "mapped Gbases/s", "value": value, "unit": "Gbases/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": dt_value / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int8 DP / int32 chaining / uint64 hashing", "data": "synthetic",
+            "ms_per_step": dt_value / a.steps * 1e3, "ms_per_step_wall": wall_value / a.steps * 1e3, "timing": "CUDA events on the launching stream, max over ranks", "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int16x2 DP (int8-range differences) / int32 chaining / uint64 hashing", "data": "synthetic",
             "config": {"workload": workload_name(a), "reads_per_gpu": n_reads, "bases_per_gpu": total_bases, "l2": "inputs larger than L2 (no flush needed)",
                        "index_hbm_bytes": int(L.mb_index_hbm_bytes(al.handle())), "index_build_s": t_index, "parallelism": f"reads sharded over {world} GPU(s), index replicated, 1 NCCL all-reduce of int64[{n_seq}] per step"},
             "total_gbases_per_s": total_bases_all * a.steps / dt_value / 1e9,

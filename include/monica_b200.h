@@ -66,6 +66,7 @@ typedef struct {
 	int64_t n_fast_tasks, n_exact_tasks;
 	int64_t chain_cells;      /* predecessors visited by the chaining DP (the oracle counts the same loop) */
 	int64_t dp_cells_exact;   /* DP cells evaluated by k_dp (the rest of dp_cells went through k_dp_fast) */
+	int64_t n_kdp_fast;       /* k_dp_fast launches (one per non-empty column class and pass) */
 } mb_stats_t;
 
 const char *mb_last_error(void);
@@ -144,8 +145,12 @@ typedef struct {
 int  mb_dp_batch(int device, const mb_opt_t *opt, mb_dp_task_t *tasks, int64_t n_tasks, const uint8_t *seqpool, int64_t n_seqpool,
                  uint32_t *cigar_pool, int64_t n_cigar_pool);
 
-/* ---- measurement helper: sustained INT32 add/max issue rate of the device (roofline denominator for K3/K4) ---- */
-int  mb_int_peak(int device, double *tera_int_ops_per_s);
+/* ---- measurement helpers ----
+ * mb_stream: the cudaStream_t on which the calling thread's batches of this index run (so a caller can bracket K batches
+ * with CUDA events recorded on the launching stream, or enqueue its NCCL all-reduce of mb_count_device_ptr() behind them). */
+void *mb_stream(mb_index_t *idx);
+/* sustained INT32 add/max issue rate of the device (roofline denominator for K3/K4) ---- */
+int  mb_int_peak(int device, double *tera_int_ops_per_s);   /* reference no counterpart: roofline denominator for K3/K4 */
 
 #ifdef __cplusplus
 }

@@ -39,7 +39,7 @@ class Stats(C.Structure):
                                          "dp_cells", "n_hits", "n_rounds")] + \
                [(n, C.c_float) for n in ("ms_sketch", "ms_seed", "ms_sort", "ms_chain", "ms_glue", "ms_dp", "ms_post",
                                          "ms_total", "ms_h2d", "ms_d2h")] + [("n_launches", C.c_int64), ("ms_kdp", C.c_float), ("n_kdp", C.c_int32), ("ms_kdp_fast", C.c_float), ("ms_kdp_exact", C.c_float),
-                  ("n_fast_tasks", C.c_int64), ("n_exact_tasks", C.c_int64), ("chain_cells", C.c_int64), ("dp_cells_exact", C.c_int64)]
+                  ("n_fast_tasks", C.c_int64), ("n_exact_tasks", C.c_int64), ("chain_cells", C.c_int64), ("dp_cells_exact", C.c_int64), ("n_kdp_fast", C.c_int64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -66,7 +66,7 @@ SYMBOLS = [
     "mb_map_batch", "mb_reads_upload", "mb_reads_free", "mb_map_resident",
     "mb_hits_n", "mb_hits_field", "mb_hits_cigar_off", "mb_hits_cigar_pool", "mb_hits_rep_len", "mb_hits_free",
     "mb_count", "mb_count_last", "mb_count_device_ptr", "mb_count_fetch",
-    "mb_sketch", "mb_seed", "mb_chain", "mb_dp_batch", "mb_int_peak",
+    "mb_sketch", "mb_seed", "mb_chain", "mb_dp_batch", "mb_int_peak", "mb_stream",
 ]
 
 _lib = None
@@ -124,6 +124,8 @@ def lib():
     L.mb_int_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.mb_count_device_ptr.argtypes = [vp]
     L.mb_count_device_ptr.restype = vp
+    L.mb_stream.argtypes = [vp]
+    L.mb_stream.restype = vp
     L.mb_count_fetch.argtypes = [vp, vp]
     L.mb_sketch.argtypes = [C.c_int, vp, vp, i32, C.c_int, C.c_int, vp, i64, vp]
     L.mb_seed.argtypes = [vp, C.POINTER(Opt), vp, vp, i32, vp, i64, vp, vp]

@@ -829,6 +829,7 @@ static mb_hits *map_device(mb_index *ix, const mb_opt_t &opt_in, ThreadCtx &c, c
 	S.dp_cells = (int64_t)(h_cells[1] + h_cells[2]); S.dp_cells_exact = (int64_t)h_cells[2]; S.chain_cells = (int64_t)h_cells[0];
 	S.n_launches = nl;
 	S.ms_kdp = runner.total_ms(); S.n_kdp = (int32_t)runner.evs.size();
+	{ int64_t nf = 0; for (int f : runner.ev_fast) nf += f; S.n_kdp_fast = nf; }
 	S.ms_kdp_fast = runner.total_ms(1); S.ms_kdp_exact = runner.total_ms(0); S.n_fast_tasks = runner.n_fast; S.n_exact_tasks = runner.n_exact;
 	S.ms_total = tall.stop();
 	if (stats) { float h2d = stats->ms_h2d; *stats = S; stats->ms_h2d = h2d; }
@@ -1001,6 +1002,12 @@ extern "C" int mb_int_peak(int device, double *tops)
 	double ops = 2.0 * 8 * 8 * iters * (double)grid * tpb;
 	if (tops) *tops = ops / (best * 1e-3) / 1e12;
 	API_END
+}
+
+extern "C" void *mb_stream(mb_index_t *ix)
+{
+	if (!ix) return nullptr;
+	try { return (void*)get_ctx(ix->device).st; } catch (...) { return nullptr; }
 }
 
 extern "C" void *mb_count_device_ptr(mb_index_t *ix)
