@@ -327,7 +327,7 @@ def main():
     # ---- roofline of the dominant kernel (k_dp_fast: packed two-piece affine DP + traceback) ----
     last = stats[-1]
     ms_fast = float(np.mean([s["ms_kdp_fast"] for s in stats]))
-    cells_fast = float(np.mean([s["dp_cells"] - s["dp_cells_exact"] for s in stats]))
+    cells_fast = float(np.mean([s["dp_cells"] - s["dp_cells_exact"] - s["dp_cells_ext"] for s in stats]))
     tiops = C.c_double(0)
     _lib.check(L.mb_int_peak(local, C.byref(tiops)))
     peak_gcups = tiops.value * 1e3 * SIMD_WIDTH / OPS_PER_CELL
@@ -341,7 +341,7 @@ def main():
     hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"
     sketch_bytes = (last["n_bases"] + 16 * last["n_mini"]) * 2   # count + write passes, 1 B/base nt4 in, 16 B/minimizer out
     seed_bytes = 32 * last["n_mini"] + 24 * last["n_anchor"] + 32 * last["n_anchor"]
-    stage_keys = ("ms_sketch", "ms_seed", "ms_chain", "ms_glue", "ms_dp", "ms_post", "ms_total", "ms_kdp", "ms_kdp_fast", "ms_kdp_exact", "ms_d2h")
+    stage_keys = ("ms_sketch", "ms_seed", "ms_chain", "ms_glue", "ms_dp", "ms_post", "ms_total", "ms_kdp", "ms_kdp_fast", "ms_kdp_exact", "ms_kdp_ext", "ms_d2h")
     stage_ms = {k: float(np.mean([s[k] for s in stats])) for k in stage_keys}
     n_fast_launches = max(1, int(last["n_kdp_fast"]))
     roofline = {
@@ -391,7 +391,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu,
             "stage_ms": stage_ms,
-            "work_per_step": {k: last[k] for k in ("n_reads", "n_bases", "n_mini", "n_anchor", "n_regs", "n_dp_tasks", "n_dp_pass2", "dp_cells", "n_hits", "n_rounds", "n_fast_tasks", "n_exact_tasks", "dp_cells_exact", "chain_cells")},
+            "work_per_step": {k: last[k] for k in ("n_reads", "n_bases", "n_mini", "n_anchor", "n_regs", "n_dp_tasks", "n_dp_pass2", "dp_cells", "n_hits", "n_rounds", "n_fast_tasks", "n_exact_tasks", "n_ext_tasks", "dp_cells_exact", "dp_cells_ext", "chain_cells")},
             "read_classes": {"mapped": int(ncls[0]), "unmapped": int(ncls[1]), "ambiguous": int(ncls[2])},
         }
         print(json.dumps(out))

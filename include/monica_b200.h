@@ -67,6 +67,8 @@ typedef struct {
 	int64_t chain_cells;      /* predecessors visited by the chaining DP (the oracle counts the same loop) */
 	int64_t dp_cells_exact;   /* DP cells evaluated by k_dp (the rest of dp_cells went through k_dp_fast) */
 	int64_t n_kdp_fast;       /* k_dp_fast launches (one per non-empty column class and pass) */
+	int64_t n_ext_tasks, dp_cells_ext; /* end extensions through k_dp_ext */
+	float   ms_kdp_ext; int32_t pad_;
 } mb_stats_t;
 
 const char *mb_last_error(void);

@@ -39,7 +39,7 @@ class Stats(C.Structure):
                                          "dp_cells", "n_hits", "n_rounds")] + \
                [(n, C.c_float) for n in ("ms_sketch", "ms_seed", "ms_sort", "ms_chain", "ms_glue", "ms_dp", "ms_post",
                                          "ms_total", "ms_h2d", "ms_d2h")] + [("n_launches", C.c_int64), ("ms_kdp", C.c_float), ("n_kdp", C.c_int32), ("ms_kdp_fast", C.c_float), ("ms_kdp_exact", C.c_float),
-                  ("n_fast_tasks", C.c_int64), ("n_exact_tasks", C.c_int64), ("chain_cells", C.c_int64), ("dp_cells_exact", C.c_int64), ("n_kdp_fast", C.c_int64)]
+                  ("n_fast_tasks", C.c_int64), ("n_exact_tasks", C.c_int64), ("chain_cells", C.c_int64), ("dp_cells_exact", C.c_int64), ("n_kdp_fast", C.c_int64), ("n_ext_tasks", C.c_int64), ("dp_cells_ext", C.c_int64), ("ms_kdp_ext", C.c_float), ("pad_", C.c_int32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -412,7 +412,8 @@ __global__ void k_set_cigar_off(DpTask *__restrict__ tasks, const int64_t *__res
 // k_dp: ksw_extd2_sse, one warp per task
 // ------------------------------------------------------------------------------------------------
 #define DP_WARPS 4
-#define DP_SMEM_PER_WARP 9216     // covers tlen,qlen <= ~1000: 8*tlen16 + qlen16 + 16 bytes
+#define DP_SMEM_PER_WARP 13568    // covers tlen,qlen <= ~1000: 8*tlen16 + qlen16 + 16 bytes of state + 4*tlen16 of H
+#define DP_SMEM_MAX (96 * 1024)   // one-warp CTAs of the long-task classes may use up to this much
 
 struct DpScoring { int8_t q, e, q2, e2, sc_mch, sc_mis, sc_N, pad; };
 
@@ -434,12 +435,13 @@ __global__ void __launch_bounds__(DP_WARPS * 32)
 k_dp(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const int32_t *__restrict__ n_order, int32_t *__restrict__ work_ctr,
      const uint8_t *__restrict__ codes, const uint32_t *__restrict__ S, const uint8_t *__restrict__ pool,
      uint8_t *__restrict__ p_scr, size_t p_stride, int8_t *__restrict__ g_ws, size_t g_stride, int32_t *__restrict__ h_scr, size_t h_stride,
-     uint32_t *__restrict__ cigar_pool, DpScoring sc, unsigned long long *__restrict__ cells_out)
+     uint32_t *__restrict__ cigar_pool, DpScoring sc, unsigned long long *__restrict__ cells_out, int smem_per_warp)
 {
 	extern __shared__ __align__(16) int8_t dp_smem[];
+	const int warps_per_cta = blockDim.x >> 5;   // 4 for the small classes; 1 with a large shared-memory slice for long tasks
 	const unsigned FULL = 0xffffffffu;
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-	const int gw = blockIdx.x * DP_WARPS + wib;
+	const int gw = blockIdx.x * warps_per_cta + wib;
 	uint8_t *P = p_scr + (size_t)gw * p_stride;
 	int32_t *H = h_scr + (size_t)gw * h_stride;
 	unsigned long long cells = 0;
@@ -470,7 +472,12 @@ k_dp(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const int32_
 		if (q2 + e2 + long_thres * e2 > q + e + long_thres * e) ++long_thres;
 		const int long_diff = long_thres * (e - e2) - (q2 - q) - e2;
 		const size_t ws_need = (size_t)T16 * 8 + (size_t)qlen_ * 16 + 16;
-		int8_t *ws = ws_need <= DP_SMEM_PER_WARP ? dp_smem + (size_t)wib * DP_SMEM_PER_WARP : g_ws + (size_t)gw * g_stride;
+		// state arrays and (exact mode) the 32-bit H row live in this warp's shared-memory slice when they fit
+		const size_t h_need = with_exact ? (size_t)T16 * 4 : 0;
+		const bool in_smem = ((ws_need + 15) & ~(size_t)15) + h_need <= (size_t)smem_per_warp;
+		int8_t *ws = in_smem ? dp_smem + (size_t)wib * smem_per_warp : g_ws + (size_t)gw * g_stride;
+		if (in_smem && with_exact) H = reinterpret_cast<int32_t*>(ws + ((ws_need + 15) & ~(size_t)15));
+		else H = h_scr + (size_t)gw * h_stride;
 		int8_t *u = ws, *v = u + T16, *x = v + T16, *y = x + T16, *x2 = y + T16, *y2 = x2 + T16, *s = y2 + T16;
 		uint8_t *sf = (uint8_t*)(s + T16), *qr = sf + T16;
 		// ---- init ----

@@ -6,6 +6,7 @@
 //   -> k_finish -> k_write_hits -> D2H hits.
 // There is no CPU fallback anywhere in this file: every compute entry point throws MB_ERR_CUDA without a device.
 #include <algorithm>
+#include <chrono>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -19,8 +20,10 @@
 #include "align.cuh"
 #include "align2.cuh"
 #include "dp_fast.cuh"
+#include "dp_ext.cuh"
 
 thread_local std::string g_mb_err;
+static thread_local std::chrono::steady_clock::time_point g_dbg_t0 = std::chrono::steady_clock::now();
 
 extern "C" const char *mb_last_error(void) { return g_mb_err.c_str(); }
 
@@ -59,11 +62,14 @@ extern "C" int mb_opt_init(mb_opt_t *opt)
 // ---------------------------------------------------------------------------------------------
 // per-thread device context
 // ---------------------------------------------------------------------------------------------
+#define MB_NSIDE 4
 struct ThreadCtx {
 	int device = -1;
 	cudaStream_t st = nullptr;
-	cudaStream_t st2[8] = {};     // high-priority side streams: the long-tailed exact DP launches overlap the fast DP kernels
-	cudaEvent_t ev_join[8] = {};
+	// high-priority side streams: the long-tailed exact DP launches and the small extension launches overlap the fast DP
+	// kernels.  Few of them on purpose: streams beyond the device's hardware queues (8 by default) alias and serialise.
+	cudaStream_t st2[MB_NSIDE] = {};
+	cudaEvent_t ev_join[MB_NSIDE] = {};
 	Arena ar;
 	int num_sms = 148;
 	uint8_t *h_pin = nullptr; size_t h_pin_cap = 0;   // pinned staging for reads
@@ -78,7 +84,7 @@ struct ThreadCtx {
 			if (h_pin) cudaFreeHost(h_pin);
 			if (d_counts) cudaFree(d_counts);
 			if (st) cudaStreamDestroy(st);
-			for (int i = 0; i < 8; ++i) { if (st2[i]) cudaStreamDestroy(st2[i]); if (ev_join[i]) cudaEventDestroy(ev_join[i]); }
+			for (int i = 0; i < MB_NSIDE; ++i) { if (st2[i]) cudaStreamDestroy(st2[i]); if (ev_join[i]) cudaEventDestroy(ev_join[i]); }
 		}
 	}
 };
@@ -106,7 +112,7 @@ static ThreadCtx &get_ctx(int device)
 	{
 		int lo = 0, hi = 0;
 		CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-		for (int i = 0; i < 8; ++i) {
+		for (int i = 0; i < MB_NSIDE; ++i) {
 			CK(cudaStreamCreateWithPriority(&c->st2[i], cudaStreamNonBlocking, hi));
 			CK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
 		}
@@ -116,7 +122,7 @@ static ThreadCtx &get_ctx(int device)
 	c->num_sms = prop.multiProcessorCount;
 	std::call_once(g_const_once[device & 15], [&]() {
 		CK(cudaMemcpyToSymbol(c_nt4, h_nt4, 256));
-		CK(cudaFuncSetAttribute(k_dp, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_WARPS * DP_SMEM_PER_WARP));
+		CK(cudaFuncSetAttribute(k_dp, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM_MAX));
 	});
 	t_ctx[device] = c;
 	return *c;
@@ -500,7 +506,9 @@ static __host__ __device__ inline DpGeom dp_geom(int qlen, int tlen, int w)
 }
 
 #define DP_NEXACT 6                 // exact-kernel classes by direction-matrix size: <=64K, <=256K, <=1M, <=4M, <=16M, larger
-#define DP_NCLS (DPF_NCLASS + DP_NEXACT)
+#define DP_XBASE DPF_NCLASS          // extension fast-path classes follow the gap-fill fast-path classes
+#define DP_EBASE (2 * DPF_NCLASS)   // then the exact-kernel classes
+#define DP_NCLS (2 * DPF_NCLASS + DP_NEXACT)
 static __host__ __device__ inline int dp_exact_class(size_t p_bytes)
 {
 	int k = 0;
@@ -519,6 +527,7 @@ __global__ void k_dp_classify(const DpTask *__restrict__ tasks, const int32_t *_
 	int id = use_ids ? ids[i] : (int)i;
 	const DpTask &t = tasks[id];
 	int cls = fast_ok ? dpf_class(t.qlen, t.tlen, t.w, t.flag, t.skip) : -1;
+	if (cls < 0 && fast_ok) { cls = dpx_class(t.qlen, t.tlen, t.w, t.flag, t.skip); if (cls >= 0) cls += DP_XBASE; }
 	if (cls >= 0 && dpf_task_ambig(t, codes, S, pool)) cls = -1; // ambiguous bases: exact kernel
 	if (cls >= 0) {
 		lists[(int64_t)cls * n + atomicAdd(&ctr[cls], 1)] = id;
@@ -527,7 +536,7 @@ __global__ void k_dp_classify(const DpTask *__restrict__ tasks, const int32_t *_
 	}
 	DpGeom g = dp_geom(t.qlen, t.tlen, t.w);
 	if (t.skip) g.p_bytes = g.ws_bytes = g.h_ints = 0;
-	cls = DPF_NCLASS + dp_exact_class(g.p_bytes);
+	cls = DP_EBASE + dp_exact_class(g.p_bytes);
 	lists[(int64_t)cls * n + atomicAdd(&ctr[cls], 1)] = id;
 	atomicMax(&maxima[cls * 3 + 0], (unsigned long long)g.p_bytes);
 	atomicMax(&maxima[cls * 3 + 1], (unsigned long long)g.ws_bytes);
@@ -537,7 +546,8 @@ __global__ void k_dp_classify(const DpTask *__restrict__ tasks, const int32_t *_
 struct DpRunner {
 	ThreadCtx &c; cudaStream_t st; int64_t *nl;
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evs; // one pair per DP launch, read back after the batch
-	std::vector<int> ev_fast; int64_t n_fast = 0, n_exact = 0;
+	cudaEvent_t ev_base = nullptr;
+	std::vector<int> ev_fast; int64_t n_fast = 0, n_exact = 0, n_ext = 0; // ev_fast: 1 k_dp_fast, 2 k_dp_ext, 0 k_dp
 	DpRunner(ThreadCtx &c_, int64_t *nl_) : c(c_), st(c_.st), nl(nl_) {}
 	~DpRunner() { for (auto &e : evs) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); } }
 	float total_ms(int which = -1) { float t = 0; for (size_t i = 0; i < evs.size(); ++i) { if (which >= 0 && ev_fast[i] != which) continue; float ms = 0; if (cudaEventElapsedTime(&ms, evs[i].first, evs[i].second) == cudaSuccess) t += ms; } return t; }
@@ -554,6 +564,8 @@ struct DpRunner {
 			if (occ < 1) occ = 1;
 		}
 		const size_t stride_words = ((size_t)32 * (size_t)(max_q + 31) * CW + 63) & ~(size_t)63;
+		// leave one CTA slot per SM (registers) to the side-stream kernels (extensions, exact DP) so they co-run instead of
+		// queueing behind a full-occupancy grid
 		int max_cta = c.num_sms * occ;
 		int64_t want = cdiv(cdiv(cnt, 2), DPF_WARPS); // two tasks per warp
 		int n_cta = (int)(want < max_cta ? want : max_cta);
@@ -565,6 +577,32 @@ struct DpRunner {
 		k_dp_fast<C><<<n_cta, DPF_WARPS * 32, 0, st>>>(tasks, list, d_cnt, wc, codes, S, pool, p_scr, stride_words, cigar_pool, sc, d_cells);
 		cudaEventRecord(e1, st);
 		evs.emplace_back(e0, e1); ev_fast.push_back(1); n_fast += cnt;
+		++*nl;
+	}
+
+	template <int C>
+	void launch_ext(DpTask *tasks, const int32_t *list, const int32_t *d_cnt, int64_t cnt, int max_q, const uint8_t *codes, const uint32_t *S, const uint8_t *pool,
+	                uint32_t *cigar_pool, const DpScoring &sc, unsigned long long *d_cells, cudaStream_t st)
+	{
+		Arena &ar = c.ar;
+		constexpr int CW = (C + 1) / 2;
+		static int occ = 0;
+		if (occ == 0) {
+			CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_dp_ext<C>, DPX_WARPS * 32, 0));
+			if (occ < 1) occ = 1;
+		}
+		const size_t stride_words = ((size_t)32 * (size_t)(max_q + 31) * CW + 63) & ~(size_t)63;
+		int max_cta = c.num_sms * (occ < 2 ? occ : 2);   // small side launches: never fill the GPU
+		int64_t want = cdiv(cdiv(cnt, 2), DPX_WARPS);
+		int n_cta = (int)(want < max_cta ? want : max_cta);
+		uint32_t *p_scr = ar.get<uint32_t>((size_t)n_cta * DPX_WARPS * stride_words);
+		int32_t *wc = ar.get<int32_t>(1);
+		CK(cudaMemsetAsync(wc, 0, sizeof(int32_t), st));
+		cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+		cudaEventRecord(e0, st);
+		k_dp_ext<C><<<n_cta, DPX_WARPS * 32, 0, st>>>(tasks, list, d_cnt, wc, codes, S, pool, p_scr, stride_words, cigar_pool, sc, d_cells);
+		cudaEventRecord(e1, st);
+		evs.emplace_back(e0, e1); ev_fast.push_back(2); n_ext += cnt;
 		++*nl;
 	}
 
@@ -584,40 +622,73 @@ struct DpRunner {
 		CK(cudaMemcpyAsync(h_ctr, ctr, sizeof(h_ctr), cudaMemcpyDeviceToHost, st));
 		CK(cudaMemcpyAsync(h_max, maxima, sizeof(h_max), cudaMemcpyDeviceToHost, st));
 		CK(cudaStreamSynchronize(st));
+		if (getenv("MB_DEBUG")) { auto t1 = std::chrono::steady_clock::now(); fprintf(stderr, "[mb]   classify done (+%.3f ms)\n", std::chrono::duration<double, std::milli>(t1 - g_dbg_t0).count()); g_dbg_t0 = t1; }
+		if (getenv("MB_DEBUG") && !ev_base) { cudaEventCreate(&ev_base); cudaEventRecord(ev_base, st); }
 		// the exact kernel goes first, on the high-priority side stream (the host synchronised `st` above, so its inputs are
 		// complete), largest class first: a handful of long band-limited tasks give each launch a long tail of a few busy
 		// warps, which the fast kernels on `st` fill
-		bool side[DP_NEXACT] = {};
+		bool side[MB_NSIDE] = {};
 		for (int b = DP_NEXACT - 1; b >= 0; --b) {
-			const int cls = DPF_NCLASS + b;
-			cudaStream_t st2 = c.st2[b];
+			const int cls = DP_EBASE + b;
+			cudaStream_t st2 = c.st2[b & 1]; // exact classes alternate over side streams 0 and 1
 			int64_t cnt = h_ctr[cls];
 			if (cnt == 0) continue;
+			if (getenv("MB_DEBUG")) fprintf(stderr, "[mb] exact class %d: %lld tasks, max p_bytes %llu, ws_bytes %llu, h_ints %llu\n", b, (long long)cnt, h_max[cls * 3], h_max[cls * 3 + 1], h_max[cls * 3 + 2]);
 			size_t p_stride = ((size_t)h_max[cls * 3 + 0] + 255) & ~(size_t)255;
 			size_t g_stride = ((size_t)h_max[cls * 3 + 1] + 255) & ~(size_t)255;
 			size_t h_stride = ((size_t)h_max[cls * 3 + 2] + 63) & ~(size_t)63;
 			if (p_stride == 0) p_stride = 256;
 			if (h_stride == 0) h_stride = 64;
-			int max_cta = c.num_sms * 6;
-			int64_t want_cta = cdiv(cnt, DP_WARPS);
+			// small tasks: 4 warps per CTA with a 9 KB state slice each; tasks whose state arrays need more get one-warp CTAs
+			// with a slice of up to 96 KB (the state lives in global memory only beyond that)
+			const size_t slice = ((g_stride + 15) & ~(size_t)15) + h_stride * 4 + 64;
+			const bool wide = slice > DP_SMEM_PER_WARP;
+			const int wpc = wide ? 1 : DP_WARPS;
+			const int smem_per_warp = wide ? (int)(slice < DP_SMEM_MAX ? slice : DP_SMEM_MAX) : DP_SMEM_PER_WARP;
+			int max_cta = c.num_sms * (wide ? 2 : 6);
+			int64_t want_cta = cdiv(cnt, wpc);
 			int n_cta = (int)(want_cta < max_cta ? want_cta : max_cta);
 			// bound total scratch to ~24 GB
-			size_t per_warp = p_stride + (g_stride > DP_SMEM_PER_WARP ? g_stride : 0) + h_stride * 4;
+			size_t per_warp = p_stride + g_stride + h_stride * 4;
 			size_t budget = (size_t)24 << 30;
-			while (n_cta > 1 && (size_t)n_cta * DP_WARPS * per_warp > budget) n_cta = (n_cta + 1) / 2;
-			size_t n_warps = (size_t)n_cta * DP_WARPS;
+			while (n_cta > 1 && (size_t)n_cta * wpc * per_warp > budget) n_cta = (n_cta + 1) / 2;
+			size_t n_warps = (size_t)n_cta * wpc;
 			uint8_t *p_scr = ar.get<uint8_t>(n_warps * p_stride);
-			int8_t *g_ws = g_stride > DP_SMEM_PER_WARP ? ar.get<int8_t>(n_warps * g_stride) : ar.get<int8_t>(16);
+			int8_t *g_ws = ar.get<int8_t>(n_warps * g_stride + 16);
 			int32_t *h_scr = ar.get<int32_t>(n_warps * h_stride);
 			int32_t *wc = ar.get<int32_t>(1);
 			CK(cudaMemsetAsync(wc, 0, sizeof(int32_t), st2));
 			cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
 			cudaEventRecord(e0, st2);
-			k_dp<<<n_cta, DP_WARPS * 32, DP_WARPS * DP_SMEM_PER_WARP, st2>>>(tasks, lists + (int64_t)cls * n, ctr + cls, wc, codes, S, pool,
-				p_scr, p_stride, g_ws, g_stride, h_scr, h_stride, cigar_pool, sc, d_cells ? d_cells + 1 : nullptr);
+			k_dp<<<n_cta, wpc * 32, wpc * smem_per_warp, st2>>>(tasks, lists + (int64_t)cls * n, ctr + cls, wc, codes, S, pool,
+				p_scr, p_stride, g_ws, g_stride, h_scr, h_stride, cigar_pool, sc, d_cells ? d_cells + 1 : nullptr, smem_per_warp);
 			cudaEventRecord(e1, st2);
 			evs.emplace_back(e0, e1); ev_fast.push_back(0); n_exact += cnt;
-			++*nl; side[b] = true;
+			++*nl; side[b & 1] = true;
+		}
+		for (int k = 0; k < DPF_NCLASS; ++k) {
+			const int64_t cnt = h_ctr[DP_XBASE + k];
+			if (cnt == 0) continue;
+			const int32_t *list = lists + (int64_t)(DP_XBASE + k) * n;
+			const int mq = (int)h_max[(DP_XBASE + k) * 3];
+			unsigned long long *xc = d_cells ? d_cells + 2 : nullptr;
+			const int si = 2 + (k & 1); // the extension classes are small launches with tails too: side streams 2 and 3
+			cudaStream_t sx = c.st2[si]; side[si] = true;
+			switch (DPF_C[k]) {
+			case 4:  launch_ext<4>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
+			case 5:  launch_ext<5>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
+			case 6:  launch_ext<6>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
+			case 7:  launch_ext<7>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
+			case 8:  launch_ext<8>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
+			case 9:  launch_ext<9>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
+			case 10: launch_ext<10>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
+			case 11: launch_ext<11>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
+			case 12: launch_ext<12>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
+			case 14: launch_ext<14>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
+			case 16: launch_ext<16>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
+			case 20: launch_ext<20>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
+			default: launch_ext<24>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
+			}
 		}
 		for (int k = 0; k < DPF_NCLASS; ++k) {
 			const int64_t cnt = h_ctr[k];
@@ -640,7 +711,7 @@ struct DpRunner {
 			default: launch_fast<24>(tasks, list, ctr + k, cnt, mq, codes, S, pool, cigar_pool, sc, d_cells); break;
 			}
 		}
-		for (int b = 0; b < DP_NEXACT; ++b)
+		for (int b = 0; b < MB_NSIDE; ++b)
 			if (side[b]) { CK(cudaEventRecord(c.ev_join[b], c.st2[b])); CK(cudaStreamWaitEvent(st, c.ev_join[b], 0)); }
 	}
 };
@@ -703,10 +774,10 @@ static mb_hits *map_device(mb_index *ix, const mb_opt_t &opt_in, ThreadCtx &c, c
 	rs.f = ar.get<int32_t>(n_a + 1), rs.p = ar.get<int32_t>(n_a + 1), rs.v = ar.get<int32_t>(n_a + 1), rs.t = ar.get<int32_t>(n_a + 1);
 	rs.b = ar.get<mb128>(n_a + 1); rs.u = ar.get<uint64_t>(n_a + 1); rs.scr = ar.get<uint64_t>(3 * n_a + 3 * (int64_t)n_reads + 3);
 	int32_t *wc = ar.get<int32_t>(4);
-	unsigned long long *d_cells = ar.get<unsigned long long>(3); // chain, DP total, DP exact kernel
+	unsigned long long *d_cells = ar.get<unsigned long long>(4); // chain, k_dp_fast, k_dp, k_dp_ext
 	int *d_err = ar.get<int>(1);
 	CK(cudaMemsetAsync(wc, 0, 4 * sizeof(int32_t), st));
-	CK(cudaMemsetAsync(d_cells, 0, 3 * sizeof(unsigned long long), st));
+	CK(cudaMemsetAsync(d_cells, 0, 4 * sizeof(unsigned long long), st));
 	CK(cudaMemsetAsync(d_err, 0, sizeof(int), st));
 	const int max_chain_gap_ref = opt.max_gap_ref > 0 ? opt.max_gap_ref : opt.max_gap, max_chain_gap_qry = opt.max_gap;
 	if (n_a > 0) {
@@ -748,6 +819,16 @@ static mb_hits *map_device(mb_index *ix, const mb_opt_t &opt_in, ThreadCtx &c, c
 	CK(cudaMemsetAsync(inv_ctr, 0, sizeof(int32_t), st));
 	DpRunner runner(c, &nl);
 	int round = 0;
+	const bool dbg = getenv("MB_DEBUG") != nullptr;
+	auto phase = [&](const char *name) {
+		auto &t0 = g_dbg_t0;
+		if (!dbg) return;
+		cudaStreamSynchronize(st);
+		auto t1 = std::chrono::steady_clock::now();
+		fprintf(stderr, "[mb] phase %-14s %8.3f ms\n", name, std::chrono::duration<double, std::milli>(t1 - t0).count());
+		t0 = t1;
+	};
+	phase("pre-align");
 	while (h_n_work > 0) {
 		++round;
 		const unsigned wb = (unsigned)cdiv(h_n_work, 128);
@@ -762,6 +843,7 @@ static mb_hits *map_device(mb_index *ix, const mb_opt_t &opt_in, ThreadCtx &c, c
 		int32_t *cig_cap = ar.get<int32_t>(n_tasks + 1);
 		int64_t *cig_off = ar.get<int64_t>(n_tasks + 2);
 		k_plan2<<<wb, 128, 0, st>>>(ac, ra, work, h_n_work, plans, task_off, tasks, cig_cap); ++nl;
+		phase("plan1+2");
 		int64_t cig_total = 0;
 		uint32_t *cigar_pool = nullptr;
 		if (n_tasks > 0) {
@@ -771,19 +853,23 @@ static mb_hits *map_device(mb_index *ix, const mb_opt_t &opt_in, ThreadCtx &c, c
 			k_set_cigar_off<<<(unsigned)cdiv(n_tasks, 256), 256, 0, st>>>(tasks, cig_off, n_tasks, (int64_t)((uintptr_t)cigar_pool / 4)); ++nl;
 			cigar_pool = nullptr; // offsets are now absolute word addresses (pools of different rounds coexist)
 			runner.run(tasks, nullptr, n_tasks, false, d_codes, ix->d.S, nullptr, cigar_pool, scoring, d_cells + 1);
+			phase("dp pass 1");
 			// Z-drop test and second pass
 			int32_t *pass2 = ar.get<int32_t>(n_tasks), *n_pass2 = ar.get<int32_t>(1);
 			CK(cudaMemsetAsync(n_pass2, 0, sizeof(int32_t), st));
 			if (!inv_pool) inv_pool = ar.get<int>((size_t)INV_SLOTS * INV_STRIDE);
 			k_ztest<<<(unsigned)cdiv(n_tasks, 128), 128, 0, st>>>(ac, tasks, n_tasks, cigar_pool, pass2, n_pass2, inv_pool, inv_ctr, d_err); ++nl;
 			const int32_t h_pass2 = d2h_scalar(n_pass2, st);
+			phase("ztest");
 			S.n_dp_pass2 += h_pass2;
 			if (h_pass2 > 0) runner.run(tasks, pass2, h_pass2, true, d_codes, ix->d.S, nullptr, cigar_pool, scoring, d_cells + 1);
 		}
 		S.n_dp_tasks += n_tasks;
 		CK(cudaMemsetAsync(n_work + 1, 0, sizeof(int32_t), st));
 		k_stitch<<<wb, 128, 0, st>>>(ac, ra, work, h_n_work, plans, tasks, cigar_pool, work2, n_work + 1, d_err); ++nl;
+		phase("stitch");
 		k_update_extra<<<(unsigned)cdiv((int64_t)h_n_work * 32, 128), 128, 0, st>>>(ac, ra, work, h_n_work, cigar_pool); ++nl;
+		phase("update_extra");
 		h_n_work = d2h_scalar(n_work + 1, st);
 		check_err(d_err, st, "alignment round");
 		std::swap(work, work2);
@@ -809,7 +895,7 @@ static mb_hits *map_device(mb_index *ix, const mb_opt_t &opt_in, ThreadCtx &c, c
 	S.ms_post = tm.stop();
 	S.n_hits = n_h;
 	c.last_fields = d_fields, c.last_hit_off = hit_off, c.last_read_off = d_off, c.last_n_hits = n_h, c.last_n_reads = n_reads, c.last_index = ix;
-	unsigned long long h_cells[3];
+	unsigned long long h_cells[4];
 	CK(cudaMemcpyAsync(h_cells, d_cells, sizeof(h_cells), cudaMemcpyDeviceToHost, st));
 	tm.start();
 	H->n = n_h;
@@ -826,11 +912,13 @@ static mb_hits *map_device(mb_index *ix, const mb_opt_t &opt_in, ThreadCtx &c, c
 	CK(cudaStreamSynchronize(st));
 	CK(cudaGetLastError());
 	S.ms_d2h = tm.stop();
-	S.dp_cells = (int64_t)(h_cells[1] + h_cells[2]); S.dp_cells_exact = (int64_t)h_cells[2]; S.chain_cells = (int64_t)h_cells[0];
+	S.dp_cells = (int64_t)(h_cells[1] + h_cells[2] + h_cells[3]); S.dp_cells_exact = (int64_t)h_cells[2]; S.dp_cells_ext = (int64_t)h_cells[3]; S.chain_cells = (int64_t)h_cells[0];
 	S.n_launches = nl;
+	if (dbg) for (size_t i = 0; i < runner.evs.size(); ++i) { float ms = 0; cudaEventElapsedTime(&ms, runner.evs[i].first, runner.evs[i].second); float a = 0, b = 0; if (runner.ev_base) { cudaEventElapsedTime(&a, runner.ev_base, runner.evs[i].first); cudaEventElapsedTime(&b, runner.ev_base, runner.evs[i].second); } fprintf(stderr, "[mb] dp launch %2zu kind %d  %8.3f ms  [%8.3f .. %8.3f]\n", i, runner.ev_fast[i], ms, a, b); }
 	S.ms_kdp = runner.total_ms(); S.n_kdp = (int32_t)runner.evs.size();
-	{ int64_t nf = 0; for (int f : runner.ev_fast) nf += f; S.n_kdp_fast = nf; }
+	{ int64_t nf = 0; for (int f : runner.ev_fast) nf += (f == 1); S.n_kdp_fast = nf; }
 	S.ms_kdp_fast = runner.total_ms(1); S.ms_kdp_exact = runner.total_ms(0); S.n_fast_tasks = runner.n_fast; S.n_exact_tasks = runner.n_exact;
+	S.ms_kdp_ext = runner.total_ms(2); S.n_ext_tasks = runner.n_ext;
 	S.ms_total = tall.stop();
 	if (stats) { float h2d = stats->ms_h2d; *stats = S; stats->ms_h2d = h2d; }
 	return H.release();

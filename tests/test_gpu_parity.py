@@ -230,12 +230,29 @@ def test_dp_fast_path_pairs(oracle, lib):
                 q = q[:750]
             if max(len(q), tl) > 752:
                 continue
-            ez = oracle.ksw_extd2(q, t, w=751, zdrop=400, end_bonus=-1, flag=0x08)
-            recs.append(dict(qlen=len(q), tlen=tl, w=751, zdrop=400, end_bonus=-1, flag=0x08, q=q, t=t, score=ez["score"], max=ez["max"],
-                             max_q=ez["max_q"], max_t=ez["max_t"], mqe=ez["mqe"], mqe_t=ez["mqe_t"], zdropped=ez["zdropped"],
-                             reach_end=ez["reach_end"], n_cigar=len(ez["cigar"]), cigar=ez["cigar"]))
+            variants = [(0x08, 400, -1)]
+            # end extensions (k_dp_ext): right and left (gaps right-aligned, reversed CIGAR), Z-drop 400 / 200, end bonus;
+            # a junk tail on the query makes the score collapse so that the Z-drop break and max tracking matter
+            if rep != 1 or tl % 11:
+                qx = q
+                if kind in (1, 2) and len(q) + 60 <= 752:
+                    qx = np.concatenate([q, rng.integers(0, 4, int(rng.integers(20, 60))).astype(np.uint8)])
+                if kind == 0 and len(q) > 120:
+                    qx = np.concatenate([q[:len(q) // 2], rng.integers(0, 4, len(q) - len(q) // 2).astype(np.uint8)])
+                for flag, zd, eb in ((0x40, 400, -1), (0x40 | 0x02 | 0x80, 400, -1), (0x40, 200, 10), (0x40 | 0x02 | 0x80, 100, 5)):
+                    ez = oracle.ksw_extd2(qx, t, w=751, zdrop=zd, end_bonus=eb, flag=flag)
+                    recs.append(dict(qlen=len(qx), tlen=tl, w=751, zdrop=zd, end_bonus=eb, flag=flag, q=qx, t=t, score=ez["score"], max=ez["max"],
+                                     max_q=ez["max_q"], max_t=ez["max_t"], mqe=ez["mqe"], mqe_t=ez["mqe_t"], zdropped=ez["zdropped"],
+                                     reach_end=ez["reach_end"], n_cigar=len(ez["cigar"]), cigar=ez["cigar"]))
+            for flag, zd, eb in variants:
+                ez = oracle.ksw_extd2(q, t, w=751, zdrop=zd, end_bonus=eb, flag=flag)
+                recs.append(dict(qlen=len(q), tlen=tl, w=751, zdrop=zd, end_bonus=eb, flag=flag, q=q, t=t, score=ez["score"], max=ez["max"],
+                                 max_q=ez["max_q"], max_t=ez["max_t"], mqe=ez["mqe"], mqe_t=ez["mqe_t"], zdropped=ez["zdropped"],
+                                 reach_end=ez["reach_end"], n_cigar=len(ez["cigar"]), cigar=ez["cigar"]))
     if len(recs) % 2 == 0:
         recs.pop()
+    assert sum(1 for r in recs if r["flag"] & 0x40 and r["zdropped"]) > 5 and sum(1 for r in recs if r["flag"] & 0x40 and not r["zdropped"]) > 5
+    assert any(r["reach_end"] for r in recs)
     tasks, cig = _run_dp(lib, opt, recs)
     _check_dp(tasks, cig, recs)
 
