@@ -57,6 +57,8 @@ static __host__ __device__ inline bool dpf_scoring_ok(const DpScoring &sc)
 }
 
 MB_D uint32_t dpf_pack2(int v) { return (uint32_t)(uint16_t)(int16_t)v * 0x10001u; }
+MB_D uint32_t dpf_and(uint32_t a, uint32_t b) { uint32_t d; asm("and.b32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+MB_D uint32_t dpf_mad(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
 // PRMT in its default mode: selector nibble bit 3 replicates the sign of the selected byte (used to produce zero bytes)
 MB_D uint32_t dpf_prmt(uint32_t a, uint32_t b, uint32_t sel) { uint32_t d; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel)); return d; }
 
@@ -112,7 +114,7 @@ k_dp_fast(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 	const uint32_t NFL1 = dpf_pack2(-(8 * (-q - e + B) + 3)), NFL2 = dpf_pack2(-(8 * (-q - e + B) + 2));
 	const uint32_t NFL3 = dpf_pack2(-(8 * (-q2 - e2 + B) + 1)), NFL4 = dpf_pack2(-(8 * (-q2 - e2 + B) + 0));
 	const uint32_t K1 = 0x00010000u + dpf_pack2(8 * (B - e)), K2 = 0x00010000u + dpf_pack2(8 * (B - e2));
-	const uint32_t EIGHT = 0x00080008u;
+	const uint32_t EIGHT = dpf_pack2(8 + sc.pad);   // sc.pad == 0: a run-time value stays in a register instead of being re-materialised per use
 	const uint32_t MCHB = (uint32_t)(8 * (sc.sc_mch + 2 * B) + 4), MISB = (uint32_t)(8 * (sc.sc_mis + 2 * B) + 4), NB = (uint32_t)(8 * (sc.sc_N + 2 * B) + 4);
 	const uint32_t MIS4 = MISB * 0x01010101u, N4 = NB * 0x01010101u, MDIFF = MCHB - MISB;
 	for (;;) {
@@ -177,7 +179,7 @@ k_dp_fast(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 					const uint32_t z0 = dpf_prmt(LA, LB, SEL[c]);
 					const uint32_t a = __vadd2(XL, VL), b = __vadd2(Y[c], U[c]), a2 = __vadd2(X2L, VL), b2 = __vadd2(Y2[c], U[c]);
 					const uint32_t zt = __vimax3_s16x2(__vimax3_s16x2(z0, a, b), a2, b2);
-					const uint32_t zc = zt & 0xfff8fff8u;
+					const uint32_t zc = dpf_and(zt, 0xfff8fff8u);          // opaque: keeps `zt - zc` a subtraction (FMA pipe) instead of a 2nd LOP3
 					const uint32_t un = zc - VL, vn = zc - U[c];          // halves are non-negative: no borrow
 					// per-half D - zc: the low half always borrows (zc > D, checked on the host), which the 0x10000 pays back
 					const uint32_t nz1 = K1 - zc, nz2 = K2 - zc;
@@ -185,7 +187,8 @@ k_dp_fast(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 					const uint32_t r3 = __viaddmax_s16x2(a2, nz2, FL3), r4 = __viaddmax_s16x2(b2, nz2, FL4);
 					const uint32_t g1 = __viaddmin_s16x2(r1, NFL1, EIGHT), g2 = __viaddmin_s16x2(r2, NFL2, EIGHT);
 					const uint32_t g3 = __viaddmin_s16x2(r3, NFL3, EIGHT), g4 = __viaddmin_s16x2(r4, NFL4, EIGHT);
-					const uint32_t wd = (zt - zc) + g1 + 2u * g2 + 4u * g3 + 8u * g4; // tag | x-cont 0x08 | y-cont 0x10 | x2-cont 0x20 | y2-cont 0x40
+					// tag | x-cont 0x08 | y-cont 0x10 | x2-cont 0x20 | y2-cont 0x40, as a chain of 2-input multiply-adds (FMA pipe)
+					const uint32_t wd = dpf_mad(g4, 8u, dpf_mad(g3, 4u, dpf_mad(g2, 2u, g1 + (zt - zc))));
 					XL = r1, X2L = r3, Y[c] = r2, Y2[c] = r4, U[c] = un, VL = vn;
 					if (c & 1) wv[c >> 1] = dpf_prmt(wprev, wd, 0x6240u);        // bytes A:c-1 A:c B:c-1 B:c
 					else if (c == C - 1) wv[c >> 1] = dpf_prmt(wd, 0u, 0x6240u);
