@@ -251,19 +251,26 @@ k_dp_fast(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 				};
 				while (i >= 0 && jj >= 0) {
 					const int ci = i - hl, cj = jj - hl;
-					uint32_t raw = 0;
+					uint32_t raw = 0xffu; // off the matrix: not a match, stops a run
 					if (ci >= 0 && cj >= 0) {
 						const int L = ci / C, c = ci - L * C;
 						raw = Pb[((((size_t)(cj + L)) * 32 + L) * CW + (c >> 1)) * 4 + (c & 1)];
 					}
-					for (int k = 0; k < 16 && i >= 0 && jj >= 0; ++k) {
+					int k = 0;
+					if (state == 0) { // a run of diagonal moves is consumed at once: leading cells whose direction is "match"
+						const unsigned stop = (__ballot_sync(gmask, (raw & 7u) != 4u) >> (grp << 4)) & 0xffffu;
+						k = stop ? __ffs(stop) - 1 : 16;
+						if (k) { push(0, k); i -= k, jj -= k; }
+					}
+					if (k < 16 && i >= 0 && jj >= 0) { // one general step of ksw_backtrack on the next fetched cell
 						const uint32_t rk = __shfl_sync(gmask, raw, (grp << 4) + k);
 						const uint32_t tmp = (4u - (rk & 7u)) | (rk & 0x78u);
 						if (state == 0) state = tmp & 7;
 						else if (!(tmp >> (state + 2) & 1)) state = 0;
 						if (state == 0) state = tmp & 7;
 						if (state == 0) { push(0, 1); --i, --jj; }
-						else { if (state == 1 || state == 3) { push(2, 1); --i; } else { push(1, 1); --jj; } break; } // left the diagonal
+						else if (state == 1 || state == 3) { push(2, 1); --i; }
+						else { push(1, 1); --jj; }
 					}
 				}
 				if (i >= 0) push(2, i + 1);
