@@ -70,14 +70,21 @@ struct ThreadCtx {
 	// kernels.  Few of them on purpose: streams beyond the device's hardware queues (8 by default) alias and serialise.
 	cudaStream_t st2[MB_NSIDE] = {};
 	cudaEvent_t ev_join[MB_NSIDE] = {};
+	cudaEvent_t ev_fast_done = nullptr;   // recorded behind the last k_dp_fast launch of a DpRunner::run
 	Arena ar;
 	int num_sms = 148;
 	uint8_t *h_pin = nullptr; size_t h_pin_cap = 0;   // pinned staging for reads
 	unsigned long long *d_counts = nullptr; int n_counts = 0; // last mb_count vector
-	// device-resident result of the last mapping call (lives in the arena until the next reset)
-	const int32_t *last_fields = nullptr; const int64_t *last_hit_off = nullptr, *last_read_off = nullptr;
-	int64_t last_n_hits = 0; int32_t last_n_reads = -1; const void *last_index = nullptr;
+	// device-resident result of the last mapping call, one entry per sub-batch (lives in the arenas until the next reset)
+	struct LastPart { const int32_t *fields; const int64_t *hit_off, *read_off; int64_t n_hits; int32_t n_reads; };
+	std::vector<LastPart> last_parts;
+	int32_t last_n_reads = -1; const void *last_index = nullptr;
+	// helper contexts (own stream + arena) for the other sub-batches of a call: a batch is cut in MB_NPART pieces that run
+	// concurrently, so the latency-bound stages of one piece (sketch, seeding, chaining, region logic, stitching) hide under
+	// the issue-bound DP kernels of the other
+	std::vector<ThreadCtx*> helpers;
 	~ThreadCtx() {
+		for (ThreadCtx *h : helpers) delete h;
 		if (device >= 0) {
 			cudaSetDevice(device);
 			ar.release();
@@ -85,6 +92,7 @@ struct ThreadCtx {
 			if (d_counts) cudaFree(d_counts);
 			if (st) cudaStreamDestroy(st);
 			for (int i = 0; i < MB_NSIDE; ++i) { if (st2[i]) cudaStreamDestroy(st2[i]); if (ev_join[i]) cudaEventDestroy(ev_join[i]); }
+			if (ev_fast_done) cudaEventDestroy(ev_fast_done);
 		}
 	}
 };
@@ -100,18 +108,28 @@ static void ensure_device(int device)
 }
 
 static std::once_flag g_const_once[16];
+static std::mutex g_dp_mutex[16];   // per device: serialises the DP stage of concurrent pieces / calling threads
 
+static ThreadCtx *make_ctx(int device);
 static ThreadCtx &get_ctx(int device)
 {
 	ensure_device(device);
 	auto it = t_ctx.find(device);
 	if (it != t_ctx.end()) return *it->second;
+	ThreadCtx *c = make_ctx(device);
+	t_ctx[device] = c;
+	return *c;
+}
+
+static ThreadCtx *make_ctx(int device)
+{
 	ThreadCtx *c = new ThreadCtx();
 	c->device = device;
 	CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
 	{
 		int lo = 0, hi = 0;
 		CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+		CK(cudaEventCreateWithFlags(&c->ev_fast_done, cudaEventDisableTiming));
 		for (int i = 0; i < MB_NSIDE; ++i) {
 			CK(cudaStreamCreateWithPriority(&c->st2[i], cudaStreamNonBlocking, hi));
 			CK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
@@ -124,8 +142,7 @@ static ThreadCtx &get_ctx(int device)
 		CK(cudaMemcpyToSymbol(c_nt4, h_nt4, 256));
 		CK(cudaFuncSetAttribute(k_dp, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM_MAX));
 	});
-	t_ctx[device] = c;
-	return *c;
+	return c;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -436,13 +453,63 @@ struct mb_reads {
 	uint8_t *d_codes = nullptr; int64_t *d_off = nullptr;
 };
 
+// Result arrays live in PINNED host memory so the device->host copies of a batch (hundreds of MB of CIGARs at the bench
+// size) run at PCIe speed; the buffers come from a process-wide pool and go back to it in mb_hits_free, so a steady stream
+// of batches allocates nothing.
+struct PinPool {
+	std::mutex m;
+	std::vector<std::pair<void*, size_t>> free_list;
+	void *get(size_t bytes, size_t *cap) {
+		if (bytes == 0) bytes = 1;
+		{
+			std::lock_guard<std::mutex> g(m);
+			int best = -1;
+			for (int i = 0; i < (int)free_list.size(); ++i)
+				if (free_list[i].second >= bytes && (best < 0 || free_list[i].second < free_list[best].second)) best = i;
+			if (best >= 0) { void *p = free_list[best].first; *cap = free_list[best].second; free_list.erase(free_list.begin() + best); return p; }
+		}
+		size_t c = (bytes + (bytes >> 3) + 4095) & ~(size_t)4095; // a little headroom: the next batch is rarely identical
+		void *p = nullptr;
+		if (cudaHostAlloc(&p, c, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); throw mb_error(MB_ERR_NOMEM, "cudaHostAlloc failed for " + std::to_string(c) + " bytes"); }
+		*cap = c;
+		return p;
+	}
+	void put(void *p, size_t cap) {
+		if (!p) return;
+		std::lock_guard<std::mutex> g(m);
+		if (free_list.size() >= 24) { // keep the pool bounded: drop the smallest buffer
+			int small = 0;
+			for (int i = 1; i < (int)free_list.size(); ++i) if (free_list[i].second < free_list[small].second) small = i;
+			if (free_list[small].second < cap) { cudaFreeHost(free_list[small].first); free_list[small] = std::make_pair(p, cap); }
+			else cudaFreeHost(p);
+			return;
+		}
+		free_list.emplace_back(p, cap);
+	}
+};
+static PinPool g_pin_pool;
+
+template <typename T> struct PinVec {
+	T *p = nullptr; size_t n = 0, cap = 0;
+	PinVec() {}
+	PinVec(const PinVec&) = delete; PinVec &operator=(const PinVec&) = delete;
+	~PinVec() { g_pin_pool.put(p, cap); }
+	void resize(size_t k) { // contents are NOT preserved or initialised
+		if (k * sizeof(T) > cap) { g_pin_pool.put(p, cap); p = nullptr; cap = 0; p = (T*)g_pin_pool.get(k * sizeof(T), &cap); }
+		n = k;
+	}
+	void assign(size_t k, T v) { resize(k); for (size_t i = 0; i < k; ++i) p[i] = v; }
+	T *data() { return p; } const T *data() const { return p; }
+	size_t size() const { return n; }
+};
+
 struct mb_hits {
 	int64_t n = 0; int32_t n_reads = 0;
-	std::vector<int32_t> fields;        // HIT_NF * n
-	std::vector<int64_t> cigar_off;
-	std::vector<uint32_t> cigar;
-	std::vector<int32_t> rep_len;
-	std::vector<int64_t> hit_off;       // [n_reads+1]
+	PinVec<int32_t> fields;             // HIT_NF * n
+	PinVec<int64_t> cigar_off;
+	PinVec<uint32_t> cigar;
+	PinVec<int32_t> rep_len;
+	PinVec<int64_t> hit_off;            // [n_reads+1]
 	std::vector<int64_t> read_off;      // [n_reads+1] (for mb_count's query_length mode)
 };
 
@@ -711,6 +778,7 @@ struct DpRunner {
 			default: launch_fast<24>(tasks, list, ctr + k, cnt, mq, codes, S, pool, cigar_pool, sc, d_cells); break;
 			}
 		}
+		CK(cudaEventRecord(c.ev_fast_done, st));
 		for (int b = 0; b < MB_NSIDE; ++b)
 			if (side[b]) { CK(cudaEventRecord(c.ev_join[b], c.st2[b])); CK(cudaStreamWaitEvent(st, c.ev_join[b], 0)); }
 	}
@@ -737,25 +805,34 @@ static void check_err(int *d_err, cudaStream_t st, const char *where)
 	if (e) throw mb_error(MB_ERR_OVERFLOW, std::string(where) + ": device error flag");
 }
 
-static mb_hits *map_device(mb_index *ix, const mb_opt_t &opt_in, ThreadCtx &c, const uint8_t *d_codes, const int64_t *d_off, const int64_t *h_off,
-                           int32_t n_reads, int64_t total, bool want_hits, mb_stats_t *stats)
+// device-resident result of one sub-batch (arrays live in the arena of `c` until its next reset)
+struct DevPart {
+	ThreadCtx *c = nullptr;
+	int32_t read_lo = 0, n_reads = 0;
+	const uint8_t *d_codes = nullptr; const int64_t *d_off = nullptr; int64_t total = 0;
+	int32_t *d_fields = nullptr; int64_t *d_hcoff = nullptr; uint32_t *d_hcig = nullptr; int64_t *d_hit_off = nullptr; int32_t *d_rep_len = nullptr;
+	int64_t n_h = 0, n_c = 0;
+	mb_stats_t S;
+	std::exception_ptr err;
+};
+
+// the whole device pipeline of one sub-batch on the stream / arena of `c`; synchronises c.st before returning
+static void map_device_part(mb_index *ix, const mb_opt_t &opt_in, DevPart &part)
 {
+	ThreadCtx &c = *part.c;
+	const uint8_t *d_codes = part.d_codes; const int64_t *d_off = part.d_off;
+	const int32_t n_reads = part.n_reads; const int64_t total = part.total;
 	cudaStream_t st = c.st;
 	Arena &ar = c.ar;
 	mb_opt_t opt = opt_in;
 	if (opt.mid_occ <= 0) opt.mid_occ = ix->mid_occ;
 	if (opt.q + opt.e >= 127 || opt.q2 + opt.e2 >= 127) throw mb_error(MB_ERR_ARG, "gap costs too large for int8 DP");
-	mb_stats_t S; memset(&S, 0, sizeof(S));
+	mb_stats_t &S = part.S; memset(&S, 0, sizeof(S));
 	S.n_reads = n_reads, S.n_bases = total;
 	int64_t nl = 0;
 	Timer tm(st), tall(st);
 	tall.start();
-	std::unique_ptr<mb_hits> H(new mb_hits());
-	H->n_reads = n_reads;
-	H->read_off.assign(h_off, h_off + n_reads + 1);
-	H->hit_off.assign(n_reads + 1, 0);
-	H->rep_len.assign(n_reads, 0);
-	if (n_reads == 0) { if (stats) *stats = S; return H.release(); }
+	if (n_reads == 0) return;
 
 	// K1
 	tm.start();
@@ -852,7 +929,12 @@ static mb_hits *map_device(mb_index *ix, const mb_opt_t &opt_in, ThreadCtx &c, c
 			cigar_pool = ar.get<uint32_t>(cig_total + 1);
 			k_set_cigar_off<<<(unsigned)cdiv(n_tasks, 256), 256, 0, st>>>(tasks, cig_off, n_tasks, (int64_t)((uintptr_t)cigar_pool / 4)); ++nl;
 			cigar_pool = nullptr; // offsets are now absolute word addresses (pools of different rounds coexist)
+			// One piece at a time in the (issue-bound) DP kernels; the other pieces meanwhile run their latency-bound stages
+			// (sketch, seeding, chaining, region logic before; stitching, mm_update_extra, finalisation after) underneath.
+			std::unique_lock<std::mutex> dp_token(g_dp_mutex[c.device & 15]);
 			runner.run(tasks, nullptr, n_tasks, false, d_codes, ix->d.S, nullptr, cigar_pool, scoring, d_cells + 1);
+			CK(cudaEventSynchronize(c.ev_fast_done)); // the long-tailed side-stream launches of this piece may still be running
+			dp_token.unlock();
 			phase("dp pass 1");
 			// Z-drop test and second pass
 			int32_t *pass2 = ar.get<int32_t>(n_tasks), *n_pass2 = ar.get<int32_t>(1);
@@ -894,24 +976,12 @@ static mb_hits *map_device(mb_index *ix, const mb_opt_t &opt_in, ThreadCtx &c, c
 	k_write_hits<<<rb, 128, 0, st>>>(ra, n_reads, hit_off, hcig_off, n_h, d_fields, d_hcoff, (const uint32_t*)nullptr, d_hcig); ++nl;
 	S.ms_post = tm.stop();
 	S.n_hits = n_h;
-	c.last_fields = d_fields, c.last_hit_off = hit_off, c.last_read_off = d_off, c.last_n_hits = n_h, c.last_n_reads = n_reads, c.last_index = ix;
+	part.d_fields = d_fields, part.d_hcoff = d_hcoff, part.d_hcig = d_hcig, part.d_hit_off = hit_off, part.d_rep_len = sd.rep_len;
+	part.n_h = n_h, part.n_c = n_c;
 	unsigned long long h_cells[4];
 	CK(cudaMemcpyAsync(h_cells, d_cells, sizeof(h_cells), cudaMemcpyDeviceToHost, st));
-	tm.start();
-	H->n = n_h;
-	if (want_hits) {
-		H->fields.resize((size_t)HIT_NF * n_h); H->cigar_off.resize(n_h); H->cigar.resize(n_c);
-		if (n_h) {
-			CK(cudaMemcpyAsync(H->fields.data(), d_fields, (size_t)HIT_NF * n_h * 4, cudaMemcpyDeviceToHost, st));
-			CK(cudaMemcpyAsync(H->cigar_off.data(), d_hcoff, n_h * 8, cudaMemcpyDeviceToHost, st));
-		}
-		if (n_c) CK(cudaMemcpyAsync(H->cigar.data(), d_hcig, n_c * 4, cudaMemcpyDeviceToHost, st));
-		CK(cudaMemcpyAsync(H->rep_len.data(), sd.rep_len, n_reads * 4, cudaMemcpyDeviceToHost, st));
-		CK(cudaMemcpyAsync(H->hit_off.data(), hit_off, (n_reads + 1) * 8, cudaMemcpyDeviceToHost, st));
-	}
 	CK(cudaStreamSynchronize(st));
 	CK(cudaGetLastError());
-	S.ms_d2h = tm.stop();
 	S.dp_cells = (int64_t)(h_cells[1] + h_cells[2] + h_cells[3]); S.dp_cells_exact = (int64_t)h_cells[2]; S.dp_cells_ext = (int64_t)h_cells[3]; S.chain_cells = (int64_t)h_cells[0];
 	S.n_launches = nl;
 	if (dbg) for (size_t i = 0; i < runner.evs.size(); ++i) { float ms = 0; cudaEventElapsedTime(&ms, runner.evs[i].first, runner.evs[i].second); float a = 0, b = 0; if (runner.ev_base) { cudaEventElapsedTime(&a, runner.ev_base, runner.evs[i].first); cudaEventElapsedTime(&b, runner.ev_base, runner.evs[i].second); } fprintf(stderr, "[mb] dp launch %2zu kind %d  %8.3f ms  [%8.3f .. %8.3f]\n", i, runner.ev_fast[i], ms, a, b); }
@@ -920,6 +990,125 @@ static mb_hits *map_device(mb_index *ix, const mb_opt_t &opt_in, ThreadCtx &c, c
 	S.ms_kdp_fast = runner.total_ms(1); S.ms_kdp_exact = runner.total_ms(0); S.n_fast_tasks = runner.n_fast; S.n_exact_tasks = runner.n_exact;
 	S.ms_kdp_ext = runner.total_ms(2); S.n_ext_tasks = runner.n_ext;
 	S.ms_total = tall.stop();
+}
+
+__global__ void k_rebase_offsets(const int64_t *__restrict__ src, int64_t *__restrict__ dst, int64_t n, int64_t base)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) dst[i] = src[i] - base;
+}
+
+#define MB_NPART_MAX 4
+static int mb_n_parts(int32_t n_reads, int64_t total)
+{
+	const char *e = getenv("MB_PARTS"); // number of concurrent pieces (default 1: measured on B200, 2-4 pieces lose more to smaller launches than they hide); MB_PARTS_MIN_READS lowers the size gate (tests)
+	int conf = e ? atoi(e) : 1; if (conf < 1) conf = 1; if (conf > MB_NPART_MAX) conf = MB_NPART_MAX;
+	const char *m = getenv("MB_PARTS_MIN_READS");
+	const int64_t min_reads = m ? atoll(m) : 1024;
+	if (n_reads < min_reads * conf || (!m && total < ((int64_t)4 << 20) * conf)) return 1; // small batches: one piece
+	return conf;
+}
+
+// Map a device-resident batch.  The batch is cut (at read boundaries, by cumulative bases) into pieces that run
+// concurrently on their own streams / arenas / host threads; results are concatenated in read order, so the outcome does
+// not depend on the number of pieces.
+static mb_hits *map_device(mb_index *ix, const mb_opt_t &opt, ThreadCtx &c, const uint8_t *d_codes, const int64_t *d_off, const int64_t *h_off,
+                           int32_t n_reads, int64_t total, bool want_hits, mb_stats_t *stats)
+{
+	auto t_begin = std::chrono::steady_clock::now();
+	std::unique_ptr<mb_hits> H(new mb_hits());
+	H->n_reads = n_reads;
+	H->read_off.assign(h_off, h_off + n_reads + 1);
+	H->hit_off.assign(n_reads + 1, 0);
+	H->rep_len.assign(n_reads, 0);
+	mb_stats_t S; memset(&S, 0, sizeof(S));
+	S.n_reads = n_reads, S.n_bases = total;
+	c.last_parts.clear(); c.last_n_reads = n_reads; c.last_index = ix;
+	if (n_reads == 0) { if (stats) *stats = S; return H.release(); }
+	const int K = mb_n_parts(n_reads, total);
+	while ((int)c.helpers.size() < K - 1) c.helpers.push_back(make_ctx(c.device));
+	std::vector<DevPart> parts(K);
+	// cut points: first read whose start offset reaches the k-th share of the bases
+	std::vector<int32_t> cut(K + 1, 0);
+	cut[K] = n_reads;
+	for (int k = 1; k < K; ++k) {
+		const int64_t target = total / K * k;
+		int32_t i = (int32_t)(std::lower_bound(h_off, h_off + n_reads, target) - h_off);
+		cut[k] = std::max(cut[k - 1], std::min(i, n_reads));
+	}
+	CK(cudaStreamSynchronize(c.st)); // the reads (and anything else queued by the caller) are complete before other streams read them
+	for (int k = 0; k < K; ++k) {
+		DevPart &p = parts[k];
+		p.c = k == 0 ? &c : c.helpers[k - 1];
+		p.read_lo = cut[k], p.n_reads = cut[k + 1] - cut[k];
+		const int64_t base = h_off[cut[k]] & ~(int64_t)15; // keep the piece's code pointer 16-byte aligned (vector loads); its first
+		p.total = h_off[cut[k + 1]] - base;                 // read then starts at offset 0..15 instead of 0
+		p.d_codes = d_codes + base;
+		if (k > 0) p.c->ar.reset();
+		if (K == 1) p.d_off = d_off;
+		else {
+			int64_t *o = p.c->ar.get<int64_t>(p.n_reads + 1);
+			k_rebase_offsets<<<(unsigned)cdiv(p.n_reads + 1, 256), 256, 0, p.c->st>>>(d_off + cut[k], o, p.n_reads + 1, base);
+			p.d_off = o;
+		}
+	}
+	auto run_part = [&](int k) {
+		try { CK(cudaSetDevice(c.device)); map_device_part(ix, opt, parts[k]); }
+		catch (...) { parts[k].err = std::current_exception(); }
+	};
+	{
+		std::vector<std::thread> th;
+		for (int k = 1; k < K; ++k) th.emplace_back(run_part, k);
+		run_part(0);
+		for (auto &t : th) t.join();
+	}
+	for (int k = 0; k < K; ++k) if (parts[k].err) { for (int j = 0; j < K; ++j) cudaStreamSynchronize(parts[j].c->st); std::rethrow_exception(parts[k].err); }
+	// ---- assemble ----
+	int64_t n_h = 0, n_c = 0;
+	std::vector<int64_t> hbase(K), cbase(K);
+	for (int k = 0; k < K; ++k) { hbase[k] = n_h, cbase[k] = n_c; n_h += parts[k].n_h; n_c += parts[k].n_c; }
+	H->n = n_h;
+	Timer tm(c.st); tm.start();
+	if (want_hits) {
+		H->fields.resize((size_t)HIT_NF * n_h); H->cigar_off.resize(n_h); H->cigar.resize(n_c);
+		for (int k = 0; k < K; ++k) {
+			const DevPart &p = parts[k];
+			cudaStream_t st = p.c->st;
+			for (int f = 0; f < HIT_NF && p.n_h; ++f)
+				CK(cudaMemcpyAsync(H->fields.data() + (size_t)f * n_h + hbase[k], p.d_fields + (size_t)f * p.n_h, (size_t)p.n_h * 4, cudaMemcpyDeviceToHost, st));
+			if (p.n_h) CK(cudaMemcpyAsync(H->cigar_off.data() + hbase[k], p.d_hcoff, (size_t)p.n_h * 8, cudaMemcpyDeviceToHost, st));
+			if (p.n_c) CK(cudaMemcpyAsync(H->cigar.data() + cbase[k], p.d_hcig, (size_t)p.n_c * 4, cudaMemcpyDeviceToHost, st));
+			if (p.n_reads) {
+				CK(cudaMemcpyAsync(H->rep_len.data() + p.read_lo, p.d_rep_len, (size_t)p.n_reads * 4, cudaMemcpyDeviceToHost, st));
+				CK(cudaMemcpyAsync(H->hit_off.data() + p.read_lo, p.d_hit_off, (size_t)(p.n_reads + (k == K - 1 ? 1 : 0)) * 8, cudaMemcpyDeviceToHost, st));
+			}
+		}
+		for (int k = 0; k < K; ++k) CK(cudaStreamSynchronize(parts[k].c->st));
+		for (int k = 1; k < K; ++k) { // piece-relative indices -> batch indices
+			const DevPart &p = parts[k];
+			int32_t *ridx = H->fields.data() + hbase[k];
+			for (int64_t i = 0; i < p.n_h; ++i) ridx[i] += p.read_lo;
+			int64_t *co = H->cigar_off.data() + hbase[k];
+			for (int64_t i = 0; i < p.n_h; ++i) co[i] += cbase[k];
+			int64_t *ho = H->hit_off.data() + p.read_lo;
+			for (int32_t i = 0; i < p.n_reads + (k == K - 1 ? 1 : 0); ++i) ho[i] += hbase[k];
+		}
+	}
+	CK(cudaGetLastError());
+	S.ms_d2h = tm.stop();
+	for (int k = 0; k < K; ++k) {
+		const DevPart &p = parts[k];
+		ThreadCtx::LastPart lp; lp.fields = p.d_fields, lp.hit_off = p.d_hit_off, lp.read_off = p.d_off, lp.n_hits = p.n_h, lp.n_reads = p.n_reads;
+		c.last_parts.push_back(lp);
+		const mb_stats_t &q = p.S;
+		S.n_mini += q.n_mini, S.n_anchor += q.n_anchor, S.n_regs += q.n_regs, S.n_dp_tasks += q.n_dp_tasks, S.n_dp_pass2 += q.n_dp_pass2;
+		S.dp_cells += q.dp_cells, S.n_hits += q.n_hits, S.n_rounds = std::max(S.n_rounds, q.n_rounds), S.n_launches += q.n_launches;
+		S.ms_sketch += q.ms_sketch, S.ms_seed += q.ms_seed, S.ms_sort += q.ms_sort, S.ms_chain += q.ms_chain, S.ms_glue += q.ms_glue;
+		S.ms_dp += q.ms_dp, S.ms_post += q.ms_post, S.ms_kdp += q.ms_kdp, S.n_kdp += q.n_kdp, S.ms_kdp_fast += q.ms_kdp_fast, S.ms_kdp_exact += q.ms_kdp_exact;
+		S.n_fast_tasks += q.n_fast_tasks, S.n_exact_tasks += q.n_exact_tasks, S.chain_cells += q.chain_cells, S.dp_cells_exact += q.dp_cells_exact;
+		S.n_kdp_fast += q.n_kdp_fast, S.n_ext_tasks += q.n_ext_tasks, S.dp_cells_ext += q.dp_cells_ext, S.ms_kdp_ext += q.ms_kdp_ext;
+	}
+	S.ms_total = (float)std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
 	if (stats) { float h2d = stats->ms_h2d; *stats = S; stats->ms_h2d = h2d; }
 	return H.release();
 }
@@ -1037,15 +1226,16 @@ extern "C" int mb_count_last(mb_index_t *ix, int32_t mapq_min, int mode, int64_t
 	ThreadCtx &c = get_ctx(ix->device);
 	if (c.last_index != ix || c.last_n_reads < 0) throw mb_error(MB_ERR_ARG, "no mapped batch of this index on this thread");
 	cudaStream_t st = c.st;
-	const int n_seq = (int)ix->names.size(), n_reads = c.last_n_reads;
+	const int n_seq = (int)ix->names.size();
 	if (c.n_counts < n_seq + 4) {
 		if (c.d_counts) cudaFree(c.d_counts);
 		CK(cudaMalloc(&c.d_counts, (size_t)(n_seq + 4) * 8));
 		c.n_counts = n_seq + 4;
 	}
 	CK(cudaMemsetAsync(c.d_counts, 0, (size_t)(n_seq + 4) * 8, st));
-	if (n_reads) k_count<<<(unsigned)cdiv(n_reads, 128), 128, 0, st>>>(n_reads, c.last_hit_off, c.last_n_hits, c.last_fields, c.last_read_off, mapq_min, mode,
-		c.d_counts, c.d_counts + n_seq, nullptr, nullptr);
+	for (const ThreadCtx::LastPart &lp : c.last_parts)
+		if (lp.n_reads) k_count<<<(unsigned)cdiv(lp.n_reads, 128), 128, 0, st>>>(lp.n_reads, lp.hit_off, lp.n_hits, lp.fields, lp.read_off, mapq_min, mode,
+			c.d_counts, c.d_counts + n_seq, nullptr, nullptr);
 	if (counts) CK(cudaMemcpyAsync(counts, c.d_counts, (size_t)n_seq * 8, cudaMemcpyDeviceToHost, st));
 	if (n_class) CK(cudaMemcpyAsync(n_class, c.d_counts + n_seq, 3 * 8, cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));

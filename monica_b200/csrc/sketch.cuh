@@ -187,6 +187,7 @@ k_sketch(const uint8_t *__restrict__ codes, const int64_t *__restrict__ off, int
 	SketchState<W> st;
 	int r = sk_find_read(off, n_reads, s);
 	int64_t pos = s;
+	if (pos < off[0]) pos = off[0]; // a sub-batch may start a few bytes into its (aligned) code array
 	int total_cnt = 0;
 	int64_t wpos = WRITE ? chunk_off[chunk] : 0;
 	while (pos < e) {
