@@ -61,7 +61,7 @@ typedef struct {
 	int64_t n_launches;       /* kernels launched for this batch */
 	float   ms_kdp;           /* CUDA-event time of the k_dp launches alone (the roofline kernel) */
 	int32_t n_kdp;            /* number of DP kernel launches */
-	float   ms_kdp_fast;      /* ... of which the register-resident fast path (k_dp_fast) */
+	float   ms_kdp_fast;      /* wall time (CUDA events) of the k_dp_fast launches, which overlap each other on 3 streams */
 	float   ms_kdp_exact;     /* ... and the exact ksw_extd2 block emulation (k_dp) */
 	int64_t n_fast_tasks, n_exact_tasks;
 	int64_t chain_cells;      /* predecessors visited by the chaining DP (the oracle counts the same loop) */
