@@ -129,6 +129,13 @@ struct SketchState {
 };
 
 struct EmitCount { int n; MB_D void operator()(uint64_t, uint32_t) { ++n; } };
+// count pass that also parks the minimizers of its chunk in a fixed-capacity staging row, so that the second run of the
+// automaton (the write pass) is only needed when some chunk overflowed its row
+#define SK_STAGE_CAP 80
+struct EmitStage {
+	mb128 *row; int n; int base; uint64_t rid_hi;
+	MB_D void operator()(uint64_t x, uint32_t y) { const int k = base + n; if (k < SK_STAGE_CAP) { row[k].x = x; row[k].y = rid_hi | y; } ++n; }
+};
 struct EmitWrite {
 	mb128 *out; int64_t pos; uint64_t rid_hi;
 	MB_D void operator()(uint64_t x, uint32_t y) { out[pos].x = x; out[pos].y = rid_hi | y; ++pos; }
@@ -149,7 +156,7 @@ template <int W, bool WRITE>
 __global__ void __launch_bounds__(SK_TPB)
 k_sketch(const uint8_t *__restrict__ codes, const int64_t *__restrict__ off, int n_reads, int64_t total,
          int w, int k, int32_t *__restrict__ chunk_cnt, int32_t *__restrict__ read_cnt,
-         const int64_t *__restrict__ chunk_off, mb128 *__restrict__ out)
+         const int64_t *__restrict__ chunk_off, mb128 *__restrict__ out, mb128 *__restrict__ stage, int *__restrict__ overflow)
 {
 	extern __shared__ __align__(16) uint8_t sm[];
 	const int64_t cta_base = (int64_t)blockIdx.x * SK_SPAN;
@@ -221,6 +228,12 @@ k_sketch(const uint8_t *__restrict__ codes, const int64_t *__restrict__ off, int
 			if (seg_end == re && st.minx != UINT64_MAX) ew(st.minx, st.miny);
 			seg_cnt = (int)(ew.pos - wpos);
 			wpos = ew.pos;
+		} else if (stage) {
+			EmitStage es; es.row = stage + chunk * SK_STAGE_CAP; es.n = 0; es.base = total_cnt; es.rid_hi = (uint64_t)(uint32_t)r << 32;
+			for (int64_t g = pos; g < seg_end; ++g) st.step(code_at(g), (uint32_t)(g - rs), w, k, mask, shift1, es);
+			if (seg_end == re && st.minx != UINT64_MAX) es(st.minx, st.miny);
+			seg_cnt = es.n;
+			if (seg_cnt) atomicAdd(&read_cnt[r], seg_cnt);
 		} else {
 			EmitCount ec; ec.n = 0;
 			for (int64_t g = pos; g < seg_end; ++g) st.step(code_at(g), (uint32_t)(g - rs), w, k, mask, shift1, ec);
@@ -232,7 +245,23 @@ k_sketch(const uint8_t *__restrict__ codes, const int64_t *__restrict__ off, int
 		pos = seg_end;
 		if (pos == re) { ++r; while (r < n_reads && off[r + 1] == off[r]) ++r; }
 	}
-	if (!WRITE) chunk_cnt[chunk] = total_cnt;
+	if (!WRITE) {
+		chunk_cnt[chunk] = total_cnt;
+		if (stage && total_cnt > SK_STAGE_CAP) *overflow = 1;
+	}
+}
+
+// staged minimizers -> their final, read-major positions: 8 lanes per chunk, 16-byte copies
+__global__ void k_sketch_compact(const mb128 *__restrict__ stage, const int32_t *__restrict__ chunk_cnt, const int64_t *__restrict__ chunk_off,
+                                 int64_t n_chunks, mb128 *__restrict__ out)
+{
+	const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const int64_t chunk = t >> 3; const int sub = (int)(t & 7);
+	if (chunk >= n_chunks) return;
+	const int n = chunk_cnt[chunk] < SK_STAGE_CAP ? chunk_cnt[chunk] : SK_STAGE_CAP;
+	const uint4 *src = reinterpret_cast<const uint4*>(stage + chunk * SK_STAGE_CAP);
+	uint4 *dst = reinterpret_cast<uint4*>(out + chunk_off[chunk]);
+	for (int i = sub; i < n; i += 8) dst[i] = src[i];
 }
 
 struct SketchOut {
@@ -265,15 +294,23 @@ static void run_sketch(Arena &ar, cudaStream_t st, const uint8_t *codes, const i
 		CK(cudaFuncSetAttribute(k_sketch<10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM_BYTES));
 		attr_set = true;
 	}
-	k_sketch<10, false><<<(unsigned)n_cta, SK_TPB, SK_SMEM_BYTES, st>>>(codes, d_off, n_reads, total, w, k, chunk_cnt, read_cnt, nullptr, nullptr);
+	mb128 *stage = ar.get<mb128>((size_t)n_chunks * SK_STAGE_CAP);
+	int *d_ovf = ar.get<int>(1);
+	CK(cudaMemsetAsync(d_ovf, 0, sizeof(int), st));
+	k_sketch<10, false><<<(unsigned)n_cta, SK_TPB, SK_SMEM_BYTES, st>>>(codes, d_off, n_reads, total, w, k, chunk_cnt, read_cnt, nullptr, nullptr, stage, d_ovf);
 	++*n_launch;
 	exclusive_scan<int32_t>(ar, st, chunk_cnt, chunk_off, n_chunks, n_launch);
 	exclusive_scan<int32_t>(ar, st, read_cnt, o.mini_off, n_reads, n_launch);
-	int64_t n_mini = 0;
+	int64_t n_mini = 0; int h_ovf = 0;
 	CK(cudaMemcpyAsync(&n_mini, chunk_off + n_chunks, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(&h_ovf, d_ovf, sizeof(int), cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));
 	o.n_mini = n_mini;
 	o.mini = ar.get<mb128>(n_mini + 1);
-	k_sketch<10, true><<<(unsigned)n_cta, SK_TPB, SK_SMEM_BYTES, st>>>(codes, d_off, n_reads, total, w, k, nullptr, nullptr, chunk_off, o.mini);
+	if (!h_ovf) { // the usual case: every chunk fitted its staging row, one 16-byte copy per minimizer finishes the job
+		k_sketch_compact<<<(unsigned)cdiv(n_chunks * 8, 256), 256, 0, st>>>(stage, chunk_cnt, chunk_off, n_chunks, o.mini);
+	} else {      // some 256-base chunk produced more than SK_STAGE_CAP minimizers (low-complexity sequence): re-run and write in place
+		k_sketch<10, true><<<(unsigned)n_cta, SK_TPB, SK_SMEM_BYTES, st>>>(codes, d_off, n_reads, total, w, k, nullptr, nullptr, chunk_off, o.mini, nullptr, nullptr);
+	}
 	++*n_launch;
 }

@@ -86,6 +86,19 @@ def test_sketch_chunk_boundaries_and_long_sequence(oracle, lib):
         got = out[ooff[i]:ooff[i + 1]].copy()
         got[:, 1] &= np.uint64(0xffffffff)
         assert np.array_equal(oracle.sketch(r), got), f"read {i} len {len(r)}"
+    # homopolymer / dinucleotide runs emit (nearly) one minimizer per base: more than a 256-base chunk's staging row holds,
+    # so the batch takes the in-place write pass instead of the staged copy
+    reads2 = reads[:6] + [np.full(2000, ord("A"), np.uint8), np.tile(np.frombuffer(b"AC", np.uint8), 700), synth.random_genome(rng, 5000)]
+    cat, off = synth.concat_reads(reads2)
+    out = np.zeros((len(cat) + 64, 2), dtype=np.uint64)
+    ooff = np.zeros(len(reads2) + 1, dtype=np.int64)
+    _lib.check(lib.mb_sketch(0, _lib._ptr(cat), _lib._ptr(off), len(reads2), 10, 15, _lib._ptr(out), len(cat) + 64, _lib._ptr(ooff)))
+    want = [oracle.sketch(r) for r in reads2]
+    assert max(len(w) for w in want[6:8]) > 1000
+    for i, r in enumerate(reads2):
+        got = out[ooff[i]:ooff[i + 1]].copy()
+        got[:, 1] &= np.uint64(0xffffffff)
+        assert np.array_equal(want[i], got), f"read {i} len {len(r)}"
 
 
 def test_seed_lookup_and_sort_bit_exact(case, lib):
