@@ -163,6 +163,118 @@ MB_D void mb_fix_cigar(Reg *r, uint32_t *cigar, const QView &qv, const TView &tv
 	r->n_cigar = n_cigar;
 }
 
+// mm_fix_cigar, warp-cooperative.  What upstream does per indel op k flanked by two match ops: shift it left by
+// l_k = min(prev_len_k, run_k), where run_k is how far the bases before the gap repeat the gap's own tail (sequence only:
+// the offsets at which an op starts never change) and prev_len_k is the current length of the preceding match op, i.e. its
+// original length plus the shift of the indel two ops earlier.  So: (A) every lane computes run_k for the indels of its
+// block of ops (the only part that reads sequence), (B) lane 0 resolves the short recurrence over the stored runs, (C) the
+// lanes apply -l / +l to the neighbouring match ops.  Zero-length ops and a leading indel (both rare) are finished by lane
+// 0 exactly as upstream.  `scr` = 2 * n_cigar ints of scratch.
+MB_D void mb_fix_cigar_warp(Reg *r, uint32_t *cigar, int32_t *scr, const QView &qv, const TView &tv, int *qshift, int *tshift, int lane)
+{
+	const unsigned FULL = 0xffffffffu;
+	int n_cigar = r->n_cigar;
+	*qshift = *tshift = 0;
+	if (n_cigar <= 1) return;
+	volatile uint32_t *cg = cigar;
+	volatile int32_t *run = scr;
+	const int per = (n_cigar + 31) / 32;
+	const int lo = min(lane * per, n_cigar), hi = min(lo + per, n_cigar);
+	int qsum = 0, tsum = 0;
+	for (int k = lo; k < hi; ++k) {
+		const uint32_t op = cg[k] & 0xf, len = cg[k] >> 4;
+		if (op == 0) qsum += len, tsum += len;
+		else if (op == 1) qsum += len;
+		else if (op == 2 || op == 3) tsum += len;
+	}
+	int qoff = qsum, toff = tsum;
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const int oq = __shfl_up_sync(FULL, qoff, d), ot = __shfl_up_sync(FULL, toff, d);
+		if (lane >= d) qoff += oq, toff += ot;
+	}
+	qoff -= qsum, toff -= tsum;
+	// (A) runs.  l_k = min(len(k-1) + l_{k-2}, run_k): wherever run_k < len(k-1) the carry from k-2 cannot matter and l_k = run_k
+	// is final; only the (few) positions with run_k >= len(k-1) depend on their predecessor and are resolved in order below.
+	int n_bound = 0;
+	for (int k = lo; k < hi; ++k) {
+		const uint32_t op = cg[k] & 0xf; const int len = (int)(cg[k] >> 4);
+		int rn = -1; // -1: not an eligible indel
+		if ((op == 1 || op == 2) && k > 0 && k < n_cigar - 1 && (cg[k - 1] & 0xf) == 0 && (cg[k + 1] & 0xf) == 0) {
+			int l = 0;
+			if (op == 1) { const int cap = qoff; while (l < cap && qv.at(qoff - 1 - l) == qv.at(qoff + len - 1 - l)) ++l; }
+			else { const int cap = toff; while (l < cap && tv.at(toff - 1 - l) == tv.at(toff + len - 1 - l)) ++l; }
+			rn = l;
+			if (l >= (int)(cg[k - 1] >> 4)) ++n_bound;
+		}
+		run[k] = rn;
+		if (op == 0) qoff += len, toff += len;
+		else if (op == 1) qoff += len;
+		else if (op == 2 || op == 3) toff += len;
+	}
+	// ordered list of the carry-dependent positions
+	int b_off = n_bound;
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(FULL, b_off, d); if (lane >= d) b_off += o; }
+	const int n_bound_all = __shfl_sync(FULL, b_off, 31);
+	b_off -= n_bound;
+	volatile int32_t *blist = scr + n_cigar;
+	if (n_bound) for (int k = lo; k < hi; ++k) { const int rn = run[k]; if (rn >= 0 && rn >= (int)(cg[k - 1] >> 4)) blist[b_off++] = k; }
+	int zero_len = 0;
+	for (int k = lo; k < hi; ++k) if ((cg[k] >> 4) == 0) zero_len = 1; // (upstream tests the current length; a spurious flag only runs a no-op compaction)
+	__syncwarp();
+	// (B) resolve the carry-dependent positions in order
+	int to_shrink = 0;
+	if (lane == 0) {
+		for (int b = 0; b < n_bound_all; ++b) {
+			const int k = blist[b];
+			const int carry = (k >= 2 && run[k - 2] > 0) ? run[k - 2] : 0; // final: k-2 is non-dependent or was resolved one step earlier
+			const int prev_len = (int)(cg[k - 1] >> 4) + carry;
+			const int rn = run[k];
+			const int l = rn < prev_len ? rn : prev_len;
+			if (l == prev_len) to_shrink = 1;
+			run[k] = l;
+		}
+	}
+	to_shrink = __any_sync(FULL, to_shrink | zero_len) ? 1 : 0;
+	__syncwarp();
+	// (C) apply
+	for (int k = lo; k < hi; ++k) {
+		const uint32_t w = cg[k];
+		if ((w & 0xf) == 0) {
+			int len = (int)(w >> 4);
+			if (k + 1 < n_cigar) { const int l = run[k + 1]; if (l > 0) len -= l; }
+			if (k > 0) { const int l = run[k - 1]; if (l > 0) len += l; }
+			cg[k] = (uint32_t)len << 4;
+		}
+	}
+	__syncwarp();
+	if (lane == 0) {
+		if (to_shrink) {
+			int l = 0;
+			for (int k = 0; k < n_cigar; ++k)
+				if (cigar[k] >> 4 != 0) cigar[l++] = cigar[k];
+			n_cigar = l;
+			l = 0;
+			for (int k = 0; k < n_cigar; ++k)
+				if (k == n_cigar - 1 || (cigar[k] & 0xf) != (cigar[k + 1] & 0xf)) cigar[l++] = cigar[k];
+				else cigar[k + 1] += cigar[k] >> 4 << 4;
+			n_cigar = l;
+		}
+		if ((cigar[0] & 0xf) == 1 || (cigar[0] & 0xf) == 2) {
+			const int32_t l = (int32_t)(cigar[0] >> 4);
+			if ((cigar[0] & 0xf) == 1) {
+				if (r->rev) r->qe -= l; else r->qs += l;
+				*qshift = l;
+			} else r->rs += l, *tshift = l;
+			--n_cigar;
+			for (int k = 0; k < n_cigar; ++k) cigar[k] = cigar[k + 1];
+		}
+		r->n_cigar = n_cigar;
+	}
+	__syncwarp();
+}
+
 // mm_update_extra for the regions stitched in this round, one WARP per region.  mm_fix_cigar (a sequential pass over the
 // CIGAR ops) is done by lane 0; the base-level scan that yields blen / mlen / n_ambi / dp_max is split over the lanes by
 // blocks of CIGAR ops.  dp_max is the maximum of the running score s <- max(s + d, 0): a lane summarises its block as the
@@ -170,7 +282,8 @@ MB_D void mb_fix_cigar(Reg *r, uint32_t *cigar, const QView &qv, const TView &tv
 // pass per lane plus a 32-step combine gives the exact sequential result.
 #define UE_NEG (-(1 << 29))
 __global__ void __launch_bounds__(128)
-k_update_extra(AlignCtx c, ReadArrays ra, const int2 *__restrict__ work, int n_work, uint32_t *__restrict__ cigar_pool)
+k_update_extra(AlignCtx c, ReadArrays ra, const int2 *__restrict__ work, int n_work, const RegPlan *__restrict__ plans, const DpTask *__restrict__ tasks,
+               uint32_t *__restrict__ cigar_pool)
 {
 	const unsigned FULL = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
@@ -191,7 +304,16 @@ k_update_extra(AlignCtx c, ReadArrays ra, const int2 *__restrict__ work, int n_w
 	TView tv; tv.S = c.ix.S; tv.bytes = nullptr; tv.idx0 = (int64_t)c.ix.seq_off[r->rid] + rs1; tv.step = 1; tv.packed = 1;
 	int qshift = 0, tshift = 0;
 	__syncwarp();
-	if (lane == 0) mb_fix_cigar(r, cigar, qv, tv, &qshift, &tshift);
+	{
+		// scratch for the per-op runs: the tail of this region's own CIGAR slots (the per-task CIGARs parked there have been
+		// consumed by k_stitch); fall back to the sequential routine in the unlikely case that it does not fit
+		const RegPlan &pl = plans[wi];
+		const DpTask &tl = tasks[pl.task0 + pl.n_tasks - 1];
+		const int64_t cap = tl.cigar_off + tl.qlen + tl.tlen + 1 - r->cigar_off;
+		const int nc = r->n_cigar;
+		if (pl.n_tasks > 0 && (int64_t)3 * nc + 2 <= cap) mb_fix_cigar_warp(r, cigar, reinterpret_cast<int32_t*>(cigar + nc), qv, tv, &qshift, &tshift, lane);
+		else if (lane == 0) mb_fix_cigar(r, cigar, qv, tv, &qshift, &tshift);
+	}
 	__syncwarp();
 	qshift = __shfl_sync(FULL, qshift, 0), tshift = __shfl_sync(FULL, tshift, 0);
 	qv.idx0 += (int64_t)qshift * qv.step, tv.idx0 += (int64_t)tshift * tv.step;

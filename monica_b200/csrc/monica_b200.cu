@@ -977,7 +977,7 @@ static void map_device_part(mb_index *ix, const mb_opt_t &opt_in, DevPart &part)
 		CK(cudaMemsetAsync(n_work + 1, 0, sizeof(int32_t), st));
 		k_stitch<<<wb, 128, 0, st>>>(ac, ra, work, h_n_work, plans, tasks, cigar_pool, work2, n_work + 1, d_err); ++nl;
 		phase("stitch");
-		k_update_extra<<<(unsigned)cdiv((int64_t)h_n_work * 32, 128), 128, 0, st>>>(ac, ra, work, h_n_work, cigar_pool); ++nl;
+		k_update_extra<<<(unsigned)cdiv((int64_t)h_n_work * 32, 128), 128, 0, st>>>(ac, ra, work, h_n_work, plans, tasks, cigar_pool); ++nl;
 		phase("update_extra");
 		h_n_work = d2h_scalar(n_work + 1, st);
 		check_err(d_err, st, "alignment round");
