@@ -157,6 +157,7 @@ k_dp_fast(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 		const uint32_t VB0 = dpf_pack2(8 * (dpf_bnd(0, q, e, e2, long_thres, long_diff) + B)), VB1 = dpf_pack2(8 * (-e + B));
 		const uint32_t VB2 = dpf_pack2(8 * (long_diff + B)), VB3 = dpf_pack2(8 * (-e2 + B));
 		uint32_t *dst = P + (size_t)lane * CW;
+		#pragma unroll 2
 		for (int s = 0; s < n_steps; ++s, dst += 32 * CW) {
 			const int j = s - lane;
 			if ((s & 31) == 0) {
