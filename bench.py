@@ -155,7 +155,30 @@ def mapped_bases_from_oracle_hits(per_read_hits, lens, mapq_min=60):
     return tot
 
 
-def cpu_arm(a, names, seqs, n_sample, steps, warmup):
+PARITY_FIELDS = ["rid", "rev", "qs", "qe", "rs", "re", "mapq", "mlen", "blen", "nm", "dp_max", "is_primary"]
+
+
+def parity_vs_oracle(gpu_aligner, cat, off, oracle_hits):
+    """The CPU-baseline sample mapped by the CUDA path, compared hit for hit (fields + CIGAR) with the oracle's result:
+    the oracle used as the checker, never on the measured path."""
+    hits = gpu_aligner.map_batch(cat=cat, off=off)
+    per = hits.per_read()
+    bad_reads, n_hits = 0, 0
+    for i, want in enumerate(oracle_hits):
+        got = per[i]
+        ok = len(want) == len(got)
+        if ok:
+            for w, g in zip(want, got):
+                n_hits += 1
+                if any(int(getattr(hits, f)[g]) != int(w[f]) for f in PARITY_FIELDS) or not np.array_equal(hits.cigar(g), w["cigar"]):
+                    ok = False
+                    break
+        bad_reads += 0 if ok else 1
+    return {"reads": len(oracle_hits), "hits_compared": n_hits, "reads_differing": bad_reads,
+            "fields": PARITY_FIELDS + ["cigar"], "against": "CPU restatement of minimap2-2.17 (oracle/), not mappy"}
+
+
+def cpu_arm(a, names, seqs, n_sample, steps, warmup, gpu_aligner=None):
     """Time the CPU restatement on a bounded sample with all host threads; returns (Gbases/s mapped, info)."""
     from oracle import oracle as O
     O.build()
@@ -165,6 +188,7 @@ def cpu_arm(a, names, seqs, n_sample, steps, warmup):
     lens = np.diff(off)
     hits, _ = oidx.map_batch(cat, off, n_threads=cores)   # one untimed pass also yields the mapped-base count
     mapped = mapped_bases_from_oracle_hits(hits, lens)
+    parity = parity_vs_oracle(gpu_aligner, cat, off, hits) if gpu_aligner is not None else None
     for _ in range(max(0, warmup - 1)):
         oidx.map_batch_raw(cat, off, n_threads=cores)
     times, cells = [], 0
@@ -175,7 +199,7 @@ def cpu_arm(a, names, seqs, n_sample, steps, warmup):
         cells = tot["dp_cells"]
     dt = float(np.mean(times))
     return mapped / dt / 1e9, dict(cores=cores, sample=f"{n_sample} reads / {int(off[-1])} bases of the same workload per step",
-                                   seconds_per_step=dt, total_gbases_per_s=float(off[-1]) / dt / 1e9, gcups=cells / dt / 1e9)
+                                   seconds_per_step=dt, total_gbases_per_s=float(off[-1]) / dt / 1e9, gcups=cells / dt / 1e9, parity=parity)
 
 
 def run_reference(a):
@@ -371,10 +395,11 @@ def main():
         cpu = None
         if world == 1 and not a.no_cpu_baseline:
             try:
-                v, info = cpu_arm(a, names, seqs, a.cpu_sample, 1, 1)
+                v, info = cpu_arm(a, names, seqs, a.cpu_sample, 1, 1, gpu_aligner=al)
                 cpu = {"value": v, "unit": "Gbases/s", "cores": info["cores"], "kind": "port", "sample": info["sample"],
                        "total_gbases_per_s": info["total_gbases_per_s"], "gcups": info["gcups"],
-                       "note": "CPU restatement of minimap2-2.17 (scalar int8 DP), not mappy"}
+                       "note": "CPU restatement of minimap2-2.17 (scalar int8 DP), not mappy",
+                       "parity_on_sample": info["parity"]}
             except Exception as e:  # the baseline must never sink the bench line
                 cpu = {"value": None, "unit": "Gbases/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
         out = {
