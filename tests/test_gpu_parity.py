@@ -469,3 +469,48 @@ def test_sub_batch_pieces_do_not_change_results(case, monkeypatch):
         counts = np.zeros(al.n_seq, np.int64); ncls = np.zeros(3, np.int64)
         _lib.check(_lib.lib().mb_count_last(al.handle(), 60, 2, _lib._ptr(counts), _lib._ptr(ncls)))
         assert np.array_equal(counts, base_counts[0]) and np.array_equal(ncls, base_counts[1]), k
+
+
+def test_long_noisy_reads_bit_exact(oracle, lib):
+    """BASELINE config 5 in miniature: 50 kb reads at 15 % error against several genomes incl. a strain copy, plus chimeric
+    reads (two fragments glued: region splits, long extensions, Z-drops).  Compared hit for hit with the oracle."""
+    from monica_b200 import synth
+    from monica_b200.mappy_shim import Aligner
+    names, seqs = synth.make_genomes(51, 4, 400000, strain_frac=0.25)
+    r1, _ = synth.simulate_reads(52, seqs, 10, 50000, 0.15, fixed_len=50000)
+    r2, _ = synth.simulate_reads(53, seqs, 8, 20000, 0.15, sigma=0.9)
+    r3, _ = synth.simulate_reads(54, seqs, 8, 6000, 0.12, fixed_len=6000)
+    chim = [np.concatenate([r3[i], r3[i + 1]]) for i in range(0, 8, 2)]              # two loci in one read: two primary hits
+    chim += [np.concatenate([r3[0], r3[1][::-1].copy()])]                              # reversed (not complemented) tail: junk
+    junk_tail = [np.concatenate([r, synth.random_genome(np.random.default_rng(60 + i), 1500)]) for i, r in enumerate(r3[:3])]
+    reads = r1 + r2 + chim + junk_tail
+    al = Aligner(names=names, seqs=seqs, device=0)
+    oidx = oracle.Index(names, seqs)
+    cat, off = synth.concat_reads(reads)
+    want, _ = oidx.map_batch(cat, off, n_threads=os.cpu_count() or 4)
+    hits = al.map_batch(cat=cat, off=off)
+    per = hits.per_read()
+    assert sum(len(w) for w in want) >= len(reads) + 3
+    for i in range(len(reads)):
+        _compare_hits(hits, per, i, want[i])
+
+
+def test_streaming_batches_accumulate_to_one_shot_counts(lib):
+    """BASELINE config 4 in miniature: 4,000-read batches mapped and counted incrementally; the running per-target counts
+    (all three of monica's modes) equal the counts of the whole run mapped at once."""
+    from monica_b200 import synth
+    from monica_b200.mappy_shim import Aligner
+    names, seqs = synth.make_genomes(71, 5, 300000, strain_frac=0.4)
+    cat, off = synth.simulate_reads_bulk(72, seqs, 12000, 3000, 0.10)
+    al = Aligner(names=names, seqs=seqs, device=0)
+    whole = al.map_batch(cat=cat, off=off)
+    for mode in ("basic", "query_length", "matching"):
+        want_counts, want_cls, _, _ = al.count(whole, 60, mode)
+        run_counts = np.zeros_like(want_counts); run_cls = np.zeros_like(want_cls)
+        for lo in range(0, 12000, 4000):
+            o = off[lo:lo + 4001] - off[lo]
+            h = al.map_batch(cat=cat[off[lo]:off[lo + 4000]], off=o)
+            c, k, _, _ = al.count(h, 60, mode)
+            run_counts += c; run_cls += k
+        assert np.array_equal(run_counts, want_counts) and np.array_equal(run_cls, want_cls), mode
+    assert want_cls[0] > 0.5 * 12000 and want_cls.sum() == 12000   # strain copies push many reads below MAPQ 60
