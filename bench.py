@@ -372,6 +372,36 @@ def main():
         streaming = {"batch_reads": sb, "batches": int(len(lat)), "latency_ms_p50": float(np.percentile(lat, 50)), "latency_ms_p99": float(np.percentile(lat, 99)),
                      "latency_ms_max": float(lat[-1]), "note": "host buffers in, hit arrays + CIGARs and per-target counts out, wall clock per batch"}
 
+    # ---- monica's own entry point: multi_threaded_aligner on a FASTQ file (native ingest -> map -> count -> routed files) ----
+    aligner_e2e = None
+    if rank == 0 and world == 1 and n_reads >= 8000:
+        try:
+            import shutil
+            import tempfile
+            from monica_b200 import aligner as galigner
+            nfq = min(20000, n_reads)
+            tmp = tempfile.mkdtemp(prefix="monica_b200_bench_")
+            q = os.path.join(tmp, "sample.fastq")
+            with open(q, "wb") as fh:                       # untimed: write the FASTQ the aligner will consume
+                qual = b"I" * int(np.diff(off[:nfq + 1]).max())
+                for i in range(nfq):
+                    sq = cat[off[i]:off[i + 1]].tobytes()
+                    fh.write(b"@read%d ch=%d\n" % (i, i % 512) + sq + b"\n+\n" + qual[:len(sq)] + b"\n")
+            fq_bases = int(off[nfq])
+            cwd = os.getcwd()
+            t0 = time.perf_counter()
+            import contextlib
+            with contextlib.redirect_stdout(sys.stderr):    # the aligner prints progress like the reference; keep stdout to the one JSON line
+                res = galigner.multi_threaded_aligner(tmp, ["resident"], mode="query_length", n_threads=1, output_folder=tmp, index_loader_fn=lambda p: al)
+            dt = time.perf_counter() - t0
+            os.chdir(cwd)
+            got = sum(sum(c.values()) for c in res["sample"].values()) if res else 0
+            aligner_e2e = {"reads": nfq, "bases": fq_bases, "seconds": dt, "gbases_per_s": got / dt / 1e9, "mapped_bases": int(got),
+                           "note": "monica_b200.aligner.multi_threaded_aligner on one FASTQ file: parse, map, best_hit/count, write routed FASTQs, alignment.pkl"}
+            shutil.rmtree(tmp, ignore_errors=True)
+        except Exception as e:  # never sink the bench line
+            aligner_e2e = {"error": repr(e)}
+
     # ---- roofline of the dominant kernel (k_dp_fast: packed two-piece affine DP + traceback) ----
     last = stats[-1]
     ms_fast = float(np.mean([s["ms_kdp_fast"] for s in stats]))
@@ -440,6 +470,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu,
             "streaming": streaming,
+            "aligner_e2e": aligner_e2e,
             "stage_ms": stage_ms,
             "work_per_step": {k: last[k] for k in ("n_reads", "n_bases", "n_mini", "n_anchor", "n_regs", "n_dp_tasks", "n_dp_pass2", "dp_cells", "n_hits", "n_rounds", "n_fast_tasks", "n_exact_tasks", "n_ext_tasks", "dp_cells_exact", "dp_cells_ext", "chain_cells")},
             "read_classes": {"mapped": int(ncls_full[0]), "unmapped": int(ncls_full[1]), "ambiguous": int(ncls_full[2])},

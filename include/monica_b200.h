@@ -95,6 +95,10 @@ int64_t mb_index_hbm_bytes(const mb_index_t *idx);
  * each calling thread gets its own CUDA stream + scratch. */
 int  mb_map_batch(mb_index_t *idx, const mb_opt_t *opt, const uint8_t *cat, const int64_t *off, int32_t n_reads,
                   mb_hits_t **out, mb_stats_t *stats);
+/* same with a choice of what is copied back: want bit 0 = hit fields, bit 1 = CIGARs (mb_map_batch == want 3).  monica reads only
+ * (ctg, NM, mlen) of each hit (aligner.py:195,217), so its path skips the CIGAR copy */
+int  mb_map_batch_ex(mb_index_t *idx, const mb_opt_t *opt, const uint8_t *cat, const int64_t *off, int32_t n_reads, int want,
+                     mb_hits_t **out, mb_stats_t *stats);
 /* device-resident variant used by bench.py's `value` leg: reads must already be uploaded with mb_reads_upload */
 typedef struct mb_reads mb_reads_t;
 int  mb_reads_upload(mb_index_t *idx, const uint8_t *cat, const int64_t *off, int32_t n_reads, mb_reads_t **out);
@@ -124,6 +128,20 @@ int  mb_count_last(mb_index_t *idx, int32_t mapq_min, int mode, int64_t *counts,
 /* device pointer to the int64[n_seq] count vector of the LAST mb_count on this thread (for the NCCL allreduce) */
 void *mb_count_device_ptr(mb_index_t *idx);
 int  mb_count_fetch(mb_index_t *idx, int64_t *counts);
+
+/* ---- FASTQ ingest and routed writers (host side, no device needed) ----
+ * mb_fastq_load      for seq_record in SeqIO.parse(sample, 'fastq')            monica/genomes/aligner.py:191,212
+ * mb_fastq_route     SeqIO.write(seq_record, <mapped|unmapped|ambiguous|focus>) monica/genomes/aligner.py:232,236,243,265
+ * The sequences come back in the concatenated layout mb_map_batch takes. */
+typedef struct mb_fastq mb_fastq_t;
+int  mb_fastq_load(const char *path, mb_fastq_t **out);              /* plain or gzip; multi-line records accepted */
+int64_t mb_fastq_n(const mb_fastq_t *fq);
+const uint8_t *mb_fastq_seqs(const mb_fastq_t *fq, const int64_t **off);
+const char *mb_fastq_header(const mb_fastq_t *fq, int64_t i, int64_t *len, int32_t *id_len);
+int  mb_fastq_ids_unique(const mb_fastq_t *fq);
+int  mb_fastq_route(const mb_fastq_t *fq, const int8_t *dest, const char *const *new_id, const uint8_t *focus,
+                    const char *mapped_path, const char *unmapped_path, const char *ambiguous_path, const char *focus_path);
+void mb_fastq_free(mb_fastq_t *fq);
 
 /* ---- per-stage entry points (parity tests) ---- */
 /* minimizers of each read: out_xy[2*cap], out_off[n_reads+1]; y carries the read index in its high 32 bits */

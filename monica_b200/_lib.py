@@ -63,10 +63,11 @@ SYMBOLS = [
     "mb_last_error", "mb_device_count", "mb_opt_init",
     "mb_index_build", "mb_index_build_fasta", "mb_index_save", "mb_index_load", "mb_index_free", "mb_index_n_seq",
     "mb_index_seq_name", "mb_index_seq_len", "mb_index_mid_occ", "mb_index_kw", "mb_index_n_minimizers", "mb_index_hbm_bytes",
-    "mb_map_batch", "mb_reads_upload", "mb_reads_free", "mb_map_resident",
+    "mb_map_batch", "mb_map_batch_ex", "mb_reads_upload", "mb_reads_free", "mb_map_resident",
     "mb_hits_n", "mb_hits_field", "mb_hits_cigar_off", "mb_hits_cigar_pool", "mb_hits_rep_len", "mb_hits_free",
     "mb_count", "mb_count_last", "mb_count_device_ptr", "mb_count_fetch",
     "mb_sketch", "mb_seed", "mb_chain", "mb_dp_batch", "mb_int_peak", "mb_stream",
+    "mb_fastq_load", "mb_fastq_n", "mb_fastq_seqs", "mb_fastq_header", "mb_fastq_ids_unique", "mb_fastq_route", "mb_fastq_free",
 ]
 
 _lib = None
@@ -103,6 +104,7 @@ def lib():
     L.mb_index_hbm_bytes.argtypes = [vp]
     L.mb_index_hbm_bytes.restype = i64
     L.mb_map_batch.argtypes = [vp, C.POINTER(Opt), vp, vp, i32, C.POINTER(vp), C.POINTER(Stats)]
+    L.mb_map_batch_ex.argtypes = [vp, C.POINTER(Opt), vp, vp, i32, C.c_int, C.POINTER(vp), C.POINTER(Stats)]
     L.mb_reads_upload.argtypes = [vp, vp, vp, i32, C.POINTER(vp)]
     L.mb_reads_free.argtypes = [vp]
     L.mb_reads_free.restype = None
@@ -126,6 +128,17 @@ def lib():
     L.mb_count_device_ptr.restype = vp
     L.mb_stream.argtypes = [vp]
     L.mb_stream.restype = vp
+    L.mb_fastq_load.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.mb_fastq_n.argtypes = [vp]
+    L.mb_fastq_n.restype = C.c_int64
+    L.mb_fastq_seqs.argtypes = [vp, C.POINTER(C.POINTER(C.c_int64))]
+    L.mb_fastq_seqs.restype = C.POINTER(C.c_uint8)
+    L.mb_fastq_header.argtypes = [vp, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+    L.mb_fastq_header.restype = C.POINTER(C.c_char)
+    L.mb_fastq_ids_unique.argtypes = [vp]
+    L.mb_fastq_route.argtypes = [vp, vp, vp, vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p]
+    L.mb_fastq_free.argtypes = [vp]
+    L.mb_fastq_free.restype = None
     L.mb_count_fetch.argtypes = [vp, vp]
     L.mb_sketch.argtypes = [C.c_int, vp, vp, i32, C.c_int, C.c_int, vp, i64, vp]
     L.mb_seed.argtypes = [vp, C.POINTER(Opt), vp, vp, i32, vp, i64, vp, vp]

@@ -139,12 +139,75 @@ class _Tally(dict):
             self[tax_unit] = Counter({accession: amount})
 
 
+def _aligner_whole_file(sample, sample_name, index, mode, mapping_quality, overnight, focus_species,
+                        mapped_folder, unmapped_folder, ambiguous_folder, focus_folder):
+    """The common case of `aligner` -- one index, nothing carried over, distinct read ids -- without a Python loop over the
+    reads: native FASTQ ingest (mb_fastq_load), one device pipeline, hit filter + best_hit + counting on the device
+    (mb_count), native routed writers (mb_fastq_route).  Returns None when the file does not qualify (duplicate ids), so
+    the caller falls back to the per-record path, which reproduces the reference's dictionary semantics."""
+    import ctypes as C
+    import numpy as np
+    from . import _lib
+    L = _lib.lib()
+    fq = C.c_void_p()
+    _lib.check(L.mb_fastq_load(os.fsencode(sample), C.byref(fq)))
+    try:
+        if not L.mb_fastq_ids_unique(fq):
+            return None
+        n = int(L.mb_fastq_n(fq))
+        offp = C.POINTER(C.c_int64)()
+        catp = L.mb_fastq_seqs(fq, C.byref(offp))
+        off = np.ctypeslib.as_array(offp, shape=(n + 1,)) if n else np.zeros(1, np.int64)
+        cat = np.ctypeslib.as_array(catp, shape=(int(off[-1]),)) if n and off[-1] else np.zeros(0, np.uint8)
+        hits = index.map_batch(cat=cat, off=off, cigars=False)
+        if mapping_quality is None and (hits.is_primary != 0).any():
+            raise TypeError("'>=' not supported between instances of 'int' and 'NoneType'")
+        _, _, read_class, read_best = index.count(hits, 0 if mapping_quality is None else mapping_quality, None)
+        contigs = index.seq_names
+        dest = np.zeros(n, np.int8)                       # 0 unmapped, 1 mapped, 2 ambiguous (mb_count's classes)
+        dest[read_class == 1] = 1
+        dest[read_class == 2] = 2
+        tally = _Tally()
+        new_ids = (C.c_char_p * max(n, 1))()
+        focus = np.zeros(max(n, 1), np.uint8)
+        lens = np.diff(off)
+        keep = {}                                         # keeps the encoded tax-unit strings alive for the C call
+        for i in np.nonzero(dest == 1)[0]:
+            h = int(read_best[i])
+            ctg = contigs[int(hits.rid[h])]
+            parts = ctg.split(sep=':')
+            tax_unit, accession = parts[0], parts[1]
+            if tax_unit in focus_species:
+                focus[i] = 1
+            if overnight:
+                tax_unit = tax_unit.split(sep='_')[0]
+            new_ids[i] = keep.setdefault(tax_unit, tax_unit.encode())
+            tally.add(mode, tax_unit, accession, int(lens[i]), int(hits.mlen[h]))
+        _lib.check(L.mb_fastq_route(fq, dest.ctypes.data_as(C.c_void_p), C.cast(new_ids, C.c_void_p),
+                                    focus.ctypes.data_as(C.c_void_p) if focus_species else None,
+                                    os.fsencode(os.path.join(mapped_folder, sample)), os.fsencode(os.path.join(unmapped_folder, sample)),
+                                    os.fsencode(os.path.join(ambiguous_folder, sample)),
+                                    os.fsencode(os.path.join(focus_folder, sample)) if focus_species else None))
+        return dict(tally)
+    finally:
+        L.mb_fastq_free(fq)
+
+
 def aligner(sample, sample_name, index, mode=None, hits_folder=None, mapping_quality=None, overnight=False,
             focus_species=[], mapped_folder=None, unmapped_folder=None, ambiguous_folder=None, focus_folder=None,
             last_index=False):
     print(f'{sample}, mode is {mode}\t')
     carry_name = sample_name + '_hits.pkl'
     carry_path = os.path.join(hits_folder, carry_name)
+    if last_index and carry_name not in os.listdir(hits_folder) and hasattr(index, 'map_batch') and hasattr(index, 'count') \
+            and os.environ.get('MONICA_B200_PER_RECORD') != '1':
+        done = _aligner_whole_file(sample, sample_name, index, mode, mapping_quality, overnight, focus_species,
+                                   mapped_folder, unmapped_folder, ambiguous_folder, focus_folder)
+        if done is not None:
+            # the reference leaves an (empty-able) carry-over pickle behind only transiently: it writes and removes it
+            print(f'{sample} done')
+            os.remove(sample)
+            return done, sample_name
     carried = _load_pickle(carry_path) if carry_name in os.listdir(hits_folder) else dict()
 
     records = list(fastx.parse(sample, 'fastq'))

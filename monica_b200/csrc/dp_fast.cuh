@@ -114,6 +114,7 @@ k_dp_fast(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 	const uint32_t NFL1 = dpf_pack2(-(8 * (-q - e + B) + 3)), NFL2 = dpf_pack2(-(8 * (-q - e + B) + 2));
 	const uint32_t NFL3 = dpf_pack2(-(8 * (-q2 - e2 + B) + 1)), NFL4 = dpf_pack2(-(8 * (-q2 - e2 + B) + 0));
 	const uint32_t K1 = 0x00010000u + dpf_pack2(8 * (B - e)), K2 = 0x00010000u + dpf_pack2(8 * (B - e2));
+	const uint32_t NEG1 = 0xffffffffu + (uint32_t)sc.pad; // sc.pad == 0, opaque to the compiler
 	const uint32_t EIGHT = dpf_pack2(8 + sc.pad);   // sc.pad == 0: a run-time value stays in a register instead of being re-materialised per use
 	const uint32_t MCHB = (uint32_t)(8 * (sc.sc_mch + 2 * B) + 4), MISB = (uint32_t)(8 * (sc.sc_mis + 2 * B) + 4), NB = (uint32_t)(8 * (sc.sc_N + 2 * B) + 4);
 	const uint32_t MIS4 = MISB * 0x01010101u, N4 = NB * 0x01010101u, MDIFF = MCHB - MISB;
@@ -183,13 +184,13 @@ k_dp_fast(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 					const uint32_t zc = dpf_and(zt, 0xfff8fff8u);          // opaque: keeps `zt - zc` a subtraction (FMA pipe) instead of a 2nd LOP3
 					const uint32_t un = zc - VL, vn = zc - U[c];          // halves are non-negative: no borrow
 					// per-half D - zc: the low half always borrows (zc > D, checked on the host), which the 0x10000 pays back
-					const uint32_t nz1 = K1 - zc, nz2 = K2 - zc;
+					const uint32_t nz1 = dpf_mad(zc, NEG1, K1), nz2 = dpf_mad(zc, NEG1, K2); // K - zc as a register-operand IMAD: FMA pipe (ptxas turns the immediate form into an ALU-pipe IADD3)
 					const uint32_t r1 = __viaddmax_s16x2(a, nz1, FL1), r2 = __viaddmax_s16x2(b, nz1, FL2);
 					const uint32_t r3 = __viaddmax_s16x2(a2, nz2, FL3), r4 = __viaddmax_s16x2(b2, nz2, FL4);
 					const uint32_t g1 = __viaddmin_s16x2(r1, NFL1, EIGHT), g2 = __viaddmin_s16x2(r2, NFL2, EIGHT);
 					const uint32_t g3 = __viaddmin_s16x2(r3, NFL3, EIGHT), g4 = __viaddmin_s16x2(r4, NFL4, EIGHT);
 					// tag | x-cont 0x08 | y-cont 0x10 | x2-cont 0x20 | y2-cont 0x40, as a chain of 2-input multiply-adds (FMA pipe)
-					const uint32_t wd = dpf_mad(g4, 8u, dpf_mad(g3, 4u, dpf_mad(g2, 2u, g1 + (zt - zc))));
+					const uint32_t wd = dpf_mad(g4, 8u, dpf_mad(g3, 4u, dpf_mad(g2, 2u, dpf_mad(zc, NEG1, zt) + g1)));
 					XL = r1, X2L = r3, Y[c] = r2, Y2[c] = r4, U[c] = un, VL = vn;
 					if (c & 1) wv[c >> 1] = dpf_prmt(wprev, wd, 0x6240u);        // bytes A:c-1 A:c B:c-1 B:c
 					else if (c == C - 1) wv[c >> 1] = dpf_prmt(wd, 0u, 0x6240u);

@@ -1040,7 +1040,7 @@ static int mb_n_parts(int32_t n_reads, int64_t total)
 // concurrently on their own streams / arenas / host threads; results are concatenated in read order, so the outcome does
 // not depend on the number of pieces.
 static mb_hits *map_device(mb_index *ix, const mb_opt_t &opt, ThreadCtx &c, const uint8_t *d_codes, const int64_t *d_off, const int64_t *h_off,
-                           int32_t n_reads, int64_t total, bool want_hits, mb_stats_t *stats)
+                           int32_t n_reads, int64_t total, int want_hits /* bit 0: hit fields, bit 1: CIGARs */, mb_stats_t *stats)
 {
 	auto t_begin = std::chrono::steady_clock::now();
 	std::unique_ptr<mb_hits> H(new mb_hits());
@@ -1097,14 +1097,15 @@ static mb_hits *map_device(mb_index *ix, const mb_opt_t &opt, ThreadCtx &c, cons
 	H->n = n_h;
 	Timer tm(c.st); tm.start();
 	if (want_hits) {
-		H->fields.resize((size_t)HIT_NF * n_h); H->cigar_off.resize(n_h); H->cigar.resize(n_c);
+		const bool want_cig = (want_hits & 2) != 0;
+		H->fields.resize((size_t)HIT_NF * n_h); H->cigar_off.resize(n_h); H->cigar.resize(want_cig ? n_c : 0);
 		for (int k = 0; k < K; ++k) {
 			const DevPart &p = parts[k];
 			cudaStream_t st = p.c->st;
 			for (int f = 0; f < HIT_NF && p.n_h; ++f)
 				CK(cudaMemcpyAsync(H->fields.data() + (size_t)f * n_h + hbase[k], p.d_fields + (size_t)f * p.n_h, (size_t)p.n_h * 4, cudaMemcpyDeviceToHost, st));
 			if (p.n_h) CK(cudaMemcpyAsync(H->cigar_off.data() + hbase[k], p.d_hcoff, (size_t)p.n_h * 8, cudaMemcpyDeviceToHost, st));
-			if (p.n_c) CK(cudaMemcpyAsync(H->cigar.data() + cbase[k], p.d_hcig, (size_t)p.n_c * 4, cudaMemcpyDeviceToHost, st));
+			if (p.n_c && want_cig) CK(cudaMemcpyAsync(H->cigar.data() + cbase[k], p.d_hcig, (size_t)p.n_c * 4, cudaMemcpyDeviceToHost, st));
 			if (p.n_reads) {
 				CK(cudaMemcpyAsync(H->rep_len.data() + p.read_lo, p.d_rep_len, (size_t)p.n_reads * 4, cudaMemcpyDeviceToHost, st));
 				CK(cudaMemcpyAsync(H->hit_off.data() + p.read_lo, p.d_hit_off, (size_t)(p.n_reads + (k == K - 1 ? 1 : 0)) * 8, cudaMemcpyDeviceToHost, st));
@@ -1157,7 +1158,16 @@ static void upload_reads(ThreadCtx &c, const uint8_t *cat, const int64_t *off, i
 	if (*total) k_encode_nt4<<<(unsigned)cdiv(cdiv(*total, 16), 256), 256, 0, st>>>(d_ascii, *d_codes, *total);
 }
 
+static int map_batch_impl(mb_index_t *ix, const mb_opt_t *opt, const uint8_t *cat, const int64_t *off, int32_t n_reads, int want, mb_hits_t **out, mb_stats_t *stats);
 extern "C" int mb_map_batch(mb_index_t *ix, const mb_opt_t *opt, const uint8_t *cat, const int64_t *off, int32_t n_reads, mb_hits_t **out, mb_stats_t *stats)
+{
+	return map_batch_impl(ix, opt, cat, off, n_reads, 3, out, stats);
+}
+extern "C" int mb_map_batch_ex(mb_index_t *ix, const mb_opt_t *opt, const uint8_t *cat, const int64_t *off, int32_t n_reads, int want, mb_hits_t **out, mb_stats_t *stats)
+{
+	return map_batch_impl(ix, opt, cat, off, n_reads, want, out, stats);
+}
+static int map_batch_impl(mb_index_t *ix, const mb_opt_t *opt, const uint8_t *cat, const int64_t *off, int32_t n_reads, int want, mb_hits_t **out, mb_stats_t *stats)
 {
 	API_BEGIN
 	if (!ix || !opt || !off || !out || (n_reads > 0 && !cat && off[n_reads] > 0)) throw mb_error(MB_ERR_ARG, "bad arguments");
@@ -1168,7 +1178,7 @@ extern "C" int mb_map_batch(mb_index_t *ix, const mb_opt_t *opt, const uint8_t *
 	upload_reads(c, cat, off, n_reads, &d_codes, &d_off, &total, false);
 	float ms_h2d = tm.stop();
 	if (stats) stats->ms_h2d = ms_h2d;
-	*out = map_device(ix, *opt, c, d_codes, d_off, off, n_reads, total, true, stats);
+	*out = map_device(ix, *opt, c, d_codes, d_off, off, n_reads, total, want, stats);
 	if (stats) { stats->ms_h2d = ms_h2d; stats->n_launches += 1; }
 	API_END
 }
@@ -1206,7 +1216,7 @@ extern "C" int mb_map_resident(mb_index_t *ix, const mb_opt_t *opt, mb_reads_t *
 	CK(cudaMemcpyAsync(h_off.data(), reads->d_off, (reads->n_reads + 1) * 8, cudaMemcpyDeviceToHost, c.st));
 	CK(cudaStreamSynchronize(c.st));
 	if (stats) stats->ms_h2d = 0;
-	*out = map_device(ix, *opt, c, reads->d_codes, reads->d_off, h_off.data(), reads->n_reads, reads->total, want_hits != 0, stats);
+	*out = map_device(ix, *opt, c, reads->d_codes, reads->d_off, h_off.data(), reads->n_reads, reads->total, want_hits ? 3 : 0, stats);
 	API_END
 }
 
@@ -1472,3 +1482,187 @@ extern "C" int mb_dp_batch(int device, const mb_opt_t *opt, mb_dp_task_t *tasks,
 	CK(cudaGetLastError());
 	API_END
 }
+
+// ---------------------------------------------------------------------------------------------
+// FASTQ ingest and routed writers (host side).  Replaces the per-record Biopython loop of
+// /root/reference/monica/genomes/aligner.py:191,212 (SeqIO.parse) and :232,236,243,265 (SeqIO.write): a whole file is
+// parsed in one pass into the concatenated-reads layout mb_map_batch takes, and the mapped / unmapped / ambiguous / focus
+// files are appended in one pass with Biopython's header rule ('@' + description when it starts with the id, else
+// '@' + id + ' ' + description).  No device is needed for these calls.
+// ---------------------------------------------------------------------------------------------
+struct mb_fastq {
+	std::string raw;                       // the decompressed file
+	std::vector<int64_t> head, head_len;   // header line without '@'
+	std::vector<int32_t> id_len;           // up to the first blank / tab
+	std::vector<int64_t> qual, qual_len;   // quality string (single line, or joined copy in `extra`)
+	std::vector<uint8_t> cat;              // concatenated sequences
+	std::vector<int64_t> off;              // [n+1]
+	std::string extra;                     // joined quality strings of multi-line records
+	std::vector<uint8_t> qual_in_extra;
+};
+
+extern "C" int mb_fastq_load(const char *path, mb_fastq_t **out)
+{
+	API_BEGIN
+	if (!path || !out) throw mb_error(MB_ERR_ARG, "bad arguments");
+	std::unique_ptr<mb_fastq> fq(new mb_fastq());
+	{
+		FILE *pf = fopen(path, "rb");
+		if (!pf) throw mb_error(MB_ERR_IO, std::string("cannot open ") + path);
+		unsigned char magic[2] = {0, 0};
+		const size_t got = fread(magic, 1, 2, pf);
+		if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) { // gzip: stream through zlib
+			fclose(pf);
+			gzFile fp = gzopen(path, "rb");
+			if (!fp) throw mb_error(MB_ERR_IO, std::string("cannot open ") + path);
+			gzbuffer(fp, 1 << 20);
+			std::vector<char> buf(1 << 22);
+			int n;
+			while ((n = gzread(fp, buf.data(), (unsigned)buf.size())) > 0) fq->raw.append(buf.data(), (size_t)n);
+			const bool bad = n < 0;
+			gzclose(fp);
+			if (bad) throw mb_error(MB_ERR_IO, std::string("read error in ") + path);
+		} else {                                                 // plain: one read of the whole file
+			fseek(pf, 0, SEEK_END);
+			const long sz = ftell(pf);
+			fseek(pf, 0, SEEK_SET);
+			fq->raw.resize(sz > 0 ? (size_t)sz : 0);
+			const size_t rd = sz > 0 ? fread(&fq->raw[0], 1, (size_t)sz, pf) : 0;
+			fclose(pf);
+			if ((long)rd != (sz > 0 ? sz : 0)) throw mb_error(MB_ERR_IO, std::string("read error in ") + path);
+		}
+	}
+	fq->cat.reserve(fq->raw.size() / 2 + 16);
+	const std::string &s = fq->raw;
+	const int64_t N = (int64_t)s.size();
+	auto line_end = [&](int64_t p) { const void *q = memchr(s.data() + p, '\n', (size_t)(N - p)); return q ? (int64_t)((const char*)q - s.data()) : N; };
+	auto rstrip = [&](int64_t b, int64_t e) { while (e > b && (s[e - 1] == '\r' || s[e - 1] == '\n')) --e; return e; };
+	fq->off.push_back(0);
+	int64_t p = 0;
+	while (p < N) {
+		int64_t e = line_end(p), le = rstrip(p, e);
+		if (le == p) { p = e + 1; continue; }                          // blank line
+		if (s[p] != '@') throw mb_error(MB_ERR_IO, std::string("unexpected line in FASTQ input: ") + path);
+		const int64_t hb = p + 1, hl = le - hb;
+		int32_t idl = 0;
+		while (idl < hl && s[hb + idl] != ' ' && s[hb + idl] != '\t') ++idl;
+		p = e + 1;
+		// sequence lines until '+'
+		int64_t seq_len = 0;
+		for (;;) {
+			if (p >= N) break;
+			e = line_end(p);
+			if (s[p] == '+') break;
+			le = rstrip(p, e);
+			fq->cat.insert(fq->cat.end(), s.begin() + p, s.begin() + le);
+			seq_len += le - p;
+			p = e + 1;
+		}
+		if (p < N) p = line_end(p) + 1;                                  // skip the '+' line
+		// quality lines until as long as the sequence
+		int64_t qb = p, ql = 0; bool multi = false; size_t xb = fq->extra.size();
+		int n_lines = 0;
+		while (ql < seq_len && p < N) {
+			e = line_end(p); le = rstrip(p, e);
+			if (n_lines == 1) { multi = true; fq->extra.append(s, (size_t)qb, (size_t)ql); }
+			if (multi) fq->extra.append(s, (size_t)p, (size_t)(le - p));
+			ql += le - p; ++n_lines;
+			p = e + 1;
+		}
+		fq->head.push_back(hb); fq->head_len.push_back(hl); fq->id_len.push_back(idl);
+		if (multi) { fq->qual.push_back((int64_t)xb); fq->qual_in_extra.push_back(1); }
+		else { fq->qual.push_back(qb); fq->qual_in_extra.push_back(0); }
+		fq->qual_len.push_back(ql);
+		fq->off.push_back((int64_t)fq->cat.size());
+	}
+	*out = fq.release();
+	API_END
+}
+
+extern "C" int64_t mb_fastq_n(const mb_fastq_t *fq) { return fq ? (int64_t)fq->head.size() : 0; }
+extern "C" const uint8_t *mb_fastq_seqs(const mb_fastq_t *fq, const int64_t **off)
+{
+	if (!fq) return nullptr;
+	if (off) *off = fq->off.data();
+	return fq->cat.data();
+}
+extern "C" const char *mb_fastq_header(const mb_fastq_t *fq, int64_t i, int64_t *len, int32_t *id_len)
+{
+	if (!fq || i < 0 || i >= (int64_t)fq->head.size()) return nullptr;
+	if (len) *len = fq->head_len[i];
+	if (id_len) *id_len = fq->id_len[i];
+	return fq->raw.data() + fq->head[i];
+}
+/* 1 if every record id of the file is distinct (the vectorised aligner path needs that; duplicates take the reference's
+ * per-record dictionary semantics in Python) */
+extern "C" int mb_fastq_ids_unique(const mb_fastq_t *fq)
+{
+	if (!fq) return 0;
+	std::vector<std::pair<const char*, int32_t>> ids(fq->head.size());
+	for (size_t i = 0; i < ids.size(); ++i) ids[i] = std::make_pair(fq->raw.data() + fq->head[i], fq->id_len[i]);
+	auto less = [](const std::pair<const char*, int32_t> &a, const std::pair<const char*, int32_t> &b) {
+		const int c = memcmp(a.first, b.first, (size_t)std::min(a.second, b.second));
+		return c != 0 ? c < 0 : a.second < b.second;
+	};
+	std::sort(ids.begin(), ids.end(), less);
+	for (size_t i = 1; i < ids.size(); ++i)
+		if (ids[i].second == ids[i - 1].second && memcmp(ids[i].first, ids[i - 1].first, (size_t)ids[i].second) == 0) return 0;
+	return 1;
+}
+
+/* dest[i]: 0 unmapped, 1 mapped, 2 ambiguous, anything else: skip.  new_id[i] (mapped reads only): the tax unit that
+ * replaces the record id (aligner.py:242).  focus[i] != 0: also append the ORIGINAL record to focus_path (aligner.py:235-236).
+ * Files are opened in append mode like the reference does; a NULL path skips that sink. */
+extern "C" int mb_fastq_route(const mb_fastq_t *fq, const int8_t *dest, const char *const *new_id, const uint8_t *focus,
+                              const char *mapped_path, const char *unmapped_path, const char *ambiguous_path, const char *focus_path)
+{
+	API_BEGIN
+	if (!fq || !dest) throw mb_error(MB_ERR_ARG, "bad arguments");
+	std::string sink[4];
+	const char *paths[4] = { unmapped_path, mapped_path, ambiguous_path, focus_path };
+	const int64_t n = (int64_t)fq->head.size();
+	auto emit = [&](std::string &o, int64_t i, const char *rid) {
+		const char *h = fq->raw.data() + fq->head[i];
+		o.push_back('@');
+		if (rid) { // Bio's writer: description is kept; it equals the title only if its first word is the (new) id
+			const size_t rl = strlen(rid);
+			if (!((size_t)fq->id_len[i] == rl && memcmp(h, rid, rl) == 0)) { o.append(rid, rl); o.push_back(' '); }
+		}
+		o.append(h, (size_t)fq->head_len[i]);
+		o.push_back('\n');
+		o.append((const char*)fq->cat.data() + fq->off[i], (size_t)(fq->off[i + 1] - fq->off[i]));
+		o.append("\n+\n", 3);
+		const char *q = fq->qual_in_extra[i] ? fq->extra.data() + fq->qual[i] : fq->raw.data() + fq->qual[i];
+		o.append(q, (size_t)fq->qual_len[i]);
+		o.push_back('\n');
+	};
+	{ // size the sinks once: a record costs its header, sequence and quality plus separators (and the new id when mapped)
+		size_t need[4] = {0, 0, 0, 0};
+		for (int64_t i = 0; i < n; ++i) {
+			const int d = dest[i];
+			if (d < 0 || d > 2) continue;
+			const size_t rec = (size_t)fq->head_len[i] + (size_t)(fq->off[i + 1] - fq->off[i]) + (size_t)fq->qual_len[i] + 8;
+			need[d] += rec + (d == 1 && new_id && new_id[i] ? strlen(new_id[i]) + 1 : 0);
+			if (focus && focus[i] && focus_path) need[3] += rec;
+		}
+		for (int k = 0; k < 4; ++k) if (paths[k]) sink[k].reserve(need[k] + 16);
+	}
+	for (int64_t i = 0; i < n; ++i) {
+		const int d = dest[i];
+		if (d < 0 || d > 2) continue;
+		if (focus && focus[i] && focus_path) emit(sink[3], i, nullptr);
+		if (!paths[d]) continue;
+		if (d == 1 && (!new_id || !new_id[i])) throw mb_error(MB_ERR_ARG, "mapped read without a new id");
+		emit(sink[d], i, d == 1 ? new_id[i] : nullptr);
+	}
+	for (int k = 0; k < 4; ++k) {
+		if (!paths[k]) continue;
+		FILE *fp = fopen(paths[k], "ab");
+		if (!fp) throw mb_error(MB_ERR_IO, std::string("cannot append to ") + paths[k]);
+		const bool ok = sink[k].empty() || fwrite(sink[k].data(), 1, sink[k].size(), fp) == sink[k].size();
+		if (fclose(fp) != 0 || !ok) throw mb_error(MB_ERR_IO, std::string("write failed: ") + paths[k]);
+	}
+	API_END
+}
+
+extern "C" void mb_fastq_free(mb_fastq_t *fq) { delete fq; }

@@ -171,9 +171,10 @@ class Aligner:
                          int(hits.blen[i]), int(hits.nm[i]), cigar, int(hits.dp_max[i]), rid)
 
     # ---- batched entry (the product path) ----
-    def map_batch(self, seqs=None, cat: np.ndarray | None = None, off: np.ndarray | None = None) -> Hits:
+    def map_batch(self, seqs=None, cat: np.ndarray | None = None, off: np.ndarray | None = None, cigars: bool = True) -> Hits:
         """Map many reads in one device pipeline.  Either `seqs` (list of bytes/str/uint8 arrays) or a
-        pre-concatenated (cat uint8[total], off int64[n+1]) pair.  Thread-safe."""
+        pre-concatenated (cat uint8[total], off int64[n+1]) pair.  `cigars=False` skips the device->host copy of the CIGAR
+        pool (monica reads only ctg / NM / mlen).  Thread-safe."""
         if self._idx is None:
             raise _lib.MonicaB200Error(-1, "empty index")
         if cat is None:
@@ -188,8 +189,8 @@ class Aligner:
         n = len(off) - 1
         h = C.c_void_p()
         st = Stats()
-        check(lib().mb_map_batch(self._idx, C.byref(self.opt), cat.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p),
-                                 n, C.byref(h), C.byref(st)))
+        check(lib().mb_map_batch_ex(self._idx, C.byref(self.opt), cat.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p),
+                                    n, 3 if cigars else 1, C.byref(h), C.byref(st)))
         self.last_stats = st.as_dict()
         return Hits(h, n)
 

@@ -191,3 +191,81 @@ def test_reference_golden_is_current(ref_aligner, small_case):
     want = json.load(open(os.path.join(GOLDEN, "ref_aligner.json")))
     got = _run(ref_aligner, names, seqs, reads, "query_length", True, ["Species_1"], False)
     assert json.loads(json.dumps(got)) == want["mode=query_length,two_indexes=True"]
+
+
+def test_native_fastq_ingest_and_routing_equal_python(tmp_path):
+    """mb_fastq_load / mb_fastq_route (host side of the C ABI, no device) against monica_b200.fastx, which mirrors
+    Bio.SeqIO: same records, and byte-identical routed files incl. the id rewrite of mapped reads."""
+    import ctypes as C
+    import gzip
+    import numpy as np
+    from monica_b200 import _lib, fastx
+    L = _lib.lib()
+    rng = np.random.default_rng(3)
+    recs = []
+    for i in range(60):
+        n = int(rng.integers(0, 400)) if i % 13 else 0
+        seq = "".join(rng.choice(list("ACGTN"), n))
+        qual = "".join(chr(int(c)) for c in rng.integers(33, 74, n))
+        head = f"read{i}" + ("" if i % 3 == 0 else f" runid=abc{i} ch={i % 7}")
+        recs.append((head, seq, qual))
+    plain = tmp_path / "a.fastq"
+    with open(plain, "w") as fh:
+        for k, (h, s, q) in enumerate(recs):
+            if k % 5 == 4 and len(s) > 120:     # multi-line record
+                fh.write(f"@{h}\n{s[:60]}\n{s[60:]}\n+{h}\n{q[:100]}\n{q[100:]}\n")
+            else:
+                fh.write(f"@{h}\n{s}\n+\n{q}\n")
+        fh.write("\n")
+    gz = tmp_path / "b.fastq.gz"
+    with open(plain, "rb") as fi, gzip.open(gz, "wb") as fo:
+        fo.write(fi.read())
+    want = list(fastx.parse(str(plain), "fastq"))
+    assert len(want) == len(recs)
+    for path in (plain, gz):
+        fq = C.c_void_p()
+        _lib.check(L.mb_fastq_load(os.fsencode(str(path)), C.byref(fq)))
+        n = L.mb_fastq_n(fq)
+        assert n == len(want) and L.mb_fastq_ids_unique(fq) == 1
+        offp = C.POINTER(C.c_int64)()
+        catp = L.mb_fastq_seqs(fq, C.byref(offp))
+        off = np.ctypeslib.as_array(offp, shape=(n + 1,))
+        cat = np.ctypeslib.as_array(catp, shape=(int(off[-1]),)).tobytes() if off[-1] else b""
+        for i, r in enumerate(want):
+            assert cat[off[i]:off[i + 1]].decode() == str(r.seq)
+            ln, il = C.c_int64(), C.c_int32()
+            hp = L.mb_fastq_header(fq, i, C.byref(ln), C.byref(il))
+            head = C.string_at(hp, ln.value).decode()
+            assert head == r.description and head[:il.value] == r.id
+        # routing: every third read mapped with a new id, some ambiguous, some focus
+        dest = np.array([(1 if i % 3 == 0 else 2 if i % 7 == 1 else 0) for i in range(n)], np.int8)
+        new_ids = (C.c_char_p * n)()
+        for i in range(n):
+            if dest[i] == 1:
+                new_ids[i] = (b"read%d" % i) if i % 9 == 0 else b"Escherichia_coli"    # i % 9 == 0: new id == old id
+        focus = np.array([1 if (dest[i] == 1 and i % 2 == 0) else 0 for i in range(n)], np.uint8)
+        out = tmp_path / ("out_" + path.name)
+        out.mkdir()
+        paths = [os.fsencode(str(out / k)) for k in ("mapped", "unmapped", "ambiguous", "focus")]
+        for _ in range(2):   # append mode: two rounds
+            _lib.check(L.mb_fastq_route(fq, dest.ctypes.data_as(C.c_void_p), C.cast(new_ids, C.c_void_p), focus.ctypes.data_as(C.c_void_p), *paths))
+        L.mb_fastq_free(fq)
+        exp = {"mapped": "", "unmapped": "", "ambiguous": "", "focus": ""}
+        for i, r in enumerate(want):
+            if dest[i] == 1:
+                if focus[i]:
+                    exp["focus"] += r.format_fastq()
+                r2 = fastx.SeqRecord(new_ids[i].decode(), r.description, str(r.seq), r.qual)
+                exp["mapped"] += r2.format_fastq()
+            else:
+                exp["ambiguous" if dest[i] == 2 else "unmapped"] += r.format_fastq()
+        for k, v in exp.items():
+            assert open(out / k).read() == v + v, k
+    # duplicate ids are detected
+    dup = tmp_path / "d.fastq"
+    dup.write_text("@x 1\nACGT\n+\nIIII\n@y\nAC\n+\nII\n@x 2\nGG\n+\nII\n")
+    fq = C.c_void_p()
+    _lib.check(L.mb_fastq_load(os.fsencode(str(dup)), C.byref(fq)))
+    assert L.mb_fastq_n(fq) == 3 and L.mb_fastq_ids_unique(fq) == 0
+    L.mb_fastq_free(fq)
+    assert L.mb_fastq_load(os.fsencode(str(tmp_path / "missing.fastq")), C.byref(fq)) != 0
