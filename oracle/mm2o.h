@@ -161,6 +161,7 @@ void mm2o_trace_destroy(mm2o_trace_t *t);
 void mm2o_map_batch(const mm2o_idx_t *mi, const mm2o_opt_t *opt, int n, const char *cat, const int64_t *off, int n_threads, mm2o_result_t **results);
 
 /* stand-alone DP entry for kernel parity tests */
+void mm2o_ksw_set_simd(int on);   /* 1: SSE4.1 16-lane core (default), 0: scalar statement of the same lanes */
 void mm2o_ksw_extd2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat,
 					int8_t q, int8_t e, int8_t q2, int8_t e2, int w, int zdrop, int end_bonus, int flag, ksw_extz_t *ez);
 void mm2o_gen_simple_mat(int m, int8_t *mat, int8_t a, int8_t b, int8_t sc_ambi);

@@ -13,6 +13,15 @@
 #include <string.h>
 #include <assert.h>
 #include "mm2o.h"
+#ifdef __SSE4_1__
+#include <smmintrin.h>
+#endif
+
+/* 1 (default): the anti-diagonal core runs 16 int8 lanes per step with SSE4.1, the way upstream's ksw2_extd2_sse.c does,
+ * so the CPU baseline has the speed class of real mappy; 0: the scalar statement of the same lanes.  Both produce identical
+ * bytes (tests/test_oracle_cpu.py compares them). */
+int mm2o_ksw_simd = 1;
+void mm2o_ksw_set_simd(int on) { mm2o_ksw_simd = on; }
 
 void mm2o_gen_simple_mat(int m, int8_t *mat, int8_t a, int8_t b, int8_t sc_ambi)
 {
@@ -206,6 +215,17 @@ void mm2o_ksw_extd2(int qlen, const uint8_t *query, int tlen, const uint8_t *tar
 			u[r] = r == 0? -q - e : r < long_thres? -e : r == long_thres? long_diff : -e2;
 		}
 		/* loop fission: set scores first (16-byte unaligned chunks from st0; may overrun into sf like upstream) */
+#ifdef __SSE4_1__
+		if (mm2o_ksw_simd) {
+			const __m128i m1_ = _mm_set1_epi8(m1), mch_ = _mm_set1_epi8(sc_mch), mis_ = _mm_set1_epi8(sc_mis), scn_ = _mm_set1_epi8(sc_N);
+			for (t = st0; t <= en0; t += 16) {
+				__m128i sq = _mm_loadu_si128((const __m128i*)(sf + t)), sq2 = _mm_loadu_si128((const __m128i*)(qrr + t));
+				__m128i isn = _mm_or_si128(_mm_cmpeq_epi8(sq, m1_), _mm_cmpeq_epi8(sq2, m1_));
+				__m128i sc = _mm_blendv_epi8(mis_, mch_, _mm_cmpeq_epi8(sq, sq2));
+				_mm_storeu_si128((__m128i*)(s + t), _mm_blendv_epi8(sc, scn_, isn));
+			}
+		} else
+#endif
 		for (t = st0; t <= en0; t += 16) {
 			int l;
 			for (l = 0; l < 16; ++l) {
@@ -219,6 +239,54 @@ void mm2o_ksw_extd2(int qlen, const uint8_t *query, int tlen, const uint8_t *tar
 			int8_t x1c = x1, x21c = x21, v1c = v1;
 			uint8_t *pr = with_cigar? p + ((size_t)r * n_col_ - st / 16) * 16 : 0;
 			if (with_cigar) off[r] = st, off_end[r] = en;
+#ifdef __SSE4_1__
+			if (mm2o_ksw_simd) {
+				const __m128i zero_ = _mm_setzero_si128(), q_ = _mm_set1_epi8(q), q2_ = _mm_set1_epi8(q2), qe_ = _mm_set1_epi8(qe), qe2_ = _mm_set1_epi8(qe2);
+				const __m128i mch_ = _mm_set1_epi8(sc_mch), one_ = _mm_set1_epi8(1), two_ = _mm_set1_epi8(2), three_ = _mm_set1_epi8(3), four_ = _mm_set1_epi8(4);
+				const __m128i f08 = _mm_set1_epi8(0x08), f10 = _mm_set1_epi8(0x10), f20 = _mm_set1_epi8(0x20), f40 = _mm_set1_epi8(0x40);
+				__m128i x1v = _mm_cvtsi32_si128((uint8_t)x1), x21v = _mm_cvtsi32_si128((uint8_t)x21), v1v = _mm_cvtsi32_si128((uint8_t)v1);
+				const int right = !!(flag & KSW_EZ_RIGHT);
+				for (t = st; t <= en; t += 16) {
+					__m128i z = _mm_loadu_si128((const __m128i*)(s + t));
+					__m128i xt = _mm_loadu_si128((const __m128i*)(x + t)), vt = _mm_loadu_si128((const __m128i*)(v + t));
+					__m128i x2t = _mm_loadu_si128((const __m128i*)(x2 + t)), ut = _mm_loadu_si128((const __m128i*)(u + t));
+					__m128i xt1 = _mm_or_si128(_mm_slli_si128(xt, 1), x1v);     x1v = _mm_srli_si128(xt, 15);   /* lane k sees element t+k-1 */
+					__m128i vt1 = _mm_or_si128(_mm_slli_si128(vt, 1), v1v);     v1v = _mm_srli_si128(vt, 15);
+					__m128i x2t1 = _mm_or_si128(_mm_slli_si128(x2t, 1), x21v);  x21v = _mm_srli_si128(x2t, 15);
+					__m128i a = _mm_add_epi8(xt1, vt1), b = _mm_add_epi8(_mm_loadu_si128((const __m128i*)(y + t)), ut);
+					__m128i a2 = _mm_add_epi8(x2t1, vt1), b2 = _mm_add_epi8(_mm_loadu_si128((const __m128i*)(y2 + t)), ut);
+					__m128i d, tmp;
+					if (!right) {
+						d = _mm_and_si128(_mm_cmpgt_epi8(a, z), one_);          z = _mm_max_epi8(z, a);
+						d = _mm_blendv_epi8(d, two_, _mm_cmpgt_epi8(b, z));      z = _mm_max_epi8(z, b);
+						d = _mm_blendv_epi8(d, three_, _mm_cmpgt_epi8(a2, z));   z = _mm_max_epi8(z, a2);
+						d = _mm_blendv_epi8(d, four_, _mm_cmpgt_epi8(b2, z));    z = _mm_max_epi8(z, b2);
+					} else {
+						d = _mm_andnot_si128(_mm_cmpgt_epi8(z, a), one_);        z = _mm_max_epi8(z, a);
+						d = _mm_blendv_epi8(two_, d, _mm_cmpgt_epi8(z, b));      z = _mm_max_epi8(z, b);
+						d = _mm_blendv_epi8(three_, d, _mm_cmpgt_epi8(z, a2));   z = _mm_max_epi8(z, a2);
+						d = _mm_blendv_epi8(four_, d, _mm_cmpgt_epi8(z, b2));    z = _mm_max_epi8(z, b2);
+					}
+					z = _mm_min_epi8(z, mch_);
+					_mm_storeu_si128((__m128i*)(u + t), _mm_sub_epi8(z, vt1));
+					_mm_storeu_si128((__m128i*)(v + t), _mm_sub_epi8(z, ut));
+					tmp = _mm_sub_epi8(z, q_);  a = _mm_sub_epi8(a, tmp);   b = _mm_sub_epi8(b, tmp);
+					tmp = _mm_sub_epi8(z, q2_); a2 = _mm_sub_epi8(a2, tmp); b2 = _mm_sub_epi8(b2, tmp);
+					if (!right) {
+						tmp = _mm_cmpgt_epi8(a, zero_);  _mm_storeu_si128((__m128i*)(x + t),  _mm_sub_epi8(_mm_and_si128(tmp, a), qe_));   d = _mm_or_si128(d, _mm_and_si128(tmp, f08));
+						tmp = _mm_cmpgt_epi8(b, zero_);  _mm_storeu_si128((__m128i*)(y + t),  _mm_sub_epi8(_mm_and_si128(tmp, b), qe_));   d = _mm_or_si128(d, _mm_and_si128(tmp, f10));
+						tmp = _mm_cmpgt_epi8(a2, zero_); _mm_storeu_si128((__m128i*)(x2 + t), _mm_sub_epi8(_mm_and_si128(tmp, a2), qe2_)); d = _mm_or_si128(d, _mm_and_si128(tmp, f20));
+						tmp = _mm_cmpgt_epi8(b2, zero_); _mm_storeu_si128((__m128i*)(y2 + t), _mm_sub_epi8(_mm_and_si128(tmp, b2), qe2_)); d = _mm_or_si128(d, _mm_and_si128(tmp, f40));
+					} else {
+						tmp = _mm_cmpgt_epi8(zero_, a);  _mm_storeu_si128((__m128i*)(x + t),  _mm_sub_epi8(_mm_andnot_si128(tmp, a), qe_));   d = _mm_or_si128(d, _mm_andnot_si128(tmp, f08));
+						tmp = _mm_cmpgt_epi8(zero_, b);  _mm_storeu_si128((__m128i*)(y + t),  _mm_sub_epi8(_mm_andnot_si128(tmp, b), qe_));   d = _mm_or_si128(d, _mm_andnot_si128(tmp, f10));
+						tmp = _mm_cmpgt_epi8(zero_, a2); _mm_storeu_si128((__m128i*)(x2 + t), _mm_sub_epi8(_mm_andnot_si128(tmp, a2), qe2_)); d = _mm_or_si128(d, _mm_andnot_si128(tmp, f20));
+						tmp = _mm_cmpgt_epi8(zero_, b2); _mm_storeu_si128((__m128i*)(y2 + t), _mm_sub_epi8(_mm_andnot_si128(tmp, b2), qe2_)); d = _mm_or_si128(d, _mm_andnot_si128(tmp, f40));
+					}
+					if (with_cigar) _mm_storeu_si128((__m128i*)(pr + t), d);
+				}
+			} else
+#endif
 			for (t = st; t <= en; ++t) {
 				int8_t z, a, b, a2, b2, xt1, x2t1, vt1, ut, tmp, d;
 				z = s[t];

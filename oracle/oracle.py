@@ -160,6 +160,11 @@ def sketch(seq, w: int = 10, k: int = 15, rid: int = 0) -> np.ndarray:
     return out[:n].copy()
 
 
+def set_simd(on: bool) -> None:
+    """Choose the SSE4.1 (default) or the scalar statement of the DP core; both give identical bytes."""
+    lib().mm2o_ksw_set_simd(1 if on else 0)
+
+
 def ksw_cells(qlen: int, tlen: int, w: int) -> int:
     return lib().mm2o_ksw_cells(qlen, tlen, w)
 

@@ -295,3 +295,27 @@ def test_golden_vectors(oracle):
             assert [h[f] for f in fields] == w.tolist()
     m = oracle.sketch(g["read_cat"][g["read_off"][3]:g["read_off"][4]])
     assert np.array_equal(m, g["sketch_read3"])
+
+
+def test_extd2_simd_core_equals_scalar(oracle):
+    """The oracle's SSE4.1 anti-diagonal core (the speed class of upstream's ksw2_extd2_sse) and its scalar statement give
+    identical scores, end points and CIGARs over shapes, bands and all flag combinations the aligner uses."""
+    rng = np.random.default_rng(91)
+    try:
+        for (ql, tl) in [(1, 1), (5, 40), (40, 5), (16, 16), (17, 33), (200, 230), (255, 257), (700, 900), (1200, 300)]:
+            t = rng.integers(0, 4, tl).astype(np.uint8)
+            q = rng.integers(0, 4, ql).astype(np.uint8)
+            n = min(ql, tl)
+            q[:n] = np.where(rng.random(n) < 0.85, t[:n], q[:n])
+            if ql > 20:
+                q[9] = 4
+            for flag, zd, eb in ((0x08, 400, -1), (0x00, 400, -1), (0x40, 100, -1), (0x40 | 0x02 | 0x80, 200, 10), (0x01 | 0x40, 400, -1)):
+                for w in (751, 60):
+                    oracle.set_simd(False)
+                    a = oracle.ksw_extd2(q, t, w=w, zdrop=zd, end_bonus=eb, flag=flag)
+                    oracle.set_simd(True)
+                    b = oracle.ksw_extd2(q, t, w=w, zdrop=zd, end_bonus=eb, flag=flag)
+                    for k in a:
+                        assert np.array_equal(a[k], b[k]), (ql, tl, hex(flag), w, k)
+    finally:
+        oracle.set_simd(True)
