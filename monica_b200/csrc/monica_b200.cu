@@ -75,6 +75,7 @@ struct ThreadCtx {
 	// warps still on their last task pair) overlaps the ramp-up of the next instead of idling the GPU 13 times per pass
 	cudaStream_t stf[2] = {};
 	cudaEvent_t ev_f[2] = {}, ev_fork = nullptr;
+	std::vector<cudaEvent_t> feed_events;   // host->device pieces of mb_map_batch (SketchFeed)
 	Arena ar;
 	int num_sms = 148;
 	uint8_t *h_pin = nullptr; size_t h_pin_cap = 0;   // pinned staging for reads
@@ -99,6 +100,7 @@ struct ThreadCtx {
 			if (ev_fast_done) cudaEventDestroy(ev_fast_done);
 			for (int i = 0; i < 2; ++i) { if (stf[i]) cudaStreamDestroy(stf[i]); if (ev_f[i]) cudaEventDestroy(ev_f[i]); }
 			if (ev_fork) cudaEventDestroy(ev_fork);
+			for (cudaEvent_t e : feed_events) cudaEventDestroy(e);
 		}
 	}
 };
@@ -841,6 +843,7 @@ struct DevPart {
 	int64_t n_h = 0, n_c = 0;
 	mb_stats_t S;
 	std::exception_ptr err;
+	const SketchFeed *feed = nullptr;     // reads still on the host: copy, encode and sketch piecewise (single-piece batches)
 };
 
 // the whole device pipeline of one sub-batch on the stream / arena of `c`; synchronises c.st before returning
@@ -864,7 +867,7 @@ static void map_device_part(mb_index *ix, const mb_opt_t &opt_in, DevPart &part)
 	// K1
 	tm.start();
 	SketchOut so;
-	run_sketch(ar, st, d_codes, d_off, n_reads, total, ix->w, ix->k, so, &nl);
+	run_sketch(ar, st, d_codes, d_off, n_reads, total, ix->w, ix->k, so, &nl, part.feed);
 	S.ms_sketch = tm.stop(); S.n_mini = so.n_mini;
 	// K2 + K2b
 	tm.start();
@@ -1040,7 +1043,7 @@ static int mb_n_parts(int32_t n_reads, int64_t total)
 // concurrently on their own streams / arenas / host threads; results are concatenated in read order, so the outcome does
 // not depend on the number of pieces.
 static mb_hits *map_device(mb_index *ix, const mb_opt_t &opt, ThreadCtx &c, const uint8_t *d_codes, const int64_t *d_off, const int64_t *h_off,
-                           int32_t n_reads, int64_t total, int want_hits /* bit 0: hit fields, bit 1: CIGARs */, mb_stats_t *stats)
+                           int32_t n_reads, int64_t total, int want_hits /* bit 0: hit fields, bit 1: CIGARs */, mb_stats_t *stats, const SketchFeed *feed = nullptr)
 {
 	auto t_begin = std::chrono::steady_clock::now();
 	std::unique_ptr<mb_hits> H(new mb_hits());
@@ -1053,6 +1056,11 @@ static mb_hits *map_device(mb_index *ix, const mb_opt_t &opt, ThreadCtx &c, cons
 	c.last_parts.clear(); c.last_n_reads = n_reads; c.last_index = ix;
 	if (n_reads == 0) { if (stats) *stats = S; return H.release(); }
 	const int K = mb_n_parts(n_reads, total);
+	if (feed && K > 1) { // several pieces read the codes from other streams: finish the upload first
+		CK(cudaMemcpyAsync(feed->d_ascii, feed->h_ascii, (size_t)total, cudaMemcpyHostToDevice, c.st));
+		k_encode_nt4<<<(unsigned)cdiv(cdiv(total, 16), 256), 256, 0, c.st>>>(feed->d_ascii, feed->d_codes, total);
+		feed = nullptr;
+	}
 	while ((int)c.helpers.size() < K - 1) c.helpers.push_back(make_ctx(c.device));
 	std::vector<DevPart> parts(K);
 	// cut points: first read whose start offset reaches the k-th share of the bases
@@ -1071,6 +1079,7 @@ static mb_hits *map_device(mb_index *ix, const mb_opt_t &opt, ThreadCtx &c, cons
 		const int64_t base = h_off[cut[k]] & ~(int64_t)15; // keep the piece's code pointer 16-byte aligned (vector loads); its first
 		p.total = h_off[cut[k + 1]] - base;                 // read then starts at offset 0..15 instead of 0
 		p.d_codes = d_codes + base;
+		p.feed = feed;
 		if (k > 0) p.c->ar.reset();
 		if (K == 1) p.d_off = d_off;
 		else {
@@ -1141,7 +1150,8 @@ static mb_hits *map_device(mb_index *ix, const mb_opt_t &opt, ThreadCtx &c, cons
 	return H.release();
 }
 
-static void upload_reads(ThreadCtx &c, const uint8_t *cat, const int64_t *off, int32_t n_reads, uint8_t **d_codes, int64_t **d_off, int64_t *total, bool persistent)
+static void upload_reads(ThreadCtx &c, const uint8_t *cat, const int64_t *off, int32_t n_reads, uint8_t **d_codes, int64_t **d_off, int64_t *total, bool persistent,
+                         SketchFeed *feed = nullptr)
 {
 	cudaStream_t st = c.st;
 	*total = n_reads > 0 ? off[n_reads] : 0;
@@ -1153,8 +1163,12 @@ static void upload_reads(ThreadCtx &c, const uint8_t *cat, const int64_t *off, i
 	uint8_t *d_ascii = c.ar.get<uint8_t>(*total + 32);
 	if (persistent) { CK(cudaMalloc(d_codes, *total + 32)); CK(cudaMalloc(d_off, (n_reads + 1) * 8)); }
 	else { *d_codes = c.ar.get<uint8_t>(*total + 32); *d_off = c.ar.get<int64_t>(n_reads + 1); }
-	if (*total) CK(cudaMemcpyAsync(d_ascii, cat, *total, cudaMemcpyHostToDevice, st));
 	CK(cudaMemcpyAsync(*d_off, off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+	if (feed) { // the caller overlaps the ASCII copy with the sketch (run_sketch, SketchFeed)
+		feed->h_ascii = cat, feed->d_ascii = d_ascii, feed->d_codes = *d_codes, feed->copy_st = c.stf[0], feed->events = &c.feed_events;
+		return;
+	}
+	if (*total) CK(cudaMemcpyAsync(d_ascii, cat, *total, cudaMemcpyHostToDevice, st));
 	if (*total) k_encode_nt4<<<(unsigned)cdiv(cdiv(*total, 16), 256), 256, 0, st>>>(d_ascii, *d_codes, *total);
 }
 
@@ -1175,10 +1189,12 @@ static int map_batch_impl(mb_index_t *ix, const mb_opt_t *opt, const uint8_t *ca
 	c.ar.reset();
 	uint8_t *d_codes; int64_t *d_off; int64_t total;
 	Timer tm(c.st); tm.start();
-	upload_reads(c, cat, off, n_reads, &d_codes, &d_off, &total, false);
+	SketchFeed feed;
+	const bool use_feed = n_reads > 0 && off[n_reads] >= ((int64_t)64 << 20);  // worth overlapping from ~64 MB of reads (measured: smaller batches lose)
+	upload_reads(c, cat, off, n_reads, &d_codes, &d_off, &total, false, use_feed ? &feed : nullptr);
 	float ms_h2d = tm.stop();
 	if (stats) stats->ms_h2d = ms_h2d;
-	*out = map_device(ix, *opt, c, d_codes, d_off, off, n_reads, total, want, stats);
+	*out = map_device(ix, *opt, c, d_codes, d_off, off, n_reads, total, want, stats, use_feed ? &feed : nullptr);
 	if (stats) { stats->ms_h2d = ms_h2d; stats->n_launches += 1; }
 	API_END
 }

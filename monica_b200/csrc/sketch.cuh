@@ -156,10 +156,10 @@ template <int W, bool WRITE>
 __global__ void __launch_bounds__(SK_TPB)
 k_sketch(const uint8_t *__restrict__ codes, const int64_t *__restrict__ off, int n_reads, int64_t total,
          int w, int k, int32_t *__restrict__ chunk_cnt, int32_t *__restrict__ read_cnt,
-         const int64_t *__restrict__ chunk_off, mb128 *__restrict__ out, mb128 *__restrict__ stage, int *__restrict__ overflow)
+         const int64_t *__restrict__ chunk_off, mb128 *__restrict__ out, mb128 *__restrict__ stage, int *__restrict__ overflow, int64_t cta0)
 {
 	extern __shared__ __align__(16) uint8_t sm[];
-	const int64_t cta_base = (int64_t)blockIdx.x * SK_SPAN;
+	const int64_t cta_base = ((int64_t)blockIdx.x + cta0) * SK_SPAN;
 	const int64_t win_lo = cta_base - SK_WARM; // logical smem index 0 <-> global win_lo (may be negative)
 	// ---- stage [win_lo, cta_base + SK_SPAN) with coalesced 16-byte loads; row padding of one word per 256 bytes ----
 	{
@@ -182,7 +182,7 @@ k_sketch(const uint8_t *__restrict__ codes, const int64_t *__restrict__ off, int
 	}
 	__syncthreads();
 	const int64_t s = cta_base + (int64_t)threadIdx.x * SK_CHUNK;
-	const int64_t chunk = (int64_t)blockIdx.x * SK_TPB + threadIdx.x;
+	const int64_t chunk = ((int64_t)blockIdx.x + cta0) * SK_TPB + threadIdx.x;
 	if (s >= total) { if (!WRITE && chunk_cnt && chunk * SK_CHUNK < total + SK_CHUNK) {} return; }
 	const int64_t e = s + SK_CHUNK < total ? s + SK_CHUNK : total;
 	const uint64_t mask = (1ULL << 2 * k) - 1, shift1 = 2 * (k - 1);
@@ -270,9 +270,20 @@ struct SketchOut {
 	int64_t n_mini = 0;
 };
 
+// Optional input feed for run_sketch: the ASCII reads are still in (pinned) host memory; they are copied in pieces on a
+// second stream and each piece is encoded and sketched as soon as it has landed, so the host->device copy of a batch hides
+// behind the sketch kernel instead of preceding it.
+struct SketchFeed {
+	const uint8_t *h_ascii = nullptr;   // host reads (concatenated ASCII)
+	uint8_t *d_ascii = nullptr;         // device staging, total + 32 bytes
+	uint8_t *d_codes = nullptr;         // nt4 codes to produce (== `codes` passed to run_sketch)
+	cudaStream_t copy_st = nullptr;
+	std::vector<cudaEvent_t> *events = nullptr; // pool, grown on demand
+};
+
 // codes: device nt4 bytes [total]; d_off: device offsets [n_reads+1].  Synchronises once to learn n_mini.
 static void run_sketch(Arena &ar, cudaStream_t st, const uint8_t *codes, const int64_t *d_off, int n_reads, int64_t total,
-                       int w, int k, SketchOut &o, int64_t *n_launch)
+                       int w, int k, SketchOut &o, int64_t *n_launch, const SketchFeed *feed = nullptr)
 {
 	if (w != 10) throw mb_error(MB_ERR_ARG, "sketch kernel is instantiated for w=10 (map-ont) only");
 	if (k < 1 || k > 28) throw mb_error(MB_ERR_ARG, "k out of range");
@@ -297,8 +308,25 @@ static void run_sketch(Arena &ar, cudaStream_t st, const uint8_t *codes, const i
 	mb128 *stage = ar.get<mb128>((size_t)n_chunks * SK_STAGE_CAP);
 	int *d_ovf = ar.get<int>(1);
 	CK(cudaMemsetAsync(d_ovf, 0, sizeof(int), st));
-	k_sketch<10, false><<<(unsigned)n_cta, SK_TPB, SK_SMEM_BYTES, st>>>(codes, d_off, n_reads, total, w, k, chunk_cnt, read_cnt, nullptr, nullptr, stage, d_ovf);
-	++*n_launch;
+	if (!feed) {
+		k_sketch<10, false><<<(unsigned)n_cta, SK_TPB, SK_SMEM_BYTES, st>>>(codes, d_off, n_reads, total, w, k, chunk_cnt, read_cnt, nullptr, nullptr, stage, d_ovf, 0);
+		++*n_launch;
+	} else {
+		// pieces of ~1/8 of the batch, whole CTA spans each; piece p is sketched while piece p+1 is in flight
+		int64_t per = cdiv(cdiv(n_cta, 8), 1); if (per < 1) per = 1;
+		int p = 0;
+		for (int64_t c0 = 0; c0 < n_cta; c0 += per, ++p) {
+			const int64_t c1 = c0 + per < n_cta ? c0 + per : n_cta;
+			const int64_t b0 = c0 * SK_SPAN, b1 = c1 * SK_SPAN < total ? c1 * SK_SPAN : total;
+			while ((int)feed->events->size() <= p) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); feed->events->push_back(e); }
+			CK(cudaMemcpyAsync(feed->d_ascii + b0, feed->h_ascii + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, feed->copy_st));
+			CK(cudaEventRecord((*feed->events)[p], feed->copy_st));
+			CK(cudaStreamWaitEvent(st, (*feed->events)[p], 0));
+			k_encode_nt4<<<(unsigned)cdiv(cdiv(b1 - b0, 16), 256), 256, 0, st>>>(feed->d_ascii + b0, feed->d_codes + b0, b1 - b0);
+			k_sketch<10, false><<<(unsigned)(c1 - c0), SK_TPB, SK_SMEM_BYTES, st>>>(codes, d_off, n_reads, total, w, k, chunk_cnt, read_cnt, nullptr, nullptr, stage, d_ovf, c0);
+			*n_launch += 2;
+		}
+	}
 	exclusive_scan<int32_t>(ar, st, chunk_cnt, chunk_off, n_chunks, n_launch);
 	exclusive_scan<int32_t>(ar, st, read_cnt, o.mini_off, n_reads, n_launch);
 	int64_t n_mini = 0; int h_ovf = 0;
@@ -310,7 +338,7 @@ static void run_sketch(Arena &ar, cudaStream_t st, const uint8_t *codes, const i
 	if (!h_ovf) { // the usual case: every chunk fitted its staging row, one 16-byte copy per minimizer finishes the job
 		k_sketch_compact<<<(unsigned)cdiv(n_chunks * 8, 256), 256, 0, st>>>(stage, chunk_cnt, chunk_off, n_chunks, o.mini);
 	} else {      // some 256-base chunk produced more than SK_STAGE_CAP minimizers (low-complexity sequence): re-run and write in place
-		k_sketch<10, true><<<(unsigned)n_cta, SK_TPB, SK_SMEM_BYTES, st>>>(codes, d_off, n_reads, total, w, k, nullptr, nullptr, chunk_off, o.mini, nullptr, nullptr);
+		k_sketch<10, true><<<(unsigned)n_cta, SK_TPB, SK_SMEM_BYTES, st>>>(codes, d_off, n_reads, total, w, k, nullptr, nullptr, chunk_off, o.mini, nullptr, nullptr, 0);
 	}
 	++*n_launch;
 }
