@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "sketch.cuh"
 #include "seed.cuh"
+#include "index_build.cuh"
 #include "chain.cuh"
 #include "glue.cuh"
 #include "align.cuh"
@@ -155,6 +156,11 @@ static ThreadCtx *make_ctx(int device)
 	return c;
 }
 
+template <typename T> static T d2h_scalar(const T *d, cudaStream_t st)
+{
+	T v; CK(cudaMemcpyAsync(&v, d, sizeof(T), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); return v;
+}
+
 // ---------------------------------------------------------------------------------------------
 // index
 // ---------------------------------------------------------------------------------------------
@@ -167,9 +173,11 @@ struct mb_index {
 	uint64_t sum_len = 0;
 	int64_t n_mini = 0, n_keys = 0;
 	int mid_occ = 0;
-	// host copies (kept for save)
+	// host copies (needed by mb_index_save only; filled lazily when the table was built on the device)
 	std::vector<uint64_t> h_hkey, h_hval, h_pos;
 	std::vector<uint32_t> h_S;
+	bool host_copies = true;
+	size_t cap = 0, n_pos = 0;
 	DevIndex d;
 	int64_t hbm_bytes = 0;
 };
@@ -274,18 +282,79 @@ static mb_index *index_build_impl(int device, int n_seq, const char *const *name
 	if (sum) k_encode_nt4<<<(unsigned)cdiv(cdiv((int64_t)sum, 16), 256), 256, 0, st>>>(d_ascii, d_codes, (int64_t)sum);
 	SketchOut so;
 	run_sketch(c.ar, st, d_codes, d_off, n_seq, (int64_t)sum, w, k, so, &nl);
-	std::vector<mb128> m(so.n_mini);
-	if (so.n_mini) CK(cudaMemcpyAsync(m.data(), so.mini, so.n_mini * sizeof(mb128), cudaMemcpyDeviceToHost, st));
+	// ---- sort, group, hash-insert on the device (index_build.cuh) ----
+	const int64_t n_m = so.n_mini;
+	ix->n_mini = n_m;
+	DevIndex &d = ix->d;
 	uint32_t *d_S = c.ar.get<uint32_t>(sum / 8 + 2);
 	if (sum) k_pack4<<<(unsigned)cdiv(cdiv((int64_t)sum, 8), 256), 256, 0, st>>>(d_codes, d_S, (int64_t)sum);
-	ix->h_S.assign((sum + 7) / 8, 0);
-	if (sum) CK(cudaMemcpyAsync(ix->h_S.data(), d_S, ix->h_S.size() * 4, cudaMemcpyDeviceToHost, st));
+	int64_t n_keys = 0, n_pos = 0;
+	mb128 *sorted = so.mini;
+	int64_t *start = nullptr, *moff = nullptr;
+	unsigned int *occ_hist = c.ar.get<unsigned int>(65536);
+	CK(cudaMemsetAsync(occ_hist, 0, 65536 * sizeof(unsigned int), st));
+	if (n_m > 0) {
+		mb128 *tmp = c.ar.get<mb128>(n_m);
+		sorted = radix_sort_minimizers(c.ar, st, so.mini, tmp, n_m, 2 * k);
+		int32_t *flag = c.ar.get<int32_t>(n_m);
+		int64_t *gid = c.ar.get<int64_t>(n_m + 1);
+		k_ib_flag<<<(unsigned)cdiv(n_m, 256), 256, 0, st>>>(sorted, n_m, flag);
+		exclusive_scan<int32_t>(c.ar, st, flag, gid, n_m, &nl);
+		n_keys = d2h_scalar(gid + n_m, st);
+		start = c.ar.get<int64_t>(n_keys + 1);
+		k_ib_start<<<(unsigned)cdiv(n_m, 256), 256, 0, st>>>(flag, gid, n_m, n_keys, start);
+		int32_t *mcnt = c.ar.get<int32_t>(n_keys);
+		moff = c.ar.get<int64_t>(n_keys + 1);
+		k_ib_multi<<<(unsigned)cdiv(n_keys, 256), 256, 0, st>>>(start, n_keys, mcnt, occ_hist);
+		exclusive_scan<int32_t>(c.ar, st, mcnt, moff, n_keys, &nl);
+		n_pos = d2h_scalar(moff + n_keys, st);
+	}
+	ix->n_keys = n_keys;
+	size_t cap = 1024; while (cap < (size_t)n_keys * 2 + 2) cap <<= 1;
+	int bits = 0; while (((size_t)1 << bits) < cap) ++bits;
+	ix->cap = cap, ix->n_pos = (size_t)n_pos;
+	CK(cudaMalloc(&d.hkey, cap * 8)); CK(cudaMalloc(&d.hval, cap * 8));
+	CK(cudaMalloc(&d.pos, ((size_t)n_pos + 1) * 8));
+	CK(cudaMalloc(&d.S, ((size_t)(sum + 7) / 8 + 1) * 4));
+	CK(cudaMalloc(&d.seq_off, (ix->offs.size() + 1) * 8));
+	CK(cudaMalloc(&d.seq_len, (ix->lens.size() + 1) * 4));
+	CK(cudaMemsetAsync(d.hkey, 0xff, cap * 8, st));
+	CK(cudaMemsetAsync(d.hval, 0, cap * 8, st));
+	d.hmask = cap - 1; d.hshift = 64 - bits;
+	if (n_keys > 0) k_ib_insert<<<(unsigned)cdiv(n_keys, 256), 256, 0, st>>>(sorted, start, moff, n_keys, (unsigned long long*)d.hkey, d.hval, d.hmask, d.hshift, d.pos);
+	if (sum) CK(cudaMemcpyAsync(d.S, d_S, ((size_t)(sum + 7) / 8) * 4, cudaMemcpyDeviceToDevice, st));
+	CK(cudaMemcpyAsync(d.seq_off, ix->offs.data(), ix->offs.size() * 8, cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(d.seq_len, ix->lens.data(), ix->lens.size() * 4, cudaMemcpyHostToDevice, st));
+	std::vector<unsigned int> h_occ(65536);
+	CK(cudaMemcpyAsync(h_occ.data(), occ_hist, 65536 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));
 	CK(cudaGetLastError());
-	index_build_table(ix.get(), m);
-	index_upload(ix.get());
+	// index.c mm_idx_cal_max_occ(mi, 2e-4): ks_ksmall(counts, (1-f)*n) + 1, from the occurrence histogram
+	if (n_keys > 0) {
+		size_t kth = (size_t)(uint32_t)((1. - (double)2e-4f) * (double)n_keys);
+		if (kth >= (size_t)n_keys) kth = (size_t)n_keys - 1;
+		size_t cum = 0; int v = 0;
+		for (v = 0; v < 65536; ++v) { cum += h_occ[v]; if (cum > kth) break; }
+		ix->mid_occ = v + 1;
+	} else ix->mid_occ = 1;
+	d.n_seq = (int)ix->names.size(); d.k = ix->k; d.w = ix->w; d.mid_occ = ix->mid_occ;
+	ix->hbm_bytes = (int64_t)(cap * 16 + (size_t)n_pos * 8 + ((size_t)(sum + 7) / 8) * 4 + ix->offs.size() * 12);
+	ix->host_copies = false;
 	c.ar.reset();
 	return ix.release();
+}
+
+// host copies of a device-built table (only mb_index_save needs them)
+static void index_ensure_host(mb_index *ix)
+{
+	if (ix->host_copies) return;
+	CK(cudaSetDevice(ix->device));
+	ix->h_hkey.resize(ix->cap); ix->h_hval.resize(ix->cap); ix->h_pos.resize(ix->n_pos); ix->h_S.resize((ix->sum_len + 7) / 8);
+	CK(cudaMemcpy(ix->h_hkey.data(), ix->d.hkey, ix->cap * 8, cudaMemcpyDeviceToHost));
+	CK(cudaMemcpy(ix->h_hval.data(), ix->d.hval, ix->cap * 8, cudaMemcpyDeviceToHost));
+	if (ix->n_pos) CK(cudaMemcpy(ix->h_pos.data(), ix->d.pos, ix->n_pos * 8, cudaMemcpyDeviceToHost));
+	if (!ix->h_S.empty()) CK(cudaMemcpy(ix->h_S.data(), ix->d.S, ix->h_S.size() * 4, cudaMemcpyDeviceToHost));
+	ix->host_copies = true;
 }
 
 extern "C" int mb_index_build(int device, int n_seq, const char *const *names, const uint8_t *const *seqs, const int64_t *lens, int w, int k, mb_index_t **out)
@@ -339,6 +408,7 @@ extern "C" int mb_index_save(const mb_index_t *ix, const char *path)
 {
 	API_BEGIN
 	if (!ix || !path) throw mb_error(MB_ERR_ARG, "bad arguments");
+	index_ensure_host(const_cast<mb_index*>(ix));
 	FILE *fp = fopen(path, "wb");
 	if (!fp) throw mb_error(MB_ERR_IO, std::string("cannot write ") + path);
 	const int b = ix->b;
@@ -549,10 +619,6 @@ struct Timer {
 	float stop() { cudaEventRecord(e[1], st); cudaEventSynchronize(e[1]); float ms = 0; cudaEventElapsedTime(&ms, e[0], e[1]); return ms; }
 };
 
-template <typename T> static T d2h_scalar(const T *d, cudaStream_t st)
-{
-	T v; CK(cudaMemcpyAsync(&v, d, sizeof(T), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); return v;
-}
 
 static DpScoring make_scoring(const mb_opt_t &o)
 {
