@@ -196,106 +196,22 @@ __global__ void k_pack4(const uint8_t *__restrict__ codes, uint32_t *__restrict_
 	S[w] = v;
 }
 
-static void index_upload(mb_index *ix)
+// minimizers (device, grouped arbitrarily, positions of one hash ascending) + 4-bit packed sequence (device) -> HBM-resident index
+static void index_finish_device(mb_index *ix, ThreadCtx &c, mb128 *d_mini, int64_t n_m, const uint32_t *d_S, int k)
 {
-	DevIndex &d = ix->d;
-	size_t cap = ix->h_hkey.size();
-	CK(cudaMalloc(&d.hkey, cap * 8)); CK(cudaMalloc(&d.hval, cap * 8));
-	CK(cudaMalloc(&d.pos, (ix->h_pos.size() + 1) * 8));
-	CK(cudaMalloc(&d.S, (ix->h_S.size() + 1) * 4));
-	CK(cudaMalloc(&d.seq_off, (ix->offs.size() + 1) * 8));
-	CK(cudaMalloc(&d.seq_len, (ix->lens.size() + 1) * 4));
-	CK(cudaMemcpy(d.hkey, ix->h_hkey.data(), cap * 8, cudaMemcpyHostToDevice));
-	CK(cudaMemcpy(d.hval, ix->h_hval.data(), cap * 8, cudaMemcpyHostToDevice));
-	if (!ix->h_pos.empty()) CK(cudaMemcpy(d.pos, ix->h_pos.data(), ix->h_pos.size() * 8, cudaMemcpyHostToDevice));
-	CK(cudaMemcpy(d.S, ix->h_S.data(), ix->h_S.size() * 4, cudaMemcpyHostToDevice));
-	CK(cudaMemcpy(d.seq_off, ix->offs.data(), ix->offs.size() * 8, cudaMemcpyHostToDevice));
-	CK(cudaMemcpy(d.seq_len, ix->lens.data(), ix->lens.size() * 4, cudaMemcpyHostToDevice));
-	d.hmask = cap - 1;
-	int bits = 0; while (((size_t)1 << bits) < cap) ++bits;
-	d.hshift = 64 - bits;
-	d.n_seq = (int)ix->names.size(); d.k = ix->k; d.w = ix->w; d.mid_occ = ix->mid_occ;
-	ix->hbm_bytes = (int64_t)(cap * 16 + ix->h_pos.size() * 8 + ix->h_S.size() * 4 + ix->offs.size() * 12);
-}
-
-// build the hash table from minimizers sorted by (hash, y): index.c worker_post() semantics
-static void index_build_table(mb_index *ix, std::vector<mb128> &m)
-{
-	std::sort(m.begin(), m.end(), [](const mb128 &a, const mb128 &b) {
-		uint64_t ha = a.x >> 8, hb = b.x >> 8;
-		return ha != hb ? ha < hb : a.y < b.y;
-	});
-	ix->n_mini = (int64_t)m.size();
-	size_t n_keys = 0;
-	for (size_t i = 0; i < m.size(); ++i) if (i == 0 || (m[i].x >> 8) != (m[i - 1].x >> 8)) ++n_keys;
-	ix->n_keys = (int64_t)n_keys;
-	size_t cap = 1024; while (cap < n_keys * 2 + 2) cap <<= 1;
-	int bits = 0; while (((size_t)1 << bits) < cap) ++bits;
-	ix->h_hkey.assign(cap, ~0ULL); ix->h_hval.assign(cap, 0);
-	ix->h_pos.clear();
-	std::vector<uint32_t> occ; occ.reserve(n_keys);
-	for (size_t i = 0; i < m.size();) {
-		size_t j = i; uint64_t h = m[i].x >> 8;
-		while (j < m.size() && (m[j].x >> 8) == h) ++j;
-		size_t n = j - i;
-		occ.push_back((uint32_t)n);
-		uint64_t slot = mb_slot_hash(h, 64 - bits) & (cap - 1);
-		while (ix->h_hkey[slot] != ~0ULL) slot = (slot + 1) & (cap - 1);
-		if (n == 1) { ix->h_hkey[slot] = h << 1 | 1; ix->h_hval[slot] = m[i].y; }
-		else {
-			ix->h_hkey[slot] = h << 1;
-			ix->h_hval[slot] = (uint64_t)ix->h_pos.size() << 32 | (uint32_t)n;
-			for (size_t k = i; k < j; ++k) ix->h_pos.push_back(m[k].y);
-		}
-		i = j;
-	}
-	// index.c mm_idx_cal_max_occ(mi, 2e-4): ks_ksmall(counts, (1-f)*n) + 1
-	if (!occ.empty()) {
-		size_t kth = (size_t)(uint32_t)((1. - (double)2e-4f) * occ.size());
-		if (kth >= occ.size()) kth = occ.size() - 1;
-		std::nth_element(occ.begin(), occ.begin() + kth, occ.end());
-		ix->mid_occ = (int)occ[kth] + 1;
-	} else ix->mid_occ = 1;
-}
-
-static mb_index *index_build_impl(int device, int n_seq, const char *const *names, const uint8_t *const *seqs, const int64_t *lens, int w, int k)
-{
-	ThreadCtx &c = get_ctx(device);
-	std::unique_ptr<mb_index> ix(new mb_index());
-	ix->device = device, ix->k = k, ix->w = w;
-	uint64_t sum = 0;
-	for (int i = 0; i < n_seq; ++i) {
-		if (lens[i] < 0 || lens[i] > 0x7fffffffLL) throw mb_error(MB_ERR_ARG, "contig longer than 2^31");
-		ix->names.push_back(names[i]); ix->lens.push_back((uint32_t)lens[i]); ix->offs.push_back(sum); sum += (uint64_t)lens[i];
-	}
-	ix->sum_len = sum;
-	c.ar.reset();
 	cudaStream_t st = c.st;
-	// upload contigs as one "read batch": the sketch kernel stores the sequence index in y>>32, which is mm_idx's rid
-	std::vector<int64_t> off(n_seq + 1, 0);
-	for (int i = 0; i < n_seq; ++i) off[i + 1] = off[i] + lens[i];
-	uint8_t *d_ascii = c.ar.get<uint8_t>(sum + 16), *d_codes = c.ar.get<uint8_t>(sum + 16);
-	int64_t *d_off = c.ar.get<int64_t>(n_seq + 1);
-	for (int i = 0; i < n_seq; ++i) if (lens[i]) CK(cudaMemcpyAsync(d_ascii + off[i], seqs[i], lens[i], cudaMemcpyHostToDevice, st));
-	CK(cudaMemcpyAsync(d_off, off.data(), (n_seq + 1) * 8, cudaMemcpyHostToDevice, st));
+	const uint64_t sum = ix->sum_len;
 	int64_t nl = 0;
-	if (sum) k_encode_nt4<<<(unsigned)cdiv(cdiv((int64_t)sum, 16), 256), 256, 0, st>>>(d_ascii, d_codes, (int64_t)sum);
-	SketchOut so;
-	run_sketch(c.ar, st, d_codes, d_off, n_seq, (int64_t)sum, w, k, so, &nl);
-	// ---- sort, group, hash-insert on the device (index_build.cuh) ----
-	const int64_t n_m = so.n_mini;
 	ix->n_mini = n_m;
 	DevIndex &d = ix->d;
-	uint32_t *d_S = c.ar.get<uint32_t>(sum / 8 + 2);
-	if (sum) k_pack4<<<(unsigned)cdiv(cdiv((int64_t)sum, 8), 256), 256, 0, st>>>(d_codes, d_S, (int64_t)sum);
 	int64_t n_keys = 0, n_pos = 0;
-	mb128 *sorted = so.mini;
+	mb128 *sorted = d_mini;
 	int64_t *start = nullptr, *moff = nullptr;
 	unsigned int *occ_hist = c.ar.get<unsigned int>(65536);
 	CK(cudaMemsetAsync(occ_hist, 0, 65536 * sizeof(unsigned int), st));
 	if (n_m > 0) {
 		mb128 *tmp = c.ar.get<mb128>(n_m);
-		sorted = radix_sort_minimizers(c.ar, st, so.mini, tmp, n_m, 2 * k);
+		sorted = radix_sort_minimizers(c.ar, st, d_mini, tmp, n_m, 2 * k);
 		int32_t *flag = c.ar.get<int32_t>(n_m);
 		int64_t *gid = c.ar.get<int64_t>(n_m + 1);
 		k_ib_flag<<<(unsigned)cdiv(n_m, 256), 256, 0, st>>>(sorted, n_m, flag);
@@ -340,6 +256,36 @@ static mb_index *index_build_impl(int device, int n_seq, const char *const *name
 	d.n_seq = (int)ix->names.size(); d.k = ix->k; d.w = ix->w; d.mid_occ = ix->mid_occ;
 	ix->hbm_bytes = (int64_t)(cap * 16 + (size_t)n_pos * 8 + ((size_t)(sum + 7) / 8) * 4 + ix->offs.size() * 12);
 	ix->host_copies = false;
+}
+
+static mb_index *index_build_impl(int device, int n_seq, const char *const *names, const uint8_t *const *seqs, const int64_t *lens, int w, int k)
+{
+	ThreadCtx &c = get_ctx(device);
+	std::unique_ptr<mb_index> ix(new mb_index());
+	ix->device = device, ix->k = k, ix->w = w;
+	uint64_t sum = 0;
+	for (int i = 0; i < n_seq; ++i) {
+		if (lens[i] < 0 || lens[i] > 0x7fffffffLL) throw mb_error(MB_ERR_ARG, "contig longer than 2^31");
+		ix->names.push_back(names[i]); ix->lens.push_back((uint32_t)lens[i]); ix->offs.push_back(sum); sum += (uint64_t)lens[i];
+	}
+	ix->sum_len = sum;
+	c.ar.reset();
+	cudaStream_t st = c.st;
+	// upload contigs as one "read batch": the sketch kernel stores the sequence index in y>>32, which is mm_idx's rid
+	std::vector<int64_t> off(n_seq + 1, 0);
+	for (int i = 0; i < n_seq; ++i) off[i + 1] = off[i] + lens[i];
+	uint8_t *d_ascii = c.ar.get<uint8_t>(sum + 16), *d_codes = c.ar.get<uint8_t>(sum + 16);
+	int64_t *d_off = c.ar.get<int64_t>(n_seq + 1);
+	for (int i = 0; i < n_seq; ++i) if (lens[i]) CK(cudaMemcpyAsync(d_ascii + off[i], seqs[i], lens[i], cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(d_off, off.data(), (n_seq + 1) * 8, cudaMemcpyHostToDevice, st));
+	int64_t nl = 0;
+	if (sum) k_encode_nt4<<<(unsigned)cdiv(cdiv((int64_t)sum, 16), 256), 256, 0, st>>>(d_ascii, d_codes, (int64_t)sum);
+	SketchOut so;
+	run_sketch(c.ar, st, d_codes, d_off, n_seq, (int64_t)sum, w, k, so, &nl);
+	// ---- sort, group, hash-insert on the device (index_build.cuh) ----
+	uint32_t *d_S = c.ar.get<uint32_t>(sum / 8 + 2);
+	if (sum) k_pack4<<<(unsigned)cdiv(cdiv((int64_t)sum, 8), 256), 256, 0, st>>>(d_codes, d_S, (int64_t)sum);
+	index_finish_device(ix.get(), c, so.mini, so.n_mini, d_S, k);
 	c.ar.reset();
 	return ix.release();
 }
@@ -503,8 +449,17 @@ extern "C" int mb_index_load(int device, const char *path, mb_index_t **out)
 	ix->h_S.assign((sum + 7) / 8, 0);
 	if (!ix->h_S.empty() && fread(ix->h_S.data(), 4, ix->h_S.size(), fp) != ix->h_S.size()) fail("damaged index (sequence)");
 	fclose(fp);
-	index_build_table(ix.get(), m);
-	index_upload(ix.get());
+	{ // same device pipeline as a fresh build: the positions of one hash come ascending out of the .mmi, the sort is stable
+		ThreadCtx &c = get_ctx(device);
+		c.ar.reset();
+		mb128 *d_m = c.ar.get<mb128>(m.size() + 1);
+		uint32_t *d_S = c.ar.get<uint32_t>(ix->h_S.size() + 2);
+		if (!m.empty()) CK(cudaMemcpyAsync(d_m, m.data(), m.size() * sizeof(mb128), cudaMemcpyHostToDevice, c.st));
+		if (!ix->h_S.empty()) CK(cudaMemcpyAsync(d_S, ix->h_S.data(), ix->h_S.size() * 4, cudaMemcpyHostToDevice, c.st));
+		index_finish_device(ix.get(), c, d_m, (int64_t)m.size(), d_S, ix->k);
+		ix->h_S.clear(); ix->h_S.shrink_to_fit();
+		c.ar.reset();
+	}
 	*out = ix.release();
 	API_END
 }
