@@ -745,7 +745,9 @@ struct DpRunner {
 			const bool wide = slice > DP_SMEM_PER_WARP;
 			const int wpc = wide ? 1 : DP_WARPS;
 			const int smem_per_warp = wide ? (int)(slice < DP_SMEM_MAX ? slice : DP_SMEM_MAX) : DP_SMEM_PER_WARP;
-			int max_cta = c.num_sms * (wide ? 2 : 6);
+			// one-warp CTAs of the long-task classes: as many per SM as their shared-memory slices allow (up to 8)
+			int wide_per_sm = (200 * 1024) / smem_per_warp; if (wide_per_sm < 1) wide_per_sm = 1; if (wide_per_sm > 8) wide_per_sm = 8;
+			int max_cta = c.num_sms * (wide ? wide_per_sm : 6);
 			int64_t want_cta = cdiv(cnt, wpc);
 			int n_cta = (int)(want_cta < max_cta ? want_cta : max_cta);
 			// bound total scratch to ~24 GB

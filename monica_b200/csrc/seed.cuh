@@ -301,7 +301,7 @@ static void run_seed(Arena &ar, cudaStream_t st, const DevIndex &ix, int mid_occ
 	k_sort_anchors<<<grid, SORT_TPB, 0, st>>>(o.a_unsorted, o.a, o.a_roff, n_reads, gkey, gidx, big_off, tie_list, ctr); ++*n_launch;
 	static bool se_attr = false;
 	if (!se_attr) { CK(cudaFuncSetAttribute(k_sort_emul, cudaFuncAttributeMaxDynamicSharedMemorySize, SE_SMEM_BYTES)); se_attr = true; }
-	const int se_grid = num_sms * 4;
+	const int se_grid = num_sms * 5;   // 43 KB of shared memory per one-warp CTA: five fit an SM
 	int *ws_pool = ar.get<int>((size_t)se_grid * 6 * SE_STACK);
 	k_sort_emul<<<se_grid, 32, SE_SMEM_BYTES, st>>>(o.a_unsorted, o.a, o.a_roff, tie_list, ctr, ctr + 1, ws_pool); ++*n_launch;
 }
