@@ -113,6 +113,30 @@ MB_D void mb_append_cigar(uint32_t *dst, int &n_dst, const uint32_t *src, int n_
 	for (; k < n_src; ++k) dst[n_dst++] = src[k];
 }
 
+// warp-cooperative mb_append_cigar: every lane runs the (uniform) bookkeeping, the copy is spread over the lanes.  The region
+// CIGAR is compacted in place at the first task's slot, so dst + n_dst never passes src: a chunk is read completely before
+// it is written.
+MB_D void mb_append_cigar_warp(uint32_t *dst, int &n_dst, const uint32_t *src, int n_src, int lane)
+{
+	if (n_src == 0) return;
+	int k = 0;
+	__syncwarp();
+	if (n_dst > 0 && (dst[n_dst - 1] & 0xf) == (src[0] & 0xf)) {
+		const uint32_t add = (src[0] >> 4) << 4;
+		__syncwarp();
+		if (lane == 0) dst[n_dst - 1] += add;
+		k = 1;
+	}
+	for (int b = k; b < n_src; b += 32) {
+		const int i = b + lane;
+		const uint32_t v = i < n_src ? src[i] : 0u;
+		__syncwarp();
+		if (i < n_src) dst[n_dst + (i - k)] = v;
+		__syncwarp();
+	}
+	n_dst += n_src - k;
+}
+
 MB_D void mb_fix_cigar(Reg *r, uint32_t *cigar, const QView &qv, const TView &tv, int *qshift, int *tshift)
 {
 	int32_t toff = 0, qoff = 0, to_shrink = 0;
@@ -387,7 +411,10 @@ __global__ void k_stitch(AlignCtx c, ReadArrays ra, const int2 *__restrict__ wor
                          DpTask *__restrict__ tasks, uint32_t *__restrict__ cigar_pool,
                          int2 *__restrict__ next_work, int32_t *__restrict__ n_next, int *__restrict__ err)
 {
-	int wi = blockIdx.x * blockDim.x + threadIdx.x;
+	// one WARP per region: every lane runs the same (uniform) control flow, lane 0 alone writes region state, and the CIGAR
+	// copies -- the bulk of the work -- are spread over the lanes
+	const int wi = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+	const int lane = threadIdx.x & 31;
 	if (wi >= n_work) return;
 	const int read = work[wi].x, slot = work[wi].y;
 	Reg *regs = ra.regs + ra.reg_off[read];
@@ -397,8 +424,10 @@ __global__ void k_stitch(AlignCtx c, ReadArrays ra, const int2 *__restrict__ wor
 	const mb_opt_t &opt = c.opt;
 	const int64_t roff = c.read_off[read];
 	const int qlen = (int)(c.read_off[read + 1] - roff);
-	r->aligned = 1;
-	if (r->cnt == 0) return;
+	const int r_cnt = r->cnt, r_as = r->as;
+	__syncwarp();
+	if (lane == 0) r->aligned = 1;
+	if (r_cnt == 0) return;
 	const int rev = r->rev, rid = r->rid;
 	const int k2 = c.ix.k >> 1;
 	DpTask *T = tasks + pl.task0;
@@ -408,7 +437,7 @@ __global__ void k_stitch(AlignCtx c, ReadArrays ra, const int2 *__restrict__ wor
 	int32_t dp_score = 0;
 	if (pl.has_left) {
 		const DpTask &t = T[ti++];
-		if (t.n_cigar > 0) { mb_append_cigar(cig, n_cig, cigar_pool + t.cigar_off, t.n_cigar); dp_score += t.max; }
+		if (t.n_cigar > 0) { mb_append_cigar_warp(cig, n_cig, cigar_pool + t.cigar_off, t.n_cigar, lane); dp_score += t.max; }
 		rs1 = rs - (t.reach_end ? t.mqe_t + 1 : t.max_t + 1);
 		qs1 = qs - (t.reach_end ? qs - pl.qs0 : t.max_q + 1);
 	} else rs1 = rs, qs1 = qs;
@@ -420,7 +449,7 @@ __global__ void k_stitch(AlignCtx c, ReadArrays ra, const int2 *__restrict__ wor
 		re1 = re, qe1 = qe;
 		if (i == pl.cnt1 - 1 || (ai.y & MB_SEED_LONG_JOIN) || (qe - qs >= opt.min_ksw_len && re - rs >= opt.min_ksw_len)) {
 			const DpTask &t = T[ti++];
-			if (t.n_cigar > 0) mb_append_cigar(cig, n_cig, cigar_pool + t.cigar_off, t.n_cigar);
+			if (t.n_cigar > 0) mb_append_cigar_warp(cig, n_cig, cigar_pool + t.cigar_off, t.n_cigar, lane);
 			if (t.zdropped) {
 				int j;
 				for (j = i - 1; j >= 0; --j)
@@ -430,9 +459,9 @@ __global__ void k_stitch(AlignCtx c, ReadArrays ra, const int2 *__restrict__ wor
 				dp_score += t.max;
 				re1 = rs + (t.max_t + 1);
 				qe1 = qs + (t.max_q + 1);
-				if (pl.cnt1 - (j + 1) >= opt.min_cnt) {
-					const int n_split = pl.as1 + j + 1 - r->as;
-					if (n_split > 0 && n_split < r->cnt) {
+				if (lane == 0 && pl.cnt1 - (j + 1) >= opt.min_cnt) {
+					const int n_split = pl.as1 + j + 1 - r_as;
+					if (n_split > 0 && n_split < r_cnt) {
 						const int ns = atomicAdd(&ra.n_regs[read], 1);
 						if (ns >= (int)(ra.reg_off[read + 1] - ra.reg_off[read])) { *err = 2; atomicSub(&ra.n_regs[read], 1); }
 						else {
@@ -452,15 +481,18 @@ __global__ void k_stitch(AlignCtx c, ReadArrays ra, const int2 *__restrict__ wor
 	}
 	if (!dropped && pl.has_right) {
 		const DpTask &t = T[pl.n_tasks - 1];
-		if (t.n_cigar > 0) { mb_append_cigar(cig, n_cig, cigar_pool + t.cigar_off, t.n_cigar); dp_score += t.max; }
+		if (t.n_cigar > 0) { mb_append_cigar_warp(cig, n_cig, cigar_pool + t.cigar_off, t.n_cigar, lane); dp_score += t.max; }
 		re1 = re + (t.reach_end ? t.mqe_t + 1 : t.max_t + 1);
 		qe1 = qe + (t.reach_end ? pl.qe0 - qe : t.max_q + 1);
 	}
-	r->rs = rs1, r->re = re1;
-	if (rev) r->qs = qlen - qe1, r->qe = qlen - qs1;
-	else r->qs = qs1, r->qe = qe1;
-	if (n_cig > 0) {
-		r->has_p = 1, r->n_cigar = n_cig, r->cigar_off = T[0].cigar_off, r->dp_score = dp_score; // mm_update_extra: k_update_extra
+	__syncwarp();
+	if (lane == 0) {
+		r->rs = rs1, r->re = re1;
+		if (rev) r->qs = qlen - qe1, r->qe = qlen - qs1;
+		else r->qs = qs1, r->qe = qe1;
+		if (n_cig > 0) {
+			r->has_p = 1, r->n_cigar = n_cig, r->cigar_off = T[0].cigar_off, r->dp_score = dp_score; // mm_update_extra: k_update_extra
+		}
 	}
 }
 

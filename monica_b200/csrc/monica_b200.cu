@@ -1001,7 +1001,7 @@ static void map_device_part(mb_index *ix, const mb_opt_t &opt_in, DevPart &part)
 		}
 		S.n_dp_tasks += n_tasks;
 		CK(cudaMemsetAsync(n_work + 1, 0, sizeof(int32_t), st));
-		k_stitch<<<wb, 128, 0, st>>>(ac, ra, work, h_n_work, plans, tasks, cigar_pool, work2, n_work + 1, d_err); ++nl;
+		k_stitch<<<(unsigned)cdiv((int64_t)h_n_work * 32, 128), 128, 0, st>>>(ac, ra, work, h_n_work, plans, tasks, cigar_pool, work2, n_work + 1, d_err); ++nl;
 		phase("stitch");
 		k_update_extra<<<(unsigned)cdiv((int64_t)h_n_work * 32, 128), 128, 0, st>>>(ac, ra, work, h_n_work, plans, tasks, cigar_pool); ++nl;
 		phase("update_extra");
