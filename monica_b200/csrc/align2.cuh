@@ -505,17 +505,19 @@ struct ReadScratch {
 	Reg *regs_tmp;     // same offsets as regs
 };
 
-// G1a: chain backtrack; writes n_u per read
-__global__ void k_chain_bt(ReadArrays ra, ReadScratch rs, int n_reads, int min_cnt, int min_sc, int32_t *__restrict__ n_u, int *__restrict__ err)
+// G1a: chain backtrack, one warp per read; writes n_u per read
+__global__ void __launch_bounds__(128)
+k_chain_bt(ReadArrays ra, ReadScratch rs, int n_reads, int min_cnt, int min_sc, int32_t *__restrict__ n_u, int *__restrict__ err)
 {
-	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	const int r = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+	const int lane = threadIdx.x & 31;
 	if (r >= n_reads) return;
 	const int64_t base = ra.a_roff[r];
 	const int n = (int)(ra.a_roff[r + 1] - base);
 	int e = 0;
-	n_u[r] = mb_chain_backtrack(n, ra.a + base, rs.f + base, rs.p + base, rs.v + base, rs.t + base, rs.b + base, rs.u + base,
-	                            rs.scr + 3 * base + 3 * r, min_cnt, min_sc, &e);
-	if (e) *err = 1;
+	const int k = mb_chain_backtrack_warp(n, ra.a + base, rs.f + base, rs.p + base, rs.v + base, rs.t + base, rs.b + base, rs.u + base,
+	                                      rs.scr + 3 * base + 3 * r, min_cnt, min_sc, &e, lane);
+	if (lane == 0) { n_u[r] = k; if (e) *err = 1; }
 }
 
 __global__ void k_reg_cap(const int32_t *__restrict__ n_u, const int64_t *__restrict__ a_roff, int n_reads, int32_t *__restrict__ cap)

@@ -202,3 +202,98 @@ MB_HD int mb_chain_backtrack(int n, mb128 *a, const int32_t *f, const int32_t *p
 	for (i = 0; i < n_u; ++i) u[i] = u2[i];
 	return n_u;
 }
+
+// Warp-cooperative form of mb_chain_backtrack: the array sweeps (marking, chain-end collection, anchor copies) are spread over
+// the lanes, the two inherently sequential parts (greedy backtrack over the score-sorted chain ends, the small sorts) run on
+// lane 0.  One warp per read also keeps a long read from stalling 31 neighbours in lock-step.  Same outputs as the scalar
+// routine: the chain ends are collected in arbitrary order, but their keys are distinct, so the sort that follows is unique.
+MB_D int mb_chain_backtrack_warp(int n, mb128 *a, const int32_t *f, const int32_t *p, int32_t *v, int32_t *t, mb128 *b, uint64_t *u, uint64_t *scr,
+                                 int min_cnt, int min_sc, int *err, int lane)
+{
+	const unsigned FULL = 0xffffffffu;
+	if (n == 0) return 0;
+	for (int i = lane; i < n; i += 32) t[i] = 0;
+	__syncwarp();
+	for (int i = lane; i < n; i += 32) if (p[i] >= 0) t[p[i]] = 1;
+	__syncwarp();
+	int n_u = 0;
+	for (int i0 = 0; i0 < n; i0 += 32) {
+		const int i = i0 + lane;
+		uint64_t key = 0; bool have = false;
+		if (i < n && t[i] == 0 && v[i] >= min_sc) {
+			int j = i;
+			while (j >= 0 && f[j] < v[j]) j = p[j];
+			if (j < 0) j = i;
+			key = (uint64_t)(uint32_t)f[j] << 32 | (uint32_t)j; have = true;
+		}
+		const unsigned m = __ballot_sync(FULL, have);
+		if (have) u[n_u + __popc(m & ((1u << lane) - 1))] = key;
+		n_u += __popc(m);
+	}
+	__syncwarp();
+	if (n_u == 0) return 0;
+	if (lane == 0) {
+		mb_sort_exact(u, n_u, KeyU64(), err);
+		for (int i = 0; i < n_u >> 1; ++i) { uint64_t tt = u[i]; u[i] = u[n_u - i - 1], u[n_u - i - 1] = tt; }
+	}
+	for (int i = lane; i < n; i += 32) t[i] = 0;
+	__syncwarp();
+	int k_chains = 0;
+	if (lane == 0) {
+		int n_v = 0, k = 0;
+		for (int i = 0; i < n_u; ++i) {
+			const int n_v0 = n_v, k0 = k;
+			int j = (int32_t)u[i];
+			do {
+				v[n_v++] = j;
+				t[j] = 1;
+				j = p[j];
+			} while (j >= 0 && t[j] == 0);
+			if (j < 0) {
+				if (n_v - n_v0 >= min_cnt) u[k++] = u[i] >> 32 << 32 | (uint32_t)(n_v - n_v0);
+			} else if ((int32_t)(u[i] >> 32) - f[j] >= min_sc) {
+				if (n_v - n_v0 >= min_cnt) u[k++] = (uint64_t)((u[i] >> 32) - (uint64_t)(int64_t)f[j]) << 32 | (uint32_t)(n_v - n_v0);
+			}
+			if (k0 == k) n_v = n_v0;
+		}
+		k_chains = k;
+	}
+	k_chains = __shfl_sync(FULL, k_chains, 0);
+	n_u = k_chains;
+	__syncwarp();
+	// b = anchors chain by chain (each chain reversed into ascending order)
+	{
+		int k = 0;
+		for (int i = 0; i < n_u; ++i) {
+			const int ni = (int32_t)u[i];
+			for (int j = lane; j < ni; j += 32) b[k + j] = a[v[k + (ni - j - 1)]];
+			k += ni;
+		}
+	}
+	__syncwarp();
+	mb128 *w = (mb128*)scr;
+	uint64_t *u2 = scr + 2 * (size_t)n_u;
+	if (lane == 0) {
+		int k = 0;
+		for (int i = 0; i < n_u; ++i) {
+			w[i].x = b[k].x, w[i].y = (uint64_t)k << 32 | (uint32_t)i;
+			k += (int32_t)u[i];
+		}
+		mb_sort_exact(w, n_u, KeyX(), err);
+		for (int i = 0; i < n_u; ++i) u2[i] = u[(int32_t)w[i].y];
+	}
+	__syncwarp();
+	{
+		int k = 0;
+		for (int i = 0; i < n_u; ++i) {
+			const int nn = (int32_t)u2[i];
+			const mb128 *src = b + (w[i].y >> 32);
+			for (int j = lane; j < nn; j += 32) a[k + j] = src[j];
+			k += nn;
+		}
+	}
+	__syncwarp();
+	for (int i = lane; i < n_u; i += 32) u[i] = u2[i];
+	__syncwarp();
+	return n_u;
+}

@@ -927,7 +927,7 @@ static void map_device_part(mb_index *ix, const mb_opt_t &opt_in, DevPart &part)
 	int64_t *reg_off = ar.get<int64_t>(n_reads + 1);
 	ra.reg_off = reg_off;
 	const unsigned rb = (unsigned)cdiv(n_reads, 128);
-	k_chain_bt<<<rb, 128, 0, st>>>(ra, rs, n_reads, opt.min_cnt, opt.min_chain_score, n_u, d_err); ++nl;
+	k_chain_bt<<<(unsigned)cdiv((int64_t)n_reads * 32, 128), 128, 0, st>>>(ra, rs, n_reads, opt.min_cnt, opt.min_chain_score, n_u, d_err); ++nl;
 	k_reg_cap<<<rb, 128, 0, st>>>(n_u, sd.a_roff, n_reads, cap); ++nl;
 	exclusive_scan<int32_t>(ar, st, cap, reg_off, n_reads, &nl);
 	const int64_t reg_total = d2h_scalar(reg_off + n_reads, st);
@@ -1454,7 +1454,7 @@ extern "C" int mb_chain(int device, const mb_opt_t *opt, const uint64_t *anchors
 		ReadArrays ra; memset(&ra, 0, sizeof(ra));
 		ra.a = d_a; ra.a_roff = d_roff;
 		int32_t *n_u = ar.get<int32_t>(n_reads + 1);
-		if (n_reads) k_chain_bt<<<(unsigned)cdiv(n_reads, 128), 128, 0, st>>>(ra, rs, n_reads, opt->min_cnt, opt->min_chain_score, n_u, d_err);
+		if (n_reads) k_chain_bt<<<(unsigned)cdiv((int64_t)n_reads * 32, 128), 128, 0, st>>>(ra, rs, n_reads, opt->min_cnt, opt->min_chain_score, n_u, d_err);
 		std::vector<int32_t> h_nu(n_reads);
 		std::vector<mb128> h_a(n_a); std::vector<uint64_t> h_u(n_a);
 		if (n_reads) CK(cudaMemcpyAsync(h_nu.data(), n_u, n_reads * 4, cudaMemcpyDeviceToHost, st));
