@@ -128,6 +128,12 @@ int  mb_count_last(mb_index_t *idx, int32_t mapq_min, int mode, int64_t *counts,
 /* device pointer to the int64[n_seq] count vector of the LAST mb_count on this thread (for the NCCL allreduce) */
 void *mb_count_device_ptr(mb_index_t *idx);
 int  mb_count_fetch(mb_index_t *idx, int64_t *counts);
+/* normalizer(alignment, genomes_length)  monica/genomes/aligner.py:305-319, on the device-resident count vector of the LAST
+ * mb_count on this thread (after the multi-GPU all-reduce, if any).  group[n_seq] maps each contig to its genome (accession)
+ * or -1, group_len[n_groups] = genome lengths, order[n_order] = the groups in the order the reference's nested dict visits
+ * them (float addition order of the sample total).  bpm[n_groups] = (count/len) / sum(count/len). */
+int  mb_normalize_last(mb_index_t *idx, const int32_t *group, int32_t n_groups, const double *group_len,
+                       const int32_t *order, int32_t n_order, double *bpm);
 
 /* ---- FASTQ ingest and routed writers (host side, no device needed) ----
  * mb_fastq_load      for seq_record in SeqIO.parse(sample, 'fastq')            monica/genomes/aligner.py:191,212
@@ -142,6 +148,14 @@ int  mb_fastq_ids_unique(const mb_fastq_t *fq);
 int  mb_fastq_route(const mb_fastq_t *fq, const int8_t *dest, const char *const *new_id, const uint8_t *focus,
                     const char *mapped_path, const char *unmapped_path, const char *ambiguous_path, const char *focus_path);
 void mb_fastq_free(mb_fastq_t *fq);
+
+/* ---- database builder (host side, no device needed) ----
+ * mb_db_build        builder(genomes_chunk, databases_path, database_name, database_number)  monica/genomes/database.py:52-67
+ * Writes one database<N>.fna.gz: every FASTA record of genome i re-headed new_headers[i] ("<tax_unit>:<accession>") the way
+ * the reference's SeqIO.parse -> SeqIO.write round trip does (title "<new id> <old title>", 60-column lines);
+ * genome_len[i] = bases of genome i (current_genomes_length.pkl). */
+int  mb_db_build(const char *out_path, int32_t n_genomes, const char *const *genome_paths, const char *const *new_headers,
+                 int64_t *genome_len);
 
 /* ---- per-stage entry points (parity tests) ---- */
 /* minimizers of each read: out_xy[2*cap], out_off[n_reads+1]; y carries the read index in its high 32 bits */

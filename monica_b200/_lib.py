@@ -65,9 +65,10 @@ SYMBOLS = [
     "mb_index_seq_name", "mb_index_seq_len", "mb_index_mid_occ", "mb_index_kw", "mb_index_n_minimizers", "mb_index_hbm_bytes",
     "mb_map_batch", "mb_map_batch_ex", "mb_reads_upload", "mb_reads_free", "mb_map_resident",
     "mb_hits_n", "mb_hits_field", "mb_hits_cigar_off", "mb_hits_cigar_pool", "mb_hits_rep_len", "mb_hits_free",
-    "mb_count", "mb_count_last", "mb_count_device_ptr", "mb_count_fetch",
+    "mb_count", "mb_count_last", "mb_count_device_ptr", "mb_count_fetch", "mb_normalize_last",
     "mb_sketch", "mb_seed", "mb_chain", "mb_dp_batch", "mb_int_peak", "mb_stream",
     "mb_fastq_load", "mb_fastq_n", "mb_fastq_seqs", "mb_fastq_header", "mb_fastq_ids_unique", "mb_fastq_route", "mb_fastq_free",
+    "mb_db_build",
 ]
 
 _lib = None
@@ -140,6 +141,8 @@ def lib():
     L.mb_fastq_free.argtypes = [vp]
     L.mb_fastq_free.restype = None
     L.mb_count_fetch.argtypes = [vp, vp]
+    L.mb_normalize_last.argtypes = [vp, vp, i32, vp, vp, i32, vp]
+    L.mb_db_build.argtypes = [C.c_char_p, i32, vp, vp, vp]
     L.mb_sketch.argtypes = [C.c_int, vp, vp, i32, C.c_int, C.c_int, vp, i64, vp]
     L.mb_seed.argtypes = [vp, C.POINTER(Opt), vp, vp, i32, vp, i64, vp, vp]
     L.mb_chain.argtypes = [C.c_int, C.POINTER(Opt), vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]

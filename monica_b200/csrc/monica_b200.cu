@@ -1381,6 +1381,65 @@ extern "C" int mb_count_fetch(mb_index_t *ix, int64_t *counts)
 	API_END
 }
 
+// ---- normaliser on the device-resident count vector: monica/genomes/aligner.py:305-319 ----
+// counts are per contig; contigs of one genome share a group (accession).  BPB = group count / genome length, sample total =
+// sum of BPB in the caller's order (the reference adds floats in dict order, so the order is part of the result), BPM =
+// BPB / total.
+__global__ void k_norm_group(const unsigned long long *__restrict__ counts, const int32_t *__restrict__ group, int n_seq, unsigned long long *__restrict__ gsum)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n_seq && group[i] >= 0 && counts[i]) atomicAdd(&gsum[group[i]], counts[i]);
+}
+__global__ void k_norm_bpb(const unsigned long long *__restrict__ gsum, const double *__restrict__ glen, int n_groups, double *__restrict__ bpb)
+{
+	const int g = blockIdx.x * blockDim.x + threadIdx.x;
+	if (g < n_groups) bpb[g] = __ddiv_rn((double)(long long)gsum[g], glen[g]);
+}
+__global__ void k_norm_total(const double *__restrict__ bpb, const int32_t *__restrict__ order, int n_order, double *__restrict__ total)
+{
+	if (blockIdx.x || threadIdx.x) return;
+	double t = 0.0;
+	for (int i = 0; i < n_order; ++i) t = __dadd_rn(t, bpb[order[i]]); // sequential on purpose: float addition order is the reference's
+	*total = t;
+}
+__global__ void k_norm_bpm(double *__restrict__ bpb, const double *__restrict__ total, int n_groups)
+{
+	const int g = blockIdx.x * blockDim.x + threadIdx.x;
+	if (g < n_groups) bpb[g] = __ddiv_rn(bpb[g], *total);
+}
+
+extern "C" int mb_normalize_last(mb_index_t *ix, const int32_t *group, int32_t n_groups, const double *group_len,
+                                 const int32_t *order, int32_t n_order, double *bpm)
+{
+	API_BEGIN
+	if (!ix || !group || n_groups <= 0 || !group_len || (n_order && !order) || n_order < 0 || !bpm) throw mb_error(MB_ERR_ARG, "bad arguments");
+	ThreadCtx &c = get_ctx(ix->device);
+	if (!c.d_counts) throw mb_error(MB_ERR_ARG, "no count vector on this thread");
+	const int n_seq = (int)ix->names.size();
+	for (int i = 0; i < n_seq; ++i) if (group[i] >= n_groups) throw mb_error(MB_ERR_ARG, "group id out of range");
+	for (int i = 0; i < n_order; ++i) if (order[i] < 0 || order[i] >= n_groups) throw mb_error(MB_ERR_ARG, "order entry out of range");
+	cudaStream_t st = c.st;
+	int32_t *d_group = nullptr, *d_order = nullptr; double *d_len = nullptr, *d_bpb = nullptr; unsigned long long *d_gsum = nullptr;
+	CK(cudaMallocAsync(&d_group, (size_t)n_seq * 4, st));
+	CK(cudaMallocAsync(&d_order, (size_t)(n_order + 1) * 4, st));
+	CK(cudaMallocAsync(&d_len, (size_t)n_groups * 8, st));
+	CK(cudaMallocAsync(&d_bpb, (size_t)(n_groups + 1) * 8, st));
+	CK(cudaMallocAsync(&d_gsum, (size_t)n_groups * 8, st));
+	CK(cudaMemcpyAsync(d_group, group, (size_t)n_seq * 4, cudaMemcpyHostToDevice, st));
+	if (n_order) CK(cudaMemcpyAsync(d_order, order, (size_t)n_order * 4, cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(d_len, group_len, (size_t)n_groups * 8, cudaMemcpyHostToDevice, st));
+	CK(cudaMemsetAsync(d_gsum, 0, (size_t)n_groups * 8, st));
+	k_norm_group<<<(unsigned)cdiv(n_seq, 256), 256, 0, st>>>(c.d_counts, d_group, n_seq, d_gsum);
+	k_norm_bpb<<<(unsigned)cdiv(n_groups, 256), 256, 0, st>>>(d_gsum, d_len, n_groups, d_bpb);
+	k_norm_total<<<1, 32, 0, st>>>(d_bpb, d_order, n_order, d_bpb + n_groups);
+	k_norm_bpm<<<(unsigned)cdiv(n_groups, 256), 256, 0, st>>>(d_bpb, d_bpb + n_groups, n_groups);
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(bpm, d_bpb, (size_t)n_groups * 8, cudaMemcpyDeviceToHost, st));
+	cudaFreeAsync(d_group, st); cudaFreeAsync(d_order, st); cudaFreeAsync(d_len, st); cudaFreeAsync(d_bpb, st); cudaFreeAsync(d_gsum, st);
+	CK(cudaStreamSynchronize(st));
+	API_END
+}
+
 // ---------------------------------------------------------------------------------------------
 // per-stage entry points (parity tests)
 // ---------------------------------------------------------------------------------------------
@@ -1705,3 +1764,68 @@ extern "C" int mb_fastq_route(const mb_fastq_t *fq, const int8_t *dest, const ch
 }
 
 extern "C" void mb_fastq_free(mb_fastq_t *fq) { delete fq; }
+
+// ---- database builder: monica/genomes/database.py:52-67 builder() ----
+// One database<N>.fna.gz = the genomes of a chunk, every record re-headed "<tax_unit>:<accession>" (what the aligner later
+// splits on ':', aligner.py:234).  The reference re-serialises each record through Biopython: title = "<new id> <old title>"
+// (the old title's first word differs from the new id; a record whose old title already starts with the new id keeps its
+// title), sequence re-wrapped at 60 columns with blanks removed.  Decompressed output is byte-identical to that writer;
+// genome_len[i] = bases of genome i (the value the reference stores in current_genomes_length.pkl).
+extern "C" int mb_db_build(const char *out_path, int32_t n_genomes, const char *const *genome_paths, const char *const *new_headers,
+                           int64_t *genome_len)
+{
+	API_BEGIN
+	if (!out_path || n_genomes < 0 || (n_genomes && (!genome_paths || !new_headers))) throw mb_error(MB_ERR_ARG, "bad arguments");
+	gzFile out = gzopen(out_path, "wb9");
+	if (!out) throw mb_error(MB_ERR_IO, std::string("cannot write ") + out_path);
+	gzbuffer(out, 1 << 20);
+	std::string rec, title, seq, line;
+	std::vector<char> buf(1 << 20);
+	bool ok = true;
+	auto put = [&](const std::string &v) { if (!v.empty() && gzwrite(out, v.data(), (unsigned)v.size()) != (int)v.size()) ok = false; };
+	for (int32_t g = 0; g < n_genomes && ok; ++g) {
+		gzFile in = gzopen(genome_paths[g], "rb");
+		if (!in) { gzclose(out); throw mb_error(MB_ERR_IO, std::string("cannot open ") + genome_paths[g]); }
+		gzbuffer(in, 1 << 20);
+		const std::string id = new_headers[g];
+		int64_t glen = 0;
+		bool have = false;
+		auto flush_record = [&]() {
+			if (!have) return;
+			// Biopython: description (= old title) kept; "id description" unless the description's first word is the id
+			size_t b0 = title.find_first_not_of(" \t\v\f\r"), e0 = b0 == std::string::npos ? b0 : title.find_first_of(" \t\v\f\r", b0);
+			const std::string first = b0 == std::string::npos ? std::string() : title.substr(b0, e0 == std::string::npos ? std::string::npos : e0 - b0);
+			rec.clear(); rec.push_back('>');
+			if (title.empty()) rec += id; else if (first == id) rec += title; else { rec += id; rec.push_back(' '); rec += title; }
+			rec.push_back('\n');
+			for (size_t i = 0; i < seq.size(); i += 60) { rec.append(seq, i, 60); rec.push_back('\n'); }
+			put(rec);
+			glen += (int64_t)seq.size();
+			have = false;
+		};
+		auto take_line = [&](std::string &l) {
+			if (!l.empty() && l[0] == '>') {
+				flush_record();
+				size_t e = l.find_last_not_of(" \t\v\f\r\n");
+				title = e == std::string::npos || e == 0 ? std::string() : l.substr(1, e);
+				seq.clear(); have = true;
+			} else if (have) {
+				const size_t e = l.find_last_not_of(" \t\v\f\r\n"); // line.rstrip(), then blanks and CRs dropped
+				for (size_t i = 0; e != std::string::npos && i <= e; ++i) if (l[i] != ' ' && l[i] != '\r') seq.push_back(l[i]);
+			}
+		};
+		int n; line.clear();
+		while ((n = gzread(in, buf.data(), (unsigned)buf.size())) > 0) {
+			for (int i = 0; i < n; ++i) {
+				if (buf[i] == '\n') { take_line(line); line.clear(); } else line.push_back(buf[i]);
+			}
+		}
+		const bool read_ok = n == 0;
+		take_line(line); flush_record();
+		gzclose(in);
+		if (!read_ok) { gzclose(out); throw mb_error(MB_ERR_IO, std::string("read failed: ") + genome_paths[g]); }
+		if (genome_len) genome_len[g] = glen;
+	}
+	if (gzclose(out) != Z_OK || !ok) throw mb_error(MB_ERR_IO, std::string("write failed: ") + out_path);
+	API_END
+}

@@ -206,6 +206,35 @@ class Aligner:
                              ncls.ctypes.data_as(C.c_void_p), rcls.ctypes.data_as(C.c_void_p), rbest.ctypes.data_as(C.c_void_p)))
         return counts, ncls, rcls[:hits.n_reads], rbest[:hits.n_reads]
 
+    def normalize_last(self, sample_alignment, genomes_length):
+        """normalizer() (aligner.py:305-319) for one sample, computed on the device from the count vector of this thread's
+        last count() (in a multi-GPU run: after the all-reduce).  `sample_alignment` = {tax_unit: Counter({accession: n})}
+        supplies the keys and -- because the reference adds the BPB floats in dict order -- the summation order; the values
+        come from the device.  Returns {tax_unit: Counter({accession: BPM})}, bit-identical to the reference's floats."""
+        from collections import Counter
+        gid = {}
+        group = np.full(max(1, self.n_seq), -1, dtype=np.int32)
+        for i, name in enumerate(self.seq_names):
+            parts = name.split(':')
+            if len(parts) >= 2:
+                group[i] = gid.setdefault((parts[0], parts[1]), len(gid))
+        order, glen = [], np.ones(max(1, len(gid)), dtype=np.float64)
+        for tax_unit, counter in sample_alignment.items():
+            for accession in counter:
+                g = gid[(tax_unit, accession)]
+                glen[g] = float(genomes_length[accession])
+                order.append(g)
+        order_a = np.asarray(order if order else [0], dtype=np.int32)
+        bpm = np.zeros(max(1, len(gid)), dtype=np.float64)
+        check(lib().mb_normalize_last(self._idx, group.ctypes.data_as(C.c_void_p), max(1, len(gid)), glen.ctypes.data_as(C.c_void_p),
+                                      order_a.ctypes.data_as(C.c_void_p), len(order), bpm.ctypes.data_as(C.c_void_p)))
+        out = {}
+        for tax_unit, counter in sample_alignment.items():
+            out[tax_unit] = Counter()
+            for accession in counter:
+                out[tax_unit][accession] = float(bpm[gid[(tax_unit, accession)]])
+        return out
+
 
 def fastx_read(fn, read_comment=False):
     """mappy.fastx_read: yields (name, seq, qual[, comment])."""

@@ -80,6 +80,55 @@ class OracleAligner:
             yield a
 
 
+class FastaRecord:
+    """What Bio.SeqIO.parse(handle, 'fasta') yields, reduced to what database.py:60-64 touches."""
+    def __init__(self, title, seq):
+        self.id = self.name = title.split(None, 1)[0] if title.split(None, 1) else ""
+        self.description = title
+        self.seq = seq
+
+    def __len__(self):
+        return len(self.seq)
+
+
+def bio_fasta_parse(handle):
+    """Restatement of Bio.SeqIO.FastaIO.SimpleFastaParser (lines before the first '>' skipped; title = line[1:].rstrip();
+    sequence lines rstrip()ped, joined, blanks and CRs removed)."""
+    title, lines = None, []
+    for line in handle:
+        if line[:1] == ">":
+            if title is not None:
+                yield FastaRecord(title, "".join(lines).replace(" ", "").replace("\r", ""))
+            title, lines = line[1:].rstrip(), []
+        elif title is not None:
+            lines.append(line.rstrip())
+    if title is not None:
+        yield FastaRecord(title, "".join(lines).replace(" ", "").replace("\r", ""))
+
+
+def bio_fasta_write(rec, handle):
+    """Restatement of Bio.SeqIO.FastaIO.as_fasta: title rule + 60-column lines."""
+    ident, desc = rec.id.replace("\n", " ").replace("\r", " "), rec.description.replace("\n", " ").replace("\r", " ")
+    if desc and desc.split(None, 1)[0] == ident:
+        title = desc
+    elif desc:
+        title = f"{ident} {desc}"
+    else:
+        title = ident
+    handle.write(f">{title}\n")
+    for i in range(0, len(rec.seq), 60):
+        handle.write(rec.seq[i:i + 60] + "\n")
+    return 1
+
+
+def _seqio_parse(handle, fmt="fastq"):
+    return bio_fasta_parse(handle) if fmt == "fasta" and not isinstance(handle, (str, bytes, os.PathLike)) else fastx.parse(handle, fmt)
+
+
+def _seqio_write(records, handle, fmt="fastq"):
+    return bio_fasta_write(records, handle) if fmt == "fasta" else fastx.write(records, handle, fmt)
+
+
 def install_reference_imports(home: str):
     """Make `import monica.genomes.aligner` from /root/reference work: fake mappy + Bio.SeqIO, and ~/.monica/.root."""
     os.makedirs(os.path.join(home, ".monica"), exist_ok=True)
@@ -92,8 +141,8 @@ def install_reference_imports(home: str):
     sys.modules["mappy"] = m
     bio = types.ModuleType("Bio")
     seqio = types.ModuleType("Bio.SeqIO")
-    seqio.parse = fastx.parse
-    seqio.write = fastx.write
+    seqio.parse = _seqio_parse
+    seqio.write = _seqio_write
     bio.SeqIO = seqio
     sys.modules["Bio"] = bio
     sys.modules["Bio.SeqIO"] = seqio

@@ -350,6 +350,66 @@ def test_count_modes_equal_python_best_hit(case):
         assert ncls.tolist() == [cls.count(1), cls.count(0), cls.count(2)]
 
 
+def test_device_normalizer_equals_python_normalizer(case):
+    """BPB/BPM from the device-resident count vector == normalizer() (aligner.py:305-319), float for float."""
+    import copy
+    from collections import Counter
+    from monica_b200 import aligner as mine
+    al, oidx, reads, traces = case
+    hits = al.map_batch(reads)
+    names = al.seq_names
+    rng = np.random.default_rng(3)
+    for mode in ("basic", "query_length", "matching"):
+        counts, ncls, rcls, rbest = al.count(hits, 60, mode)
+        # the alignment dict in the order aligner() would have filled it: first mapped read of each target
+        sample = {}
+        for i in range(len(reads)):
+            if rcls[i] != 1:
+                continue
+            tax_unit, accession = names[hits.rid[int(rbest[i])]].split(':')[0:2]
+            sample.setdefault(tax_unit, Counter())
+            sample[tax_unit].setdefault(accession, 0)
+        for nm, c in zip(names, counts):
+            tax_unit, accession = nm.split(':')[0:2]
+            if c:
+                sample[tax_unit][accession] += int(c)
+        assert sample and all(v > 0 for c in sample.values() for v in c.values())
+        glen = {acc: int(rng.integers(1000, 7_000_000)) for c in sample.values() for acc in c}
+        want = mine.normalizer({"s": copy.deepcopy(sample)}, genomes_length=glen)["s"]
+        got = al.normalize_last(sample, glen)
+        assert {k: dict(v) for k, v in got.items()} == {k: dict(v) for k, v in want.items()}, mode
+        assert list(got) == list(want)
+
+
+def test_database_builder_output_indexes_and_maps(tmp_path):
+    """a database written by mb_db_build (multi-contig genomes re-headed tax_unit:accession) goes through
+    indexer-style index build and maps reads to the renamed contigs."""
+    import gzip
+    from monica_b200 import database, synth
+    from monica_b200.mappy_shim import Aligner
+    rng = np.random.default_rng(11)
+    genomes = []
+    seqs = {}
+    for g in range(3):
+        path = tmp_path / f"GCF_{g}.fna.gz"
+        contigs = [synth.random_genome(rng, 30_000), synth.random_genome(rng, 20_000)]
+        with gzip.open(path, "wt") as fh:
+            for ci, c in enumerate(contigs):
+                fh.write(f">NZ_{g}{ci}.1 organism {g} contig {ci}\n")
+                text = c.tobytes().decode()
+                for i in range(0, len(text), 80):
+                    fh.write(text[i:i + 80] + "\n")
+        genomes.append((str(path), (f"Species_{g}", f"GCF_{g}.1")))
+        seqs[g] = contigs
+    lengths = database.builder(genomes, str(tmp_path), database.DATABASE_NAME, 1)
+    assert lengths == {f"GCF_{g}.1": 50_000 for g in range(3)}
+    al = Aligner(fn_idx_in=str(tmp_path / "database1.fna.gz"), preset="map-ont", best_n=15)
+    assert al and al.seq_names == [f"Species_{g}:GCF_{g}.1" for g in range(3) for _ in range(2)]
+    read = seqs[1][1][2_000:9_000].tobytes().decode()
+    hit = [h for h in al.map(read) if h.is_primary][0]
+    assert hit.ctg == "Species_1:GCF_1.1" and hit.mapq == 60 and hit.r_st == 2_000 and hit.r_en == 9_000
+
+
 def test_index_save_load_roundtrip(case, tmp_path):
     from monica_b200.mappy_shim import Aligner
     from monica_b200 import synth
