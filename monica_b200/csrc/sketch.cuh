@@ -12,8 +12,13 @@
 // or w+k > 48, the thread replays the read from its first base instead.  Emission is two-pass
 // (count -> exclusive scan -> write) so minimizers land in read-major, position order.
 //
-// Memory: a CTA stages its 128 chunks (+64 warm-up bytes) into shared memory with coalesced 16-byte
+// Memory: a CTA stages its 128 chunks (+64 warm-up bytes each) into shared memory with coalesced 16-byte
 // loads; chunk rows are padded by one word so the per-thread strided reads are bank-conflict free.
+//
+// Two kernels share the work (odd k <= 15, the map-ont case): chunks that lie in the interior of a read, with no ambiguous
+// base nearby, go through k_sketch_par -- one warp per chunk, every position in parallel (see there); the chunks at read
+// starts / ends, around N runs and at the edge of a copy piece go through the automaton, one thread per chunk, over a
+// compacted list.  Other (w,k) use the automaton for everything.
 #pragma once
 #include "common.cuh"
 
@@ -21,7 +26,9 @@
 #define SK_TPB   128
 #define SK_WARM  64
 #define SK_SPAN  (SK_CHUNK * SK_TPB)
-#define SK_SMEM_BYTES ((SK_SPAN + SK_WARM) + 4 * ((SK_SPAN + SK_WARM) / 256 + 2))
+#define SK_LOOK  16
+#define SK_ROW   (SK_WARM + SK_CHUNK + SK_LOOK + 4)   // shared-memory row of one chunk: warm-up + chunk + look-ahead, padded by one word (odd word stride)
+#define SK_SMEM_BYTES (SK_TPB * SK_ROW)
 
 MB_HD uint64_t mb_hash64(uint64_t key, uint64_t mask)
 {
@@ -136,6 +143,12 @@ struct EmitStage {
 	mb128 *row; int n; int base; uint64_t rid_hi;
 	MB_D void operator()(uint64_t x, uint32_t y) { const int k = base + n; if (k < SK_STAGE_CAP) { row[k].x = x; row[k].y = rid_hi | y; } ++n; }
 };
+// passes on the minimizers whose position in the read lies in [lo, hi)
+template <typename E>
+struct EmitFilter {
+	E &e; uint32_t lo, hi;
+	MB_D void operator()(uint64_t x, uint32_t y) { const uint32_t i = y >> 1; if (i >= lo && i < hi) e(x, y); }
+};
 struct EmitWrite {
 	mb128 *out; int64_t pos; uint64_t rid_hi;
 	MB_D void operator()(uint64_t x, uint32_t y) { out[pos].x = x; out[pos].y = rid_hi | y; ++pos; }
@@ -156,16 +169,31 @@ template <int W, bool WRITE>
 __global__ void __launch_bounds__(SK_TPB)
 k_sketch(const uint8_t *__restrict__ codes, const int64_t *__restrict__ off, int n_reads, int64_t total,
          int w, int k, int32_t *__restrict__ chunk_cnt, int32_t *__restrict__ read_cnt,
-         const int64_t *__restrict__ chunk_off, mb128 *__restrict__ out, mb128 *__restrict__ stage, int *__restrict__ overflow, int64_t cta0)
+         const int64_t *__restrict__ chunk_off, mb128 *__restrict__ out, mb128 *__restrict__ stage, int *__restrict__ overflow, int64_t cta0,
+         const int32_t *__restrict__ list, const int32_t *__restrict__ n_list)
 {
 	extern __shared__ __align__(16) uint8_t sm[];
-	const int64_t cta_base = ((int64_t)blockIdx.x + cta0) * SK_SPAN;
-	const int64_t win_lo = cta_base - SK_WARM; // logical smem index 0 <-> global win_lo (may be negative)
-	// ---- stage [win_lo, cta_base + SK_SPAN) with coalesced 16-byte loads; row padding of one word per 256 bytes ----
+	const unsigned FULL = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
+	// which chunk: the CTA's 128 consecutive chunks, or 128 entries of the boundary-chunk list
+	int64_t chunk = -1;
+	if (list) {
+		const int n = *n_list;
+		if ((int64_t)blockIdx.x * SK_TPB >= n) return;
+		const int64_t e = (int64_t)blockIdx.x * SK_TPB + threadIdx.x;
+		if (e < n) chunk = list[e];
+	} else {
+		chunk = ((int64_t)blockIdx.x + cta0) * SK_TPB + threadIdx.x;
+		if (chunk * SK_CHUNK >= total) chunk = -1;
+	}
+	// ---- each warp stages the rows of its own 32 chunks: [s - SK_WARM, s + SK_CHUNK + SK_LOOK) as 21 coalesced 16-byte loads per row ----
 	{
-		const int n_vec = (SK_SPAN + SK_WARM) / 16;
-		for (int v = threadIdx.x; v < n_vec; v += SK_TPB) {
-			int64_t g = win_lo + (int64_t)v * 16;
+		constexpr int VPR = (SK_WARM + SK_CHUNK + SK_LOOK) / 16;
+		for (int it = 0; it < VPR; ++it) {
+			const int idx = it * 32 + lane, row = idx / VPR, v = idx - row * VPR;
+			const int64_t ch = __shfl_sync(FULL, chunk, row);
+			if (ch < 0) continue;
+			const int64_t g = ch * SK_CHUNK - SK_WARM + (int64_t)v * 16;
 			uint4 val = make_uint4(0x04040404u, 0x04040404u, 0x04040404u, 0x04040404u);
 			if (g >= 0 && g + 16 <= total) val = *reinterpret_cast<const uint4*>(codes + g);
 			else if (g + 16 > 0 && g < total) {
@@ -174,21 +202,20 @@ k_sketch(const uint8_t *__restrict__ codes, const int64_t *__restrict__ off, int
 				for (int b = 0; b < 16; ++b) tmp[b] = (g + b >= 0 && g + b < total) ? codes[g + b] : 4;
 				val = *reinterpret_cast<uint4*>(tmp);
 			}
-			int L = v * 16;
-			int P = L + 4 * (L >> 8);
-			uint32_t *d = reinterpret_cast<uint32_t*>(sm + P); // a 16-byte group never straddles a 256-byte row
+			uint32_t *d = reinterpret_cast<uint32_t*>(sm + (size_t)((threadIdx.x & ~31) + row) * SK_ROW + v * 16);
 			d[0] = val.x, d[1] = val.y, d[2] = val.z, d[3] = val.w;
 		}
 	}
-	__syncthreads();
-	const int64_t s = cta_base + (int64_t)threadIdx.x * SK_CHUNK;
-	const int64_t chunk = ((int64_t)blockIdx.x + cta0) * SK_TPB + threadIdx.x;
-	if (s >= total) { if (!WRITE && chunk_cnt && chunk * SK_CHUNK < total + SK_CHUNK) {} return; }
+	__syncwarp();
+	if (chunk < 0) return;
+	const int64_t s = chunk * SK_CHUNK;
+	const int64_t win_lo = s - SK_WARM; // row index 0 <-> global win_lo (may be negative)
 	const int64_t e = s + SK_CHUNK < total ? s + SK_CHUNK : total;
 	const uint64_t mask = (1ULL << 2 * k) - 1, shift1 = 2 * (k - 1);
+	const uint8_t *row_sm = sm + (size_t)threadIdx.x * SK_ROW;
 	auto code_at = [&](int64_t g) -> int {
-		int L = (int)(g - win_lo);
-		if (g >= win_lo && L < SK_SPAN + SK_WARM) return sm[L + 4 * (L >> 8)];
+		const int64_t L = g - win_lo;
+		if (L >= 0 && L < SK_WARM + SK_CHUNK + SK_LOOK) return row_sm[L];
 		return codes[g];
 	};
 	SketchState<W> st;
@@ -221,23 +248,31 @@ k_sketch(const uint8_t *__restrict__ codes, const int64_t *__restrict__ off, int
 			for (int64_t g = rs; g < pos; ++g) st.step(code_at(g), (uint32_t)(g - rs), w, k, mask, shift1, nul);
 		}
 		// ---- emit for [pos, seg_end) ----
+		// A minimizer belongs to the chunk that holds its POSITION (the rule k_sketch_par uses), but the automaton writes it up
+		// to w steps later -- when it is replaced, leaves the window, or at the final flush.  So: filter by position, and when the
+		// chunk ends inside the read run on for w more steps to collect the late writes of this chunk's positions.
+		const uint32_t f_lo = (uint32_t)(pos - rs), f_hi = (uint32_t)(seg_end - rs);
+		const int64_t run_end = seg_end == re ? re : (seg_end + W < re ? seg_end + W : re);
 		int seg_cnt;
 		if (WRITE) {
 			EmitWrite ew; ew.out = out; ew.pos = wpos; ew.rid_hi = (uint64_t)(uint32_t)r << 32;
-			for (int64_t g = pos; g < seg_end; ++g) st.step(code_at(g), (uint32_t)(g - rs), w, k, mask, shift1, ew);
-			if (seg_end == re && st.minx != UINT64_MAX) ew(st.minx, st.miny);
+			EmitFilter<EmitWrite> ef{ew, f_lo, f_hi};
+			for (int64_t g = pos; g < run_end; ++g) st.step(code_at(g), (uint32_t)(g - rs), w, k, mask, shift1, ef);
+			if (run_end == re && st.minx != UINT64_MAX) ef(st.minx, st.miny);
 			seg_cnt = (int)(ew.pos - wpos);
 			wpos = ew.pos;
 		} else if (stage) {
 			EmitStage es; es.row = stage + chunk * SK_STAGE_CAP; es.n = 0; es.base = total_cnt; es.rid_hi = (uint64_t)(uint32_t)r << 32;
-			for (int64_t g = pos; g < seg_end; ++g) st.step(code_at(g), (uint32_t)(g - rs), w, k, mask, shift1, es);
-			if (seg_end == re && st.minx != UINT64_MAX) es(st.minx, st.miny);
+			EmitFilter<EmitStage> ef{es, f_lo, f_hi};
+			for (int64_t g = pos; g < run_end; ++g) st.step(code_at(g), (uint32_t)(g - rs), w, k, mask, shift1, ef);
+			if (run_end == re && st.minx != UINT64_MAX) ef(st.minx, st.miny);
 			seg_cnt = es.n;
 			if (seg_cnt) atomicAdd(&read_cnt[r], seg_cnt);
 		} else {
 			EmitCount ec; ec.n = 0;
-			for (int64_t g = pos; g < seg_end; ++g) st.step(code_at(g), (uint32_t)(g - rs), w, k, mask, shift1, ec);
-			if (seg_end == re && st.minx != UINT64_MAX) ++ec.n;
+			EmitFilter<EmitCount> ef{ec, f_lo, f_hi};
+			for (int64_t g = pos; g < run_end; ++g) st.step(code_at(g), (uint32_t)(g - rs), w, k, mask, shift1, ef);
+			if (run_end == re && st.minx != UINT64_MAX) ef(st.minx, st.miny);
 			seg_cnt = ec.n;
 			if (seg_cnt) atomicAdd(&read_cnt[r], seg_cnt);
 		}
@@ -248,6 +283,144 @@ k_sketch(const uint8_t *__restrict__ codes, const int64_t *__restrict__ off, int
 	if (!WRITE) {
 		chunk_cnt[chunk] = total_cnt;
 		if (stage && total_cnt > SK_STAGE_CAP) *overflow = 1;
+	}
+}
+
+// ---- position-parallel sketch of interior chunks (odd k <= 15, w = 10) ----
+// Away from read ends and ambiguous bases mm_sketch's automaton emits exactly the positions whose hash is minimal (ties
+// included) in at least one full window of w consecutive k-mers, in ascending order: a minimum is written when a later
+// k-mer replaces it (`<=`, so every tied minimum gets its turn) or when it leaves the window, and the rescan that follows
+// writes the tied ones that never became the running minimum.  With M[e] = min h[e-9..e] the test for position p is
+// max_{e in [p,p+9]} M[e] == h[p]: two log-step sliding passes in registers.  The quirks of the automaton (first window after
+// a read start or an N, the `l >= w+k` emission thresholds, the running minimum lost at an N, the final flush) all live
+// within w+k bases of a read end or an N; chunks that come that close are not handled here but listed for the automaton.
+//   One warp per 256-base chunk: 19 lanes stage [s-32, s+272) as 2-bit codes; lane L hashes positions s-9+9L .. s-1+9L
+// (both strands from one 64-bit window: the reverse strand is the complement of the field, the forward strand its pair
+// reversal; the invertible hash runs in 32-bit arithmetic because 2k <= 32), lane L then tests positions s+8L .. s+8L+7 and
+// the warp writes its minimizers to the chunk's staging row in position order.
+#define SKP_WARPS 4
+#define SKP_LO 32                       // bases staged before the chunk
+#define SKP_VEC 19                      // 16-byte vectors staged: [s-32, s+272)
+#define SKP_NH 288
+
+MB_D uint32_t mb_hash32(uint32_t key, uint32_t mask)
+{
+	key = (~key + (key << 21)) & mask;
+	key = key ^ key >> 24;
+	key = ((key + (key << 3)) + (key << 8)) & mask;
+	key = key ^ key >> 14;
+	key = ((key + (key << 2)) + (key << 4)) & mask;
+	key = key ^ key >> 28;
+	key = (key + (key << 31)) & mask;
+	return key;
+}
+
+__global__ void __launch_bounds__(SKP_WARPS * 32)
+k_sketch_par(const uint8_t *__restrict__ codes, const int64_t *__restrict__ off, int n_reads, int64_t limit, int k,
+             int32_t *__restrict__ chunk_cnt, int32_t *__restrict__ read_cnt, mb128 *__restrict__ stage, int *__restrict__ overflow,
+             int32_t *__restrict__ blist, int32_t *__restrict__ bctr, int64_t chunk0, int64_t chunk1)
+{
+	__shared__ uint32_t s_pk[SKP_WARPS][SKP_VEC + 3];
+	__shared__ uint32_t s_h[SKP_WARPS][SKP_NH];
+	const unsigned FULL = 0xffffffffu;
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const int64_t chunk = chunk0 + (int64_t)blockIdx.x * SKP_WARPS + wib;
+	if (chunk >= chunk1) return;
+	const int64_t s = chunk * SK_CHUNK;
+	// interior: [s-32, s+272) inside one read, already landed, free of ambiguous bases
+	bool interior = s - SKP_LO >= off[0] && s + SK_CHUNK + 16 <= limit;
+	int r = 0; int64_t rs = 0;
+	if (interior) {
+		r = sk_find_read(off, n_reads, s);
+		rs = off[r];
+		interior = s - SKP_LO >= rs && s + SK_CHUNK + 16 <= off[r + 1];
+	}
+	uint32_t amb = 0;
+	if (interior && lane < SKP_VEC) {
+		const uint4 v = *reinterpret_cast<const uint4*>(codes + s - SKP_LO + lane * 16);
+		amb = (v.x | v.y | v.z | v.w) & 0xfcfcfcfcu;
+		auto pack4 = [](uint32_t x) { const uint32_t t = x & 0x03030303u; return (t | t >> 6 | t >> 12 | t >> 18) & 0xffu; };
+		s_pk[wib][lane] = pack4(v.x) | pack4(v.y) << 8 | pack4(v.z) << 16 | pack4(v.w) << 24;
+	}
+	if (lane >= SKP_VEC && lane < SKP_VEC + 3) s_pk[wib][lane] = 0;
+	if (!interior || __any_sync(FULL, amb != 0)) {
+		if (lane == 0) blist[atomicAdd(bctr, 1)] = (int32_t)chunk;
+		return;
+	}
+	__syncwarp();
+	// ---- hashes of positions s-9+9L+j, j = 0..8 (only those <= s+264 are used) ----
+	const uint32_t mask = k < 16 ? (1u << 2 * k) - 1u : 0xffffffffu;
+	{
+		const int base0 = SKP_LO - 9 - (k - 1) + 9 * lane;        // staged index of the first base of the first k-mer
+		const int wi = base0 >> 4, sh = (base0 & 15) * 2;
+		const uint32_t a = s_pk[wib][wi], b = s_pk[wib][wi + 1], c = wi + 2 < SKP_VEC + 3 ? s_pk[wib][wi + 2] : 0u;
+		uint64_t win = ((uint64_t)b << 32 | a) >> sh;
+		if (sh) win |= (uint64_t)c << (64 - sh);
+		#pragma unroll
+		for (int j = 0; j < 9; ++j) {
+			const uint32_t f = (uint32_t)(win >> (2 * j)) & mask;           // oldest base in the low bits
+			const uint32_t k1 = ~f & mask;                                  // reverse strand: complement, newest base on top
+			const uint32_t t = __brev(f << (32 - 2 * k));
+			const uint32_t k0 = (t >> 1 & 0x55555555u) | (t & 0x55555555u) << 1; // forward strand: oldest base on top
+			const uint32_t z = k0 < k1 ? 0u : 1u;
+			s_h[wib][9 * lane + j] = mb_hash32(z ? k1 : k0, mask) | z << 31;
+		}
+	}
+	__syncwarp();
+	// ---- window test for positions s+8L+c: H[i] = hash of position s+8L-9+i ----
+	uint32_t H[26], Z = 0;
+	#pragma unroll
+	for (int i = 0; i < 26; ++i) {
+		const uint32_t v = s_h[wib][8 * lane + i];
+		H[i] = v & 0x7fffffffu;
+		if (i >= 9 && i < 17) Z |= (v >> 31) << (i - 9);
+	}
+	uint32_t m2[26], m4[26], m8[26], M[26];
+	#pragma unroll
+	for (int i = 1; i < 26; ++i) m2[i] = min(H[i], H[i - 1]);
+	#pragma unroll
+	for (int i = 3; i < 26; ++i) m4[i] = min(m2[i], m2[i - 2]);
+	#pragma unroll
+	for (int i = 7; i < 26; ++i) m8[i] = min(m4[i], m4[i - 4]);
+	#pragma unroll
+	for (int i = 9; i < 26; ++i) M[i] = min(m8[i], m2[i - 8]);       // min of H[i-9..i]
+	uint32_t x2[26], x4[26], x8[26];
+	#pragma unroll
+	for (int i = 9; i < 25; ++i) x2[i] = max(M[i], M[i + 1]);
+	#pragma unroll
+	for (int i = 9; i < 23; ++i) x4[i] = max(x2[i], x2[i + 2]);
+	#pragma unroll
+	for (int i = 9; i < 19; ++i) x8[i] = max(x4[i], x4[i + 4]);
+	uint32_t flags = 0;
+	#pragma unroll
+	for (int c = 0; c < 8; ++c) {
+		const uint32_t X = max(x8[9 + c], x2[9 + c + 8]);               // max of M[9+c .. 18+c]
+		if (X == H[9 + c]) flags |= 1u << c;
+	}
+	// ---- ordered emission into the chunk's staging row ----
+	const int cnt = __popc(flags);
+	int incl = cnt;
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }
+	const int tot = __shfl_sync(FULL, incl, 31);
+	int at = incl - cnt;
+	mb128 *row = stage + chunk * SK_STAGE_CAP;
+	const uint64_t rid_hi = (uint64_t)(uint32_t)r << 32;
+	const uint32_t i0 = (uint32_t)(s - rs) + 8u * lane;
+	#pragma unroll
+	for (int c = 0; c < 8; ++c) {
+		if (flags >> c & 1) {
+			if (at < SK_STAGE_CAP) {
+				row[at].x = (uint64_t)H[9 + c] << 8 | (uint64_t)k;
+				row[at].y = rid_hi | (uint64_t)((i0 + c) << 1 | (Z >> c & 1u));
+			}
+			++at;
+		}
+	}
+	if (lane == 0) {
+		chunk_cnt[chunk] = tot;
+		if (tot > SK_STAGE_CAP) *overflow = 1;
+		if (tot) atomicAdd(&read_cnt[r], tot);
 	}
 }
 
@@ -308,8 +481,17 @@ static void run_sketch(Arena &ar, cudaStream_t st, const uint8_t *codes, const i
 	mb128 *stage = ar.get<mb128>((size_t)n_chunks * SK_STAGE_CAP);
 	int *d_ovf = ar.get<int>(1);
 	CK(cudaMemsetAsync(d_ovf, 0, sizeof(int), st));
+	// odd k <= 15: interior chunks position-parallel, the rest (listed in blist) through the automaton
+	const bool par = (k & 1) && k <= 15 && n_chunks < INT32_MAX;
+	int32_t *blist = par ? ar.get<int32_t>(n_chunks) : nullptr;
+	int32_t *bctr = par ? ar.get<int32_t>(1) : nullptr;
+	if (par) CK(cudaMemsetAsync(bctr, 0, sizeof(int32_t), st));
 	if (!feed) {
-		k_sketch<10, false><<<(unsigned)n_cta, SK_TPB, SK_SMEM_BYTES, st>>>(codes, d_off, n_reads, total, w, k, chunk_cnt, read_cnt, nullptr, nullptr, stage, d_ovf, 0);
+		if (par) {
+			k_sketch_par<<<(unsigned)cdiv(n_chunks, SKP_WARPS), SKP_WARPS * 32, 0, st>>>(codes, d_off, n_reads, total, k, chunk_cnt, read_cnt, stage, d_ovf, blist, bctr, 0, n_chunks);
+			++*n_launch;
+		}
+		k_sketch<10, false><<<(unsigned)n_cta, SK_TPB, SK_SMEM_BYTES, st>>>(codes, d_off, n_reads, total, w, k, chunk_cnt, read_cnt, nullptr, nullptr, stage, d_ovf, 0, blist, bctr);
 		++*n_launch;
 	} else {
 		// pieces of ~1/8 of the batch, whole CTA spans each; piece p is sketched while piece p+1 is in flight
@@ -323,9 +505,16 @@ static void run_sketch(Arena &ar, cudaStream_t st, const uint8_t *codes, const i
 			CK(cudaEventRecord((*feed->events)[p], feed->copy_st));
 			CK(cudaStreamWaitEvent(st, (*feed->events)[p], 0));
 			k_encode_nt4<<<(unsigned)cdiv(cdiv(b1 - b0, 16), 256), 256, 0, st>>>(feed->d_ascii + b0, feed->d_codes + b0, b1 - b0);
-			k_sketch<10, false><<<(unsigned)(c1 - c0), SK_TPB, SK_SMEM_BYTES, st>>>(codes, d_off, n_reads, total, w, k, chunk_cnt, read_cnt, nullptr, nullptr, stage, d_ovf, c0);
+			if (par) {
+				const int64_t k0 = c0 * SK_TPB, k1 = c1 * SK_TPB < n_chunks ? c1 * SK_TPB : n_chunks;
+				k_sketch_par<<<(unsigned)cdiv(k1 - k0, SKP_WARPS), SKP_WARPS * 32, 0, st>>>(codes, d_off, n_reads, b1, k, chunk_cnt, read_cnt, stage, d_ovf, blist, bctr, k0, k1);
+			}
 			*n_launch += 2;
 		}
+		// every piece has landed: the listed boundary chunks (or, for other k, all chunks: the automaton looks w bases past its
+		// chunk) in one launch; CTAs beyond the list return at once
+		k_sketch<10, false><<<(unsigned)n_cta, SK_TPB, SK_SMEM_BYTES, st>>>(codes, d_off, n_reads, total, w, k, chunk_cnt, read_cnt, nullptr, nullptr, stage, d_ovf, 0, blist, bctr);
+		++*n_launch;
 	}
 	exclusive_scan<int32_t>(ar, st, chunk_cnt, chunk_off, n_chunks, n_launch);
 	exclusive_scan<int32_t>(ar, st, read_cnt, o.mini_off, n_reads, n_launch);
@@ -338,7 +527,7 @@ static void run_sketch(Arena &ar, cudaStream_t st, const uint8_t *codes, const i
 	if (!h_ovf) { // the usual case: every chunk fitted its staging row, one 16-byte copy per minimizer finishes the job
 		k_sketch_compact<<<(unsigned)cdiv(n_chunks * 8, 256), 256, 0, st>>>(stage, chunk_cnt, chunk_off, n_chunks, o.mini);
 	} else {      // some 256-base chunk produced more than SK_STAGE_CAP minimizers (low-complexity sequence): re-run and write in place
-		k_sketch<10, true><<<(unsigned)n_cta, SK_TPB, SK_SMEM_BYTES, st>>>(codes, d_off, n_reads, total, w, k, nullptr, nullptr, chunk_off, o.mini, nullptr, nullptr, 0);
+		k_sketch<10, true><<<(unsigned)n_cta, SK_TPB, SK_SMEM_BYTES, st>>>(codes, d_off, n_reads, total, w, k, nullptr, nullptr, chunk_off, o.mini, nullptr, nullptr, 0, nullptr, nullptr);
 	}
 	++*n_launch;
 }

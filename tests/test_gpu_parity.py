@@ -77,6 +77,22 @@ def test_sketch_chunk_boundaries_and_long_sequence(oracle, lib):
     r = synth.random_genome(rng, 3000); r[300:340] = ord("N"); r[511] = ord("N"); r[512] = ord("N"); reads.append(r)
     reads.append(np.tile(synth.random_genome(rng, 7), 300))            # low complexity: ties
     reads.append(synth.random_genome(rng, 400000))                     # contig-sized
+    # mosaic: tandem repeats of several periods (tied hashes inside a window), short homopolymers and single Ns at arbitrary
+    # offsets inside long random sequence -- the position-parallel kernel and the automaton must agree chunk by chunk
+    parts = []
+    for j in range(60):
+        parts.append(synth.random_genome(rng, int(rng.integers(150, 900))))
+        kind = j % 6
+        if kind == 0:
+            parts.append(np.tile(synth.random_genome(rng, int(rng.choice([5, 7, 11, 13]))), int(rng.integers(3, 40))))
+        elif kind == 1:
+            parts.append(np.full(int(rng.integers(16, 60)), rng.choice(list(b"ACGT")), np.uint8))
+        elif kind == 2:
+            parts.append(np.frombuffer(b"N", np.uint8))
+        elif kind == 3:
+            u = synth.random_genome(rng, int(rng.integers(16, 30)))
+            parts += [u, synth.random_genome(rng, int(rng.integers(0, 9))), u]      # the same k-mers twice within a window
+    reads.append(np.concatenate(parts))
     cat, off = synth.concat_reads(reads)
     cap = len(cat) + 64
     out = np.zeros((cap, 2), dtype=np.uint64)
