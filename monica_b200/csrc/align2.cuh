@@ -56,11 +56,61 @@ MB_D int mb_ll_score(const QView &qv, int q_end, int q_len, const TView &tv, int
 }
 
 // one thread per task of this round; gap fills only
-__global__ void k_ztest(AlignCtx c, DpTask *__restrict__ tasks, int64_t n_tasks, const uint32_t *__restrict__ cigar_pool,
+// Cheap screen before the walk: the largest drop mm_test_zdrop can see is bounded by the total penalty mass of the path,
+// and that follows from the CIGAR and the DP score alone -- with Lm aligned columns, G2 the two-piece gap costs and S the
+// score, a*Lm - S - G2 = (a+b) * mismatches (an ambiguous base only makes the estimate larger as long as b >= sc_ambi), so
+// penalty <= b * ceil((a*Lm - S - G2) / (a+b)) + sum(q + e*len).  At or below min(zdrop, zdrop_inv) the task cannot Z-drop
+// and is done without touching the sequences; the others are listed (in task order) for the walk.
+__global__ void k_ztest_screen(AlignCtx c, DpTask *__restrict__ tasks, int64_t n_tasks, const uint32_t *__restrict__ cigar_pool,
+                               int32_t *__restrict__ walk_list, int32_t *__restrict__ n_walk)
+{
+	const int64_t ti = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const int lane = threadIdx.x & 31;
+	bool walk = false;
+	if (ti < n_tasks && tasks[ti].kind == 1) {
+		DpTask &T = tasks[ti];
+		const mb_opt_t &opt = c.opt;
+		const int thr = opt.zdrop < opt.zdrop_inv ? opt.zdrop : opt.zdrop_inv;
+		walk = true;
+		if (opt.a > 0 && opt.b > 0 && opt.b >= (opt.sc_ambi > 0 ? opt.sc_ambi : -opt.sc_ambi) && thr > 0) {
+			const uint32_t *cigar = cigar_pool + T.cigar_off;
+			int64_t lm = 0, g2 = 0, g1 = 0;
+			bool odd = false;
+			for (int k = 0; k < T.n_cigar; ++k) {
+				const uint32_t op = cigar[k] & 0xf; const int64_t len = cigar[k] >> 4;
+				if (op == 0) lm += len;
+				else if (op == 1 || op == 2 || op == 3) {
+					const int64_t c1 = opt.q + opt.e * len, c2 = opt.q2 + opt.e2 * len;
+					g2 += c1 < c2 ? c1 : c2;
+					g1 += c1;
+				} else odd = true;
+			}
+			const int64_t num = (int64_t)opt.a * lm - (int64_t)T.score - g2;
+			if (!odd && num >= 0) {
+				const int64_t x_ub = (num + opt.a + opt.b - 1) / (opt.a + opt.b);
+				if (opt.b * x_ub + g1 <= thr) { walk = false; T.zdrop_code = 0; }
+			}
+		}
+	}
+	const unsigned m = __ballot_sync(0xffffffffu, walk);
+	if (m) {
+		const int leader = __ffs(m) - 1;
+		int base = 0;
+		if (lane == leader) base = atomicAdd(n_walk, __popc(m));
+		base = __shfl_sync(0xffffffffu, base, leader);
+		if (walk) walk_list[base + __popc(m & ((1u << lane) - 1))] = (int32_t)ti;
+	}
+}
+
+// One thread per task, walked as a flat event loop -- every iteration consumes exactly one event (a base of an M run or a
+// whole gap run) -- over the tasks k_ztest_screen listed (`order`, `n_order`), so the
+// lanes do not diverge over nested per-run loops.
+__global__ void k_ztest(AlignCtx c, DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const int32_t *__restrict__ n_order, int64_t n_tasks, const uint32_t *__restrict__ cigar_pool,
                         int32_t *__restrict__ pass2_list, int32_t *__restrict__ n_pass2, int *__restrict__ inv_pool, int32_t *__restrict__ inv_ctr, int *__restrict__ err)
 {
 	int64_t ti = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (ti >= n_tasks) return;
+	if (ti >= n_tasks || (n_order && ti >= *n_order)) return;
+	if (order) ti = order[ti];
 	DpTask &T = tasks[ti];
 	if (T.kind != 1) return;
 	const mb_opt_t &opt = c.opt;
@@ -70,19 +120,27 @@ __global__ void k_ztest(AlignCtx c, DpTask *__restrict__ tasks, int64_t n_tasks,
 	const int n_cigar = T.n_cigar;
 	int32_t score = 0, mx = INT32_MIN, max_i = -1, max_j = -1, i = 0, j = 0, max_zdrop = 0;
 	int pos[2][2] = {{-1, -1}, {-1, -1}};
-	for (int k = 0; k < n_cigar; ++k) {
-		const uint32_t op = cigar[k] & 0xf, len = cigar[k] >> 4;
-		if (op == 0) {
-			for (uint32_t l = 0; l < len; ++l) {
-				score += mb_mat(tv.at(i + l), qv.at(j + l), opt);
-				mb_update_max_zdrop(score, i + l, j + l, &mx, &max_i, &max_j, opt.e, &max_zdrop, pos);
-			}
-			i += len, j += len;
-		} else if (op == 1 || op == 2 || op == 3) {
-			score -= opt.q + opt.e * (int)len;
-			if (op == 1) j += len; else i += len;
-			mb_update_max_zdrop(score, i, j, &mx, &max_i, &max_j, opt.e, &max_zdrop, pos);
+	const int gap_o = opt.q, gap_e = opt.e;
+	int k = 0; uint32_t op = 0, len = 0, rem = 0;
+	for (;;) {
+		if (rem == 0) {
+			if (k >= n_cigar) break;
+			const uint32_t cg = cigar[k++];
+			op = cg & 0xf, len = cg >> 4;
+			if (op == 0) { rem = len; if (rem == 0) continue; }
+			else if (op > 3) continue;
 		}
+		int ev_i, ev_j;
+		if (op == 0) {
+			score += mb_mat(tv.at(i), qv.at(j), opt);
+			ev_i = i, ev_j = j;
+			++i, ++j, --rem;
+		} else {
+			score -= gap_o + gap_e * (int)len;
+			if (op == 1) j += len; else i += len;
+			ev_i = i, ev_j = j;
+		}
+		mb_update_max_zdrop(score, ev_i, ev_j, &mx, &max_i, &max_j, gap_e, &max_zdrop, pos);
 	}
 	int code = 0;
 	const int q_len = pos[1][1] - pos[0][1], t_len = pos[1][0] - pos[0][0];

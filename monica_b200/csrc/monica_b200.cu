@@ -993,7 +993,10 @@ static void map_device_part(mb_index *ix, const mb_opt_t &opt_in, DevPart &part)
 			int32_t *pass2 = ar.get<int32_t>(n_tasks), *n_pass2 = ar.get<int32_t>(1);
 			CK(cudaMemsetAsync(n_pass2, 0, sizeof(int32_t), st));
 			if (!inv_pool) inv_pool = ar.get<int>((size_t)INV_SLOTS * INV_STRIDE);
-			k_ztest<<<(unsigned)cdiv(n_tasks, 128), 128, 0, st>>>(ac, tasks, n_tasks, cigar_pool, pass2, n_pass2, inv_pool, inv_ctr, d_err); ++nl;
+			int32_t *walk = ar.get<int32_t>(n_tasks), *n_walk = ar.get<int32_t>(1);
+			CK(cudaMemsetAsync(n_walk, 0, sizeof(int32_t), st));
+			k_ztest_screen<<<(unsigned)cdiv(n_tasks, 128), 128, 0, st>>>(ac, tasks, n_tasks, cigar_pool, walk, n_walk); ++nl;
+			k_ztest<<<(unsigned)cdiv(n_tasks, 128), 128, 0, st>>>(ac, tasks, walk, n_walk, n_tasks, cigar_pool, pass2, n_pass2, inv_pool, inv_ctr, d_err); ++nl;
 			const int32_t h_pass2 = d2h_scalar(n_pass2, st);
 			phase("ztest");
 			S.n_dp_pass2 += h_pass2;
