@@ -365,12 +365,13 @@ MB_D void mb_fix_cigar_warp(Reg *r, uint32_t *cigar, int32_t *scr, const QView &
 #define UE_NEG (-(1 << 29))
 __global__ void __launch_bounds__(128)
 k_update_extra(AlignCtx c, ReadArrays ra, const int2 *__restrict__ work, int n_work, const RegPlan *__restrict__ plans, const DpTask *__restrict__ tasks,
-               uint32_t *__restrict__ cigar_pool)
+               uint32_t *__restrict__ cigar_pool, const int32_t *__restrict__ perm)
 {
 	const unsigned FULL = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
-	const int wi = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+	int wi = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
 	if (wi >= n_work) return;
+	if (perm) wi = perm[wi];
 	const int read = work[wi].x, slot = work[wi].y;
 	Reg *r = ra.regs + ra.reg_off[read] + slot;
 	if (r->cnt == 0 || !r->has_p) return;
@@ -401,54 +402,86 @@ k_update_extra(AlignCtx c, ReadArrays ra, const int2 *__restrict__ work, int n_w
 	qv.idx0 += (int64_t)qshift * qv.step, tv.idx0 += (int64_t)tshift * tv.step;
 	const int n_cigar = *reinterpret_cast<volatile int32_t*>(&r->n_cigar);
 	const volatile uint32_t *cg = cigar;
-	// block of ops of this lane, and the query / reference offsets at which it starts
+	// Work split: the CIGAR's base events (every base of an M, I or D run) are cut into 32 equal shares, so the lanes run the
+	// same number of iterations whatever the run lengths are.  To find where a share starts, each lane first sums a block of
+	// ops (events, query and reference bases), the warp scans the sums, and the lane walks at most one block of ops from the
+	// start of the block that holds its first event.
 	const int per = (n_cigar + 31) / 32;
 	const int lo = min(lane * per, n_cigar), hi = min(lo + per, n_cigar);
-	int qsum = 0, tsum = 0;
+	int qsum = 0, tsum = 0, esum = 0;
 	for (int k = lo; k < hi; ++k) {
 		const uint32_t op = cg[k] & 0xf, len = cg[k] >> 4;
-		if (op == 0) qsum += len, tsum += len;
-		else if (op == 1) qsum += len;
-		else if (op == 2 || op == 3) tsum += len;
+		if (op == 0) qsum += len, tsum += len, esum += len;
+		else if (op == 1) qsum += len, esum += len;
+		else if (op == 2) tsum += len, esum += len;
+		else if (op == 3) tsum += len;
 	}
-	int qoff = qsum, toff = tsum;
+	int qoff = qsum, toff = tsum, eoff = esum;
 	#pragma unroll
 	for (int d = 1; d < 32; d <<= 1) {
-		const int oq = __shfl_up_sync(FULL, qoff, d), ot = __shfl_up_sync(FULL, toff, d);
-		if (lane >= d) qoff += oq, toff += ot;
+		const int oq = __shfl_up_sync(FULL, qoff, d), ot = __shfl_up_sync(FULL, toff, d), oe = __shfl_up_sync(FULL, eoff, d);
+		if (lane >= d) qoff += oq, toff += ot, eoff += oe;
 	}
-	qoff -= qsum, toff -= tsum;
+	const int n_ev = __shfl_sync(FULL, eoff, 31);
+	qoff -= qsum, toff -= tsum, eoff -= esum;
+	const int share = (n_ev + 31) / 32;
+	const int e0 = min(lane * share, n_ev), my_ev = min(share, n_ev - e0);
+	// the block that holds event e0: the last one whose first event is <= e0 (empty blocks share their successor's offset)
+	int blk = 0;
+	#pragma unroll
+	for (int L = 1; L < 32; ++L) if (__shfl_sync(FULL, eoff, L) <= e0) blk = L;
+	int k = min(blk * per, n_cigar);
+	int q = __shfl_sync(FULL, qoff, blk), t = __shfl_sync(FULL, toff, blk), ev = __shfl_sync(FULL, eoff, blk);
+	uint32_t op = 0, len = 0, rem = 0;
+	if (my_ev > 0) {
+		for (;;) { // whole runs that end at or before e0
+			const uint32_t cgk = cg[k];
+			op = cgk & 0xf, len = cgk >> 4;
+			const int l = op <= 2 ? (int)len : 0;
+			if (l > 0 && ev + l > e0) break;
+			ev += l;
+			if (op == 0) q += len, t += len; else if (op == 1) q += len; else if (op == 2 || op == 3) t += len;
+			++k;
+		}
+		++k;
+		const int skip = e0 - ev;
+		rem = len - skip;
+		if (op != 2) q += skip;
+		if (op != 1) t += skip;
+	}
 	const int sc_a = opt.a < 0 ? -opt.a : opt.a, sc_b = opt.b > 0 ? -opt.b : opt.b, sc_n = -(opt.sc_ambi > 0 ? opt.sc_ambi : -opt.sc_ambi);
+	const int gap_o = opt.q, gap_e = opt.e;
 	int blen = 0, mlen = 0, n_ambi_t = 0;
 	int A = 0, B = UE_NEG, Cm = UE_NEG, D = UE_NEG;
 	auto apply = [&](int d) { A += d; B = max(B + d, 0); Cm = max(Cm, A); D = max(D, B); };
-	for (int k = lo; k < hi; ++k) {
-		const uint32_t op = cg[k] & 0xf, len = cg[k] >> 4;
-		if (op == 0) {
-			int n_ambi = 0, n_diff = 0;
-			for (uint32_t l = 0; l < len; ++l) {
-				const int cq = qv.at(qoff + l), ct = tv.at(toff + l);
-				int d;
-				if (ct > 3 || cq > 3) ++n_ambi, d = sc_n;
-				else if (ct != cq) ++n_diff, d = sc_b;
-				else d = sc_a;
-				apply(d);
+	// one base per iteration.  A gap run charges its penalty with its last base; its other bases apply d = 0, which changes
+	// nothing (the running score is never negative, so an extra clamp at 0 and an extra max candidate are harmless).
+	const uint8_t *qp = qv.codes + qv.idx0 + (int64_t)q * qv.step;
+	const int64_t qstep = qv.step;
+	const int cmask = qv.comp ? 3 : 0;          // 3 - c for c < 4; an ambiguous 4 becomes 7, still > 3
+	int64_t tp = tv.idx0 + t;
+	for (int it = 0; it < share; ++it) {
+		__syncwarp();
+		if (it < my_ev) {
+			while (rem == 0) {
+				const uint32_t cgk = cg[k++];
+				op = cgk & 0xf, len = cgk >> 4, rem = len;
+				if (op == 3) tp += len, rem = 0;
+				else if (op > 3) rem = 0;
 			}
-			blen += len - n_ambi, mlen += len - (n_ambi + n_diff), n_ambi_t += n_ambi;
-			toff += len, qoff += len;
-		} else if (op == 1) {
-			int n_ambi = 0;
-			for (uint32_t l = 0; l < len; ++l) if (qv.at(qoff + l) > 3) ++n_ambi;
-			blen += len - n_ambi, n_ambi_t += n_ambi;
-			apply(-(opt.q + opt.e * (int)len));
-			qoff += len;
-		} else if (op == 2) {
-			int n_ambi = 0;
-			for (uint32_t l = 0; l < len; ++l) if (tv.at(toff + l) > 3) ++n_ambi;
-			blen += len - n_ambi, n_ambi_t += n_ambi;
-			apply(-(opt.q + opt.e * (int)len));
-			toff += len;
-		} else if (op == 3) toff += len;
+			--rem;
+			int cq = 0, ct = 0;
+			if (op != 2) { cq = (int)*qp ^ cmask; qp += qstep; }
+			if (op != 1) { ct = (int)(tv.S[tp >> 3] >> ((tp & 7) << 2) & 0xf); ++tp; }
+			const int ambi = (ct > 3 || cq > 3) ? 1 : 0;
+			n_ambi_t += ambi, blen += 1 - ambi;
+			int d;
+			if (op == 0) {
+				d = ambi ? sc_n : ct != cq ? sc_b : sc_a;
+				mlen += (ambi == 0 && ct == cq) ? 1 : 0;
+			} else d = rem == 0 ? -(gap_o + gap_e * (int)len) : 0;
+			apply(d);
+		}
 	}
 	// combine the blocks in lane order
 	int s_run = 0, mx = 0;
@@ -467,13 +500,14 @@ k_update_extra(AlignCtx c, ReadArrays ra, const int2 *__restrict__ work, int n_w
 // one thread per region of this round: the part of mm_align1 after each mm_align_pair
 __global__ void k_stitch(AlignCtx c, ReadArrays ra, const int2 *__restrict__ work, int n_work, const RegPlan *__restrict__ plans,
                          DpTask *__restrict__ tasks, uint32_t *__restrict__ cigar_pool,
-                         int2 *__restrict__ next_work, int32_t *__restrict__ n_next, int *__restrict__ err)
+                         int2 *__restrict__ next_work, int32_t *__restrict__ n_next, int *__restrict__ err, const int32_t *__restrict__ perm)
 {
 	// one WARP per region: every lane runs the same (uniform) control flow, lane 0 alone writes region state, and the CIGAR
 	// copies -- the bulk of the work -- are spread over the lanes
-	const int wi = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+	int wi = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
 	const int lane = threadIdx.x & 31;
 	if (wi >= n_work) return;
+	if (perm) wi = perm[wi];
 	const int read = work[wi].x, slot = work[wi].y;
 	Reg *regs = ra.regs + ra.reg_off[read];
 	Reg *r = regs + slot;
@@ -621,6 +655,36 @@ __global__ void k_gen_regs(AlignCtx c, ReadArrays ra, ReadScratch rs, int n_read
 		for (int i = 0; i < n; ++i) work[w0 + i] = make_int2(r, i);
 	}
 	if (e) *err = 1;
+}
+
+// ---- work-list permutation: longest regions first ----
+// The warp-per-region kernels (stitch, mm_update_extra) cost time in proportion to the region's length; in read order a launch
+// ends with whatever long region happened to be scheduled late while most SMs sit idle.  A counting sort by descending query
+// span (256-base buckets) gives the order in which those kernels visit the work list; the thread-per-region plan kernels keep
+// read order (neighbouring threads then touch neighbouring anchors).
+#define WORK_NB 256
+MB_D int mb_work_bucket(const Reg *r) { const int b = (r->qe - r->qs) >> 8; return WORK_NB - 1 - (b < WORK_NB - 1 ? (b < 0 ? 0 : b) : WORK_NB - 1); }
+__global__ void k_work_hist(const int2 *__restrict__ work, int n, ReadArrays ra, int32_t *__restrict__ hist)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	atomicAdd(&hist[mb_work_bucket(ra.regs + ra.reg_off[work[i].x] + work[i].y)], 1);
+}
+__global__ void k_work_scan(int32_t *__restrict__ hist) // one block of WORK_NB threads: counts -> exclusive offsets (used as cursors)
+{
+	__shared__ int32_t s[WORK_NB];
+	const int t = threadIdx.x;
+	s[t] = hist[t];
+	__syncthreads();
+	for (int d = 1; d < WORK_NB; d <<= 1) { const int v = t >= d ? s[t - d] : 0; __syncthreads(); s[t] += v; __syncthreads(); }
+	hist[t] = s[t] - hist[t];
+}
+__global__ void k_work_scatter(const int2 *__restrict__ work, int n, ReadArrays ra, int32_t *__restrict__ cursor, int32_t *__restrict__ perm)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const int2 w = work[i];
+	perm[atomicAdd(&cursor[mb_work_bucket(ra.regs + ra.reg_off[w.x] + w.y)], 1)] = i;
 }
 
 // after the alignment rounds: restore upstream's region order (a split-off region sits right after its source), then

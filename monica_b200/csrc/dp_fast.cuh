@@ -62,22 +62,39 @@ MB_D uint32_t dpf_mad(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("mad
 // PRMT in its default mode: selector nibble bit 3 replicates the sign of the selected byte (used to produce zero bytes)
 MB_D uint32_t dpf_prmt(uint32_t a, uint32_t b, uint32_t sel) { uint32_t d; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel)); return d; }
 
-// does a contiguous run of nt4 bytes / 4-bit packed bases hold a code >= 4?
+// does a contiguous run of nt4 bytes / 4-bit packed bases hold a code >= 4?  One masked pass over the aligned 32-bit words
+// with no early exit: the threads of a warp (one task each) stay converged, which an exit-on-first-hit loop does not.
 MB_D bool dpf_bytes_ambig(const uint8_t *p, int64_t lo, int n)
 {
-	int64_t i = lo, end = lo + n;
-	for (; i < end && (i & 3); ++i) if (p[i] & 4) return true;
-	for (; i + 4 <= end; i += 4) if (*reinterpret_cast<const uint32_t*>(p + i) & 0x04040404u) return true;
-	for (; i < end; ++i) if (p[i] & 4) return true;
-	return false;
+	if (n <= 0) return false;
+	const int64_t a0 = (int64_t)(reinterpret_cast<uintptr_t>(p) + lo), a1 = a0 + n - 1; // byte addresses
+	const uint32_t *w = reinterpret_cast<const uint32_t*>(static_cast<uintptr_t>(a0 & ~(int64_t)3));
+	const int nw = (int)((a1 >> 2) - (a0 >> 2)) + 1;
+	const uint32_t first = 0x04040404u << ((a0 & 3) << 3), last = 0x04040404u >> ((3 - (a1 & 3)) << 3);
+	uint32_t acc = 0;
+	for (int i = 0; i < nw; ++i) {
+		uint32_t m = 0x04040404u;
+		if (i == 0) m &= first;
+		if (i == nw - 1) m &= last;
+		acc |= w[i] & m;
+	}
+	return acc != 0;
 }
 MB_D bool dpf_nibbles_ambig(const uint32_t *S, int64_t lo, int n)
 {
-	int64_t i = lo, end = lo + n;
-	for (; i < end && (i & 7); ++i) if (S[i >> 3] >> ((i & 7) << 2) & 4) return true;
-	for (; i + 8 <= end; i += 8) if (S[i >> 3] & 0x44444444u) return true;
-	for (; i < end; ++i) if (S[i >> 3] >> ((i & 7) << 2) & 4) return true;
-	return false;
+	if (n <= 0) return false;
+	const int64_t hi = lo + n - 1;
+	const uint32_t *w = S + (lo >> 3);
+	const int nw = (int)((hi >> 3) - (lo >> 3)) + 1;
+	const uint32_t first = 0x44444444u << ((lo & 7) << 2), last = 0x44444444u >> ((7 - (hi & 7)) << 2);
+	uint32_t acc = 0;
+	for (int i = 0; i < nw; ++i) {
+		uint32_t m = 0x44444444u;
+		if (i == 0) m &= first;
+		if (i == nw - 1) m &= last;
+		acc |= w[i] & m;
+	}
+	return acc != 0;
 }
 MB_D bool dpf_task_ambig(const DpTask &t, const uint8_t *codes, const uint32_t *S, const uint8_t *pool)
 {

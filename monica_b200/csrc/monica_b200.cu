@@ -1004,9 +1004,20 @@ static void map_device_part(mb_index *ix, const mb_opt_t &opt_in, DevPart &part)
 		}
 		S.n_dp_tasks += n_tasks;
 		CK(cudaMemsetAsync(n_work + 1, 0, sizeof(int32_t), st));
-		k_stitch<<<(unsigned)cdiv((int64_t)h_n_work * 32, 128), 128, 0, st>>>(ac, ra, work, h_n_work, plans, tasks, cigar_pool, work2, n_work + 1, d_err); ++nl;
+		// the warp-per-region kernels visit the work list longest region first (see k_work_hist)
+		int32_t *perm = nullptr;
+		if (h_n_work > 1024) {
+			int32_t *hist = ar.get<int32_t>(WORK_NB);
+			perm = ar.get<int32_t>(h_n_work);
+			CK(cudaMemsetAsync(hist, 0, WORK_NB * sizeof(int32_t), st));
+			k_work_hist<<<(unsigned)cdiv(h_n_work, 256), 256, 0, st>>>(work, h_n_work, ra, hist);
+			k_work_scan<<<1, WORK_NB, 0, st>>>(hist);
+			k_work_scatter<<<(unsigned)cdiv(h_n_work, 256), 256, 0, st>>>(work, h_n_work, ra, hist, perm);
+			nl += 3;
+		}
+		k_stitch<<<(unsigned)cdiv((int64_t)h_n_work * 32, 128), 128, 0, st>>>(ac, ra, work, h_n_work, plans, tasks, cigar_pool, work2, n_work + 1, d_err, perm); ++nl;
 		phase("stitch");
-		k_update_extra<<<(unsigned)cdiv((int64_t)h_n_work * 32, 128), 128, 0, st>>>(ac, ra, work, h_n_work, plans, tasks, cigar_pool); ++nl;
+		k_update_extra<<<(unsigned)cdiv((int64_t)h_n_work * 32, 128), 128, 0, st>>>(ac, ra, work, h_n_work, plans, tasks, cigar_pool, perm); ++nl;
 		phase("update_extra");
 		h_n_work = d2h_scalar(n_work + 1, st);
 		check_err(d_err, st, "alignment round");
