@@ -911,7 +911,7 @@ static void map_device_part(mb_index *ix, const mb_opt_t &opt_in, DevPart &part)
 	CK(cudaMemsetAsync(d_err, 0, sizeof(int), st));
 	const int max_chain_gap_ref = opt.max_gap_ref > 0 ? opt.max_gap_ref : opt.max_gap, max_chain_gap_qry = opt.max_gap;
 	if (n_a > 0) {
-		int grid = c.num_sms * 8;
+		int grid = c.num_sms * (getenv("MB_CH_GRID") ? atoi(getenv("MB_CH_GRID")) : 8);
 		k_chain_dp<<<grid, CH_WARPS * 32, 0, st>>>(sd.a, sd.a_roff, n_reads, max_chain_gap_ref, max_chain_gap_qry, opt.bw, opt.max_chain_skip, opt.max_chain_iter,
 			rs.f, rs.p, rs.v, rs.t, wc, d_cells); ++nl;
 	}

@@ -145,15 +145,14 @@ k_sort_anchors(const mb128 *__restrict__ in, mb128 *__restrict__ out, const int6
 		__syncthreads();
 		for (int k2 = 2; k2 <= np; k2 <<= 1) {
 			for (int j = k2 >> 1; j > 0; j >>= 1) {
-				for (int i = threadIdx.x; i < np; i += SORT_TPB) {
-					int l = i ^ j;
-					if (l > i) {
-						uint64_t ka = key[i], kb = key[l];
-						uint32_t ia = idx[i], ib = idx[l];
-						bool gt = ka > kb || (ka == kb && ia > ib);
-						bool up = (i & k2) == 0;
-						if (gt == up) { key[i] = kb, key[l] = ka, idx[i] = ib, idx[l] = ia; }
-					}
+				// one compare-exchange pair per thread-iteration: i = t with a 0 inserted at bit log2(j), l = i | j
+				for (int t = threadIdx.x; t < (np >> 1); t += SORT_TPB) {
+					const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+					const uint64_t ka = key[i], kb = key[l];
+					const uint32_t ia = idx[i], ib = idx[l];
+					const bool gt = ka > kb || (ka == kb && ia > ib);
+					const bool up = (i & k2) == 0;
+					if (gt == up) { key[i] = kb, key[l] = ka, idx[i] = ib, idx[l] = ia; }
 				}
 				__syncthreads();
 			}
