@@ -599,11 +599,12 @@ struct ReadScratch {
 
 // G1a: chain backtrack, one warp per read; writes n_u per read
 __global__ void __launch_bounds__(128)
-k_chain_bt(ReadArrays ra, ReadScratch rs, int n_reads, int min_cnt, int min_sc, int32_t *__restrict__ n_u, int *__restrict__ err)
+k_chain_bt(ReadArrays ra, ReadScratch rs, int n_reads, int min_cnt, int min_sc, int32_t *__restrict__ n_u, int *__restrict__ err, const int32_t *__restrict__ perm)
 {
-	const int r = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+	int r = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
 	const int lane = threadIdx.x & 31;
 	if (r >= n_reads) return;
+	if (perm) r = perm[r];
 	const int64_t base = ra.a_roff[r];
 	const int n = (int)(ra.a_roff[r + 1] - base);
 	int e = 0;

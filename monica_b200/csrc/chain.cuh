@@ -26,8 +26,10 @@ __global__ void __launch_bounds__(CH_WARPS * 32)
 k_chain_dp(const mb128 *__restrict__ a, const int64_t *__restrict__ a_roff, int n_reads,
            int max_dist_x, int max_dist_y, int bw, int max_skip, int max_iter,
            int32_t *__restrict__ f, int32_t *__restrict__ p, int32_t *__restrict__ v, int32_t *__restrict__ t,
-           int32_t *__restrict__ work_ctr, unsigned long long *__restrict__ cells_out)
+           int32_t *__restrict__ work_ctr, unsigned long long *__restrict__ cells_out,
+           const int32_t *__restrict__ perm)
 {
+	// `perm`: the order in which the warps draw the reads (longest first, see k_rp_hist), or nullptr
 	const int lane = threadIdx.x & 31;
 	const unsigned FULL = 0xffffffffu;
 	unsigned long long cells = 0;
@@ -36,6 +38,7 @@ k_chain_dp(const mb128 *__restrict__ a, const int64_t *__restrict__ a_roff, int 
 		if (lane == 0) r = atomicAdd(work_ctr, 1);
 		r = __shfl_sync(FULL, r, 0);
 		if (r >= n_reads) break;
+		if (perm) r = perm[r];
 		const int64_t base = a_roff[r];
 		const int n = (int)(a_roff[r + 1] - base);
 		if (n == 0) continue;

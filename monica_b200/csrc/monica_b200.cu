@@ -911,9 +911,9 @@ static void map_device_part(mb_index *ix, const mb_opt_t &opt_in, DevPart &part)
 	CK(cudaMemsetAsync(d_err, 0, sizeof(int), st));
 	const int max_chain_gap_ref = opt.max_gap_ref > 0 ? opt.max_gap_ref : opt.max_gap, max_chain_gap_qry = opt.max_gap;
 	if (n_a > 0) {
-		int grid = c.num_sms * (getenv("MB_CH_GRID") ? atoi(getenv("MB_CH_GRID")) : 8);
+		int grid = c.num_sms * 8;
 		k_chain_dp<<<grid, CH_WARPS * 32, 0, st>>>(sd.a, sd.a_roff, n_reads, max_chain_gap_ref, max_chain_gap_qry, opt.bw, opt.max_chain_skip, opt.max_chain_iter,
-			rs.f, rs.p, rs.v, rs.t, wc, d_cells); ++nl;
+			rs.f, rs.p, rs.v, rs.t, wc, d_cells, sd.read_perm); ++nl;
 	}
 	S.ms_chain = tm.stop();
 	// region logic
@@ -927,7 +927,7 @@ static void map_device_part(mb_index *ix, const mb_opt_t &opt_in, DevPart &part)
 	int64_t *reg_off = ar.get<int64_t>(n_reads + 1);
 	ra.reg_off = reg_off;
 	const unsigned rb = (unsigned)cdiv(n_reads, 128);
-	k_chain_bt<<<(unsigned)cdiv((int64_t)n_reads * 32, 128), 128, 0, st>>>(ra, rs, n_reads, opt.min_cnt, opt.min_chain_score, n_u, d_err); ++nl;
+	k_chain_bt<<<(unsigned)cdiv((int64_t)n_reads * 32, 128), 128, 0, st>>>(ra, rs, n_reads, opt.min_cnt, opt.min_chain_score, n_u, d_err, sd.read_perm); ++nl;
 	k_reg_cap<<<rb, 128, 0, st>>>(n_u, sd.a_roff, n_reads, cap); ++nl;
 	exclusive_scan<int32_t>(ar, st, cap, reg_off, n_reads, &nl);
 	const int64_t reg_total = d2h_scalar(reg_off + n_reads, st);
@@ -1518,7 +1518,7 @@ extern "C" int mb_chain(int device, const mb_opt_t *opt, const uint64_t *anchors
 	CK(cudaMemsetAsync(wc, 0, sizeof(int32_t), st)); CK(cudaMemsetAsync(d_err, 0, sizeof(int), st));
 	const int max_chain_gap_ref = opt->max_gap_ref > 0 ? opt->max_gap_ref : opt->max_gap;
 	if (n_a) k_chain_dp<<<c.num_sms * 8, CH_WARPS * 32, 0, st>>>(d_a, d_roff, n_reads, max_chain_gap_ref, opt->max_gap, opt->bw, opt->max_chain_skip, opt->max_chain_iter,
-		rs.f, rs.p, rs.v, rs.t, wc, nullptr);
+		rs.f, rs.p, rs.v, rs.t, wc, nullptr, nullptr);
 	if (f && n_a) CK(cudaMemcpyAsync(f, rs.f, n_a * 4, cudaMemcpyDeviceToHost, st));
 	if (p && n_a) CK(cudaMemcpyAsync(p, rs.p, n_a * 4, cudaMemcpyDeviceToHost, st));
 	if (v && n_a) CK(cudaMemcpyAsync(v, rs.v, n_a * 4, cudaMemcpyDeviceToHost, st));
@@ -1527,7 +1527,7 @@ extern "C" int mb_chain(int device, const mb_opt_t *opt, const uint64_t *anchors
 		ReadArrays ra; memset(&ra, 0, sizeof(ra));
 		ra.a = d_a; ra.a_roff = d_roff;
 		int32_t *n_u = ar.get<int32_t>(n_reads + 1);
-		if (n_reads) k_chain_bt<<<(unsigned)cdiv((int64_t)n_reads * 32, 128), 128, 0, st>>>(ra, rs, n_reads, opt->min_cnt, opt->min_chain_score, n_u, d_err);
+		if (n_reads) k_chain_bt<<<(unsigned)cdiv((int64_t)n_reads * 32, 128), 128, 0, st>>>(ra, rs, n_reads, opt->min_cnt, opt->min_chain_score, n_u, d_err, nullptr);
 		std::vector<int32_t> h_nu(n_reads);
 		std::vector<mb128> h_a(n_a); std::vector<uint64_t> h_u(n_a);
 		if (n_reads) CK(cudaMemcpyAsync(h_nu.data(), n_u, n_reads * 4, cudaMemcpyDeviceToHost, st));

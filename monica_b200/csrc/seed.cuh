@@ -116,6 +116,32 @@ __global__ void k_read_anchor_off(const int64_t *__restrict__ mini_off, const in
 	a_roff[r] = a_off[mini_off[r]];
 }
 
+// ---- reads in descending order of anchor count ----
+// The per-read kernels that follow (anchor sort, chaining, chain backtrack) give a read to one CTA or one warp, and a read's
+// cost grows with its anchor count; the longest read of a batch costs milliseconds on its own.  Visiting the reads longest
+// first lets that tail run underneath the bulk instead of after it.  Counting sort on n_anchors / 32 (256 buckets).
+#define RP_NB 256
+MB_D int mb_read_bucket(const int64_t *a_roff, int r) { const int64_t b = (a_roff[r + 1] - a_roff[r]) >> 5; return RP_NB - 1 - (int)(b < RP_NB - 1 ? b : RP_NB - 1); }
+__global__ void k_rp_hist(const int64_t *__restrict__ a_roff, int n_reads, int32_t *__restrict__ hist)
+{
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r < n_reads) atomicAdd(&hist[mb_read_bucket(a_roff, r)], 1);
+}
+__global__ void k_rp_scan(int32_t *__restrict__ hist) // one block of RP_NB threads: counts -> exclusive offsets (then used as cursors)
+{
+	__shared__ int32_t s[RP_NB];
+	const int t = threadIdx.x;
+	s[t] = hist[t];
+	__syncthreads();
+	for (int d = 1; d < RP_NB; d <<= 1) { const int v = t >= d ? s[t - d] : 0; __syncthreads(); s[t] += v; __syncthreads(); }
+	hist[t] = s[t] - hist[t];
+}
+__global__ void k_rp_scatter(const int64_t *__restrict__ a_roff, int n_reads, int32_t *__restrict__ cursor, int32_t *__restrict__ perm)
+{
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r < n_reads) perm[atomicAdd(&cursor[mb_read_bucket(a_roff, r)], 1)] = r;
+}
+
 // ---- K2b: one CTA per read; bitonic sort of (x, original index) in shared memory, global scratch beyond ----
 #define SORT_TPB 256
 #define SORT_SMEM_N 2048   // 2048 * (8+4) = 24 KB static shared memory
@@ -123,12 +149,13 @@ __global__ void k_read_anchor_off(const int64_t *__restrict__ mini_off, const in
 __global__ void __launch_bounds__(SORT_TPB)
 k_sort_anchors(const mb128 *__restrict__ in, mb128 *__restrict__ out, const int64_t *__restrict__ a_roff, int n_reads,
                uint64_t *__restrict__ gkey, uint32_t *__restrict__ gidx, const int64_t *__restrict__ g_roff,
-               int32_t *__restrict__ tie_list, int32_t *__restrict__ n_tie)
+               int32_t *__restrict__ tie_list, int32_t *__restrict__ n_tie, const int32_t *__restrict__ perm)
 {
 	__shared__ uint64_t skey[SORT_SMEM_N];
 	__shared__ uint32_t sidx[SORT_SMEM_N];
 	__shared__ int s_tie;
-	for (int r = blockIdx.x; r < n_reads; r += gridDim.x) {
+	for (int ri = blockIdx.x; ri < n_reads; ri += gridDim.x) {
+		const int r = perm ? perm[ri] : ri;
 		const int64_t base = a_roff[r];
 		const int n = (int)(a_roff[r + 1] - base);
 		if (n == 0) continue;
@@ -174,15 +201,19 @@ k_sort_anchors(const mb128 *__restrict__ in, mb128 *__restrict__ out, const int6
 #define SE_SMEM_N 2560             // 2560 * 16 B = 40 KB of anchors per warp
 #define SE_STACK  2304
 #define SE_SMEM_BYTES (SE_SMEM_N * 16 + 512 * 4 + 64)
+#define SE_BIG_N 12800             // second launch, one CTA per SM: 200 KB of anchors per warp for the few long tied reads
+#define SE_BIG_BYTES (SE_BIG_N * 16 + 512 * 4 + 64)
 
 __global__ void __launch_bounds__(32)
 k_sort_emul(const mb128 *__restrict__ in, mb128 *__restrict__ out, const int64_t *__restrict__ a_roff,
             const int32_t *__restrict__ tie_list, const int32_t *__restrict__ n_tie, int32_t *__restrict__ cursor,
-            int *__restrict__ ws_pool /* per CTA: 3*SE_STACK ints of range stack + leaf list */)
+            int *__restrict__ ws_pool /* per CTA: 3*SE_STACK ints of range stack + leaf list */, int smem_n, int n_lo)
 {
+	// this launch takes the reads with n_lo < n (and stages those with n <= smem_n in shared memory); smaller ones belong to
+	// the other launch
 	extern __shared__ __align__(16) uint8_t se_smem[];
 	mb128 *sa = reinterpret_cast<mb128*>(se_smem);
-	int *bb = reinterpret_cast<int*>(se_smem + SE_SMEM_N * 16), *be = bb + 256;
+	int *bb = reinterpret_cast<int*>(se_smem + (size_t)smem_n * 16), *be = bb + 256;
 	int *sh = be + 256; // [0] = n_leaf, [1] = work item
 	int *stk = ws_pool + (size_t)blockIdx.x * (6 * SE_STACK);
 	int *leaf = stk + 3 * SE_STACK; // (beg, end) pairs
@@ -197,7 +228,8 @@ k_sort_emul(const mb128 *__restrict__ in, mb128 *__restrict__ out, const int64_t
 		const int r = tie_list[t];
 		const int64_t base = a_roff[r];
 		const int n = (int)(a_roff[r + 1] - base);
-		mb128 *a = n <= SE_SMEM_N ? sa : out + base;
+		if (n <= n_lo || (n_lo == 0 && n > smem_n)) continue; // the other launch's read
+		mb128 *a = n <= smem_n ? sa : out + base;
 		for (int i = lane; i < n; i += 32) a[i] = in[base + i];
 		__syncwarp();
 		KeyX key;
@@ -245,6 +277,7 @@ struct SeedOut {
 	mb128 *a_unsorted = nullptr;
 	int64_t *a_roff = nullptr;     // [n_reads+1]
 	int32_t *rep_len = nullptr;    // [n_reads]
+	int32_t *read_perm = nullptr;  // [n_reads] reads by descending anchor count (nullptr for small batches)
 	int64_t n_a = 0;
 };
 
@@ -296,11 +329,30 @@ static void run_seed(Arena &ar, cudaStream_t st, const DevIndex &ix, int mid_occ
 	int32_t *tie_list = ar.get<int32_t>(n_reads);
 	int32_t *ctr = ar.get<int32_t>(2);
 	CK(cudaMemsetAsync(ctr, 0, 2 * sizeof(int32_t), st));
+	if (n_reads > 1024) {
+		int32_t *hist = ar.get<int32_t>(RP_NB);
+		o.read_perm = ar.get<int32_t>(n_reads);
+		CK(cudaMemsetAsync(hist, 0, RP_NB * sizeof(int32_t), st));
+		k_rp_hist<<<(unsigned)cdiv(n_reads, 256), 256, 0, st>>>(o.a_roff, n_reads, hist);
+		k_rp_scan<<<1, RP_NB, 0, st>>>(hist);
+		k_rp_scatter<<<(unsigned)cdiv(n_reads, 256), 256, 0, st>>>(o.a_roff, n_reads, hist, o.read_perm);
+		*n_launch += 3;
+	}
 	int grid = n_reads < num_sms * 8 ? n_reads : num_sms * 8;
-	k_sort_anchors<<<grid, SORT_TPB, 0, st>>>(o.a_unsorted, o.a, o.a_roff, n_reads, gkey, gidx, big_off, tie_list, ctr); ++*n_launch;
+	k_sort_anchors<<<grid, SORT_TPB, 0, st>>>(o.a_unsorted, o.a, o.a_roff, n_reads, gkey, gidx, big_off, tie_list, ctr, o.read_perm); ++*n_launch;
 	static bool se_attr = false;
-	if (!se_attr) { CK(cudaFuncSetAttribute(k_sort_emul, cudaFuncAttributeMaxDynamicSharedMemorySize, SE_SMEM_BYTES)); se_attr = true; }
+	if (!se_attr) { CK(cudaFuncSetAttribute(k_sort_emul, cudaFuncAttributeMaxDynamicSharedMemorySize, SE_BIG_BYTES)); se_attr = true; }
 	const int se_grid = num_sms * 5;   // 43 KB of shared memory per one-warp CTA: five fit an SM
 	int *ws_pool = ar.get<int>((size_t)se_grid * 6 * SE_STACK);
-	k_sort_emul<<<se_grid, 32, SE_SMEM_BYTES, st>>>(o.a_unsorted, o.a, o.a_roff, tie_list, ctr, ctr + 1, ws_pool); ++*n_launch;
+	int *ws_big = ar.get<int>((size_t)num_sms * 6 * SE_STACK);
+	int32_t *cur_big = ar.get<int32_t>(1);
+	CK(cudaMemsetAsync(cur_big, 0, sizeof(int32_t), st));
+	cudaStream_t se_st = st;
+	// the long reads first (they are the tail: one lane replays the sequential passes), in 200 KB of shared memory each
+	k_sort_emul<<<num_sms, 32, SE_BIG_BYTES, se_st>>>(o.a_unsorted, o.a, o.a_roff, tie_list, ctr, cur_big, ws_big, SE_BIG_N, SE_SMEM_N);
+	k_sort_emul<<<se_grid, 32, SE_SMEM_BYTES, se_st>>>(o.a_unsorted, o.a, o.a_roff, tie_list, ctr, ctr + 1, ws_pool, SE_SMEM_N, 0); *n_launch += 2;
+	if (getenv("MB_DEBUG")) {
+		int32_t h = 0; cudaMemcpyAsync(&h, ctr, sizeof(h), cudaMemcpyDeviceToHost, st); cudaStreamSynchronize(st);
+		fprintf(stderr, "[mb] reads with tied anchor keys: %d of %d\n", h, n_reads);
+	}
 }
