@@ -33,7 +33,7 @@
 #pragma once
 #include "align.cuh"
 
-#define DPF_WARPS 4
+#define DPF_WARPS 1
 #define DPF_MAX_Q 1024
 #define DPF_MAX_T 768
 
@@ -106,7 +106,7 @@ MB_D bool dpf_task_ambig(const DpTask &t, const uint8_t *codes, const uint32_t *
 }
 
 template <int C>
-__global__ void __launch_bounds__(DPF_WARPS * 32, (C <= 8 ? 5 : C <= 12 ? 4 : 1))
+__global__ void __launch_bounds__(DPF_WARPS * 32, (C <= 8 ? 20 : C <= 12 ? 16 : 4))
 k_dp_fast(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const int32_t *__restrict__ n_order, int32_t *__restrict__ work_ctr,
           const uint8_t *__restrict__ codes, const uint32_t *__restrict__ S, const uint8_t *__restrict__ pool,
           uint32_t *__restrict__ p_scr, size_t p_stride_words, uint32_t *__restrict__ cigar_pool, DpScoring sc, unsigned long long *__restrict__ cells_out)
