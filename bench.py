@@ -34,7 +34,7 @@ SIMD_WIDTH = 2      # 16x2 packed integer SIMD lanes per 32-bit lane-op (VIADD.1
 # DRAM traffic of the dominant kernel per DP cell, from the committed `ncu --set full` capture (profiles/r01_summary_b.md):
 # (dram__bytes_read.sum + dram__bytes_write.sum) = 4.24 GB for the ~2.7 G cells of that k_dp_fast<7> launch.  Algorithmic bytes:
 # 1 direction byte per cell.
-NCU_TRAFFIC_BYTES_PER_CELL = 1.6
+NCU_TRAFFIC_BYTES_PER_CELL = 1.5   # ncu --set full, k_dp_fast<7>: (dram__bytes_read.sum + dram__bytes_write.sum) / cells of that launch (profiles/r01_summary_c.md)
 
 
 def parse_args():
