@@ -31,10 +31,10 @@ sys.path.insert(0, ROOT)
 
 OPS_PER_CELL = 40   # algorithmic integer ops per DP cell of the two-piece affine recurrence with direction flags
 SIMD_WIDTH = 2      # 16x2 packed integer SIMD lanes per 32-bit lane-op (VIADD.16x2 / VIMNMX3.S16x2 / VIADDMNMX.S16x2)
-# DRAM traffic of the dominant kernel per DP cell, from the committed `ncu --set full` capture (profiles/r01_summary_b.md):
-# (dram__bytes_read.sum + dram__bytes_write.sum) = 4.24 GB for the ~2.7 G cells of that k_dp_fast<7> launch.  Algorithmic bytes:
+# DRAM traffic of the dominant kernel per DP cell, from the `ncu --set full` capture summarised in profiles/r01_summary_c.md:
+# (dram__bytes_read.sum + dram__bytes_write.sum) = 17.0 GB for the ~11.2 G cells of that k_dp_fast<7> launch.  Algorithmic bytes:
 # 1 direction byte per cell.
-NCU_TRAFFIC_BYTES_PER_CELL = 1.5   # ncu --set full, k_dp_fast<7>: (dram__bytes_read.sum + dram__bytes_write.sum) / cells of that launch (profiles/r01_summary_c.md)
+NCU_TRAFFIC_BYTES_PER_CELL = 1.5
 
 
 def parse_args():
