@@ -96,10 +96,27 @@ struct AlignCtx {
 // ------------------------------------------------------------------------------------------------
 MB_D int mb_collect_long_gaps(int as1, int cnt1, const mb128 *a, int min_gap, int *K)
 {
+	// one thread walks its region's anchors: four loads in flight per round trip instead of one
 	int n = 0;
-	for (int i = 1; i < cnt1; ++i) {
-		int gap = ((int32_t)a[as1 + i].y - (int32_t)a[as1 + i - 1].y) - ((int32_t)a[as1 + i].x - (int32_t)a[as1 + i - 1].x);
+	int32_t py = (int32_t)a[as1].y, px = (int32_t)a[as1].x;
+	int i = 1;
+	for (; i + 4 <= cnt1; i += 4) {
+		mb128 v[4];
+		#pragma unroll
+		for (int u = 0; u < 4; ++u) v[u] = a[as1 + i + u];
+		#pragma unroll
+		for (int u = 0; u < 4; ++u) {
+			const int32_t cy = (int32_t)v[u].y, cx = (int32_t)v[u].x;
+			const int gap = (cy - py) - (cx - px);
+			if (gap < -min_gap || gap > min_gap) K[n++] = i + u;
+			py = cy, px = cx;
+		}
+	}
+	for (; i < cnt1; ++i) {
+		const int32_t cy = (int32_t)a[as1 + i].y, cx = (int32_t)a[as1 + i].x;
+		const int gap = (cy - py) - (cx - px);
 		if (gap < -min_gap || gap > min_gap) K[n++] = i;
+		py = cy, px = cx;
 	}
 	return n <= 1 ? 0 : n;
 }
@@ -251,9 +268,9 @@ MB_D int mb_walk_tasks(const AlignCtx &c, const Reg *r, int reg_idx, int read, c
 		++n;
 	}
 	int rs = pl.rs, qs = pl.qs, re, qe;
-	for (int i = 1; i < pl.cnt1; ++i) {
-		const mb128 ai = a[pl.as1 + i];
-		if ((ai.y & (MB_SEED_IGNORE | MB_SEED_TANDEM)) && i != pl.cnt1 - 1) continue;
+	// anchors are read four at a time (one round trip per four anchors), then handled in order
+	auto anchor_step = [&](int i, const mb128 &ai) {
+		if ((ai.y & (MB_SEED_IGNORE | MB_SEED_TANDEM)) && i != pl.cnt1 - 1) return;
 		re = (int32_t)ai.x - k2, qe = (int32_t)ai.y - k2;
 		if (i == pl.cnt1 - 1 || (ai.y & MB_SEED_LONG_JOIN) || (qe - qs >= opt.min_ksw_len && re - rs >= opt.min_ksw_len)) {
 			if (EMIT) {
@@ -268,6 +285,13 @@ MB_D int mb_walk_tasks(const AlignCtx &c, const Reg *r, int reg_idx, int read, c
 			++n;
 			rs = re, qs = qe;
 		}
+	};
+	for (int i0 = 1; i0 < pl.cnt1; i0 += 4) {
+		mb128 pre[4];
+		#pragma unroll
+		for (int u = 0; u < 4; ++u) if (i0 + u < pl.cnt1) pre[u] = a[pl.as1 + i0 + u];
+		#pragma unroll
+		for (int u = 0; u < 4; ++u) if (i0 + u < pl.cnt1) anchor_step(i0 + u, pre[u]);
 	}
 	if (pl.has_right) {
 		if (EMIT) {
