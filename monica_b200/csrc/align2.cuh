@@ -258,8 +258,10 @@ MB_D void mb_fix_cigar_warp(Reg *r, uint32_t *cigar, int32_t *scr, const QView &
 	int n_cigar = r->n_cigar;
 	*qshift = *tshift = 0;
 	if (n_cigar <= 1) return;
-	volatile uint32_t *cg = cigar;
-	volatile int32_t *run = scr;
+	// plain (cached) accesses: every hand-over between lanes below is separated by a __syncwarp(), which orders the warp's
+	// global-memory accesses; volatile would send each access to L2
+	uint32_t *cg = cigar;
+	int32_t *run = scr;
 	const int per = (n_cigar + 31) / 32;
 	const int lo = min(lane * per, n_cigar), hi = min(lo + per, n_cigar);
 	int qsum = 0, tsum = 0;
@@ -300,7 +302,7 @@ MB_D void mb_fix_cigar_warp(Reg *r, uint32_t *cigar, int32_t *scr, const QView &
 	for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(FULL, b_off, d); if (lane >= d) b_off += o; }
 	const int n_bound_all = __shfl_sync(FULL, b_off, 31);
 	b_off -= n_bound;
-	volatile int32_t *blist = scr + n_cigar;
+	int32_t *blist = scr + n_cigar;
 	if (n_bound) for (int k = lo; k < hi; ++k) { const int rn = run[k]; if (rn >= 0 && rn >= (int)(cg[k - 1] >> 4)) blist[b_off++] = k; }
 	int zero_len = 0;
 	for (int k = lo; k < hi; ++k) if ((cg[k] >> 4) == 0) zero_len = 1; // (upstream tests the current length; a spurious flag only runs a no-op compaction)
@@ -400,8 +402,8 @@ k_update_extra(AlignCtx c, ReadArrays ra, const int2 *__restrict__ work, int n_w
 	__syncwarp();
 	qshift = __shfl_sync(FULL, qshift, 0), tshift = __shfl_sync(FULL, tshift, 0);
 	qv.idx0 += (int64_t)qshift * qv.step, tv.idx0 += (int64_t)tshift * tv.step;
-	const int n_cigar = *reinterpret_cast<volatile int32_t*>(&r->n_cigar);
-	const volatile uint32_t *cg = cigar;
+	const int n_cigar = r->n_cigar;   // written by lane 0 before the __syncwarp() above
+	const uint32_t *cg = cigar;
 	// Work split: the CIGAR's base events (every base of an M, I or D run) are cut into 32 equal shares, so the lanes run the
 	// same number of iterations whatever the run lengths are.  To find where a share starts, each lane first sums a block of
 	// ops (events, query and reference bases), the warp scans the sums, and the lane walks at most one block of ops from the
