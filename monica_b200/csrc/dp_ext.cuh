@@ -213,7 +213,7 @@ k_dp_ext(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const in
 				uint32_t *cigar = cigar_pool + T.cigar_off;
 				int n_cigar = 0, state = 0;
 				uint32_t cur_op = 0; int cur_len = 0;
-				const volatile uint8_t *Pb = reinterpret_cast<const volatile uint8_t*>(P) + (grp ? 2 : 0);
+				const uint8_t *Pb = reinterpret_cast<const uint8_t*>(P) + (grp ? 2 : 0); // plain loads: the __syncwarp() above orders them after the forward pass
 				auto push = [&](uint32_t op, int len) {
 					if (cur_len > 0 && op != cur_op) { if (hl == 0) cigar[n_cigar] = (uint32_t)cur_len << 4 | cur_op; ++n_cigar; cur_len = 0; }
 					cur_op = op, cur_len += len;
