@@ -236,34 +236,94 @@ k_sort_emul(const mb128 *__restrict__ in, mb128 *__restrict__ out, const int64_t
 		if (n <= MB_RS_MIN_SIZE) {
 			if (lane == 0) mb_insertsort(a, a + n, key);
 		} else {
-			if (lane == 0) {
-				int sp = 1, n_leaf = 0;
-				stk[0] = 0, stk[1] = n, stk[2] = 56;
-				while (sp > 0) {
-					--sp;
-					const int beg = stk[3 * sp], end = stk[3 * sp + 1];
-					int s = stk[3 * sp + 2];
-					// skip byte levels on which every key of the range agrees: such a pass moves nothing
-					uint64_t diff = 0; const uint64_t k0 = a[beg].x;
-					for (int i = beg + 1; i < end; ++i) diff |= a[i].x ^ k0;
-					while (s > 0 && !(diff >> s & 255)) s -= 8;
-					mb_rs_partition(a, beg, end, s, bb, be, key);
-					if (s) {
-						const int s2 = s > 8 ? s - 8 : 0;
-						for (int k = 0; k < 256; ++k) {
-							const int len = be[k] - bb[k];
-							if (len > MB_RS_MIN_SIZE) { stk[3 * sp] = bb[k], stk[3 * sp + 1] = be[k], stk[3 * sp + 2] = s2; ++sp; } // depth <= 8 levels x 255 siblings < SE_STACK
-							else if (len > 1) {
-								if (2 * n_leaf + 2 <= 3 * SE_STACK) { leaf[2 * n_leaf] = bb[k], leaf[2 * n_leaf + 1] = be[k]; ++n_leaf; }
-								else mb_insertsort(a + bb[k], a + be[k], key);
-							}
-						}
+			// The range stack is walked by the whole warp.  Of one partition pass (radix_emul.cuh mb_rs_partition) only the
+			// cycle-leader permutation is order-dependent and stays with lane 0; the digit histogram, the 256-entry prefix sums
+			// and the hand-out of sub-ranges are spread over the lanes.  Sub-ranges are disjoint, so the order in which they are
+			// pushed and sorted does not change the result.
+			int sp = 1, n_leaf = 0;
+			if (lane == 0) stk[0] = 0, stk[1] = n, stk[2] = 56;
+			__syncwarp();
+			while (sp > 0) {
+				--sp;
+				const int beg = stk[3 * sp], end = stk[3 * sp + 1];
+				int s = stk[3 * sp + 2];
+				__syncwarp();
+				// skip byte levels on which every key of the range agrees: such a pass moves nothing
+				const uint64_t k0 = a[beg].x;
+				uint32_t dlo = 0, dhi = 0;
+				for (int i = beg + 1 + lane; i < end; i += 32) { const uint64_t d = a[i].x ^ k0; dlo |= (uint32_t)d, dhi |= (uint32_t)(d >> 32); }
+				#pragma unroll
+				for (int d = 16; d > 0; d >>= 1) dlo |= __shfl_xor_sync(FULL, dlo, d), dhi |= __shfl_xor_sync(FULL, dhi, d);
+				const uint64_t diff = (uint64_t)dhi << 32 | dlo;
+				while (s > 0 && !(diff >> s & 255)) s -= 8;
+				// digit histogram and bucket ranges: be[k] = end of bucket k, bb[k] = its start (moving cursor during the permutation)
+				for (int k = lane; k < 256; k += 32) be[k] = 0;
+				__syncwarp();
+				for (int i = beg + lane; i < end; i += 32) atomicAdd(&be[(int)(a[i].x >> s & 255)], 1);
+				__syncwarp();
+				{
+					int c[8], tot = 0;
+					#pragma unroll
+					for (int u = 0; u < 8; ++u) { c[u] = be[lane * 8 + u]; tot += c[u]; }
+					int incl = tot;
+					#pragma unroll
+					for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }
+					int run = beg + incl - tot;
+					__syncwarp();
+					#pragma unroll
+					for (int u = 0; u < 8; ++u) { bb[lane * 8 + u] = run; run += c[u]; be[lane * 8 + u] = run; }
+				}
+				__syncwarp();
+				if (lane == 0) {
+					for (int k = 0; k < 256;) {
+						if (bb[k] != be[k]) {
+							int l = (int)(a[bb[k]].x >> s & 255);
+							if (l != k) {
+								mb128 tmp = a[bb[k]], swap;
+								do {
+									swap = tmp; tmp = a[bb[l]]; a[bb[l]++] = swap;
+									l = (int)(tmp.x >> s & 255);
+								} while (l != k);
+								a[bb[k]++] = tmp;
+							} else ++bb[k];
+						} else ++k;
 					}
 				}
-				sh[0] = n_leaf;
+				__syncwarp();
+				if (s) {
+					const int s2 = s > 8 ? s - 8 : 0;
+					// bucket k spans [k ? be[k-1] : beg, be[k]); larger than 64 -> back on the stack, 2..64 -> leaf list
+					int lo8[8], hi8[8], n_big = 0, n_lf = 0;
+					#pragma unroll
+					for (int u = 0; u < 8; ++u) {
+						const int k = lane * 8 + u;
+						lo8[u] = k ? be[k - 1] : beg, hi8[u] = be[k];
+						const int len = hi8[u] - lo8[u];
+						n_big += len > MB_RS_MIN_SIZE, n_lf += len > 1 && len <= MB_RS_MIN_SIZE;
+					}
+					int ib = n_big, il = n_lf;
+					#pragma unroll
+					for (int d = 1; d < 32; d <<= 1) {
+						const int vb = __shfl_up_sync(FULL, ib, d), vl = __shfl_up_sync(FULL, il, d);
+						if (lane >= d) ib += vb, il += vl;
+					}
+					const int tot_b = __shfl_sync(FULL, ib, 31), tot_l = __shfl_sync(FULL, il, 31);
+					int pb = sp + ib - n_big, pl = n_leaf + il - n_lf;
+					#pragma unroll
+					for (int u = 0; u < 8; ++u) {
+						const int len = hi8[u] - lo8[u];
+						if (len > MB_RS_MIN_SIZE) { stk[3 * pb] = lo8[u], stk[3 * pb + 1] = hi8[u], stk[3 * pb + 2] = s2; ++pb; } // depth <= 8 levels x 255 siblings < SE_STACK
+						else if (len > 1) {
+							if (2 * pl + 2 <= 3 * SE_STACK) { leaf[2 * pl] = lo8[u], leaf[2 * pl + 1] = hi8[u]; }
+							else mb_insertsort(a + lo8[u], a + hi8[u], key);
+							++pl;
+						}
+					}
+					sp += tot_b, n_leaf += tot_l;
+				}
+				__syncwarp();
 			}
-			__syncwarp();
-			const int n_leaf = sh[0];
+			if (n_leaf > (3 * SE_STACK) / 2) n_leaf = (3 * SE_STACK) / 2; // the overflow was sorted in place above
 			for (int l = lane; l < n_leaf; l += 32) mb_insertsort(a + leaf[2 * l], a + leaf[2 * l + 1], key);
 		}
 		__syncwarp();
