@@ -97,6 +97,12 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.begin = 0
+
+    def mark_begin(self):
+        """Samples from here on belong to the timed region (the sampler itself is started before the warm-up steps, so that
+        nvidia-smi's start-up -- process spawn, NVML initialisation -- does not land inside the timed region)."""
+        self.begin = len(self.lines)
 
     def start(self):
         try:
@@ -121,7 +127,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        window = self.lines[self.begin:] or self.lines[-1:]   # a very short timed region may fall between two samples
+        for ln in window:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -319,20 +326,28 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record(lib_stream)
-        outs = [step_fn() for _ in range(k)]
+        outs, marks = [], []
+        for _ in range(k):
+            outs.append(step_fn())
+            m = torch.cuda.Event(enable_timing=True)
+            m.record(lib_stream)
+            marks.append(m)
         e1.record(lib_stream)
         e1.synchronize()
         barrier()
         wall = time.perf_counter() - t0
         dev = e0.elapsed_time(e1) * 1e-3
+        timed.each_ms = [a_.elapsed_time(b_) for a_, b_ in zip([e0] + marks[:-1], marks)]   # this rank's steps one by one (diagnostic)
         return max_over_ranks(dev), max_over_ranks(wall), outs
 
     # ---- value leg: resident inputs ----
-    for _ in range(a.warmup):
-        step_value()
     sampler = ClockSampler(local)
     sampler.start()
+    for _ in range(a.warmup):
+        step_value()
+    sampler.mark_begin()
     dt_value, wall_value, outs = timed(step_value, a.steps)
+    each_value_ms = list(timed.each_ms)
     clocks = sampler.stop()
     stats = [o[0].as_dict() for o in outs]
     tot_counts = outs[-1][1]
@@ -457,7 +472,7 @@ def main():
                 cpu = {"value": None, "unit": "Gbases/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
         out = {
             "metric": "mapped Gbases/s", "value": value, "unit": "Gbases/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": dt_value / a.steps * 1e3, "ms_per_step_wall": wall_value / a.steps * 1e3, "timing": "CUDA events on the launching stream, max over ranks", "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": dt_value / a.steps * 1e3, "ms_per_step_wall": wall_value / a.steps * 1e3, "timing": "CUDA events on the launching stream, max over ranks", "ms_each_step_rank0": each_value_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int16x2 DP (int8-range differences) / int32 chaining / uint64 hashing", "data": "synthetic",
             "config": {"workload": workload_name(a), "reads_per_gpu": n_reads, "bases_per_gpu": total_bases, "l2": "inputs larger than L2 (no flush needed)",
                        "index_hbm_bytes": int(L.mb_index_hbm_bytes(al.handle())), "index_build_s": t_index, "parallelism": f"reads sharded over {world} GPU(s), index replicated, 1 NCCL all-reduce of int64[{n_seq}] per step"},
