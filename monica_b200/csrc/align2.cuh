@@ -536,8 +536,15 @@ __global__ void k_stitch(AlignCtx c, ReadArrays ra, const int2 *__restrict__ wor
 		qs1 = qs - (t.reach_end ? qs - pl.qs0 : t.max_q + 1);
 	} else rs1 = rs, qs1 = qs;
 	re1 = rs, qe1 = qs;
+	uint64_t bx = 0, by = 0; // the warp holds 32 anchors at a time (one coalesced load), handed out by shuffle
 	for (int i = 1; i < pl.cnt1; ++i) {
-		const mb128 ai = a[pl.as1 + i];
+		const int bi = (i - 1) & 31;
+		if (bi == 0) {
+			const int g = i + lane;
+			if (g < pl.cnt1) { const mb128 v = a[pl.as1 + g]; bx = v.x, by = v.y; }
+		}
+		mb128 ai;
+		ai.x = __shfl_sync(0xffffffffu, bx, bi), ai.y = __shfl_sync(0xffffffffu, by, bi);
 		if ((ai.y & (MB_SEED_IGNORE | MB_SEED_TANDEM)) && i != pl.cnt1 - 1) continue;
 		re = (int32_t)ai.x - k2, qe = (int32_t)ai.y - k2;
 		re1 = re, qe1 = qe;
