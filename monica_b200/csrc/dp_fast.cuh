@@ -96,6 +96,40 @@ MB_D bool dpf_nibbles_ambig(const uint32_t *S, int64_t lo, int n)
 	}
 	return acc != 0;
 }
+// warp-cooperative forms of the two scans: the 32 lanes read consecutive words of ONE range (coalesced), uniform result
+MB_D bool dpf_bytes_ambig_warp(const uint8_t *p, int64_t lo, int n, int lane)
+{
+	if (n <= 0) return false;
+	const int64_t a0 = (int64_t)(reinterpret_cast<uintptr_t>(p) + lo), a1 = a0 + n - 1;
+	const uint32_t *w = reinterpret_cast<const uint32_t*>(static_cast<uintptr_t>(a0 & ~(int64_t)3));
+	const int nw = (int)((a1 >> 2) - (a0 >> 2)) + 1;
+	const uint32_t first = 0x04040404u << ((a0 & 3) << 3), last = 0x04040404u >> ((3 - (a1 & 3)) << 3);
+	uint32_t acc = 0;
+	for (int i = lane; i < nw; i += 32) {
+		uint32_t m = 0x04040404u;
+		if (i == 0) m &= first;
+		if (i == nw - 1) m &= last;
+		acc |= w[i] & m;
+	}
+	return __any_sync(0xffffffffu, acc != 0);
+}
+MB_D bool dpf_nibbles_ambig_warp(const uint32_t *S, int64_t lo, int n, int lane)
+{
+	if (n <= 0) return false;
+	const int64_t hi = lo + n - 1;
+	const uint32_t *w = S + (lo >> 3);
+	const int nw = (int)((hi >> 3) - (lo >> 3)) + 1;
+	const uint32_t first = 0x44444444u << ((lo & 7) << 2), last = 0x44444444u >> ((7 - (hi & 7)) << 2);
+	uint32_t acc = 0;
+	for (int i = lane; i < nw; i += 32) {
+		uint32_t m = 0x44444444u;
+		if (i == 0) m &= first;
+		if (i == nw - 1) m &= last;
+		acc |= w[i] & m;
+	}
+	return __any_sync(0xffffffffu, acc != 0);
+}
+
 MB_D bool dpf_task_ambig(const DpTask &t, const uint8_t *codes, const uint32_t *S, const uint8_t *pool)
 {
 	const uint8_t *qc = t.q_comp == 2 ? pool : codes;

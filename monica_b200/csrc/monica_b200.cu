@@ -620,25 +620,55 @@ __global__ void k_dp_classify(const DpTask *__restrict__ tasks, const int32_t *_
                               int32_t *__restrict__ lists /* DP_NCLS x n */, int32_t *__restrict__ ctr /* DP_NCLS */,
                               unsigned long long *__restrict__ maxima /* DP_NCLS x 3 */)
 {
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	int id = use_ids ? ids[i] : (int)i;
-	const DpTask &t = tasks[id];
-	int cls = fast_ok ? dpf_class(t.qlen, t.tlen, t.w, t.flag, t.skip) : -1;
-	if (cls < 0 && fast_ok) { cls = dpx_class(t.qlen, t.tlen, t.w, t.flag, t.skip); if (cls >= 0) cls += DP_XBASE; }
-	if (cls >= 0 && dpf_task_ambig(t, codes, S, pool)) cls = -1; // ambiguous bases: exact kernel
-	if (cls >= 0) {
-		lists[(int64_t)cls * n + atomicAdd(&ctr[cls], 1)] = id;
-		atomicMax(&maxima[cls * 3 + 0], (unsigned long long)t.qlen);
-		return;
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const int lane = threadIdx.x & 31;
+	const bool live = i < n;
+	int id = 0, cls = -1;
+	DpTask t;
+	if (live) {
+		id = use_ids ? ids[i] : (int)i;
+		t = tasks[id];
+		cls = fast_ok ? dpf_class(t.qlen, t.tlen, t.w, t.flag, t.skip) : -1;
+		if (cls < 0 && fast_ok) { cls = dpx_class(t.qlen, t.tlen, t.w, t.flag, t.skip); if (cls >= 0) cls += DP_XBASE; }
 	}
-	DpGeom g = dp_geom(t.qlen, t.tlen, t.w);
-	if (t.skip) g.p_bytes = g.ws_bytes = g.h_ints = 0;
-	cls = DP_EBASE + dp_exact_class(g.p_bytes);
-	lists[(int64_t)cls * n + atomicAdd(&ctr[cls], 1)] = id;
-	atomicMax(&maxima[cls * 3 + 0], (unsigned long long)g.p_bytes);
-	atomicMax(&maxima[cls * 3 + 1], (unsigned long long)g.ws_bytes);
-	atomicMax(&maxima[cls * 3 + 2], (unsigned long long)g.h_ints);
+	// ambiguous bases send a task to the exact kernel.  The scan of a task's two windows is done by the whole warp, one task
+	// after the other: 32 lanes reading consecutive words of one window instead of 32 lanes each walking its own
+	const unsigned need = __ballot_sync(0xffffffffu, live && cls >= 0);
+	for (unsigned m = need; m; m &= m - 1) {
+		const int src = __ffs(m) - 1;
+		const int q_comp = __shfl_sync(0xffffffffu, (int)t.q_comp, src), q_step = __shfl_sync(0xffffffffu, (int)t.q_step, src);
+		const int t_step = __shfl_sync(0xffffffffu, (int)t.t_step, src), t_packed = __shfl_sync(0xffffffffu, (int)t.t_packed, src);
+		const int qlen = __shfl_sync(0xffffffffu, t.qlen, src), tlen = __shfl_sync(0xffffffffu, t.tlen, src);
+		const int64_t q_idx0 = __shfl_sync(0xffffffffu, (long long)t.q_idx0, src), t_idx0 = __shfl_sync(0xffffffffu, (long long)t.t_idx0, src);
+		const uint8_t *qc = q_comp == 2 ? pool : codes;
+		const int64_t qlo = q_step > 0 ? q_idx0 : q_idx0 - (qlen - 1), tlo = t_step > 0 ? t_idx0 : t_idx0 - (tlen - 1);
+		bool amb = dpf_bytes_ambig_warp(qc, qlo, qlen, lane);
+		if (!amb) amb = t_packed ? dpf_nibbles_ambig_warp(S, tlo, tlen, lane) : dpf_bytes_ambig_warp(pool, tlo, tlen, lane);
+		if (amb && lane == src) cls = -1;
+	}
+	// class counters and maxima are a handful of hot addresses: one atomic per (warp, class) instead of one per task
+	unsigned m0 = 0, m1 = 0, m2 = 0;
+	if (live) {
+		if (cls >= 0) m0 = (unsigned)t.qlen;
+		else {
+			DpGeom g = dp_geom(t.qlen, t.tlen, t.w);
+			if (t.skip) g.p_bytes = g.ws_bytes = g.h_ints = 0;
+			cls = DP_EBASE + dp_exact_class(g.p_bytes);
+			m0 = (unsigned)g.p_bytes, m1 = (unsigned)g.ws_bytes, m2 = (unsigned)g.h_ints;
+		}
+	}
+	const unsigned peers = __match_any_sync(0xffffffffu, live ? cls : -1);
+	if (!live) return;
+	const int leader = __ffs(peers) - 1, rank = __popc(peers & ((1u << lane) - 1));
+	const unsigned x0 = __reduce_max_sync(peers, m0), x1 = __reduce_max_sync(peers, m1), x2 = __reduce_max_sync(peers, m2);
+	int base = 0;
+	if (lane == leader) {
+		base = atomicAdd(&ctr[cls], __popc(peers));
+		atomicMax(&maxima[cls * 3 + 0], (unsigned long long)x0);
+		if (cls >= DP_EBASE) { atomicMax(&maxima[cls * 3 + 1], (unsigned long long)x1); atomicMax(&maxima[cls * 3 + 2], (unsigned long long)x2); }
+	}
+	base = __shfl_sync(peers, base, leader);
+	lists[(int64_t)cls * n + base + rank] = id;
 }
 
 struct DpRunner {
