@@ -54,23 +54,31 @@ __global__ void k_seed_lookup(DevIndex ix, const mb128 *__restrict__ mini, int64
 	cnt[i] = n < mid_occ ? n : 0;
 }
 
-// one thread per read: rep_len (collect_matches) -- union length of repetitive-minimizer intervals
+// one warp per read: rep_len (collect_matches) -- union length of repetitive-minimizer intervals.  The lanes test 32
+// occurrence counts at a time (coalesced); the sequential interval merge only runs for the few minimizers at or above mid_occ.
 __global__ void k_rep_len(const mb128 *__restrict__ mini, const int64_t *__restrict__ mini_off, const int32_t *__restrict__ occ,
                           int n_reads, int mid_occ, int32_t *__restrict__ rep_len)
 {
-	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	const int r = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+	const int lane = threadIdx.x & 31;
 	if (r >= n_reads) return;
 	int rep_st = 0, rep_en = 0, rl = 0;
-	for (int64_t i = mini_off[r]; i < mini_off[r + 1]; ++i) {
-		if (occ[i] >= mid_occ) {
-			uint32_t q_pos = (uint32_t)mini[i].y, q_span = (uint32_t)(mini[i].x & 0xff);
-			int en = (int)(q_pos >> 1) + 1, st = en - (int)q_span;
+	const int64_t lo = mini_off[r], hi = mini_off[r + 1];
+	for (int64_t i0 = lo; i0 < hi; i0 += 32) {
+		const int64_t i = i0 + lane;
+		const bool rep = i < hi && occ[i] >= mid_occ;
+		uint32_t q_pos = 0, q_span = 0;
+		if (rep) { q_pos = (uint32_t)mini[i].y, q_span = (uint32_t)(mini[i].x & 0xff); }
+		for (unsigned m = __ballot_sync(0xffffffffu, rep); m; m &= m - 1) {
+			const int src = __ffs(m) - 1;
+			const uint32_t qp = __shfl_sync(0xffffffffu, q_pos, src), qs = __shfl_sync(0xffffffffu, q_span, src);
+			const int en = (int)(qp >> 1) + 1, st = en - (int)qs;
 			if (st > rep_en) { rl += rep_en - rep_st; rep_st = st, rep_en = en; }
 			else rep_en = en;
 		}
 	}
 	rl += rep_en - rep_st;
-	rep_len[r] = rl;
+	if (lane == 0) rep_len[r] = rl;
 }
 
 // one thread per query minimizer: emit its anchors (collect_seed_hits) in upstream emission order
@@ -170,9 +178,13 @@ k_sort_anchors(const mb128 *__restrict__ in, mb128 *__restrict__ out, const int6
 			idx[i] = i;
 		}
 		__syncthreads();
+		// bitonic network.  Sub-steps with partner distance j >= 32 exchange through the key/idx arrays, one compare-exchange
+		// pair per thread-iteration; the tail of every stage (j <= 16: partners sit in the same warp) runs in registers with
+		// shuffles, one load and one store per element and one barrier for up to five sub-steps.
+		const unsigned wmask = np >= 32 ? 0xffffffffu : (1u << np) - 1u;
 		for (int k2 = 2; k2 <= np; k2 <<= 1) {
-			for (int j = k2 >> 1; j > 0; j >>= 1) {
-				// one compare-exchange pair per thread-iteration: i = t with a 0 inserted at bit log2(j), l = i | j
+			int j = k2 >> 1;
+			for (; j >= 32; j >>= 1) {
 				for (int t = threadIdx.x; t < (np >> 1); t += SORT_TPB) {
 					const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
 					const uint64_t ka = key[i], kb = key[l];
@@ -183,6 +195,19 @@ k_sort_anchors(const mb128 *__restrict__ in, mb128 *__restrict__ out, const int6
 				}
 				__syncthreads();
 			}
+			for (int i = threadIdx.x; i < np; i += SORT_TPB) {
+				uint64_t k = key[i]; uint32_t ix = idx[i];
+				const bool up = (i & k2) == 0;
+				for (int jj = j; jj > 0; jj >>= 1) {
+					const uint64_t ok = __shfl_xor_sync(wmask, k, jj);
+					const uint32_t oi = __shfl_xor_sync(wmask, ix, jj);
+					const bool gt = k > ok || (k == ok && ix > oi);
+					const bool keep_min = ((i & jj) == 0) == up;
+					if (gt == keep_min) k = ok, ix = oi;
+				}
+				key[i] = k, idx[i] = ix;
+			}
+			__syncthreads();
 		}
 		for (int i = threadIdx.x; i < n; i += SORT_TPB) {
 			out[base + i] = in[base + idx[i]];
@@ -365,7 +390,7 @@ static void run_seed(Arena &ar, cudaStream_t st, const DevIndex &ix, int mid_occ
 	uint64_t *val = ar.get<uint64_t>(n_mini);
 	int64_t *a_off = ar.get<int64_t>(n_mini + 1);
 	k_seed_lookup<<<(unsigned)cdiv(n_mini, 256), 256, 0, st>>>(ix, mini, n_mini, mid_occ, occ, val, cnt); ++*n_launch;
-	k_rep_len<<<(unsigned)cdiv(n_reads, 128), 128, 0, st>>>(mini, mini_off, occ, n_reads, mid_occ, o.rep_len); ++*n_launch;
+	k_rep_len<<<(unsigned)cdiv((int64_t)n_reads * 32, 128), 128, 0, st>>>(mini, mini_off, occ, n_reads, mid_occ, o.rep_len); ++*n_launch;
 	exclusive_scan<int32_t>(ar, st, cnt, a_off, n_mini, n_launch);
 	k_read_anchor_off<<<(unsigned)cdiv(n_reads + 1, 128), 128, 0, st>>>(mini_off, a_off, n_reads, o.a_roff); ++*n_launch;
 	int64_t n_a = 0;
