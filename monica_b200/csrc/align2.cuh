@@ -333,18 +333,40 @@ MB_D void mb_fix_cigar_warp(Reg *r, uint32_t *cigar, int32_t *scr, const QView &
 		}
 	}
 	__syncwarp();
-	if (lane == 0) {
-		if (to_shrink) {
-			int l = 0;
-			for (int k = 0; k < n_cigar; ++k)
-				if (cigar[k] >> 4 != 0) cigar[l++] = cigar[k];
-			n_cigar = l;
-			l = 0;
-			for (int k = 0; k < n_cigar; ++k)
-				if (k == n_cigar - 1 || (cigar[k] & 0xf) != (cigar[k + 1] & 0xf)) cigar[l++] = cigar[k];
-				else cigar[k + 1] += cigar[k] >> 4 << 4;
-			n_cigar = l;
+	if (to_shrink) {
+		// (D) drop the ops whose length became zero, then merge neighbours of the same kind -- two warp-wide compactions
+		// through the second scratch block (upstream: two sequential passes over the whole CIGAR)
+		uint32_t *tmp = reinterpret_cast<uint32_t*>(scr + n_cigar); // the carry list of (B) is dead by now
+		int cnt = 0;
+		for (int k = lo; k < hi; ++k) cnt += (cg[k] >> 4) != 0;
+		int off = cnt;
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(FULL, off, d); if (lane >= d) off += o; }
+		const int n1 = __shfl_sync(FULL, off, 31);
+		off -= cnt;
+		for (int k = lo; k < hi; ++k) { const uint32_t w = cg[k]; if (w >> 4) tmp[off++] = w; }
+		__syncwarp();
+		const int per1 = (n1 + 31) / 32;
+		const int lo1 = min(lane * per1, n1), hi1 = min(lo1 + per1, n1);
+		int heads = 0;
+		for (int k = lo1; k < hi1; ++k) heads += k == 0 || (tmp[k] & 0xf) != (tmp[k - 1] & 0xf);
+		int off2 = heads;
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(FULL, off2, d); if (lane >= d) off2 += o; }
+		const int n2 = __shfl_sync(FULL, off2, 31);
+		off2 -= heads;
+		for (int k = lo1; k < hi1; ++k) {
+			const uint32_t w = tmp[k];
+			if (k == 0 || (w & 0xf) != (tmp[k - 1] & 0xf)) { // head of a run of equal ops: the run's lengths add up
+				uint32_t len = w >> 4;
+				for (int k2 = k + 1; k2 < n1 && (tmp[k2] & 0xf) == (w & 0xf); ++k2) len += tmp[k2] >> 4;
+				cigar[off2++] = len << 4 | (w & 0xf);
+			}
 		}
+		n_cigar = n2;
+		__syncwarp();
+	}
+	if (lane == 0) {
 		if ((cigar[0] & 0xf) == 1 || (cigar[0] & 0xf) == 2) {
 			const int32_t l = (int32_t)(cigar[0] >> 4);
 			if ((cigar[0] & 0xf) == 1) {
