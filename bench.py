@@ -362,6 +362,8 @@ def main():
     dt_e2e, wall_e2e, outs_e = timed(step_e2e, a.steps)
     dt_e2e = max(dt_e2e, wall_e2e)                     # host copies of the result happen after the last event: take the wall clock
     tot_counts_e, d2h = outs_e[-1][1], outs_e[-1][2]
+    if not np.array_equal(np.asarray(tot_counts_e), np.asarray(tot_counts)):
+        raise RuntimeError("per-target counts of the end-to-end path (mb_map_batch, piecewise upload) differ from the resident path")
     e2e_value = float(tot_counts_e.sum() if world > 1 else counts.sum()) * a.steps / dt_e2e / 1e9
 
     ncls_full = ncls.copy()

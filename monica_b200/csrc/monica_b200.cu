@@ -1257,7 +1257,10 @@ static int map_batch_impl(mb_index_t *ix, const mb_opt_t *opt, const uint8_t *ca
 	uint8_t *d_codes; int64_t *d_off; int64_t total;
 	Timer tm(c.st); tm.start();
 	SketchFeed feed;
-	const bool use_feed = n_reads > 0 && off[n_reads] >= ((int64_t)64 << 20);  // worth overlapping from ~64 MB of reads (measured: smaller batches lose)
+	// worth overlapping from ~64 MB of reads (measured: smaller batches lose); MB_FEED_MIN_BYTES overrides the threshold (tests)
+	const char *feed_env = getenv("MB_FEED_MIN_BYTES");
+	const int64_t feed_min = feed_env ? atoll(feed_env) : ((int64_t)64 << 20);
+	const bool use_feed = n_reads > 0 && off[n_reads] >= feed_min;
 	upload_reads(c, cat, off, n_reads, &d_codes, &d_off, &total, false, use_feed ? &feed : nullptr);
 	float ms_h2d = tm.stop();
 	if (stats) stats->ms_h2d = ms_h2d;

@@ -547,6 +547,27 @@ def test_sub_batch_pieces_do_not_change_results(case, monkeypatch):
         assert np.array_equal(counts, base_counts[0]) and np.array_equal(ncls, base_counts[1]), k
 
 
+def test_piecewise_upload_path_equals_plain_path(lib, monkeypatch):
+    """mb_map_batch uploads big batches in pieces underneath the sketch kernels (SketchFeed): chunks at a piece edge are
+    sketched by the automaton after the last piece has landed.  Forced here on a small batch (the threshold is 64 MB)."""
+    from monica_b200 import synth
+    from monica_b200.mappy_shim import Aligner
+    names, seqs = synth.make_genomes(5, 3, 200_000)
+    reads, _ = synth.simulate_reads(6, seqs, 1500, 3000.0, 0.10)
+    cat, off = synth.concat_reads(reads)
+    assert off[-1] > 9 * 32768 and (off[-1] // 32768) % 8 != 0           # several CTA spans per piece, ragged last piece
+    al = Aligner(names=names, seqs=seqs, preset="map-ont", best_n=15)
+    assert al
+    plain = al.map_batch(cat=cat, off=off)
+    monkeypatch.setenv("MB_FEED_MIN_BYTES", "1")
+    fed = al.map_batch(cat=cat, off=off)
+    monkeypatch.delenv("MB_FEED_MIN_BYTES")
+    assert plain.n == fed.n and plain.n > 1000
+    for f in CMP_FIELDS:
+        assert np.array_equal(getattr(plain, f), getattr(fed, f)), f
+    assert np.array_equal(plain.cigar_off, fed.cigar_off) and np.array_equal(plain.cigar_pool, fed.cigar_pool)
+
+
 def test_long_noisy_reads_bit_exact(oracle, lib):
     """BASELINE config 5 in miniature: 50 kb reads at 15 % error against several genomes incl. a strain copy, plus chimeric
     reads (two fragments glued: region splits, long extensions, Z-drops).  Compared hit for hit with the oracle."""
