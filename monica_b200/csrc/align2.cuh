@@ -480,10 +480,15 @@ k_update_extra(AlignCtx c, ReadArrays ra, const int2 *__restrict__ work, int n_w
 	auto apply = [&](int d) { A += d; B = max(B + d, 0); Cm = max(Cm, A); D = max(D, B); };
 	// one base per iteration.  A gap run charges its penalty with its last base; its other bases apply d = 0, which changes
 	// nothing (the running score is never negative, so an extra clamp at 0 and an extra max candidate are harmless).
+	// The kernel is bound by L2 sector traffic (every lane walks its own stretch of both sequences and the lines do not
+	// survive in L1), so each sequence is read a 32-bit word at a time -- 4 query codes / 8 packed reference bases per load --
+	// and the word is kept in a register until the walk leaves it.
 	const uint8_t *qp = qv.codes + qv.idx0 + (int64_t)q * qv.step;
 	const int64_t qstep = qv.step;
 	const int cmask = qv.comp ? 3 : 0;          // 3 - c for c < 4; an ambiguous 4 becomes 7, still > 3
 	int64_t tp = tv.idx0 + t;
+	uintptr_t qwa = 0; uint32_t qw = 0;         // address and content of the query word held
+	int64_t twi = -1; uint32_t tw = 0;          // index and content of the reference word held
 	for (int it = 0; it < share; ++it) {
 		__syncwarp();
 		if (it < my_ev) {
@@ -495,8 +500,18 @@ k_update_extra(AlignCtx c, ReadArrays ra, const int2 *__restrict__ work, int n_w
 			}
 			--rem;
 			int cq = 0, ct = 0;
-			if (op != 2) { cq = (int)*qp ^ cmask; qp += qstep; }
-			if (op != 1) { ct = (int)(tv.S[tp >> 3] >> ((tp & 7) << 2) & 0xf); ++tp; }
+			if (op != 2) {
+				const uintptr_t pa = reinterpret_cast<uintptr_t>(qp), wa = pa & ~(uintptr_t)3;
+				if (wa != qwa) { qwa = wa; qw = *reinterpret_cast<const uint32_t*>(wa); }
+				cq = (int)(qw >> ((pa & 3) << 3) & 0xffu) ^ cmask;
+				qp += qstep;
+			}
+			if (op != 1) {
+				const int64_t wi = tp >> 3;
+				if (wi != twi) { twi = wi; tw = tv.S[wi]; }
+				ct = (int)(tw >> ((tp & 7) << 2) & 0xfu);
+				++tp;
+			}
 			const int ambi = (ct > 3 || cq > 3) ? 1 : 0;
 			n_ambi_t += ambi, blen += 1 - ambi;
 			int d;
