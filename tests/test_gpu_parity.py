@@ -117,6 +117,27 @@ def test_sketch_chunk_boundaries_and_long_sequence(oracle, lib):
         assert np.array_equal(want[i], got), f"read {i} len {len(r)}"
 
 
+@pytest.mark.parametrize("k", [11, 13, 14, 16, 19])
+def test_sketch_other_k(oracle, lib, k):
+    """Odd k <= 15 goes through the position-parallel kernel (32-bit hash, field width 2k), everything else through the
+    automaton for every chunk (even k can stall on a k-mer equal to its reverse complement; k > 15 needs the 64-bit hash)."""
+    from monica_b200 import _lib, synth
+    rng = np.random.default_rng(100 + k)
+    reads = [synth.random_genome(rng, n) for n in (40, 300, 2000, 9000, 33000)]
+    r = synth.random_genome(rng, 5000); r[1000] = ord("N"); r[2570:2580] = ord("N"); reads.append(r)
+    reads.append(np.tile(np.frombuffer(b"ACGT", np.uint8), 600))        # its even-length k-mers are their own reverse complement
+    reads.append(np.concatenate([synth.random_genome(rng, 700), np.tile(synth.random_genome(rng, 9), 60), synth.random_genome(rng, 900)]))
+    cat, off = synth.concat_reads(reads)
+    cap = len(cat) + 64
+    out = np.zeros((cap, 2), dtype=np.uint64)
+    ooff = np.zeros(len(reads) + 1, dtype=np.int64)
+    _lib.check(lib.mb_sketch(0, _lib._ptr(cat), _lib._ptr(off), len(reads), 10, k, _lib._ptr(out), cap, _lib._ptr(ooff)))
+    for i, r in enumerate(reads):
+        got = out[ooff[i]:ooff[i + 1]].copy()
+        got[:, 1] &= np.uint64(0xffffffff)
+        assert np.array_equal(oracle.sketch(r, 10, k), got), f"k {k} read {i} len {len(r)}"
+
+
 def test_seed_lookup_and_sort_bit_exact(case, lib):
     from monica_b200 import _lib, synth
     al, oidx, reads, traces = case
