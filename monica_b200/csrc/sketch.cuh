@@ -315,10 +315,19 @@ MB_D uint32_t mb_hash32(uint32_t key, uint32_t mask)
 	return key;
 }
 
+// read that holds the first base of every chunk (one thread per chunk: the binary search is then not repeated by 32 lanes)
+__global__ void k_chunk_read(const int64_t *__restrict__ off, int n_reads, int64_t n_chunks, int32_t *__restrict__ chunk_read)
+{
+	const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= n_chunks) return;
+	const int64_t s = c * SK_CHUNK;
+	chunk_read[c] = s >= off[0] ? sk_find_read(off, n_reads, s) : 0;
+}
+
 __global__ void __launch_bounds__(SKP_WARPS * 32)
 k_sketch_par(const uint8_t *__restrict__ codes, const int64_t *__restrict__ off, int n_reads, int64_t limit, int k,
              int32_t *__restrict__ chunk_cnt, int32_t *__restrict__ read_cnt, mb128 *__restrict__ stage, int *__restrict__ overflow,
-             int32_t *__restrict__ blist, int32_t *__restrict__ bctr, int64_t chunk0, int64_t chunk1)
+             int32_t *__restrict__ blist, int32_t *__restrict__ bctr, int64_t chunk0, int64_t chunk1, const int32_t *__restrict__ chunk_read)
 {
 	__shared__ uint32_t s_pk[SKP_WARPS][SKP_VEC + 3];
 	__shared__ uint32_t s_h[SKP_WARPS][SKP_NH];
@@ -331,7 +340,7 @@ k_sketch_par(const uint8_t *__restrict__ codes, const int64_t *__restrict__ off,
 	bool interior = s - SKP_LO >= off[0] && s + SK_CHUNK + 16 <= limit;
 	int r = 0; int64_t rs = 0;
 	if (interior) {
-		r = sk_find_read(off, n_reads, s);
+		r = chunk_read[chunk];
 		rs = off[r];
 		interior = s - SKP_LO >= rs && s + SK_CHUNK + 16 <= off[r + 1];
 	}
@@ -485,10 +494,14 @@ static void run_sketch(Arena &ar, cudaStream_t st, const uint8_t *codes, const i
 	const bool par = (k & 1) && k <= 15 && n_chunks < INT32_MAX;
 	int32_t *blist = par ? ar.get<int32_t>(n_chunks) : nullptr;
 	int32_t *bctr = par ? ar.get<int32_t>(1) : nullptr;
-	if (par) CK(cudaMemsetAsync(bctr, 0, sizeof(int32_t), st));
+	int32_t *chunk_read = par ? ar.get<int32_t>(n_chunks) : nullptr;
+	if (par) {
+		CK(cudaMemsetAsync(bctr, 0, sizeof(int32_t), st));
+		k_chunk_read<<<(unsigned)cdiv(n_chunks, 256), 256, 0, st>>>(d_off, n_reads, n_chunks, chunk_read); ++*n_launch;
+	}
 	if (!feed) {
 		if (par) {
-			k_sketch_par<<<(unsigned)cdiv(n_chunks, SKP_WARPS), SKP_WARPS * 32, 0, st>>>(codes, d_off, n_reads, total, k, chunk_cnt, read_cnt, stage, d_ovf, blist, bctr, 0, n_chunks);
+			k_sketch_par<<<(unsigned)cdiv(n_chunks, SKP_WARPS), SKP_WARPS * 32, 0, st>>>(codes, d_off, n_reads, total, k, chunk_cnt, read_cnt, stage, d_ovf, blist, bctr, 0, n_chunks, chunk_read);
 			++*n_launch;
 		}
 		k_sketch<10, false><<<(unsigned)n_cta, SK_TPB, SK_SMEM_BYTES, st>>>(codes, d_off, n_reads, total, w, k, chunk_cnt, read_cnt, nullptr, nullptr, stage, d_ovf, 0, blist, bctr);
@@ -507,7 +520,7 @@ static void run_sketch(Arena &ar, cudaStream_t st, const uint8_t *codes, const i
 			k_encode_nt4<<<(unsigned)cdiv(cdiv(b1 - b0, 16), 256), 256, 0, st>>>(feed->d_ascii + b0, feed->d_codes + b0, b1 - b0);
 			if (par) {
 				const int64_t k0 = c0 * SK_TPB, k1 = c1 * SK_TPB < n_chunks ? c1 * SK_TPB : n_chunks;
-				k_sketch_par<<<(unsigned)cdiv(k1 - k0, SKP_WARPS), SKP_WARPS * 32, 0, st>>>(codes, d_off, n_reads, b1, k, chunk_cnt, read_cnt, stage, d_ovf, blist, bctr, k0, k1);
+				k_sketch_par<<<(unsigned)cdiv(k1 - k0, SKP_WARPS), SKP_WARPS * 32, 0, st>>>(codes, d_off, n_reads, b1, k, chunk_cnt, read_cnt, stage, d_ovf, blist, bctr, k0, k1, chunk_read);
 			}
 			*n_launch += 2;
 		}
