@@ -659,7 +659,15 @@ __global__ void k_dp_classify(const DpTask *__restrict__ tasks, const int32_t *_
 	}
 	const unsigned peers = __match_any_sync(0xffffffffu, live ? cls : -1);
 	if (!live) return;
-	const int leader = __ffs(peers) - 1, rank = __popc(peers & ((1u << lane) - 1));
+	// rank among the warp's tasks of this class by query length: the DP kernels pair neighbouring list entries in one warp,
+	// and a pair runs for the longer of its two queries
+	const int leader = __ffs(peers) - 1;
+	int rank = 0;
+	for (unsigned m = peers; m; m &= m - 1) {
+		const int src = __ffs(m) - 1;
+		const int q = __shfl_sync(peers, t.qlen, src);
+		rank += (q < t.qlen || (q == t.qlen && src < lane)) ? 1 : 0;
+	}
 	const unsigned x0 = __reduce_max_sync(peers, m0), x1 = __reduce_max_sync(peers, m1), x2 = __reduce_max_sync(peers, m2);
 	int base = 0;
 	if (lane == leader) {
