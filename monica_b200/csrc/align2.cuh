@@ -774,23 +774,28 @@ __global__ void k_finish(AlignCtx c, ReadArrays ra, ReadScratch rs, int n_reads,
 __global__ void k_write_hits(ReadArrays ra, int n_reads, const int64_t *__restrict__ hit_off, const int64_t *__restrict__ cig_off, int64_t n_hits_total,
                              int32_t *__restrict__ fields, int64_t *__restrict__ hit_cig_off, const uint32_t *__restrict__ cigar_pool, uint32_t *__restrict__ out_cigar)
 {
-	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	// one warp per read: lane 0 writes the hit fields, the CIGAR copy (the bulk of the bytes) is spread over the lanes
+	const int r = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+	const int lane = threadIdx.x & 31;
 	if (r >= n_reads) return;
 	const Reg *regs = ra.regs + ra.reg_off[r];
 	const int n = ra.n_regs[r];
 	int64_t h = hit_off[r], co = cig_off[r];
 	for (int i = 0; i < n; ++i, ++h) {
 		const Reg &g = regs[i];
-		const int32_t vals[HIT_NF] = { r, g.rid, g.rev, g.qs, g.qe, g.rs, g.re, g.mapq, g.mlen, g.blen,
-			g.blen - g.mlen + (g.has_p ? g.n_ambi : 0), g.has_p ? g.dp_max : 0, g.has_p ? g.dp_max2 : 0, g.score, g.score0, g.cnt, g.subsc, g.n_sub,
-			g.id, g.parent, g.id == g.parent, g.sam_pri, g.has_p ? g.n_cigar : 0 };
-		#pragma unroll
-		for (int f = 0; f < HIT_NF; ++f) fields[(int64_t)f * n_hits_total + h] = vals[f];
-		hit_cig_off[h] = co;
+		if (lane == 0) {
+			const int32_t vals[HIT_NF] = { r, g.rid, g.rev, g.qs, g.qe, g.rs, g.re, g.mapq, g.mlen, g.blen,
+				g.blen - g.mlen + (g.has_p ? g.n_ambi : 0), g.has_p ? g.dp_max : 0, g.has_p ? g.dp_max2 : 0, g.score, g.score0, g.cnt, g.subsc, g.n_sub,
+				g.id, g.parent, g.id == g.parent, g.sam_pri, g.has_p ? g.n_cigar : 0 };
+			#pragma unroll
+			for (int f = 0; f < HIT_NF; ++f) fields[(int64_t)f * n_hits_total + h] = vals[f];
+			hit_cig_off[h] = co;
+		}
 		if (g.has_p) {
 			const uint32_t *src = cigar_pool + g.cigar_off;
-			for (int k = 0; k < g.n_cigar; ++k) out_cigar[co + k] = src[k];
-			co += g.n_cigar;
+			const int nc = g.n_cigar;
+			for (int k = lane; k < nc; k += 32) out_cigar[co + k] = src[k];
+			co += nc;
 		}
 	}
 }

@@ -51,11 +51,26 @@ static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 struct Arena {
 	char *base = nullptr;
 	size_t cap = 0, used = 0, high = 0;
+	size_t batch_total = 0;     // bytes handed out since the last reset, over all slabs
 	std::vector<char*> retired; // slabs outgrown during a batch; freed at reset
 	void reset() {
+		const bool grew = !retired.empty();
 		for (char *p : retired) cudaFree(p);
 		retired.clear();
-		used = 0;
+		// A batch that outgrew its slab leaves a last slab that held only the tail of its allocations; the next batch of the
+		// same size would outgrow it again (a cudaMalloc / cudaFree of gigabytes inside that batch, and again in the one after).
+		// Size the arena for the whole batch at once instead, so that the second batch already runs without any allocation.
+		if (grew) {
+			const size_t want = ((batch_total + batch_total / 4 + ((size_t)64 << 20)) + 255) & ~(size_t)255;
+			if (want > cap) {
+				char *nb = nullptr;
+				if (base) cudaFree(base);
+				base = nullptr; cap = 0;
+				if (cudaMalloc(&nb, want) == cudaSuccess) base = nb, cap = want;
+				else cudaGetLastError(); // fall back to growing on demand
+			}
+		}
+		used = 0; batch_total = 0;
 	}
 	void release() {
 		reset();
@@ -75,7 +90,7 @@ struct Arena {
 			base = nb; cap = ncap; used = 0;
 		}
 		void *p = base + used;
-		used += bytes;
+		used += bytes; batch_total += bytes;
 		if (used > high) high = used;
 		return p;
 	}

@@ -1078,7 +1078,7 @@ static void map_device_part(mb_index *ix, const mb_opt_t &opt_in, DevPart &part)
 	int64_t *d_hcoff = ar.get<int64_t>(n_h + 1);
 	uint32_t *d_hcig = ar.get<uint32_t>(n_c + 1);
 	// cigars of surviving regions live in per-round pools that are all still allocated in the arena
-	k_write_hits<<<rb, 128, 0, st>>>(ra, n_reads, hit_off, hcig_off, n_h, d_fields, d_hcoff, (const uint32_t*)nullptr, d_hcig); ++nl;
+	k_write_hits<<<(unsigned)cdiv((int64_t)n_reads * 32, 128), 128, 0, st>>>(ra, n_reads, hit_off, hcig_off, n_h, d_fields, d_hcoff, (const uint32_t*)nullptr, d_hcig); ++nl;
 	S.ms_post = tm.stop();
 	S.n_hits = n_h;
 	part.d_fields = d_fields, part.d_hcoff = d_hcoff, part.d_hcig = d_hcig, part.d_hit_off = hit_off, part.d_rep_len = sd.rep_len;
@@ -1324,7 +1324,8 @@ extern "C" int mb_count(mb_index_t *ix, const mb_hits_t *h, int32_t mapq_min, in
 	if ((int64_t)h->fields.size() != (int64_t)HIT_NF * h->n) throw mb_error(MB_ERR_ARG, "hits were produced with want_hits=0");
 	ThreadCtx &c = get_ctx(ix->device);
 	cudaStream_t st = c.st;
-	c.ar.reset();
+	// (no arena reset here: the scratch below is appended behind the last batch, whose device-resident hits mb_count_last
+	// may still be asked for; the next mapping call resets the arena)
 	const int n_seq = (int)ix->names.size(), n_reads = h->n_reads;
 	if (c.n_counts < n_seq + 4) {
 		if (c.d_counts) cudaFree(c.d_counts);
