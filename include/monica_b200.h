@@ -17,7 +17,7 @@
  *        fields hit.is_primary .mapq .ctg .NM .mlen monica/genomes/aligner.py:194-195,216-217
  *   mb_count
  *        best_hit + taxon/accession Counter update monica/genomes/aligner.py:225-263,328-339
- *   mb_sketch / mb_seed / mb_chain / mb_dp_batch
+ *   mb_sketch / mb_seed / mb_chain / mb_dp_batch / mb_ll_batch
  *        per-stage entry points for parity tests (no reference counterpart; stages of mm_map_frag)
  */
 #ifndef MONICA_B200_H
@@ -68,7 +68,9 @@ typedef struct {
 	int64_t dp_cells_exact;   /* DP cells evaluated by k_dp (the rest of dp_cells went through k_dp_fast) */
 	int64_t n_kdp_fast;       /* k_dp_fast launches (one per non-empty column class and pass) */
 	int64_t n_ext_tasks, dp_cells_ext; /* end extensions through k_dp_ext */
-	float   ms_kdp_ext; int32_t pad_;
+	float   ms_kdp_ext; int32_t n_inv; /* inversion hits produced (mm_align1_inv) */
+	int64_t arena_bytes;      /* device scratch handed out for this batch (largest piece) */
+	int32_t n_pieces, pad_;   /* sequential pieces the batch was cut into (memory budget) */
 } mb_stats_t;
 
 const char *mb_last_error(void);
@@ -178,6 +180,15 @@ typedef struct {
 } mb_dp_task_t;
 int  mb_dp_batch(int device, const mb_opt_t *opt, mb_dp_task_t *tasks, int64_t n_tasks, const uint8_t *seqpool, int64_t n_seqpool,
                  uint32_t *cigar_pool, int64_t n_cigar_pool);
+
+/* batch of stand-alone local alignments (ksw_ll_i16 as mm_test_zdrop / mm_align1_inv call it) on nt4-coded sequences:
+ * score, query end and target end with upstream's striped-layout tie rules */
+typedef struct {
+	int32_t qlen, tlen;
+	int64_t q_off, t_off;        /* into seqpool */
+	int32_t score, qe, te, pad_; /* outputs */
+} mb_ll_task_t;
+int  mb_ll_batch(int device, const mb_opt_t *opt, mb_ll_task_t *tasks, int64_t n_tasks, const uint8_t *seqpool, int64_t n_seqpool);
 
 /* ---- measurement helpers ----
  * mb_stream: the cudaStream_t on which the calling thread's batches of this index run (so a caller can bracket K batches

@@ -39,7 +39,8 @@ class Stats(C.Structure):
                                          "dp_cells", "n_hits", "n_rounds")] + \
                [(n, C.c_float) for n in ("ms_sketch", "ms_seed", "ms_sort", "ms_chain", "ms_glue", "ms_dp", "ms_post",
                                          "ms_total", "ms_h2d", "ms_d2h")] + [("n_launches", C.c_int64), ("ms_kdp", C.c_float), ("n_kdp", C.c_int32), ("ms_kdp_fast", C.c_float), ("ms_kdp_exact", C.c_float),
-                  ("n_fast_tasks", C.c_int64), ("n_exact_tasks", C.c_int64), ("chain_cells", C.c_int64), ("dp_cells_exact", C.c_int64), ("n_kdp_fast", C.c_int64), ("n_ext_tasks", C.c_int64), ("dp_cells_ext", C.c_int64), ("ms_kdp_ext", C.c_float), ("pad_", C.c_int32)]
+                  ("n_fast_tasks", C.c_int64), ("n_exact_tasks", C.c_int64), ("chain_cells", C.c_int64), ("dp_cells_exact", C.c_int64), ("n_kdp_fast", C.c_int64), ("n_ext_tasks", C.c_int64), ("dp_cells_ext", C.c_int64), ("ms_kdp_ext", C.c_float), ("n_inv", C.c_int32),
+                  ("arena_bytes", C.c_int64), ("n_pieces", C.c_int32), ("pad_", C.c_int32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -55,6 +56,11 @@ class DpTask(C.Structure):
     ]
 
 
+class LLTask(C.Structure):
+    _fields_ = [("qlen", C.c_int32), ("tlen", C.c_int32), ("q_off", C.c_int64), ("t_off", C.c_int64),
+                ("score", C.c_int32), ("qe", C.c_int32), ("te", C.c_int32), ("pad_", C.c_int32)]
+
+
 HIT_FIELDS = ["read_idx", "rid", "rev", "qs", "qe", "rs", "re", "mapq", "mlen", "blen", "nm", "dp_max", "dp_max2",
               "score", "score0", "cnt", "subsc", "n_sub", "id", "parent", "is_primary", "sam_pri", "n_cigar"]
 
@@ -66,7 +72,7 @@ SYMBOLS = [
     "mb_map_batch", "mb_map_batch_ex", "mb_reads_upload", "mb_reads_free", "mb_map_resident",
     "mb_hits_n", "mb_hits_field", "mb_hits_cigar_off", "mb_hits_cigar_pool", "mb_hits_rep_len", "mb_hits_free",
     "mb_count", "mb_count_last", "mb_count_device_ptr", "mb_count_fetch", "mb_normalize_last",
-    "mb_sketch", "mb_seed", "mb_chain", "mb_dp_batch", "mb_int_peak", "mb_stream",
+    "mb_sketch", "mb_seed", "mb_chain", "mb_dp_batch", "mb_ll_batch", "mb_int_peak", "mb_stream",
     "mb_fastq_load", "mb_fastq_n", "mb_fastq_seqs", "mb_fastq_header", "mb_fastq_ids_unique", "mb_fastq_route", "mb_fastq_free",
     "mb_db_build",
 ]
@@ -147,6 +153,7 @@ def lib():
     L.mb_seed.argtypes = [vp, C.POINTER(Opt), vp, vp, i32, vp, i64, vp, vp]
     L.mb_chain.argtypes = [C.c_int, C.POINTER(Opt), vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
     L.mb_dp_batch.argtypes = [C.c_int, C.POINTER(Opt), C.POINTER(DpTask), i64, vp, i64, vp, i64]
+    L.mb_ll_batch.argtypes = [C.c_int, C.POINTER(Opt), C.POINTER(LLTask), i64, vp, i64]
     _lib = L
     return L
 

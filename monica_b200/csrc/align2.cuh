@@ -5,8 +5,11 @@
 #pragma once
 #include "align.cuh"
 
-#define INV_SLOTS 2048
-#define INV_STRIDE (2 * 5002)
+#include "ll.cuh"
+
+// a gap fill whose CIGAR walk dropped by more than zdrop_inv: the inversion test (a local alignment of the dropped stretch
+// against its reverse complement) is run by k_ztest_ll, one warp per candidate
+struct ZCand { int32_t task, q_end, q_len, t_st, t_len, max_zdrop; };
 
 MB_D void mb_update_max_zdrop(int32_t score, int i, int j, int32_t *mx, int *max_i, int *max_j, int e, int *max_zdrop, int pos[2][2])
 {
@@ -26,33 +29,6 @@ MB_D int mb_mat(int ct, int cq, const mb_opt_t &o)
 {
 	if (ct > 3 || cq > 3) return -(o.sc_ambi > 0 ? o.sc_ambi : -o.sc_ambi);
 	return ct == cq ? (o.a < 0 ? -o.a : o.a) : (o.b > 0 ? -o.b : o.b);
-}
-
-// ksw2_ll_sse.c ksw_ll_i16: local single-affine score between qseq2 (reverse complement of q[qe-1..qs]) and t[ts..te)
-MB_D int mb_ll_score(const QView &qv, int q_end, int q_len, const TView &tv, int t_st, int t_len, const mb_opt_t &o, int *H, int *E)
-{
-	int gmax = 0;
-	for (int j = 0; j <= q_len; ++j) H[j] = E[j] = 0;
-	for (int i = 0; i < t_len; ++i) {
-		int f = 0, h_diag = 0;
-		const int ct = tv.at(t_st + i);
-		for (int j = 0; j < q_len; ++j) {
-			int c = qv.at(q_end - j - 1);
-			c = c >= 4 ? 4 : 3 - c;
-			int h = h_diag + mb_mat(ct, c, o);
-			int e = E[j + 1];
-			h_diag = H[j + 1];
-			h = h > e ? h : e;
-			h = h > f ? h : f;
-			h = h > 0 ? h : 0;
-			H[j + 1] = h;
-			gmax = gmax > h ? gmax : h;
-			h -= o.q + o.e; if (h < 0) h = 0;
-			e -= o.e; e = e > h ? e : h; E[j + 1] = e;
-			f -= o.e; f = f > h ? f : h;
-		}
-	}
-	return gmax;
 }
 
 // one thread per task of this round; gap fills only
@@ -103,10 +79,20 @@ __global__ void k_ztest_screen(AlignCtx c, DpTask *__restrict__ tasks, int64_t n
 }
 
 // One thread per task, walked as a flat event loop -- every iteration consumes exactly one event (a base of an M run or a
-// whole gap run) -- over the tasks k_ztest_screen listed (`order`, `n_order`), so the
-// lanes do not diverge over nested per-run loops.
+// whole gap run) -- over the tasks k_ztest_screen listed (`order`, `n_order`), so the lanes do not diverge over nested
+// per-run loops.  Tasks that need the inversion test are handed to k_ztest_ll through `cand`; the others are finished here.
+MB_D void mb_ztest_finish(DpTask &T, int code, const mb_opt_t &opt, int32_t *pass2_list, int32_t *n_pass2, int32_t ti)
+{
+	T.zdrop_code = code;
+	if (code) {
+		T.flag = 0; // second pass: exact max, real Z-drop
+		T.zdrop = code == 2 ? opt.zdrop_inv : opt.zdrop;
+		pass2_list[atomicAdd(n_pass2, 1)] = ti;
+	}
+}
+
 __global__ void k_ztest(AlignCtx c, DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const int32_t *__restrict__ n_order, int64_t n_tasks, const uint32_t *__restrict__ cigar_pool,
-                        int32_t *__restrict__ pass2_list, int32_t *__restrict__ n_pass2, int *__restrict__ inv_pool, int32_t *__restrict__ inv_ctr, int *__restrict__ err)
+                        int32_t *__restrict__ pass2_list, int32_t *__restrict__ n_pass2, ZCand *__restrict__ cand, int32_t *__restrict__ n_cand)
 {
 	int64_t ti = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (ti >= n_tasks || (n_order && ti >= *n_order)) return;
@@ -142,23 +128,49 @@ __global__ void k_ztest(AlignCtx c, DpTask *__restrict__ tasks, const int32_t *_
 		}
 		mb_update_max_zdrop(score, ev_i, ev_j, &mx, &max_i, &max_j, gap_e, &max_zdrop, pos);
 	}
-	int code = 0;
 	const int q_len = pos[1][1] - pos[0][1], t_len = pos[1][0] - pos[0][0];
 	if (max_zdrop > opt.zdrop_inv && q_len < opt.max_gap && t_len < opt.max_gap) {
-		int slot = atomicAdd(inv_ctr, 1);
-		if (slot >= INV_SLOTS || q_len + 1 > INV_STRIDE / 2) { *err = 3; }
-		else {
-			int *H = inv_pool + (size_t)slot * INV_STRIDE, *E = H + INV_STRIDE / 2;
-			int sc = q_len > 0 && t_len > 0 ? mb_ll_score(qv, pos[1][1], q_len, tv, pos[0][0], t_len, opt, H, E) : 0;
-			if (sc >= opt.min_chain_score * opt.a && sc >= opt.min_dp_max) code = 2;
+		if (q_len > 0 && t_len > 0) {
+			ZCand z; z.task = (int32_t)ti, z.q_end = pos[1][1], z.q_len = q_len, z.t_st = pos[0][0], z.t_len = t_len, z.max_zdrop = max_zdrop;
+			cand[atomicAdd(n_cand, 1)] = z;
+			return;
 		}
+		// an empty side: upstream's local alignment scores 0 there (0 >= the thresholds only for degenerate options)
+		if (0 >= opt.min_chain_score * opt.a && 0 >= opt.min_dp_max) { mb_ztest_finish(T, 2, opt, pass2_list, n_pass2, (int32_t)ti); return; }
 	}
-	if (code == 0) code = max_zdrop > opt.zdrop ? 1 : 0;
-	T.zdrop_code = code;
-	if (code) {
-		T.flag = 0; // second pass: exact max, real Z-drop
-		T.zdrop = code == 2 ? opt.zdrop_inv : opt.zdrop;
-		pass2_list[atomicAdd(n_pass2, 1)] = (int32_t)ti;
+	mb_ztest_finish(T, max_zdrop > opt.zdrop ? 1 : 0, opt, pass2_list, n_pass2, (int32_t)ti);
+}
+
+// mm_test_zdrop's inversion test for the candidates of k_ztest: local alignment (ll.cuh) of the target stretch against the
+// reverse complement of the query stretch.  Persistent one-warp CTAs over the candidate list; `scr` = 2*LL_MAX_LEN ints per CTA.
+__global__ void __launch_bounds__(32)
+k_ztest_ll(AlignCtx c, DpTask *__restrict__ tasks, const ZCand *__restrict__ cand, const int32_t *__restrict__ n_cand, int32_t *__restrict__ cursor,
+           int32_t *__restrict__ pass2_list, int32_t *__restrict__ n_pass2, int *__restrict__ scr_pool)
+{
+	const int lane = threadIdx.x;
+	int *scr = scr_pool + (size_t)blockIdx.x * (2 * LL_MAX_LEN);
+	const mb_opt_t &opt = c.opt;
+	const int n = *n_cand;
+	for (;;) {
+		int k = 0;
+		if (lane == 0) k = atomicAdd(cursor, 1);
+		k = __shfl_sync(0xffffffffu, k, 0);
+		if (k >= n) break;
+		const ZCand z = cand[k];
+		DpTask &T = tasks[z.task];
+		QView qv; qv.codes = c.codes; qv.idx0 = T.q_idx0; qv.step = T.q_step; qv.comp = T.q_comp == 1;
+		TView tv; tv.S = c.ix.S; tv.bytes = nullptr; tv.idx0 = T.t_idx0; tv.step = T.t_step; tv.packed = 1;
+		int qe, te;
+		// qseq2[i] = complement of qseq[q_end - 1 - i]
+		const int sc = mb_ll_warp([&](int col) { const int b = qv.at(z.q_end - 1 - col); return b >= 4 ? 4 : 3 - b; },
+		                          [&](int row) { return tv.at(z.t_st + row); }, z.q_len, z.t_len, opt, scr, false, &qe, &te, lane);
+		__syncwarp();
+		if (lane == 0) {
+			int code = (sc >= opt.min_chain_score * opt.a && sc >= opt.min_dp_max) ? 2 : 0;
+			if (code == 0) code = z.max_zdrop > opt.zdrop ? 1 : 0;
+			mb_ztest_finish(T, code, opt, pass2_list, n_pass2, z.task);
+		}
+		__syncwarp();
 	}
 }
 
@@ -398,7 +410,7 @@ k_update_extra(AlignCtx c, ReadArrays ra, const int2 *__restrict__ work, int n_w
 	if (perm) wi = perm[wi];
 	const int read = work[wi].x, slot = work[wi].y;
 	Reg *r = ra.regs + ra.reg_off[read] + slot;
-	if (r->cnt == 0 || !r->has_p) return;
+	if ((r->cnt == 0 && !r->inv) || !r->has_p) return;
 	const mb_opt_t &opt = c.opt;
 	const int64_t roff = c.read_off[read];
 	const int qlen = (int)(c.read_off[read + 1] - roff);
@@ -539,7 +551,8 @@ k_update_extra(AlignCtx c, ReadArrays ra, const int2 *__restrict__ work, int n_w
 // one thread per region of this round: the part of mm_align1 after each mm_align_pair
 __global__ void k_stitch(AlignCtx c, ReadArrays ra, const int2 *__restrict__ work, int n_work, const RegPlan *__restrict__ plans,
                          DpTask *__restrict__ tasks, uint32_t *__restrict__ cigar_pool,
-                         int2 *__restrict__ next_work, int32_t *__restrict__ n_next, int *__restrict__ err, const int32_t *__restrict__ perm)
+                         int2 *__restrict__ next_work, int32_t *__restrict__ n_next, int *__restrict__ err, const int32_t *__restrict__ perm,
+                         int4 *__restrict__ inv_list, int32_t *__restrict__ n_inv)
 {
 	// one WARP per region: every lane runs the same (uniform) control flow, lane 0 alone writes region state, and the CIGAR
 	// copies -- the bulk of the work -- are spread over the lanes
@@ -601,12 +614,15 @@ __global__ void k_stitch(AlignCtx c, ReadArrays ra, const int2 *__restrict__ wor
 					const int n_split = pl.as1 + j + 1 - r_as;
 					if (n_split > 0 && n_split < r_cnt) {
 						const int ns = atomicAdd(&ra.n_regs[read], 1);
-						if (ns >= (int)(ra.reg_off[read + 1] - ra.reg_off[read])) { *err = 2; atomicSub(&ra.n_regs[read], 1); }
+						if (ns >= (int)(ra.reg_off[read + 1] - ra.reg_off[read])) { *err = 2; atomicSub(&ra.n_regs[read], 1); } // unreachable: k_round_need sized the pool
 						else {
 							Reg *r2 = regs + ns;
 							mb_split_reg(r, r2, n_split, qlen, a);
 							r2->slot = ns;
-							if (t.zdrop_code == 2) r2->split_inv = 1;
+							if (t.zdrop_code == 2) { // mm_align1_inv is tried between r and r2 once both are aligned (k_inv_*)
+								r2->split_inv = 1, r2->inv_state = 1;
+								inv_list[atomicAdd(n_inv, 1)] = make_int4(read, ns, slot, 0);
+							}
 							r->next_split = ns;
 							next_work[atomicAdd(n_next, 1)] = make_int2(read, ns);
 						}
@@ -643,9 +659,11 @@ struct ReadScratch {
 	Reg *regs_tmp;     // same offsets as regs
 };
 
-// G1a: chain backtrack, one warp per read; writes n_u per read
+// G1a: chain backtrack, one warp per read; writes n_u per read.  Reads with more than 64 chain ends are listed in `big`
+// (their upstream sorts leave the insertion-sort range) and redone by k_chain_bt_big with the exact radix replay.
 __global__ void __launch_bounds__(128)
-k_chain_bt(ReadArrays ra, ReadScratch rs, int n_reads, int min_cnt, int min_sc, int32_t *__restrict__ n_u, int *__restrict__ err, const int32_t *__restrict__ perm)
+k_chain_bt(ReadArrays ra, ReadScratch rs, int n_reads, int min_cnt, int min_sc, int32_t *__restrict__ n_u, const int32_t *__restrict__ perm,
+           int32_t *__restrict__ big, int32_t *__restrict__ n_big)
 {
 	int r = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
 	const int lane = threadIdx.x & 31;
@@ -653,55 +671,133 @@ k_chain_bt(ReadArrays ra, ReadScratch rs, int n_reads, int min_cnt, int min_sc, 
 	if (perm) r = perm[r];
 	const int64_t base = ra.a_roff[r];
 	const int n = (int)(ra.a_roff[r + 1] - base);
-	int e = 0;
 	const int k = mb_chain_backtrack_warp(n, ra.a + base, rs.f + base, rs.p + base, rs.v + base, rs.t + base, rs.b + base, rs.u + base,
-	                                      rs.scr + 3 * base + 3 * r, min_cnt, min_sc, &e, lane);
-	if (lane == 0) { n_u[r] = k; if (e) *err = 1; }
+	                                      rs.scr + 3 * base + 3 * r, min_cnt, min_sc, nullptr, lane);
+	if (lane == 0) {
+		if (k < 0) { n_u[r] = 0; big[atomicAdd(n_big, 1)] = r; }
+		else n_u[r] = k;
+	}
 }
 
-__global__ void k_reg_cap(const int32_t *__restrict__ n_u, const int64_t *__restrict__ a_roff, int n_reads, int32_t *__restrict__ cap)
+#define BIG_SMEM_BYTES (MB_RS_WS_INTS * 4)
+__global__ void __launch_bounds__(32)
+k_chain_bt_big(ReadArrays ra, ReadScratch rs, int min_cnt, int min_sc, int32_t *__restrict__ n_u,
+               const int32_t *__restrict__ big, const int32_t *__restrict__ n_big, int32_t *__restrict__ cursor)
+{
+	extern __shared__ __align__(16) int big_ws[];
+	const int lane = threadIdx.x;
+	const int n = *n_big;
+	for (;;) {
+		int k = 0;
+		if (lane == 0) k = atomicAdd(cursor, 1);
+		k = __shfl_sync(0xffffffffu, k, 0);
+		if (k >= n) break;
+		const int r = big[k];
+		const int64_t base = ra.a_roff[r];
+		const int na = (int)(ra.a_roff[r + 1] - base);
+		const int nu = mb_chain_backtrack_warp(na, ra.a + base, rs.f + base, rs.p + base, rs.v + base, rs.t + base, rs.b + base, rs.u + base,
+		                                       rs.scr + 3 * base + 3 * r, min_cnt, min_sc, big_ws, lane);
+		if (lane == 0) n_u[r] = nu;
+		__syncwarp();
+	}
+}
+
+// region capacity per read: what the chains need now plus room for the first round of Z-drop splits (a region splits at
+// most once per round; k_round_need checks every round and the host grows the pool when a read would run out)
+__global__ void k_reg_cap(const int32_t *__restrict__ n_u, int n_reads, int tight, int32_t *__restrict__ cap)
 {
 	int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= n_reads) return;
-	int n_a = (int)(a_roff[r + 1] - a_roff[r]);
-	int extra = n_a / 3; if (extra > 32) extra = 32;
-	cap[r] = n_u[r] ? n_u[r] + extra + 2 : 0;
+	cap[r] = n_u[r] ? (tight ? n_u[r] : 2 * n_u[r] + 4) : 0;
 }
 
-// G1b: mm_gen_regs + chain_post (mm_set_parent, mm_select_sub, mm_join_long) + mm_squeeze_a of mm_align_skeleton
-__global__ void k_gen_regs(AlignCtx c, ReadArrays ra, ReadScratch rs, int n_reads, const int32_t *__restrict__ n_u, int32_t *__restrict__ n_a_sq,
-                           int2 *__restrict__ work, int32_t *__restrict__ n_work, int *__restrict__ err)
+// ---- region pool bookkeeping ----
+// need[read] += 1 per work item (each region aligned in a round can split off one new region; each inversion candidate can
+// add one inversion hit); flag the batch when a read's pool would overflow
+__global__ void k_round_need(const int2 *__restrict__ work, int n_work, const int4 *__restrict__ inv_list, ReadArrays ra, int32_t *__restrict__ need, int32_t *__restrict__ flag)
 {
-	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_work) return;
+	const int read = work ? work[i].x : inv_list[i].x;
+	const int before = atomicAdd(&need[read], 1);
+	if (ra.n_regs[read] + before + 1 > (int)(ra.reg_off[read + 1] - ra.reg_off[read])) *flag = 1;
+}
+__global__ void k_regs_newcap(ReadArrays ra, const int32_t *__restrict__ need, int n_reads, int32_t *__restrict__ cap)
+{
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= n_reads) return;
+	const int old = (int)(ra.reg_off[r + 1] - ra.reg_off[r]), want = ra.n_regs[r] + 2 * need[r] + 2;
+	cap[r] = need[r] && want > old ? want : old;
+}
+__global__ void k_regs_move(const Reg *__restrict__ src, const int64_t *__restrict__ src_off, Reg *__restrict__ dst, const int64_t *__restrict__ dst_off,
+                            const int32_t *__restrict__ n_regs, int n_reads)
+{
+	const int r = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+	if (r >= n_reads) return;
+	const int n = n_regs[r];
+	const uint32_t *s = reinterpret_cast<const uint32_t*>(src + src_off[r]);
+	uint32_t *d = reinterpret_cast<uint32_t*>(dst + dst_off[r]);
+	const int words = n * (int)(sizeof(Reg) / 4);
+	for (int i = lane; i < words; i += 32) d[i] = s[i];
+}
+
+
+// G1b: mm_gen_regs + chain_post (mm_set_parent, mm_select_sub, mm_join_long) + mm_squeeze_a of mm_align_skeleton, for one read
+MB_D void mb_gen_regs_read(const AlignCtx &c, const ReadArrays &ra, const ReadScratch &rs, int r, int n, int32_t *n_a_sq, int2 *work, int32_t *n_work, int *ws)
+{
 	const mb_opt_t &opt = c.opt;
 	const int64_t base = ra.a_roff[r];
 	const int qlen = (int)(c.read_off[r + 1] - c.read_off[r]);
-	int n = n_u[r];
-	ra.n_regs[r] = 0;
-	n_a_sq[r] = 0;
-	if (n == 0) return;
 	mb128 *a = ra.a + base;
 	Reg *regs = ra.regs + ra.reg_off[r];
 	uint64_t *scr = rs.scr + 3 * base + 3 * r;
 	int *iscr = ra.iscr + base;
-	int e = 0;
 	uint32_t hash = 0;
 	hash ^= mb_wang32((uint32_t)qlen) + mb_wang32((uint32_t)opt.seed);
 	hash = mb_wang32(hash);
-	mb_gen_regs(hash, qlen, n, rs.u + base, a, regs, (mb128*)scr, &e);
-	mb_set_parent(opt.mask_level, n, regs, opt.a * 2 + opt.b, scr, iscr, &e);
+	mb_gen_regs(hash, qlen, n, rs.u + base, a, regs, (mb128*)scr, ws);
+	mb_set_parent(opt.mask_level, n, regs, opt.a * 2 + opt.b, scr, iscr, ws);
 	mb_select_sub(opt.pri_ratio, c.ix.k * 2, opt.best_n, &n, regs, iscr);
-	mb_join_long(&opt, qlen, &n, regs, a, scr, iscr, &e);
+	mb_join_long(&opt, qlen, &n, regs, a, scr, iscr, ws);
 	// mm_align_skeleton: n_a = mm_squeeze_a(...)
-	n_a_sq[r] = mb_squeeze_a(n, regs, a, scr, &e);
-	for (int i = 0; i < n; ++i) regs[i].slot = i, regs[i].next_split = -1, regs[i].aligned = 0;
+	n_a_sq[r] = mb_squeeze_a(n, regs, a, scr, ws);
+	for (int i = 0; i < n; ++i) regs[i].slot = i, regs[i].next_split = -1, regs[i].inv_after = -1, regs[i].inv_state = 0, regs[i].aligned = 0;
 	ra.n_regs[r] = n;
 	if (n > 0) {
 		int w0 = atomicAdd(n_work, n);
 		for (int i = 0; i < n; ++i) work[w0 + i] = make_int2(r, i);
 	}
-	if (e) *err = 1;
+}
+
+// one thread per read; reads with more than 64 chains go to k_gen_regs_big (exact radix replay of upstream's sorts)
+__global__ void k_gen_regs(AlignCtx c, ReadArrays ra, ReadScratch rs, int n_reads, const int32_t *__restrict__ n_u, int32_t *__restrict__ n_a_sq,
+                           int2 *__restrict__ work, int32_t *__restrict__ n_work, int32_t *__restrict__ big, int32_t *__restrict__ n_big)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	const int n = n_u[r];
+	ra.n_regs[r] = 0;
+	n_a_sq[r] = 0;
+	if (n == 0) return;
+	if (n > MB_RS_MIN_SIZE) { big[atomicAdd(n_big, 1)] = r; return; }
+	mb_gen_regs_read(c, ra, rs, r, n, n_a_sq, work, n_work, nullptr);
+}
+
+__global__ void __launch_bounds__(32)
+k_gen_regs_big(AlignCtx c, ReadArrays ra, ReadScratch rs, const int32_t *__restrict__ n_u, int32_t *__restrict__ n_a_sq,
+               int2 *__restrict__ work, int32_t *__restrict__ n_work, const int32_t *__restrict__ big, const int32_t *__restrict__ n_big, int32_t *__restrict__ cursor)
+{
+	extern __shared__ __align__(16) int big_ws[];
+	const int lane = threadIdx.x;
+	const int n = *n_big;
+	for (;;) {
+		int k = 0;
+		if (lane == 0) k = atomicAdd(cursor, 1);
+		k = __shfl_sync(0xffffffffu, k, 0);
+		if (k >= n) break;
+		if (lane == 0) { const int r = big[k]; mb_gen_regs_read(c, ra, rs, r, n_u[r], n_a_sq, work, n_work, big_ws); }
+		__syncwarp();
+	}
 }
 
 // ---- work-list permutation: longest regions first ----
@@ -734,39 +830,196 @@ __global__ void k_work_scatter(const int2 *__restrict__ work, int n, ReadArrays 
 	perm[atomicAdd(&cursor[mb_work_bucket(ra.regs + ra.reg_off[w.x] + w.y)], 1)] = i;
 }
 
-// after the alignment rounds: restore upstream's region order (a split-off region sits right after its source), then
-// mm_filter_regs, mm_hit_sort, mm_set_parent, mm_select_sub, mm_set_sam_pri, mm_set_mapq
-__global__ void k_finish(AlignCtx c, ReadArrays ra, ReadScratch rs, int n_reads, const int32_t *__restrict__ n0_regs, const int32_t *__restrict__ rep_len,
-                         int32_t *__restrict__ n_hits, int32_t *__restrict__ n_hit_cigar, int *__restrict__ err)
+// after the alignment rounds: restore upstream's region order (a split-off region sits right after its source, an inversion
+// hit right after the split_inv region it belongs to), then mm_filter_regs, mm_hit_sort, mm_set_parent, mm_select_sub,
+// mm_set_sam_pri, mm_set_mapq (+ mm_set_inv_mapq), for one read
+MB_D void mb_finish_read(const AlignCtx &c, const ReadArrays &ra, const ReadScratch &rs, int r, int n0, int rep_len, int32_t *n_hits, int32_t *n_hit_cigar, int *ws)
 {
-	int r = blockIdx.x * blockDim.x + threadIdx.x;
-	if (r >= n_reads) return;
 	const mb_opt_t &opt = c.opt;
 	const int64_t base = ra.a_roff[r];
 	const int qlen = (int)(c.read_off[r + 1] - c.read_off[r]);
 	Reg *regs = ra.regs + ra.reg_off[r], *tmp = rs.regs_tmp + ra.reg_off[r];
 	uint64_t *scr = rs.scr + 3 * base + 3 * r;
 	int *iscr = ra.iscr + base;
-	int n_all = ra.n_regs[r], n0 = n0_regs[r], n = 0, e = 0;
-	n_hits[r] = 0, n_hit_cigar[r] = 0;
-	if (n_all == 0) return;
+	int n = 0;
 	for (int i = 0; i < n0; ++i) {
 		int s = i;
-		while (s >= 0) { tmp[n++] = regs[s]; s = regs[s].next_split; }
+		while (s >= 0) {
+			tmp[n++] = regs[s];
+			if (regs[s].inv_after >= 0) tmp[n++] = regs[regs[s].inv_after];
+			s = regs[s].next_split;
+		}
 	}
 	for (int i = 0; i < n; ++i) regs[i] = tmp[i];
 	mb_filter_regs(&opt, qlen, &n, regs);
-	mb_hit_sort(&n, regs, (mb128*)scr, tmp, &e);
-	mb_set_parent(opt.mask_level, n, regs, opt.a * 2 + opt.b, scr, iscr, &e);
+	mb_hit_sort(&n, regs, (mb128*)scr, tmp, ws);
+	mb_set_parent(opt.mask_level, n, regs, opt.a * 2 + opt.b, scr, iscr, ws);
 	mb_select_sub(opt.pri_ratio, c.ix.k * 2, opt.best_n, &n, regs, iscr);
 	mb_set_sam_pri(n, regs);
-	mb_set_mapq(n, regs, opt.min_chain_score, opt.a, rep_len[r]);
+	mb_set_mapq(n, regs, opt.min_chain_score, opt.a, rep_len);
+	mb_set_inv_mapq(n, regs, (mb128*)scr, ws);
 	ra.n_regs[r] = n;
 	n_hits[r] = n;
 	int nc = 0;
 	for (int i = 0; i < n; ++i) nc += regs[i].has_p ? regs[i].n_cigar : 0;
 	n_hit_cigar[r] = nc;
-	if (e) *err = 1;
+}
+
+// scratch note: scr holds 3*(n_a + 1) u64 per read and iscr n_a ints; a read's regions never outnumber its anchors (every
+// region keeps at least one anchor; an inversion hit belongs to a split-off region of >= min_cnt anchors)
+__global__ void k_finish(AlignCtx c, ReadArrays ra, ReadScratch rs, int n_reads, const int32_t *__restrict__ n0_regs, const int32_t *__restrict__ rep_len,
+                         int32_t *__restrict__ n_hits, int32_t *__restrict__ n_hit_cigar, int32_t *__restrict__ big, int32_t *__restrict__ n_big)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	const int n_all = ra.n_regs[r];
+	n_hits[r] = 0, n_hit_cigar[r] = 0;
+	if (n_all == 0) return;
+	if (n_all > MB_RS_MIN_SIZE) { big[atomicAdd(n_big, 1)] = r; return; }
+	mb_finish_read(c, ra, rs, r, n0_regs[r], rep_len[r], n_hits, n_hit_cigar, nullptr);
+}
+
+__global__ void __launch_bounds__(32)
+k_finish_big(AlignCtx c, ReadArrays ra, ReadScratch rs, const int32_t *__restrict__ n0_regs, const int32_t *__restrict__ rep_len,
+             int32_t *__restrict__ n_hits, int32_t *__restrict__ n_hit_cigar, const int32_t *__restrict__ big, const int32_t *__restrict__ n_big, int32_t *__restrict__ cursor)
+{
+	extern __shared__ __align__(16) int big_ws[];
+	const int lane = threadIdx.x;
+	const int n = *n_big;
+	for (;;) {
+		int k = 0;
+		if (lane == 0) k = atomicAdd(cursor, 1);
+		k = __shfl_sync(0xffffffffu, k, 0);
+		if (k >= n) break;
+		if (lane == 0) { const int r = big[k]; mb_finish_read(c, ra, rs, r, n0_regs[r], rep_len[r], n_hits, n_hit_cigar, big_ws); }
+		__syncwarp();
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// mm_align1_inv (align.c): after the rounds, for every region s that a Z-drop split flagged as a potential inversion
+// (split_inv), align the query stretch between the region before it and s -- read off the OPPOSITE strand -- to the
+// reference stretch between them.  Upstream does this inside the mm_align_skeleton loop right after s has been aligned,
+// with regs[i-1] as the left neighbour: that is the source region s was split from, unless the source's own inversion hit
+// was inserted in between (then the test `r1->split & 1` fails), so candidates are decided in chain order:
+//   k_inv_plan  (thread / candidate)  defer if the source's own candidate is undecided; upstream's eligibility tests
+//   k_inv_ll    (warp / candidate)    local alignment of the reversed stretches -> start of the inverted block, DP task
+//   DP          (k_dp / k_dp_ext)     extension alignment from there
+//   k_inv_finish(thread / DP task)    the inversion hit as a new region, linked behind s; mm_update_extra follows
+//   k_inv_close (thread / candidate)  mark the candidates of this pass decided
+// ------------------------------------------------------------------------------------------------
+struct InvTask { int32_t read, slot_s, slot_src, ql, tl; };
+
+__global__ void k_inv_plan(AlignCtx c, ReadArrays ra, const int4 *__restrict__ list, int n, int4 *__restrict__ next_list, int32_t *__restrict__ n_next,
+                           int4 *__restrict__ proc_list, int32_t *__restrict__ n_proc, InvTask *__restrict__ ll, int32_t *__restrict__ n_ll)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const int4 e = list[i];
+	const mb_opt_t &opt = c.opt;
+	const Reg *regs = ra.regs + ra.reg_off[e.x];
+	const Reg *r2 = regs + e.y, *r1 = regs + e.z;
+	if (r1->split_inv && r1->inv_state == 1) { next_list[atomicAdd(n_next, 1)] = e; return; } // the source's own inversion comes first
+	proc_list[atomicAdd(n_proc, 1)] = e;
+	if (r1->inv_after >= 0) return;   // the region before s is the source's inversion hit: its split bits are 0
+	if (!(r1->split & 1) || !(r2->split & 2)) return;
+	if (r1->id != r1->parent && r1->parent != MB_PARENT_TMP_PRI) return;
+	if (r2->id != r2->parent && r2->parent != MB_PARENT_TMP_PRI) return;
+	if (r1->rid != r2->rid || r1->rev != r2->rev) return;
+	const int ql = r1->rev ? r1->qs - r2->qe : r2->qs - r1->qe, tl = r2->rs - r1->re;
+	if (ql < opt.min_chain_score || ql > opt.max_gap) return;
+	if (tl < opt.min_chain_score || tl > opt.max_gap) return;
+	InvTask t; t.read = e.x, t.slot_s = e.y, t.slot_src = e.z, t.ql = ql, t.tl = tl;
+	ll[atomicAdd(n_ll, 1)] = t;
+}
+
+__global__ void __launch_bounds__(32)
+k_inv_ll(AlignCtx c, ReadArrays ra, const InvTask *__restrict__ ll, const int32_t *__restrict__ n_ll, int32_t *__restrict__ cursor, int *__restrict__ scr_pool,
+         DpTask *__restrict__ tasks, InvTask *__restrict__ task_inv, int32_t *__restrict__ cig_cap, int32_t *__restrict__ n_dp)
+{
+	const int lane = threadIdx.x;
+	int *scr = scr_pool + (size_t)blockIdx.x * (2 * LL_MAX_LEN);
+	const mb_opt_t &opt = c.opt;
+	const int n = *n_ll;
+	for (;;) {
+		int k = 0;
+		if (lane == 0) k = atomicAdd(cursor, 1);
+		k = __shfl_sync(0xffffffffu, k, 0);
+		if (k >= n) break;
+		const InvTask it = ll[k];
+		const Reg *regs = ra.regs + ra.reg_off[it.read];
+		const Reg *r2 = regs + it.slot_s, *r1 = regs + it.slot_src;
+		const int64_t roff = c.read_off[it.read];
+		const int qlen = (int)(c.read_off[it.read + 1] - roff);
+		const int ql = it.ql, tl = it.tl;
+		const int strand = r1->rev ? 0 : 1;                       // the inversion hit lies on the other strand
+		const int p0 = r1->rev ? r2->qe : qlen - r2->qs;          // start of the stretch in that strand's coordinates
+		const int64_t t0 = (int64_t)c.ix.seq_off[r1->rid] + r1->re;
+		const uint8_t *codes = c.codes; const uint32_t *S = c.ix.S;
+		auto qat = [&](int p) -> int { // base p of the read as seen on `strand`
+			if (!strand) return codes[roff + p];
+			const int b = codes[roff + qlen - 1 - p];
+			return b < 4 ? 3 - b : 4;
+		};
+		auto tat = [&](int p) -> int { const int64_t g = t0 + p; return (int)(S[g >> 3] >> ((g & 7) << 2) & 0xf); };
+		int qe, te;
+		// both stretches reversed, as upstream does before ksw_ll_i16
+		const int score = (ql > LL_MAX_LEN - 8 || tl > LL_MAX_LEN - 8) ? -1 :
+			mb_ll_warp([&](int col) { return qat(p0 + ql - 1 - col); }, [&](int row) { return tat(tl - 1 - row); }, ql, tl, opt, scr, true, &qe, &te, lane);
+		__syncwarp();
+		if (lane == 0 && score >= opt.min_dp_max) {
+			const int q_off = ql - (qe + 1), t_off = tl - (te + 1);  // q_off can be -1..-7 (padding columns, see ll.cuh)
+			DpTask t; memset(&t, 0, sizeof(t));
+			t.reg = -1, t.kind = 2;
+			t.qlen = ql - q_off, t.tlen = tl - t_off, t.w = (int)(opt.bw * 1.5), t.zdrop = opt.zdrop, t.end_bonus = -1, t.flag = MB_EZ_EXTZ_ONLY;
+			const int ps = p0 + q_off;
+			if (!strand) t.q_idx0 = roff + ps, t.q_step = 1, t.q_comp = 0;
+			else t.q_idx0 = roff + qlen - 1 - ps, t.q_step = -1, t.q_comp = 1;
+			t.t_idx0 = t0 + t_off, t.t_step = 1, t.t_packed = 1;
+			t.anchor_i = -1;
+			t.qs = q_off, t.rs = t_off;    // kept for k_inv_finish
+			t.skip = (opt.max_sw_mat > 0 && (int64_t)t.tlen * t.qlen > opt.max_sw_mat) ? 1 : 0;
+			const int kk = atomicAdd(n_dp, 1);
+			tasks[kk] = t; task_inv[kk] = it; cig_cap[kk] = t.qlen + t.tlen + 1;
+		}
+		__syncwarp();
+	}
+}
+
+__global__ void k_inv_finish(AlignCtx c, ReadArrays ra, const DpTask *__restrict__ tasks, const InvTask *__restrict__ task_inv, int n_dp,
+                             int2 *__restrict__ inv_work, RegPlan *__restrict__ inv_plans, int32_t *__restrict__ n_ok, int *__restrict__ err)
+{
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n_dp) return;
+	const DpTask &T = tasks[k];
+	if (T.n_cigar == 0) return; // upstream: "should never be here"
+	const InvTask it = task_inv[k];
+	Reg *regs = ra.regs + ra.reg_off[it.read];
+	Reg *r2 = regs + it.slot_s; const Reg *r1 = regs + it.slot_src;
+	const int ns = atomicAdd(&ra.n_regs[it.read], 1);
+	if (ns >= (int)(ra.reg_off[it.read + 1] - ra.reg_off[it.read])) { *err = 2; atomicSub(&ra.n_regs[it.read], 1); return; } // unreachable: pool sized before the pass
+	Reg v; memset(&v, 0, sizeof(v));
+	const int q_off = T.qs, t_off = T.rs;
+	v.id = -1, v.parent = MB_PARENT_UNSET, v.inv = 1, v.rev = !r1->rev, v.rid = r1->rid;
+	if (v.rev == 0) { v.qs = r2->qe + q_off; v.qe = v.qs + T.max_q + 1; }
+	else { v.qe = r2->qs - q_off; v.qs = v.qe - (T.max_q + 1); }
+	v.rs = r1->re + t_off, v.re = v.rs + T.max_t + 1;
+	v.has_p = 1, v.n_cigar = T.n_cigar, v.cigar_off = T.cigar_off, v.dp_score = T.max;
+	v.next_split = -1, v.inv_after = -1, v.slot = ns, v.aligned = 1;
+	regs[ns] = v;
+	r2->inv_after = ns;
+	const int w = atomicAdd(n_ok, 1);
+	inv_work[w] = make_int2(it.read, ns);
+	RegPlan pl; memset(&pl, 0, sizeof(pl));
+	pl.n_tasks = 1, pl.task0 = k;
+	inv_plans[w] = pl;
+}
+
+__global__ void k_inv_close(ReadArrays ra, const int4 *__restrict__ proc_list, const int32_t *__restrict__ n_proc)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= *n_proc) return;
+	ra.regs[ra.reg_off[proc_list[i].x] + proc_list[i].y].inv_state = 2;
 }
 
 #define HIT_NF 23

@@ -133,85 +133,30 @@ k_chain_dp(const mb128 *__restrict__ a, const int64_t *__restrict__ a_roff, int 
 	if (lane == 0 && cells_out && cells) atomicAdd(cells_out, cells);
 }
 
-// ---- exact small sorts used by the per-read glue (ranges <= 64 are upstream's insertion sort; larger ranges have a
-// unique result unless keys tie, which is reported through *err) ----
+// ---- exact sorts used by the per-read glue ----
+// Upstream sorts these small arrays with radix_sort_128x / radix_sort_64, which is an insertion sort up to 64 elements and an
+// UNSTABLE in-place MSD radix sort beyond; where keys can tie, the permutation of equal keys is part of the result.  Reads
+// with more than 64 chains / regions are therefore routed to the "big" variants of the per-read kernels (one-warp CTAs that
+// own MB_RS_WS_INTS ints of shared-memory scratch, `ws`), which replay upstream's radix passes exactly (radix_emul.cuh);
+// everything else never leaves the insertion-sort range and passes ws = nullptr.
 template <typename T, typename K>
-MB_HD void mb_sort_exact(T *a, int n, K key, int *err)
+MB_HD void mb_sort_exact(T *a, int n, K key, int *ws)
 {
-	mb_insertsort(a, a + n, key);
-	if (n > MB_RS_MIN_SIZE)
-		for (int i = 1; i < n; ++i)
-			if (key(a[i]) == key(a[i - 1])) { *err = 1; break; }
+	if (n <= MB_RS_MIN_SIZE || ws == nullptr) mb_insertsort(a, a + n, key);
+	else mb_radix_sort_emul(a, n, ws, key);
 }
 
 // chain.c mm_chain_dp(), part 2: chain ends, greedy backtrack, emit chains ordered by first-anchor x.
-// One thread per read.  In: a (sorted anchors), f, p, v; scratch: t (int32[n]), b (mb128[n]), u (u64[n]), scr (u64[3n+3]).
+// In: a (sorted anchors), f, p, v; scratch: t (int32[n]), b (mb128[n]), u (u64[n]), scr (u64[3n+3]).
 // Out: a overwritten with chained anchors (chain by chain), u[0..n_u) = score<<32|cnt; returns n_u.
-MB_HD int mb_chain_backtrack(int n, mb128 *a, const int32_t *f, const int32_t *p, int32_t *v, int32_t *t, mb128 *b, uint64_t *u, uint64_t *scr,
-                             int min_cnt, int min_sc, int *err)
-{
-	int i, j, k, n_u, n_v;
-	if (n == 0) return 0;
-	for (i = 0; i < n; ++i) t[i] = 0;
-	for (i = 0; i < n; ++i)
-		if (p[i] >= 0) t[p[i]] = 1;
-	for (i = n_u = 0; i < n; ++i)
-		if (t[i] == 0 && v[i] >= min_sc) {
-			j = i;
-			while (j >= 0 && f[j] < v[j]) j = p[j];
-			if (j < 0) j = i;
-			u[n_u++] = (uint64_t)(uint32_t)f[j] << 32 | (uint32_t)j;
-		}
-	if (n_u == 0) return 0;
-	mb_sort_exact(u, n_u, KeyU64(), err); // keys are distinct (j is unique)
-	for (i = 0; i < n_u >> 1; ++i) { uint64_t tt = u[i]; u[i] = u[n_u - i - 1], u[n_u - i - 1] = tt; }
-	for (i = 0; i < n; ++i) t[i] = 0;
-	for (i = n_v = k = 0; i < n_u; ++i) {
-		int n_v0 = n_v, k0 = k;
-		j = (int32_t)u[i];
-		do {
-			v[n_v++] = j;
-			t[j] = 1;
-			j = p[j];
-		} while (j >= 0 && t[j] == 0);
-		if (j < 0) {
-			if (n_v - n_v0 >= min_cnt) u[k++] = u[i] >> 32 << 32 | (uint32_t)(n_v - n_v0);
-		} else if ((int32_t)(u[i] >> 32) - f[j] >= min_sc) {
-			if (n_v - n_v0 >= min_cnt) u[k++] = (uint64_t)((u[i] >> 32) - (uint64_t)(int64_t)f[j]) << 32 | (uint32_t)(n_v - n_v0);
-		}
-		if (k0 == k) n_v = n_v0;
-	}
-	n_u = k;
-	for (i = 0, k = 0; i < n_u; ++i) {
-		int k0 = k, ni = (int32_t)u[i];
-		for (j = 0; j < ni; ++j)
-			b[k] = a[v[k0 + (ni - j - 1)]], ++k;
-	}
-	// sort chains by first-anchor x
-	mb128 *w = (mb128*)scr;
-	uint64_t *u2 = scr + 2 * (size_t)n_u;
-	for (i = k = 0; i < n_u; ++i) {
-		w[i].x = b[k].x, w[i].y = (uint64_t)k << 32 | (uint32_t)i;
-		k += (int32_t)u[i];
-	}
-	mb_sort_exact(w, n_u, KeyX(), err);
-	for (i = k = 0; i < n_u; ++i) {
-		int jj = (int32_t)w[i].y, nn = (int32_t)u[jj];
-		u2[i] = u[jj];
-		const mb128 *src = b + (w[i].y >> 32);
-		for (j = 0; j < nn; ++j) a[k + j] = src[j];
-		k += nn;
-	}
-	for (i = 0; i < n_u; ++i) u[i] = u2[i];
-	return n_u;
-}
-
-// Warp-cooperative form of mb_chain_backtrack: the array sweeps (marking, chain-end collection, anchor copies) are spread over
+// Warp-cooperative: the array sweeps (marking, chain-end collection, anchor copies) are spread over
 // the lanes, the two inherently sequential parts (greedy backtrack over the score-sorted chain ends, the small sorts) run on
 // lane 0.  One warp per read also keeps a long read from stalling 31 neighbours in lock-step.  Same outputs as the scalar
 // routine: the chain ends are collected in arbitrary order, but their keys are distinct, so the sort that follows is unique.
+// Returns -1 (nothing modified that a re-run would not recompute) when the read has more than 64 chain ends and no `ws`:
+// the caller then hands the read to the big variant of its kernel.
 MB_D int mb_chain_backtrack_warp(int n, mb128 *a, const int32_t *f, const int32_t *p, int32_t *v, int32_t *t, mb128 *b, uint64_t *u, uint64_t *scr,
-                                 int min_cnt, int min_sc, int *err, int lane)
+                                 int min_cnt, int min_sc, int *ws, int lane)
 {
 	const unsigned FULL = 0xffffffffu;
 	if (n == 0) return 0;
@@ -235,8 +180,9 @@ MB_D int mb_chain_backtrack_warp(int n, mb128 *a, const int32_t *f, const int32_
 	}
 	__syncwarp();
 	if (n_u == 0) return 0;
+	if (n_u > MB_RS_MIN_SIZE && ws == nullptr) return -1;
 	if (lane == 0) {
-		mb_sort_exact(u, n_u, KeyU64(), err);
+		mb_sort_exact(u, n_u, KeyU64(), ws);
 		for (int i = 0; i < n_u >> 1; ++i) { uint64_t tt = u[i]; u[i] = u[n_u - i - 1], u[n_u - i - 1] = tt; }
 	}
 	for (int i = lane; i < n; i += 32) t[i] = 0;
@@ -282,7 +228,7 @@ MB_D int mb_chain_backtrack_warp(int n, mb128 *a, const int32_t *f, const int32_
 			w[i].x = b[k].x, w[i].y = (uint64_t)k << 32 | (uint32_t)i;
 			k += (int32_t)u[i];
 		}
-		mb_sort_exact(w, n_u, KeyX(), err);
+		mb_sort_exact(w, n_u, KeyX(), ws);
 		for (int i = 0; i < n_u; ++i) u2[i] = u[(int32_t)w[i].y];
 	}
 	__syncwarp();

@@ -72,6 +72,17 @@ struct Arena {
 		}
 		used = 0; batch_total = 0;
 	}
+	// size the (empty) arena for a known demand up front, instead of doubling slab by slab (the retired slabs of a doubling
+	// sequence add up to as much again as the final one)
+	void reserve(size_t want) {
+		if (used != 0 || !retired.empty() || want <= cap) return;
+		want = (want + 255) & ~(size_t)255;
+		if (base) cudaFree(base);
+		base = nullptr; cap = 0;
+		char *nb = nullptr;
+		if (cudaMalloc(&nb, want) == cudaSuccess) base = nb, cap = want;
+		else cudaGetLastError(); // fall back to growing on demand
+	}
 	void release() {
 		reset();
 		if (base) cudaFree(base);

@@ -23,6 +23,8 @@ struct Reg {
 	int64_t cigar_off;     // into the batch cigar pool
 	int32_t next_split;    // index (within the read's reg array) of the region split off this one, or -1
 	int32_t slot;          // this region's own index in the read's reg array
+	int32_t inv_after;     // index of the inversion hit (mm_align1_inv) that upstream inserts right after this region, or -1
+	int32_t inv_state;     // split_inv regions: 1 while their inversion alignment is pending, 2 once it has been decided
 };
 
 MB_HD uint64_t mb_hash64_full(uint64_t key)
@@ -76,7 +78,7 @@ MB_HD void mb_reg_set_coor(Reg *r, int32_t qlen, const mb128 *a)
 }
 
 // mm_gen_regs: z scratch = mb128[n_u]
-MB_HD void mb_gen_regs(uint32_t hash, int qlen, int n_u, const uint64_t *u, const mb128 *a, Reg *r, mb128 *z, int *err)
+MB_HD void mb_gen_regs(uint32_t hash, int qlen, int n_u, const uint64_t *u, const mb128 *a, Reg *r, mb128 *z, int *ws)
 {
 	int i, k;
 	for (i = k = 0; i < n_u; ++i) {
@@ -85,7 +87,7 @@ MB_HD void mb_gen_regs(uint32_t hash, int qlen, int n_u, const uint64_t *u, cons
 		z[i].y = (uint64_t)k << 32 | (uint32_t)(int32_t)u[i];
 		k += (int32_t)u[i];
 	}
-	mb_sort_exact(z, n_u, KeyX(), err);
+	mb_sort_exact(z, n_u, KeyX(), ws);
 	for (i = 0; i < n_u >> 1; ++i) { mb128 tmp = z[i]; z[i] = z[n_u - 1 - i], z[n_u - 1 - i] = tmp; }
 	for (i = 0; i < n_u; ++i) {
 		Reg *ri = &r[i];
@@ -97,6 +99,7 @@ MB_HD void mb_gen_regs(uint32_t hash, int qlen, int n_u, const uint64_t *u, cons
 		ri->cnt = (int32_t)z[i].y;
 		ri->as = (int32_t)(z[i].y >> 32);
 		ri->next_split = -1;
+		ri->inv_after = -1;
 		ri->slot = i;
 		mb_reg_set_coor(ri, qlen, a);
 	}
@@ -131,7 +134,7 @@ MB_HD void mb_sync_regs(int n_regs, Reg *regs, int *tmp)
 }
 
 // cov scratch: u64[n]; w scratch: int[n]
-MB_HD void mb_set_parent(float mask_level, int n, Reg *r, int sub_diff, uint64_t *cov, int *w, int *err)
+MB_HD void mb_set_parent(float mask_level, int n, Reg *r, int sub_diff, uint64_t *cov, int *w, int *ws)
 {
 	int i, j, k;
 	if (n <= 0) return;
@@ -153,7 +156,7 @@ MB_HD void mb_set_parent(float mask_level, int n, Reg *r, int sub_diff, uint64_t
 			is_new = true;
 		} else {
 			int x = si;
-			mb_insertsort(cov, cov + n_cov, KeyU64()); // equal keys are identical values: any order gives the same array
+			mb_sort_exact(cov, n_cov, KeyU64(), ws); // equal keys are identical values: any order gives the same array
 			for (int jj = 0; jj < n_cov; ++jj) {
 				if ((int)(cov[jj] >> 32) > x) uncov_len += (int)(cov[jj] >> 32) - x;
 				x = (int32_t)cov[jj] > x ? (int32_t)cov[jj] : x;
@@ -189,7 +192,6 @@ MB_HD void mb_set_parent(float mask_level, int n, Reg *r, int sub_diff, uint64_t
 		}
 		if (is_new) w[k++] = i, ri->parent = i, ri->n_sub = 0;
 	}
-	(void)err;
 }
 
 // tmp scratch: int[n+2]
@@ -245,7 +247,7 @@ MB_HD void mb_filter_regs(const mb_opt_t *opt, int qlen, int *n_regs, Reg *regs)
 }
 
 // aux scratch: mb128[n]; t scratch: Reg[n]
-MB_HD void mb_hit_sort(int *n_regs, Reg *r, mb128 *aux, Reg *t, int *err)
+MB_HD void mb_hit_sort(int *n_regs, Reg *r, mb128 *aux, Reg *t, int *ws)
 {
 	int i, n_aux, n = *n_regs;
 	if (n <= 1) return;
@@ -256,18 +258,18 @@ MB_HD void mb_hit_sort(int *n_regs, Reg *r, mb128 *aux, Reg *t, int *err)
 			aux[n_aux++].y = (uint64_t)i;
 		}
 	}
-	mb_sort_exact(aux, n_aux, KeyX(), err);
+	mb_sort_exact(aux, n_aux, KeyX(), ws);
 	for (i = n_aux - 1; i >= 0; --i) t[n_aux - 1 - i] = r[aux[i].y];
 	for (i = 0; i < n_aux; ++i) r[i] = t[i];
 	*n_regs = n_aux;
 }
 
 // aux scratch: u64[n_regs]
-MB_HD int mb_squeeze_a(int n_regs, Reg *regs, mb128 *a, uint64_t *aux, int *err)
+MB_HD int mb_squeeze_a(int n_regs, Reg *regs, mb128 *a, uint64_t *aux, int *ws)
 {
 	int i, as = 0;
 	for (i = 0; i < n_regs; ++i) aux[i] = (uint64_t)(uint32_t)regs[i].as << 32 | (uint32_t)i;
-	mb_sort_exact(aux, n_regs, KeyU64(), err);
+	mb_sort_exact(aux, n_regs, KeyU64(), ws);
 	for (i = 0; i < n_regs; ++i) {
 		Reg *r = &regs[(int32_t)aux[i]];
 		if (r->as != as) {
@@ -280,15 +282,15 @@ MB_HD int mb_squeeze_a(int n_regs, Reg *regs, mb128 *a, uint64_t *aux, int *err)
 }
 
 // aux scratch: u64[n_regs]; tmp: int[n_regs+2]
-MB_HD void mb_join_long(const mb_opt_t *opt, int qlen, int *n_regs_, Reg *regs, mb128 *a, uint64_t *aux, int *tmp, int *err)
+MB_HD void mb_join_long(const mb_opt_t *opt, int qlen, int *n_regs_, Reg *regs, mb128 *a, uint64_t *aux, int *tmp, int *ws)
 {
 	int i, n_aux, n_regs = *n_regs_, n_drop = 0;
 	if (n_regs < 2) return;
-	mb_squeeze_a(n_regs, regs, a, aux, err);
+	mb_squeeze_a(n_regs, regs, a, aux, ws);
 	for (i = n_aux = 0; i < n_regs; ++i)
 		if (regs[i].parent == i || regs[i].parent < 0)
 			aux[n_aux++] = (uint64_t)(uint32_t)regs[i].as << 32 | (uint32_t)i;
-	mb_sort_exact(aux, n_aux, KeyU64(), err);
+	mb_sort_exact(aux, n_aux, KeyU64(), ws);
 	for (i = n_aux - 1; i >= 1; --i) {
 		Reg *r0 = &regs[(int32_t)aux[i - 1]], *r1 = &regs[(int32_t)aux[i]];
 		const mb128 *a0e, *a1s;
@@ -341,7 +343,7 @@ MB_HD bool mb_split_reg(Reg *r, Reg *r2, int n, int qlen, const mb128 *a)
 	r2->id = -1;
 	r2->sam_pri = 0;
 	r2->has_p = 0; r2->n_cigar = 0; r2->dp_score = r2->dp_max = r2->dp_max2 = r2->n_ambi = 0; r2->aligned = 0; r2->next_split = -1;
-	r2->split_inv = 0;
+	r2->split_inv = 0; r2->inv_after = -1; r2->inv_state = 0;
 	r2->cnt = r->cnt - n;
 #ifdef __CUDA_ARCH__
 	r2->score = (int32_t)__dadd_rn((double)__fmul_rn((float)r->score, __fdiv_rn((float)r2->cnt, (float)r->cnt)), .499);
@@ -471,4 +473,26 @@ MB_HD void mb_set_mapq(int n_regs, Reg *regs, int min_chain_sc, int match_sc, in
 	#undef FD
 	#undef FS
 	#undef FA
+}
+
+// hit.c mm_set_inv_mapq(): an inversion hit takes the smaller MAPQ of its two neighbours in reference order.
+// aux scratch: mb128[n_regs]
+MB_HD void mb_set_inv_mapq(int n_regs, Reg *regs, mb128 *aux, int *ws)
+{
+	int i, n_aux;
+	if (n_regs < 3) return;
+	for (i = 0; i < n_regs; ++i)
+		if (regs[i].inv) break;
+	if (i == n_regs) return;
+	for (i = n_aux = 0; i < n_regs; ++i)
+		if (regs[i].parent == i || regs[i].parent < 0)
+			aux[n_aux].y = (uint64_t)i, aux[n_aux++].x = (uint64_t)(uint32_t)regs[i].rid << 32 | (uint32_t)regs[i].rs;
+	mb_sort_exact(aux, n_aux, KeyX(), ws);
+	for (i = 1; i < n_aux - 1; ++i) {
+		Reg *inv = &regs[aux[i].y];
+		if (inv->inv) {
+			const Reg *l = &regs[aux[i - 1].y], *r = &regs[aux[i + 1].y];
+			inv->mapq = l->mapq < r->mapq ? l->mapq : r->mapq;
+		}
+	}
 }

@@ -105,7 +105,14 @@ struct ThreadCtx {
 		}
 	}
 };
-static thread_local std::map<int, ThreadCtx*> t_ctx;
+// One context per (calling thread, device), destroyed when the thread exits: monica's multi_threaded_aligner creates a fresh
+// ThreadPool per call (aligner.py:89), so contexts that outlived their thread would pile up arenas of several GB each.
+struct ThreadCtxMap {
+	std::map<int, ThreadCtx*> m;
+	~ThreadCtxMap() { for (auto &kv : m) delete kv.second; }
+};
+static thread_local ThreadCtxMap t_ctx_holder;
+#define t_ctx (t_ctx_holder.m)
 
 static void ensure_device(int device)
 {
@@ -270,6 +277,9 @@ static mb_index *index_build_impl(int device, int n_seq, const char *const *name
 	}
 	ix->sum_len = sum;
 	c.ar.reset();
+	// ASCII + codes + 4-bit sequence (2.5 B/base), the sketch's staging rows (5 B/base), ~0.19 minimizers/base x (2 x 16 B records
+	// + 32 B of grouping arrays), scans: ~20 B/base
+	if (sum > ((uint64_t)64 << 20)) c.ar.reserve((size_t)sum * 20 + ((size_t)256 << 20));
 	cudaStream_t st = c.st;
 	// upload contigs as one "read batch": the sketch kernel stores the sequence index in y>>32, which is mm_idx's rid
 	std::vector<int64_t> off(n_seq + 1, 0);
@@ -287,6 +297,7 @@ static mb_index *index_build_impl(int device, int n_seq, const char *const *name
 	if (sum) k_pack4<<<(unsigned)cdiv(cdiv((int64_t)sum, 8), 256), 256, 0, st>>>(d_codes, d_S, (int64_t)sum);
 	index_finish_device(ix.get(), c, so.mini, so.n_mini, d_S, k);
 	c.ar.reset();
+	if (c.ar.cap > ((size_t)8 << 30)) c.ar.release(); // a one-off build of a large index: hand the scratch back
 	return ix.release();
 }
 
@@ -316,29 +327,37 @@ extern "C" int mb_index_build_fasta(int device, const char *path, int w, int k, 
 	API_BEGIN
 	gzFile fp = gzopen(path, "rb");
 	if (!fp) throw mb_error(MB_ERR_IO, std::string("cannot open ") + path);
+	gzbuffer(fp, 1 << 20);
 	std::vector<std::string> names; std::vector<std::string> seqs;
-	std::vector<char> buf(1 << 20);
-	std::string line;
-	bool in_name = false;
+	// whole lines are appended with memchr / append (no per-character work); a line cut by the read buffer is carried over
+	std::vector<char> buf(1 << 24);
+	std::string carry;
 	int n;
-	auto flush_line = [&](const std::string &l) {
-		if (l.empty()) return;
+	auto take_line = [&](const char *l, size_t len) {
+		while (len && (l[len - 1] == '\r' || l[len - 1] == '\n')) --len;
+		if (len == 0) return;
 		if (l[0] == '>') {
-			size_t e = l.find_first_of(" \t", 1);
-			names.push_back(l.substr(1, e == std::string::npos ? std::string::npos : e - 1));
+			size_t e = 1;
+			while (e < len && l[e] != ' ' && l[e] != '\t') ++e;
+			names.emplace_back(l + 1, e - 1);
 			seqs.emplace_back();
-		} else if (!seqs.empty()) seqs.back() += l;
+			seqs.back().reserve(seqs.size() > 1 ? seqs[seqs.size() - 2].size() + 1024 : (size_t)1 << 20);
+		} else if (!seqs.empty()) seqs.back().append(l, len);
 	};
-	(void)in_name;
 	while ((n = gzread(fp, buf.data(), (unsigned)buf.size())) > 0) {
-		for (int i = 0; i < n; ++i) {
-			char ch = buf[i];
-			if (ch == '\n') { flush_line(line); line.clear(); }
-			else if (ch != '\r') line.push_back(ch);
+		const char *p = buf.data(), *end = p + n;
+		while (p < end) {
+			const char *nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+			if (!nl) { carry.append(p, (size_t)(end - p)); break; }
+			if (!carry.empty()) { carry.append(p, (size_t)(nl - p)); take_line(carry.data(), carry.size()); carry.clear(); }
+			else take_line(p, (size_t)(nl - p));
+			p = nl + 1;
 		}
 	}
-	flush_line(line);
+	const bool read_ok = n == 0;
+	if (!carry.empty()) take_line(carry.data(), carry.size());
 	gzclose(fp);
+	if (!read_ok) throw mb_error(MB_ERR_IO, std::string("read error in ") + path);
 	if (names.empty()) throw mb_error(MB_ERR_IO, std::string("no sequences in ") + path);
 	std::vector<const char*> np; std::vector<const uint8_t*> sp; std::vector<int64_t> lp;
 	for (size_t i = 0; i < names.size(); ++i) { np.push_back(names[i].c_str()); sp.push_back((const uint8_t*)seqs[i].data()); lp.push_back((int64_t)seqs[i].size()); }
@@ -408,15 +427,18 @@ extern "C" int mb_index_load(int device, const char *path, mb_index_t **out)
 {
 	API_BEGIN
 	get_ctx(device);
-	FILE *fp = fopen(path, "rb");
+	struct FileGuard { FILE *f; ~FileGuard() { if (f) fclose(f); } } guard{ fopen(path, "rb") };
+	FILE *fp = guard.f;
 	if (!fp) throw mb_error(MB_ERR_IO, std::string("cannot open ") + path);
 	std::unique_ptr<mb_index> ix(new mb_index());
-	auto fail = [&](const char *m) { fclose(fp); throw mb_error(MB_ERR_IO, std::string(m) + ": " + path); };
+	auto fail = [&](const char *m) { throw mb_error(MB_ERR_IO, std::string(m) + ": " + path); };
 	char magic[4]; uint32_t x[5];
 	if (fread(magic, 1, 4, fp) != 4 || memcmp(magic, "MMI\2", 4) != 0) fail("damaged or empty index (bad magic)");
 	if (fread(x, 4, 5, fp) != 5) fail("damaged index header");
 	ix->device = device, ix->w = (int)x[0], ix->k = (int)x[1], ix->b = (int)x[2];
 	if (x[4] & 3) fail("HPC / no-sequence .mmi flags are not supported");
+	if (x[2] < 1 || x[2] > 28) fail("damaged index header (bucket bits)");
+	if (x[1] < 1 || x[1] > 28 || x[0] < 1 || x[0] > 255) fail("damaged index header (k, w)");
 	uint64_t sum = 0;
 	for (uint32_t i = 0; i < x[3]; ++i) {
 		uint8_t l; char nm[256]; uint32_t len;
@@ -430,7 +452,7 @@ extern "C" int mb_index_load(int device, const char *path, mb_index_t **out)
 	const int b = ix->b;
 	for (uint64_t bi = 0; bi < ((uint64_t)1 << b); ++bi) {
 		int32_t n; uint32_t size;
-		if (fread(&n, 4, 1, fp) != 1) fail("damaged index (bucket)");
+		if (fread(&n, 4, 1, fp) != 1 || n < 0) fail("damaged index (bucket)");
 		std::vector<uint64_t> p(n);
 		if (n && fread(p.data(), 8, n, fp) != (size_t)n) fail("damaged index (bucket)");
 		if (fread(&size, 4, 1, fp) != 1) fail("damaged index (bucket)");
@@ -448,7 +470,6 @@ extern "C" int mb_index_load(int device, const char *path, mb_index_t **out)
 	}
 	ix->h_S.assign((sum + 7) / 8, 0);
 	if (!ix->h_S.empty() && fread(ix->h_S.data(), 4, ix->h_S.size(), fp) != ix->h_S.size()) fail("damaged index (sequence)");
-	fclose(fp);
 	{ // same device pipeline as a fresh build: the positions of one hash come ascending out of the .mmi, the sort is stable
 		ThreadCtx &c = get_ctx(device);
 		c.ar.reset();
@@ -888,11 +909,9 @@ __global__ void k_task_cap(const DpTask *__restrict__ tasks, int64_t n, int32_t 
 
 static void check_err(int *d_err, cudaStream_t st, const char *where)
 {
+	// the device flag only guards invariants the host established (pool sizes); read content cannot raise it
 	int e = d2h_scalar(d_err, st);
-	if (e == 1) throw mb_error(MB_ERR_OVERFLOW, std::string(where) + ": tie between sort keys in a >64-element region sort (exact upstream order not reproduced)");
-	if (e == 2) throw mb_error(MB_ERR_OVERFLOW, std::string(where) + ": region pool overflow");
-	if (e == 3) throw mb_error(MB_ERR_OVERFLOW, std::string(where) + ": inversion-test scratch overflow");
-	if (e) throw mb_error(MB_ERR_OVERFLOW, std::string(where) + ": device error flag");
+	if (e) throw mb_error(MB_ERR_OVERFLOW, std::string(where) + ": internal error, device consistency flag " + std::to_string(e));
 }
 
 // device-resident result of one sub-batch (arrays live in the arena of `c` until its next reset)
@@ -918,6 +937,8 @@ static void map_device_part(mb_index *ix, const mb_opt_t &opt_in, DevPart &part)
 	mb_opt_t opt = opt_in;
 	if (opt.mid_occ <= 0) opt.mid_occ = ix->mid_occ;
 	if (opt.q + opt.e >= 127 || opt.q2 + opt.e2 >= 127) throw mb_error(MB_ERR_ARG, "gap costs too large for int8 DP");
+	if (opt.max_gap > LL_MAX_LEN - 8) throw mb_error(MB_ERR_ARG, "max_gap above 5000 is not supported (inversion-test scratch)");
+	if (!mb_ll_scoring_ok(opt)) throw mb_error(MB_ERR_ARG, "scoring outside the range of the local-alignment kernel (needs b <= q + 2e)");
 	mb_stats_t &S = part.S; memset(&S, 0, sizeof(S));
 	S.n_reads = n_reads, S.n_bases = total;
 	int64_t nl = 0;
@@ -964,29 +985,65 @@ static void map_device_part(mb_index *ix, const mb_opt_t &opt_in, DevPart &part)
 	ra.iscr = ar.get<int32_t>(n_a + 1);
 	int64_t *reg_off = ar.get<int64_t>(n_reads + 1);
 	ra.reg_off = reg_off;
+	// reads with more than 64 chains / regions take the "big" variants of the per-read kernels (see chain.cuh mb_sort_exact)
+	int32_t *big = ar.get<int32_t>(n_reads), *big_ctr = ar.get<int32_t>(8);
+	CK(cudaMemsetAsync(big_ctr, 0, 8 * sizeof(int32_t), st));
+	const int big_grid = c.num_sms;
 	const unsigned rb = (unsigned)cdiv(n_reads, 128);
-	k_chain_bt<<<(unsigned)cdiv((int64_t)n_reads * 32, 128), 128, 0, st>>>(ra, rs, n_reads, opt.min_cnt, opt.min_chain_score, n_u, d_err, sd.read_perm); ++nl;
-	k_reg_cap<<<rb, 128, 0, st>>>(n_u, sd.a_roff, n_reads, cap); ++nl;
+	k_chain_bt<<<(unsigned)cdiv((int64_t)n_reads * 32, 128), 128, 0, st>>>(ra, rs, n_reads, opt.min_cnt, opt.min_chain_score, n_u, sd.read_perm, big, big_ctr + 0); ++nl;
+	k_chain_bt_big<<<big_grid, 32, BIG_SMEM_BYTES, st>>>(ra, rs, opt.min_cnt, opt.min_chain_score, n_u, big, big_ctr + 0, big_ctr + 1); ++nl;
+	const int tight_regs = getenv("MB_TEST_TIGHT_REGS") ? 1 : 0; // tests: no slack in the region pool, so that every growth path runs
+	k_reg_cap<<<rb, 128, 0, st>>>(n_u, n_reads, tight_regs, cap); ++nl;
 	exclusive_scan<int32_t>(ar, st, cap, reg_off, n_reads, &nl);
-	const int64_t reg_total = d2h_scalar(reg_off + n_reads, st);
+	int64_t reg_total = d2h_scalar(reg_off + n_reads, st);
 	ra.regs = ar.get<Reg>(reg_total + 1);
 	rs.regs_tmp = ar.get<Reg>(reg_total + 1);
 	int2 *work = ar.get<int2>(reg_total + 1), *work2 = ar.get<int2>(reg_total + 1);
-	int32_t *n_work = ar.get<int32_t>(2);
-	CK(cudaMemsetAsync(n_work, 0, 2 * sizeof(int32_t), st));
+	// [0] regions of round 1, [1] regions split off in the current round, [2] inversion candidates so far, [3] pool-overflow flag
+	int32_t *n_work = ar.get<int32_t>(4);
+	CK(cudaMemsetAsync(n_work, 0, 4 * sizeof(int32_t), st));
 	AlignCtx ac; ac.codes = d_codes; ac.read_off = d_off; ac.ix = ix->d; ac.opt = opt;
-	k_gen_regs<<<rb, 128, 0, st>>>(ac, ra, rs, n_reads, n_u, n_a_sq, work, n_work, d_err); ++nl;
+	k_gen_regs<<<rb, 128, 0, st>>>(ac, ra, rs, n_reads, n_u, n_a_sq, work, n_work, big, big_ctr + 2); ++nl;
+	k_gen_regs_big<<<big_grid, 32, BIG_SMEM_BYTES, st>>>(ac, ra, rs, n_u, n_a_sq, work, n_work, big, big_ctr + 2, big_ctr + 3); ++nl;
 	k_copy_i32<<<rb, 128, 0, st>>>(ra.n_regs, n0_regs, n_reads); ++nl;
 	int32_t h_n_work = d2h_scalar(n_work, st);
 	check_err(d_err, st, "region generation");
 	S.ms_glue = tm.stop(); S.n_regs = h_n_work;
+	// the work lists and the inversion list hold one entry per region: they grow with the pool
+	int64_t work_cap = reg_total + 1;
+	int4 *inv_list = ar.get<int4>(work_cap);
+	int32_t *need = ar.get<int32_t>(n_reads);
+	// make room for `n_items` more regions (one per work item of the coming pass); grows the pool when some read would run out
+	auto ensure_regs = [&](const int2 *wk, const int4 *il, int n_items) {
+		if (n_items <= 0) return;
+		CK(cudaMemsetAsync(need, 0, (size_t)n_reads * sizeof(int32_t), st));
+		CK(cudaMemsetAsync(n_work + 3, 0, sizeof(int32_t), st));
+		k_round_need<<<(unsigned)cdiv(n_items, 256), 256, 0, st>>>(wk, n_items, il, ra, need, n_work + 3); ++nl;
+		if (d2h_scalar(n_work + 3, st) == 0) return;
+		int32_t *ncap = ar.get<int32_t>(n_reads);
+		int64_t *noff = ar.get<int64_t>(n_reads + 1);
+		k_regs_newcap<<<rb, 128, 0, st>>>(ra, need, n_reads, ncap); ++nl;
+		exclusive_scan<int32_t>(ar, st, ncap, noff, n_reads, &nl);
+		const int64_t ntot = d2h_scalar(noff + n_reads, st);
+		Reg *nregs = ar.get<Reg>(ntot + 1);
+		k_regs_move<<<(unsigned)cdiv((int64_t)n_reads * 32, 128), 128, 0, st>>>(ra.regs, ra.reg_off, nregs, noff, ra.n_regs, n_reads); ++nl;
+		ra.regs = nregs, ra.reg_off = noff, reg_off = noff, reg_total = ntot;
+		rs.regs_tmp = ar.get<Reg>(ntot + 1);
+		if (ntot + 1 > work_cap) { // lists are rebuilt at the new size (work2 / inv_list contents are copied, `work` is being consumed)
+			int2 *w2 = ar.get<int2>(ntot + 1), *w1 = ar.get<int2>(ntot + 1);
+			int4 *il2 = ar.get<int4>(ntot + 1);
+			CK(cudaMemcpyAsync(w1, work, (size_t)work_cap * sizeof(int2), cudaMemcpyDeviceToDevice, st));
+			CK(cudaMemcpyAsync(w2, work2, (size_t)work_cap * sizeof(int2), cudaMemcpyDeviceToDevice, st));
+			CK(cudaMemcpyAsync(il2, inv_list, (size_t)work_cap * sizeof(int4), cudaMemcpyDeviceToDevice, st));
+			work = w1, work2 = w2, inv_list = il2, work_cap = ntot + 1;
+		}
+	};
 	// alignment rounds
 	tm.start();
 	const DpScoring scoring = make_scoring(opt);
-	int *inv_pool = nullptr; int32_t *inv_ctr = ar.get<int32_t>(1);
-	CK(cudaMemsetAsync(inv_ctr, 0, sizeof(int32_t), st));
 	DpRunner runner(c, &nl);
 	int round = 0;
+	int32_t h_n_inv = 0;
 	const bool dbg = getenv("MB_DEBUG") != nullptr;
 	auto phase = [&](const char *name) {
 		auto &t0 = g_dbg_t0;
@@ -997,12 +1054,15 @@ static void map_device_part(mb_index *ix, const mb_opt_t &opt_in, DevPart &part)
 		t0 = t1;
 	};
 	phase("pre-align");
+	const int ll_grid = c.num_sms * 4;
+	int *ll_scr = nullptr;   // scratch of the local-alignment kernels (inversion tests): allocated on first use
 	while (h_n_work > 0) {
 		++round;
 		const unsigned wb = (unsigned)cdiv(h_n_work, 128);
 		RegPlan *plans = ar.get<RegPlan>(h_n_work);
 		int32_t *nt = ar.get<int32_t>(h_n_work);
 		int64_t *task_off = ar.get<int64_t>(h_n_work + 1);
+		ensure_regs(work, nullptr, h_n_work);
 		k_plan1<<<wb, 128, 0, st>>>(ac, ra, work, h_n_work, plans); ++nl;
 		k_plan_ntasks<<<wb, 128, 0, st>>>(plans, h_n_work, nt); ++nl;
 		exclusive_scan<int32_t>(ar, st, nt, task_off, h_n_work, &nl);
@@ -1028,14 +1088,15 @@ static void map_device_part(mb_index *ix, const mb_opt_t &opt_in, DevPart &part)
 			dp_token.unlock();
 			phase("dp pass 1");
 			// Z-drop test and second pass
-			int32_t *pass2 = ar.get<int32_t>(n_tasks), *n_pass2 = ar.get<int32_t>(1);
-			CK(cudaMemsetAsync(n_pass2, 0, sizeof(int32_t), st));
-			if (!inv_pool) inv_pool = ar.get<int>((size_t)INV_SLOTS * INV_STRIDE);
-			int32_t *walk = ar.get<int32_t>(n_tasks), *n_walk = ar.get<int32_t>(1);
-			CK(cudaMemsetAsync(n_walk, 0, sizeof(int32_t), st));
-			k_ztest_screen<<<(unsigned)cdiv(n_tasks, 128), 128, 0, st>>>(ac, tasks, n_tasks, cigar_pool, walk, n_walk); ++nl;
-			k_ztest<<<(unsigned)cdiv(n_tasks, 128), 128, 0, st>>>(ac, tasks, walk, n_walk, n_tasks, cigar_pool, pass2, n_pass2, inv_pool, inv_ctr, d_err); ++nl;
-			const int32_t h_pass2 = d2h_scalar(n_pass2, st);
+			int32_t *pass2 = ar.get<int32_t>(n_tasks), *zc = ar.get<int32_t>(4); // zc: [0] second-pass tasks, [1] walk list, [2] inversion-test candidates, [3] cursor
+			CK(cudaMemsetAsync(zc, 0, 4 * sizeof(int32_t), st));
+			int32_t *walk = ar.get<int32_t>(n_tasks);
+			ZCand *zcand = ar.get<ZCand>(n_tasks);
+			if (!ll_scr) ll_scr = ar.get<int>((size_t)ll_grid * 2 * LL_MAX_LEN);
+			k_ztest_screen<<<(unsigned)cdiv(n_tasks, 128), 128, 0, st>>>(ac, tasks, n_tasks, cigar_pool, walk, zc + 1); ++nl;
+			k_ztest<<<(unsigned)cdiv(n_tasks, 128), 128, 0, st>>>(ac, tasks, walk, zc + 1, n_tasks, cigar_pool, pass2, zc + 0, zcand, zc + 2); ++nl;
+			k_ztest_ll<<<ll_grid, 32, 0, st>>>(ac, tasks, zcand, zc + 2, zc + 3, pass2, zc + 0, ll_scr); ++nl;
+			const int32_t h_pass2 = d2h_scalar(zc, st);
 			phase("ztest");
 			S.n_dp_pass2 += h_pass2;
 			if (h_pass2 > 0) runner.run(tasks, pass2, h_pass2, true, d_codes, ix->d.S, nullptr, cigar_pool, scoring, d_cells + 1);
@@ -1053,14 +1114,63 @@ static void map_device_part(mb_index *ix, const mb_opt_t &opt_in, DevPart &part)
 			k_work_scatter<<<(unsigned)cdiv(h_n_work, 256), 256, 0, st>>>(work, h_n_work, ra, hist, perm);
 			nl += 3;
 		}
-		k_stitch<<<(unsigned)cdiv((int64_t)h_n_work * 32, 128), 128, 0, st>>>(ac, ra, work, h_n_work, plans, tasks, cigar_pool, work2, n_work + 1, d_err, perm); ++nl;
+		k_stitch<<<(unsigned)cdiv((int64_t)h_n_work * 32, 128), 128, 0, st>>>(ac, ra, work, h_n_work, plans, tasks, cigar_pool, work2, n_work + 1, d_err, perm, inv_list, n_work + 2); ++nl;
 		phase("stitch");
 		k_update_extra<<<(unsigned)cdiv((int64_t)h_n_work * 32, 128), 128, 0, st>>>(ac, ra, work, h_n_work, plans, tasks, cigar_pool, perm); ++nl;
 		phase("update_extra");
-		h_n_work = d2h_scalar(n_work + 1, st);
+		{
+			int32_t h2[2];
+			CK(cudaMemcpyAsync(h2, n_work + 1, sizeof(h2), cudaMemcpyDeviceToHost, st));
+			CK(cudaStreamSynchronize(st));
+			h_n_work = h2[0], h_n_inv = h2[1];
+		}
 		check_err(d_err, st, "alignment round");
 		std::swap(work, work2);
-		if (round > 64) throw mb_error(MB_ERR_OVERFLOW, "alignment did not converge in 64 split rounds");
+	}
+	// inversion hits (mm_align1_inv), in passes over the candidate chains
+	if (h_n_inv > 0) {
+		int4 *cur = inv_list, *nxt = ar.get<int4>(h_n_inv), *proc = ar.get<int4>(h_n_inv);
+		InvTask *ll = ar.get<InvTask>(h_n_inv), *task_inv = ar.get<InvTask>(h_n_inv);
+		DpTask *itasks = ar.get<DpTask>(h_n_inv + 1);
+		int32_t *icap = ar.get<int32_t>(h_n_inv + 1);
+		int64_t *ioff = ar.get<int64_t>(h_n_inv + 2);
+		int2 *iwork = ar.get<int2>(h_n_inv);
+		RegPlan *iplans = ar.get<RegPlan>(h_n_inv);
+		int32_t *ic = ar.get<int32_t>(8);  // [0] deferred, [1] processed, [2] local alignments, [3] cursor, [4] DP tasks, [5] inversion hits
+		if (!ll_scr) ll_scr = ar.get<int>((size_t)ll_grid * 2 * LL_MAX_LEN);
+		int n_cur = h_n_inv, guard = 0;
+		ensure_regs(nullptr, cur, n_cur);
+		while (n_cur > 0) {
+			CK(cudaMemsetAsync(ic, 0, 8 * sizeof(int32_t), st));
+			k_inv_plan<<<(unsigned)cdiv(n_cur, 128), 128, 0, st>>>(ac, ra, cur, n_cur, nxt, ic + 0, proc, ic + 1, ll, ic + 2); ++nl;
+			k_inv_ll<<<ll_grid, 32, 0, st>>>(ac, ra, ll, ic + 2, ic + 3, ll_scr, itasks, task_inv, icap, ic + 4); ++nl;
+			int32_t hc[5];
+			CK(cudaMemcpyAsync(hc, ic, sizeof(hc), cudaMemcpyDeviceToHost, st));
+			CK(cudaStreamSynchronize(st));
+			const int n_dp = hc[4];
+			if (n_dp > 0) {
+				exclusive_scan<int32_t>(ar, st, icap, ioff, n_dp, &nl);
+				const int64_t ctot = d2h_scalar(ioff + n_dp, st);
+				uint32_t *ipool = ar.get<uint32_t>(ctot + 1);
+				k_set_cigar_off<<<(unsigned)cdiv(n_dp, 256), 256, 0, st>>>(itasks, ioff, n_dp, (int64_t)((uintptr_t)ipool / 4)); ++nl;
+				std::unique_lock<std::mutex> dp_token(g_dp_mutex[c.device & 15]);
+				runner.run(itasks, nullptr, n_dp, false, d_codes, ix->d.S, nullptr, nullptr, scoring, d_cells + 1);
+				CK(cudaEventSynchronize(c.ev_fast_done));
+				dp_token.unlock();
+				k_inv_finish<<<(unsigned)cdiv(n_dp, 128), 128, 0, st>>>(ac, ra, itasks, task_inv, n_dp, iwork, iplans, ic + 5, d_err); ++nl;
+				const int32_t n_ok = d2h_scalar(ic + 5, st);
+				if (n_ok > 0) { k_update_extra<<<(unsigned)cdiv((int64_t)n_ok * 32, 128), 128, 0, st>>>(ac, ra, iwork, n_ok, iplans, itasks, nullptr, nullptr); ++nl; }
+				S.n_dp_tasks += n_dp; S.n_inv += n_ok;
+				// the arrays of this pass are consumed; later passes (deeper split chains) get fresh ones
+				itasks = ar.get<DpTask>(hc[0] + 1); task_inv = ar.get<InvTask>(hc[0] + 1);
+			}
+			k_inv_close<<<(unsigned)cdiv(n_cur, 128), 128, 0, st>>>(ra, proc, ic + 1); ++nl;
+			CK(cudaStreamSynchronize(st));
+			if (hc[1] == 0 && ++guard > 2) throw mb_error(MB_ERR_OVERFLOW, "inversion pass made no progress (internal error)");
+			n_cur = hc[0];
+			std::swap(cur, nxt);
+		}
+		check_err(d_err, st, "inversion pass");
 	}
 	S.n_rounds = round;
 	S.ms_dp = tm.stop();
@@ -1068,7 +1178,8 @@ static void map_device_part(mb_index *ix, const mb_opt_t &opt_in, DevPart &part)
 	tm.start();
 	int32_t *n_hits = ar.get<int32_t>(n_reads), *n_hit_cig = ar.get<int32_t>(n_reads);
 	int64_t *hit_off = ar.get<int64_t>(n_reads + 1), *hcig_off = ar.get<int64_t>(n_reads + 1);
-	k_finish<<<rb, 128, 0, st>>>(ac, ra, rs, n_reads, n0_regs, sd.rep_len, n_hits, n_hit_cig, d_err); ++nl;
+	k_finish<<<rb, 128, 0, st>>>(ac, ra, rs, n_reads, n0_regs, sd.rep_len, n_hits, n_hit_cig, big, big_ctr + 4); ++nl;
+	k_finish_big<<<big_grid, 32, BIG_SMEM_BYTES, st>>>(ac, ra, rs, n0_regs, sd.rep_len, n_hits, n_hit_cig, big, big_ctr + 4, big_ctr + 5); ++nl;
 	exclusive_scan<int32_t>(ar, st, n_hits, hit_off, n_reads, &nl);
 	exclusive_scan<int32_t>(ar, st, n_hit_cig, hcig_off, n_reads, &nl);
 	const int64_t n_h = d2h_scalar(hit_off + n_reads, st);
@@ -1569,7 +1680,12 @@ extern "C" int mb_chain(int device, const mb_opt_t *opt, const uint64_t *anchors
 		ReadArrays ra; memset(&ra, 0, sizeof(ra));
 		ra.a = d_a; ra.a_roff = d_roff;
 		int32_t *n_u = ar.get<int32_t>(n_reads + 1);
-		if (n_reads) k_chain_bt<<<(unsigned)cdiv((int64_t)n_reads * 32, 128), 128, 0, st>>>(ra, rs, n_reads, opt->min_cnt, opt->min_chain_score, n_u, d_err, nullptr);
+		int32_t *big = ar.get<int32_t>(n_reads + 1), *big_ctr = ar.get<int32_t>(2);
+		CK(cudaMemsetAsync(big_ctr, 0, 2 * sizeof(int32_t), st));
+		if (n_reads) {
+			k_chain_bt<<<(unsigned)cdiv((int64_t)n_reads * 32, 128), 128, 0, st>>>(ra, rs, n_reads, opt->min_cnt, opt->min_chain_score, n_u, nullptr, big, big_ctr);
+			k_chain_bt_big<<<c.num_sms, 32, BIG_SMEM_BYTES, st>>>(ra, rs, opt->min_cnt, opt->min_chain_score, n_u, big, big_ctr, big_ctr + 1);
+		}
 		std::vector<int32_t> h_nu(n_reads);
 		std::vector<mb128> h_a(n_a); std::vector<uint64_t> h_u(n_a);
 		if (n_reads) CK(cudaMemcpyAsync(h_nu.data(), n_u, n_reads * 4, cudaMemcpyDeviceToHost, st));
@@ -1632,6 +1748,51 @@ extern "C" int mb_dp_batch(int device, const mb_opt_t *opt, mb_dp_task_t *tasks,
 	if (n_tasks) k_tasks_to_api<<<(unsigned)cdiv(n_tasks, 256), 256, 0, st>>>(d_t, d_in, n_tasks);
 	if (n_tasks) CK(cudaMemcpyAsync(tasks, d_in, n_tasks * sizeof(mb_dp_task_t), cudaMemcpyDeviceToHost, st));
 	if (n_cigar_pool) CK(cudaMemcpyAsync(cigar_pool, d_cig, n_cigar_pool * 4, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	CK(cudaGetLastError());
+	API_END
+}
+
+__global__ void __launch_bounds__(32)
+k_ll_batch(mb_opt_t opt, mb_ll_task_t *__restrict__ tasks, int64_t n, int32_t *__restrict__ cursor, const uint8_t *__restrict__ pool, int *__restrict__ scr_pool)
+{
+	const int lane = threadIdx.x;
+	int *scr = scr_pool + (size_t)blockIdx.x * (2 * LL_MAX_LEN);
+	for (;;) {
+		int k = 0;
+		if (lane == 0) k = atomicAdd(cursor, 1);
+		k = __shfl_sync(0xffffffffu, k, 0);
+		if (k >= n) break;
+		mb_ll_task_t &T = tasks[k];
+		const uint8_t *q = pool + T.q_off, *t = pool + T.t_off;
+		int qe, te;
+		const int sc = mb_ll_warp([&](int col) { return (int)q[col]; }, [&](int row) { return (int)t[row]; }, T.qlen, T.tlen, opt, scr, true, &qe, &te, lane);
+		__syncwarp();
+		if (lane == 0) T.score = sc, T.qe = qe, T.te = te;
+		__syncwarp();
+	}
+}
+
+extern "C" int mb_ll_batch(int device, const mb_opt_t *opt, mb_ll_task_t *tasks, int64_t n_tasks, const uint8_t *seqpool, int64_t n_seqpool)
+{
+	API_BEGIN
+	if (!opt || !tasks || n_tasks < 0) throw mb_error(MB_ERR_ARG, "bad arguments");
+	if (!mb_ll_scoring_ok(*opt)) throw mb_error(MB_ERR_ARG, "scoring outside the range of the local-alignment kernel (needs b <= q + 2e)");
+	for (int64_t i = 0; i < n_tasks; ++i)
+		if (tasks[i].qlen < 0 || tasks[i].tlen < 0 || tasks[i].qlen > LL_MAX_LEN - 8 || tasks[i].tlen > LL_MAX_LEN - 8) throw mb_error(MB_ERR_ARG, "sequence longer than 5000");
+	ThreadCtx &c = get_ctx(device);
+	c.ar.reset();
+	cudaStream_t st = c.st; Arena &ar = c.ar;
+	mb_ll_task_t *d_t = ar.get<mb_ll_task_t>(n_tasks + 1);
+	uint8_t *d_pool = ar.get<uint8_t>(n_seqpool + 16);
+	const int grid = c.num_sms * 4;
+	int *scr = ar.get<int>((size_t)grid * 2 * LL_MAX_LEN);
+	int32_t *cur = ar.get<int32_t>(1);
+	CK(cudaMemsetAsync(cur, 0, sizeof(int32_t), st));
+	if (n_tasks) CK(cudaMemcpyAsync(d_t, tasks, n_tasks * sizeof(mb_ll_task_t), cudaMemcpyHostToDevice, st));
+	if (n_seqpool) CK(cudaMemcpyAsync(d_pool, seqpool, n_seqpool, cudaMemcpyHostToDevice, st));
+	if (n_tasks) k_ll_batch<<<grid, 32, 0, st>>>(*opt, d_t, n_tasks, cur, d_pool, scr);
+	if (n_tasks) CK(cudaMemcpyAsync(tasks, d_t, n_tasks * sizeof(mb_ll_task_t), cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));
 	CK(cudaGetLastError());
 	API_END

@@ -165,6 +165,8 @@ void mm2o_ksw_set_simd(int on);   /* 1: SSE4.1 16-lane core (default), 0: scalar
 void mm2o_ksw_extd2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int8_t m, const int8_t *mat,
 					int8_t q, int8_t e, int8_t q2, int8_t e2, int w, int zdrop, int end_bonus, int flag, ksw_extz_t *ez);
 void mm2o_gen_simple_mat(int m, int8_t *mat, int8_t a, int8_t b, int8_t sc_ambi);
+/* ksw2_ll_sse.c ksw_ll_qinit + ksw_ll_i16 (striped local alignment: score, query end, target end) */
+int mm2o_ksw_ll_i16(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int m, const int8_t *mat, int gapo, int gape, int *qe, int *te);
 int64_t mm2o_ksw_cells(int qlen, int tlen, int w);
 
 /* radix sorts with upstream's exact (unstable) permutation (ksort.h KRADIX_SORT_INIT) */

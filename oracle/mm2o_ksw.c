@@ -404,3 +404,84 @@ void mm2o_ksw_extd2(int qlen, const uint8_t *query, int tlen, const uint8_t *tar
 		free(p); free(off);
 	}
 }
+
+/*
+ * ksw2_ll_sse.c ksw_ll_qinit() + ksw_ll_i16(): local (Smith-Waterman) single-affine alignment in Farrar's striped layout,
+ * 8 int16 lanes per vector, restated lane by lane as scalar code so that the upstream quirks that decide the END POSITION
+ * are kept: the query is padded to slen*8 columns whose substitution score is 0 (a maximum in the last real column is
+ * carried diagonally through the padding, so `te` can advance by up to 7 rows and `qe` can point past the query), the row
+ * maximum is taken over all lanes before the lazy-F pass, `imax >= gmax` keeps the LAST row that reaches the maximum, and
+ * the final scan keeps the LAST memory slot of that row equal to gmax (slot i <-> query column i/8 + i%8*slen).
+ * Callers: mm_test_zdrop (score only) and mm_align1_inv (score, qe, te) in align.c.
+ */
+int mm2o_ksw_ll_i16(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int m, const int8_t *mat, int gapo, int gape, int *qe, int *te)
+{
+	const int p = 8, slen = (qlen + p - 1) / p, n8 = slen * p;
+	int16_t *qp, *H0, *H1, *E, *Hmax, *tmp;
+	int a, i, j, l, gmax = 0, gapoe = gapo + gape;
+	*qe = *te = -1;
+	if (qlen <= 0) return 0;
+	qp = (int16_t*)calloc((size_t)n8 * (m + 4), sizeof(int16_t));
+	H0 = qp + (size_t)n8 * m, H1 = H0 + n8, E = H1 + n8, Hmax = E + n8;
+	for (a = 0; a < m; ++a) { /* query profile: vector j, lane l holds column j + l*slen */
+		int16_t *t = qp + (size_t)a * n8;
+		const int8_t *ma = mat + a * m;
+		for (i = 0; i < slen; ++i)
+			for (j = i; j < n8; j += slen)
+				*t++ = (int16_t)(j >= qlen? 0 : ma[query[j]]);
+	}
+#define SUBS_U16(x, y) ((uint16_t)(x) > (uint16_t)(y)? (int16_t)((uint16_t)(x) - (uint16_t)(y)) : (int16_t)0)
+#define ADDS_I16(x, y) ((int)(x) + (int)(y) > 32767? (int16_t)32767 : (int)(x) + (int)(y) < -32768? (int16_t)-32768 : (int16_t)((x) + (y)))
+	for (i = 0; i < tlen; ++i) {
+		int16_t h[8], e[8], f[8] = {0,0,0,0,0,0,0,0}, mx[8] = {0,0,0,0,0,0,0,0};
+		const int16_t *S = qp + (size_t)target[i] * n8;
+		int k, imax, done = 0;
+		for (l = 7; l >= 1; --l) h[l] = H0[(slen - 1) * 8 + l - 1]; /* _mm_slli_si128(H0[slen-1], 2) */
+		h[0] = 0;
+		for (j = 0; j < slen; ++j) {
+			for (l = 0; l < 8; ++l) {
+				int16_t hh = ADDS_I16(h[l], S[j * 8 + l]), t;
+				e[l] = E[j * 8 + l];
+				hh = hh > e[l]? hh : e[l];
+				hh = hh > f[l]? hh : f[l];
+				mx[l] = mx[l] > hh? mx[l] : hh;
+				H1[j * 8 + l] = hh;
+				t = SUBS_U16(hh, gapoe);
+				e[l] = SUBS_U16(e[l], gape);
+				e[l] = e[l] > t? e[l] : t;
+				E[j * 8 + l] = e[l];
+				f[l] = SUBS_U16(f[l], gape);
+				f[l] = f[l] > t? f[l] : t;
+				h[l] = H0[j * 8 + l];
+			}
+		}
+		for (k = 0; k < 8 && !done; ++k) { /* lazy F */
+			for (l = 7; l >= 1; --l) f[l] = f[l - 1];
+			f[0] = 0;
+			for (j = 0; j < slen; ++j) {
+				int any = 0;
+				for (l = 0; l < 8; ++l) {
+					int16_t hh = H1[j * 8 + l];
+					hh = hh > f[l]? hh : f[l];
+					H1[j * 8 + l] = hh;
+					hh = SUBS_U16(hh, gapoe);
+					f[l] = SUBS_U16(f[l], gape);
+					if (f[l] > hh) any = 1;
+				}
+				if (!any) { done = 1; break; }
+			}
+		}
+		for (l = 1, imax = mx[0]; l < 8; ++l) imax = imax > mx[l]? imax : mx[l];
+		if (imax >= gmax) {
+			gmax = imax, *te = i;
+			memcpy(Hmax, H1, (size_t)n8 * sizeof(int16_t));
+		}
+		tmp = H1, H1 = H0, H0 = tmp;
+	}
+#undef SUBS_U16
+#undef ADDS_I16
+	for (i = 0; i < n8; ++i)
+		if ((int)(uint16_t)Hmax[i] == gmax) *qe = i / 8 + i % 8 * slen;
+	free(qp);
+	return gmax;
+}

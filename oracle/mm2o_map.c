@@ -6,8 +6,8 @@
  * mm_squeeze_a), align.c (mm_align_skeleton, mm_align1, mm_align_pair, mm_test_zdrop,
  * mm_fix_bad_ends, mm_filter_bad_seeds[_alt], mm_fix_cigar, mm_update_extra, mm_append_cigar),
  * map.c (mm_map_frag, chain_post, align_regs) and python/cmappy.h (mm_reg2hitpy).
- * NOT restated: mm_align1_inv (inversion re-alignment between split regions) and mm_est_err
- * (sets mm_reg1_t::div, which mappy does not expose) -- see DESIGN.md.
+ * mm_align1_inv (inversion re-alignment between the two halves of a split_inv Z-drop split) and mm_set_inv_mapq are
+ * restated below.  NOT restated: mm_est_err (sets mm_reg1_t::div, which mappy does not expose).
  * PARITY UNPINNED -- see mm2o.h.  Call sites in the reference:
  * /root/reference/monica/genomes/aligner.py:193,215 (index.map) and :194-195,216-217 (fields read).
  */
@@ -390,6 +390,8 @@ static void mm_split_reg(mm_reg1_t *r, mm_reg1_t *r2, int n, int qlen, mm128_t *
 	r->split |= 1, r2->split |= 2;
 }
 
+static void mm_set_inv_mapq(int n_regs, mm_reg1_t *regs);
+
 static void mm_set_mapq(int n_regs, mm_reg1_t *regs, int min_chain_sc, int match_sc, int rep_len)
 {
 	static const float q_coef = 40.0f;
@@ -434,6 +436,32 @@ static void mm_set_mapq(int n_regs, mm_reg1_t *regs, int min_chain_sc, int match
 			if (r->p && r->p->dp_max > r->p->dp_max2 && r->mapq == 0) r->mapq = 1;
 		} else r->mapq = 0;
 	}
+	mm_set_inv_mapq(n_regs, regs);
+}
+
+/* hit.c mm_set_inv_mapq(): an inversion hit takes the smaller MAPQ of its two neighbours in reference order */
+static void mm_set_inv_mapq(int n_regs, mm_reg1_t *regs)
+{
+	int i, n_aux;
+	mm128_t *aux;
+	if (n_regs < 3) return;
+	for (i = 0; i < n_regs; ++i)
+		if (regs[i].inv) break;
+	if (i == n_regs) return; /* no inversion hits */
+	aux = (mm128_t*)malloc(n_regs * 16);
+	for (i = n_aux = 0; i < n_regs; ++i)
+		if (regs[i].parent == i || regs[i].parent < 0)
+			aux[n_aux].y = i, aux[n_aux++].x = (uint64_t)regs[i].rid << 32 | regs[i].rs;
+	mm2o_radix_sort_128x(aux, aux + n_aux);
+	for (i = 1; i < n_aux - 1; ++i) {
+		mm_reg1_t *inv = &regs[aux[i].y];
+		if (inv->inv) {
+			mm_reg1_t *l = &regs[aux[i-1].y];
+			mm_reg1_t *r = &regs[aux[i+1].y];
+			inv->mapq = l->mapq < r->mapq? l->mapq : r->mapq;
+		}
+	}
+	free(aux);
 }
 
 /* ---------------- align.c ---------------- */
@@ -698,7 +726,11 @@ static int mm_test_zdrop(const mm2o_opt_t *opt, const uint8_t *qseq, const uint8
 			int c = qseq[pos[1][1] - i - 1];
 			qseq2[i] = c >= 4? 4 : 3 - c;
 		}
-		score = ksw_ll_score(q_len, qseq2, t_len, tseq + pos[0][0], mat, opt->q, opt->e);
+		{
+			int q_off, t_off; /* upstream passes them and ignores the values here */
+			score = mm2o_ksw_ll_i16(q_len, qseq2, t_len, tseq + pos[0][0], 5, mat, opt->q, opt->e, &q_off, &t_off);
+			assert(score == ksw_ll_score(q_len, qseq2, t_len, tseq + pos[0][0], mat, opt->q, opt->e)); /* the plain recurrence gives the same maximum */
+		}
 		free(qseq2);
 		if (score >= opt->min_chain_score * opt->a && score >= opt->min_dp_max)
 			return 2; /* there is a potential inversion */
@@ -997,6 +1029,66 @@ static void mm_align1(actx_t *c, int qlen, uint8_t *qseq0[2], mm_reg1_t *r, mm_r
 	free(tseq);
 }
 
+/* align.c mm_align1_inv(): after a Z-drop split flagged as a potential inversion (mm_test_zdrop code 2), align the query
+ * segment between the two halves, taken from the OPPOSITE strand, to the reference segment between them: a local alignment
+ * of the reversed sequences finds where the inverted block starts (ksw_ll_i16), an extension alignment from there gives the
+ * inv region.  r1 = the region before, r2 = the split-off region (both already aligned). */
+static int mm_align1_inv(actx_t *c, int qlen, uint8_t *qseq0[2], const mm_reg1_t *r1, const mm_reg1_t *r2, mm_reg1_t *r_inv, ksw_extz_t *ez)
+{
+	const mm2o_opt_t *opt = c->opt;
+	const mm2o_idx_t *mi = c->mi;
+	int tl, ql, score, ret = 0, q_off, t_off;
+	uint8_t *tseq, *qseq;
+	int8_t mat[25];
+
+	memset(r_inv, 0, sizeof(mm_reg1_t));
+	if (!(r1->split&1) || !(r2->split&2)) return 0;
+	if (r1->id != r1->parent && r1->parent != MM_PARENT_TMP_PRI) return 0;
+	if (r2->id != r2->parent && r2->parent != MM_PARENT_TMP_PRI) return 0;
+	if (r1->rid != r2->rid || r1->rev != r2->rev) return 0;
+	ql = r1->rev? r1->qs - r2->qe : r2->qs - r1->qe;
+	tl = r2->rs - r1->re;
+	if (ql < opt->min_chain_score || ql > opt->max_gap) return 0;
+	if (tl < opt->min_chain_score || tl > opt->max_gap) return 0;
+
+	mm2o_gen_simple_mat(5, mat, opt->a, opt->b, opt->sc_ambi);
+	tseq = (uint8_t*)malloc(tl);
+	mm2o_idx_getseq(mi, r1->rid, r1->re, r2->rs, tseq);
+	qseq = r1->rev? &qseq0[0][r2->qe] : &qseq0[1][qlen - r2->qs];
+
+	mm_seq_rev(ql, qseq);
+	mm_seq_rev(tl, tseq);
+	score = mm2o_ksw_ll_i16(ql, qseq, tl, tseq, 5, mat, opt->q, opt->e, &q_off, &t_off);
+	mm_seq_rev(ql, qseq);
+	mm_seq_rev(tl, tseq);
+	if (score < opt->min_dp_max) goto end_align1_inv;
+	q_off = ql - (q_off + 1), t_off = tl - (t_off + 1); /* q_off can be -1..-7: see mm2o_ksw_ll_i16 on the padded columns */
+	mm_align_pair(c, ql - q_off, qseq + q_off, tl - t_off, tseq + t_off, mat, (int)(opt->bw * 1.5), -1, opt->zdrop, KSW_EZ_EXTZ_ONLY, ez);
+	if (ez->n_cigar == 0) goto end_align1_inv; /* should never be here */
+	mm_append_cigar(r_inv, ez->n_cigar, ez->cigar);
+	r_inv->p->dp_score = ez->max;
+	r_inv->id = -1;
+	r_inv->parent = MM_PARENT_UNSET;
+	r_inv->inv = 1;
+	r_inv->rev = !r1->rev;
+	r_inv->rid = r1->rid;
+	r_inv->div = -1.0f;
+	if (r_inv->rev == 0) {
+		r_inv->qs = r2->qe + q_off;
+		r_inv->qe = r_inv->qs + ez->max_q + 1;
+	} else {
+		r_inv->qe = r2->qs - q_off;
+		r_inv->qs = r_inv->qe - (ez->max_q + 1);
+	}
+	r_inv->rs = r1->re + t_off;
+	r_inv->re = r_inv->rs + ez->max_t + 1;
+	mm_update_extra(r_inv, &qseq[q_off], &tseq[t_off], mat, opt->q, opt->e);
+	ret = 1;
+end_align1_inv:
+	free(tseq);
+	return ret;
+}
+
 static mm_reg1_t *mm_insert_reg(const mm_reg1_t *r, int i, int *n_regs, mm_reg1_t *regs)
 {
 	regs = (mm_reg1_t*)realloc(regs, (*n_regs + 1) * sizeof(mm_reg1_t));
@@ -1026,7 +1118,12 @@ static mm_reg1_t *mm_align_skeleton(actx_t *c, int qlen, const char *qstr, int *
 		mm_reg1_t r2;
 		mm_align1(c, qlen, qseq0, &regs[i], &r2, n_a, a, &ez);
 		if (r2.cnt > 0) regs = mm_insert_reg(&r2, i, &n_regs, regs);
-		/* upstream: if (i > 0 && regs[i].split_inv) mm_align1_inv(...) -- NOT restated (see header) */
+		if (i > 0 && regs[i].split_inv) {
+			if (mm_align1_inv(c, qlen, qseq0, &regs[i-1], &regs[i], &r2, &ez)) {
+				regs = mm_insert_reg(&r2, i, &n_regs, regs);
+				++i; /* skip the inserted INV alignment */
+			}
+		}
 	}
 	*n_regs_ = n_regs;
 	free(qseq0[0]);

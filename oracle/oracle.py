@@ -119,6 +119,8 @@ def lib():
                                      C.c_int8, C.c_int8, C.c_int8, C.c_int8, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.POINTER(Ez)]
         L.mm2o_gen_simple_mat.argtypes = [C.c_int, C.c_void_p, C.c_int8, C.c_int8, C.c_int8]
+        L.mm2o_ksw_ll_i16.restype = C.c_int
+        L.mm2o_ksw_ll_i16.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.mm2o_ksw_cells.restype = C.c_int64
         L.mm2o_ksw_cells.argtypes = [C.c_int, C.c_int, C.c_int]
         L.mm2o_radix_sort_128x.argtypes = [C.c_void_p, C.c_void_p]
@@ -203,6 +205,17 @@ def ksw_extd2(query: np.ndarray, target: np.ndarray, w: int, zdrop: int, end_bon
         C.CDLL(None).free(ez.cigar)
     return dict(max=ez.max_zd & 0x7fffffff, zdropped=ez.max_zd >> 31, max_q=ez.max_q, max_t=ez.max_t,
                 mqe=ez.mqe, mqe_t=ez.mqe_t, mte=ez.mte, score=ez.score, reach_end=ez.reach_end, cigar=cig)
+
+
+def ksw_ll_i16(query: np.ndarray, target: np.ndarray, q=4, e=2, mat=None):
+    """ksw2_ll_sse.c ksw_ll_i16 on nt4-coded sequences: (score, qe, te)."""
+    if mat is None:
+        mat = simple_mat()
+    query = np.ascontiguousarray(query, dtype=np.uint8)
+    target = np.ascontiguousarray(target, dtype=np.uint8)
+    qe, te = C.c_int(-1), C.c_int(-1)
+    sc = lib().mm2o_ksw_ll_i16(len(query), query.ctypes.data, len(target), target.ctypes.data, 5, mat.ctypes.data, q, e, C.byref(qe), C.byref(te))
+    return sc, qe.value, te.value
 
 
 class Index:

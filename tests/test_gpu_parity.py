@@ -632,3 +632,143 @@ def test_streaming_batches_accumulate_to_one_shot_counts(lib):
             run_counts += c; run_cls += k
         assert np.array_equal(run_counts, want_counts) and np.array_equal(run_cls, want_cls), mode
     assert want_cls[0] > 0.5 * 12000 and want_cls.sum() == 12000   # strain copies push many reads below MAPQ 60
+
+
+def test_local_alignment_kernel_bit_exact(oracle, lib):
+    """mb_ll_batch (ll.cuh) vs the oracle's lane-by-lane restatement of ksw_ll_i16: score, query end, target end -- including
+    the padded-column quirk (best alignment ending at the query end: qe >= qlen, te carried forward) and last-row / last-slot
+    tie rules."""
+    from monica_b200 import _lib
+    rng = np.random.default_rng(91)
+    qs, ts = [], []
+    for it in range(260):
+        ql, tl = int(rng.integers(1, 400)), int(rng.integers(1, 400))
+        q = rng.integers(0, 4, ql).astype(np.uint8)
+        t = rng.integers(0, 4, tl).astype(np.uint8)
+        kind = it % 5
+        if kind == 0 and ql > 30 and tl > 40:          # planted noisy copy somewhere in the middle
+            n = min(ql, tl) // 2
+            a, b = int(rng.integers(0, ql - n + 1)), int(rng.integers(0, tl - n + 1))
+            seg = q[a:a + n].copy(); m = rng.random(n) < 0.08; seg[m] = (seg[m] + 1) % 4
+            t[b:b + n] = seg
+        elif kind == 1 and tl > ql + 8:                # whole query inside the target: ends at the last query column
+            b = int(rng.integers(0, tl - ql - 7)); t[b:b + ql] = q
+        elif kind == 2:                                # low complexity: many equal maxima
+            q[:] = q[0]; t[:] = q[0]
+        elif kind == 3 and ql > 8:
+            q[rng.integers(0, ql, 3)] = 4              # ambiguous bases
+        qs.append(q); ts.append(t)
+    qs.append(rng.integers(0, 4, 4990).astype(np.uint8)); ts.append(np.concatenate([rng.integers(0, 4, 50).astype(np.uint8), qs[-1][100:4000], rng.integers(0, 4, 60).astype(np.uint8)]))
+    pool = np.concatenate([np.concatenate([q, t]) for q, t in zip(qs, ts)])
+    tasks = (_lib.LLTask * len(qs))()
+    o = 0
+    for i, (q, t) in enumerate(zip(qs, ts)):
+        tasks[i].qlen, tasks[i].tlen, tasks[i].q_off, tasks[i].t_off = len(q), len(t), o, o + len(q)
+        o += len(q) + len(t)
+    opt = _lib.default_opt()
+    _lib.check(lib.mb_ll_batch(0, C.byref(opt), tasks, len(qs), _lib._ptr(pool), len(pool)))
+    n_pad = 0
+    for i, (q, t) in enumerate(zip(qs, ts)):
+        want = oracle.ksw_ll_i16(q, t)
+        assert (tasks[i].score, tasks[i].qe, tasks[i].te) == want, f"task {i} ({len(q)} x {len(t)}): GPU {(tasks[i].score, tasks[i].qe, tasks[i].te)} oracle {want}"
+        n_pad += want[1] >= len(q)
+    assert n_pad > 10        # the padded-column case really occurred
+
+
+def _inversion_reads(seed, g, n):
+    """Reads with one or two internal inversions (reverse-complemented blocks of 600-1500 bp)."""
+    from monica_b200 import synth
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        L = int(rng.integers(5000, 9000))
+        st = int(rng.integers(0, len(g) - L))
+        r = g[st:st + L].copy()
+        a = int(rng.integers(1500, 2500)); b = a + int(rng.integers(600, 1500))
+        r[a:b] = synth.revcomp(r[a:b])
+        if i % 3 == 0 and L > b + 3500:
+            a2 = b + int(rng.integers(1500, 2200)); b2 = a2 + int(rng.integers(600, 1200))
+            r[a2:b2] = synth.revcomp(r[a2:b2])
+        r = synth.mutate(rng, r, 0.03, 0.02, 0.02)
+        if i % 2:
+            r = synth.revcomp(r)
+        out.append(r)
+    return out
+
+
+def test_inversion_hits_and_region_pool_growth(oracle, lib, monkeypatch):
+    """mm_align1_inv: reads with internal inversions get the extra `inv` hit upstream produces between the two halves of a
+    split_inv Z-drop split (MAPQ from mm_set_inv_mapq).  Run once normally and once with no slack in the region pool
+    (MB_TEST_TIGHT_REGS), which forces the pool to grow before the first alignment round and before the inversion pass."""
+    from monica_b200 import synth
+    from monica_b200.mappy_shim import Aligner
+    names, seqs = synth.make_genomes(51, 2, 120000, strain_frac=0.0)
+    reads = _inversion_reads(52, seqs[0], 24) + synth.simulate_reads(53, seqs, 12, 3000, 0.10)[0]
+    al = Aligner(names=names, seqs=seqs, device=0)
+    oidx = oracle.Index(names, seqs)
+    cat, off = synth.concat_reads(reads)
+    want, _ = oidx.map_batch(cat, off, n_threads=os.cpu_count() or 4)
+    n_inv = sum(1 for hs in want for h in hs if h["cnt"] == 0)
+    assert n_inv >= 10, n_inv
+    for tight in (False, True):
+        if tight:
+            monkeypatch.setenv("MB_TEST_TIGHT_REGS", "1")
+        hits = al.map_batch(cat=cat, off=off)
+        per = hits.per_read()
+        for i in range(len(reads)):
+            _compare_hits(hits, per, i, want[i])
+        assert al.last_stats["n_inv"] >= n_inv
+    # an inversion hit is primary with the MAPQ of its neighbours: monica sees it as a second kept hit of the read
+    assert any(h["cnt"] == 0 and h["is_primary"] and h["mapq"] == 60 for hs in want for h in hs)
+
+
+def test_more_than_64_tied_chains(oracle, lib):
+    """Reads made of 70-90 copies of one reference segment: every copy is its own chain and all chains start on the same
+    reference position, so upstream's sorts of the chain list leave the insertion-sort range with tied keys (the unstable
+    radix permutation is part of the result).  Such reads take the `big` variants of the per-read kernels."""
+    from monica_b200 import synth
+    from monica_b200.mappy_shim import Aligner
+    names, seqs = synth.make_genomes(61, 2, 80000, strain_frac=0.0)
+    g = seqs[0]
+    rng = np.random.default_rng(62)
+    reads = [np.tile(g[5000:5150], 70), np.tile(g[9000:9200], 90), synth.revcomp(np.tile(g[12000:12160], 75)),
+             np.concatenate([np.tile(g[20000:20150], 40), np.tile(g[30000:30150], 45)]),
+             np.concatenate([g[int(s):int(s) + 160] for s in rng.integers(0, 70000, 80)])]        # 80 different loci: distinct keys, > 64 chains
+    reads += synth.simulate_reads(63, seqs, 6, 3000, 0.10)[0]
+    al = Aligner(names=names, seqs=seqs, device=0)
+    oidx = oracle.Index(names, seqs)
+    cat, off = synth.concat_reads(reads)
+    want, _ = oidx.map_batch(cat, off, n_threads=os.cpu_count() or 4)
+    assert max(len(w) for w in want) >= 5
+    hits = al.map_batch(cat=cat, off=off)
+    per = hits.per_read()
+    for i in range(len(reads)):
+        _compare_hits(hits, per, i, want[i])
+
+
+def test_thousands_of_zdrop_candidates_in_one_batch(oracle, lib):
+    """2,400 reads that each carry a ~300 bp insertion or deletion: every one of them sends a gap fill through the Z-drop
+    walk with a drop above zdrop_inv, i.e. through the inversion test (k_ztest_ll).  A fixed-size scratch pool used to abort
+    the whole batch at the 2,049th such task."""
+    from monica_b200 import synth
+    from monica_b200.mappy_shim import Aligner
+    names, seqs = synth.make_genomes(71, 2, 400000, strain_frac=0.0)
+    rng = np.random.default_rng(72)
+    g = seqs[0]
+    reads = []
+    for i in range(2400):
+        st = int(rng.integers(0, len(g) - 2600))
+        if i % 2:
+            r = np.concatenate([g[st:st + 1100], synth.random_genome(rng, int(rng.integers(250, 350))), g[st + 1100:st + 2200]])
+        else:
+            r = np.concatenate([g[st:st + 1100], g[st + 1100 + int(rng.integers(250, 350)):st + 2500]])
+        reads.append(synth.mutate(rng, r, 0.02, 0.01, 0.01))
+    al = Aligner(names=names, seqs=seqs, device=0)
+    oidx = oracle.Index(names, seqs)
+    cat, off = synth.concat_reads(reads)
+    want, _ = oidx.map_batch(cat, off, n_threads=os.cpu_count() or 4)
+    hits = al.map_batch(cat=cat, off=off)
+    per = hits.per_read()
+    for i in range(len(reads)):
+        _compare_hits(hits, per, i, want[i])
+    assert al.last_stats["n_dp_pass2"] > 2048
