@@ -1,15 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- mapped Gbases/s of the map-ont -> per-taxon-count hot path on N B200s (one process per GPU).
 
-A step = one pass of the hot path (sketch -> seed lookup -> chaining -> extension -> count) over this rank's batch of
-synthetic reads.  Workload at N=1 = BASELINE.json configs[1] (10 synthetic 5 Mb genomes, 100k simulated ONT reads, N50 8 kb,
-10 % error); at N>1 every rank maps its own 100k reads against its own index replica (weak scaling) and the per-target
-count vectors are combined with one NCCL all-reduce per step.
+A step = one pass of the hot path (sketch -> seed lookup -> chaining -> extension -> count -> all-reduce) over this rank's
+share of the synthetic read set.  Workloads are BASELINE.json's configs (`--config`):
 
-  value  whole-job Gbases/s with the reads already resident in HBM (mb_map_resident + mb_count_last)
-  e2e    the same through the C-ABI call a user makes with HOST buffers (mb_map_batch from pinned memory, hits copied back)
-  roofline   the dominant kernel (k_dp, integer pipe): DP cells/s from its own CUDA-event time vs the measured INT32 rate
-  cpu_baseline  the CPU oracle (a restatement of minimap2-2.17, NOT mappy) on the host cores, bounded sample
+  1  configs[1]  10 x 5 Mb genomes, 100k reads N50 8 kb, 10 % error            default at --gpus 1   (weak: per GPU)
+  2  configs[2]  100 genomes / 500 Mb database, 1 M reads, split over the GPUs    default at --gpus >1  (strong)
+  4  configs[4]  1,000 genomes / ~4 Gb index replicated, 50 kb reads at 15 %      (strong)
+
+Synthetic data (tools/synth): 20 % of the genomes are strain copies of others (0.3 - 4 % divergence) and 7.5 % of the reads are
+hard cases (junk insertions, inversions, exact chimeras, junk), so that secondaries, MAPQ < 60, best_hit ties, second DP
+passes, Z-drop splits and inversion hits all occur in the timed batch (counts reported in `work_per_step`).
+
+  value         whole-job mapped Gbases/s with the reads already resident in HBM (Aligner.map_resident + count_last)
+  e2e           the same through the C-ABI call a user makes with HOST buffers (mb_map_batch from pinned memory, all hit
+                arrays + CIGARs copied back), reads sharded with monica_b200.shard, counts combined by mb_allreduce_counts
+  roofline      the dominant kernel (k_dp_fast, integer pipe) from its own CUDA-event time vs the measured INT32 rate, and the
+                other stages against their SURVEY 8(d) algorithmic bytes / operations
+  cpu_baseline  the CPU oracle (a restatement of minimap2-2.17, NOT mappy) on the host cores over the SAME batch (N = 1), which
+                doubles as the full-batch parity check: every hit field and CIGAR of the timed batch is compared (`parity_full`)
 
 `--impl reference` times that CPU restatement as the reference arm (mappy itself is not installable offline).
 """
@@ -28,13 +37,17 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools", "synth"))
 
-OPS_PER_CELL = 40   # algorithmic integer ops per DP cell of the two-piece affine recurrence with direction flags
-SIMD_WIDTH = 2      # 16x2 packed integer SIMD lanes per 32-bit lane-op (VIADD.16x2 / VIMNMX3.S16x2 / VIADDMNMX.S16x2)
-# DRAM traffic of the dominant kernel per DP cell, from the `ncu --set full` capture summarised in profiles/r01_summary_c.md:
-# (dram__bytes_read.sum + dram__bytes_write.sum) = 17.0 GB for the ~11.2 G cells of that k_dp_fast<7> launch.  Algorithmic bytes:
-# 1 direction byte per cell.
-NCU_TRAFFIC_BYTES_PER_CELL = 1.5
+OPS_PER_CELL = 40    # algorithmic integer ops per DP cell of the two-piece affine recurrence with direction flags
+SIMD_WIDTH = 2       # 16x2 packed integer SIMD lanes per 32-bit lane-op (VIADD.16x2 / VIMNMX3.S16x2 / VIADDMNMX.S16x2)
+OPS_PER_CHAIN_EVAL = 20  # integer ops per predecessor evaluated by mm_chain_dp's inner loop (2 subtractions, 5 compares, |dr-dq|, min, ilog2, the gap-cost product, 2 adds, max / skip bookkeeping)
+
+CONFIGS = {
+    1: dict(name="configs[1]", genomes=10, genome_len=5_000_000, reads=100_000, per_gpu=True, n50=8000.0, sigma=0.6, error=0.10, min_len=500, max_len=0),
+    2: dict(name="configs[2]", genomes=100, genome_len=5_000_000, reads=1_000_000, per_gpu=False, n50=8000.0, sigma=0.6, error=0.10, min_len=500, max_len=0),
+    4: dict(name="configs[4]", genomes=1000, genome_len=4_000_000, reads=24_000, per_gpu=False, n50=50000.0, sigma=0.3, error=0.15, min_len=5000, max_len=250_000),
+}
 
 
 def parse_args():
@@ -43,49 +56,54 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--genomes", type=int, default=10)
-    ap.add_argument("--genome-len", type=int, default=5_000_000)
-    ap.add_argument("--reads", type=int, default=100_000, help="reads per GPU")
-    ap.add_argument("--n50", type=float, default=8000.0)
-    ap.add_argument("--error", type=float, default=0.10)
-    ap.add_argument("--cpu-sample", type=int, default=10000, help="reads in the CPU baseline sample")
+    ap.add_argument("--config", type=int, default=0, choices=[0, 1, 2, 4], help="BASELINE.json config (0: 1 at --gpus 1, else 2)")
+    ap.add_argument("--genomes", type=int, default=0)
+    ap.add_argument("--genome-len", type=int, default=0)
+    ap.add_argument("--reads", type=int, default=0, help="override the read count of the config")
+    ap.add_argument("--cpu-sample", type=int, default=10000, help="reads in the --impl reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parity-full", action="store_true", help="check every hit of the timed batch against the oracle also when it is not the default (N > 1, configs 2 / 4)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the streaming / aligner-API sections")
     ap.add_argument("--seed", type=int, default=20251018)
     return ap.parse_args()
 
 
-def workload_name(a):
-    return (f"{a.genomes} synthetic {a.genome_len / 1e6:g} Mb genomes (20% strain copies), {a.reads} simulated ONT reads per GPU, "
-            f"N50 {a.n50 / 1e3:g} kb, {a.error * 100:g}% error, map-ont")
+def config_of(a):
+    k = a.config or (1 if a.gpus == 1 else 2)
+    c = dict(CONFIGS[k]); c["id"] = k
+    if a.genomes:
+        c["genomes"] = a.genomes
+    if a.genome_len:
+        c["genome_len"] = a.genome_len
+    if a.reads:
+        c["reads"] = a.reads
+    return c
 
 
-def make_genomes(a):
-    from monica_b200 import synth
-    return synth.make_genomes(a.seed, a.genomes, a.genome_len, strain_frac=0.2)
+def workload_name(c, world):
+    reads = f"{c['reads']} simulated ONT reads per GPU" if c["per_gpu"] else f"{c['reads']} simulated ONT reads split over {world} GPU(s) by cumulative bases"
+    return (f"BASELINE {c['name']}: {c['genomes']} synthetic {c['genome_len'] / 1e6:g} Mb genomes (20% strain copies at 0.3-4% divergence), {reads}, "
+            f"N50 {c['n50'] / 1e3:g} kb, {c['error'] * 100:g}% error (4:3:3 sub:ins:del), 7.5% hard-case reads, map-ont")
 
 
-def _sim_block(args):
-    from monica_b200 import synth
-    seed, seqs, n, n50, err = args
-    return synth.simulate_reads_bulk(seed, seqs, n, n50, err)
-
-
-def make_reads(a, seqs, n_reads, seed):
-    """Simulate in parallel worker processes (the generator is numpy-bound)."""
-    from concurrent.futures import ProcessPoolExecutor
-    block = 5000
-    jobs = [(seed * 1000 + i, seqs, min(block, n_reads - s), a.n50, a.error) for i, s in enumerate(range(0, n_reads, block))]
-    nproc = max(1, min(len(jobs), (os.cpu_count() or 4) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
-    if nproc > 1:
-        with ProcessPoolExecutor(nproc) as ex:
-            parts = list(ex.map(_sim_block, jobs))
-    else:
-        parts = [_sim_block(j) for j in jobs]
-    cat = np.concatenate([p[0] for p in parts])
-    lens = np.concatenate([np.diff(p[1]) for p in parts])
-    off = np.zeros(len(lens) + 1, dtype=np.int64)
-    off[1:] = np.cumsum(lens)
-    return cat, off
+def make_data(c, seed, rank, world, pinned_alloc=None):
+    """genomes (every rank: the index is replicated) and this rank's share of the reads."""
+    import mbsynth
+    from monica_b200 import shard
+    threads = max(1, (os.cpu_count() or 4) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))))
+    names, seqs, gcat, goff = mbsynth.make_genomes(seed, c["genomes"], c["genome_len"], strain_frac=0.2, threads=threads)
+    kw = dict(n50=c["n50"], error=c["error"], sigma=c["sigma"], min_len=c["min_len"], max_len=c["max_len"], threads=threads)
+    if c["per_gpu"]:           # weak scaling: every rank has its own read set of the stated size
+        rseed, n_all, lo, hi = seed + 1 + rank, c["reads"], 0, c["reads"]
+        off_all, cls_all = mbsynth.read_lengths(rseed, gcat, goff, n_all, **kw)
+    else:                      # strong scaling: one read set, split by cumulative bases (monica_b200.shard)
+        rseed, n_all = seed + 1, c["reads"]
+        off_all, cls_all = mbsynth.read_lengths(rseed, gcat, goff, n_all, **kw)
+        lo, hi = shard.split_by_bases(off_all, world)[rank]
+    total = int(off_all[hi] - off_all[lo])
+    out = pinned_alloc(total) if pinned_alloc else None
+    cat, off, _ = mbsynth.simulate_reads(rseed, gcat, goff, n_all, first=lo, count=hi - lo, off=off_all, out=out, **kw)
+    return names, seqs, gcat, goff, cat, off, cls_all[lo:hi], dict(read_seed=rseed, first_read=int(lo), n_reads_total=int(n_all))
 
 
 class ClockSampler:
@@ -143,104 +161,175 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def mapped_bases_from_oracle_hits(per_read_hits, lens, mapq_min=60):
-    """monica's filter + best_hit on oracle hits (for the CPU arms): bases of reads assigned to a target."""
-    tot = 0
-    for hits, L in zip(per_read_hits, lens):
-        kept = [(h["nm"], h["mlen"]) for h in hits if h["is_primary"] and h["mapq"] >= mapq_min]
-        if not kept:
-            continue
-        if len(kept) > 1:
-            best, margin = float("inf"), 0
-            for nm, ml in kept:
-                r = nm / ml
-                if r <= best:
-                    margin, best = best - r, r
-            if not margin:
-                continue
-        tot += int(L)
-    return tot
-
-
+# ------------------------------------------------------------------------------------------------------------------
+# CPU side: the oracle as the checker and as the timed CPU baseline (the only places bench.py touches oracle/)
+# ------------------------------------------------------------------------------------------------------------------
 PARITY_FIELDS = ["rid", "rev", "qs", "qe", "rs", "re", "mapq", "mlen", "blen", "nm", "dp_max", "is_primary"]
 
 
-def parity_vs_oracle(gpu_aligner, cat, off, oracle_hits):
-    """The CPU-baseline sample mapped by the CUDA path, compared hit for hit (fields + CIGAR) with the oracle's result:
-    the oracle used as the checker, never on the measured path."""
-    hits = gpu_aligner.map_batch(cat=cat, off=off)
-    per = hits.per_read()
-    bad_reads, n_hits = 0, 0
-    for i, want in enumerate(oracle_hits):
-        got = per[i]
-        ok = len(want) == len(got)
-        if ok:
-            for w, g in zip(want, got):
-                n_hits += 1
-                if any(int(getattr(hits, f)[g]) != int(w[f]) for f in PARITY_FIELDS) or not np.array_equal(hits.cigar(g), w["cigar"]):
-                    ok = False
-                    break
-        bad_reads += 0 if ok else 1
-    return {"reads": len(oracle_hits), "hits_compared": n_hits, "reads_differing": bad_reads,
-            "fields": PARITY_FIELDS + ["cigar"], "against": "CPU restatement of minimap2-2.17 (oracle/), not mappy"}
+def monica_classes(fields, hit_off, lens, mapq_min=60):
+    """monica's filter + best_hit over hits given as arrays: per-read class (0 unmapped, 1 mapped, 2 ambiguous), vectorised
+    except for the few reads that keep two or more hits."""
+    n = len(hit_off) - 1
+    keep = (fields["is_primary"] != 0) & (fields["mapq"] >= mapq_min)
+    owner = np.repeat(np.arange(n), np.diff(hit_off))
+    n_kept = np.bincount(owner[keep], minlength=n)
+    cls = (n_kept > 0).astype(np.int8)
+    kidx = np.nonzero(keep)[0]
+    ko = owner[kidx]
+    for r in np.nonzero(n_kept >= 2)[0]:
+        hs = kidx[np.searchsorted(ko, r, "left"):np.searchsorted(ko, r, "right")]
+        best, margin = float("inf"), 0
+        for h in hs:
+            ratio = float(fields["nm"][h]) / fields["mlen"][h]
+            if ratio <= best:
+                margin, best = best - ratio, ratio
+        if not margin:
+            cls[r] = 2
+    return cls
 
 
-def cpu_arm(a, names, seqs, n_sample, steps, warmup, gpu_aligner=None):
-    """Time the CPU restatement on a bounded sample with all host threads; returns (Gbases/s mapped, info)."""
+def parity_full(gpu_hits, soa):
+    """Every hit of the batch: the fields north_star names (+ NM, mlen, blen, dp_max) and the CIGARs, GPU vs oracle."""
+    n = len(soa["hit_off"]) - 1
+    want_n = np.diff(soa["hit_off"])
+    got_n = np.bincount(gpu_hits.read_idx, minlength=n) if gpu_hits.n else np.zeros(n, np.int64)
+    bad = want_n != got_n
+    if not bad.any() and gpu_hits.n:
+        owner = gpu_hits.read_idx
+        diff = np.zeros(gpu_hits.n, dtype=bool)
+        for f in PARITY_FIELDS + ["n_cigar"]:
+            diff |= getattr(gpu_hits, f) != soa["fields"][f]
+        if not diff.any():
+            if len(gpu_hits.cigar_pool) != len(soa["cigar"]):
+                diff[:] = True
+            else:
+                wd = gpu_hits.cigar_pool != soa["cigar"]
+                if wd.any():
+                    hit_of_word = np.repeat(np.arange(gpu_hits.n), gpu_hits.n_cigar)
+                    diff[np.unique(hit_of_word[wd])] = True
+        bad[np.unique(owner[diff])] = True
+    else:   # a different hit count somewhere: compare read by read where the counts agree
+        pass
+    return {"reads": int(n), "hits_compared": int(gpu_hits.n), "differing": int(bad.sum()), "fields": PARITY_FIELDS + ["cigar"],
+            "against": "CPU restatement of minimap2-2.17 (oracle/), not mappy"}
+
+
+def cpu_arm_full(al, names, seqs, cat, off, threads, mode_counts):
+    """The oracle over the whole batch, timed (the CPU baseline) and used as the checker (parity_full + per-taxon counts)."""
     from oracle import oracle as O
     O.build()
-    cat, off = make_reads(a, seqs, n_sample, a.seed + 777)
-    oidx = O.Index(names, seqs)
-    cores = os.cpu_count() or 1
-    lens = np.diff(off)
-    hits, _ = oidx.map_batch(cat, off, n_threads=cores)   # one untimed pass also yields the mapped-base count
-    mapped = mapped_bases_from_oracle_hits(hits, lens)
-    parity = parity_vs_oracle(gpu_aligner, cat, off, hits) if gpu_aligner is not None else None
-    for _ in range(max(0, warmup - 1)):
-        oidx.map_batch_raw(cat, off, n_threads=cores)
-    times, cells = [], 0
-    for _ in range(steps):
-        t0 = time.perf_counter()
-        tot = oidx.map_batch_raw(cat, off, n_threads=cores)
-        times.append(time.perf_counter() - t0)
-        cells = tot["dp_cells"]
-    dt = float(np.mean(times))
-    # monica's own default is 3 mapping threads (monica.py:92): one pass over a third of the sample at that width
-    n3 = max(1, n_sample // 3)
-    off3 = off[:n3 + 1]
     t0 = time.perf_counter()
-    oidx.map_batch_raw(cat[:int(off3[-1])], off3, n_threads=min(3, cores))
+    oidx = O.Index(names, seqs)
+    t_index = time.perf_counter() - t0
+    soa = oidx.map_batch_soa(cat, off, n_threads=threads)
+    lens = np.diff(off)
+    cls = monica_classes(soa["fields"], soa["hit_off"], lens)
+    mapped = float(lens[cls == 1].sum())
+    hits = al.map_batch(cat=cat, off=off)
+    par = parity_full(hits, soa)
+    # per-taxon counts, all three modes: monica's own rule over the oracle's hits vs the device count kernel
+    counts_ok = True
+    for mode in ("basic", "query_length", "matching"):
+        got, ncls, rcls, rbest = al.count(hits, 60, mode)
+        want = np.zeros(al.n_seq, dtype=np.int64)
+        keep = (soa["fields"]["is_primary"] != 0) & (soa["fields"]["mapq"] >= 60)
+        owner = np.repeat(np.arange(len(lens)), np.diff(soa["hit_off"]))
+        # winner of every mapped read = its kept hit with the smallest NM/mlen (last one on ties of non-minimal values cannot occur for class 1)
+        kidx = np.nonzero(keep)[0]
+        ratio = soa["fields"]["nm"][kidx].astype(np.float64) / np.maximum(soa["fields"]["mlen"][kidx], 1)
+        ko = owner[kidx]
+        order = np.lexsort((-kidx, ratio, ko))          # per read: smallest ratio first, the LAST hit first among equals
+        first = np.ones(len(order), dtype=bool); first[1:] = ko[order][1:] != ko[order][:-1]
+        win = kidx[order][first]
+        wr = ko[order][first]
+        m = cls[wr] == 1
+        win, wr = win[m], wr[m]
+        inc = np.ones(len(win), np.int64) if mode == "basic" else lens[wr].astype(np.int64) if mode == "query_length" else soa["fields"]["mlen"][win].astype(np.int64)
+        np.add.at(want, soa["fields"]["rid"][win], inc)
+        counts_ok &= bool(np.array_equal(want, got)) and bool(np.array_equal(rcls, cls))
+    par["per_taxon_counts_equal_all_modes"] = counts_ok
+    hits.free()
+    # monica's own default is 3 mapping threads (monica.py:92): one pass over a tenth of the batch at that width
+    n3 = max(1, (len(off) - 1) // 10)
+    t0 = time.perf_counter()
+    oidx.map_batch_raw(cat[:int(off[n3])], np.ascontiguousarray(off[:n3 + 1]), n_threads=min(3, threads))
     dt3 = time.perf_counter() - t0
-    mapped3 = mapped_bases_from_oracle_hits(hits[:n3], lens[:n3])
-    return mapped / dt / 1e9, dict(cores=cores, sample=f"{n_sample} reads / {int(off[-1])} bases of the same workload per step",
-                                   seconds_per_step=dt, total_gbases_per_s=float(off[-1]) / dt / 1e9, gcups=cells / dt / 1e9, parity=parity,
-                                   gbases_per_s_3_threads=mapped3 / dt3 / 1e9)
+    info = dict(cores=threads, sample=f"the whole timed batch: {len(off) - 1} reads / {int(off[-1])} bases, one pass", seconds_per_step=soa["seconds"],
+                total_gbases_per_s=float(off[-1]) / soa["seconds"] / 1e9, gcups=soa["totals"]["dp_cells"] / soa["seconds"] / 1e9,
+                gbases_per_s_3_threads=float(lens[:n3][cls[:n3] == 1].sum()) / dt3 / 1e9, index_build_s=t_index, parity=par,
+                oracle_totals=soa["totals"])
+    return mapped / soa["seconds"] / 1e9, info
+
+
+def config0_cpu_aligner_loop(seed):
+    """BASELINE configs[0] end to end on the CPU: monica's per-record aligner loop (this repo's mirror of aligner.py, which the
+    tests pin to the unmodified reference) over an oracle-backed `mappy` on 1 x 100 kb reference, 1,000 reads of 5 kb mean."""
+    import contextlib
+    import shutil
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import standin
+    from monica_b200 import aligner as mirror, synth
+    names, seqs = synth.make_genomes(seed, 1, 100_000, strain_frac=0.0)
+    reads, _ = synth.simulate_reads(seed + 1, seqs, 1000, 5000, 0.10)
+    tmp = tempfile.mkdtemp(prefix="monica_b200_c0_")
+    try:
+        synth.write_fastq(os.path.join(tmp, "c0.fastq"), reads)
+        idx = standin.OracleAligner(names=names, seqs=[s.tobytes() for s in seqs])
+        bases = int(sum(len(r) for r in reads))
+        cwd = os.getcwd()
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(sys.stderr):
+            res = mirror.multi_threaded_aligner(tmp, ["oracle"], mode="query_length", n_threads=1, output_folder=tmp, index_loader_fn=lambda p: idx)
+        dt = time.perf_counter() - t0
+        os.chdir(cwd)
+        got = sum(sum(c.values()) for c in res["c0"].values()) if res else 0
+        return {"workload": "BASELINE configs[0]: 1 x 100 kb reference, 1,000 reads (5 kb mean), per-record aligner loop over the oracle-backed mappy stand-in, 1 thread",
+                "seconds": dt, "gbases_per_s": got / dt / 1e9, "bases": bases}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    names, seqs = make_genomes(a)
-    v, info = cpu_arm(a, names, seqs, a.cpu_sample, a.steps, a.warmup)
+    from oracle import oracle as O
+    import mbsynth
+    O.build()
+    c = config_of(a)
+    world = a.gpus
+    threads = os.cpu_count() or 1
+    names, seqs, gcat, goff = mbsynth.make_genomes(a.seed, c["genomes"], c["genome_len"], strain_frac=0.2)
+    n = min(a.cpu_sample, c["reads"])
+    cat, off, _ = mbsynth.simulate_reads(a.seed + 1, gcat, goff, c["reads"], first=0, count=n, n50=c["n50"], error=c["error"], sigma=c["sigma"],
+                                         min_len=c["min_len"], max_len=c["max_len"])
+    oidx = O.Index(names, seqs)
+    soa = oidx.map_batch_soa(cat, off, n_threads=threads)
+    lens = np.diff(off)
+    mapped = float(lens[monica_classes(soa["fields"], soa["hit_off"], lens) == 1].sum())
+    for _ in range(max(0, a.warmup - 1)):
+        oidx.map_batch_raw(cat, off, n_threads=threads)
+    times, cells = [], 0
+    for _ in range(a.steps):
+        t0 = time.perf_counter()
+        tot = oidx.map_batch_raw(cat, off, n_threads=threads)
+        times.append(time.perf_counter() - t0)
+        cells = tot["dp_cells"]
+    dt = float(np.mean(times))
+    v = mapped / dt / 1e9
     out = {
         "impl": "reference", "metric": "mapped Gbases/s", "value": v, "unit": "Gbases/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": info["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak" if c["per_gpu"] else "strong", "vs_baseline": None,
         "dtype": "int8 DP / uint64 hashing", "data": "synthetic",
-        "config": {"workload": workload_name(a), "note": "CPU restatement of minimap2-2.17 map-ont (oracle/, SSE4.1 DP core), NOT mappy: mappy is not installable offline"},
-        "cpu_baseline": {"value": v, "unit": "Gbases/s", "cores": info["cores"], "kind": "port", "sample": info["sample"],
-                         "total_gbases_per_s": info["total_gbases_per_s"], "gcups": info["gcups"],
-                         "value_3_threads": info["gbases_per_s_3_threads"]},
+        "config": {"workload": workload_name(c, world), "note": "CPU restatement of minimap2-2.17 map-ont (oracle/, SSE4.1 DP core), NOT mappy: mappy is not installable offline"},
+        "cpu_baseline": {"value": v, "unit": "Gbases/s", "cores": threads, "kind": "port", "sample": f"the first {n} reads / {int(off[-1])} bases of the same workload per step",
+                         "total_gbases_per_s": float(off[-1]) / dt / 1e9, "gcups": cells / dt / 1e9},
         "e2e": {"value": v, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out))
     return 0
-
-
-class CudaArray:
-    """zero-copy torch view of a raw device pointer (__cuda_array_interface__)."""
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
 
 
 def main():
@@ -249,7 +338,7 @@ def main():
         return run_reference(a)
     import torch
     import torch.distributed as dist
-    from monica_b200 import _lib
+    from monica_b200 import _lib, shard
     from monica_b200.mappy_shim import Aligner
 
     rank = int(os.environ.get("RANK", "0"))
@@ -258,53 +347,50 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        try:   # spread the ranks' host threads over the cores (H2D staging and result copies of 8 ranks otherwise pile up on the same ones)
+            ncpu = os.cpu_count() or 1
+            per = max(1, ncpu // int(os.environ.get("LOCAL_WORLD_SIZE", str(world))))
+            os.sched_setaffinity(0, set(range(local * per, min(ncpu, (local + 1) * per))))
+        except Exception:
+            pass
     torch.cuda.set_device(local)
     L = _lib.lib()
+    c = config_of(a)
 
-    names, seqs = make_genomes(a)
+    def pinned_alloc(nbytes):
+        t = torch.empty(max(1, nbytes), dtype=torch.uint8, pin_memory=True)
+        pinned_alloc.keep.append(t)
+        return t.numpy()
+    pinned_alloc.keep = []
+
+    t0 = time.perf_counter()
+    names, seqs, gcat, goff, cat, off, cls_synth, seeds = make_data(c, a.seed, rank, world, pinned_alloc)
+    t_data = time.perf_counter() - t0
     t0 = time.perf_counter()
     al = Aligner(names=names, seqs=seqs, device=local)
     t_index = time.perf_counter() - t0
-    cat_np, off = make_reads(a, seqs, a.reads, a.seed + 1 + rank)
     n_reads, total_bases = len(off) - 1, int(off[-1])
-    # pinned host copy of the reads for the e2e leg
-    pinned = torch.empty(total_bases, dtype=torch.uint8, pin_memory=True)
-    pinned.numpy()[:] = cat_np
-    cat = pinned.numpy()
-    del cat_np
     n_seq = al.n_seq
     opt = al.opt
-    counts = np.zeros(n_seq, dtype=np.int64)
-    ncls = np.zeros(3, dtype=np.int64)
+    comm = shard.Comm(local) if world > 1 else None      # the library's own NCCL communicator (mb_comm_*), id passed through torch.distributed
 
-    reads_dev = C.c_void_p()
-    _lib.check(L.mb_reads_upload(al.handle(), _lib._ptr(cat), _lib._ptr(off), n_reads, C.byref(reads_dev)))
-
-    def allreduce_counts():
-        if world == 1:
-            return counts.copy()
-        t = torch.as_tensor(CudaArray(L.mb_count_device_ptr(al.handle()), n_seq), device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)     # one NCCL all-reduce of the int64[n_targets] vector
-        return t.cpu().numpy()
+    reads_dev = al.reads_upload(cat, off)
 
     def step_value():
-        h = C.c_void_p(); st = _lib.Stats()
-        _lib.check(L.mb_map_resident(al.handle(), C.byref(opt), reads_dev, 0, C.byref(h), C.byref(st)))
-        _lib.check(L.mb_count_last(al.handle(), 60, 1, _lib._ptr(counts), _lib._ptr(ncls)))
-        L.mb_hits_free(h)
-        tot = allreduce_counts()
-        return st, tot
+        al.map_resident(reads_dev, n_reads, want_hits=False)
+        st = dict(al.last_stats)
+        counts, ncls = al.count_last(60, "query_length", comm=comm)     # device-resident count + the one NCCL all-reduce
+        return st, counts, ncls
 
     def step_e2e():
         h = C.c_void_p(); st = _lib.Stats()
         _lib.check(L.mb_map_batch(al.handle(), C.byref(opt), _lib._ptr(cat), _lib._ptr(off), n_reads, C.byref(h), C.byref(st)))
-        _lib.check(L.mb_count_last(al.handle(), 60, 1, _lib._ptr(counts), _lib._ptr(ncls)))
         nh = L.mb_hits_n(h)
         nc = C.c_int64(0); L.mb_hits_cigar_pool(h, C.byref(nc))
         d2h = nh * 4 * len(_lib.HIT_FIELDS) + nh * 8 + nc.value * 4 + n_reads * 4 + (n_reads + 1) * 8 + n_seq * 8 + 24
         L.mb_hits_free(h)
-        tot = allreduce_counts()
-        return st, tot, d2h
+        counts, ncls = al.count_last(60, "query_length", comm=comm)
+        return st.as_dict(), counts, ncls, d2h
 
     def barrier():
         torch.cuda.synchronize()
@@ -312,18 +398,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
+    def reduce_over_ranks(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
     # Device timing: CUDA events recorded on the library's own stream (the one every kernel of the step is launched on),
@@ -347,7 +426,7 @@ def main():
         wall = time.perf_counter() - t0
         dev = e0.elapsed_time(e1) * 1e-3
         timed.each_ms = [a_.elapsed_time(b_) for a_, b_ in zip([e0] + marks[:-1], marks)]   # this rank's steps one by one (diagnostic)
-        return max_over_ranks(dev), max_over_ranks(wall), outs
+        return reduce_over_ranks(dev, dist.ReduceOp.MAX), reduce_over_ranks(wall, dist.ReduceOp.MAX), outs
 
     # ---- value leg: resident inputs ----
     sampler = ClockSampler(local)
@@ -358,11 +437,10 @@ def main():
     dt_value, wall_value, outs = timed(step_value, a.steps)
     each_value_ms = list(timed.each_ms)
     clocks = sampler.stop()
-    stats = [o[0].as_dict() for o in outs]
-    tot_counts = outs[-1][1]
-    mapped_bases_rank = float(counts.sum())            # this rank's bases assigned to a target (query_length mode)
-    mapped_bases_all = float(tot_counts.sum()) if world > 1 else mapped_bases_rank
-    total_bases_all = sum_over_ranks(float(total_bases))
+    stats = [o[0] for o in outs]
+    tot_counts, ncls_full = outs[-1][1].copy(), outs[-1][2].copy()     # global after the all-reduce
+    mapped_bases_all = float(tot_counts.sum())
+    total_bases_all = reduce_over_ranks(float(total_bases), dist.ReduceOp.SUM)
     value = mapped_bases_all * a.steps / dt_value / 1e9
 
     # ---- e2e leg: host buffers through the C ABI ----
@@ -370,43 +448,61 @@ def main():
         step_e2e()
     dt_e2e, wall_e2e, outs_e = timed(step_e2e, a.steps)
     dt_e2e = max(dt_e2e, wall_e2e)                     # host copies of the result happen after the last event: take the wall clock
-    tot_counts_e, d2h = outs_e[-1][1], outs_e[-1][2]
+    tot_counts_e, d2h = outs_e[-1][1], outs_e[-1][3]
     if not np.array_equal(np.asarray(tot_counts_e), np.asarray(tot_counts)):
         raise RuntimeError("per-target counts of the end-to-end path (mb_map_batch, piecewise upload) differ from the resident path")
-    e2e_value = float(tot_counts_e.sum() if world > 1 else counts.sum()) * a.steps / dt_e2e / 1e9
-
-    ncls_full = ncls.copy()
+    e2e_value = float(tot_counts_e.sum()) * a.steps / dt_e2e / 1e9
+    e2e_stats = outs_e[-1][0]
 
     # ---- streaming mode (BASELINE configs[3]): 4,000-read batches from host memory, mapped and counted one at a time ----
     streaming = None
-    if rank == 0 and n_reads >= 8000:
+    if rank == 0 and n_reads >= 8000 and not a.no_extras and c["id"] == 1:
         sb = 4000
-        lat = []
         nb = min(25, n_reads // sb)
-        for b in range(nb + 2):
+        counts_s, ncls_s = np.zeros(n_seq, np.int64), np.zeros(3, np.int64)
+
+        def one_batch(b):
             lo = (b % nb) * sb
             o = np.ascontiguousarray(off[lo:lo + sb + 1] - off[lo])
             seg = cat[off[lo]:off[lo + sb]]
             t0 = time.perf_counter()
             h = C.c_void_p(); st_s = _lib.Stats()
             _lib.check(L.mb_map_batch(al.handle(), C.byref(opt), _lib._ptr(seg), _lib._ptr(o), sb, C.byref(h), C.byref(st_s)))
-            _lib.check(L.mb_count_last(al.handle(), 60, 1, _lib._ptr(counts), _lib._ptr(ncls)))
+            cnt = np.zeros(n_seq, np.int64); ncl = np.zeros(3, np.int64)
+            _lib.check(L.mb_count_last(al.handle(), 60, 1, _lib._ptr(cnt), _lib._ptr(ncl)))
             L.mb_hits_free(h)
+            return (time.perf_counter() - t0) * 1e3, int(o[-1]), cnt
+        lat = []
+        for b in range(nb + 2):
+            ms, _, _ = one_batch(b)
             if b >= 2:
-                lat.append((time.perf_counter() - t0) * 1e3)
+                lat.append(ms)
         lat = np.sort(np.array(lat))
+        # two calling threads, each with its own stream / arena in the library: batch i+1 is uploaded, sketched and chained while
+        # batch i sits in its DP kernels (the DP stage of one device is serialised by the library)
+        from multiprocessing.dummy import Pool
+        with Pool(2) as pool:
+            pool.map(one_batch, range(4))                                   # warm both threads' contexts
+            t0 = time.perf_counter()
+            res = pool.map(one_batch, range(nb), chunksize=1)
+            dt = time.perf_counter() - t0
+        bases = sum(r[1] for r in res)
+        mapped_s = float(sum(r[2].sum() for r in res))
         streaming = {"batch_reads": sb, "batches": int(len(lat)), "latency_ms_p50": float(np.percentile(lat, 50)), "latency_ms_p99": float(np.percentile(lat, 99)),
-                     "latency_ms_max": float(lat[-1]), "note": "host buffers in, hit arrays + CIGARs and per-target counts out, wall clock per batch"}
+                     "latency_ms_max": float(lat[-1]), "sustained_total_gbases_per_s_2_threads": bases / dt / 1e9, "sustained_mapped_gbases_per_s_2_threads": mapped_s / dt / 1e9,
+                     "note": "host buffers in, hit arrays + CIGARs and per-target counts out, wall clock per batch; sustained = two calling threads overlapping consecutive batches"}
 
     # ---- monica's own entry point: multi_threaded_aligner on a FASTQ file (native ingest -> map -> count -> routed files) ----
     aligner_e2e = None
-    if rank == 0 and world == 1 and n_reads >= 8000:
+    if rank == 0 and world == 1 and n_reads >= 8000 and not a.no_extras and c["id"] == 1:
         try:
+            import contextlib
             import shutil
             import tempfile
             from monica_b200 import aligner as galigner
             nfq = min(20000, n_reads)
-            tmp = tempfile.mkdtemp(prefix="monica_b200_bench_")
+            shm = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+            tmp = tempfile.mkdtemp(prefix="monica_b200_bench_", dir=shm)
             q = os.path.join(tmp, "sample.fastq")
             with open(q, "wb") as fh:                       # untimed: write the FASTQ the aligner will consume
                 qual = b"I" * int(np.diff(off[:nfq + 1]).max())
@@ -416,25 +512,26 @@ def main():
             fq_bases = int(off[nfq])
             cwd = os.getcwd()
             t0 = time.perf_counter()
-            import contextlib
             with contextlib.redirect_stdout(sys.stderr):    # the aligner prints progress like the reference; keep stdout to the one JSON line
                 res = galigner.multi_threaded_aligner(tmp, ["resident"], mode="query_length", n_threads=1, output_folder=tmp, index_loader_fn=lambda p: al)
             dt = time.perf_counter() - t0
             os.chdir(cwd)
-            got = sum(sum(c.values()) for c in res["sample"].values()) if res else 0
-            aligner_e2e = {"reads": nfq, "bases": fq_bases, "seconds": dt, "gbases_per_s": got / dt / 1e9, "mapped_bases": int(got),
+            got = sum(sum(cn.values()) for cn in res["sample"].values()) if res else 0
+            aligner_e2e = {"reads": nfq, "bases": fq_bases, "seconds": dt, "gbases_per_s": got / dt / 1e9, "total_gbases_per_s": fq_bases / dt / 1e9, "mapped_bases": int(got),
+                           "filesystem": "tmpfs (/dev/shm)" if shm else "default temp dir", "breakdown_s": getattr(galigner, "LAST_BREAKDOWN", None),
                            "note": "monica_b200.aligner.multi_threaded_aligner on one FASTQ file: parse, map, best_hit/count, write routed FASTQs, alignment.pkl"}
             shutil.rmtree(tmp, ignore_errors=True)
         except Exception as e:  # never sink the bench line
             aligner_e2e = {"error": repr(e)}
 
-    # ---- roofline of the dominant kernel (k_dp_fast: packed two-piece affine DP + traceback) ----
+    # ---- roofline of the dominant kernel (k_dp_fast: packed two-piece affine DP + traceback) and the other stages ----
     last = stats[-1]
     ms_fast = float(np.mean([s["ms_kdp_fast"] for s in stats]))
     cells_fast = float(np.mean([s["dp_cells"] - s["dp_cells_exact"] - s["dp_cells_ext"] for s in stats]))
     tiops = C.c_double(0)
     _lib.check(L.mb_int_peak(local, C.byref(tiops)))
     peak_gcups = tiops.value * 1e3 * SIMD_WIDTH / OPS_PER_CELL
+    peak_gcups_scalar = tiops.value * 1e3 / OPS_PER_CELL
     gcups = cells_fast / (ms_fast * 1e-3) / 1e9 if ms_fast > 0 else 0.0
     peaks = {}
     try:
@@ -442,67 +539,101 @@ def main():
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"
-    sketch_bytes = (last["n_bases"] + 16 * last["n_mini"]) * 2   # count + write passes, 1 B/base nt4 in, 16 B/minimizer out
-    seed_bytes = 32 * last["n_mini"] + 24 * last["n_anchor"] + 32 * last["n_anchor"]
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     stage_keys = ("ms_sketch", "ms_seed", "ms_chain", "ms_glue", "ms_dp", "ms_post", "ms_total", "ms_kdp", "ms_kdp_fast", "ms_kdp_exact", "ms_kdp_ext", "ms_d2h")
     stage_ms = {k: float(np.mean([s[k] for s in stats])) for k in stage_keys}
     n_fast_launches = max(1, int(last["n_kdp_fast"]))
+    Lb, M, A = float(last["n_bases"]), float(last["n_mini"]), float(last["n_anchor"])
+    traffic = None
+    try:   # measured DRAM bytes per DP cell of k_dp_fast from the committed `ncu --set full` capture of this round
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_kdp_fast_traffic.json")))
+        traffic = {"bytes_per_launch": tj["dram_bytes_per_cell"] * cells_fast / n_fast_launches, "dram_bytes_per_cell": tj["dram_bytes_per_cell"], "source": tj["source"]}
+    except Exception:
+        pass
+
+    def hbm_entry(bytes_, ms, note):
+        ach = bytes_ / (ms * 1e-3) / 1e9 if ms else None
+        return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak if ach else None, "algorithmic_bytes": bytes_, "ms": ms, "note": note}
+
+    def int_entry(units, ms, peak, unit, note):
+        ach = units / (ms * 1e-3) / 1e9 if ms else None
+        return {"bound": "int", "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak if ach and peak else None, "ms": ms, "note": note}
+    chain_evals = float(last["chain_cells"])
     roofline = {
         "kernel": "k_dp_fast<C> (two-piece affine gap-fill DP + traceback, ksw_extd2 equivalent, 2 tasks/warp in 16x2 SIMD)",
         "bound": "int", "achieved": gcups, "peak": peak_gcups, "unit": "GCUPS",
         "frac": gcups / peak_gcups if peak_gcups else None,
-        "traffic": NCU_TRAFFIC_BYTES_PER_CELL * cells_fast / n_fast_launches,
-        "traffic_note": "bytes per launch = ncu dram bytes/cell of the committed capture x cells per launch; algorithmic = 1 B/cell",
+        "traffic": traffic["bytes_per_launch"] if traffic else None,
+        "traffic_note": (f"ncu dram__bytes_read+write per DP cell ({traffic['dram_bytes_per_cell']:.2f} B, {traffic['source']}) x cells per launch; algorithmic = 1 B/cell" if traffic
+                         else "no committed ncu capture for this round"),
         "peak_source": f"measured INT32 add/max issue rate {tiops.value:.1f} Tlane-op/s on this GPU (mb_int_peak) x {SIMD_WIDTH} (16x2 SIMD) / {OPS_PER_CELL} int ops per cell",
         "cells_per_step": cells_fast, "ms_per_step": ms_fast, "launches_per_step": n_fast_launches,
         "share_of_step": ms_fast / stage_ms["ms_total"] if stage_ms["ms_total"] else None,
         "hbm_view": {"bound": "hbm", "achieved": cells_fast / (ms_fast * 1e-3) / 1e9 if ms_fast else None, "peak": hbm_peak, "unit": "GB/s",
                      "note": f"1 direction byte per cell streamed to HBM; peak {hbm_src}"},
         "other_kernels": {
-            "k_dp (exact ksw_extd2 emulation, overlapped on side streams)": {"bound": "int", "achieved": (float(np.mean([s["dp_cells_exact"] for s in stats])) / (stage_ms["ms_kdp_exact"] * 1e-3) / 1e9) if stage_ms["ms_kdp_exact"] else None, "unit": "GCUPS"},
-            "k_chain_dp": {"bound": "int", "achieved": (float(last["chain_cells"]) / (stage_ms["ms_chain"] * 1e-3) / 1e9) if stage_ms["ms_chain"] else None, "unit": "G predecessor evaluations/s"},
-            "k_sketch": {"bound": "hbm", "achieved": sketch_bytes / (stage_ms["ms_sketch"] * 1e-3) / 1e9 if stage_ms["ms_sketch"] else None,
-                         "peak": hbm_peak, "unit": "GB/s", "note": "stage time includes two scans and a host sync"},
-            "k_seed_lookup+fill+sort": {"bound": "hbm", "achieved": seed_bytes / (stage_ms["ms_seed"] * 1e-3) / 1e9 if stage_ms["ms_seed"] else None,
-                                        "peak": hbm_peak, "unit": "GB/s"},
+            "K1 sketch stage (encode/pack, k_sketch_par, k_sketch, scans, compaction)": hbm_entry(np.ceil(Lb / 4) + 16 * M, stage_ms["ms_sketch"], "SURVEY 8(d): ceil(L/4) + 16 M bytes; stage time incl. two scans and one host sync"),
+            "K2+K2b seed stage (k_seed_lookup, k_seed_fill, k_sort_anchors, k_sort_emul)": hbm_entry(32 * M + 24 * A + 32 * A, stage_ms["ms_seed"], "SURVEY 8(d): lookup 32 M + 24 A, sort 32 A bytes; random probes: latency-bound"),
+            "K3 k_chain_dp": int_entry(chain_evals * OPS_PER_CHAIN_EVAL, stage_ms["ms_chain"], tiops.value * 1e3, "G int-op/s",
+                                       f"{chain_evals:.4g} predecessor evaluations (the oracle counts the same loop) x {OPS_PER_CHAIN_EVAL} int ops, vs the measured INT32 rate"),
+            "K4 k_dp (exact ksw_extd2 block emulation, side streams)": int_entry(float(np.mean([s["dp_cells_exact"] for s in stats])), stage_ms["ms_kdp_exact"], peak_gcups_scalar, "GCUPS",
+                                                                              "int32 lanes (no 16x2 packing): peak = INT32 rate / 40 ops; summed launch times (launches overlap k_dp_fast)"),
+            "K4 k_dp_ext (end extensions, packed)": int_entry(float(np.mean([s["dp_cells_ext"] for s in stats])), stage_ms["ms_kdp_ext"], peak_gcups, "GCUPS", "summed launch times (launches overlap k_dp_fast)"),
         },
     }
 
-    out = None
-    if rank == 0:
-        cpu = None
-        if world == 1 and not a.no_cpu_baseline:
-            try:
-                v, info = cpu_arm(a, names, seqs, a.cpu_sample, 1, 1, gpu_aligner=al)
+    # ---- CPU side (rank 0 at N = 1, or every rank on request): baseline + full-batch parity ----
+    cpu, par_all = None, None
+    if not a.no_cpu_baseline and (world == 1 and c["id"] == 1 or a.parity_full):
+        try:
+            threads = max(1, (os.cpu_count() or 1) // max(1, world))
+            v, info = cpu_arm_full(al, names, seqs, cat, off, threads, None)
+            bad = reduce_over_ranks(float(info["parity"]["differing"]), dist.ReduceOp.SUM)
+            nrd = reduce_over_ranks(float(info["parity"]["reads"]), dist.ReduceOp.SUM)
+            par_all = {"reads": int(nrd), "bases": int(total_bases_all), "differing": int(bad), "per_taxon_counts_equal_all_modes": info["parity"]["per_taxon_counts_equal_all_modes"],
+                       "hits_compared_rank0": info["parity"]["hits_compared"], "fields": info["parity"]["fields"], "against": info["parity"]["against"]}
+            if rank == 0:
                 cpu = {"value": v, "unit": "Gbases/s", "cores": info["cores"], "kind": "port", "sample": info["sample"],
                        "total_gbases_per_s": info["total_gbases_per_s"], "gcups": info["gcups"], "value_3_threads": info["gbases_per_s_3_threads"],
-                       "note": "CPU restatement of minimap2-2.17 (SSE4.1 16-lane int8 DP core like upstream's ksw2, pthreads over reads), not mappy",
-                       "parity_on_sample": info["parity"]}
-            except Exception as e:  # the baseline must never sink the bench line
-                cpu = {"value": None, "unit": "Gbases/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+                       "oracle_index_build_s": info["index_build_s"],
+                       "note": "CPU restatement of minimap2-2.17 (SSE4.1 16-lane int8 DP core like upstream's ksw2, pthreads over reads), not mappy"}
+                if world == 1 and c["id"] == 1 and not a.no_extras:
+                    cpu["config0_aligner_loop"] = config0_cpu_aligner_loop(a.seed)
+        except Exception as e:  # the baseline must never sink the bench line
+            cpu = {"value": None, "unit": "Gbases/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e!r}"}
+
+    if rank == 0:
         out = {
             "metric": "mapped Gbases/s", "value": value, "unit": "Gbases/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": dt_value / a.steps * 1e3, "ms_per_step_wall": wall_value / a.steps * 1e3, "timing": "CUDA events on the launching stream, max over ranks", "ms_each_step_rank0": each_value_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": dt_value / a.steps * 1e3, "ms_per_step_wall": wall_value / a.steps * 1e3, "timing": "CUDA events on the launching stream, max over ranks", "ms_each_step_rank0": each_value_ms,
+            "higher_is_better": True, "scaling": "weak" if c["per_gpu"] else "strong", "vs_baseline": None,
             "dtype": "int16x2 DP (int8-range differences) / int32 chaining / uint64 hashing", "data": "synthetic",
-            "config": {"workload": workload_name(a), "reads_per_gpu": n_reads, "bases_per_gpu": total_bases, "l2": "inputs larger than L2 (no flush needed)",
-                       "index_hbm_bytes": int(L.mb_index_hbm_bytes(al.handle())), "index_build_s": t_index, "parallelism": f"reads sharded over {world} GPU(s), index replicated, 1 NCCL all-reduce of int64[{n_seq}] per step"},
+            "config": {"workload": workload_name(c, world), "baseline_config": c["name"], "reads_rank0": n_reads, "bases_rank0": total_bases, "bases_all_ranks": int(total_bases_all),
+                       "seeds": dict(genomes=a.seed, **seeds), "l2": "inputs larger than L2 (no flush needed)",
+                       "index_hbm_bytes": int(L.mb_index_hbm_bytes(al.handle())), "index_build_s": t_index, "data_generation_s": t_data, "mid_occ": int(al.mid_occ),
+                       "scratch_hbm_bytes_per_piece": int(last["arena_bytes"]), "sequential_pieces": int(last["n_pieces"]) or 1,
+                       "parallelism": f"reads sharded over {world} GPU(s) (monica_b200.shard), index replicated, 1 NCCL all-reduce of int64[{n_seq + 3}] per step (mb_allreduce_counts)"},
             "total_gbases_per_s": total_bases_all * a.steps / dt_value / 1e9,
             "mapped_fraction": mapped_bases_all / total_bases_all if total_bases_all else None,
             "e2e": {"value": e2e_value, "unit": "Gbases/s", "h2d_bytes_per_step": int(total_bases + 8 * (n_reads + 1)), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": dt_e2e / a.steps * 1e3},
+                    "ms_per_step": dt_e2e / a.steps * 1e3, "ms_h2d_exposed": e2e_stats["ms_h2d"], "ms_d2h": e2e_stats["ms_d2h"]},
             "gpu_launches": int(sum(s["n_launches"] for s in stats)) + a.steps,
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "parity_full": par_all,
             "streaming": streaming,
             "aligner_e2e": aligner_e2e,
             "stage_ms": stage_ms,
-            "work_per_step": {k: last[k] for k in ("n_reads", "n_bases", "n_mini", "n_anchor", "n_regs", "n_dp_tasks", "n_dp_pass2", "dp_cells", "n_hits", "n_rounds", "n_fast_tasks", "n_exact_tasks", "n_ext_tasks", "dp_cells_exact", "dp_cells_ext", "chain_cells")},
-            "read_classes": {"mapped": int(ncls_full[0]), "unmapped": int(ncls_full[1]), "ambiguous": int(ncls_full[2])},
+            "work_per_step": dict({k: last[k] for k in ("n_reads", "n_bases", "n_mini", "n_anchor", "n_regs", "n_dp_tasks", "n_dp_pass2", "dp_cells", "n_hits", "n_rounds", "n_fast_tasks",
+                                                         "n_exact_tasks", "n_ext_tasks", "dp_cells_exact", "dp_cells_ext", "chain_cells", "n_inv")},
+                                  note="rank 0's share", synthetic_read_classes=dict(zip(("plain", "junk_insert", "inversion", "exact_chimera", "junk"), np.bincount(cls_synth, minlength=5).tolist()))),
+            "read_classes": {"mapped": int(ncls_full[0]), "unmapped": int(ncls_full[1]), "ambiguous": int(ncls_full[2]), "note": "all ranks (after the all-reduce)"},
         }
         print(json.dumps(out))
-    L.mb_reads_free(reads_dev)
+    al.reads_free(reads_dev)
+    if comm is not None:
+        comm.free()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -17,6 +17,8 @@
  *        fields hit.is_primary .mapq .ctg .NM .mlen monica/genomes/aligner.py:194-195,216-217
  *   mb_count
  *        best_hit + taxon/accession Counter update monica/genomes/aligner.py:225-263,328-339
+ *   mb_allreduce_counts
+ *        the additive merge of per-shard tallies    monica/genomes/aligner.py:282-302 (alignment_update)
  *   mb_sketch / mb_seed / mb_chain / mb_dp_batch / mb_ll_batch
  *        per-stage entry points for parity tests (no reference counterpart; stages of mm_map_frag)
  */
@@ -71,6 +73,8 @@ typedef struct {
 	float   ms_kdp_ext; int32_t n_inv; /* inversion hits produced (mm_align1_inv) */
 	int64_t arena_bytes;      /* device scratch handed out for this batch (largest piece) */
 	int32_t n_pieces, pad_;   /* sequential pieces the batch was cut into (memory budget) */
+	int64_t n_band_tasks, dp_cells_band; /* large / band-limited gap fills through k_dp_band */
+	float   ms_kdp_band; int32_t pad2_;
 } mb_stats_t;
 
 const char *mb_last_error(void);
@@ -136,6 +140,18 @@ int  mb_count_fetch(mb_index_t *idx, int64_t *counts);
  * them (float addition order of the sample total).  bpm[n_groups] = (count/len) / sum(count/len). */
 int  mb_normalize_last(mb_index_t *idx, const int32_t *group, int32_t n_groups, const double *group_len,
                        const int32_t *order, int32_t n_order, double *bpm);
+
+/* ---- multi-GPU: the one collective of the path ----
+ * Reads shard over one process per GPU with the index replicated; per-sample tallies merge additively (Counter.update,
+ * monica/genomes/aligner.py:288-292), so the only exchange is ONE all-reduce of the int64[n_seq] count vector (+ the three
+ * read-class counters), done with NCCL on the mapping stream on the device-resident vector of the calling thread's last
+ * mb_count / mb_count_last.  libnccl is bound at run time (dlopen "libnccl.so.2"); without it these calls fail loudly.
+ * mb_comm_unique_id: rank 0 makes the 128-byte NCCL id, the caller hands it to the other ranks over any channel. */
+typedef struct mb_comm mb_comm_t;
+int  mb_comm_unique_id(uint8_t id[128]);
+int  mb_comm_init(int device, int rank, int world, const uint8_t id[128], mb_comm_t **out);
+void mb_comm_free(mb_comm_t *comm);
+int  mb_allreduce_counts(mb_index_t *idx, mb_comm_t *comm, int64_t *counts, int64_t *n_class);
 
 /* ---- FASTQ ingest and routed writers (host side, no device needed) ----
  * mb_fastq_load      for seq_record in SeqIO.parse(sample, 'fastq')            monica/genomes/aligner.py:191,212

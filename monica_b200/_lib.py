@@ -40,7 +40,8 @@ class Stats(C.Structure):
                [(n, C.c_float) for n in ("ms_sketch", "ms_seed", "ms_sort", "ms_chain", "ms_glue", "ms_dp", "ms_post",
                                          "ms_total", "ms_h2d", "ms_d2h")] + [("n_launches", C.c_int64), ("ms_kdp", C.c_float), ("n_kdp", C.c_int32), ("ms_kdp_fast", C.c_float), ("ms_kdp_exact", C.c_float),
                   ("n_fast_tasks", C.c_int64), ("n_exact_tasks", C.c_int64), ("chain_cells", C.c_int64), ("dp_cells_exact", C.c_int64), ("n_kdp_fast", C.c_int64), ("n_ext_tasks", C.c_int64), ("dp_cells_ext", C.c_int64), ("ms_kdp_ext", C.c_float), ("n_inv", C.c_int32),
-                  ("arena_bytes", C.c_int64), ("n_pieces", C.c_int32), ("pad_", C.c_int32)]
+                  ("arena_bytes", C.c_int64), ("n_pieces", C.c_int32), ("pad_", C.c_int32),
+                  ("n_band_tasks", C.c_int64), ("dp_cells_band", C.c_int64), ("ms_kdp_band", C.c_float), ("pad2_", C.c_int32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -72,6 +73,7 @@ SYMBOLS = [
     "mb_map_batch", "mb_map_batch_ex", "mb_reads_upload", "mb_reads_free", "mb_map_resident",
     "mb_hits_n", "mb_hits_field", "mb_hits_cigar_off", "mb_hits_cigar_pool", "mb_hits_rep_len", "mb_hits_free",
     "mb_count", "mb_count_last", "mb_count_device_ptr", "mb_count_fetch", "mb_normalize_last",
+    "mb_comm_unique_id", "mb_comm_init", "mb_comm_free", "mb_allreduce_counts",
     "mb_sketch", "mb_seed", "mb_chain", "mb_dp_batch", "mb_ll_batch", "mb_int_peak", "mb_stream",
     "mb_fastq_load", "mb_fastq_n", "mb_fastq_seqs", "mb_fastq_header", "mb_fastq_ids_unique", "mb_fastq_route", "mb_fastq_free",
     "mb_db_build",
@@ -149,6 +151,11 @@ def lib():
     L.mb_count_fetch.argtypes = [vp, vp]
     L.mb_normalize_last.argtypes = [vp, vp, i32, vp, vp, i32, vp]
     L.mb_db_build.argtypes = [C.c_char_p, i32, vp, vp, vp]
+    L.mb_comm_unique_id.argtypes = [vp]
+    L.mb_comm_init.argtypes = [C.c_int, C.c_int, C.c_int, vp, C.POINTER(vp)]
+    L.mb_comm_free.argtypes = [vp]
+    L.mb_comm_free.restype = None
+    L.mb_allreduce_counts.argtypes = [vp, vp, vp, vp]
     L.mb_sketch.argtypes = [C.c_int, vp, vp, i32, C.c_int, C.c_int, vp, i64, vp]
     L.mb_seed.argtypes = [vp, C.POINTER(Opt), vp, vp, i32, vp, i64, vp, vp]
     L.mb_chain.argtypes = [C.c_int, C.POINTER(Opt), vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]

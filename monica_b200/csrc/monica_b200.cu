@@ -12,6 +12,7 @@
 #include <mutex>
 #include <thread>
 #include <zlib.h>
+#include <dlfcn.h>
 #include "common.cuh"
 #include "sketch.cuh"
 #include "seed.cuh"
@@ -22,6 +23,7 @@
 #include "align2.cuh"
 #include "dp_fast.cuh"
 #include "dp_ext.cuh"
+#include "dp_band.cuh"
 
 thread_local std::string g_mb_err;
 static thread_local std::chrono::steady_clock::time_point g_dbg_t0 = std::chrono::steady_clock::now();
@@ -85,6 +87,9 @@ struct ThreadCtx {
 	struct LastPart { const int32_t *fields; const int64_t *hit_off, *read_off; int64_t n_hits; int32_t n_reads; };
 	std::vector<LastPart> last_parts;
 	int32_t last_n_reads = -1; const void *last_index = nullptr;
+	// batches cut into sequential pieces (memory budget): the hit fields / offsets of every piece are kept here (plain device
+	// memory, grown on demand, reused by later batches) so that mb_count_last sees the whole batch
+	char *store = nullptr; size_t store_cap = 0, store_used = 0;
 	// helper contexts (own stream + arena) for the other sub-batches of a call: a batch is cut in MB_NPART pieces that run
 	// concurrently, so the latency-bound stages of one piece (sketch, seeding, chaining, region logic, stitching) hide under
 	// the issue-bound DP kernels of the other
@@ -95,6 +100,7 @@ struct ThreadCtx {
 			cudaSetDevice(device);
 			ar.release();
 			if (h_pin) cudaFreeHost(h_pin);
+			if (store) cudaFree(store);
 			if (d_counts) cudaFree(d_counts);
 			if (st) cudaStreamDestroy(st);
 			for (int i = 0; i < MB_NSIDE; ++i) { if (st2[i]) cudaStreamDestroy(st2[i]); if (ev_join[i]) cudaEventDestroy(ev_join[i]); }
@@ -626,8 +632,9 @@ static __host__ __device__ inline DpGeom dp_geom(int qlen, int tlen, int w)
 
 #define DP_NEXACT 6                 // exact-kernel classes by direction-matrix size: <=64K, <=256K, <=1M, <=4M, <=16M, larger
 #define DP_XBASE DPF_NCLASS          // extension fast-path classes follow the gap-fill fast-path classes
-#define DP_EBASE (2 * DPF_NCLASS)   // then the exact-kernel classes
-#define DP_NCLS (2 * DPF_NCLASS + DP_NEXACT)
+#define DP_BBASE (2 * DPF_NCLASS)   // then the packed band kernel's classes (large / band-limited gap fills)
+#define DP_EBASE (2 * DPF_NCLASS + DPB_NCLASS)   // then the exact-kernel classes
+#define DP_NCLS (2 * DPF_NCLASS + DPB_NCLASS + DP_NEXACT)
 static __host__ __device__ inline int dp_exact_class(size_t p_bytes)
 {
 	int k = 0;
@@ -651,6 +658,7 @@ __global__ void k_dp_classify(const DpTask *__restrict__ tasks, const int32_t *_
 		t = tasks[id];
 		cls = fast_ok ? dpf_class(t.qlen, t.tlen, t.w, t.flag, t.skip) : -1;
 		if (cls < 0 && fast_ok) { cls = dpx_class(t.qlen, t.tlen, t.w, t.flag, t.skip); if (cls >= 0) cls += DP_XBASE; }
+		if (cls < 0 && fast_ok) { cls = dpb_class(t.qlen, t.tlen, t.w, t.flag, t.skip); if (cls >= 0) cls += DP_BBASE; }
 	}
 	// ambiguous bases send a task to the exact kernel.  The scan of a task's two windows is done by the whole warp, one task
 	// after the other: 32 lanes reading consecutive words of one window instead of 32 lanes each walking its own
@@ -670,7 +678,7 @@ __global__ void k_dp_classify(const DpTask *__restrict__ tasks, const int32_t *_
 	// class counters and maxima are a handful of hot addresses: one atomic per (warp, class) instead of one per task
 	unsigned m0 = 0, m1 = 0, m2 = 0;
 	if (live) {
-		if (cls >= 0) m0 = (unsigned)t.qlen;
+		if (cls >= 0) { m0 = (unsigned)t.qlen; if (cls >= DP_BBASE) m1 = (unsigned)t.tlen; }
 		else {
 			DpGeom g = dp_geom(t.qlen, t.tlen, t.w);
 			if (t.skip) g.p_bytes = g.ws_bytes = g.h_ints = 0;
@@ -694,7 +702,7 @@ __global__ void k_dp_classify(const DpTask *__restrict__ tasks, const int32_t *_
 	if (lane == leader) {
 		base = atomicAdd(&ctr[cls], __popc(peers));
 		atomicMax(&maxima[cls * 3 + 0], (unsigned long long)x0);
-		if (cls >= DP_EBASE) { atomicMax(&maxima[cls * 3 + 1], (unsigned long long)x1); atomicMax(&maxima[cls * 3 + 2], (unsigned long long)x2); }
+		if (cls >= DP_BBASE) { atomicMax(&maxima[cls * 3 + 1], (unsigned long long)x1); atomicMax(&maxima[cls * 3 + 2], (unsigned long long)x2); }
 	}
 	base = __shfl_sync(peers, base, leader);
 	lists[(int64_t)cls * n + base + rank] = id;
@@ -705,7 +713,7 @@ struct DpRunner {
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evs; // one pair per DP launch, read back after the batch
 	cudaEvent_t ev_base = nullptr;
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> fast_wall; // fork -> all k_dp_fast launches of a run done (they overlap each other)
-	std::vector<int> ev_fast; int64_t n_fast = 0, n_exact = 0, n_ext = 0; // ev_fast: 1 k_dp_fast, 2 k_dp_ext, 0 k_dp
+	std::vector<int> ev_fast; int64_t n_fast = 0, n_exact = 0, n_ext = 0, n_band = 0; // ev_fast: 1 k_dp_fast, 2 k_dp_ext, 3 k_dp_band, 0 k_dp
 	DpRunner(ThreadCtx &c_, int64_t *nl_) : c(c_), st(c_.st), nl(nl_) {}
 	~DpRunner() { for (auto &e : evs) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); } for (auto &e : fast_wall) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); } }
 	float fast_wall_ms() { float t = 0; for (auto &e : fast_wall) { float ms = 0; if (cudaEventElapsedTime(&ms, e.first, e.second) == cudaSuccess) t += ms; } return t; }
@@ -783,6 +791,30 @@ struct DpRunner {
 		CK(cudaStreamSynchronize(st));
 		if (getenv("MB_DEBUG")) { auto t1 = std::chrono::steady_clock::now(); fprintf(stderr, "[mb]   classify done (+%.3f ms)\n", std::chrono::duration<double, std::milli>(t1 - g_dbg_t0).count()); g_dbg_t0 = t1; }
 		if (getenv("MB_DEBUG") && !ev_base) { cudaEventCreate(&ev_base); cudaEventRecord(ev_base, st); }
+		if (getenv("MB_DEBUG_TASKS")) { // which tasks miss the packed kernels, and why (host-side histogram of the task list)
+			int64_t n_all = n;
+			if (use_ids) { int64_t mx = 0; std::vector<int32_t> hi(n); cudaMemcpy(hi.data(), ids, n * 4, cudaMemcpyDeviceToHost); for (int32_t v : hi) mx = std::max<int64_t>(mx, v + 1); n_all = mx; }
+			std::vector<DpTask> ht(n_all);
+			cudaMemcpy(ht.data(), tasks, n_all * sizeof(DpTask), cudaMemcpyDeviceToHost);
+			std::vector<int32_t> hid(n);
+			if (use_ids) cudaMemcpy(hid.data(), ids, n * 4, cudaMemcpyDeviceToHost); else for (int64_t i = 0; i < n; ++i) hid[i] = (int32_t)i;
+			struct Cat { int64_t n = 0; double cells = 0; };
+			std::map<std::string, Cat> cats;
+			for (int64_t i = 0; i < n; ++i) {
+				const DpTask &t = ht[hid[i]];
+				if (t.skip || t.qlen <= 0 || t.tlen <= 0) continue;
+				if (dpf_class(t.qlen, t.tlen, t.w, t.flag, t.skip) >= 0 || dpx_class(t.qlen, t.tlen, t.w, t.flag, t.skip) >= 0) continue;
+				int w = t.w < 0 ? std::max(t.qlen, t.tlen) : t.w;
+				const int mx = std::max(t.qlen, t.tlen);
+				std::string k = t.flag == 0 ? "pass2" : (t.flag & MB_EZ_EXTZ_ONLY) ? "ext" : "fill";
+				k += mx > w + 1 ? "/band-limited" : "/band-free";
+				k += mx <= 768 ? "/<=768" : mx <= 1536 ? "/<=1536" : mx <= 3072 ? "/<=3072" : "/>3072";
+				Cat &c2 = cats[k]; ++c2.n;
+				double cells = 0; for (int r = 0; r < t.qlen + t.tlen - 1; ++r) { int st0 = std::max(std::max(0, r - t.qlen + 1), (r - w + 1) >> 1), en0 = std::min(std::min(t.tlen - 1, r), (r + w) >> 1); if (en0 >= st0) cells += en0 - st0 + 1; }
+				c2.cells += cells;
+			}
+			for (auto &kv : cats) fprintf(stderr, "[mb-tasks] %-36s %8lld tasks %10.3f Gcells (full band area)\n", kv.first.c_str(), (long long)kv.second.n, kv.second.cells / 1e9);
+		}
 		// the exact kernel goes first, on the high-priority side stream (the host synchronised `st` above, so its inputs are
 		// complete), largest class first: a handful of long band-limited tasks give each launch a long tail of a few busy
 		// warps, which the fast kernels on `st` fill
@@ -826,6 +858,27 @@ struct DpRunner {
 			cudaEventRecord(e1, st2);
 			evs.emplace_back(e0, e1); ev_fast.push_back(0); n_exact += cnt;
 			++*nl; side[b & 1] = true;
+		}
+		for (int k = DPB_NCLASS - 1; k >= 0; --k) { // large / band-limited gap fills: packed systolic kernel with upstream's band (dp_band.cuh)
+			const int cls = DP_BBASE + k;
+			const int64_t cnt = h_ctr[cls];
+			if (cnt == 0) continue;
+			const int mq = (int)h_max[cls * 3], mt = (int)h_max[cls * 3 + 1];
+			const int n_strips = (mt + DPB_STRIP - 1) / DPB_STRIP;
+			const size_t stride_words = (DPB_EDGE_WORDS + (size_t)n_strips * (size_t)(mq + 31) * 32 * DPB_CW + 63) & ~(size_t)63;
+			const int max_cta = c.num_sms * (k == 0 ? 8 : 4);
+			const int64_t want = cdiv(cnt, 2);
+			const int n_cta = (int)(want < max_cta ? want : max_cta);
+			uint32_t *p_scr = ar.get<uint32_t>((size_t)n_cta * stride_words);
+			int32_t *wc = ar.get<int32_t>(1);
+			cudaStream_t sb = c.st2[k & 1]; side[k & 1] = true;
+			CK(cudaMemsetAsync(wc, 0, sizeof(int32_t), sb));
+			cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+			cudaEventRecord(e0, sb);
+			k_dp_band<<<n_cta, 32, 0, sb>>>(tasks, lists + (int64_t)cls * n, ctr + cls, wc, codes, S, pool, p_scr, stride_words, cigar_pool, sc, d_cells ? d_cells + 3 : nullptr);
+			cudaEventRecord(e1, sb);
+			evs.emplace_back(e0, e1); ev_fast.push_back(3); n_band += cnt;
+			++*nl;
 		}
 		for (int k = 0; k < DPF_NCLASS; ++k) {
 			const int64_t cnt = h_ctr[DP_XBASE + k];
@@ -963,10 +1016,10 @@ static void map_device_part(mb_index *ix, const mb_opt_t &opt_in, DevPart &part)
 	rs.f = ar.get<int32_t>(n_a + 1), rs.p = ar.get<int32_t>(n_a + 1), rs.v = ar.get<int32_t>(n_a + 1), rs.t = ar.get<int32_t>(n_a + 1);
 	rs.b = ar.get<mb128>(n_a + 1); rs.u = ar.get<uint64_t>(n_a + 1); rs.scr = ar.get<uint64_t>(3 * n_a + 3 * (int64_t)n_reads + 3);
 	int32_t *wc = ar.get<int32_t>(4);
-	unsigned long long *d_cells = ar.get<unsigned long long>(4); // chain, k_dp_fast, k_dp, k_dp_ext
+	unsigned long long *d_cells = ar.get<unsigned long long>(6); // chain, k_dp_fast, k_dp, k_dp_ext, k_dp_band
 	int *d_err = ar.get<int>(1);
 	CK(cudaMemsetAsync(wc, 0, 4 * sizeof(int32_t), st));
-	CK(cudaMemsetAsync(d_cells, 0, 4 * sizeof(unsigned long long), st));
+	CK(cudaMemsetAsync(d_cells, 0, 6 * sizeof(unsigned long long), st));
 	CK(cudaMemsetAsync(d_err, 0, sizeof(int), st));
 	const int max_chain_gap_ref = opt.max_gap_ref > 0 ? opt.max_gap_ref : opt.max_gap, max_chain_gap_qry = opt.max_gap;
 	if (n_a > 0) {
@@ -1194,17 +1247,19 @@ static void map_device_part(mb_index *ix, const mb_opt_t &opt_in, DevPart &part)
 	S.n_hits = n_h;
 	part.d_fields = d_fields, part.d_hcoff = d_hcoff, part.d_hcig = d_hcig, part.d_hit_off = hit_off, part.d_rep_len = sd.rep_len;
 	part.n_h = n_h, part.n_c = n_c;
-	unsigned long long h_cells[4];
+	unsigned long long h_cells[6];
 	CK(cudaMemcpyAsync(h_cells, d_cells, sizeof(h_cells), cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));
 	CK(cudaGetLastError());
-	S.dp_cells = (int64_t)(h_cells[1] + h_cells[2] + h_cells[3]); S.dp_cells_exact = (int64_t)h_cells[2]; S.dp_cells_ext = (int64_t)h_cells[3]; S.chain_cells = (int64_t)h_cells[0];
+	S.dp_cells = (int64_t)(h_cells[1] + h_cells[2] + h_cells[3] + h_cells[4]); S.dp_cells_exact = (int64_t)h_cells[2]; S.dp_cells_ext = (int64_t)h_cells[3]; S.chain_cells = (int64_t)h_cells[0];
+	S.dp_cells_band = (int64_t)h_cells[4]; S.ms_kdp_band = runner.total_ms(3); S.n_band_tasks = runner.n_band;
 	S.n_launches = nl;
 	if (dbg) for (size_t i = 0; i < runner.evs.size(); ++i) { float ms = 0; cudaEventElapsedTime(&ms, runner.evs[i].first, runner.evs[i].second); float a = 0, b = 0; if (runner.ev_base) { cudaEventElapsedTime(&a, runner.ev_base, runner.evs[i].first); cudaEventElapsedTime(&b, runner.ev_base, runner.evs[i].second); } fprintf(stderr, "[mb] dp launch %2zu kind %d  %8.3f ms  [%8.3f .. %8.3f]\n", i, runner.ev_fast[i], ms, a, b); }
 	S.ms_kdp = runner.total_ms(); S.n_kdp = (int32_t)runner.evs.size();
 	{ int64_t nf = 0; for (int f : runner.ev_fast) nf += (f == 1); S.n_kdp_fast = nf; }
 	S.ms_kdp_fast = runner.fast_wall_ms(); S.ms_kdp_exact = runner.total_ms(0); S.n_fast_tasks = runner.n_fast; S.n_exact_tasks = runner.n_exact;
 	S.ms_kdp_ext = runner.total_ms(2); S.n_ext_tasks = runner.n_ext;
+	S.arena_bytes = (int64_t)ar.batch_total;
 	S.ms_total = tall.stop();
 }
 
@@ -1330,6 +1385,8 @@ static mb_hits *map_device(mb_index *ix, const mb_opt_t &opt, ThreadCtx &c, cons
 		S.ms_dp += q.ms_dp, S.ms_post += q.ms_post, S.ms_kdp += q.ms_kdp, S.n_kdp += q.n_kdp, S.ms_kdp_fast += q.ms_kdp_fast, S.ms_kdp_exact += q.ms_kdp_exact;
 		S.n_fast_tasks += q.n_fast_tasks, S.n_exact_tasks += q.n_exact_tasks, S.chain_cells += q.chain_cells, S.dp_cells_exact += q.dp_cells_exact;
 		S.n_kdp_fast += q.n_kdp_fast, S.n_ext_tasks += q.n_ext_tasks, S.dp_cells_ext += q.dp_cells_ext, S.ms_kdp_ext += q.ms_kdp_ext;
+		S.n_inv += q.n_inv, S.arena_bytes = std::max(S.arena_bytes, q.arena_bytes);
+		S.dp_cells_band += q.dp_cells_band, S.ms_kdp_band += q.ms_kdp_band, S.n_band_tasks += q.n_band_tasks;
 	}
 	S.ms_total = (float)std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
 	if (stats) { float h2d = stats->ms_h2d; *stats = S; stats->ms_h2d = h2d; }
@@ -1358,6 +1415,169 @@ static void upload_reads(ThreadCtx &c, const uint8_t *cat, const int64_t *off, i
 	if (*total) k_encode_nt4<<<(unsigned)cdiv(cdiv(*total, 16), 256), 256, 0, st>>>(d_ascii, *d_codes, *total);
 }
 
+// ---- sequential pieces: batches whose scratch would not fit the device are mapped piece by piece ----
+static int64_t mb_piece_bases()
+{
+	const char *e = getenv("MB_PIECE_BASES"); // bases per sequential piece; the default keeps the scratch of a piece around 40 GB
+	const int64_t v = e ? atoll(e) : (int64_t)800000000;
+	return v < 1000 ? 1000 : v;
+}
+
+static size_t store_put(ThreadCtx &c, const void *d_src, size_t bytes)
+{
+	bytes = (bytes + 255) & ~(size_t)255;
+	if (c.store_used + bytes > c.store_cap) {
+		size_t ncap = c.store_cap ? c.store_cap * 2 : ((size_t)64 << 20);
+		while (ncap < c.store_used + bytes) ncap <<= 1;
+		char *nb = nullptr;
+		CK(cudaMalloc(&nb, ncap));
+		if (c.store_used) CK(cudaMemcpyAsync(nb, c.store, c.store_used, cudaMemcpyDeviceToDevice, c.st));
+		CK(cudaStreamSynchronize(c.st));
+		if (c.store) cudaFree(c.store);
+		c.store = nb, c.store_cap = ncap;
+	}
+	const size_t o = c.store_used;
+	if (bytes) CK(cudaMemcpyAsync(c.store + o, d_src, bytes, cudaMemcpyDeviceToDevice, c.st));
+	c.store_used += bytes;
+	return o;
+}
+
+template <typename T> static void concat_pin(PinVec<T> &dst, const std::vector<std::pair<const T*, size_t>> &src)
+{
+	size_t n = 0;
+	for (auto &p : src) n += p.second;
+	dst.resize(n);
+	std::vector<std::thread> th;
+	size_t o = 0;
+	for (auto &p : src) {
+		if (p.second) {
+			T *d = dst.data() + o; const T *sp = p.first; const size_t cnt = p.second;
+			if (cnt * sizeof(T) > ((size_t)8 << 20)) th.emplace_back([d, sp, cnt]() { memcpy(d, sp, cnt * sizeof(T)); });
+			else memcpy(d, sp, cnt * sizeof(T));
+		}
+		o += p.second;
+	}
+	for (auto &t : th) t.join();
+}
+
+// h_cat != nullptr: reads in host memory (uploaded piece by piece); otherwise d_codes_all / d_off_all hold the resident batch
+static mb_hits *map_in_pieces(mb_index *ix, const mb_opt_t &opt, ThreadCtx &c, const uint8_t *h_cat, const uint8_t *d_codes_all, const int64_t *d_off_all,
+                              const int64_t *h_off, int32_t n_reads, int want, mb_stats_t *stats)
+{
+	const int64_t piece = mb_piece_bases();
+	std::vector<int32_t> cut(1, 0);
+	while (cut.back() < n_reads) { // at least one read per piece, then as many as fit
+		int32_t lo = cut.back(), hi = lo + 1;
+		hi = (int32_t)(std::upper_bound(h_off + hi, h_off + n_reads + 1, h_off[lo] + piece) - h_off) - 1;
+		if (hi <= lo) hi = lo + 1;
+		cut.push_back(hi);
+	}
+	const int K = (int)cut.size() - 1;
+	std::vector<std::unique_ptr<mb_hits>> parts(K);
+	struct Kept { size_t fields, hit_off, read_off; int64_t n_hits; int32_t n_reads; };
+	std::vector<Kept> kept;
+	c.store_used = 0;
+	mb_stats_t S; memset(&S, 0, sizeof(S));
+	float ms_h2d = 0;
+	for (int k = 0; k < K; ++k) {
+		const int32_t lo = cut[k], n = cut[k + 1] - lo;
+		std::vector<int64_t> po(n + 1);
+		for (int32_t i = 0; i <= n; ++i) po[i] = h_off[lo + i] - h_off[lo];
+		c.ar.reset();
+		uint8_t *d_codes; int64_t *d_off; int64_t total = po[n];
+		SketchFeed feed; bool use_feed = false;
+		if (h_cat) {
+			Timer tm(c.st); tm.start();
+			const char *feed_env = getenv("MB_FEED_MIN_BYTES");
+			const int64_t feed_min = feed_env ? atoll(feed_env) : ((int64_t)64 << 20);
+			use_feed = total >= feed_min;
+			upload_reads(c, h_cat + h_off[lo], po.data(), n, &d_codes, &d_off, &total, false, use_feed ? &feed : nullptr);
+			ms_h2d += tm.stop();
+		} else {
+			const int64_t base = h_off[lo] & ~(int64_t)15;   // keep the code pointer 16-byte aligned (vector loads)
+			for (int32_t i = 0; i <= n; ++i) po[i] = h_off[lo + i] - base;
+			total = po[n];
+			d_codes = const_cast<uint8_t*>(d_codes_all) + base;
+			d_off = c.ar.get<int64_t>(n + 1);
+			k_rebase_offsets<<<(unsigned)cdiv(n + 1, 256), 256, 0, c.st>>>(d_off_all + lo, d_off, n + 1, base);
+		}
+		mb_stats_t st1; memset(&st1, 0, sizeof(st1));
+		parts[k].reset(map_device(ix, opt, c, d_codes, d_off, po.data(), n, total, want, &st1, use_feed ? &feed : nullptr));
+		// keep what mb_count_last needs beyond the next arena reset
+		for (const ThreadCtx::LastPart &lp : c.last_parts) {
+			Kept kp; kp.n_hits = lp.n_hits, kp.n_reads = lp.n_reads;
+			kp.fields = store_put(c, lp.fields, (size_t)HIT_NF * lp.n_hits * 4);
+			kp.hit_off = store_put(c, lp.hit_off, (size_t)(lp.n_reads + 1) * 8);
+			kp.read_off = store_put(c, lp.read_off, (size_t)(lp.n_reads + 1) * 8);
+			kept.push_back(kp);
+		}
+		CK(cudaStreamSynchronize(c.st));
+		S.n_reads += st1.n_reads, S.n_bases += st1.n_bases, S.n_mini += st1.n_mini, S.n_anchor += st1.n_anchor, S.n_regs += st1.n_regs;
+		S.n_dp_tasks += st1.n_dp_tasks, S.n_dp_pass2 += st1.n_dp_pass2, S.dp_cells += st1.dp_cells, S.n_hits += st1.n_hits;
+		S.n_rounds = std::max(S.n_rounds, st1.n_rounds), S.n_launches += st1.n_launches + (h_cat ? 1 : 0);
+		S.ms_sketch += st1.ms_sketch, S.ms_seed += st1.ms_seed, S.ms_sort += st1.ms_sort, S.ms_chain += st1.ms_chain, S.ms_glue += st1.ms_glue;
+		S.ms_dp += st1.ms_dp, S.ms_post += st1.ms_post, S.ms_total += st1.ms_total, S.ms_d2h += st1.ms_d2h;
+		S.ms_kdp += st1.ms_kdp, S.n_kdp += st1.n_kdp, S.ms_kdp_fast += st1.ms_kdp_fast, S.ms_kdp_exact += st1.ms_kdp_exact, S.ms_kdp_ext += st1.ms_kdp_ext;
+		S.n_fast_tasks += st1.n_fast_tasks, S.n_exact_tasks += st1.n_exact_tasks, S.chain_cells += st1.chain_cells, S.dp_cells_exact += st1.dp_cells_exact;
+		S.n_kdp_fast += st1.n_kdp_fast, S.n_ext_tasks += st1.n_ext_tasks, S.dp_cells_ext += st1.dp_cells_ext, S.n_inv += st1.n_inv;
+		S.arena_bytes = std::max(S.arena_bytes, st1.arena_bytes);
+		S.dp_cells_band += st1.dp_cells_band, S.ms_kdp_band += st1.ms_kdp_band, S.n_band_tasks += st1.n_band_tasks;
+	}
+	S.ms_h2d = ms_h2d, S.n_pieces = K;
+	// device-resident view of the whole batch for mb_count_last
+	c.last_parts.clear(); c.last_n_reads = n_reads; c.last_index = ix;
+	for (const Kept &kp : kept) {
+		ThreadCtx::LastPart lp;
+		lp.fields = reinterpret_cast<const int32_t*>(c.store + kp.fields), lp.hit_off = reinterpret_cast<const int64_t*>(c.store + kp.hit_off);
+		lp.read_off = reinterpret_cast<const int64_t*>(c.store + kp.read_off), lp.n_hits = kp.n_hits, lp.n_reads = kp.n_reads;
+		c.last_parts.push_back(lp);
+	}
+	// ---- one result object for the caller ----
+	std::unique_ptr<mb_hits> H(new mb_hits());
+	H->n_reads = n_reads;
+	H->read_off.assign(h_off, h_off + n_reads + 1);
+	int64_t n_h = 0, n_c = 0;
+	for (int k = 0; k < K; ++k) { n_h += parts[k]->n; n_c += (int64_t)parts[k]->cigar.size(); }
+	H->n = n_h;
+	H->hit_off.resize(n_reads + 1); H->rep_len.resize(n_reads);
+	{
+		int64_t hb = 0;
+		for (int k = 0; k < K; ++k) {
+			const int32_t lo = cut[k], n = cut[k + 1] - lo;
+			for (int32_t i = 0; i < n; ++i) { H->hit_off.data()[lo + i] = parts[k]->hit_off.data()[i] + hb; H->rep_len.data()[lo + i] = parts[k]->rep_len.data()[i]; }
+			hb += parts[k]->n;
+		}
+		H->hit_off.data()[n_reads] = hb;
+	}
+	if (want) {
+		H->fields.resize((size_t)HIT_NF * n_h);
+		std::vector<std::thread> th;
+		for (int f = 0; f < HIT_NF; ++f) th.emplace_back([&, f]() {
+			int64_t hb = 0;
+			for (int k = 0; k < K; ++k) {
+				const int64_t m = parts[k]->n;
+				int32_t *d = H->fields.data() + (size_t)f * n_h + hb;
+				if (m) memcpy(d, parts[k]->fields.data() + (size_t)f * m, (size_t)m * 4);
+				if (f == 0) for (int64_t i = 0; i < m; ++i) d[i] += cut[k]; // read_idx: piece-relative -> batch
+				hb += m;
+			}
+		});
+		for (auto &t : th) t.join();
+		H->cigar_off.resize(n_h);
+		int64_t hb = 0, cb = 0;
+		std::vector<std::pair<const uint32_t*, size_t>> cg;
+		for (int k = 0; k < K; ++k) {
+			const int64_t m = parts[k]->n;
+			for (int64_t i = 0; i < m; ++i) H->cigar_off.data()[hb + i] = parts[k]->cigar_off.data()[i] + cb;
+			cg.emplace_back(parts[k]->cigar.data(), parts[k]->cigar.size());
+			hb += m, cb += (int64_t)parts[k]->cigar.size();
+		}
+		concat_pin(H->cigar, cg);
+	}
+	if (stats) *stats = S;
+	return H.release();
+}
+
 static int map_batch_impl(mb_index_t *ix, const mb_opt_t *opt, const uint8_t *cat, const int64_t *off, int32_t n_reads, int want, mb_hits_t **out, mb_stats_t *stats);
 extern "C" int mb_map_batch(mb_index_t *ix, const mb_opt_t *opt, const uint8_t *cat, const int64_t *off, int32_t n_reads, mb_hits_t **out, mb_stats_t *stats)
 {
@@ -1372,6 +1592,14 @@ static int map_batch_impl(mb_index_t *ix, const mb_opt_t *opt, const uint8_t *ca
 	API_BEGIN
 	if (!ix || !opt || !off || !out || (n_reads > 0 && !cat && off[n_reads] > 0)) throw mb_error(MB_ERR_ARG, "bad arguments");
 	ThreadCtx &c = get_ctx(ix->device);
+	if (n_reads > 1 && off[n_reads] > mb_piece_bases()) {
+		for (int i = 0; i < n_reads; ++i) {
+			if (off[i + 1] < off[i] || off[0] != 0) throw mb_error(MB_ERR_ARG, "offsets must start at 0 and be non-decreasing");
+			if (off[i + 1] - off[i] > 0x3fffffff) throw mb_error(MB_ERR_ARG, "read longer than 2^30");
+		}
+		*out = map_in_pieces(ix, *opt, c, cat, nullptr, nullptr, off, n_reads, want, stats);
+		return MB_OK;
+	}
 	c.ar.reset();
 	uint8_t *d_codes; int64_t *d_off; int64_t total;
 	Timer tm(c.st); tm.start();
@@ -1421,6 +1649,10 @@ extern "C" int mb_map_resident(mb_index_t *ix, const mb_opt_t *opt, mb_reads_t *
 	CK(cudaMemcpyAsync(h_off.data(), reads->d_off, (reads->n_reads + 1) * 8, cudaMemcpyDeviceToHost, c.st));
 	CK(cudaStreamSynchronize(c.st));
 	if (stats) stats->ms_h2d = 0;
+	if (reads->n_reads > 1 && reads->total > mb_piece_bases()) {
+		*out = map_in_pieces(ix, *opt, c, nullptr, reads->d_codes, reads->d_off, h_off.data(), reads->n_reads, want_hits ? 3 : 0, stats);
+		return MB_OK;
+	}
 	*out = map_device(ix, *opt, c, reads->d_codes, reads->d_off, h_off.data(), reads->n_reads, reads->total, want_hits ? 3 : 0, stats);
 	API_END
 }
@@ -1545,6 +1777,92 @@ extern "C" int mb_count_fetch(mb_index_t *ix, int64_t *counts)
 	ThreadCtx &c = get_ctx(ix->device);
 	if (!c.d_counts) throw mb_error(MB_ERR_ARG, "no count vector on this thread");
 	CK(cudaMemcpy(counts, c.d_counts, ix->names.size() * 8, cudaMemcpyDeviceToHost));
+	API_END
+}
+
+// ---- the one collective: NCCL all-reduce of the count vector ----
+// libnccl is bound at run time so that the library loads on hosts without it (index building, CPU-side FASTQ tools).
+namespace {
+struct NcclId { char internal[128]; };
+typedef void *NcclComm;
+struct NcclApi {
+	void *h = nullptr;
+	int (*GetUniqueId)(NcclId*) = nullptr;
+	int (*CommInitRank)(NcclComm*, int, NcclId, int) = nullptr;
+	int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+	int (*CommDestroy)(NcclComm) = nullptr;
+	const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi &nccl_api()
+{
+	static NcclApi api;
+	static std::once_flag once;
+	std::call_once(once, []() {
+		const char *names[] = { "libnccl.so.2", "libnccl.so" };
+		for (const char *n : names) { api.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (api.h) break; }
+		if (!api.h) return;
+		api.GetUniqueId = (int (*)(NcclId*))dlsym(api.h, "ncclGetUniqueId");
+		api.CommInitRank = (int (*)(NcclComm*, int, NcclId, int))dlsym(api.h, "ncclCommInitRank");
+		api.AllReduce = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(api.h, "ncclAllReduce");
+		api.CommDestroy = (int (*)(NcclComm))dlsym(api.h, "ncclCommDestroy");
+		api.GetErrorString = (const char *(*)(int))dlsym(api.h, "ncclGetErrorString");
+	});
+	if (!api.h || !api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy)
+		throw mb_error(MB_ERR_CUDA, "libnccl.so.2 not found (or incomplete): the multi-GPU all-reduce has no fallback");
+	return api;
+}
+void nccl_check(int rc, const char *what)
+{
+	if (rc == 0) return;
+	NcclApi &a = nccl_api();
+	throw mb_error(MB_ERR_CUDA, std::string(what) + ": NCCL error " + std::to_string(rc) + (a.GetErrorString ? std::string(" (") + a.GetErrorString(rc) + ")" : std::string()));
+}
+}
+struct mb_comm { NcclComm comm = nullptr; int device = 0, rank = 0, world = 1; };
+
+extern "C" int mb_comm_unique_id(uint8_t id[128])
+{
+	API_BEGIN
+	if (!id) throw mb_error(MB_ERR_ARG, "bad arguments");
+	NcclId nid;
+	nccl_check(nccl_api().GetUniqueId(&nid), "ncclGetUniqueId");
+	memcpy(id, nid.internal, 128);
+	API_END
+}
+
+extern "C" int mb_comm_init(int device, int rank, int world, const uint8_t id[128], mb_comm_t **out)
+{
+	API_BEGIN
+	if (!id || !out || world < 1 || rank < 0 || rank >= world) throw mb_error(MB_ERR_ARG, "bad arguments");
+	ensure_device(device);
+	std::unique_ptr<mb_comm> c(new mb_comm());
+	c->device = device, c->rank = rank, c->world = world;
+	NcclId nid; memcpy(nid.internal, id, 128);
+	nccl_check(nccl_api().CommInitRank(&c->comm, world, nid, rank), "ncclCommInitRank");
+	*out = c.release();
+	API_END
+}
+
+extern "C" void mb_comm_free(mb_comm_t *comm)
+{
+	if (!comm) return;
+	try { if (comm->comm) { cudaSetDevice(comm->device); nccl_api().CommDestroy(comm->comm); } } catch (...) {}
+	delete comm;
+}
+
+extern "C" int mb_allreduce_counts(mb_index_t *ix, mb_comm_t *comm, int64_t *counts, int64_t *n_class)
+{
+	API_BEGIN
+	if (!ix || !comm) throw mb_error(MB_ERR_ARG, "bad arguments");
+	ThreadCtx &c = get_ctx(ix->device);
+	if (!c.d_counts) throw mb_error(MB_ERR_ARG, "no count vector on this thread (call mb_count / mb_count_last first)");
+	const int n_seq = (int)ix->names.size();
+	// counts[n_seq] and the three read-class counters are contiguous: one collective
+	nccl_check(nccl_api().AllReduce(c.d_counts, c.d_counts, (size_t)n_seq + 3, /*ncclInt64*/ 4, /*ncclSum*/ 0, comm->comm, c.st), "ncclAllReduce");
+	if (counts) CK(cudaMemcpyAsync(counts, c.d_counts, (size_t)n_seq * 8, cudaMemcpyDeviceToHost, c.st));
+	if (n_class) CK(cudaMemcpyAsync(n_class, c.d_counts + n_seq, 3 * 8, cudaMemcpyDeviceToHost, c.st));
+	CK(cudaStreamSynchronize(c.st));
+	CK(cudaGetLastError());
 	API_END
 }
 

@@ -194,6 +194,29 @@ class Aligner:
         self.last_stats = st.as_dict()
         return Hits(h, n)
 
+    # ---- device-resident reads (measurement of the kernels alone; a caller that maps one batch against several option sets) ----
+    def reads_upload(self, cat: np.ndarray, off: np.ndarray):
+        """Upload a concatenated batch once; returns an opaque handle for map_resident / reads_free."""
+        cat = np.ascontiguousarray(cat, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        h = C.c_void_p()
+        check(lib().mb_reads_upload(self._idx, cat.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p), len(off) - 1, C.byref(h)))
+        return h
+
+    def reads_free(self, handle):
+        lib().mb_reads_free(handle)
+
+    def map_resident(self, handle, n_reads: int, want_hits: bool = False):
+        """Map an uploaded batch.  With want_hits=False nothing is copied back: follow with count_last()."""
+        h = C.c_void_p()
+        st = Stats()
+        check(lib().mb_map_resident(self._idx, C.byref(self.opt), handle, 1 if want_hits else 0, C.byref(h), C.byref(st)))
+        self.last_stats = st.as_dict()
+        if want_hits:
+            return Hits(h, n_reads)
+        lib().mb_hits_free(h)
+        return None
+
     def count(self, hits: Hits, mapq_min: int = 60, mode: str | None = "basic"):
         """monica's hit filter + best_hit + per-target sum on the device (aligner.py:193-195,225-263,328-339).
         Returns (counts int64[n_seq], n_class [mapped, unmapped, ambiguous], read_class int8[n_reads], read_best int64[n_reads])."""
@@ -205,6 +228,20 @@ class Aligner:
         check(lib().mb_count(self._idx, hits.handle(), mapq_min, m, counts.ctypes.data_as(C.c_void_p),
                              ncls.ctypes.data_as(C.c_void_p), rcls.ctypes.data_as(C.c_void_p), rbest.ctypes.data_as(C.c_void_p)))
         return counts, ncls, rcls[:hits.n_reads], rbest[:hits.n_reads]
+
+    def count_last(self, mapq_min: int = 60, mode: str | None = "basic", comm=None):
+        """The same filter + best_hit + per-target sum on the DEVICE-RESIDENT hits of this thread's last map_batch (no host
+        round trip of the hit arrays), optionally followed by the one NCCL all-reduce over the ranks of `comm`
+        (monica_b200.shard.Comm).  Returns (counts int64[n_seq], n_class [mapped, unmapped, ambiguous])."""
+        m = {"basic": 0, "query_length": 1, "matching": 2}.get(mode, 3)
+        counts = np.zeros(self.n_seq, dtype=np.int64)
+        ncls = np.zeros(3, dtype=np.int64)
+        if comm is None:
+            check(lib().mb_count_last(self._idx, mapq_min, m, counts.ctypes.data_as(C.c_void_p), ncls.ctypes.data_as(C.c_void_p)))
+        else:
+            check(lib().mb_count_last(self._idx, mapq_min, m, None, None))
+            check(lib().mb_allreduce_counts(self._idx, comm.handle(), counts.ctypes.data_as(C.c_void_p), ncls.ctypes.data_as(C.c_void_p)))
+        return counts, ncls
 
     def normalize_last(self, sample_alignment, genomes_length):
         """normalizer() (aligner.py:305-319) for one sample, computed on the device from the count vector of this thread's

@@ -38,30 +38,76 @@ def shard_reads(cat: np.ndarray, off: np.ndarray, rank: int, world: int):
     return cat[int(o[0]):int(o[-1])], o - o[0], lo
 
 
+class Comm:
+    """NCCL communicator of the C library (include/monica_b200.h mb_comm_*): one per (process, device).  The 128-byte NCCL id
+    is made by rank 0 and handed to the other ranks through `torch.distributed` (any backend) -- plumbing only; the
+    all-reduce itself is issued by the library on its own mapping stream, on the count vector that never left HBM."""
+
+    def __init__(self, device: int, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        from . import _lib
+        L = _lib.lib()
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        buf = (C.c_uint8 * 128)()
+        if self.rank == 0:
+            _lib.check(L.mb_comm_unique_id(buf))
+        box = [bytes(buf)]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        ident = (C.c_uint8 * 128).from_buffer_copy(box[0])
+        self._h = C.c_void_p()
+        _lib.check(L.mb_comm_init(device, self.rank, self.world, ident, C.byref(self._h)))
+
+    def handle(self):
+        return self._h
+
+    def free(self):
+        if getattr(self, "_h", None):
+            from . import _lib
+            _lib.lib().mb_comm_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 def allreduce_counts(counts, group=None):
-    """Sum an int64 count vector over all ranks.  Accepts a numpy array (reduced through a CPU tensor: gloo) or a torch
-    tensor on any device (reduced in place: NCCL for CUDA tensors).  Without an initialised process group it is the
-    identity, so single-GPU callers need no special case."""
+    """Sum an int64 count vector over all ranks through torch.distributed (host-side logic and CPU tests; the product path
+    reduces the device-resident vector with mb_allreduce_counts, see map_and_count_sharded).  Accepts a numpy array or a torch
+    tensor.  Under the NCCL backend a numpy array travels through a CUDA tensor.  Without an initialised process group it is
+    the identity, so single-GPU callers need no special case."""
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return counts
     if isinstance(counts, np.ndarray):
         t = torch.from_numpy(np.ascontiguousarray(counts, dtype=np.int64).copy())
+        if dist.get_backend(group) == "nccl":
+            t = t.cuda()
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-        return t.numpy()
+        return t.cpu().numpy()
     dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
     return counts
 
 
-def map_and_count_sharded(aligner, cat: np.ndarray, off: np.ndarray, mode: str = "query_length", mapq_min: int = 60, group=None):
+def map_and_count_sharded(aligner, cat: np.ndarray, off: np.ndarray, mode: str = "query_length", mapq_min: int = 60, group=None,
+                          comm: "Comm | None" = None, cigars: bool = True):
     """Map this rank's share of a batch on its GPU and return (global per-target counts, global [mapped, unmapped,
-    ambiguous] read classes, local Hits).  `aligner` is a monica_b200.mappy_shim.Aligner bound to this rank's device."""
+    ambiguous] read classes, local Hits).  `aligner` is a monica_b200.mappy_shim.Aligner bound to this rank's device.
+    With `comm` (a shard.Comm) the counting and the all-reduce stay on the device: mb_count_last on the device-resident hits,
+    then ONE NCCL all-reduce issued by the library (mb_allreduce_counts).  Without it the host-side vector is reduced through
+    torch.distributed (CPU tests over gloo)."""
     import torch.distributed as dist
     rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     cat_r, off_r, _ = shard_reads(cat, off, rank, world)
-    hits = aligner.map_batch(cat=cat_r, off=off_r)
+    hits = aligner.map_batch(cat=cat_r, off=off_r, cigars=cigars)
+    if comm is not None:
+        counts, ncls = aligner.count_last(mapq_min, mode, comm=comm)
+        return counts, ncls, hits
     counts, ncls, _, _ = aligner.count(hits, mapq_min, mode)
     both = np.concatenate([np.asarray(counts, dtype=np.int64), np.asarray(ncls, dtype=np.int64)])
     both = allreduce_counts(both, group)

@@ -146,6 +146,7 @@ void mm2o_sketch(const char *str, int len, int w, int k, uint32_t rid, mm128_v *
 int64_t mm2o_sketch_buf(const char *str, int len, int w, int k, uint32_t rid, uint64_t *out_xy, int64_t cap);
 
 mm2o_idx_t *mm2o_idx_build(int n_seq, const char **names, const char **seqs, const int64_t *lens, int w, int k);
+mm2o_idx_t *mm2o_idx_build_mt(int n_seq, const char **names, const char **seqs, const int64_t *lens, int w, int k, int n_threads);
 void mm2o_idx_destroy(mm2o_idx_t *mi);
 const uint64_t *mm2o_idx_get(const mm2o_idx_t *mi, uint64_t minier, int *n);
 int32_t mm2o_idx_cal_max_occ(const mm2o_idx_t *mi, float f);
@@ -159,6 +160,9 @@ void mm2o_trace_destroy(mm2o_trace_t *t);
 
 /* batch mapping over n reads with n_threads pthreads; results[i] allocated, free each with mm2o_result_destroy */
 void mm2o_map_batch(const mm2o_idx_t *mi, const mm2o_opt_t *opt, int n, const char *cat, const int64_t *off, int n_threads, mm2o_result_t **results);
+
+/* struct-of-arrays export of a mapped batch (two passes: sizes, then data); see mm2o_map.c */
+int64_t mm2o_batch_export(mm2o_result_t **results, int n, int32_t *fields, int64_t *hit_off, uint32_t *cigar, int64_t *n_cigar_words);
 
 /* stand-alone DP entry for kernel parity tests */
 void mm2o_ksw_set_simd(int on);   /* 1: SSE4.1 16-lane core (default), 0: scalar statement of the same lanes */

@@ -5,6 +5,7 @@
  * PARITY UNPINNED -- see mm2o.h.
  */
 #include <stdlib.h>
+#include <pthread.h>
 #include <string.h>
 #include <assert.h>
 #include <stdio.h>
@@ -222,7 +223,43 @@ static int cmp_hy(const void *a_, const void *b_)
 /* index.c mm_idx_gen()/worker_post(): one record per distinct hash, positions sorted by y.
  * The bucket/khash layout of upstream is an implementation detail; lookups return the same
  * (n, sorted position list) and mm_idx_cal_max_occ sees the same multiset of counts. */
-mm2o_idx_t *mm2o_idx_build(int n_seq, const char **names, const char **seqs, const int64_t *lens, int w, int k)
+/* sketch the contigs on several threads (contig i -> its own vector), then concatenate in contig order: the same array a
+ * sequential pass produces */
+typedef struct { int n_seq; const char **seqs; const int64_t *lens; int w, k; mm128_v *per; volatile int next; pthread_mutex_t mu; } sk_job_t;
+static void *sk_worker(void *arg)
+{
+	sk_job_t *j = (sk_job_t*)arg;
+	for (;;) {
+		int s;
+		pthread_mutex_lock(&j->mu); s = j->next++; pthread_mutex_unlock(&j->mu);
+		if (s >= j->n_seq) break;
+		if (j->lens[s] > 0) mm2o_sketch(j->seqs[s], (int)j->lens[s], j->w, j->k, (uint32_t)s, &j->per[s]);
+	}
+	return 0;
+}
+
+/* stable LSD radix sort of the minimizers on the hash (x >> 8): equal hashes keep their (contig, position) order, which is
+ * the order by y that upstream's worker_post establishes with its own sort */
+static void sort_by_hash(mm128_t *a, size_t n, int key_bits)
+{
+	mm128_t *tmp, *src = a, *dst;
+	int shift;
+	if (n < 2) return;
+	tmp = (mm128_t*)malloc(n * sizeof(mm128_t));
+	dst = tmp;
+	for (shift = 0; shift < key_bits; shift += 11) {
+		size_t cnt[2049], i;
+		memset(cnt, 0, sizeof(cnt));
+		for (i = 0; i < n; ++i) ++cnt[((src[i].x >> 8) >> shift & 2047) + 1];
+		for (i = 1; i <= 2048; ++i) cnt[i] += cnt[i - 1];
+		for (i = 0; i < n; ++i) dst[cnt[(src[i].x >> 8) >> shift & 2047]++] = src[i];
+		{ mm128_t *t = src; src = dst; dst = t; }
+	}
+	if (src != a) memcpy(a, src, n * sizeof(mm128_t));
+	free(tmp);
+}
+
+mm2o_idx_t *mm2o_idx_build_mt(int n_seq, const char **names, const char **seqs, const int64_t *lens, int w, int k, int n_threads)
 {
 	mm2o_idx_t *mi = (mm2o_idx_t*)calloc(1, sizeof(mm2o_idx_t));
 	mm128_v a = {0,0,0};
@@ -245,9 +282,29 @@ mm2o_idx_t *mm2o_idx_build(int n_seq, const char **names, const char **seqs, con
 			uint64_t pos = o + j;
 			mi->S[pos>>3] |= c << ((pos & 7) << 2); /* mm_seq4_set */
 		}
-		if (lens[s] > 0) mm2o_sketch(seqs[s], (int)lens[s], w, k, (uint32_t)s, &a);
 	}
-	qsort(a.a, a.n, sizeof(mm128_t), cmp_hy);
+	{
+		sk_job_t job; pthread_t th[256]; int t; size_t tot = 0, at = 0;
+		if (n_threads < 1) n_threads = 1;
+		if (n_threads > 256) n_threads = 256;
+		if (n_threads > n_seq) n_threads = n_seq > 0 ? n_seq : 1;
+		job.n_seq = n_seq, job.seqs = seqs, job.lens = lens, job.w = w, job.k = k, job.next = 0;
+		job.per = (mm128_v*)calloc(n_seq > 0 ? n_seq : 1, sizeof(mm128_v));
+		pthread_mutex_init(&job.mu, 0);
+		for (t = 0; t < n_threads; ++t) pthread_create(&th[t], 0, sk_worker, &job);
+		for (t = 0; t < n_threads; ++t) pthread_join(th[t], 0);
+		pthread_mutex_destroy(&job.mu);
+		for (s = 0; s < n_seq; ++s) tot += job.per[s].n;
+		a.n = a.m = tot;
+		a.a = (mm128_t*)malloc((tot + 1) * sizeof(mm128_t));
+		for (s = 0; s < n_seq; ++s) {
+			if (job.per[s].n) memcpy(a.a + at, job.per[s].a, job.per[s].n * sizeof(mm128_t));
+			at += job.per[s].n;
+			free(job.per[s].a);
+		}
+		free(job.per);
+	}
+	sort_by_hash(a.a, a.n, 2 * k);
 	mi->n_pos = a.n;
 	for (i = 0, mi->n_keys = 0; i < a.n; ++i)
 		if (i == 0 || (a.a[i].x>>8) != (a.a[i-1].x>>8)) ++mi->n_keys;
@@ -272,6 +329,11 @@ mm2o_idx_t *mm2o_idx_build(int n_seq, const char **names, const char **seqs, con
 		mi->tab[h] = (uint32_t)(i + 1);
 	}
 	return mi;
+}
+
+mm2o_idx_t *mm2o_idx_build(int n_seq, const char **names, const char **seqs, const int64_t *lens, int w, int k)
+{
+	return mm2o_idx_build_mt(n_seq, names, seqs, lens, w, k, 1);
 }
 
 void mm2o_idx_destroy(mm2o_idx_t *mi)

@@ -1283,3 +1283,28 @@ void mm2o_map_batch(const mm2o_idx_t *mi, const mm2o_opt_t *opt, int n, const ch
 	free(th);
 	pthread_mutex_destroy(&b.mu);
 }
+
+/* ---- struct-of-arrays export of a mapped batch (checker side of the full-batch parity runs in bench.py / tests) ----
+ * Pass 1 (fields == NULL): returns the number of hits and stores the number of CIGAR words in *n_cigar_words.
+ * Pass 2: fields[n_hits * 22] in the column order of mm2o_hit_t (cigar_off excluded), hit_off[n + 1], cigar[n_cigar_words]. */
+int64_t mm2o_batch_export(mm2o_result_t **results, int n, int32_t *fields, int64_t *hit_off, uint32_t *cigar, int64_t *n_cigar_words)
+{
+	int64_t nh = 0, nc = 0;
+	int i, j;
+	for (i = 0; i < n; ++i) {
+		const mm2o_result_t *r = results[i];
+		if (hit_off) hit_off[i] = nh;
+		for (j = 0; j < r->n_hits; ++j) {
+			const mm2o_hit_t *h = &r->hits[j];
+			if (fields) {
+				memcpy(fields + (nh + j) * 22, h, 22 * sizeof(int32_t));
+				memcpy(cigar + nc, r->cigar_pool + h->cigar_off, (size_t)h->n_cigar * 4);
+			}
+			nc += h->n_cigar;
+		}
+		nh += r->n_hits;
+	}
+	if (hit_off) hit_off[n] = nh;
+	if (n_cigar_words) *n_cigar_words = nc;
+	return nh;
+}

@@ -105,6 +105,8 @@ def lib():
         L.mm2o_sketch_buf.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_int64]
         L.mm2o_idx_build.restype = C.c_void_p
         L.mm2o_idx_build.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_void_p, C.c_int, C.c_int]
+        L.mm2o_idx_build_mt.restype = C.c_void_p
+        L.mm2o_idx_build_mt.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.mm2o_idx_destroy.argtypes = [C.c_void_p]
         L.mm2o_idx_cal_max_occ.restype = C.c_int32
         L.mm2o_idx_cal_max_occ.argtypes = [C.c_void_p, C.c_float]
@@ -115,6 +117,8 @@ def lib():
         L.mm2o_trace_new.restype = C.POINTER(Trace)
         L.mm2o_trace_destroy.argtypes = [C.POINTER(Trace)]
         L.mm2o_map_batch.argtypes = [C.c_void_p, C.POINTER(Opt), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.mm2o_batch_export.restype = C.c_int64
+        L.mm2o_batch_export.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
         L.mm2o_ksw_extd2.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int8, C.c_void_p,
                                      C.c_int8, C.c_int8, C.c_int8, C.c_int8, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.POINTER(Ez)]
@@ -221,16 +225,17 @@ def ksw_ll_i16(query: np.ndarray, target: np.ndarray, q=4, e=2, mat=None):
 class Index:
     """Oracle index over named sequences (index.c mm_idx_gen)."""
 
-    def __init__(self, names, seqs, w: int = 10, k: int = 15):
+    def __init__(self, names, seqs, w: int = 10, k: int = 15, n_threads: int = 0):
         L = lib()
         n = len(names)
-        self._bufs = [_as_bytes(s) for s in seqs]
+        # uint8 arrays are passed by address (no copy: the 4 Gb configuration would not fit twice); anything else goes through bytes
+        self._bufs = [s if isinstance(s, np.ndarray) and s.dtype == np.uint8 and s.flags["C_CONTIGUOUS"] else np.frombuffer(_as_bytes(s), dtype=np.uint8) for s in seqs]
         nm = (C.c_char_p * n)(*[x.encode() if isinstance(x, str) else x for x in names])
-        sq = (C.c_char_p * n)(*self._bufs)
+        sq = (C.c_void_p * n)(*[b.ctypes.data for b in self._bufs])
         lens = np.array([len(b) for b in self._bufs], dtype=np.int64)
         self.names = list(names)
         self.lens = lens
-        self.h = L.mm2o_idx_build(n, nm, sq, lens.ctypes.data, w, k)
+        self.h = L.mm2o_idx_build_mt(n, nm, sq, lens.ctypes.data, w, k, n_threads or (os.cpu_count() or 1))
         self.opt = default_opt()
         L.mm2o_mapopt_update(C.byref(self.opt), self.h)
 
@@ -316,6 +321,39 @@ class Index:
                 tot[k] += getattr(r, k)
             L.mm2o_result_destroy(arr[i])
         return out, tot
+
+    def map_batch_soa(self, cat: np.ndarray, off: np.ndarray, n_threads: int = 1):
+        """Map a concatenated batch and return the hits as arrays: dict(fields={name: int32[n_hits]}, hit_off int64[n+1],
+        cigar uint32[...], cigar_off int64[n_hits], totals, seconds) -- the checker side of full-batch parity runs.  `seconds` is
+        the wall time of the mapping call alone (the CPU-baseline figure)."""
+        import time
+        L = lib()
+        n = len(off) - 1
+        cat = np.ascontiguousarray(cat, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        arr = (C.POINTER(Result) * n)()
+        t0 = time.perf_counter()
+        L.mm2o_map_batch(self.h, C.byref(self.opt), n, cat.ctypes.data, off.ctypes.data, n_threads, arr)
+        seconds = time.perf_counter() - t0
+        ncw = C.c_int64(0)
+        nh = L.mm2o_batch_export(arr, n, None, None, None, C.byref(ncw))
+        fields = np.zeros((max(nh, 1), 22), dtype=np.int32)
+        hit_off = np.zeros(n + 1, dtype=np.int64)
+        cigar = np.zeros(max(ncw.value, 1), dtype=np.uint32)
+        L.mm2o_batch_export(arr, n, fields.ctypes.data, hit_off.ctypes.data, cigar.ctypes.data, C.byref(ncw))
+        tot = dict(n_mini=0, n_anchor=0, chain_cells=0, dp_cells=0, n_dp_calls=0)
+        for i in range(n):
+            r = arr[i].contents
+            for k in tot:
+                tot[k] += getattr(r, k)
+            L.mm2o_result_destroy(arr[i])
+        fields = fields[:nh]
+        names = HIT_FIELDS[:22]
+        cols = {nm: np.ascontiguousarray(fields[:, j]) for j, nm in enumerate(names)}
+        cigar_off = np.zeros(nh, dtype=np.int64)
+        if nh:
+            cigar_off[1:] = np.cumsum(cols["n_cigar"][:-1].astype(np.int64))
+        return dict(fields=cols, hit_off=hit_off, cigar=cigar[:ncw.value], cigar_off=cigar_off, totals=tot, seconds=seconds)
 
     def map_batch_raw(self, cat: np.ndarray, off: np.ndarray, n_threads: int = 1):
         """Timing entry: map the batch, return only totals (no Python-side unpacking in the timed region)."""
