@@ -165,6 +165,9 @@ const char *mb_fastq_header(const mb_fastq_t *fq, int64_t i, int64_t *len, int32
 int  mb_fastq_ids_unique(const mb_fastq_t *fq);
 int  mb_fastq_route(const mb_fastq_t *fq, const int8_t *dest, const char *const *new_id, const uint8_t *focus,
                     const char *mapped_path, const char *unmapped_path, const char *ambiguous_path, const char *focus_path);
+/* the same with the mapped reads' new ids given as a table: read i takes ids[target[i]] (one entry per contig / tax unit) */
+int  mb_fastq_route_targets(const mb_fastq_t *fq, const int8_t *dest, const int32_t *target, const char *const *ids, int32_t n_ids, const uint8_t *focus,
+                            const char *mapped_path, const char *unmapped_path, const char *ambiguous_path, const char *focus_path);
 void mb_fastq_free(mb_fastq_t *fq);
 
 /* ---- database builder (host side, no device needed) ----

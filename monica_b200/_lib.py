@@ -75,7 +75,7 @@ SYMBOLS = [
     "mb_count", "mb_count_last", "mb_count_device_ptr", "mb_count_fetch", "mb_normalize_last",
     "mb_comm_unique_id", "mb_comm_init", "mb_comm_free", "mb_allreduce_counts",
     "mb_sketch", "mb_seed", "mb_chain", "mb_dp_batch", "mb_ll_batch", "mb_int_peak", "mb_stream",
-    "mb_fastq_load", "mb_fastq_n", "mb_fastq_seqs", "mb_fastq_header", "mb_fastq_ids_unique", "mb_fastq_route", "mb_fastq_free",
+    "mb_fastq_load", "mb_fastq_n", "mb_fastq_seqs", "mb_fastq_header", "mb_fastq_ids_unique", "mb_fastq_route", "mb_fastq_route_targets", "mb_fastq_free",
     "mb_db_build",
 ]
 
@@ -146,6 +146,7 @@ def lib():
     L.mb_fastq_header.restype = C.POINTER(C.c_char)
     L.mb_fastq_ids_unique.argtypes = [vp]
     L.mb_fastq_route.argtypes = [vp, vp, vp, vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p]
+    L.mb_fastq_route_targets.argtypes = [vp, vp, vp, vp, i32, vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p]
     L.mb_fastq_free.argtypes = [vp]
     L.mb_fastq_free.restype = None
     L.mb_count_fetch.argtypes = [vp, vp]

@@ -139,21 +139,30 @@ class _Tally(dict):
             self[tax_unit] = Counter({accession: amount})
 
 
+LAST_BREAKDOWN = None   # seconds spent in the stages of the last whole-file call (diagnostic; bench.py reports it)
+
+
 def _aligner_whole_file(sample, sample_name, index, mode, mapping_quality, overnight, focus_species,
                         mapped_folder, unmapped_folder, ambiguous_folder, focus_folder):
     """The common case of `aligner` -- one index, nothing carried over, distinct read ids -- without a Python loop over the
-    reads: native FASTQ ingest (mb_fastq_load), one device pipeline, hit filter + best_hit + counting on the device
-    (mb_count), native routed writers (mb_fastq_route).  Returns None when the file does not qualify (duplicate ids), so
-    the caller falls back to the per-record path, which reproduces the reference's dictionary semantics."""
+    reads: native FASTQ ingest (mb_fastq_load: mmap, parallel record scan, sequences gathered into page-locked memory), one
+    device pipeline, hit filter + best_hit + counting on the device (mb_count), a vectorised tally (per-contig sums folded by
+    name in first-occurrence order, which is the reference's dict order), native routed writers (mb_fastq_route_targets:
+    writev straight from the input pages).  Returns None when the file does not qualify (duplicate ids), so the caller falls
+    back to the per-record path, which reproduces the reference's dictionary semantics."""
     import ctypes as C
+    import time
     import numpy as np
     from . import _lib
+    global LAST_BREAKDOWN
     L = _lib.lib()
     fq = C.c_void_p()
+    t0 = time.perf_counter()
     _lib.check(L.mb_fastq_load(os.fsencode(sample), C.byref(fq)))
     try:
         if not L.mb_fastq_ids_unique(fq):
             return None
+        t1 = time.perf_counter()
         n = int(L.mb_fastq_n(fq))
         offp = C.POINTER(C.c_int64)()
         catp = L.mb_fastq_seqs(fq, C.byref(offp))
@@ -163,31 +172,47 @@ def _aligner_whole_file(sample, sample_name, index, mode, mapping_quality, overn
         if mapping_quality is None and (hits.is_primary != 0).any():
             raise TypeError("'>=' not supported between instances of 'int' and 'NoneType'")
         _, _, read_class, read_best = index.count(hits, 0 if mapping_quality is None else mapping_quality, None)
+        t2 = time.perf_counter()
         contigs = index.seq_names
-        dest = np.zeros(n, np.int8)                       # 0 unmapped, 1 mapped, 2 ambiguous (mb_count's classes)
-        dest[read_class == 1] = 1
-        dest[read_class == 2] = 2
+        dest = read_class.astype(np.int8, copy=True)      # 0 unmapped, 1 mapped, 2 ambiguous (mb_count's classes)
+        mapped = np.nonzero(dest == 1)[0]
+        best = read_best[mapped]
+        rid = hits.rid[best].astype(np.int64) if len(mapped) else np.zeros(0, np.int64)
+        # per contig: (tax unit written into the record id, tax unit before the `overnight` cut, accession)
+        parts = [c.split(sep=':') for c in contigs]
+        unit_full = [p[0] for p in parts]
+        unit = [u.split(sep='_')[0] if overnight else u for u in unit_full]
+        ids = (C.c_char_p * max(len(contigs), 1))(*[u.encode() for u in unit])
+        target = np.full(max(n, 1), -1, np.int32)
+        target[mapped] = rid
+        focus = None
+        if focus_species:
+            is_focus = np.array([u in focus_species for u in unit_full], dtype=bool)
+            focus = np.zeros(max(n, 1), np.uint8)
+            focus[mapped] = is_focus[rid]
         tally = _Tally()
-        new_ids = (C.c_char_p * max(n, 1))()
-        focus = np.zeros(max(n, 1), np.uint8)
-        lens = np.diff(off)
-        keep = {}                                         # keeps the encoded tax-unit strings alive for the C call
-        for i in np.nonzero(dest == 1)[0]:
-            h = int(read_best[i])
-            ctg = contigs[int(hits.rid[h])]
-            parts = ctg.split(sep=':')
-            tax_unit, accession = parts[0], parts[1]
-            if tax_unit in focus_species:
-                focus[i] = 1
-            if overnight:
-                tax_unit = tax_unit.split(sep='_')[0]
-            new_ids[i] = keep.setdefault(tax_unit, tax_unit.encode())
-            tally.add(mode, tax_unit, accession, int(lens[i]), int(hits.mlen[h]))
-        _lib.check(L.mb_fastq_route(fq, dest.ctypes.data_as(C.c_void_p), C.cast(new_ids, C.c_void_p),
-                                    focus.ctypes.data_as(C.c_void_p) if focus_species else None,
-                                    os.fsencode(os.path.join(mapped_folder, sample)), os.fsencode(os.path.join(unmapped_folder, sample)),
-                                    os.fsencode(os.path.join(ambiguous_folder, sample)),
-                                    os.fsencode(os.path.join(focus_folder, sample)) if focus_species else None))
+        if mode in _MODES and len(mapped):
+            lens = np.diff(off)
+            amount = np.ones(len(mapped), np.int64) if mode == 'basic' else lens[mapped].astype(np.int64) if mode == 'query_length' \
+                else hits.mlen[best].astype(np.int64)
+            total = np.zeros(len(contigs), np.int64)
+            np.add.at(total, rid, amount)
+            seen, first = np.unique(rid, return_index=True)
+            for r in seen[np.argsort(first)]:            # first-occurrence order = the order in which the reference creates its dict keys
+                if len(parts[r]) < 2:
+                    raise IndexError('list index out of range')   # the reference indexes ctg.split(':')[1]
+                if unit[r] in tally:
+                    tally[unit[r]].update({parts[r][1]: int(total[r])})
+                else:
+                    tally[unit[r]] = Counter({parts[r][1]: int(total[r])})
+        t3 = time.perf_counter()
+        _lib.check(L.mb_fastq_route_targets(fq, dest.ctypes.data_as(C.c_void_p), target.ctypes.data_as(C.c_void_p), C.cast(ids, C.c_void_p), len(contigs),
+                                            focus.ctypes.data_as(C.c_void_p) if focus is not None else None,
+                                            os.fsencode(os.path.join(mapped_folder, sample)), os.fsencode(os.path.join(unmapped_folder, sample)),
+                                            os.fsencode(os.path.join(ambiguous_folder, sample)),
+                                            os.fsencode(os.path.join(focus_folder, sample)) if focus_species else None))
+        t4 = time.perf_counter()
+        LAST_BREAKDOWN = {"fastq_load": t1 - t0, "map_and_count": t2 - t1, "tally": t3 - t2, "route_write": t4 - t3}
         return dict(tally)
     finally:
         L.mb_fastq_free(fq)

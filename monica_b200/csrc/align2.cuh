@@ -163,7 +163,8 @@ k_ztest_ll(AlignCtx c, DpTask *__restrict__ tasks, const ZCand *__restrict__ can
 		int qe, te;
 		// qseq2[i] = complement of qseq[q_end - 1 - i]
 		const int sc = mb_ll_warp([&](int col) { const int b = qv.at(z.q_end - 1 - col); return b >= 4 ? 4 : 3 - b; },
-		                          [&](int row) { return tv.at(z.t_st + row); }, z.q_len, z.t_len, opt, scr, false, &qe, &te, lane);
+		                          [&](int row) { return tv.at(z.t_st + row); }, z.q_len, z.t_len, opt, scr, false, &qe, &te, lane,
+		                          max(opt.min_chain_score * opt.a, opt.min_dp_max));   // only `score >= both thresholds` is asked
 		__syncwarp();
 		if (lane == 0) {
 			int code = (sc >= opt.min_chain_score * opt.a && sc >= opt.min_dp_max) ? 2 : 0;

@@ -1,0 +1,301 @@
+// align_cta.cuh -- k_dp_cta: the block-exact ksw_extd2 kernel of align.cuh (k_dp) with one CTA of 256 threads per task.
+//
+// k_dp gives a task to ONE warp and walks its anti-diagonals 32 cells at a time; a band-limited extension over a 5 kb
+// window is ~10,000 dependent diagonals of up to 24 such steps each, tens of milliseconds for a single warp, and those
+// few long tasks are what the other DP kernels end up waiting for (second passes, Z-drop split rounds, the inversion
+// pass: phases in which nothing else is running).  Here the cells of a diagonal are spread over 256 threads (three cells
+// per thread at w = 751), the per-diagonal state lives in the same shared-memory arrays with upstream's layout, and a
+// diagonal costs two barriers: every thread first LOADS what its cells need (own column state, the left neighbour's x, v,
+// x2 from before this diagonal, the stored score), then computes and STORES.  The semantics are k_dp's, statement for
+// statement: 16-aligned block ranges, stale scores outside the fill range, exact per-diagonal maximum with upstream's
+// SSE-lane tie order, Z-drop, approximate H0 walk.  The traceback is done by warp 0, which fetches 32 cells of the current
+// diagonal per round trip.
+#pragma once
+#include "align.cuh"
+
+#define DPC_THREADS 256
+#define DPC_SMEM_MAX (100 * 1024)
+
+__global__ void __launch_bounds__(DPC_THREADS)
+k_dp_cta(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const int32_t *__restrict__ n_order, int32_t *__restrict__ work_ctr,
+         const uint8_t *__restrict__ codes, const uint32_t *__restrict__ S, const uint8_t *__restrict__ pool,
+         uint8_t *__restrict__ p_scr, size_t p_stride, int8_t *__restrict__ g_ws, size_t g_stride, int32_t *__restrict__ h_scr, size_t h_stride,
+         uint32_t *__restrict__ cigar_pool, DpScoring sc, unsigned long long *__restrict__ cells_out, int smem_bytes)
+{
+	extern __shared__ __align__(16) int8_t dpc_smem[];
+	__shared__ long long s_red[DPC_THREADS / 32];
+	__shared__ int s_task;
+	const unsigned FULL = 0xffffffffu;
+	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	uint8_t *P = p_scr + (size_t)blockIdx.x * p_stride;
+	unsigned long long cells = 0;
+	const int n_total = *n_order;
+	for (;;) {
+		__syncthreads();
+		if (tid == 0) s_task = atomicAdd(work_ctr, 1);
+		__syncthreads();
+		const int oi = s_task;
+		if (oi >= n_total) break;
+		DpTask &T = tasks[order[oi]];
+		const int qlen = T.qlen, tlen = T.tlen, flag = T.flag, zdrop = T.zdrop, end_bonus = T.end_bonus;
+		if (tid == 0) dp_reset(T);
+		if (T.skip) { if (tid == 0) T.zdropped = 1; continue; }
+		if (qlen <= 0 || tlen <= 0) continue;
+		int8_t q = sc.q, e = sc.e, q2 = sc.q2, e2 = sc.e2;
+		if (q2 + e2 < q + e) { int8_t t_ = q; q = q2, q2 = t_; t_ = e; e = e2, e2 = t_; }
+		const int qe = q + e, qe2 = q2 + e2;
+		int w = T.w;
+		if (w < 0) w = tlen > qlen ? tlen : qlen;
+		const int tlen_ = (tlen + 15) / 16, qlen_ = (qlen + 15) / 16;
+		int n_col_ = qlen < tlen ? qlen : tlen;
+		n_col_ = ((n_col_ < w + 1 ? n_col_ : w + 1) + 15) / 16 + 1;
+		const int ncol16 = n_col_ * 16;
+		const int T16 = tlen_ * 16;
+		const bool with_exact = !(flag & MB_EZ_APPROX_MAX);
+		const bool right = (flag & MB_EZ_RIGHT) != 0;
+		int long_thres = e != e2 ? (q2 - q) / (e - e2) - 1 : 0;
+		if (q2 + e2 + long_thres * e2 > q + e + long_thres * e) ++long_thres;
+		const int long_diff = long_thres * (e - e2) - (q2 - q) - e2;
+		const size_t ws_need = (size_t)T16 * 8 + (size_t)qlen_ * 16 + 16;
+		const size_t h_need = with_exact ? (size_t)T16 * 4 : 0;
+		const bool in_smem = ((ws_need + 15) & ~(size_t)15) + h_need <= (size_t)smem_bytes;
+		int8_t *ws = in_smem ? dpc_smem : g_ws + (size_t)blockIdx.x * g_stride;
+		int32_t *H = (in_smem && with_exact) ? reinterpret_cast<int32_t*>(ws + ((ws_need + 15) & ~(size_t)15)) : h_scr + (size_t)blockIdx.x * h_stride;
+		int8_t *u = ws, *v = u + T16, *x = v + T16, *y = x + T16, *x2 = y + T16, *y2 = x2 + T16, *s = y2 + T16;
+		uint8_t *sf = (uint8_t*)(s + T16), *qr = sf + T16;
+		const int8_t I1 = (int8_t)(-q - e), I2 = (int8_t)(-q2 - e2);
+		{
+			QView qv; qv.codes = T.q_comp == 2 ? pool : codes; qv.idx0 = T.q_idx0; qv.step = T.q_step; qv.comp = T.q_comp == 1;
+			TView tv; tv.S = S; tv.bytes = pool; tv.idx0 = T.t_idx0; tv.step = T.t_step; tv.packed = T.t_packed;
+			for (int t = tid; t < T16; t += DPC_THREADS) {
+				u[t] = I1, v[t] = I1, x[t] = I1, y[t] = I1, x2[t] = I2, y2[t] = I2, s[t] = 0;
+				sf[t] = t < tlen ? (uint8_t)tv.at(t) : 0;
+				if (with_exact) H[t] = MB_KSW_NEG_INF;
+			}
+			for (int t = tid; t < qlen_ * 16 + 16; t += DPC_THREADS) qr[t] = t < qlen ? (uint8_t)qv.at(qlen - 1 - t) : 0;
+		}
+		__syncthreads();
+		// ez state: every thread keeps the same copy
+		int ez_max = 0, ez_max_t = -1, ez_max_q = -1, ez_mqe = MB_KSW_NEG_INF, ez_mqe_t = -1, ez_mte = MB_KSW_NEG_INF, ez_score = MB_KSW_NEG_INF, ez_zdropped = 0;
+		int32_t H0 = 0, last_H0_t = 0;
+		int last_st = -1, last_en = -1;
+		const int n_rows = qlen + tlen - 1;
+		auto bnd = [&](int r) { return (int8_t)(r == 0 ? -q - e : r < long_thres ? -e : r == long_thres ? long_diff : -e2); };
+		for (int r = 0; r < n_rows; ++r) {
+			int st = 0, en = tlen - 1;
+			if (st < r - qlen + 1) st = r - qlen + 1;
+			if (en > r) en = r;
+			if (st < (r - w + 1) >> 1) st = (r - w + 1) >> 1;
+			if (en > (r + w) >> 1) en = (r + w) >> 1;
+			if (st > en) { ez_zdropped = 1; break; }
+			const int st0 = st, en0 = en;
+			st = st / 16 * 16, en = (en + 16) / 16 * 16 - 1;
+			const int fill_end = min(st0 + ((en0 - st0) / 16 + 1) * 16, T16);   // scores are refreshed for [st0, fill_end)
+			const int span_end = max(en + 1, fill_end);
+			const uint8_t *qrr = qr + (qlen - 1 - r);
+			// ---- phase A: loads (everything a cell reads is from before this diagonal) ----
+			constexpr int KMAX = 4;  // (752 + 30) / 256 cells per thread, rounded up
+			int8_t uo[KMAX], yo[KMAX], y2o[KMAX], xl[KMAX], vl[KMAX], x2l[KMAX], zz[KMAX];
+			int32_t hold[KMAX], hprev = 0;
+			bool fresh[KMAX];
+			#pragma unroll
+			for (int k = 0; k < KMAX; ++k) {
+				const int t = st + tid + k * DPC_THREADS;
+				fresh[k] = false; uo[k] = yo[k] = y2o[k] = xl[k] = vl[k] = x2l[k] = zz[k] = 0; hold[k] = 0;
+				if (t >= span_end) continue;
+				if (t >= st0 && t < fill_end) {
+					const uint8_t sq = sf[t], sq2 = qrr[t];
+					zz[k] = (sq == 4 || sq2 == 4) ? sc.sc_N : (sq == sq2 ? sc.sc_mch : sc.sc_mis);
+					fresh[k] = true;
+				} else if (t <= en) zz[k] = s[t];
+				if (t > en) continue;
+				uo[k] = u[t], yo[k] = y[t], y2o[k] = y2[t];
+				if (t > st) xl[k] = x[t - 1], vl[k] = v[t - 1], x2l[k] = x2[t - 1];
+				else if (st > 0) {
+					if (st - 1 >= last_st && st - 1 <= last_en) xl[k] = x[st - 1], x2l[k] = x2[st - 1], vl[k] = v[st - 1];
+					else xl[k] = I1, x2l[k] = I2, vl[k] = I1;
+				} else { xl[k] = I1, x2l[k] = I2; vl[k] = bnd(r); }
+				if (en >= r && t == r) { yo[k] = I1, y2o[k] = I2; uo[k] = bnd(r); }
+				if (with_exact && r > 0) {
+					if (t >= st0 && t <= en0) hold[k] = H[t];
+					if (t == en0 && en0 > 0) hprev = H[en0 - 1];
+				}
+			}
+			__syncthreads();
+			// ---- phase B: compute and store ----
+			long long best = ((long long)MB_KSW_NEG_INF << 32);
+			#pragma unroll
+			for (int k = 0; k < KMAX; ++k) {
+				const int t = st + tid + k * DPC_THREADS;
+				if (t >= span_end) continue;
+				if (fresh[k]) s[t] = zz[k];
+				if (t > en) continue;
+				int8_t z = zz[k];
+				const int8_t xt1 = xl[k], vt1 = vl[k], x2t1 = x2l[k], ut = uo[k];
+				int8_t a = (int8_t)(xt1 + vt1), b = (int8_t)(yo[k] + ut), a2 = (int8_t)(x2t1 + vt1), b2 = (int8_t)(y2o[k] + ut);
+				int8_t d;
+				if (!right) {
+					d = a > z ? 1 : 0;   z = z > a ? z : a;
+					d = b > z ? 2 : d;   z = z > b ? z : b;
+					d = a2 > z ? 3 : d;  z = z > a2 ? z : a2;
+					d = b2 > z ? 4 : d;  z = z > b2 ? z : b2;
+				} else {
+					d = z > a ? 0 : 1;   z = z > a ? z : a;
+					d = z > b ? d : 2;   z = z > b ? z : b;
+					d = z > a2 ? d : 3;  z = z > a2 ? z : a2;
+					d = z > b2 ? d : 4;  z = z > b2 ? z : b2;
+				}
+				z = z < sc.sc_mch ? z : sc.sc_mch;
+				const int8_t un = (int8_t)(z - vt1), vn = (int8_t)(z - ut);
+				u[t] = un, v[t] = vn;
+				int8_t tmp = (int8_t)(z - q);
+				a = (int8_t)(a - tmp), b = (int8_t)(b - tmp);
+				tmp = (int8_t)(z - q2);
+				a2 = (int8_t)(a2 - tmp), b2 = (int8_t)(b2 - tmp);
+				if (!right) {
+					x[t]  = (int8_t)((a  > 0 ? a  : 0) - qe);  if (a  > 0) d |= 0x08;
+					y[t]  = (int8_t)((b  > 0 ? b  : 0) - qe);  if (b  > 0) d |= 0x10;
+					x2[t] = (int8_t)((a2 > 0 ? a2 : 0) - qe2); if (a2 > 0) d |= 0x20;
+					y2[t] = (int8_t)((b2 > 0 ? b2 : 0) - qe2); if (b2 > 0) d |= 0x40;
+				} else {
+					x[t]  = (int8_t)((0 > a  ? 0 : a)  - qe);  if (!(0 > a))  d |= 0x08;
+					y[t]  = (int8_t)((0 > b  ? 0 : b)  - qe);  if (!(0 > b))  d |= 0x10;
+					x2[t] = (int8_t)((0 > a2 ? 0 : a2) - qe2); if (!(0 > a2)) d |= 0x20;
+					y2[t] = (int8_t)((0 > b2 ? 0 : b2) - qe2); if (!(0 > b2)) d |= 0x40;
+				}
+				P[(size_t)r * ncol16 + (t - st)] = (uint8_t)d;
+				if (with_exact) {
+					if (r > 0) {
+						if (t >= st0 && t < en0) {
+							const int32_t h = hold[k] + (int32_t)vn;
+							H[t] = h;
+							const int en1 = st0 + (en0 - st0) / 4 * 4;
+							const unsigned rank = t < en1 ? 1u + ((unsigned)((t - st0) & 3) << 22) + (unsigned)((t - st0) >> 2) : 1u + (4u << 22) + (unsigned)(t - en1);
+							const long long key = ((long long)h << 32) | (unsigned)(0x7fffffffu - rank);
+							best = key > best ? key : best;
+						}
+						if (t == en0) {
+							const int32_t he = en0 > 0 ? hprev + (int32_t)un : hold[k] + (int32_t)vn;
+							H[en0] = he;
+							const long long key = ((long long)he << 32) | (unsigned)0x7fffffffu;
+							best = key > best ? key : best;
+						}
+					} else if (t == 0) H[0] = (int32_t)vn - qe;
+				}
+			}
+			if (with_exact && r > 0) {
+				#pragma unroll
+				for (int dlt = 16; dlt > 0; dlt >>= 1) { const long long o = __shfl_xor_sync(FULL, best, dlt); best = o > best ? o : best; }
+				if (lane == 0) s_red[wid] = best;
+			}
+			__syncthreads();
+			cells += tid == 0 ? (unsigned)(en0 - st0 + 1) : 0u;
+			if (with_exact) {
+				int32_t max_H, max_t;
+				if (r > 0) {
+					long long bb = s_red[0];
+					#pragma unroll
+					for (int k = 1; k < DPC_THREADS / 32; ++k) { const long long o = s_red[k]; bb = o > bb ? o : bb; }
+					max_H = (int32_t)(bb >> 32);
+					const int en1 = st0 + (en0 - st0) / 4 * 4;
+					const unsigned rank = 0x7fffffffu - (unsigned)(bb & 0xffffffffu);
+					if (rank == 0) max_t = en0;
+					else if (rank < 1u + (4u << 22)) { const unsigned rr = rank - 1; max_t = st0 + (int)((rr & ((1u << 22) - 1)) << 2) + (int)(rr >> 22); }
+					else max_t = en1 + (int)(rank - 1u - (4u << 22));
+				} else { max_H = (int32_t)v[0] - qe, max_t = 0; }
+				if (en0 == tlen - 1) { const int32_t h = H[en0]; if (h > ez_mte) ez_mte = h; }
+				if (r - st0 == qlen - 1) { const int32_t h = H[st0]; if (h > ez_mqe) ez_mqe = h, ez_mqe_t = st0; }
+				bool brk = false;
+				if (max_H > ez_max) { ez_max = max_H, ez_max_t = max_t, ez_max_q = r - max_t; }
+				else if (max_t >= ez_max_t && r - max_t >= ez_max_q) {
+					const int tl = max_t - ez_max_t, ql = (r - max_t) - ez_max_q;
+					const int l = tl > ql ? tl - ql : ql - tl;
+					if (zdrop >= 0 && ez_max - max_H > zdrop + l * e2) { ez_zdropped = 1; brk = true; }
+				}
+				if (brk) break;
+				if (r == qlen + tlen - 2 && en0 == tlen - 1) ez_score = H[tlen - 1];
+			} else {
+				if (r > 0) {
+					if (last_H0_t >= st0 && last_H0_t <= en0 && last_H0_t + 1 >= st0 && last_H0_t + 1 <= en0) {
+						const int32_t d0 = v[last_H0_t], d1 = u[last_H0_t + 1];
+						if (d0 > d1) H0 += d0;
+						else H0 += d1, ++last_H0_t;
+					} else if (last_H0_t >= st0 && last_H0_t <= en0) {
+						H0 += v[last_H0_t];
+					} else {
+						++last_H0_t, H0 += u[last_H0_t];
+					}
+				} else H0 = v[0] - qe, last_H0_t = 0;
+				if (r == qlen + tlen - 2 && en0 == tlen - 1) ez_score = H0;
+			}
+			last_st = st, last_en = en;
+		}
+		__syncthreads();
+		// ---- backtrack: warp 0; 32 cells of the current diagonal per fetch, ksw_backtrack's state machine replayed through shuffles ----
+		if (wid == 0) {
+			int reach_end = 0, n_cigar = 0;
+			int i0 = -1, j0 = -1;
+			const bool rev_cigar = flag & MB_EZ_REV_CIGAR;
+			if (!ez_zdropped && !(flag & MB_EZ_EXTZ_ONLY)) i0 = tlen - 1, j0 = qlen - 1;
+			else if (!ez_zdropped && (flag & MB_EZ_EXTZ_ONLY) && ez_mqe + end_bonus > ez_max) reach_end = 1, i0 = ez_mqe_t, j0 = qlen - 1;
+			else if (ez_max_t >= 0 && ez_max_q >= 0) i0 = ez_max_t, j0 = ez_max_q;
+			uint32_t *cigar = cigar_pool + T.cigar_off;
+			uint32_t cur_op = 0; int cur_len = 0;
+			auto push = [&](uint32_t op, int len) {
+				if (cur_len > 0 && op != cur_op) { if (lane == 0) cigar[n_cigar] = (uint32_t)cur_len << 4 | cur_op; ++n_cigar; cur_len = 0; }
+				cur_op = op, cur_len += len;
+			};
+			auto range = [&](int r, int &st, int &en) {
+				st = 0, en = tlen - 1;
+				if (st < r - qlen + 1) st = r - qlen + 1;
+				if (en > r) en = r;
+				if (st < (r - w + 1) >> 1) st = (r - w + 1) >> 1;
+				if (en > (r + w) >> 1) en = (r + w) >> 1;
+				st = st / 16 * 16, en = (en + 16) / 16 * 16 - 1;
+			};
+			if (i0 >= 0 && j0 >= 0) {
+				int i = i0, j = j0, state = 0;
+				while (i >= 0 && j >= 0) {
+					const int ci = i - lane, cj = j - lane;
+					uint32_t raw = 0xffu; // off the matrix or outside the computed range: stops a run
+					if (ci >= 0 && cj >= 0) {
+						int st, en; range(ci + cj, st, en);
+						if (ci >= st && ci <= en) raw = P[(size_t)(ci + cj) * ncol16 + ci - st];
+					}
+					int k = 0;
+					if (state == 0) { // leading cells of the diagonal whose direction is "match" (d == 0)
+						const unsigned stop = __ballot_sync(FULL, (raw & 7u) != 0u || raw == 0xffu);
+						k = stop ? __ffs(stop) - 1 : 32;
+						if (k) { push(0, k); i -= k, j -= k; }
+					}
+					if (k < 32 && i >= 0 && j >= 0) {
+						const uint32_t rk = __shfl_sync(FULL, raw, k);
+						int st, en, force = -1;
+						range(i + j, st, en);
+						if (i < st) force = 2;
+						if (i > en) force = 1;
+						const uint32_t tmp = force < 0 ? rk : 0u;
+						if (state == 0) state = tmp & 7;
+						else if (!(tmp >> (state + 2) & 1)) state = 0;
+						if (state == 0) state = tmp & 7;
+						if (force >= 0) state = force;
+						if (state == 0) { push(0, 1); --i, --j; }
+						else if (state == 1 || state == 3) { push(2, 1); --i; }
+						else { push(1, 1); --j; }
+					}
+				}
+				if (i >= 0) push(2, i + 1);
+				if (j >= 0) push(1, j + 1);
+				if (cur_len > 0) { if (lane == 0) cigar[n_cigar] = (uint32_t)cur_len << 4 | cur_op; ++n_cigar; }
+				__syncwarp();
+				if (!rev_cigar)
+					for (int k = lane; k < n_cigar >> 1; k += 32) { uint32_t t_ = cigar[k]; cigar[k] = cigar[n_cigar - 1 - k], cigar[n_cigar - 1 - k] = t_; }
+			}
+			if (lane == 0) {
+				T.score = ez_score, T.max = ez_max, T.max_q = ez_max_q, T.max_t = ez_max_t, T.mqe = ez_mqe, T.mqe_t = ez_mqe_t;
+				T.zdropped = ez_zdropped, T.reach_end = reach_end, T.n_cigar = n_cigar;
+			}
+		}
+	}
+	if (tid == 0 && cells_out && cells) atomicAdd(cells_out, cells);
+}

@@ -171,9 +171,10 @@ k_dp_band(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 					// well inside both bands (or outside a matrix, where anything may be computed): no predicates needed
 					const int dlo = t0 - j, dhi = t0 + C - 1 - j;
 					const bool inA = j < gA.Q && t0 < gA.T, inB = hasB && j < gB.Q && t0 < gB.T;
-					const bool plainA = !inA || (t0 + C <= gA.T && t0 > 0 && dlo > -(gA.w - 40) && dhi < gA.w - 40);
-					const bool plainB = !inB || (t0 + C <= gB.T && t0 > 0 && dlo > -(gB.w - 40) && dhi < gB.w - 40);
+					const bool plainA = !inA || (t0 + C <= gA.T && dlo > -(gA.w - 40) && dhi < gA.w - 40);
+					const bool plainB = !inB || (t0 + C <= gB.T && dlo > -(gB.w - 40) && dhi < gB.w - 40);
 					if (plainA && plainB) {
+						if (t0 == 0) { XL = X_INIT, X2L = X2_INIT; VL = dpf_pack2(8 * (rowbnd(j) + B)); }   // column 0: the row boundary
 						#pragma unroll
 						for (int c = 0; c < C; ++c) {
 							const uint32_t z0 = dpf_prmt(LA, LB, SEL[c]);

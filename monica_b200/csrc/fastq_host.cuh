@@ -310,20 +310,48 @@ struct Sink {
 	std::string small;              // new ids + separators live here (reserved up front: pointers stay valid)
 	bool ok = true; std::string err;
 	void add(const void *p, size_t n) { if (n) { struct iovec v; v.iov_base = const_cast<void*>(p); v.iov_len = n; iov.push_back(v); } }
-	void flush_to_file() {
-		const int fd = open(path, O_WRONLY | O_CREAT | O_APPEND, 0666);
-		if (fd < 0) { ok = false; err = std::string("cannot append to ") + path; return; }
-		size_t i = 0;
-		while (i < iov.size() && ok) {
-			const int cnt = (int)std::min<size_t>(iov.size() - i, 1024);
-			ssize_t w = writev(fd, &iov[i], cnt);
-			if (w < 0) { ok = false; err = std::string("write failed: ") + path; break; }
-			// advance over fully written entries; finish a partially written one
-			while (w > 0 && i < iov.size()) {
+	// write iov[lo, hi) at file offset `pos` (pwritev: several threads fill disjoint ranges of one sink)
+	bool write_range(int fd, size_t lo, size_t hi, off_t pos) {
+		size_t i = lo;
+		while (i < hi) {
+			const int cnt = (int)std::min<size_t>(hi - i, 1024);
+			ssize_t w = pwritev(fd, &iov[i], cnt, pos);
+			if (w < 0) return false;
+			pos += w;
+			while (w > 0 && i < hi) { // advance over fully written entries; finish a partially written one
 				if ((size_t)w >= iov[i].iov_len) { w -= (ssize_t)iov[i].iov_len; ++i; }
 				else { iov[i].iov_base = (char*)iov[i].iov_base + w; iov[i].iov_len -= (size_t)w; w = 0; }
 			}
 		}
+		return true;
+	}
+	void flush_to_file() {
+		// appended like the reference does (open mode 'a'): the records go behind whatever the file holds already
+		const int fd = open(path, O_WRONLY | O_CREAT, 0666);
+		if (fd < 0) { ok = false; err = std::string("cannot append to ") + path; return; }
+		struct stat sb;
+		if (fstat(fd, &sb) != 0) { ok = false; err = std::string("cannot stat ") + path; close(fd); return; }
+		size_t total = 0;
+		for (const struct iovec &v : iov) total += v.iov_len;
+		int T = total > ((size_t)32 << 20) ? 4 : 1;
+		if (T > 1 && ftruncate(fd, sb.st_size + (off_t)total) != 0) T = 1;
+		if (T == 1) ok = write_range(fd, 0, iov.size(), sb.st_size);
+		else {
+			std::vector<size_t> cut(T + 1, iov.size()); std::vector<off_t> pos(T + 1, 0);
+			cut[0] = 0; pos[0] = sb.st_size;
+			size_t acc = 0; int k = 1;
+			for (size_t i = 0; i < iov.size() && k < T; ++i) {
+				if (acc >= total / T * k) { cut[k] = i; pos[k] = sb.st_size + (off_t)acc; ++k; }
+				acc += iov[i].iov_len;
+			}
+			for (; k <= T; ++k) { cut[k] = iov.size(); pos[k] = sb.st_size + (off_t)total; }
+			std::vector<char> good(T, 1);
+			std::vector<std::thread> th;
+			for (int t = 0; t < T; ++t) th.emplace_back([&, t]() { good[t] = write_range(fd, cut[t], cut[t + 1], pos[t]) ? 1 : 0; });
+			for (auto &x : th) x.join();
+			for (int t = 0; t < T; ++t) if (!good[t]) ok = false;
+		}
+		if (!ok && err.empty()) err = std::string("write failed: ") + path;
 		if (close(fd) != 0 && ok) { ok = false; err = std::string("write failed: ") + path; }
 	}
 };

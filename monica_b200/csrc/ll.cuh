@@ -31,8 +31,9 @@ static __host__ __device__ inline bool mb_ll_scoring_ok(const mb_opt_t &o)
 
 // QF(c): query code of column c (0 <= c < ql), TF(i): target code of row i (0 <= i < tl).  Returns the maximum score;
 // *qe / *te as upstream (or -1).  want_pos = false skips the end-position bookkeeping.  All lanes get the same results.
+// `enough`: stop as soon as the maximum reaches it (the returned score is then a lower bound >= enough).
 template <typename QF, typename TF>
-MB_D int mb_ll_warp(QF qf, TF tf, int ql, int tl, const mb_opt_t &o, int *__restrict__ scr, bool want_pos, int *qe, int *te, int lane)
+MB_D int mb_ll_warp(QF qf, TF tf, int ql, int tl, const mb_opt_t &o, int *__restrict__ scr, bool want_pos, int *qe, int *te, int lane, int enough = 0x7fffffff)
 {
 	const unsigned FULL = 0xffffffffu;
 	const int slen = (ql + 7) >> 3, P = slen << 3;
@@ -91,6 +92,7 @@ MB_D int mb_ll_warp(QF qf, TF tf, int ql, int tl, const mb_opt_t &o, int *__rest
 			if (oh > key_h || (oh == key_h && os > key_s)) key_h = oh, key_s = os;
 		}
 		if (key_h >= gmax) gmax = key_h, best_te = i, best_slot = key_s;
+		if (gmax >= enough) break;   // score-only callers that test a threshold need no more
 		__syncwarp();
 	}
 	if (want_pos && best_slot >= 0) { *te = best_te; *qe = best_slot / 8 + (best_slot % 8) * slen; }

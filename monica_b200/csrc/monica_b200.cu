@@ -24,6 +24,7 @@
 #include "dp_fast.cuh"
 #include "dp_ext.cuh"
 #include "dp_band.cuh"
+#include "align_cta.cuh"
 
 thread_local std::string g_mb_err;
 static thread_local std::chrono::steady_clock::time_point g_dbg_t0 = std::chrono::steady_clock::now();
@@ -165,6 +166,7 @@ static ThreadCtx *make_ctx(int device)
 	std::call_once(g_const_once[device & 15], [&]() {
 		CK(cudaMemcpyToSymbol(c_nt4, h_nt4, 256));
 		CK(cudaFuncSetAttribute(k_dp, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM_MAX));
+		CK(cudaFuncSetAttribute(k_dp_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_SMEM_MAX));
 	});
 	return c;
 }
@@ -633,8 +635,10 @@ static __host__ __device__ inline DpGeom dp_geom(int qlen, int tlen, int w)
 #define DP_NEXACT 6                 // exact-kernel classes by direction-matrix size: <=64K, <=256K, <=1M, <=4M, <=16M, larger
 #define DP_XBASE DPF_NCLASS          // extension fast-path classes follow the gap-fill fast-path classes
 #define DP_BBASE (2 * DPF_NCLASS)   // then the packed band kernel's classes (large / band-limited gap fills)
-#define DP_EBASE (2 * DPF_NCLASS + DPB_NCLASS)   // then the exact-kernel classes
-#define DP_NCLS (2 * DPF_NCLASS + DPB_NCLASS + DP_NEXACT)
+#define DP_EBASE (2 * DPF_NCLASS + DPB_NCLASS)   // then the exact-kernel classes (one warp per task)
+#define DP_NCTA 4                    // and the CTA-per-task exact kernel for the large ones (exact classes 2..5)
+#define DP_CBASE (DP_EBASE + DP_NEXACT)
+#define DP_NCLS (DP_CBASE + DP_NCTA)
 static __host__ __device__ inline int dp_exact_class(size_t p_bytes)
 {
 	int k = 0;
@@ -682,7 +686,10 @@ __global__ void k_dp_classify(const DpTask *__restrict__ tasks, const int32_t *_
 		else {
 			DpGeom g = dp_geom(t.qlen, t.tlen, t.w);
 			if (t.skip) g.p_bytes = g.ws_bytes = g.h_ints = 0;
-			cls = DP_EBASE + dp_exact_class(g.p_bytes);
+			const int ec = dp_exact_class(g.p_bytes);
+			int wd = t.w < 0 ? (t.tlen > t.qlen ? t.tlen : t.qlen) : t.w;
+			int dw = t.qlen < t.tlen ? t.qlen : t.tlen; dw = dw < wd + 1 ? dw : wd + 1;      // widest diagonal
+			cls = (ec >= 2 && dw + 48 <= DPC_THREADS * 4) ? DP_CBASE + (ec - 2) : DP_EBASE + ec;
 			m0 = (unsigned)g.p_bytes, m1 = (unsigned)g.ws_bytes, m2 = (unsigned)g.h_ints;
 		}
 	}
@@ -819,6 +826,36 @@ struct DpRunner {
 		// complete), largest class first: a handful of long band-limited tasks give each launch a long tail of a few busy
 		// warps, which the fast kernels on `st` fill
 		bool side[MB_NSIDE] = {};
+		for (int b = DP_NCTA - 1; b >= 0; --b) { // the large exact tasks: one CTA per task (align_cta.cuh), largest class first
+			const int cls = DP_CBASE + b;
+			cudaStream_t st2 = c.st2[b & 1];
+			const int64_t cnt = h_ctr[cls];
+			if (cnt == 0) continue;
+			size_t p_stride = ((size_t)h_max[cls * 3 + 0] + 255) & ~(size_t)255;
+			const size_t g_stride = ((size_t)h_max[cls * 3 + 1] + 255) & ~(size_t)255;
+			size_t h_stride = ((size_t)h_max[cls * 3 + 2] + 63) & ~(size_t)63;
+			if (p_stride == 0) p_stride = 256;
+			if (h_stride == 0) h_stride = 64;
+			const size_t need = ((g_stride + 15) & ~(size_t)15) + h_stride * 4 + 64;
+			const int smem = (int)(need < DPC_SMEM_MAX ? need : DPC_SMEM_MAX);
+			int per_sm = (200 * 1024) / (smem > 4096 ? smem : 4096); if (per_sm < 1) per_sm = 1; if (per_sm > 4) per_sm = 4;
+			int n_cta = (int)std::min<int64_t>(cnt, (int64_t)c.num_sms * per_sm);
+			const size_t per_cta = p_stride + g_stride + h_stride * 4;
+			while (n_cta > 1 && (size_t)n_cta * per_cta > ((size_t)24 << 30)) n_cta = (n_cta + 1) / 2;
+			uint8_t *p_scr = ar.get<uint8_t>((size_t)n_cta * p_stride);
+			int8_t *g_ws = ar.get<int8_t>((size_t)n_cta * g_stride + 16);
+			int32_t *h_scr = ar.get<int32_t>((size_t)n_cta * h_stride);
+			int32_t *wc = ar.get<int32_t>(1);
+			CK(cudaMemsetAsync(wc, 0, sizeof(int32_t), st2));
+			cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+			cudaEventRecord(e0, st2);
+			k_dp_cta<<<n_cta, DPC_THREADS, smem, st2>>>(tasks, lists + (int64_t)cls * n, ctr + cls, wc, codes, S, pool,
+				p_scr, p_stride, g_ws, g_stride, h_scr, h_stride, cigar_pool, sc, d_cells ? d_cells + 1 : nullptr, smem);
+			{ cudaError_t le = cudaGetLastError(); if (le != cudaSuccess) throw mb_error(MB_ERR_CUDA, std::string("k_dp_cta launch: ") + cudaGetErrorString(le) + " grid " + std::to_string(n_cta) + " smem " + std::to_string(smem)); }
+			cudaEventRecord(e1, st2);
+			evs.emplace_back(e0, e1); ev_fast.push_back(0); n_exact += cnt;
+			++*nl; side[b & 1] = true;
+		}
 		for (int b = DP_NEXACT - 1; b >= 0; --b) {
 			const int cls = DP_EBASE + b;
 			cudaStream_t st2 = c.st2[b & 1]; // exact classes alternate over side streams 0 and 1
@@ -866,7 +903,7 @@ struct DpRunner {
 			const int mq = (int)h_max[cls * 3], mt = (int)h_max[cls * 3 + 1];
 			const int n_strips = (mt + DPB_STRIP - 1) / DPB_STRIP;
 			const size_t stride_words = (DPB_EDGE_WORDS + (size_t)n_strips * (size_t)(mq + 31) * 32 * DPB_CW + 63) & ~(size_t)63;
-			const int max_cta = c.num_sms * (k == 0 ? 8 : 4);
+			const int max_cta = c.num_sms * (k == 0 ? 12 : 8);
 			const int64_t want = cdiv(cnt, 2);
 			const int n_cta = (int)(want < max_cta ? want : max_cta);
 			uint32_t *p_scr = ar.get<uint32_t>((size_t)n_cta * stride_words);
@@ -876,6 +913,7 @@ struct DpRunner {
 			cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
 			cudaEventRecord(e0, sb);
 			k_dp_band<<<n_cta, 32, 0, sb>>>(tasks, lists + (int64_t)cls * n, ctr + cls, wc, codes, S, pool, p_scr, stride_words, cigar_pool, sc, d_cells ? d_cells + 3 : nullptr);
+			{ cudaError_t le = cudaGetLastError(); if (le != cudaSuccess) throw mb_error(MB_ERR_CUDA, std::string("k_dp_band launch: ") + cudaGetErrorString(le) + " grid " + std::to_string(n_cta)); }
 			cudaEventRecord(e1, sb);
 			evs.emplace_back(e0, e1); ev_fast.push_back(3); n_band += cnt;
 			++*nl;
@@ -1107,7 +1145,7 @@ static void map_device_part(mb_index *ix, const mb_opt_t &opt_in, DevPart &part)
 		t0 = t1;
 	};
 	phase("pre-align");
-	const int ll_grid = c.num_sms * 4;
+	const int ll_grid = c.num_sms * 8;
 	int *ll_scr = nullptr;   // scratch of the local-alignment kernels (inversion tests): allocated on first use
 	while (h_n_work > 0) {
 		++round;
@@ -2116,189 +2154,7 @@ extern "C" int mb_ll_batch(int device, const mb_opt_t *opt, mb_ll_task_t *tasks,
 	API_END
 }
 
-// ---------------------------------------------------------------------------------------------
-// FASTQ ingest and routed writers (host side).  Replaces the per-record Biopython loop of
-// /root/reference/monica/genomes/aligner.py:191,212 (SeqIO.parse) and :232,236,243,265 (SeqIO.write): a whole file is
-// parsed in one pass into the concatenated-reads layout mb_map_batch takes, and the mapped / unmapped / ambiguous / focus
-// files are appended in one pass with Biopython's header rule ('@' + description when it starts with the id, else
-// '@' + id + ' ' + description).  No device is needed for these calls.
-// ---------------------------------------------------------------------------------------------
-struct mb_fastq {
-	std::string raw;                       // the decompressed file
-	std::vector<int64_t> head, head_len;   // header line without '@'
-	std::vector<int32_t> id_len;           // up to the first blank / tab
-	std::vector<int64_t> qual, qual_len;   // quality string (single line, or joined copy in `extra`)
-	std::vector<uint8_t> cat;              // concatenated sequences
-	std::vector<int64_t> off;              // [n+1]
-	std::string extra;                     // joined quality strings of multi-line records
-	std::vector<uint8_t> qual_in_extra;
-};
-
-extern "C" int mb_fastq_load(const char *path, mb_fastq_t **out)
-{
-	API_BEGIN
-	if (!path || !out) throw mb_error(MB_ERR_ARG, "bad arguments");
-	std::unique_ptr<mb_fastq> fq(new mb_fastq());
-	{
-		FILE *pf = fopen(path, "rb");
-		if (!pf) throw mb_error(MB_ERR_IO, std::string("cannot open ") + path);
-		unsigned char magic[2] = {0, 0};
-		const size_t got = fread(magic, 1, 2, pf);
-		if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) { // gzip: stream through zlib
-			fclose(pf);
-			gzFile fp = gzopen(path, "rb");
-			if (!fp) throw mb_error(MB_ERR_IO, std::string("cannot open ") + path);
-			gzbuffer(fp, 1 << 20);
-			std::vector<char> buf(1 << 22);
-			int n;
-			while ((n = gzread(fp, buf.data(), (unsigned)buf.size())) > 0) fq->raw.append(buf.data(), (size_t)n);
-			const bool bad = n < 0;
-			gzclose(fp);
-			if (bad) throw mb_error(MB_ERR_IO, std::string("read error in ") + path);
-		} else {                                                 // plain: one read of the whole file
-			fseek(pf, 0, SEEK_END);
-			const long sz = ftell(pf);
-			fseek(pf, 0, SEEK_SET);
-			fq->raw.resize(sz > 0 ? (size_t)sz : 0);
-			const size_t rd = sz > 0 ? fread(&fq->raw[0], 1, (size_t)sz, pf) : 0;
-			fclose(pf);
-			if ((long)rd != (sz > 0 ? sz : 0)) throw mb_error(MB_ERR_IO, std::string("read error in ") + path);
-		}
-	}
-	fq->cat.reserve(fq->raw.size() / 2 + 16);
-	const std::string &s = fq->raw;
-	const int64_t N = (int64_t)s.size();
-	auto line_end = [&](int64_t p) { const void *q = memchr(s.data() + p, '\n', (size_t)(N - p)); return q ? (int64_t)((const char*)q - s.data()) : N; };
-	auto rstrip = [&](int64_t b, int64_t e) { while (e > b && (s[e - 1] == '\r' || s[e - 1] == '\n')) --e; return e; };
-	fq->off.push_back(0);
-	int64_t p = 0;
-	while (p < N) {
-		int64_t e = line_end(p), le = rstrip(p, e);
-		if (le == p) { p = e + 1; continue; }                          // blank line
-		if (s[p] != '@') throw mb_error(MB_ERR_IO, std::string("unexpected line in FASTQ input: ") + path);
-		const int64_t hb = p + 1, hl = le - hb;
-		int32_t idl = 0;
-		while (idl < hl && s[hb + idl] != ' ' && s[hb + idl] != '\t') ++idl;
-		p = e + 1;
-		// sequence lines until '+'
-		int64_t seq_len = 0;
-		for (;;) {
-			if (p >= N) break;
-			e = line_end(p);
-			if (s[p] == '+') break;
-			le = rstrip(p, e);
-			fq->cat.insert(fq->cat.end(), s.begin() + p, s.begin() + le);
-			seq_len += le - p;
-			p = e + 1;
-		}
-		if (p < N) p = line_end(p) + 1;                                  // skip the '+' line
-		// quality lines until as long as the sequence
-		int64_t qb = p, ql = 0; bool multi = false; size_t xb = fq->extra.size();
-		int n_lines = 0;
-		while (ql < seq_len && p < N) {
-			e = line_end(p); le = rstrip(p, e);
-			if (n_lines == 1) { multi = true; fq->extra.append(s, (size_t)qb, (size_t)ql); }
-			if (multi) fq->extra.append(s, (size_t)p, (size_t)(le - p));
-			ql += le - p; ++n_lines;
-			p = e + 1;
-		}
-		fq->head.push_back(hb); fq->head_len.push_back(hl); fq->id_len.push_back(idl);
-		if (multi) { fq->qual.push_back((int64_t)xb); fq->qual_in_extra.push_back(1); }
-		else { fq->qual.push_back(qb); fq->qual_in_extra.push_back(0); }
-		fq->qual_len.push_back(ql);
-		fq->off.push_back((int64_t)fq->cat.size());
-	}
-	*out = fq.release();
-	API_END
-}
-
-extern "C" int64_t mb_fastq_n(const mb_fastq_t *fq) { return fq ? (int64_t)fq->head.size() : 0; }
-extern "C" const uint8_t *mb_fastq_seqs(const mb_fastq_t *fq, const int64_t **off)
-{
-	if (!fq) return nullptr;
-	if (off) *off = fq->off.data();
-	return fq->cat.data();
-}
-extern "C" const char *mb_fastq_header(const mb_fastq_t *fq, int64_t i, int64_t *len, int32_t *id_len)
-{
-	if (!fq || i < 0 || i >= (int64_t)fq->head.size()) return nullptr;
-	if (len) *len = fq->head_len[i];
-	if (id_len) *id_len = fq->id_len[i];
-	return fq->raw.data() + fq->head[i];
-}
-/* 1 if every record id of the file is distinct (the vectorised aligner path needs that; duplicates take the reference's
- * per-record dictionary semantics in Python) */
-extern "C" int mb_fastq_ids_unique(const mb_fastq_t *fq)
-{
-	if (!fq) return 0;
-	std::vector<std::pair<const char*, int32_t>> ids(fq->head.size());
-	for (size_t i = 0; i < ids.size(); ++i) ids[i] = std::make_pair(fq->raw.data() + fq->head[i], fq->id_len[i]);
-	auto less = [](const std::pair<const char*, int32_t> &a, const std::pair<const char*, int32_t> &b) {
-		const int c = memcmp(a.first, b.first, (size_t)std::min(a.second, b.second));
-		return c != 0 ? c < 0 : a.second < b.second;
-	};
-	std::sort(ids.begin(), ids.end(), less);
-	for (size_t i = 1; i < ids.size(); ++i)
-		if (ids[i].second == ids[i - 1].second && memcmp(ids[i].first, ids[i - 1].first, (size_t)ids[i].second) == 0) return 0;
-	return 1;
-}
-
-/* dest[i]: 0 unmapped, 1 mapped, 2 ambiguous, anything else: skip.  new_id[i] (mapped reads only): the tax unit that
- * replaces the record id (aligner.py:242).  focus[i] != 0: also append the ORIGINAL record to focus_path (aligner.py:235-236).
- * Files are opened in append mode like the reference does; a NULL path skips that sink. */
-extern "C" int mb_fastq_route(const mb_fastq_t *fq, const int8_t *dest, const char *const *new_id, const uint8_t *focus,
-                              const char *mapped_path, const char *unmapped_path, const char *ambiguous_path, const char *focus_path)
-{
-	API_BEGIN
-	if (!fq || !dest) throw mb_error(MB_ERR_ARG, "bad arguments");
-	std::string sink[4];
-	const char *paths[4] = { unmapped_path, mapped_path, ambiguous_path, focus_path };
-	const int64_t n = (int64_t)fq->head.size();
-	auto emit = [&](std::string &o, int64_t i, const char *rid) {
-		const char *h = fq->raw.data() + fq->head[i];
-		o.push_back('@');
-		if (rid) { // Bio's writer: description is kept; it equals the title only if its first word is the (new) id
-			const size_t rl = strlen(rid);
-			if (!((size_t)fq->id_len[i] == rl && memcmp(h, rid, rl) == 0)) { o.append(rid, rl); o.push_back(' '); }
-		}
-		o.append(h, (size_t)fq->head_len[i]);
-		o.push_back('\n');
-		o.append((const char*)fq->cat.data() + fq->off[i], (size_t)(fq->off[i + 1] - fq->off[i]));
-		o.append("\n+\n", 3);
-		const char *q = fq->qual_in_extra[i] ? fq->extra.data() + fq->qual[i] : fq->raw.data() + fq->qual[i];
-		o.append(q, (size_t)fq->qual_len[i]);
-		o.push_back('\n');
-	};
-	{ // size the sinks once: a record costs its header, sequence and quality plus separators (and the new id when mapped)
-		size_t need[4] = {0, 0, 0, 0};
-		for (int64_t i = 0; i < n; ++i) {
-			const int d = dest[i];
-			if (d < 0 || d > 2) continue;
-			const size_t rec = (size_t)fq->head_len[i] + (size_t)(fq->off[i + 1] - fq->off[i]) + (size_t)fq->qual_len[i] + 8;
-			need[d] += rec + (d == 1 && new_id && new_id[i] ? strlen(new_id[i]) + 1 : 0);
-			if (focus && focus[i] && focus_path) need[3] += rec;
-		}
-		for (int k = 0; k < 4; ++k) if (paths[k]) sink[k].reserve(need[k] + 16);
-	}
-	for (int64_t i = 0; i < n; ++i) {
-		const int d = dest[i];
-		if (d < 0 || d > 2) continue;
-		if (focus && focus[i] && focus_path) emit(sink[3], i, nullptr);
-		if (!paths[d]) continue;
-		if (d == 1 && (!new_id || !new_id[i])) throw mb_error(MB_ERR_ARG, "mapped read without a new id");
-		emit(sink[d], i, d == 1 ? new_id[i] : nullptr);
-	}
-	for (int k = 0; k < 4; ++k) {
-		if (!paths[k]) continue;
-		FILE *fp = fopen(paths[k], "ab");
-		if (!fp) throw mb_error(MB_ERR_IO, std::string("cannot append to ") + paths[k]);
-		const bool ok = sink[k].empty() || fwrite(sink[k].data(), 1, sink[k].size(), fp) == sink[k].size();
-		if (fclose(fp) != 0 || !ok) throw mb_error(MB_ERR_IO, std::string("write failed: ") + paths[k]);
-	}
-	API_END
-}
-
-extern "C" void mb_fastq_free(mb_fastq_t *fq) { delete fq; }
+#include "fastq_host.cuh"   // FASTQ ingest and routed writers (host side)
 
 // ---- database builder: monica/genomes/database.py:52-67 builder() ----
 // One database<N>.fna.gz = the genomes of a chunk, every record re-headed "<tax_unit>:<accession>" (what the aligner later

@@ -71,7 +71,7 @@ def make_genomes(seed: int, n_genomes: int, genome_len: int, strain_frac: float 
 
 
 # fractions of the read classes described in mbsynth.c (junk insertion, inversion, exact chimera, junk)
-HARD_MIX = dict(f_junkins=0.03, f_inv=0.01, f_chim=0.025, f_junk=0.01)
+HARD_MIX = dict(f_junkins=0.015, f_inv=0.005, f_chim=0.025, f_junk=0.01)
 PLAIN_MIX = dict(f_junkins=0.0, f_inv=0.0, f_chim=0.0, f_junk=0.0)
 
 
