@@ -6,9 +6,11 @@
 // Same machinery as k_dp_fast (dp_fast.cuh): register-resident systolic wavefront, lane L owns 8 consecutive target
 // columns, two tasks per warp in 16x2 packed integer SIMD, values stored as 8*(value + bias) + priority tag.  On top:
 //
-//   * Column strips.  The target is cut into strips of 256 columns (32 lanes x 8); a strip is one pass over all query rows.
-//     What the next strip needs of the previous one -- x, v, x2 of its last column, row by row -- goes through a small
-//     per-warp buffer (written at step j + 31, read by the next pass at step j: in place).
+//   * Column strips, pipelined over the warps of a CTA.  The target is cut into strips of 256 columns (32 lanes x 8); a strip
+//     is one pass over all query rows and belongs to one warp.  What strip k+1 needs of strip k -- x, v, x2 of its last column,
+//     row by row -- goes through a per-strip buffer in global memory; warp k publishes its progress every 32 steps (a counter
+//     in shared memory) and warp k+1 follows a few dozen rows behind, so all strips of a window are in flight at once and a
+//     2048 x 2048 window costs about 2048 + 8*32 steps of latency instead of 8 * 2079.
 //   * upstream's band, exactly.  ksw_extd2_sse walks anti-diagonals r and computes, for each, the 16-ALIGNED column range
 //     [st(r), en(r)] around the in-band range [st0(r), en0(r)]: up to 15 columns on either side of the band are computed
 //     too, from whatever their neighbours hold, and in-band cells at the band edge read them.  Which cell is computed on
@@ -67,16 +69,22 @@ static __host__ __device__ inline int dpb_class(int qlen, int tlen, int w, int f
 	return mx <= 1024 ? 0 : 1;
 }
 
-__global__ void __launch_bounds__(32, 12)
+#define DPB_NW 4                      // warps per CTA; warp w takes strips w, w + 4 (a 2048-column window has 8)
+#define DPB_MAX_STRIPS (DPB_MAX_LEN / DPB_STRIP)
+__global__ void __launch_bounds__(DPB_NW * 32, 3)
 k_dp_band(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const int32_t *__restrict__ n_order, int32_t *__restrict__ work_ctr,
           const uint8_t *__restrict__ codes, const uint32_t *__restrict__ S, const uint8_t *__restrict__ pool,
           uint32_t *__restrict__ p_scr, size_t p_stride_words, uint32_t *__restrict__ cigar_pool, DpScoring sc, unsigned long long *__restrict__ cells_out)
 {
 	constexpr int C = DPB_C, CW = DPB_CW;
 	const unsigned FULL = 0xffffffffu;
-	const int lane = threadIdx.x & 31;
-	uint32_t *EDGE = p_scr + (size_t)blockIdx.x * p_stride_words;      // [row] x (X, V, X2, pad)
-	uint32_t *P = EDGE + DPB_EDGE_WORDS;
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	uint32_t *EDGE = p_scr + (size_t)blockIdx.x * p_stride_words;      // [strip][row] x (X, V, X2, pad)
+	constexpr int NW = DPB_NW;
+	uint32_t *P = EDGE + (size_t)DPB_MAX_STRIPS * DPB_EDGE_WORDS;
+	__shared__ volatile int s_prog[DPB_MAX_STRIPS];   // rows of strip k whose last-column values are in EDGE
+	__shared__ int s_task;
+	__shared__ long long s_acc[NW][2];
 	unsigned long long cells = 0;
 	const int n_total = *n_order;
 	int q = sc.q, e = sc.e, q2 = sc.q2, e2 = sc.e2;
@@ -99,9 +107,11 @@ k_dp_band(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 	const uint32_t MCHC = dpf_pack2(8 * (sc.sc_mch + 2 * B));
 	auto rowbnd = [&](int r) { return r == 0 ? -q - e : r < long_thres ? -e : r == long_thres ? long_diff : -e2; };
 	for (;;) {
-		int oi = 0;
-		if (lane == 0) oi = atomicAdd(work_ctr, 1) * 2;
-		oi = __shfl_sync(FULL, oi, 0);
+		__syncthreads();
+		if (threadIdx.x == 0) s_task = atomicAdd(work_ctr, 1) * 2;
+		if (threadIdx.x < DPB_MAX_STRIPS) s_prog[threadIdx.x] = 0;
+		__syncthreads();
+		const int oi = s_task;
 		if (oi >= n_total) break;
 		const bool hasB = oi + 1 < n_total;
 		DpTask &TA = tasks[order[oi]];
@@ -122,7 +132,8 @@ k_dp_band(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 			const int a = r < gA.Q ? qvA.at(r) : 0, b = r < gB.Q ? qvB.at(r) : 0;
 			la = a < 4 ? MIS4 + (MDIFF << (a * 8)) : N4, lb = b < 4 ? MIS4 + (MDIFF << (b * 8)) : N4;
 		};
-		for (int strip = 0; strip < n_strips; ++strip) {
+		for (int strip = wid; strip < n_strips; strip += NW) {
+			uint32_t *EDGE_IN = EDGE + (size_t)(strip > 0 ? strip - 1 : 0) * DPB_EDGE_WORDS, *EDGE_OUT = EDGE + (size_t)strip * DPB_EDGE_WORDS;
 			const int t0 = strip * DPB_STRIP + lane * C;
 			uint32_t SEL[C], U[C], Y[C], Y2[C], SZ[C];
 			#pragma unroll
@@ -156,13 +167,18 @@ k_dp_band(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 				if ((s & 31) == 0) {
 					if (s) LAc = LAn, LBc = LBn;
 					if (s + 32 < Qm) row_tables(s + 32 + lane, LAn, LBn);
+					if (strip > 0 && s < Qm) { // rows s .. s+31 of the previous strip must have been published
+						const int need = min(s + 32, Qm);
+						while (s_prog[strip - 1] < need) { }
+						__threadfence_block();
+					}
 				}
 				const uint32_t LA0 = __shfl_sync(FULL, LAc, s & 31), LB0 = __shfl_sync(FULL, LBc, s & 31);
 				uint32_t LA = __shfl_up_sync(FULL, LAo, 1), LB = __shfl_up_sync(FULL, LBo, 1);
 				uint32_t XL = __shfl_up_sync(FULL, XLo, 1), VL = __shfl_up_sync(FULL, VLo, 1), X2L = __shfl_up_sync(FULL, X2Lo, 1);
 				if (lane == 0) {
 					LA = LA0, LB = LB0;
-					if (strip > 0 && s < Qm) { const uint4 ev = *reinterpret_cast<const uint4*>(EDGE + 4 * s); XL = ev.x, VL = ev.y, X2L = ev.z; }
+					if (strip > 0 && s < Qm) { const uint4 ev = __ldcg(reinterpret_cast<const uint4*>(EDGE_IN + 4 * s)); XL = ev.x, VL = ev.y, X2L = ev.z; }
 				}
 				LAo = LA, LBo = LB;
 				if (lane_live && j >= 0 && j < Qm) {
@@ -253,10 +269,24 @@ k_dp_band(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 					*reinterpret_cast<uint4*>(dst) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
 				}
 				// the strip's last column, row by row, for the next strip (lane 31 evaluated row s - 31 in this step)
-				if (lane == 31 && strip + 1 < n_strips && j >= 0 && j < Qm) *reinterpret_cast<uint4*>(EDGE + 4 * j) = make_uint4(XLo, VLo, X2Lo, 0u);
+				if (strip + 1 < n_strips) {
+					if (lane == 31 && j >= 0 && j < Qm) __stcg(reinterpret_cast<uint4*>(EDGE_OUT + 4 * j), make_uint4(XLo, VLo, X2Lo, 0u));
+					if ((s & 31) == 31 || s == n_steps - 1) { // publish: rows <= s - 31 are out
+						__threadfence_block();
+						__syncwarp();
+						if (lane == 31) s_prog[strip] = s == n_steps - 1 ? Qm : s - 30;
+					}
+				}
 			}
-			__syncwarp();
 		}
+		// ---- combine the per-strip partial sums of the score path ----
+		#pragma unroll
+		for (int dlt = 16; dlt > 0; dlt >>= 1) { accA += __shfl_xor_sync(FULL, accA, dlt); accB += __shfl_xor_sync(FULL, accB, dlt); }
+		if (lane == 0) s_acc[wid][0] = accA, s_acc[wid][1] = accB;
+		__syncthreads();
+		if (wid != 0) continue;     // the rest (cell count, end scores, traceback) is warp 0's
+		accA = accB = 0;
+		for (int k = 0; k < NW; ++k) accA += s_acc[k][0], accB += s_acc[k][1];
 		{ // in-band cells, as the oracle counts them
 			unsigned long long cc = 0;
 			for (int r = lane; r < gA.Q + gA.T - 1; r += 32) { int st0, en0; dpb_range(gA, r, st0, en0); cc += en0 >= st0 ? (unsigned)(en0 - st0 + 1) : 0u; }
@@ -266,8 +296,6 @@ k_dp_band(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 			cells += cc;
 		}
 		// ---- end scores: z along the main diagonal (8*(z+2B) each), then u along the last row / v along the last column (8*(.+B) each) ----
-		#pragma unroll
-		for (int dlt = 16; dlt > 0; dlt >>= 1) { accA += __shfl_xor_sync(FULL, accA, dlt); accB += __shfl_xor_sync(FULL, accB, dlt); }
 		const int ndA = min(gA.Q, gA.T), ndB = min(gB.Q, gB.T);
 		const int scoreA = (int)(accA >> 3) - 2 * B * ndA - B * (max(gA.Q, gA.T) - ndA);
 		const int scoreB = (int)(accB >> 3) - 2 * B * ndB - B * (max(gB.Q, gB.T) - ndB);
@@ -332,5 +360,5 @@ k_dp_band(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 		}
 		__syncwarp();
 	}
-	if (lane == 0 && cells_out && cells) atomicAdd(cells_out, cells);
+	if (threadIdx.x == 0 && cells_out && cells) atomicAdd(cells_out, cells);
 }

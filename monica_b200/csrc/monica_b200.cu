@@ -902,8 +902,15 @@ struct DpRunner {
 			if (cnt == 0) continue;
 			const int mq = (int)h_max[cls * 3], mt = (int)h_max[cls * 3 + 1];
 			const int n_strips = (mt + DPB_STRIP - 1) / DPB_STRIP;
-			const size_t stride_words = (DPB_EDGE_WORDS + (size_t)n_strips * (size_t)(mq + 31) * 32 * DPB_CW + 63) & ~(size_t)63;
-			const int max_cta = c.num_sms * (k == 0 ? 12 : 8);
+			const size_t stride_words = ((size_t)DPB_MAX_STRIPS * DPB_EDGE_WORDS + (size_t)n_strips * (size_t)(mq + 31) * 32 * DPB_CW + 63) & ~(size_t)63;
+			// Band CTAs are register-heavy and latency-bound; the grid is sized by the band kernel's share of the DP work of this run
+			// (cells, weighted x3: edge cells cost more) so that the gap-fill kernels keep the rest of the machine
+			double w_band = 0, w_fast = 0;
+			for (int kk = 0; kk < DPB_NCLASS; ++kk) w_band += 3.0 * (double)h_ctr[DP_BBASE + kk] * (double)h_max[(DP_BBASE + kk) * 3] * (double)h_max[(DP_BBASE + kk) * 3 + 1];
+			for (int kk = 0; kk < DPF_NCLASS; ++kk) w_fast += (double)h_ctr[kk] * (double)h_max[kk * 3] * (double)(DPF_C[kk] * 32);
+			const double share = w_band / (w_band + w_fast + 1.0);
+			int max_cta = (int)(c.num_sms * 3 * std::min(1.0, share * 3.0 + 0.15));
+			if (max_cta < 16) max_cta = 16;
 			const int64_t want = cdiv(cnt, 2);
 			const int n_cta = (int)(want < max_cta ? want : max_cta);
 			uint32_t *p_scr = ar.get<uint32_t>((size_t)n_cta * stride_words);
@@ -912,7 +919,7 @@ struct DpRunner {
 			CK(cudaMemsetAsync(wc, 0, sizeof(int32_t), sb));
 			cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
 			cudaEventRecord(e0, sb);
-			k_dp_band<<<n_cta, 32, 0, sb>>>(tasks, lists + (int64_t)cls * n, ctr + cls, wc, codes, S, pool, p_scr, stride_words, cigar_pool, sc, d_cells ? d_cells + 3 : nullptr);
+			k_dp_band<<<n_cta, DPB_NW * 32, 0, sb>>>(tasks, lists + (int64_t)cls * n, ctr + cls, wc, codes, S, pool, p_scr, stride_words, cigar_pool, sc, d_cells ? d_cells + 3 : nullptr);
 			{ cudaError_t le = cudaGetLastError(); if (le != cudaSuccess) throw mb_error(MB_ERR_CUDA, std::string("k_dp_band launch: ") + cudaGetErrorString(le) + " grid " + std::to_string(n_cta)); }
 			cudaEventRecord(e1, sb);
 			evs.emplace_back(e0, e1); ev_fast.push_back(3); n_band += cnt;
