@@ -66,6 +66,7 @@ def parse_args():
     ap.add_argument("--parity-full", action="store_true", help="check every hit of the timed batch against the oracle also when it is not the default (N > 1, configs 2 / 4)")
     ap.add_argument("--no-extras", action="store_true", help="skip the streaming / aligner-API sections")
     ap.add_argument("--seed", type=int, default=20251018)
+    ap.add_argument("--plain-reads", action="store_true", help="diagnostic: no hard-case reads (the round-1 kind of workload)")
     return ap.parse_args()
 
 
@@ -78,6 +79,7 @@ def config_of(a):
         c["genome_len"] = a.genome_len
     if a.reads:
         c["reads"] = a.reads
+    c["plain_reads"] = bool(getattr(a, "plain_reads", False))
     return c
 
 
@@ -94,6 +96,8 @@ def make_data(c, seed, rank, world, pinned_alloc=None):
     threads = max(1, (os.cpu_count() or 4) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))))
     names, seqs, gcat, goff = mbsynth.make_genomes(seed, c["genomes"], c["genome_len"], strain_frac=STRAIN_FRAC, threads=threads)
     kw = dict(n50=c["n50"], error=c["error"], sigma=c["sigma"], min_len=c["min_len"], max_len=c["max_len"], threads=threads)
+    if c.get("plain_reads"):
+        kw["classes"] = mbsynth.PLAIN_MIX
     if c["per_gpu"]:           # weak scaling: every rank has its own read set of the stated size
         rseed, n_all, lo, hi = seed + 1 + rank, c["reads"], 0, c["reads"]
         off_all, cls_all = mbsynth.read_lengths(rseed, gcat, goff, n_all, **kw)

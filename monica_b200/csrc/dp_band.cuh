@@ -189,7 +189,11 @@ k_dp_band(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 					const bool inA = j < gA.Q && t0 < gA.T, inB = hasB && j < gB.Q && t0 < gB.T;
 					const bool plainA = !inA || (t0 + C <= gA.T && dlo > -(gA.w - 40) && dhi < gA.w - 40);
 					const bool plainB = !inB || (t0 + C <= gB.T && dlo > -(gB.w - 40) && dhi < gB.w - 40);
-					if (plainA && plainB) {
+					// beyond the block ranges on either side of the band (the corners of a large window): upstream computes nothing there
+					const bool voidA = !inA || dlo > gA.w + 40 || dhi < -(gA.w + 40), voidB = !inB || dlo > gB.w + 40 || dhi < -(gB.w + 40);
+					if (voidA && voidB) {
+						wv[0] = wv[1] = wv[2] = wv[3] = 0u;
+					} else if (plainA && plainB) {
 						if (t0 == 0) { XL = X_INIT, X2L = X2_INIT; VL = dpf_pack2(8 * (rowbnd(j) + B)); }   // column 0: the row boundary
 						#pragma unroll
 						for (int c = 0; c < C; ++c) {

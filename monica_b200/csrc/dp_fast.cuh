@@ -31,6 +31,7 @@
 // The end score is H(tlen-1, qlen-1) = sum_{j<qlen} bnd(j) + sum_{t<tlen} u(t, qlen-1), which is what upstream's
 // approximate H0 tracking telescopes to.  Tasks whose sequences contain an ambiguous base never get here (k_dp_classify).
 #pragma once
+#include <type_traits>
 #include "align.cuh"
 
 #define DPF_WARPS 1
@@ -209,8 +210,10 @@ k_dp_fast(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 		const uint32_t VB0 = dpf_pack2(8 * (dpf_bnd(0, q, e, e2, long_thres, long_diff) + B)), VB1 = dpf_pack2(8 * (-e + B));
 		const uint32_t VB2 = dpf_pack2(8 * (long_diff + B)), VB3 = dpf_pack2(8 * (-e2 + B));
 		uint32_t *dst = P + (size_t)lane * CW;
-		#pragma unroll 2
-		for (int s = 0; s < n_steps; ++s, dst += 32 * CW) {
+		// One step of the wavefront.  CAPTURE: this step may be some lane's last query row (j == QA-1 or QB-1), where the lane adds
+		// its columns' u to the end-score sum; the steps before min(QA, QB) - 1 cannot be, and run without that code.
+		auto step = [&](int s, auto capture) {
+			constexpr bool CAPTURE = decltype(capture)::value;
 			const int j = s - lane;
 			if ((s & 31) == 0) {
 				if (s) LAc = LAn, LBc = LBn;
@@ -259,15 +262,25 @@ k_dp_fast(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 					#pragma unroll
 					for (int k = 0; k < CW; ++k) dst[k] = wv[k];
 				}
-				if (j == QA - 1) {
-					#pragma unroll
-					for (int c = 0; c < C; ++c) if (t0 + c < TLA) sumA += (int)(U[c] & 0xffffu);
-				}
-				if (j == QB - 1) {
-					#pragma unroll
-					for (int c = 0; c < C; ++c) if (t0 + c < TLB) sumB += (int)(U[c] >> 16);
+				if (CAPTURE) {
+					if (j == QA - 1) {
+						#pragma unroll
+						for (int c = 0; c < C; ++c) if (t0 + c < TLA) sumA += (int)(U[c] & 0xffffu);
+					}
+					if (j == QB - 1) {
+						#pragma unroll
+						for (int c = 0; c < C; ++c) if (t0 + c < TLB) sumB += (int)(U[c] >> 16);
+					}
 				}
 			}
+		};
+		{
+			int s = 0;
+			const int s_plain = (QA < QB ? QA : QB) - 1;   // steps [0, s_plain): no lane is on its last query row yet
+			#pragma unroll 2
+			for (; s < s_plain; ++s, dst += 32 * CW) step(s, std::false_type());
+			#pragma unroll 1
+			for (; s < n_steps; ++s, dst += 32 * CW) step(s, std::true_type());
 		}
 		cells += (unsigned long long)TLA * (unsigned)QA + (hasB ? (unsigned long long)TLB * (unsigned)QB : 0ULL); // warp-uniform; lane 0 reports
 		// ---- end scores ----

@@ -555,12 +555,24 @@ static PinPool g_pin_pool;
 
 template <typename T> struct PinVec {
 	T *p = nullptr; size_t n = 0, cap = 0;
+	bool plain = false;   // pageable memory (results assembled on the host from several pieces: never a DMA target)
 	PinVec() {}
 	PinVec(const PinVec&) = delete; PinVec &operator=(const PinVec&) = delete;
-	~PinVec() { g_pin_pool.put(p, cap); }
+	~PinVec() { if (plain) free(p); else g_pin_pool.put(p, cap); }
 	void resize(size_t k) { // contents are NOT preserved or initialised
+		if (plain) { if (k * sizeof(T) > cap) { free(p); cap = k * sizeof(T) + 64; p = (T*)malloc(cap); if (!p) throw mb_error(MB_ERR_NOMEM, "out of host memory"); } n = k; return; }
 		if (k * sizeof(T) > cap) { g_pin_pool.put(p, cap); p = nullptr; cap = 0; p = (T*)g_pin_pool.get(k * sizeof(T), &cap); }
 		n = k;
+	}
+	void append_plain(const T *src, size_t k) { // plain mode only: grow geometrically, keep the contents
+		if ((n + k) * sizeof(T) > cap) {
+			size_t nc = std::max((n + k) * sizeof(T), cap + cap / 2) + 64;
+			T *np = (T*)realloc(p, nc);
+			if (!np) throw mb_error(MB_ERR_NOMEM, "out of host memory");
+			p = np, cap = nc;
+		}
+		if (k) memcpy(p + n, src, k * sizeof(T));
+		n += k;
 	}
 	void assign(size_t k, T v) { resize(k); for (size_t i = 0; i < k; ++i) p[i] = v; }
 	T *data() { return p; } const T *data() const { return p; }
@@ -963,6 +975,7 @@ struct DpRunner {
 				const int k = ord[oi];
 				const int64_t cnt = h_ctr[k];
 				if (cnt == 0) continue;
+				if (getenv("MB_DEBUG")) fprintf(stderr, "[mb] fast class C=%d: %lld tasks, max qlen %d (launch %zu)\n", DPF_C[k], (long long)cnt, (int)h_max[k * 3], evs.size());
 				const int32_t *list = lists + (int64_t)k * n;
 				const int mq = (int)h_max[k * 3];
 				cudaStream_t sf = slot == 0 ? st : c.stf[slot - 1];
@@ -1518,12 +1531,22 @@ static mb_hits *map_in_pieces(mb_index *ix, const mb_opt_t &opt, ThreadCtx &c, c
 		cut.push_back(hi);
 	}
 	const int K = (int)cut.size() - 1;
-	std::vector<std::unique_ptr<mb_hits>> parts(K);
 	struct Kept { size_t fields, hit_off, read_off; int64_t n_hits; int32_t n_reads; };
 	std::vector<Kept> kept;
 	c.store_used = 0;
 	mb_stats_t S; memset(&S, 0, sizeof(S));
 	float ms_h2d = 0;
+	// The caller's result object is put together on the host piece by piece (pageable memory, grown geometrically), so that a
+	// piece's page-locked buffers go back to the pool before the next piece needs them: a 1 M-read batch then page-locks what
+	// one piece returns, not what nine do.
+	std::unique_ptr<mb_hits> H(new mb_hits());
+	H->n_reads = n_reads;
+	H->read_off.assign(h_off, h_off + n_reads + 1);
+	H->fields.plain = H->cigar_off.plain = H->cigar.plain = H->rep_len.plain = H->hit_off.plain = true;
+	H->hit_off.resize(n_reads + 1); H->rep_len.resize(n_reads);
+	std::vector<PinVec<int32_t>> fcol(HIT_NF);   // hit fields by column while the total is unknown
+	for (auto &v : fcol) v.plain = true;
+	int64_t n_h = 0, n_c = 0;
 	for (int k = 0; k < K; ++k) {
 		const int32_t lo = cut[k], n = cut[k + 1] - lo;
 		std::vector<int64_t> po(n + 1);
@@ -1547,7 +1570,7 @@ static mb_hits *map_in_pieces(mb_index *ix, const mb_opt_t &opt, ThreadCtx &c, c
 			k_rebase_offsets<<<(unsigned)cdiv(n + 1, 256), 256, 0, c.st>>>(d_off_all + lo, d_off, n + 1, base);
 		}
 		mb_stats_t st1; memset(&st1, 0, sizeof(st1));
-		parts[k].reset(map_device(ix, opt, c, d_codes, d_off, po.data(), n, total, want, &st1, use_feed ? &feed : nullptr));
+		std::unique_ptr<mb_hits> part(map_device(ix, opt, c, d_codes, d_off, po.data(), n, total, want, &st1, use_feed ? &feed : nullptr));
 		// keep what mb_count_last needs beyond the next arena reset
 		for (const ThreadCtx::LastPart &lp : c.last_parts) {
 			Kept kp; kp.n_hits = lp.n_hits, kp.n_reads = lp.n_reads;
@@ -1557,6 +1580,23 @@ static mb_hits *map_in_pieces(mb_index *ix, const mb_opt_t &opt, ThreadCtx &c, c
 			kept.push_back(kp);
 		}
 		CK(cudaStreamSynchronize(c.st));
+		// append this piece to the caller's result
+		const int64_t m = part->n;
+		if (want) {
+			for (int32_t i = 0; i < n; ++i) { H->hit_off.data()[lo + i] = part->hit_off.data()[i] + n_h; H->rep_len.data()[lo + i] = part->rep_len.data()[i]; }
+			std::vector<std::thread> th;
+			for (int f = 0; f < HIT_NF; ++f) th.emplace_back([&, f]() {
+				const size_t at = fcol[f].n;
+				fcol[f].append_plain(part->fields.data() + (size_t)f * m, (size_t)m);
+				if (f == 0) for (int64_t i = 0; i < m; ++i) fcol[0].p[at + i] += lo;   // read_idx: piece-relative -> batch
+			});
+			const size_t at = H->cigar_off.n;
+			H->cigar_off.append_plain(part->cigar_off.data(), (size_t)m);
+			for (int64_t i = 0; i < m; ++i) H->cigar_off.p[at + i] += n_c;
+			H->cigar.append_plain(part->cigar.data(), part->cigar.size());
+			for (auto &t : th) t.join();
+		}
+		n_h += m, n_c += (int64_t)part->cigar.size();
 		S.n_reads += st1.n_reads, S.n_bases += st1.n_bases, S.n_mini += st1.n_mini, S.n_anchor += st1.n_anchor, S.n_regs += st1.n_regs;
 		S.n_dp_tasks += st1.n_dp_tasks, S.n_dp_pass2 += st1.n_dp_pass2, S.dp_cells += st1.dp_cells, S.n_hits += st1.n_hits;
 		S.n_rounds = std::max(S.n_rounds, st1.n_rounds), S.n_launches += st1.n_launches + (h_cat ? 1 : 0);
@@ -1577,47 +1617,14 @@ static mb_hits *map_in_pieces(mb_index *ix, const mb_opt_t &opt, ThreadCtx &c, c
 		lp.read_off = reinterpret_cast<const int64_t*>(c.store + kp.read_off), lp.n_hits = kp.n_hits, lp.n_reads = kp.n_reads;
 		c.last_parts.push_back(lp);
 	}
-	// ---- one result object for the caller ----
-	std::unique_ptr<mb_hits> H(new mb_hits());
-	H->n_reads = n_reads;
-	H->read_off.assign(h_off, h_off + n_reads + 1);
-	int64_t n_h = 0, n_c = 0;
-	for (int k = 0; k < K; ++k) { n_h += parts[k]->n; n_c += (int64_t)parts[k]->cigar.size(); }
 	H->n = n_h;
-	H->hit_off.resize(n_reads + 1); H->rep_len.resize(n_reads);
-	{
-		int64_t hb = 0;
-		for (int k = 0; k < K; ++k) {
-			const int32_t lo = cut[k], n = cut[k + 1] - lo;
-			for (int32_t i = 0; i < n; ++i) { H->hit_off.data()[lo + i] = parts[k]->hit_off.data()[i] + hb; H->rep_len.data()[lo + i] = parts[k]->rep_len.data()[i]; }
-			hb += parts[k]->n;
-		}
-		H->hit_off.data()[n_reads] = hb;
-	}
-	if (want) {
+	H->hit_off.data()[n_reads] = n_h;
+	if (!want) { for (int32_t i = 0; i < n_reads; ++i) H->hit_off.data()[i] = 0, H->rep_len.data()[i] = 0; }
+	if (want) { // the SoA block [field][hit]
 		H->fields.resize((size_t)HIT_NF * n_h);
 		std::vector<std::thread> th;
-		for (int f = 0; f < HIT_NF; ++f) th.emplace_back([&, f]() {
-			int64_t hb = 0;
-			for (int k = 0; k < K; ++k) {
-				const int64_t m = parts[k]->n;
-				int32_t *d = H->fields.data() + (size_t)f * n_h + hb;
-				if (m) memcpy(d, parts[k]->fields.data() + (size_t)f * m, (size_t)m * 4);
-				if (f == 0) for (int64_t i = 0; i < m; ++i) d[i] += cut[k]; // read_idx: piece-relative -> batch
-				hb += m;
-			}
-		});
+		for (int f = 0; f < HIT_NF; ++f) th.emplace_back([&, f]() { if (n_h) memcpy(H->fields.data() + (size_t)f * n_h, fcol[f].p, (size_t)n_h * 4); });
 		for (auto &t : th) t.join();
-		H->cigar_off.resize(n_h);
-		int64_t hb = 0, cb = 0;
-		std::vector<std::pair<const uint32_t*, size_t>> cg;
-		for (int k = 0; k < K; ++k) {
-			const int64_t m = parts[k]->n;
-			for (int64_t i = 0; i < m; ++i) H->cigar_off.data()[hb + i] = parts[k]->cigar_off.data()[i] + cb;
-			cg.emplace_back(parts[k]->cigar.data(), parts[k]->cigar.size());
-			hb += m, cb += (int64_t)parts[k]->cigar.size();
-		}
-		concat_pin(H->cigar, cg);
 	}
 	if (stats) *stats = S;
 	return H.release();

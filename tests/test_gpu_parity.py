@@ -830,3 +830,37 @@ def test_dp_band_kernel_large_and_band_limited_fills(oracle, lib):
     assert len(recs) > 200
     tasks, cig = _run_dp(lib, opt, recs)
     _check_dp(tasks, cig, recs)
+
+
+def test_sequential_pieces_equal_one_piece(case, lib, monkeypatch):
+    """Batches beyond the scratch budget are mapped piece by piece (MB_PIECE_BASES; BASELINE configs[2] on one GPU is nine
+    pieces): hit arrays, CIGARs, the device-resident counting (count_last) and the resident-reads entry must not notice."""
+    al, oidx, reads, traces = case
+    from monica_b200 import synth
+    cat, off = synth.concat_reads(reads)
+    want = al.map_batch(cat=cat, off=off)
+    cw, nw = al.count_last(60, "query_length")
+    monkeypatch.setenv("MB_PIECE_BASES", "20000")
+    got = al.map_batch(cat=cat, off=off)
+    assert al.last_stats["n_pieces"] >= 4
+    cg, ng = al.count_last(60, "query_length")
+    for f in CMP_FIELDS + ["read_idx"]:
+        assert np.array_equal(getattr(want, f), getattr(got, f)), f
+    assert np.array_equal(want.cigar_pool, got.cigar_pool) and np.array_equal(want.cigar_off, got.cigar_off)
+    assert np.array_equal(want.rep_len, got.rep_len)
+    assert np.array_equal(cw, cg) and np.array_equal(nw, ng)
+    c2, n2, _, _ = al.count(got, 60, "query_length")
+    assert np.array_equal(c2, cw) and np.array_equal(n2, nw)
+    h = al.reads_upload(cat, off)
+    try:
+        res = al.map_resident(h, len(reads), want_hits=True)
+        assert al.last_stats["n_pieces"] >= 4
+        for f in CMP_FIELDS + ["read_idx"]:
+            assert np.array_equal(getattr(want, f), getattr(res, f)), f
+        assert np.array_equal(want.cigar_pool, res.cigar_pool)
+        al.map_resident(h, len(reads), want_hits=False)
+        c3, n3 = al.count_last(60, "basic")
+        c4, n4, _, _ = al.count(want, 60, "basic")
+        assert np.array_equal(c3, c4) and np.array_equal(n3, n4)
+    finally:
+        al.reads_free(h)
