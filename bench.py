@@ -94,7 +94,28 @@ def make_data(c, seed, rank, world, pinned_alloc=None):
     import mbsynth
     from monica_b200 import shard
     threads = max(1, (os.cpu_count() or 4) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))))
-    names, seqs, gcat, goff = mbsynth.make_genomes(seed, c["genomes"], c["genome_len"], strain_frac=STRAIN_FRAC, threads=threads)
+    big = world > 1 and c["genomes"] * c["genome_len"] >= 1_000_000_000 and os.path.isdir("/dev/shm")
+    if big:   # a multi-gigabase database: rank 0 generates it once with all host threads, the other ranks map the same pages
+        import torch.distributed as dist
+        path = f"/dev/shm/monica_b200_genomes_{seed}_{c['genomes']}_{c['genome_len']}"
+        if rank == 0:
+            try:
+                os.sched_setaffinity(0, set(range(os.cpu_count() or 1)))
+            except Exception:
+                pass
+            names, seqs, gcat, goff = mbsynth.make_genomes(seed, c["genomes"], c["genome_len"], strain_frac=STRAIN_FRAC, threads=os.cpu_count() or 4)
+            np.save(path + "_cat.npy", gcat); np.save(path + "_off.npy", goff)
+            del gcat, seqs
+        dist.barrier()
+        gcat = np.load(path + "_cat.npy", mmap_mode="r"); goff = np.load(path + "_off.npy")
+        gcat = np.asarray(gcat)
+        names = [f"Species_{g}:ACC{g:05d}.1" for g in range(c["genomes"])]
+        seqs = [gcat[int(goff[g]):int(goff[g + 1])] for g in range(c["genomes"])]
+        dist.barrier()
+        if rank == 0:
+            make_data.cleanup = [path + "_cat.npy", path + "_off.npy"]
+    else:
+        names, seqs, gcat, goff = mbsynth.make_genomes(seed, c["genomes"], c["genome_len"], strain_frac=STRAIN_FRAC, threads=threads)
     kw = dict(n50=c["n50"], error=c["error"], sigma=c["sigma"], min_len=c["min_len"], max_len=c["max_len"], threads=threads)
     if c.get("plain_reads"):
         kw["classes"] = mbsynth.PLAIN_MIX
@@ -648,6 +669,11 @@ def main():
         }
         print(json.dumps(out))
     al.reads_free(reads_dev)
+    for f in getattr(make_data, "cleanup", []):
+        try:
+            os.remove(f)
+        except OSError:
+            pass
     if comm is not None:
         comm.free()
     if world > 1:

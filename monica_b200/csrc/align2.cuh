@@ -142,13 +142,13 @@ __global__ void k_ztest(AlignCtx c, DpTask *__restrict__ tasks, const int32_t *_
 }
 
 // mm_test_zdrop's inversion test for the candidates of k_ztest: local alignment (ll.cuh) of the target stretch against the
-// reverse complement of the query stretch.  Persistent one-warp CTAs over the candidate list; `scr` = 2*LL_MAX_LEN ints per CTA.
+// reverse complement of the query stretch.  Persistent one-warp CTAs over the candidate list; `scr` = 4*LL_MAX_LEN ints per CTA.
 __global__ void __launch_bounds__(32)
 k_ztest_ll(AlignCtx c, DpTask *__restrict__ tasks, const ZCand *__restrict__ cand, const int32_t *__restrict__ n_cand, int32_t *__restrict__ cursor,
            int32_t *__restrict__ pass2_list, int32_t *__restrict__ n_pass2, int *__restrict__ scr_pool)
 {
 	const int lane = threadIdx.x;
-	int *scr = scr_pool + (size_t)blockIdx.x * (2 * LL_MAX_LEN);
+	int *scr = scr_pool + (size_t)blockIdx.x * (4 * LL_MAX_LEN);
 	const mb_opt_t &opt = c.opt;
 	const int n = *n_cand;
 	for (;;) {
@@ -939,7 +939,7 @@ k_inv_ll(AlignCtx c, ReadArrays ra, const InvTask *__restrict__ ll, const int32_
          DpTask *__restrict__ tasks, InvTask *__restrict__ task_inv, int32_t *__restrict__ cig_cap, int32_t *__restrict__ n_dp)
 {
 	const int lane = threadIdx.x;
-	int *scr = scr_pool + (size_t)blockIdx.x * (2 * LL_MAX_LEN);
+	int *scr = scr_pool + (size_t)blockIdx.x * (4 * LL_MAX_LEN);
 	const mb_opt_t &opt = c.opt;
 	const int n = *n_ll;
 	for (;;) {

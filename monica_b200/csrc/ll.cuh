@@ -15,9 +15,11 @@
 // keeps the LAST row that reaches the global maximum, and within that row the LAST memory slot equal to the maximum wins,
 // where column c lives in slot (c % slen) * 8 + c / slen of the striped layout.
 //
-// One warp per problem, row by row; the 32 lanes take 32 consecutive columns per step.  F along a row is a max-plus prefix
-// (F(c) = max_{c'<c} h0(c') - q - (c-c') e, where h0 is the cell before F is applied), resolved with a 5-step warp scan.
-// H and E of the previous row live in a scratch of 2*P ints per warp.
+// One warp per problem, as a systolic wavefront like the DP kernels: the columns are cut into strips of 256 (32 lanes x 8
+// columns held in registers: H and E of the previous row); lane L works on row s - L at step s, so the horizontal-gap value F
+// and the diagonal H(i-1, c-1) arrive from lane L-1 by shuffle, one step old.  Between strips, each row's last-column H, its
+// outgoing F and the row's running (maximum, best slot) go through a scratch of 4 ints per row.  ~12 integer instructions
+// per cell and no scans; a 1,000 x 1,000 problem takes a fraction of a millisecond.
 #pragma once
 #include "align.cuh"
 
@@ -32,70 +34,79 @@ static __host__ __device__ inline bool mb_ll_scoring_ok(const mb_opt_t &o)
 // QF(c): query code of column c (0 <= c < ql), TF(i): target code of row i (0 <= i < tl).  Returns the maximum score;
 // *qe / *te as upstream (or -1).  want_pos = false skips the end-position bookkeeping.  All lanes get the same results.
 // `enough`: stop as soon as the maximum reaches it (the returned score is then a lower bound >= enough).
+// scr: 4 * LL_MAX_LEN ints.
+#define LL_C 8
 template <typename QF, typename TF>
 MB_D int mb_ll_warp(QF qf, TF tf, int ql, int tl, const mb_opt_t &o, int *__restrict__ scr, bool want_pos, int *qe, int *te, int lane, int enough = 0x7fffffff)
 {
 	const unsigned FULL = 0xffffffffu;
+	constexpr int C = LL_C;
 	const int slen = (ql + 7) >> 3, P = slen << 3;
-	const int gq = o.q, ge = o.e, gqe = o.q + o.e;
-	int *H = scr, *E = scr + P;
+	const int ge = o.e, gqe = o.q + o.e;
+	const int sa = o.a < 0 ? -o.a : o.a, sb = o.b > 0 ? -o.b : o.b, sn = -(o.sc_ambi > 0 ? o.sc_ambi : -o.sc_ambi);
+	int4 *edge = reinterpret_cast<int4*>(scr);   // per row: H(i, last column so far), F leaving it, the row's maximum so far, its best slot
 	*qe = *te = -1;
-	if (ql <= 0) return 0;
-	for (int c = lane; c < P; c += 32) H[c] = 0, E[c] = 0;
+	if (ql <= 0 || tl <= 0) return 0;
+	for (int i = lane; i < tl; i += 32) edge[i] = make_int4(0, 0, 0, -1);
 	__syncwarp();
-	int gmax = 0, best_te = -1, best_slot = -1;
-	for (int i = 0; i < tl; ++i) {
-		const int ct = tf(i);
-		int carry_h = 0;                 // H(i-1, cb-1)
-		int carry_f = -(1 << 28);        // F entering column cb, stored as F + cb*e
-		int row_max = 0, row_slot = -1;  // per lane: best H of this row and the largest slot that holds it
-		for (int cb = 0; cb < P; cb += 32) {
-			const int c = cb + lane;
-			const bool act = c < P;
-			const int hp = act ? H[c] : 0;
-			int diag = __shfl_up_sync(FULL, hp, 1);
-			if (lane == 0) diag = carry_h;
-			carry_h = __shfl_sync(FULL, hp, 31);
-			const int e = act ? E[c] : 0;
-			const int s = (act && c < ql) ? mb_mat(ct, qf(c), o) : 0;
-			int h0 = diag + s; h0 = h0 > e ? h0 : e;                 // >= 0: E never goes below 0
-			// F(c) + c*e = max(carry_f, max_{cb <= c' < c} (h0(c') - q + c'*e)): exclusive prefix max over the lanes
-			int v = act ? h0 - gq + c * ge : -(1 << 28);
-			int incl = v;
-			#pragma unroll
-			for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl = incl > t ? incl : t; }
-			int excl = __shfl_up_sync(FULL, incl, 1);
-			if (lane == 0) excl = -(1 << 28);
-			excl = excl > carry_f ? excl : carry_f;
-			const int f = excl - c * ge;
-			int h = h0 > f ? h0 : f; h = h > 0 ? h : 0;
-			{ const int nf = __shfl_sync(FULL, incl, 31); carry_f = nf > carry_f ? nf : carry_f; }
-			if (act) {
-				H[c] = h;
-				int en = e - ge, t2 = h - gqe;
-				en = en > t2 ? en : t2;
-				E[c] = en > 0 ? en : 0;
-				if (want_pos) {
-					if (h >= row_max) {
-						const int slot = (c % slen) * 8 + c / slen;
-						if (h > row_max || slot > row_slot) row_slot = slot;
-						row_max = h;
-					}
-				} else row_max = row_max > h ? row_max : h;
-			}
-		}
-		// row maximum (and, among the cells that hold it, the largest slot)
-		int key_h = row_max, key_s = row_slot;
+	int lmax = 0;
+	const int n_steps = tl + 31;
+	for (int cb = 0; cb < P; cb += 32 * C) {
+		const int c0 = cb + lane * C;
+		const bool live = c0 < P, last_strip = cb + 32 * C >= P;
+		int qc[C], slot[C], H[C], E[C];
 		#pragma unroll
-		for (int d = 16; d > 0; d >>= 1) {
-			const int oh = __shfl_xor_sync(FULL, key_h, d), os = __shfl_xor_sync(FULL, key_s, d);
-			if (oh > key_h || (oh == key_h && os > key_s)) key_h = oh, key_s = os;
+		for (int c = 0; c < C; ++c) {
+			const int col = c0 + c;
+			qc[c] = col < ql ? qf(col) : 5;                                    // 5: padding column (scores 0 against anything)
+			slot[c] = (want_pos && col < P) ? (col % slen) * 8 + col / slen : -1;
+			H[c] = 0, E[c] = 0;
 		}
-		if (key_h >= gmax) gmax = key_h, best_te = i, best_slot = key_s;
-		if (gmax >= enough) break;   // score-only callers that test a threshold need no more
+		int F_o = 0, Hd_o = 0, rm_o = 0, rs_o = -1, hd_edge = 0;
+		for (int s = 0; s < n_steps; ++s) {
+			const int i = s - lane;
+			int F = __shfl_up_sync(FULL, F_o, 1), Hd = __shfl_up_sync(FULL, Hd_o, 1), rm = __shfl_up_sync(FULL, rm_o, 1), rs = __shfl_up_sync(FULL, rs_o, 1);
+			if (lane == 0) {
+				Hd = hd_edge;                                                    // H(i-1, cb-1)
+				if (s < tl) { const int4 ev = edge[s]; hd_edge = ev.x; F = ev.y; rm = ev.z; rs = ev.w; }
+			}
+			if (live && i >= 0 && i < tl) {
+				const int ct = tf(i);
+				int hd = Hd, f = F;
+				#pragma unroll
+				for (int c = 0; c < C; ++c) {
+					const int sc = qc[c] == 5 ? 0 : (qc[c] > 3 || ct > 3) ? sn : (qc[c] == ct ? sa : sb);
+					int h = hd + sc;
+					h = max(h, E[c]); h = max(h, f); h = max(h, 0);
+					hd = H[c];
+					H[c] = h;
+					const int t = max(h - gqe, 0);
+					E[c] = max(E[c] - ge, t);
+					f = max(f - ge, t);
+					if (want_pos) { if (h > rm || (h == rm && slot[c] > rs)) rm = h, rs = slot[c]; }
+					else rm = max(rm, h);
+				}
+				F_o = f, Hd_o = hd, rm_o = rm, rs_o = rs;
+				lmax = max(lmax, rm);
+				if (lane == 31 || c0 + C >= P) edge[i] = make_int4(H[C - 1], f, rm, rs);    // the strip's (or the matrix's) last live lane
+			}
+			if (!want_pos && (s & 31) == 31 && __any_sync(FULL, lmax >= enough)) return enough;
+		}
 		__syncwarp();
+		(void)last_strip;
 	}
-	if (want_pos && best_slot >= 0) { *te = best_te; *qe = best_slot / 8 + (best_slot % 8) * slen; }
-	else if (want_pos) *te = best_te;
-	return gmax;
+	// upstream keeps the LAST row that reaches the global maximum, and that row's best slot
+	int bh = -1, bi = -1;
+	for (int i = lane; i < tl; i += 32) { const int h = edge[i].z; if (h > bh || (h == bh && i > bi)) bh = h, bi = i; }
+	#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) {
+		const int oh = __shfl_xor_sync(FULL, bh, d), oi = __shfl_xor_sync(FULL, bi, d);
+		if (oh > bh || (oh == bh && oi > bi)) bh = oh, bi = oi;
+	}
+	if (want_pos && bi >= 0) {
+		const int sl = edge[bi].w;
+		*te = bi;
+		if (sl >= 0) *qe = sl / 8 + (sl % 8) * slen;
+	}
+	return bh > 0 ? bh : 0;
 }

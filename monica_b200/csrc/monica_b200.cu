@@ -269,6 +269,7 @@ static void index_finish_device(mb_index *ix, ThreadCtx &c, mb128 *d_mini, int64
 		ix->mid_occ = v + 1;
 	} else ix->mid_occ = 1;
 	d.n_seq = (int)ix->names.size(); d.k = ix->k; d.w = ix->w; d.mid_occ = ix->mid_occ;
+	d.max_seq_len = 0; for (uint32_t l : ix->lens) d.max_seq_len = std::max(d.max_seq_len, l);
 	ix->hbm_bytes = (int64_t)(cap * 16 + (size_t)n_pos * 8 + ((size_t)(sum + 7) / 8) * 4 + ix->offs.size() * 12);
 	ix->host_copies = false;
 }
@@ -1203,7 +1204,7 @@ static void map_device_part(mb_index *ix, const mb_opt_t &opt_in, DevPart &part)
 			CK(cudaMemsetAsync(zc, 0, 4 * sizeof(int32_t), st));
 			int32_t *walk = ar.get<int32_t>(n_tasks);
 			ZCand *zcand = ar.get<ZCand>(n_tasks);
-			if (!ll_scr) ll_scr = ar.get<int>((size_t)ll_grid * 2 * LL_MAX_LEN);
+			if (!ll_scr) ll_scr = ar.get<int>((size_t)ll_grid * 4 * LL_MAX_LEN);
 			k_ztest_screen<<<(unsigned)cdiv(n_tasks, 128), 128, 0, st>>>(ac, tasks, n_tasks, cigar_pool, walk, zc + 1); ++nl;
 			k_ztest<<<(unsigned)cdiv(n_tasks, 128), 128, 0, st>>>(ac, tasks, walk, zc + 1, n_tasks, cigar_pool, pass2, zc + 0, zcand, zc + 2); ++nl;
 			k_ztest_ll<<<ll_grid, 32, 0, st>>>(ac, tasks, zcand, zc + 2, zc + 3, pass2, zc + 0, ll_scr); ++nl;
@@ -1248,7 +1249,7 @@ static void map_device_part(mb_index *ix, const mb_opt_t &opt_in, DevPart &part)
 		int2 *iwork = ar.get<int2>(h_n_inv);
 		RegPlan *iplans = ar.get<RegPlan>(h_n_inv);
 		int32_t *ic = ar.get<int32_t>(8);  // [0] deferred, [1] processed, [2] local alignments, [3] cursor, [4] DP tasks, [5] inversion hits
-		if (!ll_scr) ll_scr = ar.get<int>((size_t)ll_grid * 2 * LL_MAX_LEN);
+		if (!ll_scr) ll_scr = ar.get<int>((size_t)ll_grid * 4 * LL_MAX_LEN);
 		int n_cur = h_n_inv, guard = 0;
 		ensure_regs(nullptr, cur, n_cur);
 		while (n_cur > 0) {
@@ -1476,8 +1477,8 @@ static void upload_reads(ThreadCtx &c, const uint8_t *cat, const int64_t *off, i
 // ---- sequential pieces: batches whose scratch would not fit the device are mapped piece by piece ----
 static int64_t mb_piece_bases()
 {
-	const char *e = getenv("MB_PIECE_BASES"); // bases per sequential piece; the default keeps the scratch of a piece around 40 GB
-	const int64_t v = e ? atoll(e) : (int64_t)800000000;
+	const char *e = getenv("MB_PIECE_BASES"); // bases per sequential piece; the default keeps the scratch of a piece around 65 GB
+	const int64_t v = e ? atoll(e) : (int64_t)1000000000;
 	return v < 1000 ? 1000 : v;
 }
 
@@ -1590,6 +1591,13 @@ static mb_hits *map_in_pieces(mb_index *ix, const mb_opt_t &opt, ThreadCtx &c, c
 				fcol[f].append_plain(part->fields.data() + (size_t)f * m, (size_t)m);
 				if (f == 0) for (int64_t i = 0; i < m; ++i) fcol[0].p[at + i] += lo;   // read_idx: piece-relative -> batch
 			});
+			if (k == 0 && K > 1) { // size the result once from the first piece (reads are alike): later appends then do not move it
+				const double scale = 1.08 * (double)(h_off[n_reads] - h_off[0]) / (double)std::max<int64_t>(1, po[n] - po[0]);
+				H->cigar.append_plain(nullptr, 0); H->cigar_off.append_plain(nullptr, 0);
+				auto reserve = [&](auto &v, size_t want) { if (want * sizeof(*v.p) > v.cap) { void *np = realloc(v.p, want * sizeof(*v.p) + 64); if (np) { v.p = (decltype(v.p))np; v.cap = want * sizeof(*v.p) + 64; } } };
+				reserve(H->cigar, (size_t)(scale * (double)part->cigar.size()));
+				reserve(H->cigar_off, (size_t)(scale * (double)m));
+			}
 			const size_t at = H->cigar_off.n;
 			H->cigar_off.append_plain(part->cigar_off.data(), (size_t)m);
 			for (int64_t i = 0; i < m; ++i) H->cigar_off.p[at + i] += n_c;
@@ -2127,7 +2135,7 @@ __global__ void __launch_bounds__(32)
 k_ll_batch(mb_opt_t opt, mb_ll_task_t *__restrict__ tasks, int64_t n, int32_t *__restrict__ cursor, const uint8_t *__restrict__ pool, int *__restrict__ scr_pool)
 {
 	const int lane = threadIdx.x;
-	int *scr = scr_pool + (size_t)blockIdx.x * (2 * LL_MAX_LEN);
+	int *scr = scr_pool + (size_t)blockIdx.x * (4 * LL_MAX_LEN);
 	for (;;) {
 		int k = 0;
 		if (lane == 0) k = atomicAdd(cursor, 1);
@@ -2156,7 +2164,7 @@ extern "C" int mb_ll_batch(int device, const mb_opt_t *opt, mb_ll_task_t *tasks,
 	mb_ll_task_t *d_t = ar.get<mb_ll_task_t>(n_tasks + 1);
 	uint8_t *d_pool = ar.get<uint8_t>(n_seqpool + 16);
 	const int grid = c.num_sms * 4;
-	int *scr = ar.get<int>((size_t)grid * 2 * LL_MAX_LEN);
+	int *scr = ar.get<int>((size_t)grid * 4 * LL_MAX_LEN);
 	int32_t *cur = ar.get<int32_t>(1);
 	CK(cudaMemsetAsync(cur, 0, sizeof(int32_t), st));
 	if (n_tasks) CK(cudaMemcpyAsync(d_t, tasks, n_tasks * sizeof(mb_ll_task_t), cudaMemcpyHostToDevice, st));

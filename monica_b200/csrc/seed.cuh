@@ -24,6 +24,7 @@ struct DevIndex {
 	uint64_t *seq_off = nullptr;
 	uint32_t *seq_len = nullptr;
 	int n_seq = 0, k = 15, w = 10, mid_occ = 0;
+	uint32_t max_seq_len = 0;   // longest contig (bounds the position bytes of an anchor's x)
 };
 
 MB_HD uint64_t mb_slot_hash(uint64_t h, int shift) { return (h * 0x9E3779B97F4A7C15ULL) >> shift; }
@@ -156,7 +157,6 @@ __global__ void k_rp_scatter(const int64_t *__restrict__ a_roff, int n_reads, in
 
 __global__ void __launch_bounds__(SORT_TPB)
 k_sort_anchors(const mb128 *__restrict__ in, mb128 *__restrict__ out, const int64_t *__restrict__ a_roff, int n_reads,
-               uint64_t *__restrict__ gkey, uint32_t *__restrict__ gidx, const int64_t *__restrict__ g_roff,
                int32_t *__restrict__ tie_list, int32_t *__restrict__ n_tie, const int32_t *__restrict__ perm)
 {
 	__shared__ uint64_t skey[SORT_SMEM_N];
@@ -169,9 +169,8 @@ k_sort_anchors(const mb128 *__restrict__ in, mb128 *__restrict__ out, const int6
 		if (n == 0) continue;
 		if (n == 1) { if (threadIdx.x == 0) out[base] = in[base]; continue; }
 		int np = 1; while (np < n) np <<= 1;
-		uint64_t *key; uint32_t *idx;
-		if (np <= SORT_SMEM_N) key = skey, idx = sidx;
-		else key = gkey + g_roff[r], idx = gidx + g_roff[r];
+		if (np > SORT_SMEM_N) continue;          // sorted by k_sort_anchors_big (LSD radix in global memory)
+		uint64_t *key = skey; uint32_t *idx = sidx;
 		if (threadIdx.x == 0) s_tie = 0;
 		for (int i = threadIdx.x; i < np; i += SORT_TPB) {
 			key[i] = i < n ? in[base + i].x : ~0ULL;
@@ -217,6 +216,104 @@ k_sort_anchors(const mb128 *__restrict__ in, mb128 *__restrict__ out, const int6
 		if (threadIdx.x == 0 && s_tie) tie_list[atomicAdd(n_tie, 1)] = r;
 		__syncthreads();
 	}
+}
+
+// Reads with more anchors than the shared-memory sort holds (long reads against a large database: tens of thousands of
+// anchors each): one CTA per read, stable LSD radix sort on x in global memory, 8 bits per pass, only over the byte positions
+// of x that can differ (position bytes up to the longest contig, contig-id bytes up to n_seq, the strand byte).  Each pass:
+// digit histogram of the read's segment -> 256-bin scan in shared memory -> in-order scatter of 256-anchor tiles, ranked with
+// __match_any_sync like the index build's k_rs_scatter.  The unsorted input is left intact (the exact replay of upstream's
+// unstable sort for reads with tied keys starts from it); the passes alternate between `tmp` and `out` so that the last one
+// lands in `out`.
+#define SB_TPB 256
+__global__ void __launch_bounds__(SB_TPB)
+k_sort_anchors_big(const mb128 *__restrict__ in, mb128 *__restrict__ out, mb128 *__restrict__ tmp, const int64_t *__restrict__ a_roff,
+                   const int32_t *__restrict__ big_list, const int32_t *__restrict__ n_big, int32_t *__restrict__ cursor, const int64_t *__restrict__ tmp_roff,
+                   unsigned pass_mask /* bit b: byte b of x takes part */, int32_t *__restrict__ tie_list, int32_t *__restrict__ n_tie)
+{
+	__shared__ int32_t s_hist[256];
+	__shared__ int32_t s_off[256];
+	__shared__ int32_t s_wcnt[SB_TPB / 32][256];
+	__shared__ int s_item, s_tie;
+	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	const int n_pass = __popc(pass_mask);
+	for (;;) {
+		__syncthreads();
+		if (tid == 0) s_item = atomicAdd(cursor, 1);
+		__syncthreads();
+		const int item = s_item;
+		if (item >= *n_big) break;
+		const int r = big_list[item];
+		const int64_t base = a_roff[r];
+		const int n = (int)(a_roff[r + 1] - base);
+		mb128 *T = tmp + tmp_roff[r], *O = out + base;
+		const mb128 *src = in + base;
+		int done = 0;
+		for (int b = 0; b < 8; ++b) {
+			if (!(pass_mask >> b & 1)) continue;
+			// pass number `done` of n_pass writes to: the last one to O, the one before to T, ...
+			mb128 *dst = ((n_pass - 1 - done) & 1) ? T : O;
+			const int shift = b * 8;
+			s_hist[tid] = 0;
+			__syncthreads();
+			for (int i = tid; i < n; i += SB_TPB) atomicAdd(&s_hist[(int)(src[i].x >> shift & 255)], 1);
+			__syncthreads();
+			if (wid == 0) { // exclusive scan of the 256 bins: 8 per lane
+				int c[8], tot = 0;
+				#pragma unroll
+				for (int u = 0; u < 8; ++u) { c[u] = s_hist[lane * 8 + u]; tot += c[u]; }
+				int incl = tot;
+				#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+				int run = incl - tot;
+				#pragma unroll
+				for (int u = 0; u < 8; ++u) { s_off[lane * 8 + u] = run; run += c[u]; }
+			}
+			__syncthreads();
+			for (int t0 = 0; t0 < n; t0 += SB_TPB) {
+				for (int w = 0; w < SB_TPB / 32; ++w) s_wcnt[w][tid] = 0;
+				__syncthreads();
+				const int i = t0 + tid;
+				const bool ok = i < n;
+				mb128 v; v.x = v.y = 0;
+				int d = 256;
+				if (ok) { v = src[i]; d = (int)(v.x >> shift & 255); }
+				const unsigned peers = __match_any_sync(0xffffffffu, d);
+				const int rank = __popc(peers & ((1u << lane) - 1));
+				if (ok && rank == 0) s_wcnt[wid][d] = __popc(peers);
+				__syncthreads();
+				int run = 0;
+				for (int w = 0; w < SB_TPB / 32; ++w) { const int cc = s_wcnt[w][tid]; s_wcnt[w][tid] = run; run += cc; }   // thread t owns digit t
+				__syncthreads();
+				if (ok) dst[s_off[d] + s_wcnt[wid][d] + rank] = v;
+				__syncthreads();
+				s_off[tid] += run;
+				__syncthreads();
+			}
+			src = dst;
+			++done;
+		}
+		if (n_pass == 0) for (int i = tid; i < n; i += SB_TPB) O[i] = in[base + i];
+		__syncthreads();
+		// tied keys -> the exact replay (k_sort_emul) redoes this read from the unsorted input
+		if (tid == 0) s_tie = 0;
+		__syncthreads();
+		for (int i = tid + 1; i < n; i += SB_TPB) if (O[i].x == O[i - 1].x) s_tie = 1;
+		__syncthreads();
+		if (tid == 0 && s_tie) tie_list[atomicAdd(n_tie, 1)] = r;
+	}
+}
+
+// list the reads that take the big sort and give each its slice of the ping-pong buffer
+__global__ void k_big_sort_list(const int64_t *__restrict__ a_roff, int n_reads, int32_t *__restrict__ sz, int32_t *__restrict__ big_list, int32_t *__restrict__ n_big)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	int64_t n = a_roff[r + 1] - a_roff[r];
+	int np = 1; while (np < n) np <<= 1;
+	const bool big = np > SORT_SMEM_N;
+	sz[r] = big ? (int32_t)n : 0;
+	if (big) big_list[atomicAdd(n_big, 1)] = r;
 }
 
 // reads whose anchors tie on x: reproduce upstream's unstable radix permutation exactly.  One warp per read, spread over
@@ -366,14 +463,6 @@ struct SeedOut {
 	int64_t n_a = 0;
 };
 
-__global__ void k_big_sort_sizes(const int64_t *__restrict__ a_roff, int n_reads, int32_t *__restrict__ sz)
-{
-	int r = blockIdx.x * blockDim.x + threadIdx.x;
-	if (r >= n_reads) return;
-	int64_t n = a_roff[r + 1] - a_roff[r];
-	int np = 1; while (np < n) np <<= 1;
-	sz[r] = np > SORT_SMEM_N ? np : 0;
-}
 
 static void run_seed(Arena &ar, cudaStream_t st, const DevIndex &ix, int mid_occ, const mb128 *mini, const int64_t *mini_off, int64_t n_mini,
                      const int64_t *d_read_off, int n_reads, SeedOut &o, int64_t *n_launch, int num_sms)
@@ -401,19 +490,19 @@ static void run_seed(Arena &ar, cudaStream_t st, const DevIndex &ix, int mid_occ
 	o.a = ar.get<mb128>(n_a + 1);
 	if (n_a == 0) return;
 	k_seed_fill<<<(unsigned)cdiv(n_mini, 256), 256, 0, st>>>(ix, mini, mini_off, n_mini, d_read_off, cnt, val, a_off, o.a_unsorted); ++*n_launch;
-	// scratch for reads too large for the shared-memory sort
+	// reads too large for the shared-memory sort: listed, and given a slice of a ping-pong buffer for the global-memory radix sort
 	int32_t *big_sz = ar.get<int32_t>(n_reads);
 	int64_t *big_off = ar.get<int64_t>(n_reads + 1);
-	k_big_sort_sizes<<<(unsigned)cdiv(n_reads, 128), 128, 0, st>>>(o.a_roff, n_reads, big_sz); ++*n_launch;
+	int32_t *big_list = ar.get<int32_t>(n_reads);
+	int32_t *ctr = ar.get<int32_t>(4);     // [0] reads with tied keys, [1] cursor of k_sort_emul, [2] big reads, [3] cursor of k_sort_anchors_big
+	CK(cudaMemsetAsync(ctr, 0, 4 * sizeof(int32_t), st));
+	k_big_sort_list<<<(unsigned)cdiv(n_reads, 128), 128, 0, st>>>(o.a_roff, n_reads, big_sz, big_list, ctr + 2); ++*n_launch;
 	exclusive_scan<int32_t>(ar, st, big_sz, big_off, n_reads, n_launch);
 	int64_t big_total = 0;
 	CK(cudaMemcpyAsync(&big_total, big_off + n_reads, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));
-	uint64_t *gkey = ar.get<uint64_t>(big_total + 1);
-	uint32_t *gidx = ar.get<uint32_t>(big_total + 1);
+	mb128 *big_tmp = ar.get<mb128>(big_total + 1);
 	int32_t *tie_list = ar.get<int32_t>(n_reads);
-	int32_t *ctr = ar.get<int32_t>(2);
-	CK(cudaMemsetAsync(ctr, 0, 2 * sizeof(int32_t), st));
 	if (n_reads > 1024) {
 		int32_t *hist = ar.get<int32_t>(RP_NB);
 		o.read_perm = ar.get<int32_t>(n_reads);
@@ -423,8 +512,16 @@ static void run_seed(Arena &ar, cudaStream_t st, const DevIndex &ix, int mid_occ
 		k_rp_scatter<<<(unsigned)cdiv(n_reads, 256), 256, 0, st>>>(o.a_roff, n_reads, hist, o.read_perm);
 		*n_launch += 3;
 	}
+	if (big_total > 0) { // byte positions of x that can differ: position bytes, contig-id bytes, the strand byte
+		unsigned pass_mask = 0x80u;
+		uint32_t max_len = ix.max_seq_len ? ix.max_seq_len : 0xffffffffu;
+		for (int b = 0; b < 4; ++b) if (b == 0 || (max_len >> (8 * b)) != 0) pass_mask |= 1u << b;
+		uint32_t max_rid = ix.n_seq > 0 ? (uint32_t)(ix.n_seq - 1) : 0;
+		for (int b = 0; b < 4; ++b) if ((b == 0 && max_rid) || (b > 0 && (max_rid >> (8 * b)) != 0)) pass_mask |= 1u << (4 + b);
+		k_sort_anchors_big<<<num_sms * 4, SB_TPB, 0, st>>>(o.a_unsorted, o.a, big_tmp, o.a_roff, big_list, ctr + 2, ctr + 3, big_off, pass_mask, tie_list, ctr); ++*n_launch;
+	}
 	int grid = n_reads < num_sms * 8 ? n_reads : num_sms * 8;
-	k_sort_anchors<<<grid, SORT_TPB, 0, st>>>(o.a_unsorted, o.a, o.a_roff, n_reads, gkey, gidx, big_off, tie_list, ctr, o.read_perm); ++*n_launch;
+	k_sort_anchors<<<grid, SORT_TPB, 0, st>>>(o.a_unsorted, o.a, o.a_roff, n_reads, tie_list, ctr, o.read_perm); ++*n_launch;
 	static bool se_attr = false;
 	if (!se_attr) { CK(cudaFuncSetAttribute(k_sort_emul, cudaFuncAttributeMaxDynamicSharedMemorySize, SE_BIG_BYTES)); se_attr = true; }
 	const int se_grid = num_sms * 5;   // 43 KB of shared memory per one-warp CTA: five fit an SM
