@@ -91,12 +91,22 @@ struct Arena {
 	// NB: growing mid-batch keeps old allocations valid (old slab retired, not freed) but they are NOT moved.
 	void *alloc(size_t bytes) {
 		bytes = (bytes + 255) & ~(size_t)255;
+		if (const char *lim = getenv("MB_TEST_ARENA_LIMIT"))   // tests: pretend the device holds this much scratch
+			if (batch_total + bytes > (size_t)atoll(lim)) throw mb_error(MB_ERR_NOMEM, "scratch limit (MB_TEST_ARENA_LIMIT) reached");
 		if (used + bytes > cap) {
 			size_t ncap = cap ? cap * 2 : ((size_t)256 << 20);
 			while (ncap < bytes * 2) ncap <<= 1;
 			if (base) retired.push_back(base);
 			char *nb = nullptr;
 			cudaError_t e = cudaMalloc(&nb, ncap);
+			if (e != cudaSuccess) { // doubling does not fit: take what is left, if that covers the request with some room
+				cudaGetLastError();
+				size_t fr = 0, tot = 0;
+				if (cudaMemGetInfo(&fr, &tot) == cudaSuccess && fr > ((size_t)2 << 30)) {
+					const size_t fit = (fr - ((size_t)1 << 30)) & ~(size_t)255;
+					if (fit >= bytes + bytes / 4 && fit < ncap) { ncap = fit; e = cudaMalloc(&nb, ncap); if (e != cudaSuccess) cudaGetLastError(); }
+				}
+			}
 			if (e != cudaSuccess) throw mb_error(MB_ERR_NOMEM, std::string("cudaMalloc failed for ") + std::to_string(ncap) + " bytes: " + cudaGetErrorString(e));
 			base = nb; cap = ncap; used = 0;
 		}

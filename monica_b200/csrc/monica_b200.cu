@@ -80,6 +80,8 @@ struct ThreadCtx {
 	cudaStream_t stf[2] = {};
 	cudaEvent_t ev_f[2] = {}, ev_fork = nullptr;
 	std::vector<cudaEvent_t> feed_events;   // host->device pieces of mb_map_batch (SketchFeed)
+	int64_t piece_bases = 0;                // bases per sequential piece once a batch did not fit the device (0: the default)
+	const void *piece_index = nullptr;      // ... for this index
 	Arena ar;
 	int num_sms = 148;
 	uint8_t *h_pin = nullptr; size_t h_pin_cap = 0;   // pinned staging for reads
@@ -1519,11 +1521,26 @@ template <typename T> static void concat_pin(PinVec<T> &dst, const std::vector<s
 	for (auto &t : th) t.join();
 }
 
+// The scratch a piece needs depends on the database (anchors per base grow with its size and repetitiveness), so the piece
+// size is found by doing: a batch (or piece) that runs out of device memory is retried in pieces of half the size, and the
+// size that worked is remembered for the following calls of this thread.
+static int64_t piece_now(const ThreadCtx &c, const void *ix) { const int64_t d = mb_piece_bases(); return c.piece_index == ix && c.piece_bases > 0 && c.piece_bases < d ? c.piece_bases : d; }
+static bool shrink_piece(ThreadCtx &c, const void *ix, const mb_error &e, int64_t total, int32_t n_reads)
+{
+	const int64_t piece = piece_now(c, ix);
+	if (e.code != MB_ERR_NOMEM || n_reads <= 1 || piece <= 1000) return false;
+	cudaDeviceSynchronize(); cudaGetLastError();
+	c.ar.release();
+	c.last_parts.clear();
+	c.piece_bases = std::max<int64_t>(1000, std::min(piece, total) / 2); c.piece_index = ix;
+	if (getenv("MB_DEBUG")) fprintf(stderr, "[mb] device scratch did not fit: retrying in pieces of %lld bases\n", (long long)c.piece_bases);
+	return true;
+}
+
 // h_cat != nullptr: reads in host memory (uploaded piece by piece); otherwise d_codes_all / d_off_all hold the resident batch
 static mb_hits *map_in_pieces(mb_index *ix, const mb_opt_t &opt, ThreadCtx &c, const uint8_t *h_cat, const uint8_t *d_codes_all, const int64_t *d_off_all,
-                              const int64_t *h_off, int32_t n_reads, int want, mb_stats_t *stats)
+                              const int64_t *h_off, int32_t n_reads, int want, mb_stats_t *stats, int64_t piece)
 {
-	const int64_t piece = mb_piece_bases();
 	std::vector<int32_t> cut(1, 0);
 	while (cut.back() < n_reads) { // at least one read per piece, then as many as fit
 		int32_t lo = cut.back(), hi = lo + 1;
@@ -1652,12 +1669,13 @@ static int map_batch_impl(mb_index_t *ix, const mb_opt_t *opt, const uint8_t *ca
 	API_BEGIN
 	if (!ix || !opt || !off || !out || (n_reads > 0 && !cat && off[n_reads] > 0)) throw mb_error(MB_ERR_ARG, "bad arguments");
 	ThreadCtx &c = get_ctx(ix->device);
-	if (n_reads > 1 && off[n_reads] > mb_piece_bases()) {
+	for (;;) try {
+	if (n_reads > 1 && off[n_reads] > piece_now(c, ix)) {
 		for (int i = 0; i < n_reads; ++i) {
 			if (off[i + 1] < off[i] || off[0] != 0) throw mb_error(MB_ERR_ARG, "offsets must start at 0 and be non-decreasing");
 			if (off[i + 1] - off[i] > 0x3fffffff) throw mb_error(MB_ERR_ARG, "read longer than 2^30");
 		}
-		*out = map_in_pieces(ix, *opt, c, cat, nullptr, nullptr, off, n_reads, want, stats);
+		*out = map_in_pieces(ix, *opt, c, cat, nullptr, nullptr, off, n_reads, want, stats, piece_now(c, ix));
 		return MB_OK;
 	}
 	c.ar.reset();
@@ -1673,6 +1691,8 @@ static int map_batch_impl(mb_index_t *ix, const mb_opt_t *opt, const uint8_t *ca
 	if (stats) stats->ms_h2d = ms_h2d;
 	*out = map_device(ix, *opt, c, d_codes, d_off, off, n_reads, total, want, stats, use_feed ? &feed : nullptr);
 	if (stats) { stats->ms_h2d = ms_h2d; stats->n_launches += 1; }
+	return MB_OK;
+	} catch (const mb_error &e) { if (!shrink_piece(c, ix, e, off[n_reads], n_reads)) throw; }
 	API_END
 }
 
@@ -1709,11 +1729,15 @@ extern "C" int mb_map_resident(mb_index_t *ix, const mb_opt_t *opt, mb_reads_t *
 	CK(cudaMemcpyAsync(h_off.data(), reads->d_off, (reads->n_reads + 1) * 8, cudaMemcpyDeviceToHost, c.st));
 	CK(cudaStreamSynchronize(c.st));
 	if (stats) stats->ms_h2d = 0;
-	if (reads->n_reads > 1 && reads->total > mb_piece_bases()) {
-		*out = map_in_pieces(ix, *opt, c, nullptr, reads->d_codes, reads->d_off, h_off.data(), reads->n_reads, want_hits ? 3 : 0, stats);
+	for (;;) try {
+		if (reads->n_reads > 1 && reads->total > piece_now(c, ix)) {
+			*out = map_in_pieces(ix, *opt, c, nullptr, reads->d_codes, reads->d_off, h_off.data(), reads->n_reads, want_hits ? 3 : 0, stats, piece_now(c, ix));
+			return MB_OK;
+		}
+		c.ar.reset();
+		*out = map_device(ix, *opt, c, reads->d_codes, reads->d_off, h_off.data(), reads->n_reads, reads->total, want_hits ? 3 : 0, stats);
 		return MB_OK;
-	}
-	*out = map_device(ix, *opt, c, reads->d_codes, reads->d_off, h_off.data(), reads->n_reads, reads->total, want_hits ? 3 : 0, stats);
+	} catch (const mb_error &e) { if (!shrink_piece(c, ix, e, reads->total, reads->n_reads)) throw; }
 	API_END
 }
 

@@ -226,10 +226,12 @@ k_sort_anchors(const mb128 *__restrict__ in, mb128 *__restrict__ out, const int6
 // unstable sort for reads with tied keys starts from it); the passes alternate between `tmp` and `out` so that the last one
 // lands in `out`.
 #define SB_TPB 256
+#define TL_MAX 64     // tie positions kept per read; a read with more is replayed in full
 __global__ void __launch_bounds__(SB_TPB)
 k_sort_anchors_big(const mb128 *__restrict__ in, mb128 *__restrict__ out, mb128 *__restrict__ tmp, const int64_t *__restrict__ a_roff,
                    const int32_t *__restrict__ big_list, const int32_t *__restrict__ n_big, int32_t *__restrict__ cursor, const int64_t *__restrict__ tmp_roff,
-                   unsigned pass_mask /* bit b: byte b of x takes part */, int32_t *__restrict__ tie_list, int32_t *__restrict__ n_tie)
+                   unsigned pass_mask /* bit b: byte b of x takes part */, int32_t *__restrict__ tie_list, int32_t *__restrict__ n_tie,
+                   int32_t *__restrict__ tie_pos /* [n_reads][TL_MAX] sorted positions i with x[i] == x[i-1] */, int32_t *__restrict__ tie_n)
 {
 	__shared__ int32_t s_hist[256];
 	__shared__ int32_t s_off[256];
@@ -298,9 +300,10 @@ k_sort_anchors_big(const mb128 *__restrict__ in, mb128 *__restrict__ out, mb128 
 		// tied keys -> the exact replay (k_sort_emul) redoes this read from the unsorted input
 		if (tid == 0) s_tie = 0;
 		__syncthreads();
-		for (int i = tid + 1; i < n; i += SB_TPB) if (O[i].x == O[i - 1].x) s_tie = 1;
+		for (int i = tid + 1; i < n; i += SB_TPB)
+			if (O[i].x == O[i - 1].x) { const int j = atomicAdd(&s_tie, 1); if (j < TL_MAX) tie_pos[(size_t)r * TL_MAX + j] = i; }
 		__syncthreads();
-		if (tid == 0 && s_tie) tie_list[atomicAdd(n_tie, 1)] = r;
+		if (tid == 0 && s_tie) { tie_list[atomicAdd(n_tie, 1)] = r; tie_n[r] = s_tie; }
 	}
 }
 
@@ -316,6 +319,144 @@ __global__ void k_big_sort_list(const int64_t *__restrict__ a_roff, int n_reads,
 	if (big) big_list[atomicAdd(n_big, 1)] = r;
 }
 
+// ---- exact replay for LONG reads with tied keys ----
+// What has to be reproduced is the order in which upstream's in-place MSD radix sort (ksort.h rs_sort: cycle-leader
+// permutation per byte level, insertion sort below 65 elements) leaves anchors of EQUAL key; everything else is fixed by the
+// keys and already sits in `out` from the stable sort.  A range of the recursion that holds no tied pair ends up as its stable
+// order, so the replay only descends into ranges that hold one: per tied pair one chain of nested ranges, top level = the
+// whole read.  The cycle-leader walk of a range is inherently sequential (which slot an element lands in depends on every
+// element visited before it), so the parallelism is across ranges: a device-wide queue of (read, range, shift) items, ONE
+// LANE per item, each lane a small state machine that advances by one element per iteration, so that the lanes of a warp stay
+// in lock step whatever mix of items they hold and nobody spins while a warp-mate works (sub-ranges are pushed by the lanes
+// themselves; `pending` counts items pushed and not yet finished).  The 256 moving bucket heads of a lane live in shared
+// memory (1 KB per lane, 192 lanes per SM); the working copy W of a read is the radix sort's ping-pong slice; leaves and
+// last-level buckets that hold ties are copied from W into `out`.  A long read costs ~1.7 walks of its length, all long tied
+// reads of a batch walk concurrently.
+#define SQ_TPB 192
+struct EmulQ { int4 *items; int *ready; int *ctr; int cap; };   // ctr: [0] tail, [1] head, [2] pending
+
+static __device__ __forceinline__ mb128 sq_ld(const mb128 *p) { const ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(p)); mb128 r; r.x = v.x, r.y = v.y; return r; }
+static __device__ __forceinline__ void sq_st(mb128 *p, const mb128 &v) { __stcg(reinterpret_cast<ulonglong2*>(p), make_ulonglong2(v.x, v.y)); }
+static __device__ __forceinline__ uint64_t sq_ldx(const mb128 *p) { return __ldcg(reinterpret_cast<const unsigned long long*>(&p->x)); }
+
+static __device__ __forceinline__ void sq_push(const EmulQ &q, int r, int lo, int hi, int s)
+{
+	atomicAdd(&q.ctr[2], 1);
+	const int sl = atomicAdd(&q.ctr[0], 1);
+	if (sl < q.cap) { __stcg(&q.items[sl], make_int4(r, lo, hi, s)); __threadfence(); *((volatile int*)&q.ready[sl]) = 1; }
+	else atomicSub(&q.ctr[2], 1);   // cannot happen: cap covers n/65 ranges per level on 8 levels
+}
+
+__global__ void k_sort_emul_q_seed(const mb128 *__restrict__ in, mb128 *__restrict__ wbuf, const int64_t *__restrict__ a_roff, const int64_t *__restrict__ w_roff,
+                                   const int32_t *__restrict__ tie_list, const int32_t *__restrict__ n_tie, int32_t *__restrict__ tie_pos, const int32_t *__restrict__ tie_n,
+                                   EmulQ q, int n_lo)
+{
+	for (int t = blockIdx.x; t < *n_tie; t += gridDim.x) {
+		const int r = tie_list[t];
+		const int64_t base = a_roff[r];
+		const int n = (int)(a_roff[r + 1] - base);
+		if (n <= n_lo) continue;   // short reads: k_sort_emul, in shared memory
+		mb128 *W = wbuf + w_roff[r];
+		for (int i = threadIdx.x; i < n; i += blockDim.x) W[i] = in[base + i];
+		if (threadIdx.x == 0) {
+			const int nt = tie_n[r];
+			if (nt <= TL_MAX) { // ascending positions (collected in arbitrary order)
+				int32_t *T = tie_pos + (size_t)r * TL_MAX;
+				for (int i = 1; i < nt; ++i) { const int v = T[i]; int j = i; while (j > 0 && T[j - 1] > v) { T[j] = T[j - 1]; --j; } T[j] = v; }
+			}
+			sq_push(q, r, 0, n, 56);
+		}
+	}
+}
+
+__global__ void __launch_bounds__(SQ_TPB)
+k_sort_emul_q(mb128 *__restrict__ out, mb128 *__restrict__ wbuf, const int64_t *__restrict__ a_roff, const int64_t *__restrict__ w_roff,
+              const int32_t *__restrict__ tie_pos, const int32_t *__restrict__ tie_n, EmulQ q, int *__restrict__ ends_pool)
+{
+	extern __shared__ int sq_bb[];                 // [256][SQ_TPB]: bucket heads, one column per lane
+	int *bb = sq_bb + threadIdx.x;
+	#define BB(k) bb[(k) * SQ_TPB]
+	int *be = ends_pool + (size_t)(blockIdx.x * SQ_TPB + threadIdx.x) * 256;   // bucket ends of the lane's current item
+	volatile int *ready = q.ready; volatile int *ctr = q.ctr;
+	const unsigned FULL = 0xffffffffu;
+	int state = 0, slot = -1;
+	mb128 *W = nullptr, *O = nullptr; const int32_t *T = nullptr;
+	int r = 0, nt = 0, beg = 0, end = 0, s = 0, i = 0, k = 0, bek = 0, l = 0, ti = 0, prev_end = 0;
+	bool in_cycle = false, all_ranges = false;
+	mb128 tmp; tmp.x = tmp.y = 0;
+	uint64_t k0 = 0, diff = 0;
+	for (;;) {
+		if (state == 0) { // take an item
+			if (slot < 0) slot = atomicAdd(&q.ctr[1], 1);
+			if (slot >= q.cap) state = 9;
+			else if (ready[slot]) {
+				__threadfence();
+				const int4 it = __ldcg(&q.items[slot]);
+				r = it.x, beg = it.y, end = it.z, s = it.w; slot = -1;
+				W = wbuf + w_roff[r]; O = out + a_roff[r];
+				T = tie_pos + (size_t)r * TL_MAX; nt = tie_n[r]; all_ranges = nt > TL_MAX;
+				k0 = sq_ldx(W + beg); diff = 0; i = beg + 1; state = 1;
+			} else if (ctr[2] == 0 && !ready[slot]) state = 9;
+		} else if (state == 1) { // byte levels on which the whole range agrees move nothing: skip them
+			#pragma unroll
+			for (int u = 0; u < 8; ++u) if (i < end) { diff |= sq_ldx(W + i) ^ k0; ++i; }
+			if (i >= end) {
+				while (s > 0 && !(diff >> s & 255)) s -= 8;
+				for (int kk = 0; kk < 256; ++kk) BB(kk) = 0;
+				i = beg; state = 2;
+			}
+		} else if (state == 2) { // digit histogram
+			#pragma unroll
+			for (int u = 0; u < 8; ++u) if (i < end) { BB((int)(sq_ldx(W + i) >> s & 255)) += 1; ++i; }
+			if (i >= end) {
+				int run = beg;
+				for (int kk = 0; kk < 256; ++kk) { const int c = BB(kk); BB(kk) = run; run += c; be[kk] = run; }
+				k = 0; bek = be[0]; in_cycle = false; state = 3;
+			}
+		} else if (state == 3) { // the cycle-leader walk, one element per iteration
+			if (!in_cycle) {
+				const int bk = BB(k);
+				if (bk == bek) {
+					if (++k == 256) { k = 0; ti = 0; prev_end = beg; state = 4; }
+					else bek = be[k];
+				} else {
+					tmp = sq_ld(W + bk); l = (int)(tmp.x >> s & 255);
+					if (l == k) BB(k) = bk + 1; else in_cycle = true;
+				}
+			} else {
+				const int p = BB(l); BB(l) = p + 1;
+				const mb128 nx = sq_ld(W + p);
+				sq_st(W + p, tmp);
+				tmp = nx; l = (int)(tmp.x >> s & 255);
+				if (l == k) { const int bk = BB(k); sq_st(W + bk, tmp); BB(k) = bk + 1; in_cycle = false; }
+			}
+		} else if (state == 4) { // one bucket per iteration: descend where a tied pair sits, final order there -> out
+			const int lo = prev_end, hi = be[k], len = hi - lo;
+			prev_end = hi;
+			if (len > 1) {
+				while (ti < nt && ti < TL_MAX && T[ti] <= lo) ++ti;
+				const bool has = all_ranges || (ti < nt && T[ti] < hi);
+				if (has) {
+					if (s > 0 && len > MB_RS_MIN_SIZE) sq_push(q, r, lo, hi, s > 8 ? s - 8 : 0);
+					else if (s > 0) { // leaf: upstream's insertion sort = stable order of the current arrangement
+						for (int a = lo; a < hi; ++a) {
+							const mb128 v = sq_ld(W + a);
+							int rank = 0;
+							for (int b = lo; b < hi; ++b) { const uint64_t xb = sq_ldx(W + b); rank += (xb < v.x) || (xb == v.x && b < a); }
+							O[lo + rank] = v;
+						}
+					} else for (int a = lo; a < hi; ++a) O[a] = sq_ld(W + a);
+				}
+			}
+			if (++k == 256) { __threadfence(); atomicSub(&q.ctr[2], 1); state = 0; }
+		}
+		const bool idle = state == 0 || state == 9;
+		if (__all_sync(FULL, state == 9)) break;
+		if (__all_sync(FULL, idle)) __nanosleep(400);
+	}
+	#undef BB
+}
+
 // reads whose anchors tie on x: reproduce upstream's unstable radix permutation exactly.  One warp per read, spread over
 // the whole GPU: the anchors are staged in shared memory (global scratch beyond SE_SMEM_N), lane 0 replays the sequential
 // cycle-leader passes there (byte levels on which the whole range agrees are no-ops and are skipped), and the <= 64-element
@@ -323,8 +464,6 @@ __global__ void k_big_sort_list(const int64_t *__restrict__ a_roff, int n_reads,
 #define SE_SMEM_N 2560             // 2560 * 16 B = 40 KB of anchors per warp
 #define SE_STACK  2304
 #define SE_SMEM_BYTES (SE_SMEM_N * 16 + 512 * 4 + 64)
-#define SE_BIG_N 12800             // second launch, one CTA per SM: 200 KB of anchors per warp for the few long tied reads
-#define SE_BIG_BYTES (SE_BIG_N * 16 + 512 * 4 + 64)
 
 __global__ void __launch_bounds__(32)
 k_sort_emul(const mb128 *__restrict__ in, mb128 *__restrict__ out, const int64_t *__restrict__ a_roff,
@@ -503,6 +642,7 @@ static void run_seed(Arena &ar, cudaStream_t st, const DevIndex &ix, int mid_occ
 	CK(cudaStreamSynchronize(st));
 	mb128 *big_tmp = ar.get<mb128>(big_total + 1);
 	int32_t *tie_list = ar.get<int32_t>(n_reads);
+	int32_t *tie_pos = ar.get<int32_t>(big_total > 0 ? (size_t)n_reads * TL_MAX : 1), *tie_n = ar.get<int32_t>(n_reads);
 	if (n_reads > 1024) {
 		int32_t *hist = ar.get<int32_t>(RP_NB);
 		o.read_perm = ar.get<int32_t>(n_reads);
@@ -518,21 +658,30 @@ static void run_seed(Arena &ar, cudaStream_t st, const DevIndex &ix, int mid_occ
 		for (int b = 0; b < 4; ++b) if (b == 0 || (max_len >> (8 * b)) != 0) pass_mask |= 1u << b;
 		uint32_t max_rid = ix.n_seq > 0 ? (uint32_t)(ix.n_seq - 1) : 0;
 		for (int b = 0; b < 4; ++b) if ((b == 0 && max_rid) || (b > 0 && (max_rid >> (8 * b)) != 0)) pass_mask |= 1u << (4 + b);
-		k_sort_anchors_big<<<num_sms * 4, SB_TPB, 0, st>>>(o.a_unsorted, o.a, big_tmp, o.a_roff, big_list, ctr + 2, ctr + 3, big_off, pass_mask, tie_list, ctr); ++*n_launch;
+		k_sort_anchors_big<<<num_sms * 4, SB_TPB, 0, st>>>(o.a_unsorted, o.a, big_tmp, o.a_roff, big_list, ctr + 2, ctr + 3, big_off, pass_mask, tie_list, ctr, tie_pos, tie_n); ++*n_launch;
 	}
 	int grid = n_reads < num_sms * 8 ? n_reads : num_sms * 8;
 	k_sort_anchors<<<grid, SORT_TPB, 0, st>>>(o.a_unsorted, o.a, o.a_roff, n_reads, tie_list, ctr, o.read_perm); ++*n_launch;
 	static bool se_attr = false;
-	if (!se_attr) { CK(cudaFuncSetAttribute(k_sort_emul, cudaFuncAttributeMaxDynamicSharedMemorySize, SE_BIG_BYTES)); se_attr = true; }
+	if (!se_attr) {
+		CK(cudaFuncSetAttribute(k_sort_emul, cudaFuncAttributeMaxDynamicSharedMemorySize, SE_SMEM_BYTES));
+		CK(cudaFuncSetAttribute(k_sort_emul_q, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * SQ_TPB * (int)sizeof(int)));
+		se_attr = true;
+	}
+	if (big_total > 0) { // long reads with ties: queue of ranges, one lane per range (the long walks start first)
+		EmulQ q;
+		q.cap = (int)std::min<int64_t>(big_total / 8 + n_reads + (int64_t)num_sms * SQ_TPB + 4096, 0x7fffff00);
+		q.items = ar.get<int4>(q.cap); q.ready = ar.get<int>(q.cap); q.ctr = ar.get<int>(4);
+		int *ends_pool = ar.get<int>((size_t)num_sms * SQ_TPB * 256);
+		CK(cudaMemsetAsync(q.ready, 0, (size_t)q.cap * sizeof(int), st));
+		CK(cudaMemsetAsync(q.ctr, 0, 4 * sizeof(int), st));
+		k_sort_emul_q_seed<<<num_sms * 4, 256, 0, st>>>(o.a_unsorted, big_tmp, o.a_roff, big_off, tie_list, ctr, tie_pos, tie_n, q, SE_SMEM_N);
+		k_sort_emul_q<<<num_sms, SQ_TPB, 256 * SQ_TPB * sizeof(int), st>>>(o.a, big_tmp, o.a_roff, big_off, tie_pos, tie_n, q, ends_pool);
+		*n_launch += 2;
+	}
 	const int se_grid = num_sms * 5;   // 43 KB of shared memory per one-warp CTA: five fit an SM
 	int *ws_pool = ar.get<int>((size_t)se_grid * 6 * SE_STACK);
-	int *ws_big = ar.get<int>((size_t)num_sms * 6 * SE_STACK);
-	int32_t *cur_big = ar.get<int32_t>(1);
-	CK(cudaMemsetAsync(cur_big, 0, sizeof(int32_t), st));
-	cudaStream_t se_st = st;
-	// the long reads first (they are the tail: one lane replays the sequential passes), in 200 KB of shared memory each
-	k_sort_emul<<<num_sms, 32, SE_BIG_BYTES, se_st>>>(o.a_unsorted, o.a, o.a_roff, tie_list, ctr, cur_big, ws_big, SE_BIG_N, SE_SMEM_N);
-	k_sort_emul<<<se_grid, 32, SE_SMEM_BYTES, se_st>>>(o.a_unsorted, o.a, o.a_roff, tie_list, ctr, ctr + 1, ws_pool, SE_SMEM_N, 0); *n_launch += 2;
+	k_sort_emul<<<se_grid, 32, SE_SMEM_BYTES, st>>>(o.a_unsorted, o.a, o.a_roff, tie_list, ctr, ctr + 1, ws_pool, SE_SMEM_N, 0); ++*n_launch;
 	if (getenv("MB_DEBUG")) {
 		int32_t h = 0; cudaMemcpyAsync(&h, ctr, sizeof(h), cudaMemcpyDeviceToHost, st); cudaStreamSynchronize(st);
 		fprintf(stderr, "[mb] reads with tied anchor keys: %d of %d\n", h, n_reads);

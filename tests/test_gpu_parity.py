@@ -864,3 +864,80 @@ def test_sequential_pieces_equal_one_piece(case, lib, monkeypatch):
         assert np.array_equal(c3, c4) and np.array_equal(n3, n4)
     finally:
         al.reads_free(h)
+
+
+def test_batch_beyond_device_scratch_is_retried_in_smaller_pieces(lib, monkeypatch):
+    """The scratch a batch needs depends on the database; a batch (or piece) that runs out of device memory is retried in
+    pieces of half the size and the size that worked is kept for the index.  The device limit is imitated here
+    (MB_TEST_ARENA_LIMIT); results must equal the unrestricted run's."""
+    from monica_b200 import synth
+    from monica_b200.mappy_shim import Aligner
+    names, seqs = synth.make_genomes(77, 3, 150_000)
+    reads, _ = synth.simulate_reads(78, seqs, 400, 2500.0, 0.12)
+    cat, off = synth.concat_reads(reads)
+    al = Aligner(names=names, seqs=seqs, preset="map-ont", best_n=15)
+    want = al.map_batch(cat=cat, off=off)
+    assert al.last_stats["n_pieces"] <= 1
+    need = int(al.last_stats["arena_bytes"])
+    assert need > 0
+    monkeypatch.setenv("MB_TEST_ARENA_LIMIT", str(need // 3))
+    got = al.map_batch(cat=cat, off=off)
+    assert al.last_stats["n_pieces"] >= 2
+    for f in CMP_FIELDS + ["read_idx"]:
+        assert np.array_equal(getattr(want, f), getattr(got, f)), f
+    assert np.array_equal(want.cigar_pool, got.cigar_pool) and np.array_equal(want.cigar_off, got.cigar_off)
+    n1 = al.last_stats["n_pieces"]
+    al.map_batch(cat=cat, off=off)                      # the size that worked is remembered: no second search
+    assert al.last_stats["n_pieces"] == n1
+    h = al.reads_upload(cat, off)
+    try:
+        res = al.map_resident(h, len(reads), want_hits=True)
+        for f in CMP_FIELDS + ["read_idx"]:
+            assert np.array_equal(getattr(want, f), getattr(res, f)), f
+    finally:
+        al.reads_free(h)
+    monkeypatch.setenv("MB_TEST_ARENA_LIMIT", "4096")   # nothing fits: the error surfaces instead of looping
+    with pytest.raises(Exception):
+        al.map_batch(cat=cat, off=off)
+
+
+def test_long_reads_with_tied_anchors_sort_bit_exact(oracle, lib):
+    """Long reads (more anchors than the shared-memory sorts hold) whose anchors tie on x: the radix sort in global memory plus
+    the queued replay of upstream's unstable sort (only the ranges that hold a tied pair are walked; more than 64 tied pairs
+    -> the whole recursion).  Anchor arrays must equal the oracle's element for element."""
+    from monica_b200 import _lib, synth
+    from monica_b200.mappy_shim import Aligner
+    rng = np.random.default_rng(4242)
+    names, seqs = synth.make_genomes(91, 6, 250_000, strain_frac=0.5)
+    al = Aligner(names=names, seqs=seqs, preset="map-ont", best_n=15)
+    oidx = oracle.Index(names, seqs)
+    g = seqs[0]
+    reads = []
+    # few ties: a short block of the read copied to a second place (each repeated minimizer ties once per reference hit)
+    r = g[10_000:50_000].copy(); r[30_000:30_030] = r[5_000:5_030]; reads.append(r)
+    r = g[60_000:95_000].copy(); r[20_000:20_022] = r[1_000:1_022]; r[33_000:33_025] = r[9_000:9_025]; reads.append(r)
+    # many ties: a 3 kb block duplicated, and a read made of one segment three times
+    r = g[100_000:150_000].copy(); r[40_000:43_000] = r[2_000:5_000]; reads.append(r)
+    reads.append(np.concatenate([g[160_000:172_000]] * 3))
+    # no ties at all, and a mid-size read just past the shared-memory limit
+    reads.append(g[180_000:240_000].copy())
+    reads.append(np.concatenate([g[200_000:214_000], g[200_000:200_020]]))
+    reads += [synth.random_genome(rng, 3000), g[5_000:6_000].copy()]
+    cat, off = synth.concat_reads(reads)
+    cap = len(cat) * 4 + 1024
+    out = np.zeros((cap, 2), dtype=np.uint64)
+    ooff = np.zeros(len(reads) + 1, dtype=np.int64)
+    rep = np.zeros(len(reads), dtype=np.int32)
+    _lib.check(lib.mb_seed(al.handle(), C.byref(al.opt), _lib._ptr(cat), _lib._ptr(off), len(reads), _lib._ptr(out), cap, _lib._ptr(ooff), _lib._ptr(rep)))
+    n_ties = []
+    for i, r in enumerate(reads):
+        _, stats, tr = oidx.map(r, trace=True)
+        got = out[ooff[i]:ooff[i + 1]]
+        assert len(tr["anchors"]) == len(got), f"read {i}"
+        bad = np.nonzero(np.any(tr["anchors"] != got, axis=1))[0]
+        assert len(bad) == 0, f"read {i}: {len(bad)} anchors differ, first at {bad[:5]} of {len(got)}"
+        n_ties.append(int(np.sum(got[1:, 0] == got[:-1, 0])) if len(got) > 1 else 0)
+    assert len(out[ooff[0]:ooff[1]]) > 2560
+    assert 0 < n_ties[0] <= 64 and 0 < n_ties[1] <= 64, n_ties
+    assert n_ties[2] > 64 and n_ties[3] > 64, n_ties
+    assert n_ties[4] == 0, n_ties
