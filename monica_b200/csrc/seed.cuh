@@ -347,24 +347,105 @@ static __device__ __forceinline__ void sq_push(const EmulQ &q, int r, int lo, in
 	else atomicSub(&q.ctr[2], 1);   // cannot happen: cap covers n/65 ranges per level on 8 levels
 }
 
-__global__ void k_sort_emul_q_seed(const mb128 *__restrict__ in, mb128 *__restrict__ wbuf, const int64_t *__restrict__ a_roff, const int64_t *__restrict__ w_roff,
-                                   const int32_t *__restrict__ tie_list, const int32_t *__restrict__ n_tie, int32_t *__restrict__ tie_pos, const int32_t *__restrict__ tie_n,
-                                   EmulQ q, int n_lo)
+// Start of the replay for one long tied read, one CTA per read: working copy W of the unsorted anchors and the first item.
+// A level with exactly TWO occupied buckets (the usual first one: the strand byte) has a closed form and is applied here in
+// parallel instead of being walked: with bucket 0 = [0, c0), p_1 < p_2 < ... the elements of bucket 0's region that belong
+// to bucket 1 and q_1 < q_2 < ... those of bucket 1's region that belong to bucket 0, the i-th cycle of the walk puts X(p_i)
+// at the head of bucket 1, shifts the elements up to q_i - 1 right by one and closes with Y(q_i) going to p_i.
+#define SQS_TPB 256
+__global__ void __launch_bounds__(SQS_TPB)
+k_sort_emul_q_seed(const mb128 *__restrict__ in, mb128 *__restrict__ wbuf, mb128 *__restrict__ out, const int64_t *__restrict__ a_roff, const int64_t *__restrict__ w_roff,
+                   const int32_t *__restrict__ tie_list, const int32_t *__restrict__ n_tie, int32_t *__restrict__ tie_pos, const int32_t *__restrict__ tie_n,
+                   EmulQ q, int n_lo, int32_t *__restrict__ scr_pool /* one int per anchor of the long reads */)
 {
+	__shared__ int s_hist[256];
+	__shared__ unsigned long long s_diff;
+	__shared__ int s_w[SQS_TPB / 32], s_d[2];
+	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	const unsigned FULL = 0xffffffffu;
 	for (int t = blockIdx.x; t < *n_tie; t += gridDim.x) {
 		const int r = tie_list[t];
 		const int64_t base = a_roff[r];
 		const int n = (int)(a_roff[r + 1] - base);
 		if (n <= n_lo) continue;   // short reads: k_sort_emul, in shared memory
-		mb128 *W = wbuf + w_roff[r];
-		for (int i = threadIdx.x; i < n; i += blockDim.x) W[i] = in[base + i];
-		if (threadIdx.x == 0) {
-			const int nt = tie_n[r];
-			if (nt <= TL_MAX) { // ascending positions (collected in arbitrary order)
-				int32_t *T = tie_pos + (size_t)r * TL_MAX;
+		mb128 *W = wbuf + w_roff[r], *O = out + base;
+		const mb128 *src = in + base;
+		int32_t *T = tie_pos + (size_t)r * TL_MAX;
+		const int nt = tie_n[r];
+		__syncthreads();
+		if (tid == 0) {
+			if (nt <= TL_MAX) // ascending positions (collected in arbitrary order)
 				for (int i = 1; i < nt; ++i) { const int v = T[i]; int j = i; while (j > 0 && T[j - 1] > v) { T[j] = T[j - 1]; --j; } T[j] = v; }
+			s_diff = 0; s_d[0] = 256; s_d[1] = -1;
+		}
+		s_hist[tid] = 0;
+		__syncthreads();
+		{ // first byte level on which the keys differ
+			const uint64_t k0 = src[0].x; uint64_t d = 0;
+			for (int i = tid; i < n; i += SQS_TPB) d |= src[i].x ^ k0;
+			#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) d |= __shfl_xor_sync(FULL, d, o);
+			if (lane == 0 && d) atomicOr(&s_diff, (unsigned long long)d);
+		}
+		__syncthreads();
+		int s = 56;
+		{ const uint64_t diff = s_diff; while (s > 0 && !(diff >> s & 255)) s -= 8; }
+		for (int i = tid; i < n; i += SQS_TPB) atomicAdd(&s_hist[(int)(src[i].x >> s & 255)], 1);
+		__syncthreads();
+		const int n_ne = __syncthreads_count(s_hist[tid] > 0);
+		if (n_ne != 2 || s == 0) { // general first level: walked like every other range
+			for (int i = tid; i < n; i += SQS_TPB) W[i] = src[i];
+			if (tid == 0) sq_push(q, r, 0, n, 56);
+			continue;
+		}
+		if (s_hist[tid] > 0) { atomicMin(&s_d[0], tid); atomicMax(&s_d[1], tid); }
+		__syncthreads();
+		const int d0 = s_d[0], d1 = s_d[1], c0 = s_hist[d0];
+		const int m_max = c0 < n - c0 ? c0 : n - c0;
+		int32_t *ppos = scr_pool + w_roff[r], *qpos = ppos + m_max;
+		// ranks of the misplaced elements of either region; sweep() calls f(i, flag, exclusive rank) for lo <= i < hi in order
+		auto sweep = [&](int lo, int hi, int bad, auto f) {
+			int carry = 0;
+			for (int c = lo; c < hi; c += SQS_TPB) {
+				const int i = c + tid;
+				const bool flag = i < hi && (int)(src[i].x >> s & 255) == bad;
+				const unsigned bal = __ballot_sync(FULL, flag);
+				if (lane == 0) s_w[wid] = __popc(bal);
+				__syncthreads();
+				int woff = 0, tot = 0;
+				#pragma unroll
+				for (int w = 0; w < SQS_TPB / 32; ++w) { const int v = s_w[w]; woff += w < wid ? v : 0; tot += v; }
+				if (i < hi) f(i, flag, carry + woff + __popc(bal & ((1u << lane) - 1)));
+				__syncthreads();
+				carry += tot;
 			}
-			sq_push(q, r, 0, n, 56);
+			return carry;
+		};
+		const int m = sweep(0, c0, d1, [&](int i, bool flag, int rk) { if (flag) ppos[rk] = i; });
+		sweep(c0, n, d0, [&](int i, bool flag, int rk) { if (flag) qpos[rk] = i; });
+		__syncthreads();
+		sweep(0, c0, d1, [&](int i, bool flag, int rk) { W[i] = flag ? src[qpos[rk]] : src[i]; });
+		sweep(c0, n, d0, [&](int i, bool, int e) {
+			const bool first = i == c0 || (int)(src[i - 1].x >> s & 255) == d0;
+			W[i] = e >= m ? src[i] : first ? src[ppos[e]] : src[i - 1];
+		});
+		__syncthreads();
+		if (tid == 0) { // the two buckets: descend where a tied pair sits
+			const int s2 = s > 8 ? s - 8 : 0;
+			for (int h = 0; h < 2; ++h) {
+				const int lo = h ? c0 : 0, hi = h ? n : c0;
+				if (hi - lo < 2) continue;
+				bool has = nt > TL_MAX;
+				for (int j = 0; j < nt && j < TL_MAX && !has; ++j) has = T[j] > lo && T[j] < hi;
+				if (!has) continue;
+				if (hi - lo > MB_RS_MIN_SIZE) sq_push(q, r, lo, hi, s2);
+				else for (int a = lo; a < hi; ++a) { // leaf: stable order of the current arrangement
+					const mb128 v = W[a];
+					int rank = 0;
+					for (int bb2 = lo; bb2 < hi; ++bb2) { const uint64_t xb = W[bb2].x; rank += (xb < v.x) || (xb == v.x && bb2 < a); }
+					O[lo + rank] = v;
+				}
+			}
 		}
 	}
 }
@@ -379,24 +460,31 @@ k_sort_emul_q(mb128 *__restrict__ out, mb128 *__restrict__ wbuf, const int64_t *
 	int *be = ends_pool + (size_t)(blockIdx.x * SQ_TPB + threadIdx.x) * 256;   // bucket ends of the lane's current item
 	volatile int *ready = q.ready; volatile int *ctr = q.ctr;
 	const unsigned FULL = 0xffffffffu;
-	int state = 0, slot = -1;
+	const int lane = threadIdx.x & 31;
+	// the first slots go to lane 0 of every warp, the next to lane 1, ...: the long first-level walks of a batch spread over
+	// all SMs instead of filling the first few CTAs; later claims take the slots behind those
+	const int n_thr = gridDim.x * SQ_TPB, n_warp = n_thr >> 5;
+	int state = 0, slot = lane * n_warp + ((blockIdx.x * SQ_TPB + threadIdx.x) >> 5);
 	mb128 *W = nullptr, *O = nullptr; const int32_t *T = nullptr;
 	int r = 0, nt = 0, beg = 0, end = 0, s = 0, i = 0, k = 0, bek = 0, l = 0, ti = 0, prev_end = 0;
-	bool in_cycle = false, all_ranges = false;
+	bool in_cycle = false, all_ranges = false, warp_idle = true;
 	mb128 tmp; tmp.x = tmp.y = 0;
 	uint64_t k0 = 0, diff = 0;
-	for (;;) {
-		if (state == 0) { // take an item
-			if (slot < 0) slot = atomicAdd(&q.ctr[1], 1);
+	for (unsigned iter = 0;; ++iter) {
+		bool want_leaf = false; int leaf_lo = 0, leaf_hi = 0;
+		if (state == 0) { // take an item (polled every 8th iteration while warp-mates work: a poll is two trips to L2)
+			if (slot < 0) slot = n_thr + atomicAdd(&q.ctr[1], 1);
 			if (slot >= q.cap) state = 9;
-			else if (ready[slot]) {
-				__threadfence();
-				const int4 it = __ldcg(&q.items[slot]);
-				r = it.x, beg = it.y, end = it.z, s = it.w; slot = -1;
-				W = wbuf + w_roff[r]; O = out + a_roff[r];
-				T = tie_pos + (size_t)r * TL_MAX; nt = tie_n[r]; all_ranges = nt > TL_MAX;
-				k0 = sq_ldx(W + beg); diff = 0; i = beg + 1; state = 1;
-			} else if (ctr[2] == 0 && !ready[slot]) state = 9;
+			else if (warp_idle || (iter & 7) == 0) {
+				if (ready[slot]) {
+					__threadfence();
+					const int4 it = __ldcg(&q.items[slot]);
+					r = it.x, beg = it.y, end = it.z, s = it.w; slot = -1;
+					W = wbuf + w_roff[r]; O = out + a_roff[r];
+					T = tie_pos + (size_t)r * TL_MAX; nt = tie_n[r]; all_ranges = nt > TL_MAX;
+					k0 = sq_ldx(W + beg); diff = 0; i = beg + 1; state = 1;
+				} else if (ctr[2] == 0 && !ready[slot]) state = 9;
+			}
 		} else if (state == 1) { // byte levels on which the whole range agrees move nothing: skip them
 			#pragma unroll
 			for (int u = 0; u < 8; ++u) if (i < end) { diff |= sq_ldx(W + i) ^ k0; ++i; }
@@ -438,21 +526,37 @@ k_sort_emul_q(mb128 *__restrict__ out, mb128 *__restrict__ wbuf, const int64_t *
 				const bool has = all_ranges || (ti < nt && T[ti] < hi);
 				if (has) {
 					if (s > 0 && len > MB_RS_MIN_SIZE) sq_push(q, r, lo, hi, s > 8 ? s - 8 : 0);
-					else if (s > 0) { // leaf: upstream's insertion sort = stable order of the current arrangement
-						for (int a = lo; a < hi; ++a) {
-							const mb128 v = sq_ld(W + a);
-							int rank = 0;
-							for (int b = lo; b < hi; ++b) { const uint64_t xb = sq_ldx(W + b); rank += (xb < v.x) || (xb == v.x && b < a); }
-							O[lo + rank] = v;
-						}
-					} else for (int a = lo; a < hi; ++a) O[a] = sq_ld(W + a);
+					else if (s > 0) want_leaf = true, leaf_lo = lo, leaf_hi = hi;
+					else for (int a = lo; a < hi; ++a) O[a] = sq_ld(W + a);
 				}
 			}
-			if (++k == 256) { __threadfence(); atomicSub(&q.ctr[2], 1); state = 0; }
+			if (++k == 256) state = 5;
 		}
-		const bool idle = state == 0 || state == 9;
+		// leaves (<= 64 elements; upstream's insertion sort = stable order of the current arrangement), by the whole warp:
+		// two elements per lane, ranks by comparing against all of them
+		unsigned need = __ballot_sync(FULL, want_leaf);
+		while (need) {
+			const int src = __ffs(need) - 1; need &= need - 1;
+			const mb128 *Wl = reinterpret_cast<const mb128*>(__shfl_sync(FULL, (unsigned long long)W, src));
+			mb128 *Ol = reinterpret_cast<mb128*>(__shfl_sync(FULL, (unsigned long long)O, src));
+			const int lo = __shfl_sync(FULL, leaf_lo, src), len = __shfl_sync(FULL, leaf_hi, src) - lo;
+			mb128 v0, v1; v0.x = v0.y = v1.x = v1.y = 0;
+			if (lane < len) v0 = sq_ld(Wl + lo + lane);
+			if (lane + 32 < len) v1 = sq_ld(Wl + lo + lane + 32);
+			int r0 = 0, r1 = 0;
+			for (int b = 0; b < len; ++b) {
+				const uint64_t xa = __shfl_sync(FULL, v0.x, b & 31), xc = __shfl_sync(FULL, v1.x, b & 31);
+				const uint64_t xb = b < 32 ? xa : xc;
+				r0 += (xb < v0.x) || (xb == v0.x && b < lane);
+				r1 += (xb < v1.x) || (xb == v1.x && b < lane + 32);
+			}
+			if (lane < len) Ol[lo + r0] = v0;
+			if (lane + 32 < len) Ol[lo + r1] = v1;
+		}
+		if (state == 5) { __threadfence(); atomicSub(&q.ctr[2], 1); state = 0; }
 		if (__all_sync(FULL, state == 9)) break;
-		if (__all_sync(FULL, idle)) __nanosleep(400);
+		warp_idle = __all_sync(FULL, state == 0 || state == 9);
+		if (warp_idle) __nanosleep(300);
 	}
 	#undef BB
 }
@@ -614,6 +718,16 @@ static void run_seed(Arena &ar, cudaStream_t st, const DevIndex &ix, int mid_occ
 		o.a = o.a_unsorted = ar.get<mb128>(1); o.n_a = 0;
 		return;
 	}
+	const bool dbg = getenv("MB_DEBUG") != nullptr;
+	cudaEvent_t dbg_ev[2] = {nullptr, nullptr};
+	if (dbg) { cudaEventCreate(&dbg_ev[0]); cudaEventCreate(&dbg_ev[1]); cudaEventRecord(dbg_ev[0], st); }
+	auto mark = [&](const char *what) { // MB_DEBUG: time since the previous mark (synchronises)
+		if (!dbg) return;
+		cudaEventRecord(dbg_ev[1], st); cudaEventSynchronize(dbg_ev[1]);
+		float ms = 0; cudaEventElapsedTime(&ms, dbg_ev[0], dbg_ev[1]);
+		fprintf(stderr, "[mb]   seed: %-22s %9.3f ms\n", what, ms);
+		cudaEventRecord(dbg_ev[0], st);
+	};
 	int32_t *occ = ar.get<int32_t>(n_mini), *cnt = ar.get<int32_t>(n_mini);
 	uint64_t *val = ar.get<uint64_t>(n_mini);
 	int64_t *a_off = ar.get<int64_t>(n_mini + 1);
@@ -621,6 +735,7 @@ static void run_seed(Arena &ar, cudaStream_t st, const DevIndex &ix, int mid_occ
 	k_rep_len<<<(unsigned)cdiv((int64_t)n_reads * 32, 128), 128, 0, st>>>(mini, mini_off, occ, n_reads, mid_occ, o.rep_len); ++*n_launch;
 	exclusive_scan<int32_t>(ar, st, cnt, a_off, n_mini, n_launch);
 	k_read_anchor_off<<<(unsigned)cdiv(n_reads + 1, 128), 128, 0, st>>>(mini_off, a_off, n_reads, o.a_roff); ++*n_launch;
+	mark("lookup+scan");
 	int64_t n_a = 0;
 	CK(cudaMemcpyAsync(&n_a, a_off + n_mini, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));
@@ -629,6 +744,7 @@ static void run_seed(Arena &ar, cudaStream_t st, const DevIndex &ix, int mid_occ
 	o.a = ar.get<mb128>(n_a + 1);
 	if (n_a == 0) return;
 	k_seed_fill<<<(unsigned)cdiv(n_mini, 256), 256, 0, st>>>(ix, mini, mini_off, n_mini, d_read_off, cnt, val, a_off, o.a_unsorted); ++*n_launch;
+	mark("fill");
 	// reads too large for the shared-memory sort: listed, and given a slice of a ping-pong buffer for the global-memory radix sort
 	int32_t *big_sz = ar.get<int32_t>(n_reads);
 	int64_t *big_off = ar.get<int64_t>(n_reads + 1);
@@ -659,9 +775,11 @@ static void run_seed(Arena &ar, cudaStream_t st, const DevIndex &ix, int mid_occ
 		uint32_t max_rid = ix.n_seq > 0 ? (uint32_t)(ix.n_seq - 1) : 0;
 		for (int b = 0; b < 4; ++b) if ((b == 0 && max_rid) || (b > 0 && (max_rid >> (8 * b)) != 0)) pass_mask |= 1u << (4 + b);
 		k_sort_anchors_big<<<num_sms * 4, SB_TPB, 0, st>>>(o.a_unsorted, o.a, big_tmp, o.a_roff, big_list, ctr + 2, ctr + 3, big_off, pass_mask, tie_list, ctr, tie_pos, tie_n); ++*n_launch;
+		mark("radix sort (long)");
 	}
 	int grid = n_reads < num_sms * 8 ? n_reads : num_sms * 8;
 	k_sort_anchors<<<grid, SORT_TPB, 0, st>>>(o.a_unsorted, o.a, o.a_roff, n_reads, tie_list, ctr, o.read_perm); ++*n_launch;
+	mark("bitonic sort (short)");
 	static bool se_attr = false;
 	if (!se_attr) {
 		CK(cudaFuncSetAttribute(k_sort_emul, cudaFuncAttributeMaxDynamicSharedMemorySize, SE_SMEM_BYTES));
@@ -670,18 +788,22 @@ static void run_seed(Arena &ar, cudaStream_t st, const DevIndex &ix, int mid_occ
 	}
 	if (big_total > 0) { // long reads with ties: queue of ranges, one lane per range (the long walks start first)
 		EmulQ q;
-		q.cap = (int)std::min<int64_t>(big_total / 8 + n_reads + (int64_t)num_sms * SQ_TPB + 4096, 0x7fffff00);
+		q.cap = (int)std::min<int64_t>(big_total / 8 + n_reads + 2 * (int64_t)num_sms * SQ_TPB + 4096, 0x7fffff00);
 		q.items = ar.get<int4>(q.cap); q.ready = ar.get<int>(q.cap); q.ctr = ar.get<int>(4);
 		int *ends_pool = ar.get<int>((size_t)num_sms * SQ_TPB * 256);
+		int32_t *scr_pool = ar.get<int32_t>(big_total + 1);
 		CK(cudaMemsetAsync(q.ready, 0, (size_t)q.cap * sizeof(int), st));
 		CK(cudaMemsetAsync(q.ctr, 0, 4 * sizeof(int), st));
-		k_sort_emul_q_seed<<<num_sms * 4, 256, 0, st>>>(o.a_unsorted, big_tmp, o.a_roff, big_off, tie_list, ctr, tie_pos, tie_n, q, SE_SMEM_N);
+		k_sort_emul_q_seed<<<num_sms * 4, SQS_TPB, 0, st>>>(o.a_unsorted, big_tmp, o.a, o.a_roff, big_off, tie_list, ctr, tie_pos, tie_n, q, SE_SMEM_N, scr_pool);
 		k_sort_emul_q<<<num_sms, SQ_TPB, 256 * SQ_TPB * sizeof(int), st>>>(o.a, big_tmp, o.a_roff, big_off, tie_pos, tie_n, q, ends_pool);
 		*n_launch += 2;
+		mark("replay (long, queued)");
 	}
 	const int se_grid = num_sms * 5;   // 43 KB of shared memory per one-warp CTA: five fit an SM
 	int *ws_pool = ar.get<int>((size_t)se_grid * 6 * SE_STACK);
 	k_sort_emul<<<se_grid, 32, SE_SMEM_BYTES, st>>>(o.a_unsorted, o.a, o.a_roff, tie_list, ctr, ctr + 1, ws_pool, SE_SMEM_N, 0); ++*n_launch;
+	mark("replay (short)");
+	if (dbg) { cudaEventDestroy(dbg_ev[0]); cudaEventDestroy(dbg_ev[1]); }
 	if (getenv("MB_DEBUG")) {
 		int32_t h = 0; cudaMemcpyAsync(&h, ctr, sizeof(h), cudaMemcpyDeviceToHost, st); cudaStreamSynchronize(st);
 		fprintf(stderr, "[mb] reads with tied anchor keys: %d of %d\n", h, n_reads);
