@@ -15,7 +15,14 @@
 
 #define DPC_THREADS 256
 #define DPC_SMEM_MAX (100 * 1024)
+// WIN: the per-diagonal state only lives inside the band, [st - 1, en + 16] of the current diagonal, and both ends only move
+// right: with WIN = true the state arrays (and the target / query codes) are circular buffers of DPC_WIN entries indexed by
+// t & (DPC_WIN - 1) (query: j & (DPC_WIN - 1)), topped up with pristine entries one diagonal ahead.  A 5 kb x 10 kb end
+// extension then keeps its state in 14 KB of shared memory instead of 125 KB of global memory.  Needs w + 64 < DPC_WIN.
+#define DPC_WIN 1024
+#define DPC_WIN_SMEM (DPC_WIN * 9 + DPC_WIN * 4 + 64)
 
+template <bool WIN>
 __global__ void __launch_bounds__(DPC_THREADS)
 k_dp_cta(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const int32_t *__restrict__ n_order, int32_t *__restrict__ work_ctr,
          const uint8_t *__restrict__ codes, const uint32_t *__restrict__ S, const uint8_t *__restrict__ pool,
@@ -58,22 +65,28 @@ k_dp_cta(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const in
 		const int long_diff = long_thres * (e - e2) - (q2 - q) - e2;
 		const size_t ws_need = (size_t)T16 * 8 + (size_t)qlen_ * 16 + 16;
 		const size_t h_need = with_exact ? (size_t)T16 * 4 : 0;
-		const bool in_smem = ((ws_need + 15) & ~(size_t)15) + h_need <= (size_t)smem_bytes;
+		const bool in_smem = WIN || ((ws_need + 15) & ~(size_t)15) + h_need <= (size_t)smem_bytes;
+		const int A = WIN ? DPC_WIN : T16;   // entries per state array
 		int8_t *ws = in_smem ? dpc_smem : g_ws + (size_t)blockIdx.x * g_stride;
-		int32_t *H = (in_smem && with_exact) ? reinterpret_cast<int32_t*>(ws + ((ws_need + 15) & ~(size_t)15)) : h_scr + (size_t)blockIdx.x * h_stride;
-		int8_t *u = ws, *v = u + T16, *x = v + T16, *y = x + T16, *x2 = y + T16, *y2 = x2 + T16, *s = y2 + T16;
-		uint8_t *sf = (uint8_t*)(s + T16), *qr = sf + T16;
+		int32_t *H = WIN ? reinterpret_cast<int32_t*>(dpc_smem + DPC_WIN * 9)
+		           : (in_smem && with_exact) ? reinterpret_cast<int32_t*>(ws + ((ws_need + 15) & ~(size_t)15)) : h_scr + (size_t)blockIdx.x * h_stride;
+		int8_t *u = ws, *v = u + A, *x = v + A, *y = x + A, *x2 = y + A, *y2 = x2 + A, *s = y2 + A;
+		uint8_t *sf = (uint8_t*)(s + A), *qr = sf + A;   // WIN: qr holds the query by position j (not reversed), circular
 		const int8_t I1 = (int8_t)(-q - e), I2 = (int8_t)(-q2 - e2);
-		{
-			QView qv; qv.codes = T.q_comp == 2 ? pool : codes; qv.idx0 = T.q_idx0; qv.step = T.q_step; qv.comp = T.q_comp == 1;
-			TView tv; tv.S = S; tv.bytes = pool; tv.idx0 = T.t_idx0; tv.step = T.t_step; tv.packed = T.t_packed;
-			for (int t = tid; t < T16; t += DPC_THREADS) {
-				u[t] = I1, v[t] = I1, x[t] = I1, y[t] = I1, x2[t] = I2, y2[t] = I2, s[t] = 0;
-				sf[t] = t < tlen ? (uint8_t)tv.at(t) : 0;
-				if (with_exact) H[t] = MB_KSW_NEG_INF;
-			}
-			for (int t = tid; t < qlen_ * 16 + 16; t += DPC_THREADS) qr[t] = t < qlen ? (uint8_t)qv.at(qlen - 1 - t) : 0;
-		}
+		QView qv; qv.codes = T.q_comp == 2 ? pool : codes; qv.idx0 = T.q_idx0; qv.step = T.q_step; qv.comp = T.q_comp == 1;
+		TView tv; tv.S = S; tv.bytes = pool; tv.idx0 = T.t_idx0; tv.step = T.t_step; tv.packed = T.t_packed;
+		auto ix = [](int t) { return WIN ? (t & (DPC_WIN - 1)) : t; };
+		auto fresh_t = [&](int t) { // a pristine entry, as upstream's arrays are before a diagonal touches them
+			const int k = ix(t);
+			u[k] = I1, v[k] = I1, x[k] = I1, y[k] = I1, x2[k] = I2, y2[k] = I2, s[k] = 0;
+			sf[k] = t < tlen ? (uint8_t)tv.at(t) : 0;
+			if (with_exact) H[k] = MB_KSW_NEG_INF;
+		};
+		int hi_t = (WIN && T16 > DPC_WIN ? DPC_WIN : T16) - 1;            // entries 0..hi_t are set up
+		int hi_j = WIN ? (qlen > DPC_WIN ? DPC_WIN : qlen) - 1 : 0;
+		for (int t = tid; t <= hi_t; t += DPC_THREADS) fresh_t(t);
+		if (WIN) { for (int j = tid; j <= hi_j; j += DPC_THREADS) qr[j] = (uint8_t)qv.at(j); }
+		else for (int t = tid; t < qlen_ * 16 + 16; t += DPC_THREADS) qr[t] = t < qlen ? (uint8_t)qv.at(qlen - 1 - t) : 0;
 		__syncthreads();
 		// ez state: every thread keeps the same copy
 		int ez_max = 0, ez_max_t = -1, ez_max_q = -1, ez_mqe = MB_KSW_NEG_INF, ez_mqe_t = -1, ez_mte = MB_KSW_NEG_INF, ez_score = MB_KSW_NEG_INF, ez_zdropped = 0;
@@ -104,21 +117,22 @@ k_dp_cta(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const in
 				fresh[k] = false; uo[k] = yo[k] = y2o[k] = xl[k] = vl[k] = x2l[k] = zz[k] = 0; hold[k] = 0;
 				if (t >= span_end) continue;
 				if (t >= st0 && t < fill_end) {
-					const uint8_t sq = sf[t], sq2 = qrr[t];
+					const int jq = r - t;
+					const uint8_t sq = sf[ix(t)], sq2 = WIN ? ((jq >= 0 && jq < qlen) ? qr[jq & (DPC_WIN - 1)] : (uint8_t)0) : qrr[t];
 					zz[k] = (sq == 4 || sq2 == 4) ? sc.sc_N : (sq == sq2 ? sc.sc_mch : sc.sc_mis);
 					fresh[k] = true;
-				} else if (t <= en) zz[k] = s[t];
+				} else if (t <= en) zz[k] = s[ix(t)];
 				if (t > en) continue;
-				uo[k] = u[t], yo[k] = y[t], y2o[k] = y2[t];
-				if (t > st) xl[k] = x[t - 1], vl[k] = v[t - 1], x2l[k] = x2[t - 1];
+				uo[k] = u[ix(t)], yo[k] = y[ix(t)], y2o[k] = y2[ix(t)];
+				if (t > st) xl[k] = x[ix(t - 1)], vl[k] = v[ix(t - 1)], x2l[k] = x2[ix(t - 1)];
 				else if (st > 0) {
-					if (st - 1 >= last_st && st - 1 <= last_en) xl[k] = x[st - 1], x2l[k] = x2[st - 1], vl[k] = v[st - 1];
+					if (st - 1 >= last_st && st - 1 <= last_en) xl[k] = x[ix(st - 1)], x2l[k] = x2[ix(st - 1)], vl[k] = v[ix(st - 1)];
 					else xl[k] = I1, x2l[k] = I2, vl[k] = I1;
 				} else { xl[k] = I1, x2l[k] = I2; vl[k] = bnd(r); }
 				if (en >= r && t == r) { yo[k] = I1, y2o[k] = I2; uo[k] = bnd(r); }
 				if (with_exact && r > 0) {
-					if (t >= st0 && t <= en0) hold[k] = H[t];
-					if (t == en0 && en0 > 0) hprev = H[en0 - 1];
+					if (t >= st0 && t <= en0) hold[k] = H[ix(t)];
+					if (t == en0 && en0 > 0) hprev = H[ix(en0 - 1)];
 				}
 			}
 			__syncthreads();
@@ -128,7 +142,7 @@ k_dp_cta(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const in
 			for (int k = 0; k < KMAX; ++k) {
 				const int t = st + tid + k * DPC_THREADS;
 				if (t >= span_end) continue;
-				if (fresh[k]) s[t] = zz[k];
+				if (fresh[k]) s[ix(t)] = zz[k];
 				if (t > en) continue;
 				int8_t z = zz[k];
 				const int8_t xt1 = xl[k], vt1 = vl[k], x2t1 = x2l[k], ut = uo[k];
@@ -147,28 +161,28 @@ k_dp_cta(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const in
 				}
 				z = z < sc.sc_mch ? z : sc.sc_mch;
 				const int8_t un = (int8_t)(z - vt1), vn = (int8_t)(z - ut);
-				u[t] = un, v[t] = vn;
+				u[ix(t)] = un, v[ix(t)] = vn;
 				int8_t tmp = (int8_t)(z - q);
 				a = (int8_t)(a - tmp), b = (int8_t)(b - tmp);
 				tmp = (int8_t)(z - q2);
 				a2 = (int8_t)(a2 - tmp), b2 = (int8_t)(b2 - tmp);
 				if (!right) {
-					x[t]  = (int8_t)((a  > 0 ? a  : 0) - qe);  if (a  > 0) d |= 0x08;
-					y[t]  = (int8_t)((b  > 0 ? b  : 0) - qe);  if (b  > 0) d |= 0x10;
-					x2[t] = (int8_t)((a2 > 0 ? a2 : 0) - qe2); if (a2 > 0) d |= 0x20;
-					y2[t] = (int8_t)((b2 > 0 ? b2 : 0) - qe2); if (b2 > 0) d |= 0x40;
+					x[ix(t)]  = (int8_t)((a  > 0 ? a  : 0) - qe);  if (a  > 0) d |= 0x08;
+					y[ix(t)]  = (int8_t)((b  > 0 ? b  : 0) - qe);  if (b  > 0) d |= 0x10;
+					x2[ix(t)] = (int8_t)((a2 > 0 ? a2 : 0) - qe2); if (a2 > 0) d |= 0x20;
+					y2[ix(t)] = (int8_t)((b2 > 0 ? b2 : 0) - qe2); if (b2 > 0) d |= 0x40;
 				} else {
-					x[t]  = (int8_t)((0 > a  ? 0 : a)  - qe);  if (!(0 > a))  d |= 0x08;
-					y[t]  = (int8_t)((0 > b  ? 0 : b)  - qe);  if (!(0 > b))  d |= 0x10;
-					x2[t] = (int8_t)((0 > a2 ? 0 : a2) - qe2); if (!(0 > a2)) d |= 0x20;
-					y2[t] = (int8_t)((0 > b2 ? 0 : b2) - qe2); if (!(0 > b2)) d |= 0x40;
+					x[ix(t)]  = (int8_t)((0 > a  ? 0 : a)  - qe);  if (!(0 > a))  d |= 0x08;
+					y[ix(t)]  = (int8_t)((0 > b  ? 0 : b)  - qe);  if (!(0 > b))  d |= 0x10;
+					x2[ix(t)] = (int8_t)((0 > a2 ? 0 : a2) - qe2); if (!(0 > a2)) d |= 0x20;
+					y2[ix(t)] = (int8_t)((0 > b2 ? 0 : b2) - qe2); if (!(0 > b2)) d |= 0x40;
 				}
 				P[(size_t)r * ncol16 + (t - st)] = (uint8_t)d;
 				if (with_exact) {
 					if (r > 0) {
 						if (t >= st0 && t < en0) {
 							const int32_t h = hold[k] + (int32_t)vn;
-							H[t] = h;
+							H[ix(t)] = h;
 							const int en1 = st0 + (en0 - st0) / 4 * 4;
 							const unsigned rank = t < en1 ? 1u + ((unsigned)((t - st0) & 3) << 22) + (unsigned)((t - st0) >> 2) : 1u + (4u << 22) + (unsigned)(t - en1);
 							const long long key = ((long long)h << 32) | (unsigned)(0x7fffffffu - rank);
@@ -176,17 +190,31 @@ k_dp_cta(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const in
 						}
 						if (t == en0) {
 							const int32_t he = en0 > 0 ? hprev + (int32_t)un : hold[k] + (int32_t)vn;
-							H[en0] = he;
+							H[ix(en0)] = he;
 							const long long key = ((long long)he << 32) | (unsigned)0x7fffffffu;
 							best = key > best ? key : best;
 						}
-					} else if (t == 0) H[0] = (int32_t)vn - qe;
+					} else if (t == 0) H[0] = (int32_t)vn - qe;   // ix(0) == 0
 				}
 			}
 			if (with_exact && r > 0) {
 				#pragma unroll
 				for (int dlt = 16; dlt > 0; dlt >>= 1) { const long long o = __shfl_xor_sync(FULL, best, dlt); best = o > best ? o : best; }
 				if (lane == 0) s_red[wid] = best;
+			}
+			if (WIN && r + 1 < n_rows) { // pristine entries for what the next diagonal reaches beyond the entries set up so far
+				const int r1 = r + 1;
+				int st1 = 0, en1 = tlen - 1;
+				if (st1 < r1 - qlen + 1) st1 = r1 - qlen + 1;
+				if (en1 > r1) en1 = r1;
+				if (st1 < (r1 - w + 1) >> 1) st1 = (r1 - w + 1) >> 1;
+				if (en1 > (r1 + w) >> 1) en1 = (r1 + w) >> 1;
+				int need_t = (en1 + 16) / 16 * 16 + 31; if (need_t > T16 - 1) need_t = T16 - 1;
+				for (int t = hi_t + 1 + tid; t <= need_t; t += DPC_THREADS) fresh_t(t);
+				if (need_t > hi_t) hi_t = need_t;
+				int need_j = r1 - st1 + 16; if (need_j > qlen - 1) need_j = qlen - 1;
+				for (int j = hi_j + 1 + tid; j <= need_j; j += DPC_THREADS) qr[j & (DPC_WIN - 1)] = (uint8_t)qv.at(j);
+				if (need_j > hi_j) hi_j = need_j;
 			}
 			__syncthreads();
 			cells += tid == 0 ? (unsigned)(en0 - st0 + 1) : 0u;
@@ -203,8 +231,8 @@ k_dp_cta(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const in
 					else if (rank < 1u + (4u << 22)) { const unsigned rr = rank - 1; max_t = st0 + (int)((rr & ((1u << 22) - 1)) << 2) + (int)(rr >> 22); }
 					else max_t = en1 + (int)(rank - 1u - (4u << 22));
 				} else { max_H = (int32_t)v[0] - qe, max_t = 0; }
-				if (en0 == tlen - 1) { const int32_t h = H[en0]; if (h > ez_mte) ez_mte = h; }
-				if (r - st0 == qlen - 1) { const int32_t h = H[st0]; if (h > ez_mqe) ez_mqe = h, ez_mqe_t = st0; }
+				if (en0 == tlen - 1) { const int32_t h = H[ix(en0)]; if (h > ez_mte) ez_mte = h; }
+				if (r - st0 == qlen - 1) { const int32_t h = H[ix(st0)]; if (h > ez_mqe) ez_mqe = h, ez_mqe_t = st0; }
 				bool brk = false;
 				if (max_H > ez_max) { ez_max = max_H, ez_max_t = max_t, ez_max_q = r - max_t; }
 				else if (max_t >= ez_max_t && r - max_t >= ez_max_q) {
@@ -213,17 +241,17 @@ k_dp_cta(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const in
 					if (zdrop >= 0 && ez_max - max_H > zdrop + l * e2) { ez_zdropped = 1; brk = true; }
 				}
 				if (brk) break;
-				if (r == qlen + tlen - 2 && en0 == tlen - 1) ez_score = H[tlen - 1];
+				if (r == qlen + tlen - 2 && en0 == tlen - 1) ez_score = H[ix(tlen - 1)];
 			} else {
 				if (r > 0) {
 					if (last_H0_t >= st0 && last_H0_t <= en0 && last_H0_t + 1 >= st0 && last_H0_t + 1 <= en0) {
-						const int32_t d0 = v[last_H0_t], d1 = u[last_H0_t + 1];
+						const int32_t d0 = v[ix(last_H0_t)], d1 = u[ix(last_H0_t + 1)];
 						if (d0 > d1) H0 += d0;
 						else H0 += d1, ++last_H0_t;
 					} else if (last_H0_t >= st0 && last_H0_t <= en0) {
-						H0 += v[last_H0_t];
+						H0 += v[ix(last_H0_t)];
 					} else {
-						++last_H0_t, H0 += u[last_H0_t];
+						++last_H0_t, H0 += u[ix(last_H0_t)];
 					}
 				} else H0 = v[0] - qe, last_H0_t = 0;
 				if (r == qlen + tlen - 2 && en0 == tlen - 1) ez_score = H0;

@@ -79,6 +79,8 @@ struct ThreadCtx {
 	// warps still on their last task pair) overlaps the ramp-up of the next instead of idling the GPU 13 times per pass
 	cudaStream_t stf[2] = {};
 	cudaEvent_t ev_f[2] = {}, ev_fork = nullptr;
+	cudaEvent_t ev_x[4] = {}, ev_fork2 = nullptr;
+	cudaStream_t st_defer = nullptr; cudaEvent_t ev_defer = nullptr;   // long exact END EXTENSIONS of a first pass: run behind the gap-fill kernels, joined before the stitch   // extension / band launches done (before the gap-fill launches start)
 	std::vector<cudaEvent_t> feed_events;   // host->device pieces of mb_map_batch (SketchFeed)
 	int64_t piece_bases = 0;                // bases per sequential piece once a batch did not fit the device (0: the default)
 	const void *piece_index = nullptr;      // ... for this index
@@ -110,6 +112,10 @@ struct ThreadCtx {
 			if (ev_fast_done) cudaEventDestroy(ev_fast_done);
 			for (int i = 0; i < 2; ++i) { if (stf[i]) cudaStreamDestroy(stf[i]); if (ev_f[i]) cudaEventDestroy(ev_f[i]); }
 			if (ev_fork) cudaEventDestroy(ev_fork);
+			if (ev_fork2) cudaEventDestroy(ev_fork2);
+			for (int i = 0; i < 4; ++i) if (ev_x[i]) cudaEventDestroy(ev_x[i]);
+			if (st_defer) cudaStreamDestroy(st_defer);
+			if (ev_defer) cudaEventDestroy(ev_defer);
 			for (cudaEvent_t e : feed_events) cudaEventDestroy(e);
 		}
 	}
@@ -156,9 +162,12 @@ static ThreadCtx *make_ctx(int device)
 		CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
 		CK(cudaEventCreateWithFlags(&c->ev_fast_done, cudaEventDisableTiming));
 		CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&c->ev_fork2, cudaEventDisableTiming));
+		CK(cudaStreamCreateWithFlags(&c->st_defer, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->ev_defer, cudaEventDisableTiming));
+		for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&c->ev_x[i], cudaEventDisableTiming));
 		for (int i = 0; i < 2; ++i) { CK(cudaStreamCreateWithFlags(&c->stf[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->ev_f[i], cudaEventDisableTiming)); }
 		for (int i = 0; i < MB_NSIDE; ++i) {
-			CK(cudaStreamCreateWithPriority(&c->st2[i], cudaStreamNonBlocking, hi));
+			CK(cudaStreamCreateWithPriority(&c->st2[i], cudaStreamNonBlocking, getenv("MB_SIDE_PRIO0") ? 0 : hi));
 			CK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
 		}
 	}
@@ -168,7 +177,7 @@ static ThreadCtx *make_ctx(int device)
 	std::call_once(g_const_once[device & 15], [&]() {
 		CK(cudaMemcpyToSymbol(c_nt4, h_nt4, 256));
 		CK(cudaFuncSetAttribute(k_dp, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM_MAX));
-		CK(cudaFuncSetAttribute(k_dp_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_SMEM_MAX));
+		CK(cudaFuncSetAttribute(k_dp_cta<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DPC_SMEM_MAX));
 	});
 	return c;
 }
@@ -653,7 +662,8 @@ static __host__ __device__ inline DpGeom dp_geom(int qlen, int tlen, int w)
 #define DP_EBASE (2 * DPF_NCLASS + DPB_NCLASS)   // then the exact-kernel classes (one warp per task)
 #define DP_NCTA 4                    // and the CTA-per-task exact kernel for the large ones (exact classes 2..5)
 #define DP_CBASE (DP_EBASE + DP_NEXACT)
-#define DP_NCLS (DP_CBASE + DP_NCTA)
+#define DP_DBASE (DP_CBASE + DP_NCTA)   // the same for end extensions whose results are not needed before the stitch (deferred launches)
+#define DP_NCLS (DP_DBASE + DP_NCTA)
 static __host__ __device__ inline int dp_exact_class(size_t p_bytes)
 {
 	int k = 0;
@@ -663,7 +673,7 @@ static __host__ __device__ inline int dp_exact_class(size_t p_bytes)
 
 // classify tasks: fast path by columns-per-lane class, the rest into small / big scratch classes; record maxima
 __global__ void k_dp_classify(const DpTask *__restrict__ tasks, const int32_t *__restrict__ ids, int64_t n, int use_ids,
-                              const uint8_t *__restrict__ codes, const uint32_t *__restrict__ S, const uint8_t *__restrict__ pool, int fast_ok,
+                              const uint8_t *__restrict__ codes, const uint32_t *__restrict__ S, const uint8_t *__restrict__ pool, int fast_ok, int defer_ext,
                               int32_t *__restrict__ lists /* DP_NCLS x n */, int32_t *__restrict__ ctr /* DP_NCLS */,
                               unsigned long long *__restrict__ maxima /* DP_NCLS x 3 */)
 {
@@ -704,7 +714,7 @@ __global__ void k_dp_classify(const DpTask *__restrict__ tasks, const int32_t *_
 			const int ec = dp_exact_class(g.p_bytes);
 			int wd = t.w < 0 ? (t.tlen > t.qlen ? t.tlen : t.qlen) : t.w;
 			int dw = t.qlen < t.tlen ? t.qlen : t.tlen; dw = dw < wd + 1 ? dw : wd + 1;      // widest diagonal
-			cls = (ec >= 2 && dw + 48 <= DPC_THREADS * 4) ? DP_CBASE + (ec - 2) : DP_EBASE + ec;
+			cls = (ec >= 2 && dw + 64 <= DPC_WIN) ? ((defer_ext && t.kind != 1) ? DP_DBASE : DP_CBASE) + (ec - 2) : DP_EBASE + ec;
 			m0 = (unsigned)g.p_bytes, m1 = (unsigned)g.ws_bytes, m2 = (unsigned)g.h_ints;
 		}
 	}
@@ -729,6 +739,10 @@ __global__ void k_dp_classify(const DpTask *__restrict__ tasks, const int32_t *_
 	base = __shfl_sync(peers, base, leader);
 	lists[(int64_t)cls * n + base + rank] = id;
 }
+
+// grids of the side-stream kernels (exact, band, extension) relative to their defaults (MB_SIDE_SCALE; tuning knob)
+static double mb_side_scale() { static double v = -1; if (v < 0) { const char *e = getenv("MB_SIDE_SCALE"); v = e ? atof(e) : 1.0; if (v <= 0) v = 1.0; } return v; }
+static int mb_side_grid(int n) { const int v = (int)(n * mb_side_scale()); return v < 8 ? (n < 8 ? n : 8) : v; }
 
 struct DpRunner {
 	ThreadCtx &c; cudaStream_t st; int64_t *nl;
@@ -781,7 +795,7 @@ struct DpRunner {
 			if (occ < 1) occ = 1;
 		}
 		const size_t stride_words = ((size_t)32 * (size_t)(max_q + 31) * CW + 63) & ~(size_t)63;
-		int max_cta = c.num_sms * (occ < 2 ? occ : 2);   // small side launches: never fill the GPU
+		int max_cta = c.num_sms * occ;   // run at full occupancy and leave: the gap-fill launches wait for these
 		int64_t want = cdiv(cdiv(cnt, 2), DPX_WARPS);
 		int n_cta = (int)(want < max_cta ? want : max_cta);
 		uint32_t *p_scr = ar.get<uint32_t>((size_t)n_cta * DPX_WARPS * stride_words);
@@ -796,8 +810,12 @@ struct DpRunner {
 	}
 
 	// run the DP kernels over `n` tasks (ids[] if use_ids else 0..n-1)
+	// defer_ext: the large exact END EXTENSIONS (kind != 1; only the stitch reads their results) are launched on c.st_defer
+	// behind the gap-fill kernels and NOT joined: the caller waits for c.ev_defer (join_deferred) before it reads them.
+	bool deferred = false;
+	void join_deferred() { if (deferred) { CK(cudaStreamWaitEvent(st, c.ev_defer, 0)); deferred = false; } }
 	void run(DpTask *tasks, const int32_t *ids, int64_t n, bool use_ids, const uint8_t *codes, const uint32_t *S, const uint8_t *pool,
-	         uint32_t *cigar_pool, const DpScoring &sc, unsigned long long *d_cells)
+	         uint32_t *cigar_pool, const DpScoring &sc, unsigned long long *d_cells, bool defer_ext = false)
 	{
 		if (n <= 0) return;
 		Arena &ar = c.ar;
@@ -806,7 +824,7 @@ struct DpRunner {
 		unsigned long long *maxima = ar.get<unsigned long long>(DP_NCLS * 3);
 		CK(cudaMemsetAsync(ctr, 0, DP_NCLS * sizeof(int32_t), st));
 		CK(cudaMemsetAsync(maxima, 0, DP_NCLS * 3 * sizeof(unsigned long long), st));
-		k_dp_classify<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(tasks, ids, n, use_ids ? 1 : 0, codes, S, pool, dpf_scoring_ok(sc) ? 1 : 0, lists, ctr, maxima); ++*nl;
+		k_dp_classify<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(tasks, ids, n, use_ids ? 1 : 0, codes, S, pool, dpf_scoring_ok(sc) ? 1 : 0, defer_ext ? 1 : 0, lists, ctr, maxima); ++*nl;
 		int32_t h_ctr[DP_NCLS]; unsigned long long h_max[DP_NCLS * 3];
 		CK(cudaMemcpyAsync(h_ctr, ctr, sizeof(h_ctr), cudaMemcpyDeviceToHost, st));
 		CK(cudaMemcpyAsync(h_max, maxima, sizeof(h_max), cudaMemcpyDeviceToHost, st));
@@ -841,39 +859,107 @@ struct DpRunner {
 		// complete), largest class first: a handful of long band-limited tasks give each launch a long tail of a few busy
 		// warps, which the fast kernels on `st` fill
 		bool side[MB_NSIDE] = {};
-		for (int b = DP_NCTA - 1; b >= 0; --b) { // the large exact tasks: one CTA per task (align_cta.cuh), largest class first
-			const int cls = DP_CBASE + b;
-			cudaStream_t st2 = c.st2[b & 1];
+		const bool serial = getenv("MB_DEBUG_SERIAL") != nullptr;   // every launch on `st`, one after the other: stand-alone durations
+		for (int k = DPB_NCLASS - 1; k >= 0; --k) { // large / band-limited gap fills: packed systolic kernel with upstream's band (dp_band.cuh)
+			const int cls = DP_BBASE + k;
 			const int64_t cnt = h_ctr[cls];
 			if (cnt == 0) continue;
+			const int mq = (int)h_max[cls * 3], mt = (int)h_max[cls * 3 + 1];
+			const int n_strips = (mt + DPB_STRIP - 1) / DPB_STRIP;
+			const size_t stride_words = ((size_t)DPB_MAX_STRIPS * DPB_EDGE_WORDS + (size_t)n_strips * (size_t)(mq + 31) * 32 * DPB_CW + 63) & ~(size_t)63;
+			int max_cta = c.num_sms * 3;   // full occupancy: the gap-fill launches wait for the band launches
+			const int64_t want = cdiv(cnt, 2);
+			const int n_cta = (int)(want < max_cta ? want : max_cta);
+			uint32_t *p_scr = ar.get<uint32_t>((size_t)n_cta * stride_words);
+			int32_t *wc = ar.get<int32_t>(1);
+			cudaStream_t sb = serial ? st : c.st2[2]; side[2] = true;
+			CK(cudaMemsetAsync(wc, 0, sizeof(int32_t), sb));
+			cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+			cudaEventRecord(e0, sb);
+			k_dp_band<<<n_cta, DPB_NW * 32, 0, sb>>>(tasks, lists + (int64_t)cls * n, ctr + cls, wc, codes, S, pool, p_scr, stride_words, cigar_pool, sc, d_cells ? d_cells + 3 : nullptr);
+			{ cudaError_t le = cudaGetLastError(); if (le != cudaSuccess) throw mb_error(MB_ERR_CUDA, std::string("k_dp_band launch: ") + cudaGetErrorString(le) + " grid " + std::to_string(n_cta)); }
+			cudaEventRecord(e1, sb);
+			evs.emplace_back(e0, e1); ev_fast.push_back(3); n_band += cnt;
+			++*nl;
+		}
+		CK(cudaEventRecord(c.ev_fork, st));
+		CK(cudaStreamWaitEvent(c.stf[0], c.ev_fork, 0)); CK(cudaStreamWaitEvent(c.stf[1], c.ev_fork, 0));
+		int n_ext_launch = 0;
+		for (int k = DPF_NCLASS - 1; k >= 0; --k) { // widest class first: its tasks are the longest
+			const int64_t cnt = h_ctr[DP_XBASE + k];
+			if (cnt == 0) continue;
+			const int32_t *list = lists + (int64_t)(DP_XBASE + k) * n;
+			const int mq = (int)h_max[(DP_XBASE + k) * 3];
+			unsigned long long *xc = d_cells ? d_cells + 2 : nullptr;
+			// the extension classes: small launches with tails, spread over four streams (three of them carry gap-fill launches
+			// afterwards) so that they overlap each other and are gone within a few milliseconds
+			const int si = n_ext_launch++ & 3;
+			cudaStream_t sx = serial ? st : (si == 0 ? c.st2[3] : si == 1 ? st : c.stf[si - 2]);
+			if (si == 0) side[3] = true;
+			switch (DPF_C[k]) {
+			case 4:  launch_ext<4>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
+			case 5:  launch_ext<5>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
+			case 6:  launch_ext<6>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
+			case 7:  launch_ext<7>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
+			case 8:  launch_ext<8>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
+			case 9:  launch_ext<9>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
+			case 10: launch_ext<10>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
+			case 11: launch_ext<11>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
+			case 12: launch_ext<12>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
+			case 14: launch_ext<14>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
+			case 16: launch_ext<16>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
+			case 20: launch_ext<20>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
+			default: launch_ext<24>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
+			}
+		}
+		if (!serial) { // the gap-fill and exact launches start when the extension and band launches are done
+			CK(cudaEventRecord(c.ev_x[0], c.st2[2])); CK(cudaEventRecord(c.ev_x[1], c.st2[3]));
+			CK(cudaEventRecord(c.ev_x[2], c.stf[0])); CK(cudaEventRecord(c.ev_x[3], c.stf[1]));
+			for (int i = 0; i < 4; ++i) CK(cudaStreamWaitEvent(st, c.ev_x[i], 0));
+			CK(cudaEventRecord(c.ev_fork2, st));
+			CK(cudaStreamWaitEvent(c.stf[0], c.ev_fork2, 0)); CK(cudaStreamWaitEvent(c.stf[1], c.ev_fork2, 0));
+			CK(cudaStreamWaitEvent(c.st2[0], c.ev_fork2, 0)); CK(cudaStreamWaitEvent(c.st2[1], c.ev_fork2, 0));
+		}
+		// The exact kernels start AFTER the band and extension kernels are done: their CTAs hold most of an SM's shared memory for
+		// tens of milliseconds (long dependency chains, few tasks) and would keep the short extension / band CTAs from becoming
+		// resident.  They run beside the gap-fill launches.
+		auto launch_cta = [&](int cls, cudaStream_t st2) { // the large exact tasks: one CTA per task (align_cta.cuh)
+			const int64_t cnt = h_ctr[cls];
+			if (cnt == 0) return false;
 			size_t p_stride = ((size_t)h_max[cls * 3 + 0] + 255) & ~(size_t)255;
 			const size_t g_stride = ((size_t)h_max[cls * 3 + 1] + 255) & ~(size_t)255;
 			size_t h_stride = ((size_t)h_max[cls * 3 + 2] + 63) & ~(size_t)63;
 			if (p_stride == 0) p_stride = 256;
 			if (h_stride == 0) h_stride = 64;
+			static const bool nowin = getenv("MB_CTA_NOWIN") != nullptr;   // debug: state arrays of full length (shared memory if they fit, else global)
 			const size_t need = ((g_stride + 15) & ~(size_t)15) + h_stride * 4 + 64;
-			const int smem = (int)(need < DPC_SMEM_MAX ? need : DPC_SMEM_MAX);
-			int per_sm = (200 * 1024) / (smem > 4096 ? smem : 4096); if (per_sm < 1) per_sm = 1; if (per_sm > 4) per_sm = 4;
-			int n_cta = (int)std::min<int64_t>(cnt, (int64_t)c.num_sms * per_sm);
-			const size_t per_cta = p_stride + g_stride + h_stride * 4;
+			const int smem = nowin ? (int)(need < DPC_SMEM_MAX ? need : DPC_SMEM_MAX) : DPC_WIN_SMEM;
+			int per_sm = (200 * 1024) / (smem > 4096 ? smem : 4096); if (per_sm < 1) per_sm = 1; if (per_sm > (nowin ? 4 : 6)) per_sm = nowin ? 4 : 6;   // 6 x 256 threads: leaves thread slots to the kernels of the other streams
+			int n_cta = (int)std::min<int64_t>(cnt, (int64_t)mb_side_grid(c.num_sms * per_sm));
+			const size_t per_cta = p_stride + (nowin ? g_stride + h_stride * 4 : 0);
 			while (n_cta > 1 && (size_t)n_cta * per_cta > ((size_t)24 << 30)) n_cta = (n_cta + 1) / 2;
 			uint8_t *p_scr = ar.get<uint8_t>((size_t)n_cta * p_stride);
-			int8_t *g_ws = ar.get<int8_t>((size_t)n_cta * g_stride + 16);
-			int32_t *h_scr = ar.get<int32_t>((size_t)n_cta * h_stride);
+			int8_t *g_ws = ar.get<int8_t>(nowin ? (size_t)n_cta * g_stride + 16 : 16);     // full-length state arrays: only without the window
+			int32_t *h_scr = ar.get<int32_t>(nowin ? (size_t)n_cta * h_stride : 16);
 			int32_t *wc = ar.get<int32_t>(1);
 			CK(cudaMemsetAsync(wc, 0, sizeof(int32_t), st2));
 			cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
 			cudaEventRecord(e0, st2);
-			k_dp_cta<<<n_cta, DPC_THREADS, smem, st2>>>(tasks, lists + (int64_t)cls * n, ctr + cls, wc, codes, S, pool,
+			if (nowin) k_dp_cta<false><<<n_cta, DPC_THREADS, smem, st2>>>(tasks, lists + (int64_t)cls * n, ctr + cls, wc, codes, S, pool,
+				p_scr, p_stride, g_ws, g_stride, h_scr, h_stride, cigar_pool, sc, d_cells ? d_cells + 1 : nullptr, smem);
+			else k_dp_cta<true><<<n_cta, DPC_THREADS, smem, st2>>>(tasks, lists + (int64_t)cls * n, ctr + cls, wc, codes, S, pool,
 				p_scr, p_stride, g_ws, g_stride, h_scr, h_stride, cigar_pool, sc, d_cells ? d_cells + 1 : nullptr, smem);
 			{ cudaError_t le = cudaGetLastError(); if (le != cudaSuccess) throw mb_error(MB_ERR_CUDA, std::string("k_dp_cta launch: ") + cudaGetErrorString(le) + " grid " + std::to_string(n_cta) + " smem " + std::to_string(smem)); }
 			cudaEventRecord(e1, st2);
 			evs.emplace_back(e0, e1); ev_fast.push_back(0); n_exact += cnt;
-			++*nl; side[b & 1] = true;
-		}
+			++*nl;
+			return true;
+		};
+		for (int b = DP_NCTA - 1; b >= 0; --b) // largest class first
+			if (launch_cta(DP_CBASE + b, serial ? st : c.st2[b & 1])) side[b & 1] = true;
 		for (int b = DP_NEXACT - 1; b >= 0; --b) {
 			const int cls = DP_EBASE + b;
-			cudaStream_t st2 = c.st2[b & 1]; // exact classes alternate over side streams 0 and 1
+			cudaStream_t st2 = serial ? st : c.st2[b & 1]; // exact classes alternate over side streams 0 and 1
 			int64_t cnt = h_ctr[cls];
 			if (cnt == 0) continue;
 			if (getenv("MB_DEBUG")) fprintf(stderr, "[mb] exact class %d: %lld tasks, max p_bytes %llu, ws_bytes %llu, h_ints %llu\n", b, (long long)cnt, h_max[cls * 3], h_max[cls * 3 + 1], h_max[cls * 3 + 2]);
@@ -890,7 +976,7 @@ struct DpRunner {
 			const int smem_per_warp = wide ? (int)(slice < DP_SMEM_MAX ? slice : DP_SMEM_MAX) : DP_SMEM_PER_WARP;
 			// one-warp CTAs of the long-task classes: as many per SM as their shared-memory slices allow (up to 8)
 			int wide_per_sm = (200 * 1024) / smem_per_warp; if (wide_per_sm < 1) wide_per_sm = 1; if (wide_per_sm > 8) wide_per_sm = 8;
-			int max_cta = c.num_sms * (wide ? wide_per_sm : 6);
+			int max_cta = mb_side_grid(c.num_sms * (wide ? wide_per_sm : 6));
 			int64_t want_cta = cdiv(cnt, wpc);
 			int n_cta = (int)(want_cta < max_cta ? want_cta : max_cta);
 			// bound total scratch to ~24 GB
@@ -911,59 +997,6 @@ struct DpRunner {
 			evs.emplace_back(e0, e1); ev_fast.push_back(0); n_exact += cnt;
 			++*nl; side[b & 1] = true;
 		}
-		for (int k = DPB_NCLASS - 1; k >= 0; --k) { // large / band-limited gap fills: packed systolic kernel with upstream's band (dp_band.cuh)
-			const int cls = DP_BBASE + k;
-			const int64_t cnt = h_ctr[cls];
-			if (cnt == 0) continue;
-			const int mq = (int)h_max[cls * 3], mt = (int)h_max[cls * 3 + 1];
-			const int n_strips = (mt + DPB_STRIP - 1) / DPB_STRIP;
-			const size_t stride_words = ((size_t)DPB_MAX_STRIPS * DPB_EDGE_WORDS + (size_t)n_strips * (size_t)(mq + 31) * 32 * DPB_CW + 63) & ~(size_t)63;
-			// Band CTAs are register-heavy and latency-bound; the grid is sized by the band kernel's share of the DP work of this run
-			// (cells, weighted x3: edge cells cost more) so that the gap-fill kernels keep the rest of the machine
-			double w_band = 0, w_fast = 0;
-			for (int kk = 0; kk < DPB_NCLASS; ++kk) w_band += 3.0 * (double)h_ctr[DP_BBASE + kk] * (double)h_max[(DP_BBASE + kk) * 3] * (double)h_max[(DP_BBASE + kk) * 3 + 1];
-			for (int kk = 0; kk < DPF_NCLASS; ++kk) w_fast += (double)h_ctr[kk] * (double)h_max[kk * 3] * (double)(DPF_C[kk] * 32);
-			const double share = w_band / (w_band + w_fast + 1.0);
-			int max_cta = (int)(c.num_sms * 3 * std::min(1.0, share * 3.0 + 0.15));
-			if (max_cta < 16) max_cta = 16;
-			const int64_t want = cdiv(cnt, 2);
-			const int n_cta = (int)(want < max_cta ? want : max_cta);
-			uint32_t *p_scr = ar.get<uint32_t>((size_t)n_cta * stride_words);
-			int32_t *wc = ar.get<int32_t>(1);
-			cudaStream_t sb = c.st2[k & 1]; side[k & 1] = true;
-			CK(cudaMemsetAsync(wc, 0, sizeof(int32_t), sb));
-			cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-			cudaEventRecord(e0, sb);
-			k_dp_band<<<n_cta, DPB_NW * 32, 0, sb>>>(tasks, lists + (int64_t)cls * n, ctr + cls, wc, codes, S, pool, p_scr, stride_words, cigar_pool, sc, d_cells ? d_cells + 3 : nullptr);
-			{ cudaError_t le = cudaGetLastError(); if (le != cudaSuccess) throw mb_error(MB_ERR_CUDA, std::string("k_dp_band launch: ") + cudaGetErrorString(le) + " grid " + std::to_string(n_cta)); }
-			cudaEventRecord(e1, sb);
-			evs.emplace_back(e0, e1); ev_fast.push_back(3); n_band += cnt;
-			++*nl;
-		}
-		for (int k = 0; k < DPF_NCLASS; ++k) {
-			const int64_t cnt = h_ctr[DP_XBASE + k];
-			if (cnt == 0) continue;
-			const int32_t *list = lists + (int64_t)(DP_XBASE + k) * n;
-			const int mq = (int)h_max[(DP_XBASE + k) * 3];
-			unsigned long long *xc = d_cells ? d_cells + 2 : nullptr;
-			const int si = 2 + (k & 1); // the extension classes are small launches with tails too: side streams 2 and 3
-			cudaStream_t sx = c.st2[si]; side[si] = true;
-			switch (DPF_C[k]) {
-			case 4:  launch_ext<4>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
-			case 5:  launch_ext<5>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
-			case 6:  launch_ext<6>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
-			case 7:  launch_ext<7>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
-			case 8:  launch_ext<8>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
-			case 9:  launch_ext<9>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
-			case 10: launch_ext<10>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
-			case 11: launch_ext<11>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
-			case 12: launch_ext<12>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
-			case 14: launch_ext<14>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
-			case 16: launch_ext<16>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
-			case 20: launch_ext<20>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
-			default: launch_ext<24>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
-			}
-		}
 		{
 			// largest classes first, rotating over three streams
 			int ord[DPF_NCLASS];
@@ -971,8 +1004,6 @@ struct DpRunner {
 			std::sort(ord, ord + DPF_NCLASS, [&](int a, int b) { return (int64_t)h_ctr[a] * DPF_C[a] > (int64_t)h_ctr[b] * DPF_C[b]; });
 			cudaEvent_t w0, w1; cudaEventCreate(&w0); cudaEventCreate(&w1);
 			cudaEventRecord(w0, st);
-			CK(cudaEventRecord(c.ev_fork, st));
-			CK(cudaStreamWaitEvent(c.stf[0], c.ev_fork, 0)); CK(cudaStreamWaitEvent(c.stf[1], c.ev_fork, 0));
 			int slot = 0;
 			for (int oi = 0; oi < DPF_NCLASS; ++oi) {
 				const int k = ord[oi];
@@ -981,7 +1012,7 @@ struct DpRunner {
 				if (getenv("MB_DEBUG")) fprintf(stderr, "[mb] fast class C=%d: %lld tasks, max qlen %d (launch %zu)\n", DPF_C[k], (long long)cnt, (int)h_max[k * 3], evs.size());
 				const int32_t *list = lists + (int64_t)k * n;
 				const int mq = (int)h_max[k * 3];
-				cudaStream_t sf = slot == 0 ? st : c.stf[slot - 1];
+				cudaStream_t sf = (slot == 0 || serial) ? st : c.stf[slot - 1];
 				slot = (slot + 1) % 3;
 				switch (DPF_C[k]) {
 				case 4:  launch_fast<4>(tasks, list, ctr + k, cnt, mq, codes, S, pool, cigar_pool, sc, d_cells, sf); break;
@@ -1004,6 +1035,16 @@ struct DpRunner {
 			fast_wall.emplace_back(w0, w1);
 		}
 		CK(cudaEventRecord(c.ev_fast_done, st));
+		{ // deferred end extensions: behind the gap-fill kernels, beside whatever the caller does next (Z-drop test, second pass)
+			bool any = false;
+			for (int b = DP_NCTA - 1; b >= 0; --b) {
+				if (h_ctr[DP_DBASE + b] == 0) continue;
+				if (!any && !serial) CK(cudaStreamWaitEvent(c.st_defer, c.ev_fast_done, 0));
+				any = true;
+				launch_cta(DP_DBASE + b, serial ? st : c.st_defer);
+			}
+			if (any && !serial) { CK(cudaEventRecord(c.ev_defer, c.st_defer)); deferred = true; }
+		}
 		for (int b = 0; b < MB_NSIDE; ++b)
 			if (side[b]) { CK(cudaEventRecord(c.ev_join[b], c.st2[b])); CK(cudaStreamWaitEvent(st, c.ev_join[b], 0)); }
 	}
@@ -1197,7 +1238,7 @@ static void map_device_part(mb_index *ix, const mb_opt_t &opt_in, DevPart &part)
 			// One piece at a time in the (issue-bound) DP kernels; the other pieces meanwhile run their latency-bound stages
 			// (sketch, seeding, chaining, region logic before; stitching, mm_update_extra, finalisation after) underneath.
 			std::unique_lock<std::mutex> dp_token(g_dp_mutex[c.device & 15]);
-			runner.run(tasks, nullptr, n_tasks, false, d_codes, ix->d.S, nullptr, cigar_pool, scoring, d_cells + 1);
+			runner.run(tasks, nullptr, n_tasks, false, d_codes, ix->d.S, nullptr, cigar_pool, scoring, d_cells + 1, true);
 			CK(cudaEventSynchronize(c.ev_fast_done)); // the long-tailed side-stream launches of this piece may still be running
 			dp_token.unlock();
 			phase("dp pass 1");
@@ -1228,6 +1269,7 @@ static void map_device_part(mb_index *ix, const mb_opt_t &opt_in, DevPart &part)
 			k_work_scatter<<<(unsigned)cdiv(h_n_work, 256), 256, 0, st>>>(work, h_n_work, ra, hist, perm);
 			nl += 3;
 		}
+		runner.join_deferred();   // the long end extensions of the first pass
 		k_stitch<<<(unsigned)cdiv((int64_t)h_n_work * 32, 128), 128, 0, st>>>(ac, ra, work, h_n_work, plans, tasks, cigar_pool, work2, n_work + 1, d_err, perm, inv_list, n_work + 2); ++nl;
 		phase("stitch");
 		k_update_extra<<<(unsigned)cdiv((int64_t)h_n_work * 32, 128), 128, 0, st>>>(ac, ra, work, h_n_work, plans, tasks, cigar_pool, perm); ++nl;
