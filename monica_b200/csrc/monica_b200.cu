@@ -931,6 +931,7 @@ struct DpRunner {
 			size_t h_stride = ((size_t)h_max[cls * 3 + 2] + 63) & ~(size_t)63;
 			if (p_stride == 0) p_stride = 256;
 			if (h_stride == 0) h_stride = 64;
+			static const bool cta_old = getenv("MB_CTA_OLD") != nullptr;   // debug: one cell at a time in 32-bit registers
 			static const bool nowin = getenv("MB_CTA_NOWIN") != nullptr;   // debug: state arrays of full length (shared memory if they fit, else global)
 			const size_t need = ((g_stride + 15) & ~(size_t)15) + h_stride * 4 + 64;
 			const int smem = nowin ? (int)(need < DPC_SMEM_MAX ? need : DPC_SMEM_MAX) : DPC_WIN_SMEM;
@@ -947,7 +948,9 @@ struct DpRunner {
 			cudaEventRecord(e0, st2);
 			if (nowin) k_dp_cta<false><<<n_cta, DPC_THREADS, smem, st2>>>(tasks, lists + (int64_t)cls * n, ctr + cls, wc, codes, S, pool,
 				p_scr, p_stride, g_ws, g_stride, h_scr, h_stride, cigar_pool, sc, d_cells ? d_cells + 1 : nullptr, smem);
-			else k_dp_cta<true><<<n_cta, DPC_THREADS, smem, st2>>>(tasks, lists + (int64_t)cls * n, ctr + cls, wc, codes, S, pool,
+			else if (cta_old) k_dp_cta<true><<<n_cta, DPC_THREADS, smem, st2>>>(tasks, lists + (int64_t)cls * n, ctr + cls, wc, codes, S, pool,
+				p_scr, p_stride, g_ws, g_stride, h_scr, h_stride, cigar_pool, sc, d_cells ? d_cells + 1 : nullptr, smem);
+			else k_dp_cta2<<<n_cta, DPC_THREADS, smem, st2>>>(tasks, lists + (int64_t)cls * n, ctr + cls, wc, codes, S, pool,
 				p_scr, p_stride, g_ws, g_stride, h_scr, h_stride, cigar_pool, sc, d_cells ? d_cells + 1 : nullptr, smem);
 			{ cudaError_t le = cudaGetLastError(); if (le != cudaSuccess) throw mb_error(MB_ERR_CUDA, std::string("k_dp_cta launch: ") + cudaGetErrorString(le) + " grid " + std::to_string(n_cta) + " smem " + std::to_string(smem)); }
 			cudaEventRecord(e1, st2);
@@ -2308,3 +2311,4 @@ extern "C" int mb_db_build(const char *out_path, int32_t n_genomes, const char *
 	if (gzclose(out) != Z_OK || !ok) throw mb_error(MB_ERR_IO, std::string("write failed: ") + out_path);
 	API_END
 }
+
