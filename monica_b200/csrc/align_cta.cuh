@@ -22,6 +22,7 @@
 // extension then keeps its state in 14 KB of shared memory instead of 125 KB of global memory.  Needs w + 64 < DPC_WIN.
 #define DPC_WIN 1024
 #define DPC_WIN_SMEM (DPC_WIN * 9 + DPC_WIN * 4 + 64)
+#define DPC2_THREADS 224             // k_dp_cta2: 4 cells per thread, 224 x 4 = 896 >= the widest block range (w + 1 + 30 + 16)
 
 template <bool WIN>
 __global__ void __launch_bounds__(DPC_THREADS)
@@ -330,7 +331,7 @@ k_dp_cta(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const in
 }
 
 // k_dp_cta2: the same kernel with the cells of a diagonal computed four per thread in packed 16-bit lanes (see phase B).
-__global__ void __launch_bounds__(DPC_THREADS)
+__global__ void __launch_bounds__(DPC2_THREADS)
 k_dp_cta2(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const int32_t *__restrict__ n_order, int32_t *__restrict__ work_ctr,
          const uint8_t *__restrict__ codes, const uint32_t *__restrict__ S, const uint8_t *__restrict__ pool,
          uint8_t *__restrict__ p_scr, size_t p_stride, int8_t *__restrict__ g_ws, size_t g_stride, int32_t *__restrict__ h_scr, size_t h_stride,
@@ -338,7 +339,7 @@ k_dp_cta2(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 {
 	constexpr bool WIN = true;
 	extern __shared__ __align__(16) int8_t dpc_smem[];
-	__shared__ long long s_red[DPC_THREADS / 32];
+	__shared__ uint32_t s_red[DPC2_THREADS / 32];
 	__shared__ int s_task;
 	const unsigned FULL = 0xffffffffu;
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -392,9 +393,9 @@ k_dp_cta2(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 		};
 		int hi_t = (WIN && T16 > DPC_WIN ? DPC_WIN : T16) - 1;            // entries 0..hi_t are set up
 		int hi_j = WIN ? (qlen > DPC_WIN ? DPC_WIN : qlen) - 1 : 0;
-		for (int t = tid; t <= hi_t; t += DPC_THREADS) fresh_t(t);
-		if (WIN) { for (int j = tid; j <= hi_j; j += DPC_THREADS) qr[(-j) & (DPC_WIN - 1)] = (uint8_t)qv.at(j); }
-		else for (int t = tid; t < qlen_ * 16 + 16; t += DPC_THREADS) qr[t] = t < qlen ? (uint8_t)qv.at(qlen - 1 - t) : 0;
+		for (int t = tid; t <= hi_t; t += DPC2_THREADS) fresh_t(t);
+		if (WIN) { for (int j = tid; j <= hi_j; j += DPC2_THREADS) qr[(-j) & (DPC_WIN - 1)] = (uint8_t)qv.at(j); }
+		else for (int t = tid; t < qlen_ * 16 + 16; t += DPC2_THREADS) qr[t] = t < qlen ? (uint8_t)qv.at(qlen - 1 - t) : 0;
 		__syncthreads();
 		// ez state: every thread keeps the same copy
 		int ez_max = 0, ez_max_t = -1, ez_max_q = -1, ez_mqe = MB_KSW_NEG_INF, ez_mqe_t = -1, ez_mte = MB_KSW_NEG_INF, ez_score = MB_KSW_NEG_INF, ez_zdropped = 0;
@@ -460,7 +461,9 @@ k_dp_cta2(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 			__syncthreads();
 			// ---- phase B: compute (two cells per 32-bit register: int8 value in the high byte of a 16-bit lane, so that 16-bit
 			//      wrap-around IS upstream's int8 wrap-around; candidate priority tags in the low byte) and store ----
-			long long best = ((long long)MB_KSW_NEG_INF << 32);
+			// per-diagonal maximum of H with upstream's order among equal scores: key = (H + 2^20) << 11 | (2047 - rank); |H| stays far
+			// below 2^20 for the task sizes this kernel takes (lengths <= max_gap windows, a few ten thousand at most)
+			uint32_t best = 0u;
 			if (any_on) {
 				// scores of the fresh cells [st0, fill_end); the others keep the stored one
 				uint32_t Wz = Ws;
@@ -527,14 +530,16 @@ k_dp_cta2(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 								if (t >= st0 && t < en0) {
 									const int32_t h = hv[c] + vn;
 									hv[c] = h;
-									const unsigned rank = t < en1 ? 1u + ((unsigned)((t - st0) & 3) << 22) + (unsigned)((t - st0) >> 2) : 1u + (4u << 22) + (unsigned)(t - en1);
-									const long long key = ((long long)h << 32) | (unsigned)(0x7fffffffu - rank);
+									const unsigned rank = t < en1 ? 1u + ((unsigned)((t - st0) & 3) << 8) + (unsigned)((t - st0) >> 2) : 1025u + (unsigned)(t - en1);
+									const int32_t hc = h < -0xfffff ? -0xfffff : (h > 0xfffff ? 0xfffff : h);
+									const uint32_t key = (uint32_t)(hc + 0x100000) << 11 | (2047u - rank);
 									best = key > best ? key : best;
 								} else if (t == en0) {
 									const int32_t un = (int32_t)(int16_t)((c & 1) ? nu[c >> 1] >> 16 : nu[c >> 1] & 0xffffu) >> 8;
 									const int32_t he = en0 > 0 ? hprev + un : hv[c] + vn;
 									hv[c] = he;
-									const long long key = ((long long)he << 32) | (unsigned)0x7fffffffu;
+									const int32_t hc = he < -0xfffff ? -0xfffff : (he > 0xfffff ? 0xfffff : he);
+									const uint32_t key = (uint32_t)(hc + 0x100000) << 11 | 2047u;
 									best = key > best ? key : best;
 								}
 							}
@@ -544,22 +549,21 @@ k_dp_cta2(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 				}
 			}
 			if (with_exact && r > 0) {
-				#pragma unroll
-				for (int dlt = 16; dlt > 0; dlt >>= 1) { const long long o = __shfl_xor_sync(FULL, best, dlt); best = o > best ? o : best; }
+				best = __reduce_max_sync(FULL, best);
 				if (lane == 0) s_red[wid] = best;
 			}
-			if (WIN && r + 1 < n_rows) { // pristine entries for what the next diagonal reaches beyond the entries set up so far
-				const int r1 = r + 1;
+			if ((r & 15) == 15 && r + 1 < n_rows) { // every 16th diagonal: pristine entries for what the next 16 diagonals reach
+				const int r1 = r + 16 < n_rows ? r + 16 : n_rows - 1;
 				int st1 = 0, en1 = tlen - 1;
 				if (st1 < r1 - qlen + 1) st1 = r1 - qlen + 1;
 				if (en1 > r1) en1 = r1;
 				if (st1 < (r1 - w + 1) >> 1) st1 = (r1 - w + 1) >> 1;
 				if (en1 > (r1 + w) >> 1) en1 = (r1 + w) >> 1;
 				int need_t = (en1 + 16) / 16 * 16 + 31; if (need_t > T16 - 1) need_t = T16 - 1;
-				for (int t = hi_t + 1 + tid; t <= need_t; t += DPC_THREADS) fresh_t(t);
+				for (int t = hi_t + 1 + tid; t <= need_t; t += DPC2_THREADS) fresh_t(t);
 				if (need_t > hi_t) hi_t = need_t;
 				int need_j = r1 - st1 + 16; if (need_j > qlen - 1) need_j = qlen - 1;
-				for (int j = hi_j + 1 + tid; j <= need_j; j += DPC_THREADS) qr[(-j) & (DPC_WIN - 1)] = (uint8_t)qv.at(j);
+				for (int j = hi_j + 1 + tid; j <= need_j; j += DPC2_THREADS) qr[(-j) & (DPC_WIN - 1)] = (uint8_t)qv.at(j);
 				if (need_j > hi_j) hi_j = need_j;
 			}
 			__syncthreads();
@@ -567,15 +571,15 @@ k_dp_cta2(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 			if (with_exact) {
 				int32_t max_H, max_t;
 				if (r > 0) {
-					long long bb = s_red[0];
+					uint32_t bb = s_red[0];
 					#pragma unroll
-					for (int k = 1; k < DPC_THREADS / 32; ++k) { const long long o = s_red[k]; bb = o > bb ? o : bb; }
-					max_H = (int32_t)(bb >> 32);
+					for (int k = 1; k < DPC2_THREADS / 32; ++k) { const uint32_t o = s_red[k]; bb = o > bb ? o : bb; }
+					max_H = (int32_t)(bb >> 11) - 0x100000;
 					const int en1 = st0 + (en0 - st0) / 4 * 4;
-					const unsigned rank = 0x7fffffffu - (unsigned)(bb & 0xffffffffu);
+					const unsigned rank = 2047u - (bb & 2047u);
 					if (rank == 0) max_t = en0;
-					else if (rank < 1u + (4u << 22)) { const unsigned rr = rank - 1; max_t = st0 + (int)((rr & ((1u << 22) - 1)) << 2) + (int)(rr >> 22); }
-					else max_t = en1 + (int)(rank - 1u - (4u << 22));
+					else if (rank < 1025u) { const unsigned rr = rank - 1; max_t = st0 + (int)((rr & 255u) << 2) + (int)(rr >> 8); }
+					else max_t = en1 + (int)(rank - 1025u);
 				} else { max_H = (int32_t)v[0] - qe, max_t = 0; }
 				if (en0 == tlen - 1) { const int32_t h = H[ix(en0)]; if (h > ez_mte) ez_mte = h; }
 				if (r - st0 == qlen - 1) { const int32_t h = H[ix(st0)]; if (h > ez_mqe) ez_mqe = h, ez_mqe_t = st0; }

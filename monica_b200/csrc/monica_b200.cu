@@ -714,7 +714,7 @@ __global__ void k_dp_classify(const DpTask *__restrict__ tasks, const int32_t *_
 			const int ec = dp_exact_class(g.p_bytes);
 			int wd = t.w < 0 ? (t.tlen > t.qlen ? t.tlen : t.qlen) : t.w;
 			int dw = t.qlen < t.tlen ? t.qlen : t.tlen; dw = dw < wd + 1 ? dw : wd + 1;      // widest diagonal
-			cls = (ec >= 2 && dw + 64 <= DPC_WIN) ? ((defer_ext && t.kind != 1) ? DP_DBASE : DP_CBASE) + (ec - 2) : DP_EBASE + ec;
+			cls = (ec >= 2 && dw + 80 <= DPC2_THREADS * 4) ? ((defer_ext && t.kind != 1) ? DP_DBASE : DP_CBASE) + (ec - 2) : DP_EBASE + ec;
 			m0 = (unsigned)g.p_bytes, m1 = (unsigned)g.ws_bytes, m2 = (unsigned)g.h_ints;
 		}
 	}
@@ -935,7 +935,7 @@ struct DpRunner {
 			static const bool nowin = getenv("MB_CTA_NOWIN") != nullptr;   // debug: state arrays of full length (shared memory if they fit, else global)
 			const size_t need = ((g_stride + 15) & ~(size_t)15) + h_stride * 4 + 64;
 			const int smem = nowin ? (int)(need < DPC_SMEM_MAX ? need : DPC_SMEM_MAX) : DPC_WIN_SMEM;
-			int per_sm = (200 * 1024) / (smem > 4096 ? smem : 4096); if (per_sm < 1) per_sm = 1; if (per_sm > (nowin ? 4 : 6)) per_sm = nowin ? 4 : 6;   // 6 x 256 threads: leaves thread slots to the kernels of the other streams
+			int per_sm = (200 * 1024) / (smem > 4096 ? smem : 4096); if (per_sm < 1) per_sm = 1; if (per_sm > (nowin ? 4 : 7)) per_sm = nowin ? 4 : 7;   // 7 x 224 threads: leaves thread slots to the kernels of the other streams
 			int n_cta = (int)std::min<int64_t>(cnt, (int64_t)mb_side_grid(c.num_sms * per_sm));
 			const size_t per_cta = p_stride + (nowin ? g_stride + h_stride * 4 : 0);
 			while (n_cta > 1 && (size_t)n_cta * per_cta > ((size_t)24 << 30)) n_cta = (n_cta + 1) / 2;
@@ -950,7 +950,7 @@ struct DpRunner {
 				p_scr, p_stride, g_ws, g_stride, h_scr, h_stride, cigar_pool, sc, d_cells ? d_cells + 1 : nullptr, smem);
 			else if (cta_old) k_dp_cta<true><<<n_cta, DPC_THREADS, smem, st2>>>(tasks, lists + (int64_t)cls * n, ctr + cls, wc, codes, S, pool,
 				p_scr, p_stride, g_ws, g_stride, h_scr, h_stride, cigar_pool, sc, d_cells ? d_cells + 1 : nullptr, smem);
-			else k_dp_cta2<<<n_cta, DPC_THREADS, smem, st2>>>(tasks, lists + (int64_t)cls * n, ctr + cls, wc, codes, S, pool,
+			else k_dp_cta2<<<n_cta, DPC2_THREADS, smem, st2>>>(tasks, lists + (int64_t)cls * n, ctr + cls, wc, codes, S, pool,
 				p_scr, p_stride, g_ws, g_stride, h_scr, h_stride, cigar_pool, sc, d_cells ? d_cells + 1 : nullptr, smem);
 			{ cudaError_t le = cudaGetLastError(); if (le != cudaSuccess) throw mb_error(MB_ERR_CUDA, std::string("k_dp_cta launch: ") + cudaGetErrorString(le) + " grid " + std::to_string(n_cta) + " smem " + std::to_string(smem)); }
 			cudaEventRecord(e1, st2);
