@@ -563,7 +563,7 @@ def main():
     # ---- roofline of the dominant kernel (k_dp_fast: packed two-piece affine DP + traceback) and the other stages ----
     last = stats[-1]
     ms_fast = float(np.mean([s["ms_kdp_fast"] for s in stats]))
-    cells_fast = float(np.mean([s["dp_cells"] - s["dp_cells_exact"] - s["dp_cells_ext"] for s in stats]))
+    cells_fast = float(np.mean([s["dp_cells"] - s["dp_cells_exact"] - s["dp_cells_ext"] - s.get("dp_cells_band", 0) for s in stats]))
     tiops = C.c_double(0)
     _lib.check(L.mb_int_peak(local, C.byref(tiops)))
     peak_gcups = tiops.value * 1e3 * SIMD_WIDTH / OPS_PER_CELL
@@ -612,8 +612,12 @@ def main():
             "K2+K2b seed stage (k_seed_lookup, k_seed_fill, k_sort_anchors, k_sort_emul)": hbm_entry(32 * M + 24 * A + 32 * A, stage_ms["ms_seed"], "SURVEY 8(d): lookup 32 M + 24 A, sort 32 A bytes; random probes: latency-bound"),
             "K3 k_chain_dp": int_entry(chain_evals * OPS_PER_CHAIN_EVAL, stage_ms["ms_chain"], tiops.value * 1e3, "G int-op/s",
                                        f"{chain_evals:.4g} predecessor evaluations (the oracle counts the same loop) x {OPS_PER_CHAIN_EVAL} int ops, vs the measured INT32 rate"),
-            "K4 k_dp (exact ksw_extd2 block emulation, side streams)": int_entry(float(np.mean([s["dp_cells_exact"] for s in stats])), stage_ms["ms_kdp_exact"], peak_gcups_scalar, "GCUPS",
-                                                                              "int32 lanes (no 16x2 packing): peak = INT32 rate / 40 ops; summed launch times (launches overlap k_dp_fast)"),
+            "K4 k_dp_cta2 / k_dp (exact ksw_extd2 block emulation incl. out-of-band lanes, exact maxima, Z-drop: band-limited extensions, second passes)":
+                int_entry(float(np.mean([s["dp_cells_exact"] for s in stats])), stage_ms["ms_kdp_exact"], peak_gcups, "GCUPS",
+                          "one CTA per task, 4 cells per thread in 16x2 lanes; latency-bound (two barriers per anti-diagonal); summed launch times, launches overlap other kernels"),
+            "K4 k_dp_band (large / band-limited gap fills, packed, upstream's band emulated)":
+                int_entry(float(np.mean([s.get("dp_cells_band", 0) for s in stats])), float(np.mean([s.get("ms_kdp_band", 0.0) for s in stats])), peak_gcups, "GCUPS",
+                          "column strips pipelined over 4 warps; summed launch times"),
             "K4 k_dp_ext (end extensions, packed)": int_entry(float(np.mean([s["dp_cells_ext"] for s in stats])), stage_ms["ms_kdp_ext"], peak_gcups, "GCUPS", "summed launch times (launches overlap k_dp_fast)"),
         },
     }
@@ -663,7 +667,7 @@ def main():
             "aligner_e2e": aligner_e2e,
             "stage_ms": stage_ms,
             "work_per_step": dict({k: last[k] for k in ("n_reads", "n_bases", "n_mini", "n_anchor", "n_regs", "n_dp_tasks", "n_dp_pass2", "dp_cells", "n_hits", "n_rounds", "n_fast_tasks",
-                                                         "n_exact_tasks", "n_ext_tasks", "dp_cells_exact", "dp_cells_ext", "chain_cells", "n_inv")},
+                                                         "n_exact_tasks", "n_ext_tasks", "n_band_tasks", "dp_cells_exact", "dp_cells_ext", "dp_cells_band", "chain_cells", "n_inv", "n_pieces") if k in last},
                                   note="rank 0's share", synthetic_read_classes=dict(zip(("plain", "junk_insert", "inversion", "exact_chimera", "junk"), np.bincount(cls_synth, minlength=5).tolist()))),
             "read_classes": {"mapped": int(ncls_full[0]), "unmapped": int(ncls_full[1]), "ambiguous": int(ncls_full[2]), "note": "all ranks (after the all-reduce)"},
         }

@@ -16,6 +16,8 @@
 //   * routed records are written with writev straight from the input pages (a record that is plain four-line FASTQ is
 //     byte-identical in the output apart from the mapped reads' new id), one thread per sink.
 #pragma once
+#include <chrono>
+#include <mutex>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -25,6 +27,36 @@
 #include <zlib.h>
 #include "common.cuh"
 
+// One page-locked read buffer is kept between files (the aligner loads FASTQ after FASTQ: page-locking ~130 MB costs tens of
+// milliseconds per file, and more while the device is busy).
+namespace fqh {
+struct PinCache { std::mutex mu; void *p = nullptr; size_t cap = 0; ~PinCache() { if (p) cudaFreeHost(p); } };
+static PinCache g_pin_cache;
+static void *pin_take(size_t n, size_t *cap)
+{
+	{
+		std::lock_guard<std::mutex> g(g_pin_cache.mu);
+		if (g_pin_cache.p && g_pin_cache.cap >= n) { void *p = g_pin_cache.p; *cap = g_pin_cache.cap; g_pin_cache.p = nullptr; g_pin_cache.cap = 0; return p; }
+	}
+	void *p = nullptr;
+	const size_t want = n + n / 8 + 4096;
+	if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+	*cap = want;
+	return p;
+}
+static void pin_give(void *p, size_t cap)
+{
+	void *drop = nullptr;
+	{
+		std::lock_guard<std::mutex> g(g_pin_cache.mu);
+		if (cap <= ((size_t)2 << 30) && cap > g_pin_cache.cap) { drop = g_pin_cache.p; g_pin_cache.p = p; g_pin_cache.cap = cap; }
+		else drop = p;
+	}
+	if (drop) cudaFreeHost(drop);
+}
+}
+
+
 struct mb_fastq {
 	const char *raw = nullptr; size_t raw_len = 0;   // the (decompressed) file
 	void *map_base = nullptr; size_t map_len = 0;    // mmap backing, if any
@@ -33,12 +65,12 @@ struct mb_fastq {
 	std::vector<int32_t> id_len;                     // up to the first blank / tab
 	std::vector<int64_t> qual, qual_len;             // quality string (single line, or joined copy in `extra`)
 	std::vector<int64_t> rec_end;                    // canonical records: one past the record's final '\n' in raw; else -1
-	uint8_t *cat = nullptr; size_t cat_len = 0; bool cat_pinned = false; // concatenated sequences
+	uint8_t *cat = nullptr; size_t cat_len = 0, cat_cap = 0; bool cat_pinned = false; // concatenated sequences
 	std::vector<int64_t> off;                        // [n+1]
 	std::string extra;                               // joined quality strings of multi-line records
 	std::vector<uint8_t> qual_in_extra;
 	~mb_fastq() {
-		if (cat) { if (cat_pinned) cudaFreeHost(cat); else free(cat); }
+		if (cat) { if (cat_pinned) fqh::pin_give(cat, cat_cap); else free(cat); }
 		if (map_base) munmap(map_base, map_len);
 	}
 };
@@ -100,7 +132,7 @@ static void fastq_alloc_cat(mb_fastq *fq, size_t n)
 	if (n == 0) n = 1;
 	void *p = nullptr;
 	int ndev = 0;
-	if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0 && cudaHostAlloc(&p, n + 32, cudaHostAllocDefault) == cudaSuccess) { fq->cat = (uint8_t*)p; fq->cat_pinned = true; return; }
+	if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0 && (p = fqh::pin_take(n + 32, &fq->cat_cap)) != nullptr) { fq->cat = (uint8_t*)p; fq->cat_pinned = true; return; }
 	cudaGetLastError();
 	fq->cat = (uint8_t*)malloc(n + 32);
 	if (!fq->cat) throw mb_error(MB_ERR_NOMEM, "out of host memory for the read buffer");
@@ -141,7 +173,9 @@ static bool fastq_parse_parallel(mb_fastq *fq)
 		for (const fqh::Rec &r : recs[t]) sl += r.seq_len;
 		base[t + 1] = base[t] + recs[t].size(); sbase[t + 1] = sbase[t] + sl;
 	}
+	const auto t_a0 = std::chrono::steady_clock::now();
 	fastq_alloc_cat(fq, (size_t)sbase[T]);
+	if (getenv("MB_DEBUG")) fprintf(stderr, "[mb] fastq read buffer (%s) %.1f ms\n", fq->cat_pinned ? "page-locked" : "pageable", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a0).count());
 	{
 		std::vector<std::thread> th;
 		for (int t = 0; t < T; ++t) th.emplace_back([&, t]() {
@@ -196,11 +230,14 @@ extern "C" int mb_fastq_load(const char *path, mb_fastq_t **out)
 			close(fd);
 		} else close(fd);
 	}
+	const bool fq_dbg = getenv("MB_DEBUG") != nullptr;
+	const auto fq_t0 = std::chrono::steady_clock::now();
 	if (!fastq_parse_parallel(fq.get())) {
 		fq->head.clear(); fq->head_len.clear(); fq->id_len.clear(); fq->qual.clear(); fq->qual_len.clear(); fq->rec_end.clear(); fq->qual_in_extra.clear(); fq->off.clear();
-		if (fq->cat) { if (fq->cat_pinned) cudaFreeHost(fq->cat); else free(fq->cat); fq->cat = nullptr; fq->cat_len = 0; fq->cat_pinned = false; }
+		if (fq->cat) { if (fq->cat_pinned) fqh::pin_give(fq->cat, fq->cat_cap); else free(fq->cat); fq->cat = nullptr; fq->cat_len = 0; fq->cat_pinned = false; }
 		fastq_parse_sequential(fq.get(), path);
 	}
+	if (fq_dbg) fprintf(stderr, "[mb] fastq parse %.1f ms (%zu bytes)\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - fq_t0).count(), fq->raw_len);
 	*out = fq.release();
 	API_END
 }

@@ -80,7 +80,7 @@ struct ThreadCtx {
 	cudaStream_t stf[2] = {};
 	cudaEvent_t ev_f[2] = {}, ev_fork = nullptr;
 	cudaEvent_t ev_x[4] = {}, ev_fork2 = nullptr;
-	cudaStream_t st_defer = nullptr; cudaEvent_t ev_defer = nullptr;   // long exact END EXTENSIONS of a first pass: run behind the gap-fill kernels, joined before the stitch   // extension / band launches done (before the gap-fill launches start)
+	cudaStream_t st_defer[3] = {}; cudaEvent_t ev_defer[3] = {};   // long exact END EXTENSIONS of a first pass: run behind the gap-fill kernels, joined before the stitch   // extension / band launches done (before the gap-fill launches start)
 	std::vector<cudaEvent_t> feed_events;   // host->device pieces of mb_map_batch (SketchFeed)
 	int64_t piece_bases = 0;                // bases per sequential piece once a batch did not fit the device (0: the default)
 	const void *piece_index = nullptr;      // ... for this index
@@ -114,8 +114,7 @@ struct ThreadCtx {
 			if (ev_fork) cudaEventDestroy(ev_fork);
 			if (ev_fork2) cudaEventDestroy(ev_fork2);
 			for (int i = 0; i < 4; ++i) if (ev_x[i]) cudaEventDestroy(ev_x[i]);
-			if (st_defer) cudaStreamDestroy(st_defer);
-			if (ev_defer) cudaEventDestroy(ev_defer);
+			for (int i = 0; i < 3; ++i) { if (st_defer[i]) cudaStreamDestroy(st_defer[i]); if (ev_defer[i]) cudaEventDestroy(ev_defer[i]); }
 			for (cudaEvent_t e : feed_events) cudaEventDestroy(e);
 		}
 	}
@@ -163,7 +162,7 @@ static ThreadCtx *make_ctx(int device)
 		CK(cudaEventCreateWithFlags(&c->ev_fast_done, cudaEventDisableTiming));
 		CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
 		CK(cudaEventCreateWithFlags(&c->ev_fork2, cudaEventDisableTiming));
-		CK(cudaStreamCreateWithFlags(&c->st_defer, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->ev_defer, cudaEventDisableTiming));
+		for (int i = 0; i < 3; ++i) { CK(cudaStreamCreateWithFlags(&c->st_defer[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->ev_defer[i], cudaEventDisableTiming)); }
 		for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&c->ev_x[i], cudaEventDisableTiming));
 		for (int i = 0; i < 2; ++i) { CK(cudaStreamCreateWithFlags(&c->stf[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->ev_f[i], cudaEventDisableTiming)); }
 		for (int i = 0; i < MB_NSIDE; ++i) {
@@ -812,8 +811,8 @@ struct DpRunner {
 	// run the DP kernels over `n` tasks (ids[] if use_ids else 0..n-1)
 	// defer_ext: the large exact END EXTENSIONS (kind != 1; only the stitch reads their results) are launched on c.st_defer
 	// behind the gap-fill kernels and NOT joined: the caller waits for c.ev_defer (join_deferred) before it reads them.
-	bool deferred = false;
-	void join_deferred() { if (deferred) { CK(cudaStreamWaitEvent(st, c.ev_defer, 0)); deferred = false; } }
+	int deferred = 0;   // bit i: c.st_defer[i] carries a deferred launch
+	void join_deferred() { for (int i = 0; i < 3; ++i) if (deferred >> i & 1) CK(cudaStreamWaitEvent(st, c.ev_defer[i], 0)); deferred = 0; }
 	void run(DpTask *tasks, const int32_t *ids, int64_t n, bool use_ids, const uint8_t *codes, const uint32_t *S, const uint8_t *pool,
 	         uint32_t *cigar_pool, const DpScoring &sc, unsigned long long *d_cells, bool defer_ext = false)
 	{
@@ -859,6 +858,7 @@ struct DpRunner {
 		// complete), largest class first: a handful of long band-limited tasks give each launch a long tail of a few busy
 		// warps, which the fast kernels on `st` fill
 		bool side[MB_NSIDE] = {};
+		bool band_fills = false;   // a band launch with a full grid: worth waiting for (else it is a few long tasks: run beside it)
 		const bool serial = getenv("MB_DEBUG_SERIAL") != nullptr;   // every launch on `st`, one after the other: stand-alone durations
 		for (int k = DPB_NCLASS - 1; k >= 0; --k) { // large / band-limited gap fills: packed systolic kernel with upstream's band (dp_band.cuh)
 			const int cls = DP_BBASE + k;
@@ -873,6 +873,7 @@ struct DpRunner {
 			uint32_t *p_scr = ar.get<uint32_t>((size_t)n_cta * stride_words);
 			int32_t *wc = ar.get<int32_t>(1);
 			cudaStream_t sb = serial ? st : c.st2[2]; side[2] = true;
+			if (want >= max_cta) band_fills = true;
 			CK(cudaMemsetAsync(wc, 0, sizeof(int32_t), sb));
 			cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
 			cudaEventRecord(e0, sb);
@@ -915,7 +916,7 @@ struct DpRunner {
 		if (!serial) { // the gap-fill and exact launches start when the extension and band launches are done
 			CK(cudaEventRecord(c.ev_x[0], c.st2[2])); CK(cudaEventRecord(c.ev_x[1], c.st2[3]));
 			CK(cudaEventRecord(c.ev_x[2], c.stf[0])); CK(cudaEventRecord(c.ev_x[3], c.stf[1]));
-			for (int i = 0; i < 4; ++i) CK(cudaStreamWaitEvent(st, c.ev_x[i], 0));
+			for (int i = band_fills ? 0 : 1; i < 4; ++i) CK(cudaStreamWaitEvent(st, c.ev_x[i], 0));
 			CK(cudaEventRecord(c.ev_fork2, st));
 			CK(cudaStreamWaitEvent(c.stf[0], c.ev_fork2, 0)); CK(cudaStreamWaitEvent(c.stf[1], c.ev_fork2, 0));
 			CK(cudaStreamWaitEvent(c.st2[0], c.ev_fork2, 0)); CK(cudaStreamWaitEvent(c.st2[1], c.ev_fork2, 0));
@@ -1039,14 +1040,16 @@ struct DpRunner {
 		}
 		CK(cudaEventRecord(c.ev_fast_done, st));
 		{ // deferred end extensions: behind the gap-fill kernels, beside whatever the caller does next (Z-drop test, second pass)
-			bool any = false;
+			int k = 0;   // one stream per class: a small batch has a few long tasks per class, and the classes then run side by side
 			for (int b = DP_NCTA - 1; b >= 0; --b) {
 				if (h_ctr[DP_DBASE + b] == 0) continue;
-				if (!any && !serial) CK(cudaStreamWaitEvent(c.st_defer, c.ev_fast_done, 0));
-				any = true;
-				launch_cta(DP_DBASE + b, serial ? st : c.st_defer);
+				const int i = k++ % 3;
+				if (serial) { launch_cta(DP_DBASE + b, st); continue; }
+				if (!(deferred >> i & 1)) CK(cudaStreamWaitEvent(c.st_defer[i], c.ev_fast_done, 0));
+				launch_cta(DP_DBASE + b, c.st_defer[i]);
+				deferred |= 1 << i;
 			}
-			if (any && !serial) { CK(cudaEventRecord(c.ev_defer, c.st_defer)); deferred = true; }
+			for (int i = 0; i < 3; ++i) if (deferred >> i & 1) CK(cudaEventRecord(c.ev_defer[i], c.st_defer[i]));
 		}
 		for (int b = 0; b < MB_NSIDE; ++b)
 			if (side[b]) { CK(cudaEventRecord(c.ev_join[b], c.st2[b])); CK(cudaStreamWaitEvent(st, c.ev_join[b], 0)); }
