@@ -331,7 +331,7 @@ k_dp_cta(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const in
 }
 
 // k_dp_cta2: the same kernel with the cells of a diagonal computed four per thread in packed 16-bit lanes (see phase B).
-__global__ void __launch_bounds__(DPC2_THREADS)
+__global__ void __launch_bounds__(DPC2_THREADS, 5)
 k_dp_cta2(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const int32_t *__restrict__ n_order, int32_t *__restrict__ work_ctr,
          const uint8_t *__restrict__ codes, const uint32_t *__restrict__ S, const uint8_t *__restrict__ pool,
          uint8_t *__restrict__ p_scr, size_t p_stride, int8_t *__restrict__ g_ws, size_t g_stride, int32_t *__restrict__ h_scr, size_t h_stride,

@@ -155,16 +155,19 @@ static ThreadCtx *make_ctx(int device)
 {
 	ThreadCtx *c = new ThreadCtx();
 	c->device = device;
-	CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
 	{
+		// three priority levels: side streams (exact / band / extension kernels of the running pass) > the main and gap-fill
+		// streams > the deferred exact end extensions, whose CTAs must not queue ahead of the Z-drop test's small kernels
 		int lo = 0, hi = 0;
 		CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+		const int mid = (lo - hi >= 2) ? lo - 1 : lo;
+		CK(cudaStreamCreateWithPriority(&c->st, cudaStreamNonBlocking, mid));
 		CK(cudaEventCreateWithFlags(&c->ev_fast_done, cudaEventDisableTiming));
 		CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
 		CK(cudaEventCreateWithFlags(&c->ev_fork2, cudaEventDisableTiming));
-		for (int i = 0; i < 3; ++i) { CK(cudaStreamCreateWithFlags(&c->st_defer[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->ev_defer[i], cudaEventDisableTiming)); }
+		for (int i = 0; i < 3; ++i) { CK(cudaStreamCreateWithPriority(&c->st_defer[i], cudaStreamNonBlocking, lo)); CK(cudaEventCreateWithFlags(&c->ev_defer[i], cudaEventDisableTiming)); }
 		for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&c->ev_x[i], cudaEventDisableTiming));
-		for (int i = 0; i < 2; ++i) { CK(cudaStreamCreateWithFlags(&c->stf[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->ev_f[i], cudaEventDisableTiming)); }
+		for (int i = 0; i < 2; ++i) { CK(cudaStreamCreateWithPriority(&c->stf[i], cudaStreamNonBlocking, mid)); CK(cudaEventCreateWithFlags(&c->ev_f[i], cudaEventDisableTiming)); }
 		for (int i = 0; i < MB_NSIDE; ++i) {
 			CK(cudaStreamCreateWithPriority(&c->st2[i], cudaStreamNonBlocking, getenv("MB_SIDE_PRIO0") ? 0 : hi));
 			CK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
@@ -936,7 +939,12 @@ struct DpRunner {
 			static const bool nowin = getenv("MB_CTA_NOWIN") != nullptr;   // debug: state arrays of full length (shared memory if they fit, else global)
 			const size_t need = ((g_stride + 15) & ~(size_t)15) + h_stride * 4 + 64;
 			const int smem = nowin ? (int)(need < DPC_SMEM_MAX ? need : DPC_SMEM_MAX) : DPC_WIN_SMEM;
-			int per_sm = (200 * 1024) / (smem > 4096 ? smem : 4096); if (per_sm < 1) per_sm = 1; if (per_sm > (nowin ? 4 : 7)) per_sm = nowin ? 4 : 7;   // 7 x 224 threads: leaves thread slots to the kernels of the other streams
+			int per_sm = (200 * 1024) / (smem > 4096 ? smem : 4096); if (per_sm < 1) per_sm = 1; if (per_sm > (nowin ? 4 : 7)) per_sm = nowin ? 4 : 7;
+			if (!nowin && !cta_old) { // persistent CTAs: exactly as many as are resident at once (registers), so that none queues ahead of other streams' kernels
+				static int occ2 = 0;
+				if (occ2 == 0) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_dp_cta2, DPC2_THREADS, DPC_WIN_SMEM)); if (occ2 < 1) occ2 = 1; }
+				if (per_sm > occ2) per_sm = occ2;
+			}
 			int n_cta = (int)std::min<int64_t>(cnt, (int64_t)mb_side_grid(c.num_sms * per_sm));
 			const size_t per_cta = p_stride + (nowin ? g_stride + h_stride * 4 : 0);
 			while (n_cta > 1 && (size_t)n_cta * per_cta > ((size_t)24 << 30)) n_cta = (n_cta + 1) / 2;
@@ -1040,12 +1048,13 @@ struct DpRunner {
 		}
 		CK(cudaEventRecord(c.ev_fast_done, st));
 		{ // deferred end extensions: behind the gap-fill kernels, beside whatever the caller does next (Z-drop test, second pass)
+			static const bool defer_early = getenv("MB_DEFER_EARLY") != nullptr;   // experiment: lowest-priority CTAs fill the gaps of the gap-fill launches
 			int k = 0;   // one stream per class: a small batch has a few long tasks per class, and the classes then run side by side
 			for (int b = DP_NCTA - 1; b >= 0; --b) {
 				if (h_ctr[DP_DBASE + b] == 0) continue;
 				const int i = k++ % 3;
 				if (serial) { launch_cta(DP_DBASE + b, st); continue; }
-				if (!(deferred >> i & 1)) CK(cudaStreamWaitEvent(c.st_defer[i], c.ev_fast_done, 0));
+				if (!(deferred >> i & 1)) CK(cudaStreamWaitEvent(c.st_defer[i], defer_early ? c.ev_fork2 : c.ev_fast_done, 0));
 				launch_cta(DP_DBASE + b, c.st_defer[i]);
 				deferred |= 1 << i;
 			}

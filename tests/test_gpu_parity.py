@@ -941,3 +941,57 @@ def test_long_reads_with_tied_anchors_sort_bit_exact(oracle, lib):
     assert 0 < n_ties[0] <= 64 and 0 < n_ties[1] <= 64, n_ties
     assert n_ties[2] > 64 and n_ties[3] > 64, n_ties
     assert n_ties[4] == 0, n_ties
+
+
+def test_exact_cta_kernel_long_windows(oracle, lib):
+    """The CTA-per-task exact kernel (align_cta.cuh, four cells per thread in packed 16-bit lanes, state in circular 1024-entry
+    shared-memory windows): windows far longer than the window (the buffers wrap several times), end extensions that Z-drop
+    after a junk end and ones that align to the end, second passes (flag 0) with a 300-base insertion, N bases, both tie-break
+    variants, bands 751 and 500, and several tasks per CTA in a row (stale shared memory between tasks)."""
+    from monica_b200 import _lib
+    rng = np.random.default_rng(77)
+    opt = _lib.default_opt()
+    recs = []
+
+    def noisy(t, err):
+        out = []
+        for b in t:
+            r = rng.random()
+            if r < err * 0.4:
+                out.append(int(rng.integers(0, 4)))
+            elif r < err * 0.7:
+                out += [int(b), int(rng.integers(0, 4))]
+            elif r < err:
+                continue
+            else:
+                out.append(int(b))
+        return np.array(out, np.uint8)
+
+    shapes = [(5000, 9998, "junk"), (4200, 8000, "half"), (3000, 3300, "good"), (2600, 2400, "ins"), (1800, 5000, "good"), (5000, 5200, "N")]
+    for rep in range(3):
+        for (ql, tl, kind) in shapes:
+            t = rng.integers(0, 4, tl).astype(np.uint8)
+            if kind == "junk":
+                q = np.concatenate([noisy(t[:300], 0.1), rng.integers(0, 4, ql).astype(np.uint8)])[:ql]
+            elif kind == "half":
+                q = np.concatenate([noisy(t[:ql // 2], 0.12), rng.integers(0, 4, ql).astype(np.uint8)])[:ql]
+            elif kind == "ins":
+                q = np.concatenate([noisy(t[:1000], 0.1), rng.integers(0, 4, 300).astype(np.uint8), noisy(t[1000:], 0.1)])[:ql]
+            else:
+                q = noisy(t, 0.13)[:ql]
+            if len(q) < ql:
+                q = np.concatenate([q, rng.integers(0, 4, ql - len(q)).astype(np.uint8)])
+            if kind == "N":
+                q[rng.integers(0, ql, 12)] = 4
+                t = t.copy(); t[rng.integers(0, tl, 12)] = 4
+            for flag, zdrop, eb in ((0x40, 400, -1), (0x40 | 0x02 | 0x80, 400, 10), (0x00, 200, -1), (0x08, 400, -1)):
+                w = 751 if rep < 2 else 500
+                ez = oracle.ksw_extd2(q, t, w=w, zdrop=zdrop, end_bonus=eb, flag=flag)
+                recs.append(dict(qlen=ql, tlen=tl, w=w, zdrop=zdrop, end_bonus=eb, flag=flag, q=q, t=t, score=ez["score"], max=ez["max"],
+                                 max_q=ez["max_q"], max_t=ez["max_t"], mqe=ez["mqe"], mqe_t=ez["mqe_t"], zdropped=ez["zdropped"],
+                                 reach_end=ez["reach_end"], n_cigar=len(ez["cigar"]), cigar=ez["cigar"]))
+    assert any(r["zdropped"] for r in recs) and any(not r["zdropped"] for r in recs)
+    # many more tasks than resident CTAs would be needed to force several per CTA; repeating the list does it for a class
+    recs = recs * 3
+    tasks, cig = _run_dp(lib, opt, recs)
+    _check_dp(tasks, cig, recs)
