@@ -870,13 +870,14 @@ struct DpRunner {
 			const int mq = (int)h_max[cls * 3], mt = (int)h_max[cls * 3 + 1];
 			const int n_strips = (mt + DPB_STRIP - 1) / DPB_STRIP;
 			const size_t stride_words = ((size_t)DPB_MAX_STRIPS * DPB_EDGE_WORDS + (size_t)n_strips * (size_t)(mq + 31) * 32 * DPB_CW + 63) & ~(size_t)63;
-			int max_cta = c.num_sms * 3;   // full occupancy: the gap-fill launches wait for the band launches
+			static const int band_per_sm = getenv("MB_BAND_PER_SM") ? atoi(getenv("MB_BAND_PER_SM")) : 3;
+			int max_cta = c.num_sms * (band_per_sm >= 1 && band_per_sm <= 3 ? band_per_sm : 3);   // 3 = full occupancy: the gap-fill launches wait for the band launches
 			const int64_t want = cdiv(cnt, 2);
 			const int n_cta = (int)(want < max_cta ? want : max_cta);
 			uint32_t *p_scr = ar.get<uint32_t>((size_t)n_cta * stride_words);
 			int32_t *wc = ar.get<int32_t>(1);
 			cudaStream_t sb = serial ? st : c.st2[2]; side[2] = true;
-			if (want >= max_cta) band_fills = true;
+			if (want >= max_cta && band_per_sm >= 3) band_fills = true;
 			CK(cudaMemsetAsync(wc, 0, sizeof(int32_t), sb));
 			cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
 			cudaEventRecord(e0, sb);
