@@ -79,7 +79,7 @@ struct ThreadCtx {
 	// warps still on their last task pair) overlaps the ramp-up of the next instead of idling the GPU 13 times per pass
 	cudaStream_t stf[2] = {};
 	cudaEvent_t ev_f[2] = {}, ev_fork = nullptr;
-	cudaEvent_t ev_x[4] = {}, ev_fork2 = nullptr;
+	cudaEvent_t ev_x[5] = {}, ev_fork2 = nullptr;
 	cudaStream_t st_defer[3] = {}; cudaEvent_t ev_defer[3] = {};   // long exact END EXTENSIONS of a first pass: run behind the gap-fill kernels, joined before the stitch   // extension / band launches done (before the gap-fill launches start)
 	std::vector<cudaEvent_t> feed_events;   // host->device pieces of mb_map_batch (SketchFeed)
 	int64_t piece_bases = 0;                // bases per sequential piece once a batch did not fit the device (0: the default)
@@ -113,7 +113,7 @@ struct ThreadCtx {
 			for (int i = 0; i < 2; ++i) { if (stf[i]) cudaStreamDestroy(stf[i]); if (ev_f[i]) cudaEventDestroy(ev_f[i]); }
 			if (ev_fork) cudaEventDestroy(ev_fork);
 			if (ev_fork2) cudaEventDestroy(ev_fork2);
-			for (int i = 0; i < 4; ++i) if (ev_x[i]) cudaEventDestroy(ev_x[i]);
+			for (int i = 0; i < 5; ++i) if (ev_x[i]) cudaEventDestroy(ev_x[i]);
 			for (int i = 0; i < 3; ++i) { if (st_defer[i]) cudaStreamDestroy(st_defer[i]); if (ev_defer[i]) cudaEventDestroy(ev_defer[i]); }
 			for (cudaEvent_t e : feed_events) cudaEventDestroy(e);
 		}
@@ -166,7 +166,7 @@ static ThreadCtx *make_ctx(int device)
 		CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
 		CK(cudaEventCreateWithFlags(&c->ev_fork2, cudaEventDisableTiming));
 		for (int i = 0; i < 3; ++i) { CK(cudaStreamCreateWithPriority(&c->st_defer[i], cudaStreamNonBlocking, lo)); CK(cudaEventCreateWithFlags(&c->ev_defer[i], cudaEventDisableTiming)); }
-		for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&c->ev_x[i], cudaEventDisableTiming));
+		for (int i = 0; i < 5; ++i) CK(cudaEventCreateWithFlags(&c->ev_x[i], cudaEventDisableTiming));
 		for (int i = 0; i < 2; ++i) { CK(cudaStreamCreateWithPriority(&c->stf[i], cudaStreamNonBlocking, mid)); CK(cudaEventCreateWithFlags(&c->ev_f[i], cudaEventDisableTiming)); }
 		for (int i = 0; i < MB_NSIDE; ++i) {
 			CK(cudaStreamCreateWithPriority(&c->st2[i], cudaStreamNonBlocking, getenv("MB_SIDE_PRIO0") ? 0 : hi));
@@ -742,6 +742,23 @@ __global__ void k_dp_classify(const DpTask *__restrict__ tasks, const int32_t *_
 	lists[(int64_t)cls * n + base + rank] = id;
 }
 
+// Longest task first for the classes whose launches are a few long tasks per CTA (band, CTA exact): the launch then ends
+// with short tasks instead of a straggler, and neighbouring list entries (the band kernel pairs them in one warp) are alike.
+#define DPL_MAX 4096
+__global__ void __launch_bounds__(1024)
+k_list_longest_first(const DpTask *__restrict__ tasks, const int32_t *__restrict__ list, int n, int32_t *__restrict__ out)
+{
+	__shared__ unsigned long long s_key[DPL_MAX];
+	for (int i = threadIdx.x; i < n; i += 1024) { const DpTask &t = tasks[list[i]]; s_key[i] = (unsigned long long)((unsigned)(t.qlen + t.tlen)) << 32 | (unsigned)(n - 1 - i); }
+	__syncthreads();
+	for (int i = threadIdx.x; i < n; i += 1024) {
+		const unsigned long long k = s_key[i];
+		int rank = 0;
+		for (int j = 0; j < n; ++j) rank += s_key[j] > k;
+		out[rank] = list[i];
+	}
+}
+
 // grids of the side-stream kernels (exact, band, extension) relative to their defaults (MB_SIDE_SCALE; tuning knob)
 static double mb_side_scale() { static double v = -1; if (v < 0) { const char *e = getenv("MB_SIDE_SCALE"); v = e ? atof(e) : 1.0; if (v <= 0) v = 1.0; } return v; }
 static int mb_side_grid(int n) { const int v = (int)(n * mb_side_scale()); return v < 8 ? (n < 8 ? n : 8) : v; }
@@ -860,6 +877,14 @@ struct DpRunner {
 		// the exact kernel goes first, on the high-priority side stream (the host synchronised `st` above, so its inputs are
 		// complete), largest class first: a handful of long band-limited tasks give each launch a long tail of a few busy
 		// warps, which the fast kernels on `st` fill
+		auto longest_first = [&](int cls, cudaStream_t s2) -> const int32_t* { // sorted copy of a class list (small classes only)
+			const int64_t cnt = h_ctr[cls];
+			const int32_t *list = lists + (int64_t)cls * n;
+			if (cnt < 3 || cnt > DPL_MAX) return list;
+			int32_t *out = ar.get<int32_t>(cnt);
+			k_list_longest_first<<<1, 1024, 0, s2>>>(tasks, list, (int)cnt, out); ++*nl;
+			return out;
+		};
 		bool side[MB_NSIDE] = {};
 		bool band_fills = false;   // a band launch with a full grid: worth waiting for (else it is a few long tasks: run beside it)
 		const bool serial = getenv("MB_DEBUG_SERIAL") != nullptr;   // every launch on `st`, one after the other: stand-alone durations
@@ -876,12 +901,13 @@ struct DpRunner {
 			const int n_cta = (int)(want < max_cta ? want : max_cta);
 			uint32_t *p_scr = ar.get<uint32_t>((size_t)n_cta * stride_words);
 			int32_t *wc = ar.get<int32_t>(1);
-			cudaStream_t sb = serial ? st : c.st2[2]; side[2] = true;
+			cudaStream_t sb = serial ? st : (k & 1) ? c.st2[0] : c.st2[2]; side[(k & 1) ? 0 : 2] = true;   // the two classes side by side
+			const int32_t *blist = longest_first(cls, sb);
 			if (want >= max_cta && band_per_sm >= 3) band_fills = true;
 			CK(cudaMemsetAsync(wc, 0, sizeof(int32_t), sb));
 			cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
 			cudaEventRecord(e0, sb);
-			k_dp_band<<<n_cta, DPB_NW * 32, 0, sb>>>(tasks, lists + (int64_t)cls * n, ctr + cls, wc, codes, S, pool, p_scr, stride_words, cigar_pool, sc, d_cells ? d_cells + 3 : nullptr);
+			k_dp_band<<<n_cta, DPB_NW * 32, 0, sb>>>(tasks, blist, ctr + cls, wc, codes, S, pool, p_scr, stride_words, cigar_pool, sc, d_cells ? d_cells + 3 : nullptr);
 			{ cudaError_t le = cudaGetLastError(); if (le != cudaSuccess) throw mb_error(MB_ERR_CUDA, std::string("k_dp_band launch: ") + cudaGetErrorString(le) + " grid " + std::to_string(n_cta)); }
 			cudaEventRecord(e1, sb);
 			evs.emplace_back(e0, e1); ev_fast.push_back(3); n_band += cnt;
@@ -920,7 +946,9 @@ struct DpRunner {
 		if (!serial) { // the gap-fill and exact launches start when the extension and band launches are done
 			CK(cudaEventRecord(c.ev_x[0], c.st2[2])); CK(cudaEventRecord(c.ev_x[1], c.st2[3]));
 			CK(cudaEventRecord(c.ev_x[2], c.stf[0])); CK(cudaEventRecord(c.ev_x[3], c.stf[1]));
+			CK(cudaEventRecord(c.ev_x[4], c.st2[0]));   // the second band class
 			for (int i = band_fills ? 0 : 1; i < 4; ++i) CK(cudaStreamWaitEvent(st, c.ev_x[i], 0));
+			if (band_fills) CK(cudaStreamWaitEvent(st, c.ev_x[4], 0));
 			CK(cudaEventRecord(c.ev_fork2, st));
 			CK(cudaStreamWaitEvent(c.stf[0], c.ev_fork2, 0)); CK(cudaStreamWaitEvent(c.stf[1], c.ev_fork2, 0));
 			CK(cudaStreamWaitEvent(c.st2[0], c.ev_fork2, 0)); CK(cudaStreamWaitEvent(c.st2[1], c.ev_fork2, 0));
@@ -956,11 +984,12 @@ struct DpRunner {
 			CK(cudaMemsetAsync(wc, 0, sizeof(int32_t), st2));
 			cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
 			cudaEventRecord(e0, st2);
-			if (nowin) k_dp_cta<false><<<n_cta, DPC_THREADS, smem, st2>>>(tasks, lists + (int64_t)cls * n, ctr + cls, wc, codes, S, pool,
+			const int32_t *clist = longest_first(cls, st2);
+			if (nowin) k_dp_cta<false><<<n_cta, DPC_THREADS, smem, st2>>>(tasks, clist, ctr + cls, wc, codes, S, pool,
 				p_scr, p_stride, g_ws, g_stride, h_scr, h_stride, cigar_pool, sc, d_cells ? d_cells + 1 : nullptr, smem);
-			else if (cta_old) k_dp_cta<true><<<n_cta, DPC_THREADS, smem, st2>>>(tasks, lists + (int64_t)cls * n, ctr + cls, wc, codes, S, pool,
+			else if (cta_old) k_dp_cta<true><<<n_cta, DPC_THREADS, smem, st2>>>(tasks, clist, ctr + cls, wc, codes, S, pool,
 				p_scr, p_stride, g_ws, g_stride, h_scr, h_stride, cigar_pool, sc, d_cells ? d_cells + 1 : nullptr, smem);
-			else k_dp_cta2<<<n_cta, DPC2_THREADS, smem, st2>>>(tasks, lists + (int64_t)cls * n, ctr + cls, wc, codes, S, pool,
+			else k_dp_cta2<<<n_cta, DPC2_THREADS, smem, st2>>>(tasks, clist, ctr + cls, wc, codes, S, pool,
 				p_scr, p_stride, g_ws, g_stride, h_scr, h_stride, cigar_pool, sc, d_cells ? d_cells + 1 : nullptr, smem);
 			{ cudaError_t le = cudaGetLastError(); if (le != cudaSuccess) throw mb_error(MB_ERR_CUDA, std::string("k_dp_cta launch: ") + cudaGetErrorString(le) + " grid " + std::to_string(n_cta) + " smem " + std::to_string(smem)); }
 			cudaEventRecord(e1, st2);

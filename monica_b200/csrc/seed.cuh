@@ -568,6 +568,8 @@ k_sort_emul_q(mb128 *__restrict__ out, mb128 *__restrict__ wbuf, const int64_t *
 #define SE_SMEM_N 2560             // 2560 * 16 B = 40 KB of anchors per warp
 #define SE_STACK  2304
 #define SE_SMEM_BYTES (SE_SMEM_N * 16 + 512 * 4 + 64)
+#define SE_MID_N 12800             // second launch, one warp per SM with 200 KB: reads up to 12,800 anchors are replayed at shared-memory latency
+#define SE_MID_BYTES (SE_MID_N * 16 + 512 * 4 + 64)
 
 __global__ void __launch_bounds__(32)
 k_sort_emul(const mb128 *__restrict__ in, mb128 *__restrict__ out, const int64_t *__restrict__ a_roff,
@@ -593,7 +595,7 @@ k_sort_emul(const mb128 *__restrict__ in, mb128 *__restrict__ out, const int64_t
 		const int r = tie_list[t];
 		const int64_t base = a_roff[r];
 		const int n = (int)(a_roff[r + 1] - base);
-		if (n <= n_lo || (n_lo == 0 && n > smem_n)) continue; // the other launch's read
+		if (n <= n_lo || n > smem_n) continue; // another launch's read
 		mb128 *a = n <= smem_n ? sa : out + base;
 		for (int i = lane; i < n; i += 32) a[i] = in[base + i];
 		__syncwarp();
@@ -782,9 +784,16 @@ static void run_seed(Arena &ar, cudaStream_t st, const DevIndex &ix, int mid_occ
 	mark("bitonic sort (short)");
 	static bool se_attr = false;
 	if (!se_attr) {
-		CK(cudaFuncSetAttribute(k_sort_emul, cudaFuncAttributeMaxDynamicSharedMemorySize, SE_SMEM_BYTES));
+		CK(cudaFuncSetAttribute(k_sort_emul, cudaFuncAttributeMaxDynamicSharedMemorySize, SE_MID_BYTES));
 		CK(cudaFuncSetAttribute(k_sort_emul_q, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * SQ_TPB * (int)sizeof(int)));
 		se_attr = true;
+	}
+	if (big_total > 0) { // mid-size reads with ties (the long ones of a 50 Mb database): whole replay in 200 KB of shared memory, one warp per SM
+		int *ws_mid = ar.get<int>((size_t)num_sms * 6 * SE_STACK);
+		int32_t *cur_mid = ar.get<int32_t>(1);
+		CK(cudaMemsetAsync(cur_mid, 0, sizeof(int32_t), st));
+		k_sort_emul<<<num_sms, 32, SE_MID_BYTES, st>>>(o.a_unsorted, o.a, o.a_roff, tie_list, ctr, cur_mid, ws_mid, SE_MID_N, SE_SMEM_N); ++*n_launch;
+		mark("replay (mid, shared memory)");
 	}
 	if (big_total > 0) { // long reads with ties: queue of ranges, one lane per range (the long walks start first)
 		EmulQ q;
@@ -794,7 +803,7 @@ static void run_seed(Arena &ar, cudaStream_t st, const DevIndex &ix, int mid_occ
 		int32_t *scr_pool = ar.get<int32_t>(big_total + 1);
 		CK(cudaMemsetAsync(q.ready, 0, (size_t)q.cap * sizeof(int), st));
 		CK(cudaMemsetAsync(q.ctr, 0, 4 * sizeof(int), st));
-		k_sort_emul_q_seed<<<num_sms * 4, SQS_TPB, 0, st>>>(o.a_unsorted, big_tmp, o.a, o.a_roff, big_off, tie_list, ctr, tie_pos, tie_n, q, SE_SMEM_N, scr_pool);
+		k_sort_emul_q_seed<<<num_sms * 4, SQS_TPB, 0, st>>>(o.a_unsorted, big_tmp, o.a, o.a_roff, big_off, tie_list, ctr, tie_pos, tie_n, q, SE_MID_N, scr_pool);
 		k_sort_emul_q<<<num_sms, SQ_TPB, 256 * SQ_TPB * sizeof(int), st>>>(o.a, big_tmp, o.a_roff, big_off, tie_pos, tie_n, q, ends_pool);
 		*n_launch += 2;
 		mark("replay (long, queued)");
