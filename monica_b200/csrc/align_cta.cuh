@@ -340,7 +340,7 @@ k_dp_cta2(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 	constexpr bool WIN = true;
 	extern __shared__ __align__(16) int8_t dpc_smem[];
 	__shared__ uint32_t s_red[DPC2_THREADS / 32];
-	__shared__ int s_task;
+	__shared__ int s_task, s_brk;   // s_brk: warp 0 found the Z-drop break on the previous diagonal
 	const unsigned FULL = 0xffffffffu;
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	uint8_t *P = p_scr + (size_t)blockIdx.x * p_stride;
@@ -354,7 +354,7 @@ k_dp_cta2(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 		if (oi >= n_total) break;
 		DpTask &T = tasks[order[oi]];
 		const int qlen = T.qlen, tlen = T.tlen, flag = T.flag, zdrop = T.zdrop, end_bonus = T.end_bonus;
-		if (tid == 0) dp_reset(T);
+		if (tid == 0) { dp_reset(T); s_brk = 0; }
 		if (T.skip) { if (tid == 0) T.zdropped = 1; continue; }
 		if (qlen <= 0 || tlen <= 0) continue;
 		int8_t q = sc.q, e = sc.e, q2 = sc.q2, e2 = sc.e2;
@@ -459,6 +459,7 @@ k_dp_cta2(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 				}
 			}
 			__syncthreads();
+			if (s_brk) break;   // (set by warp 0 in the bookkeeping of the previous diagonal; nothing of this diagonal has been stored yet)
 			// ---- phase B: compute (two cells per 32-bit register: int8 value in the high byte of a 16-bit lane, so that 16-bit
 			//      wrap-around IS upstream's int8 wrap-around; candidate priority tags in the low byte) and store ----
 			// per-diagonal maximum of H with upstream's order among equal scores: key = (H + 2^20) << 11 | (2047 - rank); |H| stays far
@@ -568,6 +569,9 @@ k_dp_cta2(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 			}
 			__syncthreads();
 			cells += tid == 0 ? (unsigned)(en0 - st0 + 1) : 0u;
+			// the per-diagonal bookkeeping (ez state, Z-drop) is warp 0's alone: it also does the traceback; the other warps go on to
+			// the next diagonal's loads and learn of a break at its first barrier
+			if (wid != 0) { last_st = st, last_en = en; continue; }
 			if (with_exact) {
 				int32_t max_H, max_t;
 				if (r > 0) {
@@ -590,8 +594,8 @@ k_dp_cta2(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 					const int l = tl > ql ? tl - ql : ql - tl;
 					if (zdrop >= 0 && ez_max - max_H > zdrop + l * e2) { ez_zdropped = 1; brk = true; }
 				}
-				if (brk) break;
-				if (r == qlen + tlen - 2 && en0 == tlen - 1) ez_score = H[ix(tlen - 1)];
+				if (brk) { if (lane == 0) s_brk = 1; }
+				else if (r == qlen + tlen - 2 && en0 == tlen - 1) ez_score = H[ix(tlen - 1)];
 			} else {
 				if (r > 0) {
 					if (last_H0_t >= st0 && last_H0_t <= en0 && last_H0_t + 1 >= st0 && last_H0_t + 1 <= en0) {

@@ -903,7 +903,8 @@ struct DpRunner {
 			int32_t *wc = ar.get<int32_t>(1);
 			cudaStream_t sb = serial ? st : (k & 1) ? c.st2[0] : c.st2[2]; side[(k & 1) ? 0 : 2] = true;   // the two classes side by side
 			const int32_t *blist = longest_first(cls, sb);
-			if (want >= max_cta && band_per_sm >= 3) band_fills = true;
+			static const bool band_nowait = getenv("MB_BAND_NOWAIT") != nullptr;
+			if (want >= max_cta && band_per_sm >= 3 && !band_nowait) band_fills = true;
 			CK(cudaMemsetAsync(wc, 0, sizeof(int32_t), sb));
 			cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
 			cudaEventRecord(e0, sb);
