@@ -213,6 +213,10 @@ def _aligner_whole_file(sample, sample_name, index, mode, mapping_quality, overn
                                             os.fsencode(os.path.join(focus_folder, sample)) if focus_species else None))
         t4 = time.perf_counter()
         LAST_BREAKDOWN = {"fastq_load": t1 - t0, "map_and_count": t2 - t1, "tally": t3 - t2, "route_write": t4 - t3}
+        if os.environ.get("MB_DEBUG"):
+            import sys
+            print(f"[mb] aligner {sample}: load {t1 - t0:.3f} map+count {t2 - t1:.3f} tally {t3 - t2:.3f} route {t4 - t3:.3f} s "
+                  f"(started {t0:.3f}, ended {t4:.3f})", file=sys.stderr)
         return dict(tally)
     finally:
         L.mb_fastq_free(fq)

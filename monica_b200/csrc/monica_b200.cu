@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <chrono>
 #include <map>
+#include <atomic>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -119,11 +120,30 @@ struct ThreadCtx {
 		}
 	}
 };
-// One context per (calling thread, device), destroyed when the thread exits: monica's multi_threaded_aligner creates a fresh
-// ThreadPool per call (aligner.py:89), so contexts that outlived their thread would pile up arenas of several GB each.
+// One context per (calling thread, device).  monica's multi_threaded_aligner creates a fresh ThreadPool per call (aligner.py:89):
+// a context that outlived its thread would leak its arena (several GB), and one that died with it would make every file of a run
+// pay for streams, events and a cold arena again.  So a thread that exits hands its contexts to a small process-wide pool and the
+// next new thread takes one from there (warm arena, sized by the batches it has seen); contexts beyond the pool's size are freed.
+struct CtxPool { std::mutex mu; std::vector<ThreadCtx*> idle[16]; };
+static CtxPool *g_ctx_pool = new CtxPool();   // never destroyed: a context must not be freed after the CUDA runtime has shut down
+#define MB_CTX_POOL_MAX 4
 struct ThreadCtxMap {
 	std::map<int, ThreadCtx*> m;
-	~ThreadCtxMap() { for (auto &kv : m) delete kv.second; }
+	~ThreadCtxMap() {
+		for (auto &kv : m) {
+			ThreadCtx *c = kv.second;
+			if (cudaSetDevice(c->device) == cudaSuccess) cudaStreamSynchronize(c->st);
+			cudaGetLastError();
+			c->last_parts.clear(); c->last_index = nullptr; c->last_n_reads = 0;
+			bool kept = false;
+			{
+				std::lock_guard<std::mutex> g(g_ctx_pool->mu);
+				auto &v = g_ctx_pool->idle[c->device & 15];
+				if ((int)v.size() < MB_CTX_POOL_MAX) { v.push_back(c); kept = true; }
+			}
+			if (!kept) delete c;
+		}
+	}
 };
 static thread_local ThreadCtxMap t_ctx_holder;
 #define t_ctx (t_ctx_holder.m)
@@ -137,6 +157,7 @@ static void ensure_device(int device)
 	CK(cudaSetDevice(device));
 }
 
+static std::atomic<long long> g_scratch_per_base_x16{0};   // arena bytes per read base of the last batch (x16), for a cold arena's first reservation
 static std::once_flag g_const_once[16];
 static std::mutex g_dp_mutex[16];   // per device: serialises the DP stage of concurrent pieces / calling threads
 
@@ -146,7 +167,13 @@ static ThreadCtx &get_ctx(int device)
 	ensure_device(device);
 	auto it = t_ctx.find(device);
 	if (it != t_ctx.end()) return *it->second;
-	ThreadCtx *c = make_ctx(device);
+	ThreadCtx *c = nullptr;
+	{
+		std::lock_guard<std::mutex> g(g_ctx_pool->mu);
+		auto &v = g_ctx_pool->idle[device & 15];
+		for (size_t i = 0; i < v.size(); ++i) if (v[i]->device == device) { c = v[i]; v.erase(v.begin() + i); break; }
+	}
+	if (!c) c = make_ctx(device);
 	t_ctx[device] = c;
 	return *c;
 }
@@ -1409,6 +1436,7 @@ static void map_device_part(mb_index *ix, const mb_opt_t &opt_in, DevPart &part)
 	S.ms_kdp_fast = runner.fast_wall_ms(); S.ms_kdp_exact = runner.total_ms(0); S.n_fast_tasks = runner.n_fast; S.n_exact_tasks = runner.n_exact;
 	S.ms_kdp_ext = runner.total_ms(2); S.n_ext_tasks = runner.n_ext;
 	S.arena_bytes = (int64_t)ar.batch_total;
+	if (total > ((int64_t)1 << 20)) g_scratch_per_base_x16.store((long long)(ar.batch_total * 16 / (size_t)total));
 	S.ms_total = tall.stop();
 }
 
@@ -1432,6 +1460,17 @@ static int mb_n_parts(int32_t n_reads, int64_t total)
 // Map a device-resident batch.  The batch is cut (at read boundaries, by cumulative bases) into pieces that run
 // concurrently on their own streams / arenas / host threads; results are concatenated in read order, so the outcome does
 // not depend on the number of pieces.
+// cold or too small arena: one reservation from what the last batch of the process needed per base, instead of doubling slab by slab
+static void cold_reserve(ThreadCtx &c, int64_t total)
+{
+	if (total <= 0) return;
+	const long long per16 = g_scratch_per_base_x16.load();
+	size_t fr = 0, tot = 0;
+	if (per16 <= 0 || cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); return; }
+	const size_t want = (size_t)((double)per16 / 16.0 * (double)total * 1.15) + ((size_t)256 << 20);
+	if (want > c.ar.cap && want + ((size_t)4 << 30) < fr + c.ar.cap) c.ar.reserve(want);   // (also a warm arena that is too small: one slab, not a doubling sequence)
+}
+
 static mb_hits *map_device(mb_index *ix, const mb_opt_t &opt, ThreadCtx &c, const uint8_t *d_codes, const int64_t *d_off, const int64_t *h_off,
                            int32_t n_reads, int64_t total, int want_hits /* bit 0: hit fields, bit 1: CIGARs */, mb_stats_t *stats, const SketchFeed *feed = nullptr)
 {
@@ -1658,6 +1697,7 @@ static mb_hits *map_in_pieces(mb_index *ix, const mb_opt_t &opt, ThreadCtx &c, c
 		std::vector<int64_t> po(n + 1);
 		for (int32_t i = 0; i <= n; ++i) po[i] = h_off[lo + i] - h_off[lo];
 		c.ar.reset();
+		cold_reserve(c, po[n]);
 		uint8_t *d_codes; int64_t *d_off; int64_t total = po[n];
 		SketchFeed feed; bool use_feed = false;
 		if (h_cat) {
@@ -1767,6 +1807,7 @@ static int map_batch_impl(mb_index_t *ix, const mb_opt_t *opt, const uint8_t *ca
 		return MB_OK;
 	}
 	c.ar.reset();
+	cold_reserve(c, n_reads > 0 ? off[n_reads] : 0);
 	uint8_t *d_codes; int64_t *d_off; int64_t total;
 	Timer tm(c.st); tm.start();
 	SketchFeed feed;
@@ -1823,6 +1864,7 @@ extern "C" int mb_map_resident(mb_index_t *ix, const mb_opt_t *opt, mb_reads_t *
 			return MB_OK;
 		}
 		c.ar.reset();
+		cold_reserve(c, reads->total);
 		*out = map_device(ix, *opt, c, reads->d_codes, reads->d_off, h_off.data(), reads->n_reads, reads->total, want_hits ? 3 : 0, stats);
 		return MB_OK;
 	} catch (const mb_error &e) { if (!shrink_piece(c, ix, e, reads->total, reads->n_reads)) throw; }
