@@ -216,6 +216,12 @@ void *mb_stream(mb_index_t *idx);
 /* sustained INT32 add/max issue rate of the device (roofline denominator for K3/K4) ---- */
 int  mb_int_peak(int device, double *tera_int_ops_per_s);   /* reference no counterpart: roofline denominator for K3/K4 */
 
+/* mm_set_mapq's logf (the float that minimap2's `(int)(... * logf(...))` truncates) against the caller's libm, bit for bit:
+ * x runs over the n consecutive float bit patterns from first_bits, expected[i] = logf(x_i) of the host libm the CPU path
+ * links.  device >= 0: evaluated by the GPU routine of the MAPQ kernel; device < 0: by its host twin.  n_bad = values whose
+ * bits differ, first_bad = the smallest differing input pattern (0xffffffff if none).  No reference counterpart (test hook). */
+int  mb_logf_sweep(int device, uint32_t first_bits, int64_t n, const float *expected, int64_t *n_bad, uint32_t *first_bad);
+
 #ifdef __cplusplus
 }
 #endif

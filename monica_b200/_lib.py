@@ -74,7 +74,7 @@ SYMBOLS = [
     "mb_hits_n", "mb_hits_field", "mb_hits_cigar_off", "mb_hits_cigar_pool", "mb_hits_rep_len", "mb_hits_free",
     "mb_count", "mb_count_last", "mb_count_device_ptr", "mb_count_fetch", "mb_normalize_last",
     "mb_comm_unique_id", "mb_comm_init", "mb_comm_free", "mb_allreduce_counts",
-    "mb_sketch", "mb_seed", "mb_chain", "mb_dp_batch", "mb_ll_batch", "mb_int_peak", "mb_stream",
+    "mb_sketch", "mb_seed", "mb_chain", "mb_dp_batch", "mb_ll_batch", "mb_int_peak", "mb_stream", "mb_logf_sweep",
     "mb_fastq_load", "mb_fastq_n", "mb_fastq_seqs", "mb_fastq_header", "mb_fastq_ids_unique", "mb_fastq_route", "mb_fastq_route_targets", "mb_fastq_free",
     "mb_db_build",
 ]
@@ -133,6 +133,7 @@ def lib():
     L.mb_count.argtypes = [vp, vp, i32, C.c_int, vp, vp, vp, vp]
     L.mb_count_last.argtypes = [vp, i32, C.c_int, vp, vp]
     L.mb_int_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    L.mb_logf_sweep.argtypes = [C.c_int, C.c_uint32, i64, vp, C.POINTER(i64), C.POINTER(C.c_uint32)]
     L.mb_count_device_ptr.argtypes = [vp]
     L.mb_count_device_ptr.restype = vp
     L.mb_stream.argtypes = [vp]

@@ -363,8 +363,9 @@ MB_HD bool mb_split_reg(Reg *r, Reg *r2, int n, int qlen, const mb128 *a)
 // logf with glibc's exact algorithm (sysdeps/ieee754/flt-32/e_logf.c + logf_data.c, i.e. ARM optimized-routines logf:
 // 16-entry table, degree-3 polynomial evaluated in double, rounded once to float).  mm_set_mapq truncates a float product
 // containing logf(), so MAPQ parity needs the same float as the host libm the CPU path links; glibc's logf is NOT
-// correctly rounded, so (float)log((double)x) would differ on a few percent of inputs.  tests/hostcheck verifies this
-// routine against the system logf (exhaustively checked over all 2^31 positive normal floats during development).
+// correctly rounded, so (float)log((double)x) would differ on a few percent of inputs.  mb_logf_sweep (monica_b200.cu) compares
+// this routine with the system logf bit for bit: tests/test_gpu_parity.py sweeps every positive normal float on the device,
+// tests/test_boundary_cpu.py the host twin over [1, 2^24) and a stride through the rest.
 MB_HD float mb_logf(float x)
 {
 	const double T[16][2] = {

@@ -1971,6 +1971,57 @@ extern "C" int mb_int_peak(int device, double *tops)
 	API_END
 }
 
+// mm_set_mapq's logf (glue.cuh: mb_logf) against the caller's libm values, bit for bit, over a run of consecutive float bit
+// patterns: device >= 0 evaluates on that GPU (the code path k_finish runs), device < 0 on the host.
+__global__ void k_logf_sweep(uint32_t first_bits, int64_t n, const uint32_t *__restrict__ want, unsigned long long *__restrict__ n_bad, uint32_t *__restrict__ first_bad)
+{
+	unsigned long long bad = 0;
+	uint32_t fb = 0xffffffffu;
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+		const uint32_t b = first_bits + (uint32_t)i;
+		if (__float_as_uint(mb_logf(__uint_as_float(b))) != want[i]) { ++bad; if (b < fb) fb = b; }
+	}
+	if (bad) { atomicAdd(n_bad, bad); atomicMin(first_bad, fb); }
+}
+
+extern "C" int mb_logf_sweep(int device, uint32_t first_bits, int64_t n, const float *expected, int64_t *n_bad, uint32_t *first_bad)
+{
+	API_BEGIN
+	if (n < 0 || (n && !expected) || (uint64_t)first_bits + (uint64_t)n > 0x100000000ull) throw mb_error(MB_ERR_ARG, "bad arguments");
+	const uint32_t *want = reinterpret_cast<const uint32_t*>(expected);
+	unsigned long long bad = 0;
+	uint32_t fb = 0xffffffffu;
+	if (device < 0) {
+		for (int64_t i = 0; i < n; ++i) {
+			const uint32_t b = first_bits + (uint32_t)i;
+			float x, y; uint32_t yb;
+			memcpy(&x, &b, 4); y = mb_logf(x); memcpy(&yb, &y, 4);
+			if (yb != want[i]) { ++bad; if (b < fb) fb = b; }
+		}
+	} else if (n) {
+		ThreadCtx &c = get_ctx(device);
+		uint32_t *d_want = nullptr; unsigned long long *d_bad = nullptr;
+		CK(cudaMalloc(&d_want, (size_t)n * 4));
+		if (cudaMalloc(&d_bad, 16) != cudaSuccess) { cudaFree(d_want); throw mb_error(MB_ERR_NOMEM, "out of device memory"); }
+		const unsigned long long init[2] = { 0ull, 0xffffffffull };
+		cudaError_t e = cudaMemcpyAsync(d_bad, init, 16, cudaMemcpyHostToDevice, c.st);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(d_want, want, (size_t)n * 4, cudaMemcpyHostToDevice, c.st);
+		if (e == cudaSuccess) {
+			k_logf_sweep<<<c.num_sms * 8, 256, 0, c.st>>>(first_bits, n, d_want, d_bad, reinterpret_cast<uint32_t*>(d_bad + 1));
+			e = cudaGetLastError();
+		}
+		unsigned long long out[2] = { 0, 0 };
+		if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_bad, 16, cudaMemcpyDeviceToHost, c.st);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(c.st);
+		cudaFree(d_want); cudaFree(d_bad);
+		CK(e);
+		bad = out[0], fb = (uint32_t)out[1];
+	}
+	if (n_bad) *n_bad = (int64_t)bad;
+	if (first_bad) *first_bad = fb;
+	API_END
+}
+
 extern "C" void *mb_stream(mb_index_t *ix)
 {
 	if (!ix) return nullptr;

@@ -181,6 +181,9 @@ void mm2o_radix_sort_64(uint64_t *beg, uint64_t *end);
 mm128_t *mm2o_chain_dp(int max_dist_x, int max_dist_y, int bw, int max_skip, int max_iter, int min_cnt, int min_sc,
 					   int64_t n, mm128_t *a, int *n_u_, uint64_t **_u, mm2o_trace_t *trace, int64_t *cells);
 
+/* the host libm's logf -- the function mm_set_mapq (hit.c) calls -- over n consecutive float bit patterns from first_bits */
+void mm2o_logf_range(uint32_t first_bits, int64_t n, float *out);
+
 #ifdef __cplusplus
 }
 #endif

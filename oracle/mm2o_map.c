@@ -1308,3 +1308,16 @@ int64_t mm2o_batch_export(mm2o_result_t **results, int n, int32_t *fields, int64
 	if (n_cigar_words) *n_cigar_words = nc;
 	return nh;
 }
+
+/* libm's logf over a run of float bit patterns: what mm_set_mapq's `logf(...)` (hit.c, minimap2-2.17) evaluates to on this
+ * host.  Used to sweep the device's logf against it (tests/test_gpu_parity.py). */
+void mm2o_logf_range(uint32_t first_bits, int64_t n, float *out)
+{
+	int64_t i;
+	for (i = 0; i < n; ++i) {
+		uint32_t b = first_bits + (uint32_t)i;
+		float x;
+		memcpy(&x, &b, 4);
+		out[i] = logf(x);
+	}
+}

@@ -125,6 +125,8 @@ def lib():
         L.mm2o_gen_simple_mat.argtypes = [C.c_int, C.c_void_p, C.c_int8, C.c_int8, C.c_int8]
         L.mm2o_ksw_ll_i16.restype = C.c_int
         L.mm2o_ksw_ll_i16.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.mm2o_logf_range.restype = None
+        L.mm2o_logf_range.argtypes = [C.c_uint32, C.c_int64, C.c_void_p]
         L.mm2o_ksw_cells.restype = C.c_int64
         L.mm2o_ksw_cells.argtypes = [C.c_int, C.c_int, C.c_int]
         L.mm2o_radix_sort_128x.argtypes = [C.c_void_p, C.c_void_p]
@@ -368,3 +370,10 @@ class Index:
                 tot[k] += getattr(r, k)
             L.mm2o_result_destroy(arr[i])
         return tot
+
+
+def logf_range(first_bits: int, n: int) -> np.ndarray:
+    """libm logf (the function mm_set_mapq calls) of the n consecutive float32 bit patterns from first_bits."""
+    out = np.empty(n, np.float32)
+    lib().mm2o_logf_range(first_bits, n, out.ctypes.data)
+    return out

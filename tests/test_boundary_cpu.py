@@ -269,3 +269,31 @@ def test_native_fastq_ingest_and_routing_equal_python(tmp_path):
     assert L.mb_fastq_n(fq) == 3 and L.mb_fastq_ids_unique(fq) == 0
     L.mb_fastq_free(fq)
     assert L.mb_fastq_load(os.fsencode(str(tmp_path / "missing.fastq")), C.byref(fq)) != 0
+
+
+def test_host_logf_twin_equals_libm(oracle):
+    """The MAPQ formula's logf (glue.cuh: mb_logf, host twin of the device routine; mm_set_mapq, hit.c) against the libm the
+    oracle links, bit for bit: every float in [1, 2^24) -- all integer-valued arguments (scores, n_sub + 1) and the
+    dp_max / match_sc ratios -- and a stride through all positive normals.  The GPU suite sweeps all 2^31 - 2^24 on the device."""
+    import ctypes as C
+    from monica_b200 import _lib
+    L = _lib.lib()
+
+    def sweep(first, n):
+        exp = oracle.logf_range(first, n)
+        nb, f = C.c_int64(0), C.c_uint32(0)
+        _lib.check(L.mb_logf_sweep(-1, first, n, exp.ctypes.data, C.byref(nb), C.byref(f)))
+        assert nb.value == 0, f"{nb.value} floats differ from libm in [{first:#x}, +{n}), the first at bits {f.value:#010x}"
+        return exp
+
+    for e in range(24):                              # the binades [2^e, 2^(e+1)), e = 0 .. 23
+        exp = sweep(0x3f800000 + (e << 23), 1 << 23)
+    assert exp[0] == np.float32(np.log(np.float64(2.0 ** 23)))
+    for first in range(0x00800000, 0x7f800000, 1 << 26):
+        sweep(first, 1 << 16)
+    # a wrong expectation is reported, with its position
+    exp = oracle.logf_range(0x40000000, 1024)
+    exp[5] = np.nextafter(exp[5], np.float32(10))
+    nb, f = C.c_int64(0), C.c_uint32(0)
+    _lib.check(L.mb_logf_sweep(-1, 0x40000000, 1024, exp.ctypes.data, C.byref(nb), C.byref(f)))
+    assert (nb.value, f.value) == (1, 0x40000005)

@@ -995,3 +995,34 @@ def test_exact_cta_kernel_long_windows(oracle, lib):
     recs = recs * 3
     tasks, cig = _run_dp(lib, opt, recs)
     _check_dp(tasks, cig, recs)
+
+
+def test_device_logf_equals_libm_on_every_positive_normal_float(oracle, lib):
+    """mm_set_mapq (hit.c, minimap2-2.17) truncates a float product that contains logf(), so one differing ulp can move a MAPQ
+    across monica's `hit.mapq >= mapping_quality` filter (aligner.py:194,216).  The device routine (glue.cuh: mb_logf) must
+    return the host libm's float for EVERY input: all 2^31 - 2^24 positive normal bit patterns are swept, 2^24 at a time, the
+    expected values from the libm the oracle links (oracle.logf_range), the comparison on the device."""
+    from concurrent.futures import ThreadPoolExecutor
+    from monica_b200 import _lib
+    CH = 1 << 24
+    firsts = list(range(0x00800000, 0x7f800000, CH))
+    assert len(firsts) == 127
+
+    def want(fb):
+        return fb, oracle.logf_range(fb, CH)
+
+    total_bad, first_bad = 0, None
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:   # ctypes releases the GIL inside libm's loop
+        for fb, exp in pool.map(want, firsts):
+            nb, f = C.c_int64(0), C.c_uint32(0)
+            _lib.check(lib.mb_logf_sweep(0, fb, CH, exp.ctypes.data, C.byref(nb), C.byref(f)))
+            if nb.value and first_bad is None:
+                first_bad = f.value
+            total_bad += nb.value
+    assert total_bad == 0, f"{total_bad} floats differ from libm logf, the first at bits {first_bad:#010x}"
+    # the sweep itself can fail: a wrong expectation is reported, with its position
+    exp = oracle.logf_range(0x40000000, 1024)
+    exp[77] = np.nextafter(exp[77], np.float32(10))
+    nb, f = C.c_int64(0), C.c_uint32(0)
+    _lib.check(lib.mb_logf_sweep(0, 0x40000000, 1024, exp.ctypes.data, C.byref(nb), C.byref(f)))
+    assert (nb.value, f.value) == (1, 0x40000000 + 77)
