@@ -13,8 +13,10 @@ hard cases (1.5 % junk insertions, 0.5 % inversions, 2.5 % exact chimeras, 1 % j
 passes, Z-drop splits and inversion hits all occur in the timed batch (counts reported in `work_per_step`).
 
   value         whole-job mapped Gbases/s with the reads already resident in HBM (Aligner.map_resident + count_last)
-  e2e           the same through the C-ABI call a user makes with HOST buffers (mb_map_batch from pinned memory, all hit
-                arrays + CIGARs copied back), reads sharded with monica_b200.shard, counts combined by mb_allreduce_counts
+  e2e           the same through the C-ABI call a user makes with HOST buffers: mb_map_packed from page-locked memory (the
+                batch as 2-bit words + runs of ambiguous bases, packed once by mb_reads_pack like the FASTQ parse: 0.25 B/base
+                over PCIe; `e2e.ascii_input` is mb_map_batch on the ASCII, 1 B/base), all hit arrays + CIGARs copied back,
+                reads sharded with monica_b200.shard, counts combined by mb_allreduce_counts
   roofline      the dominant kernel (k_dp_fast, integer pipe) from its own CUDA-event time vs the measured INT32 rate, and the
                 other stages against their SURVEY 8(d) algorithmic bytes / operations
   cpu_baseline  the CPU oracle (a restatement of minimap2-2.17, NOT mappy) on the host cores over the SAME batch (N = 1), which
@@ -418,9 +420,26 @@ def main():
         counts, ncls = al.count_last(60, "query_length", comm=comm)     # device-resident count + the one NCCL all-reduce
         return st, counts, ncls
 
-    def step_e2e():
+    # the batch as the loader hands it over: packed once on the host (2-bit words + runs of ambiguous bases, page-locked;
+    # mb_reads_pack / mb_fastq_pack), outside the timed region like the FASTQ parse; its cost is reported as host_pack_ms
+    try:
+        pack_threads = len(os.sched_getaffinity(0))
+    except Exception:
+        pack_threads = os.cpu_count() or 1
+    pack_threads = max(1, min(32, pack_threads))
+    packed, host_pack_ms = None, None
+    for _ in range(2):                                  # the second call reuses the page-locked buffer of the first
+        packed = None
+        t0 = time.perf_counter()
+        packed = Aligner.pack_reads(cat, off, n_threads=pack_threads)
+        host_pack_ms = (time.perf_counter() - t0) * 1e3
+
+    def step_e2e(ascii_input=False):
         h = C.c_void_p(); st = _lib.Stats()
-        _lib.check(L.mb_map_batch(al.handle(), C.byref(opt), _lib._ptr(cat), _lib._ptr(off), n_reads, C.byref(h), C.byref(st)))
+        if ascii_input:
+            _lib.check(L.mb_map_batch(al.handle(), C.byref(opt), _lib._ptr(cat), _lib._ptr(off), n_reads, C.byref(h), C.byref(st)))
+        else:
+            _lib.check(L.mb_map_packed(al.handle(), C.byref(opt), packed.handle, 3, C.byref(h), C.byref(st)))
         nh = L.mb_hits_n(h)
         nc = C.c_int64(0); L.mb_hits_cigar_pool(h, C.byref(nc))
         d2h = nh * 4 * len(_lib.HIT_FIELDS) + nh * 8 + nc.value * 4 + n_reads * 4 + (n_reads + 1) * 8 + n_seq * 8 + 24
@@ -486,9 +505,18 @@ def main():
     dt_e2e = max(dt_e2e, wall_e2e)                     # host copies of the result happen after the last event: take the wall clock
     tot_counts_e, d2h = outs_e[-1][1], outs_e[-1][3]
     if not np.array_equal(np.asarray(tot_counts_e), np.asarray(tot_counts)):
-        raise RuntimeError("per-target counts of the end-to-end path (mb_map_batch, piecewise upload) differ from the resident path")
+        raise RuntimeError("per-target counts of the end-to-end path (mb_map_packed, piecewise upload) differ from the resident path")
     e2e_value = float(tot_counts_e.sum()) * a.steps / dt_e2e / 1e9
     e2e_stats = outs_e[-1][0]
+    # the same with the ASCII reads as input (mb_map_batch: 1 B/base uploaded in pieces underneath the sketch kernels)
+    step_e2e(True)
+    dt_asc, wall_asc, outs_a = timed(lambda: step_e2e(True), a.steps)
+    dt_asc = max(dt_asc, wall_asc)
+    if not np.array_equal(np.asarray(outs_a[-1][1]), np.asarray(tot_counts)):
+        raise RuntimeError("per-target counts of the ASCII end-to-end path differ from the resident path")
+    e2e_ascii = {"value": float(outs_a[-1][1].sum()) * a.steps / dt_asc / 1e9, "unit": "Gbases/s", "ms_per_step": dt_asc / a.steps * 1e3,
+                 "h2d_bytes_per_step": int(total_bases + 8 * (n_reads + 1)), "ms_h2d_exposed": outs_a[-1][0]["ms_h2d"],
+                 "note": "mb_map_batch: concatenated ASCII from page-locked memory"}
 
     # ---- streaming mode (BASELINE configs[3]): 4,000-read batches from host memory, mapped and counted one at a time ----
     streaming = None
@@ -684,8 +712,11 @@ def main():
                        "parallelism": f"reads sharded over {world} GPU(s) (monica_b200.shard), index replicated, 1 NCCL all-reduce of int64[{n_seq + 3}] per step (mb_allreduce_counts)"},
             "total_gbases_per_s": total_bases_all * a.steps / dt_value / 1e9,
             "mapped_fraction": mapped_bases_all / total_bases_all if total_bases_all else None,
-            "e2e": {"value": e2e_value, "unit": "Gbases/s", "h2d_bytes_per_step": int(total_bases + 8 * (n_reads + 1)), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": dt_e2e / a.steps * 1e3, "ms_h2d_exposed": e2e_stats["ms_h2d"], "ms_d2h": e2e_stats["ms_d2h"]},
+            "e2e": {"value": e2e_value, "unit": "Gbases/s", "h2d_bytes_per_step": int(packed.upload_bytes), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": dt_e2e / a.steps * 1e3, "ms_h2d_exposed": e2e_stats["ms_h2d"], "ms_d2h": e2e_stats["ms_d2h"],
+                    "input": "mb_map_packed: the batch as 2-bit words + runs of ambiguous bases in page-locked host memory (0.25 B/base), packed once "
+                             "by mb_reads_pack outside the timed region like the FASTQ parse (host_pack_ms, this rank's cores); all hit arrays + CIGARs copied back",
+                    "host_pack_ms": host_pack_ms, "host_pack_threads": pack_threads, "ascii_input": e2e_ascii},
             "gpu_launches": int(sum(s["n_launches"] for s in stats)) + a.steps,
             "clocks": clocks,
             "roofline": roofline,

@@ -12,7 +12,7 @@
  *        monica/genomes/aligner.py:45-46 (indexer, :31-53)
  *   mb_index_load
  *        mappy.Aligner(fn_idx_in=<mmi>)            monica/genomes/aligner.py:59 (index_loader, :56-62)
- *   mb_map_batch (+ mb_hits_*)
+ *   mb_map_batch / mb_map_packed (+ mb_hits_*)
  *        for hit in index.map(str(seq_record.seq)) monica/genomes/aligner.py:193,215
  *        fields hit.is_primary .mapq .ctg .NM .mlen monica/genomes/aligner.py:194-195,216-217
  *   mb_count
@@ -111,6 +111,21 @@ int  mb_reads_upload(mb_index_t *idx, const uint8_t *cat, const int64_t *off, in
 void mb_reads_free(mb_reads_t *r);
 int  mb_map_resident(mb_index_t *idx, const mb_opt_t *opt, mb_reads_t *reads, int want_hits, mb_hits_t **out, mb_stats_t *stats);
 
+/* packed reads: the batch reduced ONCE on the host (n_threads threads; <= 0: all cores) to 2-bit words -- base i of the
+ * concatenation in bits [2(i&15), 2(i&15)+2) of word i>>4, nt4 codes A/a 0, C/c 1, G/g 2, T/t/U/u 3 -- plus the (start, length)
+ * runs of every other character, in page-locked memory when a device is present.  mb_map_packed == mb_map_batch_ex on such
+ * a batch: it uploads 0.25 B/base instead of 1 and expands the words on the device to the byte codes the kernels read, so
+ * results are identical.  mappy takes a Python str per read (aligner.py:193,215); nothing after the nt4 table sees the
+ * characters.  mb_reads_pack / mb_fastq_pack need no device. */
+typedef struct mb_packed mb_packed_t;
+typedef struct mb_fastq mb_fastq_t;
+int  mb_reads_pack(const uint8_t *cat, const int64_t *off, int32_t n_reads, int n_threads, mb_packed_t **out);
+int  mb_fastq_pack(const mb_fastq_t *fq, int n_threads, mb_packed_t **out);
+void mb_packed_free(mb_packed_t *p);
+int64_t mb_packed_upload_bytes(const mb_packed_t *p);   /* bytes one mb_map_packed moves host -> device */
+const uint32_t *mb_packed_words(const mb_packed_t *p, int64_t *n_words, const int64_t **intervals, int64_t *n_intervals);
+int  mb_map_packed(mb_index_t *idx, const mb_opt_t *opt, const mb_packed_t *reads, int want, mb_hits_t **out, mb_stats_t *stats);
+
 /* hits: struct-of-arrays, n = mb_hits_n(); arrays stay valid until mb_hits_free */
 int64_t mb_hits_n(const mb_hits_t *h);
 const int32_t *mb_hits_field(const mb_hits_t *h, const char *name);
@@ -157,7 +172,6 @@ int  mb_allreduce_counts(mb_index_t *idx, mb_comm_t *comm, int64_t *counts, int6
  * mb_fastq_load      for seq_record in SeqIO.parse(sample, 'fastq')            monica/genomes/aligner.py:191,212
  * mb_fastq_route     SeqIO.write(seq_record, <mapped|unmapped|ambiguous|focus>) monica/genomes/aligner.py:232,236,243,265
  * The sequences come back in the concatenated layout mb_map_batch takes. */
-typedef struct mb_fastq mb_fastq_t;
 int  mb_fastq_load(const char *path, mb_fastq_t **out);              /* plain or gzip; multi-line records accepted */
 int64_t mb_fastq_n(const mb_fastq_t *fq);
 const uint8_t *mb_fastq_seqs(const mb_fastq_t *fq, const int64_t **off);

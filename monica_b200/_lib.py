@@ -70,7 +70,7 @@ SYMBOLS = [
     "mb_last_error", "mb_device_count", "mb_opt_init",
     "mb_index_build", "mb_index_build_fasta", "mb_index_save", "mb_index_load", "mb_index_free", "mb_index_n_seq",
     "mb_index_seq_name", "mb_index_seq_len", "mb_index_mid_occ", "mb_index_kw", "mb_index_n_minimizers", "mb_index_hbm_bytes",
-    "mb_map_batch", "mb_map_batch_ex", "mb_reads_upload", "mb_reads_free", "mb_map_resident",
+    "mb_map_batch", "mb_map_batch_ex", "mb_reads_pack", "mb_fastq_pack", "mb_packed_free", "mb_packed_upload_bytes", "mb_packed_words", "mb_map_packed", "mb_reads_upload", "mb_reads_free", "mb_map_resident",
     "mb_hits_n", "mb_hits_field", "mb_hits_cigar_off", "mb_hits_cigar_pool", "mb_hits_rep_len", "mb_hits_free",
     "mb_count", "mb_count_last", "mb_count_device_ptr", "mb_count_fetch", "mb_normalize_last",
     "mb_comm_unique_id", "mb_comm_init", "mb_comm_free", "mb_allreduce_counts",
@@ -114,6 +114,15 @@ def lib():
     L.mb_index_hbm_bytes.restype = i64
     L.mb_map_batch.argtypes = [vp, C.POINTER(Opt), vp, vp, i32, C.POINTER(vp), C.POINTER(Stats)]
     L.mb_map_batch_ex.argtypes = [vp, C.POINTER(Opt), vp, vp, i32, C.c_int, C.POINTER(vp), C.POINTER(Stats)]
+    L.mb_reads_pack.argtypes = [vp, vp, i32, C.c_int, C.POINTER(vp)]
+    L.mb_fastq_pack.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    L.mb_packed_free.argtypes = [vp]
+    L.mb_packed_free.restype = None
+    L.mb_packed_upload_bytes.argtypes = [vp]
+    L.mb_packed_upload_bytes.restype = i64
+    L.mb_packed_words.argtypes = [vp, C.POINTER(i64), C.POINTER(vp), C.POINTER(i64)]
+    L.mb_packed_words.restype = vp
+    L.mb_map_packed.argtypes = [vp, C.POINTER(Opt), vp, C.c_int, C.POINTER(vp), C.POINTER(Stats)]
     L.mb_reads_upload.argtypes = [vp, vp, vp, i32, C.POINTER(vp)]
     L.mb_reads_free.argtypes = [vp]
     L.mb_reads_free.restype = None

@@ -1581,7 +1581,8 @@ static mb_hits *map_device(mb_index *ix, const mb_opt_t &opt, ThreadCtx &c, cons
 	return H.release();
 }
 
-static void upload_reads(ThreadCtx &c, const uint8_t *cat, const int64_t *off, int32_t n_reads, uint8_t **d_codes, int64_t **d_off, int64_t *total, bool persistent,
+// src: the whole batch on the host (ASCII or packed); g0: the first base of this piece within it; off: the piece's own offsets (from 0)
+static void upload_reads(ThreadCtx &c, const HostSrc &src, int64_t g0, const int64_t *off, int32_t n_reads, uint8_t **d_codes, int64_t **d_off, int64_t *total, bool persistent,
                          SketchFeed *feed = nullptr)
 {
 	cudaStream_t st = c.st;
@@ -1591,16 +1592,46 @@ static void upload_reads(ThreadCtx &c, const uint8_t *cat, const int64_t *off, i
 		if (off[i + 1] < off[i]) throw mb_error(MB_ERR_ARG, "offsets must be non-decreasing");
 		if (off[i + 1] - off[i] > 0x3fffffff) throw mb_error(MB_ERR_ARG, "read longer than 2^30");
 	}
-	uint8_t *d_ascii = c.ar.get<uint8_t>(*total + 32);
+	uint8_t *d_ascii = nullptr; uint32_t *d_words = nullptr; int64_t *d_iv = nullptr;
+	const uint32_t *h_words = nullptr;
+	int64_t n_w = 0, n_iv = 0;
+	const int r = (int)(g0 & 15);
+	if (src.pk) { // words [g0 >> 4, ...) of the batch: the piece starts r bases into its first word
+		const mb_packed &P = *src.pk;
+		if (g0 + *total > P.total) throw mb_error(MB_ERR_ARG, "piece beyond the packed batch");
+		h_words = P.words + (g0 >> 4);
+		n_w = ((r + *total + 15) >> 4) + 2;
+		if ((size_t)((g0 >> 4) + n_w) > P.n_words) n_w = (int64_t)P.n_words - (g0 >> 4);
+		d_words = c.ar.get<uint32_t>((size_t)n_w + 4);
+		// the runs of ambiguous bases that touch [g0, g0 + total)
+		const int64_t n_all = (int64_t)P.iv.size() / 2;
+		int64_t lo = 0, hi = n_all;
+		while (lo < hi) { const int64_t m = (lo + hi) >> 1; if (P.iv[2 * m] + P.iv[2 * m + 1] <= g0) lo = m + 1; else hi = m; }
+		int64_t k1 = lo;
+		while (k1 < n_all && P.iv[2 * k1] < g0 + *total) ++k1;
+		n_iv = k1 - lo;
+		if (n_iv) {
+			d_iv = c.ar.get<int64_t>((size_t)n_iv * 2);
+			CK(cudaMemcpyAsync(d_iv, P.iv.data() + 2 * lo, (size_t)n_iv * 16, cudaMemcpyHostToDevice, st));
+		}
+	} else d_ascii = c.ar.get<uint8_t>(*total + 32);
 	if (persistent) { CK(cudaMalloc(d_codes, *total + 32)); CK(cudaMalloc(d_off, (n_reads + 1) * 8)); }
 	else { *d_codes = c.ar.get<uint8_t>(*total + 32); *d_off = c.ar.get<int64_t>(n_reads + 1); }
 	CK(cudaMemcpyAsync(*d_off, off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
-	if (feed) { // the caller overlaps the ASCII copy with the sketch (run_sketch, SketchFeed)
-		feed->h_ascii = cat, feed->d_ascii = d_ascii, feed->d_codes = *d_codes, feed->copy_st = c.stf[0], feed->events = &c.feed_events;
+	if (feed) { // the caller overlaps the copy with the sketch (run_sketch, SketchFeed)
+		feed->h_ascii = src.pk ? nullptr : src.ascii + g0, feed->d_ascii = d_ascii, feed->d_codes = *d_codes, feed->copy_st = c.stf[0], feed->events = &c.feed_events;
+		feed->h_words = h_words, feed->d_words = d_words, feed->sh = 2 * r, feed->d_iv = d_iv, feed->n_iv = n_iv, feed->g0 = g0;
 		return;
 	}
-	if (*total) CK(cudaMemcpyAsync(d_ascii, cat, *total, cudaMemcpyHostToDevice, st));
-	if (*total) k_encode_nt4<<<(unsigned)cdiv(cdiv(*total, 16), 256), 256, 0, st>>>(d_ascii, *d_codes, *total);
+	if (!*total) return;
+	if (src.pk) {
+		CK(cudaMemcpyAsync(d_words, h_words, (size_t)n_w * 4, cudaMemcpyHostToDevice, st));
+		k_unpack_nt4<<<(unsigned)cdiv(cdiv(*total, 16), 256), 256, 0, st>>>(d_words, 2 * r, *d_codes, *total);
+		if (n_iv) k_apply_amb<<<(unsigned)cdiv(n_iv * 32, 256), 256, 0, st>>>(d_iv, n_iv, g0, *d_codes, 0, *total);
+	} else {
+		CK(cudaMemcpyAsync(d_ascii, src.ascii + g0, *total, cudaMemcpyHostToDevice, st));
+		k_encode_nt4<<<(unsigned)cdiv(cdiv(*total, 16), 256), 256, 0, st>>>(d_ascii, *d_codes, *total);
+	}
 }
 
 // ---- sequential pieces: batches whose scratch would not fit the device are mapped piece by piece ----
@@ -1664,8 +1695,8 @@ static bool shrink_piece(ThreadCtx &c, const void *ix, const mb_error &e, int64_
 	return true;
 }
 
-// h_cat != nullptr: reads in host memory (uploaded piece by piece); otherwise d_codes_all / d_off_all hold the resident batch
-static mb_hits *map_in_pieces(mb_index *ix, const mb_opt_t &opt, ThreadCtx &c, const uint8_t *h_cat, const uint8_t *d_codes_all, const int64_t *d_off_all,
+// h_src.any(): reads in host memory (uploaded piece by piece); otherwise d_codes_all / d_off_all hold the resident batch
+static mb_hits *map_in_pieces(mb_index *ix, const mb_opt_t &opt, ThreadCtx &c, const HostSrc &h_src, const uint8_t *d_codes_all, const int64_t *d_off_all,
                               const int64_t *h_off, int32_t n_reads, int want, mb_stats_t *stats, int64_t piece)
 {
 	std::vector<int32_t> cut(1, 0);
@@ -1700,12 +1731,12 @@ static mb_hits *map_in_pieces(mb_index *ix, const mb_opt_t &opt, ThreadCtx &c, c
 		cold_reserve(c, po[n]);
 		uint8_t *d_codes; int64_t *d_off; int64_t total = po[n];
 		SketchFeed feed; bool use_feed = false;
-		if (h_cat) {
+		if (h_src.any()) {
 			Timer tm(c.st); tm.start();
 			const char *feed_env = getenv("MB_FEED_MIN_BYTES");
 			const int64_t feed_min = feed_env ? atoll(feed_env) : ((int64_t)64 << 20);
 			use_feed = total >= feed_min;
-			upload_reads(c, h_cat + h_off[lo], po.data(), n, &d_codes, &d_off, &total, false, use_feed ? &feed : nullptr);
+			upload_reads(c, h_src, h_off[lo], po.data(), n, &d_codes, &d_off, &total, false, use_feed ? &feed : nullptr);
 			ms_h2d += tm.stop();
 		} else {
 			const int64_t base = h_off[lo] & ~(int64_t)15;   // keep the code pointer 16-byte aligned (vector loads)
@@ -1752,7 +1783,7 @@ static mb_hits *map_in_pieces(mb_index *ix, const mb_opt_t &opt, ThreadCtx &c, c
 		n_h += m, n_c += (int64_t)part->cigar.size();
 		S.n_reads += st1.n_reads, S.n_bases += st1.n_bases, S.n_mini += st1.n_mini, S.n_anchor += st1.n_anchor, S.n_regs += st1.n_regs;
 		S.n_dp_tasks += st1.n_dp_tasks, S.n_dp_pass2 += st1.n_dp_pass2, S.dp_cells += st1.dp_cells, S.n_hits += st1.n_hits;
-		S.n_rounds = std::max(S.n_rounds, st1.n_rounds), S.n_launches += st1.n_launches + (h_cat ? 1 : 0);
+		S.n_rounds = std::max(S.n_rounds, st1.n_rounds), S.n_launches += st1.n_launches + (h_src.any() ? 1 : 0);
 		S.ms_sketch += st1.ms_sketch, S.ms_seed += st1.ms_seed, S.ms_sort += st1.ms_sort, S.ms_chain += st1.ms_chain, S.ms_glue += st1.ms_glue;
 		S.ms_dp += st1.ms_dp, S.ms_post += st1.ms_post, S.ms_total += st1.ms_total, S.ms_d2h += st1.ms_d2h;
 		S.ms_kdp += st1.ms_kdp, S.n_kdp += st1.n_kdp, S.ms_kdp_fast += st1.ms_kdp_fast, S.ms_kdp_exact += st1.ms_kdp_exact, S.ms_kdp_ext += st1.ms_kdp_ext;
@@ -1783,19 +1814,48 @@ static mb_hits *map_in_pieces(mb_index *ix, const mb_opt_t &opt, ThreadCtx &c, c
 	return H.release();
 }
 
-static int map_batch_impl(mb_index_t *ix, const mb_opt_t *opt, const uint8_t *cat, const int64_t *off, int32_t n_reads, int want, mb_hits_t **out, mb_stats_t *stats);
+static int map_batch_impl(mb_index_t *ix, const mb_opt_t *opt, const HostSrc &src, const int64_t *off, int32_t n_reads, int want, mb_hits_t **out, mb_stats_t *stats);
 extern "C" int mb_map_batch(mb_index_t *ix, const mb_opt_t *opt, const uint8_t *cat, const int64_t *off, int32_t n_reads, mb_hits_t **out, mb_stats_t *stats)
 {
-	return map_batch_impl(ix, opt, cat, off, n_reads, 3, out, stats);
+	HostSrc src; src.ascii = cat;
+	return map_batch_impl(ix, opt, src, off, n_reads, 3, out, stats);
 }
 extern "C" int mb_map_batch_ex(mb_index_t *ix, const mb_opt_t *opt, const uint8_t *cat, const int64_t *off, int32_t n_reads, int want, mb_hits_t **out, mb_stats_t *stats)
 {
-	return map_batch_impl(ix, opt, cat, off, n_reads, want, out, stats);
+	HostSrc src; src.ascii = cat;
+	return map_batch_impl(ix, opt, src, off, n_reads, want, out, stats);
 }
-static int map_batch_impl(mb_index_t *ix, const mb_opt_t *opt, const uint8_t *cat, const int64_t *off, int32_t n_reads, int want, mb_hits_t **out, mb_stats_t *stats)
+// ---- packed reads (pack.cuh): packed once on the host, a quarter of the bytes over PCIe ----
+extern "C" int mb_reads_pack(const uint8_t *cat, const int64_t *off, int32_t n_reads, int n_threads, mb_packed_t **out)
 {
 	API_BEGIN
-	if (!ix || !opt || !off || !out || (n_reads > 0 && !cat && off[n_reads] > 0)) throw mb_error(MB_ERR_ARG, "bad arguments");
+	if (!out) throw mb_error(MB_ERR_ARG, "bad arguments");
+	*out = pk::pack(cat, off, n_reads, n_threads);
+	API_END
+}
+extern "C" void mb_packed_free(mb_packed_t *p) { delete p; }
+extern "C" int64_t mb_packed_upload_bytes(const mb_packed_t *p)
+{
+	return p ? (int64_t)(((p->total + 15) >> 4) + 2) * 4 + (int64_t)p->iv.size() * 8 + (int64_t)(p->n_reads + 1) * 8 : 0;
+}
+extern "C" const uint32_t *mb_packed_words(const mb_packed_t *p, int64_t *n_words, const int64_t **intervals, int64_t *n_intervals)
+{
+	if (!p) return nullptr;
+	if (n_words) *n_words = (int64_t)p->n_words;
+	if (intervals) *intervals = p->iv.data();
+	if (n_intervals) *n_intervals = (int64_t)p->iv.size() / 2;
+	return p->words;
+}
+extern "C" int mb_map_packed(mb_index_t *ix, const mb_opt_t *opt, const mb_packed_t *reads, int want, mb_hits_t **out, mb_stats_t *stats)
+{
+	if (!reads) { g_mb_err = "bad arguments"; return MB_ERR_ARG; }
+	HostSrc src; src.pk = reads;
+	return map_batch_impl(ix, opt, src, reads->off.data(), reads->n_reads, want, out, stats);
+}
+static int map_batch_impl(mb_index_t *ix, const mb_opt_t *opt, const HostSrc &src, const int64_t *off, int32_t n_reads, int want, mb_hits_t **out, mb_stats_t *stats)
+{
+	API_BEGIN
+	if (!ix || !opt || !off || !out || (n_reads > 0 && !src.any() && off[n_reads] > 0)) throw mb_error(MB_ERR_ARG, "bad arguments");
 	ThreadCtx &c = get_ctx(ix->device);
 	for (;;) try {
 	if (n_reads > 1 && off[n_reads] > piece_now(c, ix)) {
@@ -1803,7 +1863,7 @@ static int map_batch_impl(mb_index_t *ix, const mb_opt_t *opt, const uint8_t *ca
 			if (off[i + 1] < off[i] || off[0] != 0) throw mb_error(MB_ERR_ARG, "offsets must start at 0 and be non-decreasing");
 			if (off[i + 1] - off[i] > 0x3fffffff) throw mb_error(MB_ERR_ARG, "read longer than 2^30");
 		}
-		*out = map_in_pieces(ix, *opt, c, cat, nullptr, nullptr, off, n_reads, want, stats, piece_now(c, ix));
+		*out = map_in_pieces(ix, *opt, c, src, nullptr, nullptr, off, n_reads, want, stats, piece_now(c, ix));
 		return MB_OK;
 	}
 	c.ar.reset();
@@ -1815,7 +1875,7 @@ static int map_batch_impl(mb_index_t *ix, const mb_opt_t *opt, const uint8_t *ca
 	const char *feed_env = getenv("MB_FEED_MIN_BYTES");
 	const int64_t feed_min = feed_env ? atoll(feed_env) : ((int64_t)64 << 20);
 	const bool use_feed = n_reads > 0 && off[n_reads] >= feed_min;
-	upload_reads(c, cat, off, n_reads, &d_codes, &d_off, &total, false, use_feed ? &feed : nullptr);
+	upload_reads(c, src, 0, off, n_reads, &d_codes, &d_off, &total, false, use_feed ? &feed : nullptr);
 	float ms_h2d = tm.stop();
 	if (stats) stats->ms_h2d = ms_h2d;
 	*out = map_device(ix, *opt, c, d_codes, d_off, off, n_reads, total, want, stats, use_feed ? &feed : nullptr);
@@ -1833,7 +1893,8 @@ extern "C" int mb_reads_upload(mb_index_t *ix, const uint8_t *cat, const int64_t
 	c.ar.reset();
 	std::unique_ptr<mb_reads> r(new mb_reads());
 	r->device = ix->device; r->n_reads = n_reads;
-	upload_reads(c, cat, off, n_reads, &r->d_codes, &r->d_off, &r->total, true);
+	HostSrc src; src.ascii = cat;
+	upload_reads(c, src, 0, off, n_reads, &r->d_codes, &r->d_off, &r->total, true);
 	CK(cudaStreamSynchronize(c.st));
 	c.ar.reset();
 	*out = r.release();
@@ -1860,7 +1921,7 @@ extern "C" int mb_map_resident(mb_index_t *ix, const mb_opt_t *opt, mb_reads_t *
 	if (stats) stats->ms_h2d = 0;
 	for (;;) try {
 		if (reads->n_reads > 1 && reads->total > piece_now(c, ix)) {
-			*out = map_in_pieces(ix, *opt, c, nullptr, reads->d_codes, reads->d_off, h_off.data(), reads->n_reads, want_hits ? 3 : 0, stats, piece_now(c, ix));
+			*out = map_in_pieces(ix, *opt, c, HostSrc(), reads->d_codes, reads->d_off, h_off.data(), reads->n_reads, want_hits ? 3 : 0, stats, piece_now(c, ix));
 			return MB_OK;
 		}
 		c.ar.reset();
@@ -2199,7 +2260,8 @@ extern "C" int mb_sketch(int device, const uint8_t *cat, const int64_t *off, int
 	ThreadCtx &c = get_ctx(device);
 	c.ar.reset();
 	uint8_t *d_codes; int64_t *d_off; int64_t total; int64_t nl = 0;
-	upload_reads(c, cat, off, n_reads, &d_codes, &d_off, &total, false);
+	HostSrc src; src.ascii = cat;
+	upload_reads(c, src, 0, off, n_reads, &d_codes, &d_off, &total, false);
 	SketchOut so;
 	run_sketch(c.ar, c.st, d_codes, d_off, n_reads, total, w, k, so, &nl);
 	if (so.n_mini > cap) throw mb_error(MB_ERR_OVERFLOW, "output capacity too small");
@@ -2218,7 +2280,8 @@ extern "C" int mb_seed(mb_index_t *ix, const mb_opt_t *opt, const uint8_t *cat, 
 	ThreadCtx &c = get_ctx(ix->device);
 	c.ar.reset();
 	uint8_t *d_codes; int64_t *d_off; int64_t total; int64_t nl = 0;
-	upload_reads(c, cat, off, n_reads, &d_codes, &d_off, &total, false);
+	HostSrc src; src.ascii = cat;
+	upload_reads(c, src, 0, off, n_reads, &d_codes, &d_off, &total, false);
 	SketchOut so;
 	run_sketch(c.ar, c.st, d_codes, d_off, n_reads, total, ix->w, ix->k, so, &nl);
 	SeedOut sd;
@@ -2382,6 +2445,17 @@ extern "C" int mb_ll_batch(int device, const mb_opt_t *opt, mb_ll_task_t *tasks,
 }
 
 #include "fastq_host.cuh"   // FASTQ ingest and routed writers (host side)
+
+// the reads of a loaded FASTQ file in packed form (what mb_map_packed uploads)
+extern "C" int mb_fastq_pack(const mb_fastq_t *fq, int n_threads, mb_packed_t **out)
+{
+	API_BEGIN
+	if (!fq || !out) throw mb_error(MB_ERR_ARG, "bad arguments");
+	const int64_t zero = 0;
+	const int32_t n = fq->off.empty() ? 0 : (int32_t)(fq->off.size() - 1);
+	*out = pk::pack(fq->cat, n ? fq->off.data() : &zero, n, n_threads);
+	API_END
+}
 
 // ---- database builder: monica/genomes/database.py:52-67 builder() ----
 // One database<N>.fna.gz = the genomes of a chunk, every record re-headed "<tax_unit>:<accession>" (what the aligner later

@@ -21,6 +21,7 @@
 // compacted list.  Other (w,k) use the automaton for everything.
 #pragma once
 #include "common.cuh"
+#include "pack.cuh"
 
 #define SK_CHUNK 256
 #define SK_TPB   128
@@ -458,6 +459,11 @@ struct SketchOut {
 struct SketchFeed {
 	const uint8_t *h_ascii = nullptr;   // host reads (concatenated ASCII)
 	uint8_t *d_ascii = nullptr;         // device staging, total + 32 bytes
+	// ... or 2-bit packed words (pack.cuh): h_words[k] / d_words[k] hold bases [16k - sh/2, 16k - sh/2 + 16) of this batch
+	const uint32_t *h_words = nullptr;
+	uint32_t *d_words = nullptr;
+	int sh = 0;                         // 2 x (bases of the first word that precede the batch)
+	const int64_t *d_iv = nullptr; int64_t n_iv = 0, g0 = 0; // runs of ambiguous bases that touch the batch (global coordinates; g0 = the batch's first base)
 	uint8_t *d_codes = nullptr;         // nt4 codes to produce (== `codes` passed to run_sketch)
 	cudaStream_t copy_st = nullptr;
 	std::vector<cudaEvent_t> *events = nullptr; // pool, grown on demand
@@ -514,10 +520,16 @@ static void run_sketch(Arena &ar, cudaStream_t st, const uint8_t *codes, const i
 			const int64_t c1 = c0 + per < n_cta ? c0 + per : n_cta;
 			const int64_t b0 = c0 * SK_SPAN, b1 = c1 * SK_SPAN < total ? c1 * SK_SPAN : total;
 			while ((int)feed->events->size() <= p) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); feed->events->push_back(e); }
-			CK(cudaMemcpyAsync(feed->d_ascii + b0, feed->h_ascii + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, feed->copy_st));
+			if (feed->h_words) { // b0 is a multiple of 16: the piece's words start at b0 / 16, the last thread reads one word ahead
+				const int64_t k0w = b0 >> 4, k1w = ((feed->sh / 2 + b1 + 15) >> 4) + 1;
+				CK(cudaMemcpyAsync(feed->d_words + k0w, feed->h_words + k0w, (size_t)(k1w - k0w) * 4, cudaMemcpyHostToDevice, feed->copy_st));
+			} else CK(cudaMemcpyAsync(feed->d_ascii + b0, feed->h_ascii + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, feed->copy_st));
 			CK(cudaEventRecord((*feed->events)[p], feed->copy_st));
 			CK(cudaStreamWaitEvent(st, (*feed->events)[p], 0));
-			k_encode_nt4<<<(unsigned)cdiv(cdiv(b1 - b0, 16), 256), 256, 0, st>>>(feed->d_ascii + b0, feed->d_codes + b0, b1 - b0);
+			if (feed->h_words) {
+				k_unpack_nt4<<<(unsigned)cdiv(cdiv(b1 - b0, 16), 256), 256, 0, st>>>(feed->d_words + (b0 >> 4), feed->sh, feed->d_codes + b0, b1 - b0);
+				if (feed->n_iv) { k_apply_amb<<<(unsigned)cdiv(feed->n_iv * 32, 256), 256, 0, st>>>(feed->d_iv, feed->n_iv, feed->g0, feed->d_codes, b0, b1); ++*n_launch; }
+			} else k_encode_nt4<<<(unsigned)cdiv(cdiv(b1 - b0, 16), 256), 256, 0, st>>>(feed->d_ascii + b0, feed->d_codes + b0, b1 - b0);
 			if (par) {
 				const int64_t k0 = c0 * SK_TPB, k1 = c1 * SK_TPB < n_chunks ? c1 * SK_TPB : n_chunks;
 				k_sketch_par<<<(unsigned)cdiv(k1 - k0, SKP_WARPS), SKP_WARPS * 32, 0, st>>>(codes, d_off, n_reads, b1, k, chunk_cnt, read_cnt, stage, d_ovf, blist, bctr, k0, k1, chunk_read);

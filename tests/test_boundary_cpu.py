@@ -297,3 +297,62 @@ def test_host_logf_twin_equals_libm(oracle):
     nb, f = C.c_int64(0), C.c_uint32(0)
     _lib.check(L.mb_logf_sweep(-1, 0x40000000, 1024, exp.ctypes.data, C.byref(nb), C.byref(f)))
     assert (nb.value, f.value) == (1, 0x40000005)
+
+
+def _nt4_table():
+    t = np.full(256, 4, np.uint8)
+    for ch, v in (("A", 0), ("C", 1), ("G", 2), ("T", 3), ("U", 3)):
+        t[ord(ch)] = t[ord(ch.lower())] = v
+    return t
+
+
+def _unpack_packed(L, pk, total):
+    """numpy statement of what k_unpack_nt4 + k_apply_amb produce on the device from a packed batch."""
+    import ctypes as C
+    nw, ivp, niv = C.c_int64(0), C.c_void_p(), C.c_int64(0)
+    wp = L.mb_packed_words(pk, C.byref(nw), C.byref(ivp), C.byref(niv))
+    words = np.ctypeslib.as_array(C.cast(wp, C.POINTER(C.c_uint32)), shape=(nw.value,)).copy()
+    iv = (np.ctypeslib.as_array(C.cast(ivp, C.POINTER(C.c_int64)), shape=(2 * niv.value,)).copy().reshape(-1, 2)
+          if niv.value else np.zeros((0, 2), np.int64))
+    assert nw.value == (total + 15) // 16 + 2 and words[-1] == 0 and words[-2] == 0
+    codes = ((words[:, None] >> (2 * np.arange(16, dtype=np.uint32))[None, :]) & 3).astype(np.uint8).reshape(-1)[:total]
+    for s, n in iv:
+        assert np.all(codes[s:s + n] == 0)          # ambiguous bases travel as 0 in the words
+        codes[s:s + n] = 4
+    return codes, iv
+
+
+@pytest.mark.parametrize("n_threads", [1, 5])
+def test_read_packer_equals_nt4_table(n_threads):
+    """mb_reads_pack (pack.cuh): 2-bit words + runs of ambiguous bases must expand to exactly the nt4 codes of the ASCII
+    (minimap2's seq_nt4_table: A/a 0, C/c 1, G/g 2, T/t/U/u 3, everything else 4) -- the bytes mb_map_batch's own encode
+    kernel produces -- for mixed case, U, IUPAC letters, arbitrary bytes, runs of N across word and thread boundaries,
+    lengths that are not multiples of 16, and the empty batch."""
+    import ctypes as C
+    from monica_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(5)
+    tab = _nt4_table()
+    for total in (0, 1, 15, 16, 17, 4099, (3 << 20) + 7):
+        cat = np.frombuffer(b"ACGTacgtUuNnRYKM-*", np.uint8)[rng.integers(0, 8 if total > 100000 else 18, total)].copy()
+        if total > 100000:   # a few long and short runs of other characters, one across each thread cut, one at the very end
+            for s, n in ((5, 1), (31, 2), (1000, 40), (total // 5 - 3, 9), (2 * (total // 5) - 16, 33), (total - 4, 4)):
+                cat[s:s + n] = ord("N")
+            cat[77] = 0; cat[78] = 255; cat[79] = ord("@")
+        cuts = np.sort(rng.integers(0, total + 1, 6)) if total else np.zeros(0, np.int64)
+        off = np.concatenate([[0], cuts, [total]]).astype(np.int64)
+        pk = C.c_void_p()
+        _lib.check(L.mb_reads_pack(cat.ctypes.data, off.ctypes.data, len(off) - 1, n_threads, C.byref(pk)))
+        try:
+            codes, iv = _unpack_packed(L, pk, total)
+            want = tab[cat]
+            assert np.array_equal(codes, want)
+            # maximal, ascending, non-touching runs == the runs of code 4
+            amb = np.flatnonzero(np.diff(np.concatenate([[0], (want == 4).astype(np.int8), [0]])))
+            assert np.array_equal(iv.reshape(-1), np.stack([amb[0::2], amb[1::2] - amb[0::2]], 1).reshape(-1))
+            assert L.mb_packed_upload_bytes(pk) == ((total + 15) // 16 + 2) * 4 + 16 * len(iv) + 8 * len(off)
+        finally:
+            L.mb_packed_free(pk)
+    bad = np.array([1, 5], np.int64)
+    pk = C.c_void_p()
+    assert L.mb_reads_pack(cat.ctypes.data, bad.ctypes.data, 1, 1, C.byref(pk)) == -1   # MB_ERR_ARG: offsets must start at 0

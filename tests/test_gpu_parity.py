@@ -1026,3 +1026,58 @@ def test_device_logf_equals_libm_on_every_positive_normal_float(oracle, lib):
     nb, f = C.c_int64(0), C.c_uint32(0)
     _lib.check(lib.mb_logf_sweep(0, 0x40000000, 1024, exp.ctypes.data, C.byref(nb), C.byref(f)))
     assert (nb.value, f.value) == (1, 0x40000000 + 77)
+
+
+def test_packed_reads_map_like_ascii_reads(lib, monkeypatch):
+    """mb_map_packed (2-bit words + runs of ambiguous bases, expanded on the device) must return exactly what mb_map_batch
+    returns from the ASCII: reads with N runs, IUPAC letters, lower case and U; the plain upload, the piecewise upload under
+    the sketch kernels (SketchFeed: pieces of whole CTA spans, one word of look-ahead) and sequential pieces whose first
+    base is not word-aligned (MB_PIECE_BASES)."""
+    from monica_b200 import synth
+    from monica_b200.mappy_shim import Aligner
+    rng = np.random.default_rng(9)
+    names, seqs = synth.make_genomes(5, 3, 200_000)
+    reads, _ = synth.simulate_reads(6, seqs, 1500, 3000.0, 0.10)
+    reads = [np.frombuffer(r.encode() if isinstance(r, str) else bytes(r), np.uint8).copy() for r in reads]
+    for i in range(0, len(reads), 7):            # every 7th read carries other characters
+        r = reads[i]
+        if len(r) < 400:
+            continue
+        k = i // 7 % 5
+        if k == 0:
+            s = int(rng.integers(0, len(r) - 300)); r[s:s + int(rng.integers(1, 300))] = ord("N")
+        elif k == 1:
+            r[rng.integers(0, len(r), 20)] = np.frombuffer(b"RYKMSWn-", np.uint8)[rng.integers(0, 8, 20)]
+        elif k == 2:
+            r[:] = np.frombuffer(bytes(r).lower(), np.uint8)
+        elif k == 3:
+            r[r == ord("T")] = ord("U")
+        else:
+            r[-17:] = ord("N"); r[:3] = ord("N")
+    cat, off = synth.concat_reads(reads)
+    assert off[-1] > 9 * 32768 and (off[-1] // 32768) % 8 != 0
+    al = Aligner(names=names, seqs=seqs, preset="map-ont", best_n=15)
+    pk = Aligner.pack_reads(cat, off, n_threads=3)
+    assert pk.upload_bytes < 0.27 * len(cat) + 8 * len(off) + 4096
+    base = al.map_batch(cat=cat, off=off)
+    assert base.n > 1000
+
+    def same(got, tag):
+        assert got.n == base.n, tag
+        for f in ["read_idx"] + CMP_FIELDS:
+            assert np.array_equal(getattr(got, f), getattr(base, f)), (tag, f)
+        assert np.array_equal(got.cigar_off, base.cigar_off) and np.array_equal(got.cigar_pool, base.cigar_pool), tag
+        assert np.array_equal(got.rep_len, base.rep_len), tag
+
+    same(al.map_packed(pk), "plain")
+    monkeypatch.setenv("MB_FEED_MIN_BYTES", "1")
+    same(al.map_packed(pk), "piecewise upload")
+    monkeypatch.setenv("MB_PIECE_BASES", "700001")
+    same(al.map_packed(pk), "sequential pieces, piecewise upload")
+    monkeypatch.delenv("MB_FEED_MIN_BYTES")
+    same(al.map_packed(pk), "sequential pieces")
+    monkeypatch.delenv("MB_PIECE_BASES")
+    # a batch of one empty read, and the empty batch
+    for reads0 in ([np.zeros(0, np.uint8)], []):
+        c0, o0 = (np.zeros(0, np.uint8), np.zeros(len(reads0) + 1, np.int64))
+        assert al.map_packed(Aligner.pack_reads(c0, o0)).n == 0
