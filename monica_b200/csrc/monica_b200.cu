@@ -160,6 +160,11 @@ static void ensure_device(int device)
 static std::atomic<long long> g_scratch_per_base_x16{0};   // arena bytes per read base of the last batch (x16), for a cold arena's first reservation
 static std::once_flag g_const_once[16];
 static std::mutex g_dp_mutex[16];   // per device: serialises the DP stage of concurrent pieces / calling threads
+static int64_t mb_dp_lock_min_bases()
+{
+	static const int64_t v = getenv("MB_DP_LOCK_MIN_BASES") ? atoll(getenv("MB_DP_LOCK_MIN_BASES")) : ((int64_t)64 << 20);
+	return v;
+}
 
 static ThreadCtx *make_ctx(int device);
 static ThreadCtx &get_ctx(int device)
@@ -1310,10 +1315,13 @@ static void map_device_part(mb_index *ix, const mb_opt_t &opt_in, DevPart &part)
 			cigar_pool = nullptr; // offsets are now absolute word addresses (pools of different rounds coexist)
 			// One piece at a time in the (issue-bound) DP kernels; the other pieces meanwhile run their latency-bound stages
 			// (sketch, seeding, chaining, region logic before; stitching, mm_update_extra, finalisation after) underneath.
-			std::unique_lock<std::mutex> dp_token(g_dp_mutex[c.device & 15]);
+			// (only batches that fill the GPU: the DP launches of a small batch -- streaming mode, a few thousand reads per call --
+			// are latency-bound, and the batches of several calling threads then overlap instead of queueing)
+			std::unique_lock<std::mutex> dp_token(g_dp_mutex[c.device & 15], std::defer_lock);
+			if (total >= mb_dp_lock_min_bases()) dp_token.lock();
 			runner.run(tasks, nullptr, n_tasks, false, d_codes, ix->d.S, nullptr, cigar_pool, scoring, d_cells + 1, true);
 			CK(cudaEventSynchronize(c.ev_fast_done)); // the long-tailed side-stream launches of this piece may still be running
-			dp_token.unlock();
+			if (dp_token.owns_lock()) dp_token.unlock();
 			phase("dp pass 1");
 			// Z-drop test and second pass
 			int32_t *pass2 = ar.get<int32_t>(n_tasks), *zc = ar.get<int32_t>(4); // zc: [0] second-pass tasks, [1] walk list, [2] inversion-test candidates, [3] cursor
@@ -1382,10 +1390,11 @@ static void map_device_part(mb_index *ix, const mb_opt_t &opt_in, DevPart &part)
 				const int64_t ctot = d2h_scalar(ioff + n_dp, st);
 				uint32_t *ipool = ar.get<uint32_t>(ctot + 1);
 				k_set_cigar_off<<<(unsigned)cdiv(n_dp, 256), 256, 0, st>>>(itasks, ioff, n_dp, (int64_t)((uintptr_t)ipool / 4)); ++nl;
-				std::unique_lock<std::mutex> dp_token(g_dp_mutex[c.device & 15]);
+				std::unique_lock<std::mutex> dp_token(g_dp_mutex[c.device & 15], std::defer_lock);
+				if (total >= mb_dp_lock_min_bases()) dp_token.lock();
 				runner.run(itasks, nullptr, n_dp, false, d_codes, ix->d.S, nullptr, nullptr, scoring, d_cells + 1);
 				CK(cudaEventSynchronize(c.ev_fast_done));
-				dp_token.unlock();
+				if (dp_token.owns_lock()) dp_token.unlock();
 				k_inv_finish<<<(unsigned)cdiv(n_dp, 128), 128, 0, st>>>(ac, ra, itasks, task_inv, n_dp, iwork, iplans, ic + 5, d_err); ++nl;
 				const int32_t n_ok = d2h_scalar(ic + 5, st);
 				if (n_ok > 0) { k_update_extra<<<(unsigned)cdiv((int64_t)n_ok * 32, 128), 128, 0, st>>>(ac, ra, iwork, n_ok, iplans, itasks, nullptr, nullptr); ++nl; }

@@ -1081,3 +1081,22 @@ def test_packed_reads_map_like_ascii_reads(lib, monkeypatch):
     for reads0 in ([np.zeros(0, np.uint8)], []):
         c0, o0 = (np.zeros(0, np.uint8), np.zeros(len(reads0) + 1, np.int64))
         assert al.map_packed(Aligner.pack_reads(c0, o0)).n == 0
+
+
+def test_one_harness_two_libraries_same_arrays(lib, small_case):
+    """the boundary is implemented twice -- the CUDA library and the CPU oracle behind the same entry points
+    (oracle/mm2o_abi.c).  tests/abi_harness.py drives both through raw ctypes with identical calls (options, index build,
+    mb_map_batch, every hit array, mb_count in all modes, mb_sketch); every array that comes back must be identical."""
+    import abi_harness as H
+    from monica_b200 import synth
+    names, seqs, reads = small_case
+    cat, off = synth.concat_reads(reads)
+    gpu = H.run(H.load(H.CUDA_SO), names, seqs, cat, off, device=0)
+    cpu = H.run(H.oracle_library(), names, seqs, cat, off, device=0)
+    assert gpu.keys() == cpu.keys() and gpu["n_hits"][0] > 30
+    for k in gpu:
+        a, b = gpu[k], cpu[k]
+        if k == "sketch_xy":     # y carries the read index in its high word on both sides
+            assert np.array_equal(a, b), k
+        else:
+            assert a.shape == b.shape and np.array_equal(a, b), k
