@@ -84,7 +84,7 @@ struct ThreadCtx {
 	cudaStream_t st_defer[3] = {}; cudaEvent_t ev_defer[3] = {};   // long exact END EXTENSIONS of a first pass: run behind the gap-fill kernels, joined before the stitch   // extension / band launches done (before the gap-fill launches start)
 	std::vector<cudaEvent_t> feed_events;   // host->device pieces of mb_map_batch (SketchFeed)
 	int64_t piece_bases = 0;                // bases per sequential piece once a batch did not fit the device (0: the default)
-	const void *piece_index = nullptr;      // ... for this index
+	uint64_t piece_index = 0;               // ... for this index (mb_index::uid)
 	Arena ar;
 	int num_sms = 148;
 	uint8_t *h_pin = nullptr; size_t h_pin_cap = 0;   // pinned staging for reads
@@ -92,7 +92,7 @@ struct ThreadCtx {
 	// device-resident result of the last mapping call, one entry per sub-batch (lives in the arenas until the next reset)
 	struct LastPart { const int32_t *fields; const int64_t *hit_off, *read_off; int64_t n_hits; int32_t n_reads; };
 	std::vector<LastPart> last_parts;
-	int32_t last_n_reads = -1; const void *last_index = nullptr;
+	int32_t last_n_reads = -1; uint64_t last_index = 0;   // mb_index::uid of the last mapped batch
 	// batches cut into sequential pieces (memory budget): the hit fields / offsets of every piece are kept here (plain device
 	// memory, grown on demand, reused by later batches) so that mb_count_last sees the whole batch
 	char *store = nullptr; size_t store_cap = 0, store_used = 0;
@@ -134,7 +134,7 @@ struct ThreadCtxMap {
 			ThreadCtx *c = kv.second;
 			if (cudaSetDevice(c->device) == cudaSuccess) cudaStreamSynchronize(c->st);
 			cudaGetLastError();
-			c->last_parts.clear(); c->last_index = nullptr; c->last_n_reads = 0;
+			c->last_parts.clear(); c->last_index = 0; c->last_n_reads = 0;
 			bool kept = false;
 			{
 				std::lock_guard<std::mutex> g(g_ctx_pool->mu);
@@ -162,7 +162,9 @@ static std::once_flag g_const_once[16];
 static std::mutex g_dp_mutex[16];   // per device: serialises the DP stage of concurrent pieces / calling threads
 static int64_t mb_dp_lock_min_bases()
 {
-	static const int64_t v = getenv("MB_DP_LOCK_MIN_BASES") ? atoll(getenv("MB_DP_LOCK_MIN_BASES")) : ((int64_t)64 << 20);
+	// 0: every batch takes its turn.  Measured (4,000-read batches, 2 calling threads): letting small batches overlap in the DP
+	// stage is slower (0.55 vs 0.71 Gbases/s) -- their grids are sized for the whole GPU and get in each other's way
+	static const int64_t v = getenv("MB_DP_LOCK_MIN_BASES") ? atoll(getenv("MB_DP_LOCK_MIN_BASES")) : 0;
 	return v;
 }
 
@@ -224,7 +226,9 @@ template <typename T> static T d2h_scalar(const T *d, cudaStream_t st)
 // ---------------------------------------------------------------------------------------------
 // index
 // ---------------------------------------------------------------------------------------------
+static std::atomic<uint64_t> g_index_uid{1};
 struct mb_index {
+	const uint64_t uid = g_index_uid.fetch_add(1);   // never reused (a pointer is: a new index may land where a freed one was)
 	int device = 0;
 	int k = 15, w = 10, b = 14;
 	std::vector<std::string> names;
@@ -1315,8 +1319,7 @@ static void map_device_part(mb_index *ix, const mb_opt_t &opt_in, DevPart &part)
 			cigar_pool = nullptr; // offsets are now absolute word addresses (pools of different rounds coexist)
 			// One piece at a time in the (issue-bound) DP kernels; the other pieces meanwhile run their latency-bound stages
 			// (sketch, seeding, chaining, region logic before; stitching, mm_update_extra, finalisation after) underneath.
-			// (only batches that fill the GPU: the DP launches of a small batch -- streaming mode, a few thousand reads per call --
-			// are latency-bound, and the batches of several calling threads then overlap instead of queueing)
+			// (MB_DP_LOCK_MIN_BASES: batches below that size skip the turn-taking; default 0 = none do, see mb_dp_lock_min_bases)
 			std::unique_lock<std::mutex> dp_token(g_dp_mutex[c.device & 15], std::defer_lock);
 			if (total >= mb_dp_lock_min_bases()) dp_token.lock();
 			runner.run(tasks, nullptr, n_tasks, false, d_codes, ix->d.S, nullptr, cigar_pool, scoring, d_cells + 1, true);
@@ -1491,7 +1494,7 @@ static mb_hits *map_device(mb_index *ix, const mb_opt_t &opt, ThreadCtx &c, cons
 	H->rep_len.assign(n_reads, 0);
 	mb_stats_t S; memset(&S, 0, sizeof(S));
 	S.n_reads = n_reads, S.n_bases = total;
-	c.last_parts.clear(); c.last_n_reads = n_reads; c.last_index = ix;
+	c.last_parts.clear(); c.last_n_reads = n_reads; c.last_index = ix->uid;
 	if (n_reads == 0) { if (stats) *stats = S; return H.release(); }
 	const int K = mb_n_parts(n_reads, total);
 	if (feed && K > 1) { // several pieces read the codes from other streams: finish the upload first
@@ -1691,15 +1694,15 @@ template <typename T> static void concat_pin(PinVec<T> &dst, const std::vector<s
 // The scratch a piece needs depends on the database (anchors per base grow with its size and repetitiveness), so the piece
 // size is found by doing: a batch (or piece) that runs out of device memory is retried in pieces of half the size, and the
 // size that worked is remembered for the following calls of this thread.
-static int64_t piece_now(const ThreadCtx &c, const void *ix) { const int64_t d = mb_piece_bases(); return c.piece_index == ix && c.piece_bases > 0 && c.piece_bases < d ? c.piece_bases : d; }
-static bool shrink_piece(ThreadCtx &c, const void *ix, const mb_error &e, int64_t total, int32_t n_reads)
+static int64_t piece_now(const ThreadCtx &c, const mb_index *ix) { const int64_t d = mb_piece_bases(); return c.piece_index == ix->uid && c.piece_bases > 0 && c.piece_bases < d ? c.piece_bases : d; }
+static bool shrink_piece(ThreadCtx &c, const mb_index *ix, const mb_error &e, int64_t total, int32_t n_reads)
 {
 	const int64_t piece = piece_now(c, ix);
 	if (e.code != MB_ERR_NOMEM || n_reads <= 1 || piece <= 1000) return false;
 	cudaDeviceSynchronize(); cudaGetLastError();
 	c.ar.release();
 	c.last_parts.clear();
-	c.piece_bases = std::max<int64_t>(1000, std::min(piece, total) / 2); c.piece_index = ix;
+	c.piece_bases = std::max<int64_t>(1000, std::min(piece, total) / 2); c.piece_index = ix->uid;
 	if (getenv("MB_DEBUG")) fprintf(stderr, "[mb] device scratch did not fit: retrying in pieces of %lld bases\n", (long long)c.piece_bases);
 	return true;
 }
@@ -1803,7 +1806,7 @@ static mb_hits *map_in_pieces(mb_index *ix, const mb_opt_t &opt, ThreadCtx &c, c
 	}
 	S.ms_h2d = ms_h2d, S.n_pieces = K;
 	// device-resident view of the whole batch for mb_count_last
-	c.last_parts.clear(); c.last_n_reads = n_reads; c.last_index = ix;
+	c.last_parts.clear(); c.last_n_reads = n_reads; c.last_index = ix->uid;
 	for (const Kept &kp : kept) {
 		ThreadCtx::LastPart lp;
 		lp.fields = reinterpret_cast<const int32_t*>(c.store + kp.fields), lp.hit_off = reinterpret_cast<const int64_t*>(c.store + kp.hit_off);
@@ -1983,7 +1986,7 @@ extern "C" int mb_count_last(mb_index_t *ix, int32_t mapq_min, int mode, int64_t
 	API_BEGIN
 	if (!ix) throw mb_error(MB_ERR_ARG, "bad arguments");
 	ThreadCtx &c = get_ctx(ix->device);
-	if (c.last_index != ix || c.last_n_reads < 0) throw mb_error(MB_ERR_ARG, "no mapped batch of this index on this thread");
+	if (c.last_index != ix->uid || c.last_n_reads < 0) throw mb_error(MB_ERR_ARG, "no mapped batch of this index on this thread");
 	cudaStream_t st = c.st;
 	const int n_seq = (int)ix->names.size();
 	if (c.n_counts < n_seq + 4) {

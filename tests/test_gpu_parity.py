@@ -899,6 +899,15 @@ def test_batch_beyond_device_scratch_is_retried_in_smaller_pieces(lib, monkeypat
     monkeypatch.setenv("MB_TEST_ARENA_LIMIT", "4096")   # nothing fits: the error surfaces instead of looping
     with pytest.raises(Exception):
         al.map_batch(cat=cat, off=off)
+    # the piece size found for one index must not leak to the next one (which may be allocated where the freed one was)
+    monkeypatch.delenv("MB_TEST_ARENA_LIMIT")
+    import gc
+    del al, got, res
+    gc.collect()
+    al2 = Aligner(names=names, seqs=seqs, preset="map-ont", best_n=15)
+    again = al2.map_batch(cat=cat, off=off)
+    assert al2.last_stats["n_pieces"] <= 1
+    assert np.array_equal(want.mapq, again.mapq) and np.array_equal(want.cigar_pool, again.cigar_pool)
 
 
 def test_long_reads_with_tied_anchors_sort_bit_exact(oracle, lib):
