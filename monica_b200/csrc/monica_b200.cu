@@ -23,6 +23,7 @@
 #include "align.cuh"
 #include "align2.cuh"
 #include "dp_fast.cuh"
+#include "dp_fast_chain.cuh"
 #include "dp_ext.cuh"
 #include "dp_band.cuh"
 #include "align_cta.cuh"
@@ -826,6 +827,38 @@ struct DpRunner {
 		// queueing behind a full-occupancy grid
 		int max_cta = c.num_sms * occ;
 		int64_t want = cdiv(cdiv(cnt, 2), DPF_WARPS); // two tasks per warp
+		// Experiment, off by default (MB_FAST_CHAIN=G turns it on): the pairs of a warp chained through the lanes in groups of G
+		// (dp_fast_chain.cuh), which pays the 31-step ramp of the systolic wavefront once per group.  G shrinks with the pairs a
+		// warp gets (a group is the unit of work stealing) and with the direction-byte scratch (G regions per warp, at most 2 GB
+		// per launch).  Bit-identical results; measured on configs[1]: 155.7 ms of gap-fill launches at G = 4 against 150.9 ms
+		// unchained -- a lane's switch to the next pair (32 one-lane executions per boundary) and the backtracks reading direction
+		// bytes that have left the L2 by then cost more than the removed ramps save (profiles/r02_summary.md).
+		const char *chain_env = getenv("MB_FAST_CHAIN");
+		const int chain_g = chain_env ? atoi(chain_env) : 0;
+		if (chain_g >= 2) {
+			static int occ_c = 0;
+			if (occ_c == 0) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_dp_fast_chain<C>, 32, 0)); if (occ_c < 1) occ_c = 1; }
+			const int max_cta_c = c.num_sms * occ_c;
+			int G = chain_g < DPF_GMAX ? chain_g : DPF_GMAX;
+			const int64_t per_warp = want / max_cta_c;
+			const bool chain_force = getenv("MB_FAST_CHAIN_FORCE") != nullptr;   // tests: chain small classes too
+			if (per_warp / 4 < G && !chain_force) G = (int)(per_warp / 4);
+			while (G >= 2 && (size_t)max_cta_c * stride_words * 4 * G > ((size_t)2 << 30)) --G;
+			if (G >= 2) {
+				const int64_t want_c = cdiv(want, G);
+				const int n_cta = (int)(want_c < max_cta_c ? want_c : max_cta_c);
+				uint32_t *p_scr = ar.get<uint32_t>((size_t)n_cta * stride_words * G);
+				int32_t *wc = ar.get<int32_t>(1);
+				CK(cudaMemsetAsync(wc, 0, sizeof(int32_t), st));
+				cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+				cudaEventRecord(e0, st);
+				k_dp_fast_chain<C><<<n_cta, 32, 0, st>>>(tasks, list, d_cnt, wc, codes, S, pool, p_scr, stride_words * G, cigar_pool, sc, d_cells, G);
+				cudaEventRecord(e1, st);
+				evs.emplace_back(e0, e1); ev_fast.push_back(1); n_fast += cnt;
+				++*nl;
+				return;
+			}
+		}
 		int n_cta = (int)(want < max_cta ? want : max_cta);
 		uint32_t *p_scr = ar.get<uint32_t>((size_t)n_cta * DPF_WARPS * stride_words);
 		int32_t *wc = ar.get<int32_t>(1);
@@ -921,6 +954,51 @@ struct DpRunner {
 			k_list_longest_first<<<1, 1024, 0, s2>>>(tasks, list, (int)cnt, out); ++*nl;
 			return out;
 		};
+		// The exact kernels start AFTER the band and extension kernels are done: their CTAs hold most of an SM's shared memory for
+		// tens of milliseconds (long dependency chains, few tasks) and would keep the short extension / band CTAs from becoming
+		// resident.  They run beside the gap-fill launches.
+		auto launch_cta = [&](int cls, cudaStream_t st2, int cap_per_sm = 0) { // the large exact tasks: one CTA per task (align_cta.cuh)
+			const int64_t cnt = h_ctr[cls];
+			if (cnt == 0) return false;
+			size_t p_stride = ((size_t)h_max[cls * 3 + 0] + 255) & ~(size_t)255;
+			const size_t g_stride = ((size_t)h_max[cls * 3 + 1] + 255) & ~(size_t)255;
+			size_t h_stride = ((size_t)h_max[cls * 3 + 2] + 63) & ~(size_t)63;
+			if (p_stride == 0) p_stride = 256;
+			if (h_stride == 0) h_stride = 64;
+			static const bool cta_old = getenv("MB_CTA_OLD") != nullptr;   // debug: one cell at a time in 32-bit registers
+			static const bool nowin = getenv("MB_CTA_NOWIN") != nullptr;   // debug: state arrays of full length (shared memory if they fit, else global)
+			const size_t need = ((g_stride + 15) & ~(size_t)15) + h_stride * 4 + 64;
+			const int smem = nowin ? (int)(need < DPC_SMEM_MAX ? need : DPC_SMEM_MAX) : DPC_WIN_SMEM;
+			int per_sm = (200 * 1024) / (smem > 4096 ? smem : 4096); if (per_sm < 1) per_sm = 1; if (per_sm > (nowin ? 4 : 7)) per_sm = nowin ? 4 : 7;
+			if (!nowin && !cta_old) { // persistent CTAs: exactly as many as are resident at once (registers), so that none queues ahead of other streams' kernels
+				static int occ2 = 0;
+				if (occ2 == 0) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_dp_cta2, DPC2_THREADS, DPC_WIN_SMEM)); if (occ2 < 1) occ2 = 1; }
+				if (per_sm > occ2) per_sm = occ2;
+			}
+			if (cap_per_sm > 0 && per_sm > cap_per_sm) per_sm = cap_per_sm;
+			int n_cta = (int)std::min<int64_t>(cnt, (int64_t)mb_side_grid(c.num_sms * per_sm));
+			const size_t per_cta = p_stride + (nowin ? g_stride + h_stride * 4 : 0);
+			while (n_cta > 1 && (size_t)n_cta * per_cta > ((size_t)24 << 30)) n_cta = (n_cta + 1) / 2;
+			uint8_t *p_scr = ar.get<uint8_t>((size_t)n_cta * p_stride);
+			int8_t *g_ws = ar.get<int8_t>(nowin ? (size_t)n_cta * g_stride + 16 : 16);     // full-length state arrays: only without the window
+			int32_t *h_scr = ar.get<int32_t>(nowin ? (size_t)n_cta * h_stride : 16);
+			int32_t *wc = ar.get<int32_t>(1);
+			CK(cudaMemsetAsync(wc, 0, sizeof(int32_t), st2));
+			cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+			cudaEventRecord(e0, st2);
+			const int32_t *clist = longest_first(cls, st2);
+			if (nowin) k_dp_cta<false><<<n_cta, DPC_THREADS, smem, st2>>>(tasks, clist, ctr + cls, wc, codes, S, pool,
+				p_scr, p_stride, g_ws, g_stride, h_scr, h_stride, cigar_pool, sc, d_cells ? d_cells + 1 : nullptr, smem);
+			else if (cta_old) k_dp_cta<true><<<n_cta, DPC_THREADS, smem, st2>>>(tasks, clist, ctr + cls, wc, codes, S, pool,
+				p_scr, p_stride, g_ws, g_stride, h_scr, h_stride, cigar_pool, sc, d_cells ? d_cells + 1 : nullptr, smem);
+			else k_dp_cta2<<<n_cta, DPC2_THREADS, smem, st2>>>(tasks, clist, ctr + cls, wc, codes, S, pool,
+				p_scr, p_stride, g_ws, g_stride, h_scr, h_stride, cigar_pool, sc, d_cells ? d_cells + 1 : nullptr, smem);
+			{ cudaError_t le = cudaGetLastError(); if (le != cudaSuccess) throw mb_error(MB_ERR_CUDA, std::string("k_dp_cta launch: ") + cudaGetErrorString(le) + " grid " + std::to_string(n_cta) + " smem " + std::to_string(smem)); }
+			cudaEventRecord(e1, st2);
+			evs.emplace_back(e0, e1); ev_fast.push_back(0); n_exact += cnt;
+			++*nl;
+			return true;
+		};
 		bool side[MB_NSIDE] = {};
 		bool band_fills = false;   // a band launch with a full grid: worth waiting for (else it is a few long tasks: run beside it)
 		const bool serial = getenv("MB_DEBUG_SERIAL") != nullptr;   // every launch on `st`, one after the other: stand-alone durations
@@ -980,6 +1058,21 @@ struct DpRunner {
 			default: launch_ext<24>(tasks, list, ctr + DP_XBASE + k, cnt, mq, codes, S, pool, cigar_pool, sc, xc, sx); break;
 			}
 		}
+		// experiment (MB_DEFER_MODE=1): the deferred exact end extensions beside the extension / band launches, at MB_DEFER_PER_SM CTAs per SM
+		static const int defer_mode = getenv("MB_DEFER_MODE") ? atoi(getenv("MB_DEFER_MODE")) : 0;
+		static const int defer_cap = getenv("MB_DEFER_PER_SM") ? atoi(getenv("MB_DEFER_PER_SM")) : 3;
+		bool deferred_early = false;
+		if (defer_mode == 1 && !serial) {
+			int k = 0;
+			for (int b = DP_NCTA - 1; b >= 0; --b) {
+				if (h_ctr[DP_DBASE + b] == 0) continue;
+				const int i = k++ % 3;
+				if (!(deferred >> i & 1)) CK(cudaStreamWaitEvent(c.st_defer[i], c.ev_fork, 0));
+				launch_cta(DP_DBASE + b, c.st_defer[i], defer_cap);
+				deferred |= 1 << i;
+			}
+			deferred_early = true;
+		}
 		if (!serial) { // the gap-fill and exact launches start when the extension and band launches are done
 			CK(cudaEventRecord(c.ev_x[0], c.st2[2])); CK(cudaEventRecord(c.ev_x[1], c.st2[3]));
 			CK(cudaEventRecord(c.ev_x[2], c.stf[0])); CK(cudaEventRecord(c.ev_x[3], c.stf[1]));
@@ -990,50 +1083,6 @@ struct DpRunner {
 			CK(cudaStreamWaitEvent(c.stf[0], c.ev_fork2, 0)); CK(cudaStreamWaitEvent(c.stf[1], c.ev_fork2, 0));
 			CK(cudaStreamWaitEvent(c.st2[0], c.ev_fork2, 0)); CK(cudaStreamWaitEvent(c.st2[1], c.ev_fork2, 0));
 		}
-		// The exact kernels start AFTER the band and extension kernels are done: their CTAs hold most of an SM's shared memory for
-		// tens of milliseconds (long dependency chains, few tasks) and would keep the short extension / band CTAs from becoming
-		// resident.  They run beside the gap-fill launches.
-		auto launch_cta = [&](int cls, cudaStream_t st2) { // the large exact tasks: one CTA per task (align_cta.cuh)
-			const int64_t cnt = h_ctr[cls];
-			if (cnt == 0) return false;
-			size_t p_stride = ((size_t)h_max[cls * 3 + 0] + 255) & ~(size_t)255;
-			const size_t g_stride = ((size_t)h_max[cls * 3 + 1] + 255) & ~(size_t)255;
-			size_t h_stride = ((size_t)h_max[cls * 3 + 2] + 63) & ~(size_t)63;
-			if (p_stride == 0) p_stride = 256;
-			if (h_stride == 0) h_stride = 64;
-			static const bool cta_old = getenv("MB_CTA_OLD") != nullptr;   // debug: one cell at a time in 32-bit registers
-			static const bool nowin = getenv("MB_CTA_NOWIN") != nullptr;   // debug: state arrays of full length (shared memory if they fit, else global)
-			const size_t need = ((g_stride + 15) & ~(size_t)15) + h_stride * 4 + 64;
-			const int smem = nowin ? (int)(need < DPC_SMEM_MAX ? need : DPC_SMEM_MAX) : DPC_WIN_SMEM;
-			int per_sm = (200 * 1024) / (smem > 4096 ? smem : 4096); if (per_sm < 1) per_sm = 1; if (per_sm > (nowin ? 4 : 7)) per_sm = nowin ? 4 : 7;
-			if (!nowin && !cta_old) { // persistent CTAs: exactly as many as are resident at once (registers), so that none queues ahead of other streams' kernels
-				static int occ2 = 0;
-				if (occ2 == 0) { CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_dp_cta2, DPC2_THREADS, DPC_WIN_SMEM)); if (occ2 < 1) occ2 = 1; }
-				if (per_sm > occ2) per_sm = occ2;
-			}
-			int n_cta = (int)std::min<int64_t>(cnt, (int64_t)mb_side_grid(c.num_sms * per_sm));
-			const size_t per_cta = p_stride + (nowin ? g_stride + h_stride * 4 : 0);
-			while (n_cta > 1 && (size_t)n_cta * per_cta > ((size_t)24 << 30)) n_cta = (n_cta + 1) / 2;
-			uint8_t *p_scr = ar.get<uint8_t>((size_t)n_cta * p_stride);
-			int8_t *g_ws = ar.get<int8_t>(nowin ? (size_t)n_cta * g_stride + 16 : 16);     // full-length state arrays: only without the window
-			int32_t *h_scr = ar.get<int32_t>(nowin ? (size_t)n_cta * h_stride : 16);
-			int32_t *wc = ar.get<int32_t>(1);
-			CK(cudaMemsetAsync(wc, 0, sizeof(int32_t), st2));
-			cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-			cudaEventRecord(e0, st2);
-			const int32_t *clist = longest_first(cls, st2);
-			if (nowin) k_dp_cta<false><<<n_cta, DPC_THREADS, smem, st2>>>(tasks, clist, ctr + cls, wc, codes, S, pool,
-				p_scr, p_stride, g_ws, g_stride, h_scr, h_stride, cigar_pool, sc, d_cells ? d_cells + 1 : nullptr, smem);
-			else if (cta_old) k_dp_cta<true><<<n_cta, DPC_THREADS, smem, st2>>>(tasks, clist, ctr + cls, wc, codes, S, pool,
-				p_scr, p_stride, g_ws, g_stride, h_scr, h_stride, cigar_pool, sc, d_cells ? d_cells + 1 : nullptr, smem);
-			else k_dp_cta2<<<n_cta, DPC2_THREADS, smem, st2>>>(tasks, clist, ctr + cls, wc, codes, S, pool,
-				p_scr, p_stride, g_ws, g_stride, h_scr, h_stride, cigar_pool, sc, d_cells ? d_cells + 1 : nullptr, smem);
-			{ cudaError_t le = cudaGetLastError(); if (le != cudaSuccess) throw mb_error(MB_ERR_CUDA, std::string("k_dp_cta launch: ") + cudaGetErrorString(le) + " grid " + std::to_string(n_cta) + " smem " + std::to_string(smem)); }
-			cudaEventRecord(e1, st2);
-			evs.emplace_back(e0, e1); ev_fast.push_back(0); n_exact += cnt;
-			++*nl;
-			return true;
-		};
 		for (int b = DP_NCTA - 1; b >= 0; --b) // largest class first
 			if (launch_cta(DP_CBASE + b, serial ? st : c.st2[b & 1])) side[b & 1] = true;
 		for (int b = DP_NEXACT - 1; b >= 0; --b) {
@@ -1117,7 +1166,7 @@ struct DpRunner {
 		{ // deferred end extensions: behind the gap-fill kernels, beside whatever the caller does next (Z-drop test, second pass)
 			static const bool defer_early = getenv("MB_DEFER_EARLY") != nullptr;   // experiment: lowest-priority CTAs fill the gaps of the gap-fill launches
 			int k = 0;   // one stream per class: a small batch has a few long tasks per class, and the classes then run side by side
-			for (int b = DP_NCTA - 1; b >= 0; --b) {
+			for (int b = DP_NCTA - 1; b >= 0 && !deferred_early; --b) {
 				if (h_ctr[DP_DBASE + b] == 0) continue;
 				const int i = k++ % 3;
 				if (serial) { launch_cta(DP_DBASE + b, st); continue; }

@@ -309,6 +309,15 @@ def test_dp_fast_path_pairs(oracle, lib):
     assert any(r["reach_end"] for r in recs)
     tasks, cig = _run_dp(lib, opt, recs)
     _check_dp(tasks, cig, recs)
+    # the chained variant of the kernel (dp_fast_chain.cuh, an opt-in experiment: the pairs of a warp back to back through the
+    # lanes) must give the same answers: groups of 2, 3 and 4 pairs, every class, ragged group at the end of each list
+    for g in ("2", "3", "4"):
+        os.environ["MB_FAST_CHAIN"], os.environ["MB_FAST_CHAIN_FORCE"] = g, "1"
+        try:
+            tasks, cig = _run_dp(lib, opt, recs + recs[:-1] + recs[3:])
+        finally:
+            del os.environ["MB_FAST_CHAIN"], os.environ["MB_FAST_CHAIN_FORCE"]
+        _check_dp(tasks, cig, recs + recs[:-1] + recs[3:])
 
 
 def _compare_hits(hits, per, i, want):
