@@ -16,7 +16,7 @@
 //   * every pair keeps its own [step][lane][C/2] region of direction bytes, the regions back to back, so a lane's store
 //     pointer advances by one step per step and by 31 more at a switch; the backtracks of the group run after its forward
 //     pass with the code of k_dp_fast,
-//   * the end-score sums (sum of u over the last row) are flushed to shared memory by each lane at its switch.
+//   * each lane leaves its share of the end-score sums (sum of u over the last row) in shared memory at its switch.
 // The cell arithmetic is k_dp_fast's, statement for statement; results are identical by construction and by test
 // (tests/test_gpu_parity.py::test_dp_fast_path_pairs runs both kernels).
 #pragma once
@@ -32,7 +32,10 @@ k_dp_fast_chain(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, c
 {
 	constexpr int CW = (C + 1) / 2;
 	__shared__ uint32_t sSEL[DPF_GMAX][C][32];
-	__shared__ int sQA[DPF_GMAX], sQB[DPF_GMAX], sTLA[DPF_GMAX], sTLB[DPF_GMAX], sQm[DPF_GMAX], sBase[DPF_GMAX + 1], sSumA[DPF_GMAX], sSumB[DPF_GMAX];
+	__shared__ int sQA[DPF_GMAX], sQB[DPF_GMAX], sTLA[DPF_GMAX], sTLB[DPF_GMAX], sQm[DPF_GMAX], sBase[DPF_GMAX + 1];
+	__shared__ int4 sMeta[DPF_GMAX];                     // what a lane needs when it enters pair g: rows, last row of A, last row of B
+	__shared__ uint32_t sCMA[DPF_GMAX][32], sCMB[DPF_GMAX][32];   // ... and which of its columns belong to task A / B
+	__shared__ int sSum[DPF_GMAX][2][32];                // each lane's share of the end-score sums of pair g, written when it leaves the pair
 	__shared__ int sIdA[DPF_GMAX], sIdB[DPF_GMAX];
 	__shared__ QView sqA[DPF_GMAX], sqB[DPF_GMAX];
 	const unsigned FULL = 0xffffffffu;
@@ -84,7 +87,7 @@ k_dp_fast_chain(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, c
 				QView va; va.codes = TA.q_comp == 2 ? pool : codes; va.idx0 = TA.q_idx0; va.step = TA.q_step; va.comp = TA.q_comp == 1;
 				QView vb; vb.codes = TB.q_comp == 2 ? pool : codes; vb.idx0 = TB.q_idx0; vb.step = TB.q_step; vb.comp = TB.q_comp == 1;
 				sqA[lane] = va, sqB[lane] = vb;
-				sSumA[lane] = 0, sSumB[lane] = 0;
+				sMeta[lane] = make_int4(sQm[lane], TA.qlen - 1, TB.qlen - 1, 0);
 			} else sQm[lane] = 0;
 		}
 		__syncwarp();
@@ -106,6 +109,9 @@ k_dp_fast_chain(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, c
 				const uint32_t a = t < TLA ? (uint32_t)tvA.at(t) & 3u : 0u, b = t < TLB ? (uint32_t)tvB.at(t) & 3u : 0u;
 				sSEL[g][c][lane] = a | (8u | a) << 4 | (4u + b) << 8 | (12u + b) << 12;
 			}
+			const int na = TLA - t0, nb = TLB - t0;
+			sCMA[g][lane] = na <= 0 ? 0u : na >= C ? (1u << C) - 1u : (1u << na) - 1u;
+			sCMB[g][lane] = nb <= 0 ? 0u : nb >= C ? (1u << C) - 1u : (1u << nb) - 1u;
 		}
 		// (a lane reads back only what it wrote itself: no barrier needed for sSEL)
 		uint32_t SEL[C], U[C], Y[C], Y2[C];
@@ -113,11 +119,9 @@ k_dp_fast_chain(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, c
 		uint32_t cmA, cmB;   // bit c: column t0 + c belongs to task A / B of the current pair
 		bool live;
 		auto enter_pair = [&](int g) {
-			rows = sQm[g], qa1 = sQA[g] - 1, qb1 = sQB[g] - 1;
-			const int TLA = sTLA[g], TLB = sTLB[g];
-			const int na = TLA - t0, nb = TLB - t0;
-			cmA = na <= 0 ? 0u : na >= C ? (1u << C) - 1u : (1u << na) - 1u;
-			cmB = nb <= 0 ? 0u : nb >= C ? (1u << C) - 1u : (1u << nb) - 1u;
+			const int4 m = sMeta[g];
+			rows = m.x, qa1 = m.y, qb1 = m.z;
+			cmA = sCMA[g][lane], cmB = sCMB[g][lane];
 			live = (cmA | cmB) != 0u;
 			#pragma unroll
 			for (int c = 0; c < C; ++c) {
@@ -201,8 +205,7 @@ k_dp_fast_chain(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, c
 				}
 			}
 			if (++j == rows) { // this lane moves on to the next pair of the group
-				if (sumA) atomicAdd(&sSumA[g_cur], sumA);
-				if (sumB) atomicAdd(&sSumB[g_cur], sumB);
+				sSum[g_cur][0][lane] = sumA, sSum[g_cur][1][lane] = sumB;
 				sumA = sumB = 0;
 				++g_cur, j = 0;
 				if (g_cur < n_g) enter_pair(g_cur);
@@ -218,15 +221,18 @@ k_dp_fast_chain(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, c
 			DpTask &TB = tasks[hasB ? sIdB[g] : sIdA[g]];
 			const int QA = sQA[g], QB = sQB[g], TLA = sTLA[g], TLB = sTLB[g], Qm = sQm[g];
 			cells += (unsigned long long)TLA * (unsigned)QA + (hasB ? (unsigned long long)TLB * (unsigned)QB : 0ULL);
-			int bsA = 0, bsB = 0;
+			int bsA = 0, bsB = 0, suA = sSum[g][0][lane], suB = sSum[g][1][lane];
 			for (int r = lane; r < Qm; r += 32) {
 				const int bv = dpf_bnd(r, q, e, e2, long_thres, long_diff);
 				if (r < QA) bsA += bv;
 				if (r < QB) bsB += bv;
 			}
 			#pragma unroll
-			for (int dlt = 16; dlt > 0; dlt >>= 1) bsA += __shfl_xor_sync(FULL, bsA, dlt), bsB += __shfl_xor_sync(FULL, bsB, dlt);
-			const int scoreA = bsA + (sSumA[g] >> 3) - B * TLA, scoreB = bsB + (sSumB[g] >> 3) - B * TLB;
+			for (int dlt = 16; dlt > 0; dlt >>= 1) {
+				bsA += __shfl_xor_sync(FULL, bsA, dlt), bsB += __shfl_xor_sync(FULL, bsB, dlt);
+				suA += __shfl_xor_sync(FULL, suA, dlt), suB += __shfl_xor_sync(FULL, suB, dlt);
+			}
+			const int scoreA = bsA + (suA >> 3) - B * TLA, scoreB = bsB + (suB >> 3) - B * TLB;
 			const uint32_t *Pg = P + ((size_t)sBase[g] + (size_t)31 * g) * 32 * CW;
 			const int grp = lane >> 4, hl = lane & 15;
 			const unsigned gmask = grp ? 0xffff0000u : 0x0000ffffu;

@@ -830,9 +830,11 @@ struct DpRunner {
 		// Experiment, off by default (MB_FAST_CHAIN=G turns it on): the pairs of a warp chained through the lanes in groups of G
 		// (dp_fast_chain.cuh), which pays the 31-step ramp of the systolic wavefront once per group.  G shrinks with the pairs a
 		// warp gets (a group is the unit of work stealing) and with the direction-byte scratch (G regions per warp, at most 2 GB
-		// per launch).  Bit-identical results; measured on configs[1]: 155.7 ms of gap-fill launches at G = 4 against 150.9 ms
-		// unchained -- a lane's switch to the next pair (32 one-lane executions per boundary) and the backtracks reading direction
-		// bytes that have left the L2 by then cost more than the removed ramps save (profiles/r02_summary.md).
+		// per launch).  Bit-identical results; measured on configs[1]: 149.5 ms of gap-fill launches at G = 4 (151.8 at G = 2)
+		// against 150.6 - 151.1 ms unchained.  A lane's switch to the next pair is executed by one lane at a time, 32 times per
+		// boundary (66 instructions each: 3.4 % of a pair), and the backtracks of a group read direction bytes that have left the
+		// L2 by then, so most of what the removed ramps save is spent again; 1 % does not pay for 4x the direction-byte scratch
+		// (profiles/r02_summary.md).
 		const char *chain_env = getenv("MB_FAST_CHAIN");
 		const int chain_g = chain_env ? atoi(chain_env) : 0;
 		if (chain_g >= 2) {
