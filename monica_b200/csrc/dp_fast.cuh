@@ -61,6 +61,7 @@ MB_D uint32_t dpf_pack2(int v) { return (uint32_t)(uint16_t)(int16_t)v * 0x10001
 MB_D uint32_t dpf_and(uint32_t a, uint32_t b) { uint32_t d; asm("and.b32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
 MB_D uint32_t dpf_mad(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
 // PRMT in its default mode: selector nibble bit 3 replicates the sign of the selected byte (used to produce zero bytes)
+MB_D uint32_t dpf_sel(bool p, uint32_t a, uint32_t b) { uint32_t d; asm("{ .reg .pred q; setp.ne.u32 q, %3, 0; selp.b32 %0, %1, %2, q; }" : "=r"(d) : "r"(a), "r"(b), "r"((uint32_t)p)); return d; }
 MB_D uint32_t dpf_prmt(uint32_t a, uint32_t b, uint32_t sel) { uint32_t d; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel)); return d; }
 
 // does a contiguous run of nt4 bytes / 4-bit packed bases hold a code >= 4?  One masked pass over the aligned 32-bit words
@@ -149,6 +150,9 @@ k_dp_fast(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 	constexpr int CW = (C + 1) / 2; // 32-bit words of direction bytes per lane per step (two tasks x C columns)
 	const unsigned FULL = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
+	const bool lane0 = lane == 0;
+	__shared__ uint2 ring_all[DPF_WARPS][128];   // substitution tables of the query rows in flight (see the main loop)
+	uint2 *ring = ring_all[threadIdx.x >> 5];
 	const int gw = blockIdx.x * DPF_WARPS + (threadIdx.x >> 5);
 	uint32_t *P = p_scr + (size_t)gw * p_stride_words;
 	unsigned long long cells = 0;
@@ -205,8 +209,11 @@ k_dp_fast(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 			const int a = r < QA ? qvA.at(r) : 0, b = r < QB ? qvB.at(r) : 0;
 			la = a < 4 ? MIS4 + (MDIFF << (a * 8)) : N4, lb = b < 4 ? MIS4 + (MDIFF << (b * 8)) : N4;
 		};
-		uint32_t LAc, LBc, LAn = 0, LBn = 0, LAo = 0, LBo = 0;
-		row_tables(lane, LAc, LBc);
+		// The tables of rows [32k, 32k + 32) are computed by the 32 lanes one block ahead (registers LAn | LBn) and parked in a
+		// 128-entry ring in shared memory when their block starts; lane L then reads row s - L with one 8-byte load per step.
+		uint32_t LAn = 0, LBn = 0;
+		row_tables(lane, LAn, LBn);
+		__syncwarp();   // the previous pair's last reads of the ring
 		const uint32_t VB0 = dpf_pack2(8 * (dpf_bnd(0, q, e, e2, long_thres, long_diff) + B)), VB1 = dpf_pack2(8 * (-e + B));
 		const uint32_t VB2 = dpf_pack2(8 * (long_diff + B)), VB3 = dpf_pack2(8 * (-e2 + B));
 		uint32_t *dst = P + (size_t)lane * CW;
@@ -216,17 +223,17 @@ k_dp_fast(DpTask *__restrict__ tasks, const int32_t *__restrict__ order, const i
 			constexpr bool CAPTURE = decltype(capture)::value;
 			const int j = s - lane;
 			if ((s & 31) == 0) {
-				if (s) LAc = LAn, LBc = LBn;
+				ring[(s + lane) & 127] = make_uint2(LAn, LBn);
+				__syncwarp();
 				if (s + 32 < Qm) row_tables(s + 32 + lane, LAn, LBn);
 			}
-			const uint32_t LA0 = __shfl_sync(FULL, LAc, s & 31), LB0 = __shfl_sync(FULL, LBc, s & 31);
-			uint32_t LA = __shfl_up_sync(FULL, LAo, 1), LB = __shfl_up_sync(FULL, LBo, 1);
+			const uint2 LAB = ring[(s - lane) & 127];
+			const uint32_t LA = LAB.x, LB = LAB.y;
 			uint32_t XL = __shfl_up_sync(FULL, XLo, 1), VL = __shfl_up_sync(FULL, VLo, 1), X2L = __shfl_up_sync(FULL, X2Lo, 1);
-			if (lane == 0) {
-				LA = LA0, LB = LB0, XL = X_INIT, X2L = X2_INIT;
-				VL = s == 0 ? VB0 : s < long_thres ? VB1 : s == long_thres ? VB2 : VB3;
-			}
-			LAo = LA, LBo = LB;
+			// lane 0 takes the matrix's left boundary instead of a neighbour's values (selects on a loop-invariant predicate; the
+			// boundary value of row s is warp-uniform)
+			const uint32_t VB = s == 0 ? VB0 : s < long_thres ? VB1 : s == long_thres ? VB2 : VB3;
+			XL = dpf_sel(lane0, X_INIT, XL), X2L = dpf_sel(lane0, X2_INIT, X2L), VL = dpf_sel(lane0, VB, VL);
 			if (lane_live && j >= 0 && j < Qm) {
 				uint32_t wv[CW];
 				uint32_t wprev = 0;

@@ -1173,7 +1173,17 @@ struct DpRunner {
 				const int i = k++ % 3;
 				if (serial) { launch_cta(DP_DBASE + b, st); continue; }
 				if (!(deferred >> i & 1)) CK(cudaStreamWaitEvent(c.st_defer[i], defer_early ? c.ev_fork2 : c.ev_fast_done, 0));
-				launch_cta(DP_DBASE + b, c.st_defer[i]);
+				// At full occupancy (6 CTAs per SM) the persistent CTAs of the deferred launches take every SM's registers, and the Z-drop
+				// test and second pass that follow on the main stream wait for them to drain: 18 ms on the configs[1] batch.  When the
+				// deferred classes are small (a few tasks per CTA: their duration is set by the longest tasks, not by occupancy) they
+				// run at 4 CTAs per SM and the main stream's kernels fit beside them (265.8 -> 261.5 ms per step; 5, 3 and 2 per SM
+				// measured worse).  Large deferred classes (long reads) keep the full occupancy.  MB_DEFER_CAP / MB_DEFER_CAP_TASKS override.
+				static const int defer_cap2 = getenv("MB_DEFER_CAP") ? atoi(getenv("MB_DEFER_CAP")) : 4;
+				static const long long defer_cap_tasks = getenv("MB_DEFER_CAP_TASKS") ? atoll(getenv("MB_DEFER_CAP_TASKS")) : 8192;
+				long long n_def = 0;
+				for (int b2 = 0; b2 < DP_NCTA; ++b2) n_def += h_ctr[DP_DBASE + b2];
+				if (getenv("MB_DEBUG")) fprintf(stderr, "[mb] deferred exact class %d: %lld tasks (of %lld deferred)\n", b, (long long)h_ctr[DP_DBASE + b], n_def);
+				launch_cta(DP_DBASE + b, c.st_defer[i], n_def <= defer_cap_tasks ? defer_cap2 : 0);
 				deferred |= 1 << i;
 			}
 			for (int i = 0; i < 3; ++i) if (deferred >> i & 1) CK(cudaEventRecord(c.ev_defer[i], c.st_defer[i]));
