@@ -1559,8 +1559,15 @@ static mb_hits *map_device(mb_index *ix, const mb_opt_t &opt, ThreadCtx &c, cons
 	if (n_reads == 0) { if (stats) *stats = S; return H.release(); }
 	const int K = mb_n_parts(n_reads, total);
 	if (feed && K > 1) { // several pieces read the codes from other streams: finish the upload first
-		CK(cudaMemcpyAsync(feed->d_ascii, feed->h_ascii, (size_t)total, cudaMemcpyHostToDevice, c.st));
-		k_encode_nt4<<<(unsigned)cdiv(cdiv(total, 16), 256), 256, 0, c.st>>>(feed->d_ascii, feed->d_codes, total);
+		if (feed->h_words) { // packed input: all words of the batch (one word of look-ahead), then the runs of ambiguous bases
+			const int64_t n_w = ((feed->sh / 2 + total + 15) >> 4) + 1;
+			CK(cudaMemcpyAsync(feed->d_words, feed->h_words, (size_t)n_w * 4, cudaMemcpyHostToDevice, c.st));
+			k_unpack_nt4<<<(unsigned)cdiv(cdiv(total, 16), 256), 256, 0, c.st>>>(feed->d_words, feed->sh, feed->d_codes, total);
+			if (feed->n_iv) k_apply_amb<<<(unsigned)cdiv(feed->n_iv * 32, 256), 256, 0, c.st>>>(feed->d_iv, feed->n_iv, feed->g0, feed->d_codes, 0, total);
+		} else {
+			CK(cudaMemcpyAsync(feed->d_ascii, feed->h_ascii, (size_t)total, cudaMemcpyHostToDevice, c.st));
+			k_encode_nt4<<<(unsigned)cdiv(cdiv(total, 16), 256), 256, 0, c.st>>>(feed->d_ascii, feed->d_codes, total);
+		}
 		feed = nullptr;
 	}
 	while ((int)c.helpers.size() < K - 1) c.helpers.push_back(make_ctx(c.device));

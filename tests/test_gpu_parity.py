@@ -1095,6 +1095,11 @@ def test_packed_reads_map_like_ascii_reads(lib, monkeypatch):
     monkeypatch.delenv("MB_FEED_MIN_BYTES")
     same(al.map_packed(pk), "sequential pieces")
     monkeypatch.delenv("MB_PIECE_BASES")
+    # a batch cut into concurrent sub-batches finishes the upload before the pieces start (packed words included)
+    monkeypatch.setenv("MB_PARTS", "2"); monkeypatch.setenv("MB_PARTS_MIN_READS", "4"); monkeypatch.setenv("MB_FEED_MIN_BYTES", "1")
+    same(al.map_packed(pk), "two concurrent sub-batches, piecewise upload requested")
+    for k in ("MB_PARTS", "MB_PARTS_MIN_READS", "MB_FEED_MIN_BYTES"):
+        monkeypatch.delenv(k)
     # a batch of one empty read, and the empty batch
     for reads0 in ([np.zeros(0, np.uint8)], []):
         c0, o0 = (np.zeros(0, np.uint8), np.zeros(len(reads0) + 1, np.int64))
