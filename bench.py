@@ -510,11 +510,12 @@ def main():
     e2e_stats = outs_e[-1][0]
     # the same with the ASCII reads as input (mb_map_batch: 1 B/base uploaded in pieces underneath the sketch kernels)
     step_e2e(True)
-    dt_asc, wall_asc, outs_a = timed(lambda: step_e2e(True), a.steps)
+    k_asc = max(1, min(a.steps, 3))                    # a comparison figure: a few steps are enough
+    dt_asc, wall_asc, outs_a = timed(lambda: step_e2e(True), k_asc)
     dt_asc = max(dt_asc, wall_asc)
     if not np.array_equal(np.asarray(outs_a[-1][1]), np.asarray(tot_counts)):
         raise RuntimeError("per-target counts of the ASCII end-to-end path differ from the resident path")
-    e2e_ascii = {"value": float(outs_a[-1][1].sum()) * a.steps / dt_asc / 1e9, "unit": "Gbases/s", "ms_per_step": dt_asc / a.steps * 1e3,
+    e2e_ascii = {"value": float(outs_a[-1][1].sum()) * k_asc / dt_asc / 1e9, "unit": "Gbases/s", "ms_per_step": dt_asc / k_asc * 1e3, "steps": k_asc,
                  "h2d_bytes_per_step": int(total_bases + 8 * (n_reads + 1)), "ms_h2d_exposed": outs_a[-1][0]["ms_h2d"],
                  "note": "mb_map_batch: concatenated ASCII from page-locked memory"}
 
