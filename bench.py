@@ -709,6 +709,7 @@ def main():
         out = {
             "metric": "mapped Gbases/s", "value": value, "unit": "Gbases/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": dt_value / a.steps * 1e3, "ms_per_step_wall": wall_value / a.steps * 1e3, "timing": "CUDA events on the launching stream, max over ranks", "ms_each_step_rank0": each_value_ms,
+            "ms_per_step_median_rank0": float(np.median(each_value_ms)) if each_value_ms else None,   # diagnostic: some boxes show single-step outliers
             "higher_is_better": True, "scaling": "weak" if c["per_gpu"] else "strong", "vs_baseline": None,
             "dtype": "int16x2 DP (int8-range differences) / int32 chaining / uint64 hashing", "data": "synthetic",
             "config": {"workload": workload_name(c, world), "baseline_config": c["name"], "reads_rank0": n_reads, "bases_rank0": total_bases, "bases_all_ranks": int(total_bases_all),
