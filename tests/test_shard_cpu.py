@@ -110,3 +110,91 @@ def test_two_ranks_allreduce_equals_single_process():
     for _, total, _ in got:
         assert total == want.tolist()
     assert want[:len(names)].sum() > 0
+
+
+class _TwinAligner:
+    """What shard.map_and_count_sharded needs from an aligner (map_batch + count), served by the CPU oracle behind the C ABI
+    of include/monica_b200.h (oracle/mm2o_abi.c) through the same raw ctypes calls the CUDA library gets."""
+
+    def __init__(self, names, seqs):
+        import ctypes as C
+        import abi_harness as H
+        from monica_b200 import _lib
+        self.C, self.L, self._lib = C, H.oracle_library(), _lib
+        self.opt = _lib.Opt()
+        assert self.L.mb_opt_init(C.byref(self.opt)) == 0
+        n = len(names)
+        self._arrs = [np.ascontiguousarray(s, dtype=np.uint8) for s in seqs]
+        c_names = (C.c_char_p * n)(*[s.encode() for s in names])
+        c_seqs = (C.c_void_p * n)(*[a.ctypes.data for a in self._arrs])
+        lens = np.array([len(a) for a in self._arrs], np.int64)
+        self.idx = C.c_void_p()
+        assert self.L.mb_index_build(0, n, c_names, c_seqs, lens.ctypes.data_as(C.c_void_p), 10, 15, C.byref(self.idx)) == 0
+        self.n_seq = n
+
+    def map_batch(self, cat=None, off=None, cigars=True):
+        C = self.C
+        cat = np.ascontiguousarray(cat, np.uint8); off = np.ascontiguousarray(off, np.int64)
+        h = C.c_void_p()
+        assert self.L.mb_map_batch_ex(self.idx, C.byref(self.opt), cat.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p),
+                                      len(off) - 1, 3 if cigars else 1, C.byref(h), None) == 0
+        return h
+
+    def count(self, hits, mapq_min, mode):
+        C = self.C
+        m = {"basic": 0, "query_length": 1, "matching": 2}.get(mode, -1)
+        counts, ncls = np.zeros(self.n_seq, np.int64), np.zeros(3, np.int64)
+        assert self.L.mb_count(self.idx, hits, mapq_min, m, counts.ctypes.data_as(C.c_void_p), ncls.ctypes.data_as(C.c_void_p), None, None) == 0
+        return counts, ncls, None, None
+
+
+def _worker_product(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from monica_b200 import synth
+        from monica_b200.shard import map_and_count_sharded
+        from test_shard_cpu import _TwinAligner
+        names, seqs = synth.make_genomes(3, 3, 40000, strain_frac=0.34)
+        reads, _ = synth.simulate_reads(4, seqs, 24, 2000, 0.10, junk_frac=0.1)
+        cat, off = synth.concat_reads(reads)
+        al = _TwinAligner(names, seqs)
+        out = {}
+        for mode in ("basic", "query_length", "matching"):
+            counts, ncls, _ = map_and_count_sharded(al, cat, off, mode=mode, mapq_min=60)   # this rank's share, then the all-reduce
+            out[mode] = (np.asarray(counts).tolist(), np.asarray(ncls).tolist())
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_product_sharding_function_over_gloo_equals_one_process():
+    """monica_b200.shard.map_and_count_sharded itself, world_size 2 over gloo: every rank maps its share through the C ABI
+    (served here by the oracle twin: no GPU), counts with mb_count, and the one all-reduce must give every rank the counts of
+    the unsharded batch in all three modes."""
+    import torch.multiprocessing as mp
+    from monica_b200 import synth
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_product, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    names, seqs = synth.make_genomes(3, 3, 40000, strain_frac=0.34)
+    reads, _ = synth.simulate_reads(4, seqs, 24, 2000, 0.10, junk_frac=0.1)
+    cat, off = synth.concat_reads(reads)
+    al = _TwinAligner(names, seqs)
+    h = al.map_batch(cat=cat, off=off)
+    assert sorted(g[0] for g in got) == [0, 1]
+    for mode in ("basic", "query_length", "matching"):
+        counts, ncls, _, _ = al.count(h, 60, mode)
+        assert counts.sum() > 0 and ncls.sum() == len(reads)
+        for _, out in got:
+            assert out[mode] == (counts.tolist(), ncls.tolist()), mode
