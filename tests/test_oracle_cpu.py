@@ -319,3 +319,120 @@ def test_extd2_simd_core_equals_scalar(oracle):
                         assert np.array_equal(a[k], b[k]), (ql, tl, hex(flag), w, k)
     finally:
         oracle.set_simd(True)
+
+
+def test_chain_dp_equals_the_recurrence_written_out_in_python(oracle, small_case):
+    """The chaining DP (chain.c mm_chain_dp, 2.17 form) restated a SECOND time, in plain Python straight from the recurrence
+    as SURVEY.md Appendix A.4 writes it, and held against the f / p / v arrays the C oracle traces for real reads: anchors of
+    both strands and several references, reads with repeats (the max_skip break), the max_iter window, float32 avg_qspan and the
+    double-precision gap cost truncated to int.  Independent of oracle/mm2o_map.c apart from the shared recollection."""
+    names, seqs, reads = small_case
+    oidx = oracle.Index(names, seqs)
+    opt = oidx.opt
+    max_dist = opt.max_gap                      # max_gap_ref = -1: both chain gaps are max_gap (map.c mm_map_frag)
+    bw, max_skip, max_iter = opt.bw, opt.max_chain_skip, opt.max_chain_iter
+    checked = n_break = 0
+    for r in reads[:26]:
+        _, _, tr = oidx.map(r, trace=True)
+        a = tr["anchors"]
+        n = len(a)
+        if n == 0:
+            continue
+        assert len(tr["f"]) == n
+        X = [int(v) for v in a[:, 0]]
+        Y = [int(v) for v in a[:, 1]]
+        span = [(y >> 32) & 0xff for y in Y]
+        qpos = [((y & 0xffffffff) ^ 0x80000000) - 0x80000000 for y in Y]     # (int32_t)a[i].y
+        avg_qspan = float(np.float32(sum(span)) / np.float32(n))             # (float)sum / n, then promoted in the product
+        f, p, v, t = [0] * n, [-1] * n, [0] * n, [0] * n
+        st = 0
+        for i in range(n):
+            while st < i and X[i] > X[st] + max_dist:
+                st += 1
+            if i - st > max_iter:
+                st = i - max_iter
+            max_f, max_j, n_skip = span[i], -1, 0
+            for j in range(i - 1, st - 1, -1):
+                dr, dq = X[i] - X[j], qpos[i] - qpos[j]
+                if dr == 0 or dq <= 0:
+                    continue
+                if dq > max_dist:
+                    continue
+                dd = abs(dr - dq)
+                if dd > bw:
+                    continue
+                min_d = min(dq, dr)
+                sc = span[i] if min_d > span[i] else min_d
+                log_dd = dd.bit_length() - 1 if dd else 0
+                sc -= int(dd * .01 * avg_qspan) + (log_dd >> 1)
+                sc += f[j]
+                if sc > max_f:
+                    max_f, max_j = sc, j
+                    if n_skip > 0:
+                        n_skip -= 1
+                elif t[j] == i:
+                    n_skip += 1
+                    if n_skip > max_skip:
+                        n_break += 1
+                        break
+                if p[j] >= 0:
+                    t[p[j]] = i
+            f[i], p[i] = max_f, max_j
+            v[i] = v[max_j] if max_j >= 0 and v[max_j] > max_f else max_f
+        assert np.array_equal(np.array(f, np.int32), tr["f"]), "f"
+        assert np.array_equal(np.array(p, np.int32), tr["p"]), "p"
+        assert np.array_equal(np.array(v, np.int32), tr["v"]), "v"
+        checked += n
+    assert checked > 5000
+
+
+def test_mapq_equals_the_formula_written_out_in_float32(oracle, small_case):
+    """mm_set_mapq (hit.c, 2.17) a second time, in numpy float32 one rounding per operation, from the formula as SURVEY.md
+    Appendix A.7 states it (uniq_ratio, pen_s1, pen_cm, the dp_max2 branch with its BWA-like cap, the n_sub penalty, the clamp
+    to [0, 60] and the 0 -> 1 rule), evaluated on the fields the oracle reports for real reads and compared with its MAPQ.
+    The simulated reads only: the hand-shaped edge reads may carry inversion hits, whose MAPQ comes from mm_set_inv_mapq."""
+    from monica_b200 import synth
+    names, seqs, reads = small_case
+    n_edge = len(synth.edge_reads(13, seqs))
+    oidx = oracle.Index(names, seqs)
+    f32 = np.float32
+    match_sc, min_chain_sc = oidx.opt.a, oidx.opt.min_chain_score
+
+    def logf(x):
+        return oracle.logf_range(int(np.array([x], np.float32).view(np.uint32)[0]), 1)[0]
+
+    n_checked = n_lt60 = n_branch2 = 0
+    for r in reads[n_edge:]:
+        hits, stats = oidx.map(r)
+        if not hits:
+            continue
+        sum_sc = sum(h["score"] for h in hits if h["parent"] == h["id"])
+        uniq_ratio = f32(sum_sc) / f32(sum_sc + stats["rep_len"])
+        for h in hits:
+            if h["parent"] != h["id"]:
+                want = 0
+            else:
+                pen_s1 = (f32(1.0) if h["score"] > 100 else f32(0.01) * f32(h["score"])) * uniq_ratio
+                pen_cm = f32(1.0) if h["cnt"] > 10 else f32(0.1) * f32(h["cnt"])
+                pen_cm = pen_s1 if pen_s1 < pen_cm else pen_cm
+                subsc = max(h["subsc"], min_chain_sc)
+                identity = f32(h["mlen"]) / f32(h["blen"])
+                lg = logf(f32(h["dp_max"]) / f32(match_sc))
+                if h["dp_max2"] > 0 and h["dp_max"] > 0:
+                    n_branch2 += 1
+                    x = f32(h["dp_max2"]) * f32(subsc) / f32(h["dp_max"]) / f32(h["score0"])
+                    mapq = int(identity * pen_cm * f32(40.0) * (f32(1.0) - x * x) * lg)
+                    alt = int(f32(6.02) * identity * identity * f32(h["dp_max"] - h["dp_max2"]) / f32(match_sc) + f32(.499))
+                    mapq = min(mapq, alt)
+                else:
+                    x = f32(subsc) / f32(h["score0"])
+                    mapq = int(identity * pen_cm * f32(40.0) * (f32(1.0) - x) * lg)
+                mapq -= int(f32(4.343) * logf(f32(h["n_sub"] + 1)) + f32(.499))
+                mapq = min(max(mapq, 0), 60)
+                if h["dp_max"] > h["dp_max2"] and mapq == 0:
+                    mapq = 1
+                want = mapq
+            assert h["mapq"] == want, (h, want)
+            n_checked += 1
+            n_lt60 += 0 < want < 60
+    assert n_checked >= 30 and n_lt60 >= 1 and n_branch2 >= 1
