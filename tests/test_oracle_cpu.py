@@ -436,3 +436,93 @@ def test_mapq_equals_the_formula_written_out_in_float32(oracle, small_case):
             n_checked += 1
             n_lt60 += 0 < want < 60
     assert n_checked >= 30 and n_lt60 >= 1 and n_branch2 >= 1
+
+
+def test_hit_fields_follow_from_the_cigar_and_the_sequences(oracle, small_case):
+    """mlen, blen, NM (what monica's best_hit divides: aligner.py:195,217,328-339) and dp_max recomputed in plain Python from
+    each hit's CIGAR and the two sequences it claims to align (mm_update_extra's definitions: M columns with equal bases count
+    into mlen, ambiguous columns into neither mlen nor blen, NM = blen - mlen + n_ambi; dp_max = the best running score with
+    the (q, e) gap cost, floored at 0), for hits on both strands, secondaries and split regions of the small case."""
+    names, seqs, reads = small_case
+    oidx = oracle.Index(names, seqs)
+    opt = oidx.opt
+    tab = np.full(256, 4, np.uint8)
+    for ch, val in (("A", 0), ("C", 1), ("G", 2), ("T", 3), ("U", 3)):
+        tab[ord(ch)] = tab[ord(ch.lower())] = val
+    ref = [tab[np.frombuffer(bytes(s), np.uint8)] if not isinstance(s, np.ndarray) else tab[s] for s in seqs]
+    n_hits = n_rev = 0
+    for r in reads:
+        q = tab[np.asarray(r, np.uint8)]
+        qrc = np.where(q[::-1] < 4, 3 - q[::-1], 4).astype(np.uint8)
+        hits, _ = oidx.map(r)
+        for h in hits:
+            qq = (qrc[len(q) - h["qe"]:len(q) - h["qs"]] if h["rev"] else q[h["qs"]:h["qe"]])
+            tt = ref[h["rid"]][h["rs"]:h["re"]]
+            qo = to = 0
+            mlen = blen = n_ambi = s = best = 0
+            for c in h["cigar"]:
+                op, ln = int(c) & 0xf, int(c) >> 4
+                if op == 0:
+                    a, b = qq[qo:qo + ln], tt[to:to + ln]
+                    amb = (a > 3) | (b > 3)
+                    eq = (a == b) & ~amb
+                    mlen += int(eq.sum()); blen += ln - int(amb.sum()); n_ambi += int(amb.sum())
+                    for am, e_ in zip(amb.tolist(), eq.tolist()):
+                        s += -opt.sc_ambi if am else (opt.a if e_ else -opt.b)
+                        if s < 0:
+                            s = 0
+                        elif s > best:
+                            best = s
+                    qo += ln; to += ln
+                else:
+                    seg = qq[qo:qo + ln] if op == 1 else tt[to:to + ln]
+                    amb = int((seg > 3).sum())
+                    blen += ln - amb; n_ambi += amb
+                    s = max(s - (opt.q + opt.e * ln), 0)
+                    if op == 1:
+                        qo += ln
+                    else:
+                        to += ln
+            assert (qo, to) == (len(qq), len(tt))
+            assert (h["mlen"], h["blen"], h["nm"], h["dp_max"]) == (mlen, blen, blen - mlen + n_ambi, best), h
+            n_hits += 1; n_rev += h["rev"]
+    assert n_hits > 50 and 5 < n_rev < n_hits - 5
+
+
+def test_cigars_are_in_mm_fix_cigar_normal_form(oracle, small_case):
+    """What mm_fix_cigar (align.c) guarantees, checked as properties of every final CIGAR instead of by re-running it: no
+    zero-length ops, no two neighbouring ops of the same kind, first and last op are M, and every indel that follows an M sits
+    at its LEFTMOST position (the base before the gap differs from the gap's last base on the gapped sequence -- otherwise
+    upstream would have shifted it one further left)."""
+    names, seqs, reads = small_case
+    oidx = oracle.Index(names, seqs)
+    tab = np.full(256, 4, np.uint8)
+    for ch, val in (("A", 0), ("C", 1), ("G", 2), ("T", 3)):
+        tab[ord(ch)] = tab[ord(ch.lower())] = val
+    ref = [tab[np.asarray(s, np.uint8)] for s in seqs]
+    n_indel = 0
+    for r in reads:
+        q = tab[np.asarray(r, np.uint8)]
+        qrc = np.where(q[::-1] < 4, 3 - q[::-1], 4).astype(np.uint8)
+        for h in oidx.map(r)[0]:
+            qq = qrc[len(q) - h["qe"]:len(q) - h["qs"]] if h["rev"] else q[h["qs"]:h["qe"]]
+            tt = ref[h["rid"]][h["rs"]:h["re"]]
+            ops = [(int(c) & 0xf, int(c) >> 4) for c in h["cigar"]]
+            assert ops and ops[0][0] == 0 and ops[-1][0] == 0 and all(ln > 0 for _, ln in ops)
+            assert all(ops[k][0] != ops[k - 1][0] for k in range(1, len(ops)))
+            qo = to = 0
+            prev = None
+            for op, ln in ops:
+                if op == 0:
+                    qo += ln; to += ln
+                else:
+                    seq, at = (qq, qo) if op == 1 else (tt, to)
+                    if prev == 0:
+                        assert seq[at - 1] != seq[at + ln - 1], (h["rid"], h["qs"], op, ln, at)
+                        n_indel += 1
+                    if op == 1:
+                        qo += ln
+                    else:
+                        to += ln
+                prev = op
+    assert n_indel > 5000
