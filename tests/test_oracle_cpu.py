@@ -526,3 +526,47 @@ def test_cigars_are_in_mm_fix_cigar_normal_form(oracle, small_case):
                         to += ln
                 prev = op
     assert n_indel > 5000
+
+
+def test_region_logic_properties_of_the_final_hits(oracle):
+    """hit.c's region logic checked through what it must leave behind, on strain copies (secondaries) and chimeric reads
+    (several primaries): primaries overlap each other on the query by at most mask_level x the shorter one (mm_set_parent);
+    every secondary hangs off a primary that it overlaps, with score >= pri_ratio x the parent's or within 2k of it, at most
+    best_n of them per read (mm_select_sub); is_primary == (id == parent) and only primaries carry a non-zero MAPQ
+    (mm_set_mapq); hits come ordered by dp_max within what mm_hit_sort compares."""
+    from monica_b200 import synth
+    names, seqs = synth.make_genomes(11, 3, 60000, strain_frac=0.34)       # the small case's genomes: one is a close strain copy
+    plain, _ = synth.simulate_reads(32, seqs, 100, 2500, 0.10, junk_frac=0.05)
+    rng = np.random.default_rng(33)
+    chim = [np.concatenate([plain[int(a)], plain[int(b)]]) for a, b in rng.integers(0, len(plain), (30, 2))]
+    reads = plain + chim
+    oidx = oracle.Index(names, seqs)
+    opt = oidx.opt
+    cat, off = synth.concat_reads(reads)
+    all_hits, _ = oidx.map_batch(cat, off, n_threads=4)
+    n_pairs = n_sec = n_multi = 0
+    for hits in all_hits:
+        byid = {h["id"]: h for h in hits}
+        assert len(byid) == len(hits)
+        pri = [h for h in hits if h["id"] == h["parent"]]
+        n_multi += len(pri) > 1
+        for h in hits:
+            assert h["is_primary"] == (h["id"] == h["parent"])
+            if not h["is_primary"]:
+                assert h["mapq"] == 0
+        for a in range(len(pri)):
+            for b in range(a + 1, len(pri)):
+                x, y = pri[a], pri[b]
+                ol = min(x["qe"], y["qe"]) - max(x["qs"], y["qs"])
+                assert ol <= opt.mask_level * min(x["qe"] - x["qs"], y["qe"] - y["qs"]), (x, y)
+                n_pairs += 1
+        sec = [h for h in hits if h["id"] != h["parent"]]
+        assert len(sec) <= opt.best_n
+        for h in sec:
+            p = byid[h["parent"]]
+            assert p["id"] == p["parent"]
+            assert min(h["qe"], p["qe"]) > max(h["qs"], p["qs"])
+            # (float32 like upstream: 810 * 0.8f rounds to 648.0f, so a secondary with score 648 stays)
+            assert np.float32(h["score"]) >= np.float32(p["score"]) * np.float32(opt.pri_ratio) or h["score"] + 2 * 15 >= p["score"], (h, p)
+            n_sec += 1
+    assert n_pairs >= 20 and n_sec >= 30 and n_multi >= 15, (n_pairs, n_sec, n_multi)
