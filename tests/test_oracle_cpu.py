@@ -570,3 +570,39 @@ def test_region_logic_properties_of_the_final_hits(oracle):
             assert np.float32(h["score"]) >= np.float32(p["score"]) * np.float32(opt.pri_ratio) or h["score"] + 2 * 15 >= p["score"], (h, p)
             n_sec += 1
     assert n_pairs >= 20 and n_sec >= 30 and n_multi >= 15, (n_pairs, n_sec, n_multi)
+
+
+def test_anchors_equal_seeding_from_the_definition(oracle, small_case):
+    """Index, lookup, the mid_occ filter and the anchor coordinates (index.c mm_idx_get, map.c collect_seed_hits) a second time
+    in plain Python: a dict from minimizer hash to every (contig, position, strand) of the reference sketches, every query
+    minimizer whose hash occurs fewer than mid_occ times paired with each occurrence, forward anchors (x = rid<<32 | rpos,
+    y = span<<32 | qpos) and reverse ones (bit 63; qpos mirrored to the reverse-complemented read) as SURVEY Appendix A.3
+    gives them.  Compared as multisets with the anchors the C oracle feeds to chaining (flag bits above the span masked)."""
+    names, seqs, reads = small_case
+    oidx = oracle.Index(names, seqs)
+    occ = {}
+    for rid, s in enumerate(seqs):
+        for x, y in oracle.sketch(s, 10, 15, rid).tolist():
+            occ.setdefault(x >> 8, []).append((rid, (y & 0xffffffff) >> 1, y & 1))
+    mid_occ = oidx.mid_occ
+    n_anchor = n_dropped = 0
+    for r in reads[:30]:
+        _, _, tr = oidx.map(r, trace=True)
+        want = []
+        qlen = len(r)
+        for x, y in tr["mini"].tolist():
+            hits = occ.get(x >> 8, [])
+            if len(hits) >= mid_occ:
+                n_dropped += len(hits) > 0
+                continue
+            span, qpos, qstrand = x & 0xff, (y & 0xffffffff) >> 1, y & 1
+            for rid, rpos, rstrand in hits:
+                if rstrand == qstrand:
+                    want.append((rid << 32 | rpos, span << 32 | qpos))
+                else:
+                    want.append((1 << 63 | rid << 32 | rpos, span << 32 | (qlen - (qpos + 1 - span) - 1)))
+        got = [(int(ax), int(ay) & 0xffffffffff) for ax, ay in tr["anchors"].tolist()]
+        assert sorted(got) == sorted(want)
+        assert [g[0] for g in got] == sorted(g[0] for g in got)      # radix_sort_128x: ascending x
+        n_anchor += len(got)
+    assert n_anchor > 5000 and n_dropped > 0
