@@ -606,3 +606,77 @@ def test_anchors_equal_seeding_from_the_definition(oracle, small_case):
         assert [g[0] for g in got] == sorted(g[0] for g in got)      # radix_sort_128x: ascending x
         n_anchor += len(got)
     assert n_anchor > 5000 and n_dropped > 0
+
+
+def test_chain_backtrack_equals_the_procedure_written_out_in_python(oracle, small_case):
+    """The second half of mm_chain_dp (chain.c, 2.17) a second time in plain Python, starting from the traced f / p / v: chain
+    ends are the anchors nobody chose as predecessor with v >= min_chain_score; each end walks back to its f peak; peaks are
+    taken best first (keys f<<32 | index are unique, so the sort has one answer); a backtrack stops at an anchor that is
+    already used and then keeps score - f[that anchor]; chains need min_cnt anchors and min_chain_score; the survivors are
+    emitted oldest anchor first and ordered by their first anchor's x.  Compared with the oracle's u[] and chained anchors."""
+    names, seqs, reads = small_case
+    oidx = oracle.Index(names, seqs)
+    min_sc, min_cnt = oidx.opt.min_chain_score, oidx.opt.min_cnt
+    # plus a read across a tandem repeat (12 diverged copies of a 400-base unit): many anchors share predecessors there, so
+    # backtracks run into anchors that better chains have taken
+    rng = np.random.default_rng(5)
+
+    def mutated(s, rate):
+        s = s.copy(); m = rng.random(len(s)) < rate; s[m] = rng.integers(0, 4, int(m.sum())); return s
+    unit = rng.integers(0, 4, 400)
+    g = np.concatenate([rng.integers(0, 4, 20000)] + [mutated(unit, 0.03) for _ in range(12)] + [rng.integers(0, 4, 20000)])
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    ridx = oracle.Index(["Sp:ACC1"], [acgt[g]])
+    cases = [(oidx, r) for r in reads] + [(ridx, acgt[mutated(g[18000:27500], 0.08)])]
+    n_chains = n_cut = 0
+    for ix, r in cases:
+        _, _, tr = ix.map(r, trace=True)
+        a, f, p, v = tr["anchors"].tolist(), tr["f"].tolist(), tr["p"].tolist(), tr["v"].tolist()
+        n = len(a)
+        if n == 0:
+            assert len(tr["u"]) == 0
+            continue
+        used_as_pred = [False] * n
+        for i in range(n):
+            if p[i] >= 0:
+                used_as_pred[p[i]] = True
+        ends = []
+        for i in range(n):
+            if not used_as_pred[i] and v[i] >= min_sc:
+                j = i
+                while j >= 0 and f[j] < v[j]:
+                    j = p[j]
+                if j < 0:
+                    j = i
+                ends.append((f[j], j))
+        ends.sort(reverse=True)
+        taken = [False] * n
+        chains = []                                   # (score, [anchor indices, newest first])
+        for sc, j in ends:
+            idx = []
+            while True:
+                idx.append(j); taken[j] = True
+                j = p[j]
+                if j < 0 or taken[j]:
+                    break
+            keep = None
+            if j < 0:
+                keep = sc
+            else:
+                n_cut += 1                            # ran into an anchor of a better chain
+                if sc - f[j] >= min_sc:
+                    keep = sc - f[j]
+            if keep is not None and len(idx) >= min_cnt:
+                chains.append((keep, idx))
+            # (upstream leaves t[] set for a dropped chain too: its anchors keep blocking later backtracks)
+        firsts = [a[idx[-1]][0] for _, idx in chains]
+        order = sorted(range(len(chains)), key=lambda k: firsts[k])
+        want_u = [chains[k][0] << 32 | len(chains[k][1]) for k in order]
+        want_a = [a[i] for k in order for i in reversed(chains[k][1])]
+        got_u, got_a = [int(x) for x in tr["u"]], tr["chained"].tolist()
+        if len(set(firsts)) == len(firsts):
+            assert got_u == want_u and got_a == want_a
+        else:     # two chains start at the same x: upstream's unstable sort decides their order
+            assert sorted(got_u) == sorted(want_u) and sorted(map(tuple, got_a)) == sorted(map(tuple, want_a))
+        n_chains += len(chains)
+    assert n_chains >= 40 and n_cut >= 1
