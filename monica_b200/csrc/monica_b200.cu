@@ -554,7 +554,7 @@ extern "C" void mb_index_free(mb_index_t *ix)
 }
 extern "C" int mb_index_n_seq(const mb_index_t *ix) { return ix ? (int)ix->names.size() : 0; }
 extern "C" const char *mb_index_seq_name(const mb_index_t *ix, int rid) { return (ix && rid >= 0 && rid < (int)ix->names.size()) ? ix->names[rid].c_str() : nullptr; }
-extern "C" int64_t mb_index_seq_len(const mb_index_t *ix, int rid) { return (ix && rid >= 0 && rid < (int)ix->lens.size()) ? ix->lens[rid] : -1; }
+extern "C" int64_t mb_index_seq_len(const mb_index_t *ix, int rid) { return (ix && rid >= 0 && rid < (int)ix->lens.size()) ? (int64_t)ix->lens[rid] : (int64_t)-1; }
 extern "C" int mb_index_mid_occ(const mb_index_t *ix) { return ix ? ix->mid_occ : 0; }
 extern "C" int mb_index_kw(const mb_index_t *ix, int *k, int *w) { if (!ix) return MB_ERR_ARG; if (k) *k = ix->k; if (w) *w = ix->w; return MB_OK; }
 extern "C" int64_t mb_index_n_minimizers(const mb_index_t *ix) { return ix ? ix->n_mini : 0; }

@@ -43,6 +43,23 @@ def test_no_device_fails_loudly():
     assert ei.value.code == -2 and "no CPU fallback" in str(ei.value)
 
 
+def test_null_handle_accessors_answer_like_the_oracle_twin():
+    """Accessors on a null index handle take no device: both libraries behind include/monica_b200.h must give the same
+    out-of-range answers (mb_index_seq_len: -1 as int64, not a wrapped uint32)."""
+    import ctypes as C
+    from monica_b200 import _lib
+    twin = C.CDLL(os.path.join(ROOT, "oracle", "_build", "libmonica_b200_oracle.so"))
+    for L in (_lib.lib(), twin):
+        L.mb_index_seq_len.argtypes = [C.c_void_p, C.c_int]
+        L.mb_index_seq_len.restype = C.c_int64
+        L.mb_index_n_seq.argtypes = [C.c_void_p]
+        L.mb_index_seq_name.argtypes = [C.c_void_p, C.c_int]
+        L.mb_index_seq_name.restype = C.c_char_p
+        assert L.mb_index_seq_len(None, 0) == -1
+        assert L.mb_index_n_seq(None) == 0
+        assert L.mb_index_seq_name(None, 0) is None
+
+
 def test_product_never_imports_oracle():
     """The shipped package must not reference oracle/ (the judge checks the same thing)."""
     pkg = os.path.join(ROOT, "monica_b200")
