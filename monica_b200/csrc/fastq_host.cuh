@@ -69,6 +69,7 @@ static bool parse_strict(const char *s, int64_t N, int64_t p, int64_t stop, std:
 		Rec r; r.head = p + 1, r.head_len = e1 - (p + 1), r.seq = e1 + 1, r.seq_len = e2 - (e1 + 1), r.qual = qb, r.qual_len = e4 - qb, r.end = e4 + 1;
 		if (r.qual_len != r.seq_len || r.seq_len == 0 || r.head_len <= 0) return false;
 		if (s[e1 - 1] == '\r' || s[e2 - 1] == '\r' || s[e4 - 1] == '\r') return false;
+		if (s[e1 - 1] == ' ' || s[e1 - 1] == '\t' || s[e1 - 1] == '\v' || s[e1 - 1] == '\f') return false;   // Bio strips the title: general parser
 		int32_t idl = 0;
 		while (idl < r.head_len && s[r.head + idl] != ' ' && s[r.head + idl] != '\t') ++idl;
 		r.id_len = idl;
@@ -184,7 +185,7 @@ extern "C" int mb_fastq_load(const char *path, mb_fastq_t **out)
 			std::vector<char> buf(1 << 22);
 			int n;
 			while ((n = gzread(fp, buf.data(), (unsigned)buf.size())) > 0) fq->owned.append(buf.data(), (size_t)n);
-			const bool bad = n < 0;
+			const bool bad = n < 0 || !mb_gz_clean_eof(fp);   // a truncated .gz ends with n == 0 and Z_BUF_ERROR
 			gzclose(fp);
 			if (bad) throw mb_error(MB_ERR_IO, std::string("read error in ") + path);
 			fq->raw = fq->owned.data(), fq->raw_len = fq->owned.size();
@@ -229,10 +230,14 @@ static void fastq_parse_sequential(mb_fastq *fq, const char *path)
 		if (le == p) { p = e + 1; continue; }                          // blank line
 		if (s[p] != '@') throw mb_error(MB_ERR_IO, std::string("unexpected line in FASTQ input: ") + path);
 		const int64_t rec_begin = p;
-		const int64_t hb = p + 1, hl = le - hb;
+		const int64_t hb = p + 1;
+		int64_t hl = le - hb;
+		bool canonical = le == e;                                       // no '\r'
+		while (hl > 0 && (s[hb + hl - 1] == ' ' || s[hb + hl - 1] == '\t' || s[hb + hl - 1] == '\v' || s[hb + hl - 1] == '\f' || s[hb + hl - 1] == '\r')) {
+			--hl; canonical = false;                                    // Bio.SeqIO right-strips the title line
+		}
 		int32_t idl = 0;
 		while (idl < hl && s[hb + idl] != ' ' && s[hb + idl] != '\t') ++idl;
-		bool canonical = le == e;                                       // no '\r'
 		p = e + 1;
 		// sequence lines until '+'
 		int64_t seq_len = 0; int n_seq_lines = 0;

@@ -28,6 +28,15 @@
 #include "dp_band.cuh"
 #include "align_cta.cuh"
 
+// zlib reports a stream that ends before its trailer (a truncated .gz) through gzerror() only: gzread() hands out the bytes
+// it could inflate and then returns 0 like at a proper end of file.
+static inline bool mb_gz_clean_eof(gzFile fp)
+{
+	int e = Z_OK;
+	gzerror(fp, &e);
+	return e == Z_OK || e == Z_STREAM_END;
+}
+
 thread_local std::string g_mb_err;
 static thread_local std::chrono::steady_clock::time_point g_dbg_t0 = std::chrono::steady_clock::now();
 
@@ -413,7 +422,7 @@ extern "C" int mb_index_build_fasta(int device, const char *path, int w, int k, 
 			p = nl + 1;
 		}
 	}
-	const bool read_ok = n == 0;
+	const bool read_ok = n == 0 && mb_gz_clean_eof(fp);
 	if (!carry.empty()) take_line(carry.data(), carry.size());
 	gzclose(fp);
 	if (!read_ok) throw mb_error(MB_ERR_IO, std::string("read error in ") + path);
@@ -2592,7 +2601,7 @@ extern "C" int mb_db_build(const char *out_path, int32_t n_genomes, const char *
 				if (buf[i] == '\n') { take_line(line); line.clear(); } else line.push_back(buf[i]);
 			}
 		}
-		const bool read_ok = n == 0;
+		const bool read_ok = n == 0 && mb_gz_clean_eof(in);
 		take_line(line); flush_record();
 		gzclose(in);
 		if (!read_ok) { gzclose(out); throw mb_error(MB_ERR_IO, std::string("read failed: ") + genome_paths[g]); }

@@ -24,8 +24,24 @@ def _open(fn):
     return open(fn, "r"), True
 
 
+def _split_title(head):
+    """kseq-style split of a title line: the name ends at the first blank or tab, the rest is the comment."""
+    name, _, comment = head.partition(" ")
+    if "\t" in name:
+        name, _, c2 = name.partition("\t")
+        comment = c2 + (" " + comment if comment else "")
+    return name, comment
+
+
 def parse_fastx(fn):
     """Yield (name, comment, seq, qual) with qual None for FASTA."""
+    for head, seq, qual in _iter_records(fn):
+        name, comment = _split_title(head)
+        yield name, comment, seq, qual
+
+
+def _iter_records(fn):
+    """Yield (title line without its marker and line end, seq, qual) with qual None for FASTA."""
     fh, close = _open(fn)
     try:
         line = fh.readline()
@@ -48,11 +64,7 @@ def parse_fastx(fn):
                     if not q:
                         break
                     qual += q.rstrip("\r\n")
-                name, _, comment = head.partition(" ")
-                if "\t" in name:
-                    name, _, c2 = name.partition("\t")
-                    comment = c2 + (" " + comment if comment else "")
-                yield name, comment, seq, qual
+                yield head, seq, qual
                 line = fh.readline()
             elif line[0] == ">":
                 head = line[1:]
@@ -61,8 +73,7 @@ def parse_fastx(fn):
                 while line and not line.startswith(">"):
                     parts.append(line.strip())
                     line = fh.readline()
-                name, _, comment = head.partition(" ")
-                yield name, comment, "".join(parts), None
+                yield head, "".join(parts), None
             else:
                 raise ValueError(f"unexpected line in FASTA/FASTQ input: {line[:40]!r}")
     finally:
@@ -100,9 +111,11 @@ def parse(handle, fmt="fastq"):
     """Bio.SeqIO.parse(handle, 'fastq') look-alike."""
     if fmt not in ("fastq", "fasta"):
         raise ValueError("only fastq/fasta are supported")
-    for name, comment, seq, qual in parse_fastx(handle):
-        desc = name + (" " + comment if comment else "")
-        yield SeqRecord(name, desc, seq, qual if qual is not None else "")
+    for head, seq, qual in _iter_records(handle):
+        # Bio.SeqIO.QualityIO: description = the title line right-stripped (inner tabs kept), id = its first word
+        desc = head.rstrip()
+        words = desc.split(None, 1)
+        yield SeqRecord(words[0] if words else "", desc, seq, qual if qual is not None else "")
 
 
 def write(records, handle, fmt="fastq"):

@@ -373,3 +373,121 @@ def test_read_packer_equals_nt4_table(n_threads):
     bad = np.array([1, 5], np.int64)
     pk = C.c_void_p()
     assert L.mb_reads_pack(cat.ctypes.data, bad.ctypes.data, 1, 1, C.byref(pk)) == -1   # MB_ERR_ARG: offsets must start at 0
+
+
+_ODD_FASTQ = {
+    "empty": b"",
+    "only_newlines": b"\n\n\n",
+    "no_trailing_newline": b"@r1\nACGT\n+\nIIII",
+    "crlf": b"@r1 d\r\nACGT\r\n+\r\nIIII\r\n@r2\r\nGG\r\n+\r\nII\r\n",
+    "cut_after_sequence": b"@r1\nACGT\n",
+    "cut_after_plus": b"@r1\nACGT\n+\n",
+    "quality_too_short": b"@r1\nACGT\n+\nII\n",
+    "header_only": b"@r1",
+    "quality_starts_with_at": b"@r1\nACGT\n+\n@III\n@r2\nAC\n+\n@I\n",
+    "empty_sequence": b"@r1\n\n+\n\n@r2\nAC\n+\nII\n",
+    "tab_in_title": b"@r1\tx y\nACGT\n+\nIIII\n",
+    "title_ends_in_blanks": b"@r1 d  \nACGT\n+\nIIII\n@r2\t\nAC\n+\nII\n",
+    "lower_case_and_iupac": b"@r1\nacgtnRYKM\n+\nIIIIIIIII\n",
+    "blank_lines_between": b"@r1\nACGT\n+\nIIII\n\n\n@r2\nAC\n+\nII\n",
+    "long_title": b"@" + b"x" * 100000 + b" c\nACGT\n+\nIIII\n",
+}
+
+
+def _native_fastq_records(path):
+    import ctypes as C
+    from monica_b200 import _lib
+    L = _lib.lib()
+    fq = C.c_void_p()
+    rc = L.mb_fastq_load(os.fsencode(str(path)), C.byref(fq))
+    if rc != 0:
+        return rc, None
+    n = L.mb_fastq_n(fq)
+    offp = C.POINTER(C.c_int64)()
+    catp = L.mb_fastq_seqs(fq, C.byref(offp))
+    off = np.ctypeslib.as_array(offp, shape=(n + 1,))
+    cat = np.ctypeslib.as_array(catp, shape=(int(off[-1]),)).tobytes() if n and off[-1] else b""
+    recs = []
+    for i in range(n):
+        ln, il = C.c_int64(), C.c_int32()
+        hp = L.mb_fastq_header(fq, i, C.byref(ln), C.byref(il))
+        head = C.string_at(hp, ln.value).decode()
+        recs.append((head[:il.value], head, cat[off[i]:off[i + 1]].decode()))
+    # route everything to "unmapped": the file a Bio.SeqIO writer would produce from these records
+    out = str(path) + ".unmapped"
+    dest = np.zeros(max(n, 1), np.int8)
+    _lib.check(L.mb_fastq_route(fq, dest.ctypes.data_as(C.c_void_p), None, None, None, os.fsencode(out), None, None))
+    L.mb_fastq_free(fq)
+    return 0, (recs, open(out, "rb").read() if os.path.exists(out) else b"")
+
+
+@pytest.mark.parametrize("case", sorted(_ODD_FASTQ))
+def test_native_fastq_loader_on_odd_input_equals_the_seqio_mirror(tmp_path, case):
+    """Cut-off, CRLF, blank-line, tabbed and blank-padded title lines: mb_fastq_load sees the records monica_b200.fastx
+    (Bio.SeqIO's rules: description = right-stripped title line, id = its first word) sees, and writes them back the same."""
+    from monica_b200 import fastx
+    p = tmp_path / "x.fastq"
+    p.write_bytes(_ODD_FASTQ[case])
+    want = list(fastx.parse(str(p), "fastq"))
+    rc, got = _native_fastq_records(p)
+    assert rc == 0
+    recs, written = got
+    assert recs == [(r.id, r.description, str(r.seq)) for r in want]
+    if all(len(r.qual) == len(r.seq) for r in want):
+        assert written.decode() == "".join(r.format_fastq() for r in want)
+
+
+def test_fastx_title_rule_is_seqio_s():
+    """Bio.SeqIO.QualityIO: description = title line right-stripped (inner tabs kept), id = first whitespace-separated word;
+    mappy.fastx_read (kseq): name up to the first blank or tab, the rest is the comment."""
+    import io
+    from monica_b200 import fastx
+    txt = "@r1\tx y  \nACGT\n+\nIIII\n"
+    (r,) = list(fastx.parse(io.StringIO(txt), "fastq"))
+    assert (r.id, r.description) == ("r1", "r1\tx y")
+    assert r.format_fastq() == "@r1\tx y\nACGT\n+\nIIII\n"
+    r.id = "Species_1"
+    assert r.format_fastq() == "@Species_1 r1\tx y\nACGT\n+\nIIII\n"
+    assert list(fastx.parse_fastx(io.StringIO(txt))) == [("r1", "x y  ", "ACGT", "IIII")]
+
+
+def test_native_loaders_refuse_a_cut_off_gzip(tmp_path):
+    """zlib hands out what it could inflate of a truncated .gz and then reports a plain end of file; the error is only in
+    gzerror().  A FASTQ cut in half must not be mapped and counted as if it were whole."""
+    import ctypes as C
+    import gzip
+    from monica_b200 import _lib
+    L = _lib.lib()
+    whole = gzip.compress(b"".join(b"@r%d\nACGTACGTAC\n+\nIIIIIIIIII\n" % i for i in range(3000)))
+    good, cut, junk = tmp_path / "good.fastq.gz", tmp_path / "cut.fastq.gz", tmp_path / "junk.fastq"
+    good.write_bytes(whole)
+    cut.write_bytes(whole[:len(whole) // 2])
+    junk.write_bytes(b"hello world\nfoo\n")
+    fq = C.c_void_p()
+    assert L.mb_fastq_load(os.fsencode(str(good)), C.byref(fq)) == 0 and L.mb_fastq_n(fq) == 3000
+    L.mb_fastq_free(fq)
+    for bad in (cut, junk):
+        fq = C.c_void_p()
+        assert L.mb_fastq_load(os.fsencode(str(bad)), C.byref(fq)) == -3          # MB_ERR_IO
+        assert os.path.basename(str(bad)).encode() in L.mb_last_error()
+
+
+def test_native_fastq_loader_large_file_with_one_odd_record(tmp_path):
+    """A file large enough for the multi-threaded four-line parser (>= 8 MB) with one blank-padded title in the middle: the
+    strict parser hands the file to the general one, and every record still equals the SeqIO mirror's."""
+    from monica_b200 import fastx
+    rng = np.random.default_rng(5)
+    seq = "".join(rng.choice(list("ACGT"), 3000))
+    p = tmp_path / "big.fastq"
+    with open(p, "w") as fh:
+        for i in range(1500):
+            title = f"read{i} ch={i % 512}" + ("  " if i == 777 else "")
+            s = seq[i % 100:] + seq[:i % 100]
+            fh.write(f"@{title}\n{s}\n+\n{'I' * len(s)}\n")
+    assert os.path.getsize(p) > (8 << 20)
+    want = list(fastx.parse(str(p), "fastq"))
+    rc, got = _native_fastq_records(p)
+    assert rc == 0
+    recs, written = got
+    assert recs == [(r.id, r.description, str(r.seq)) for r in want] and recs[777][1] == "read777 ch=265"
+    assert written.decode() == "".join(r.format_fastq() for r in want)

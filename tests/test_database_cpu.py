@@ -123,3 +123,23 @@ def test_multi_threaded_builder_equals_unmodified_reference(max_chunk):
             assert pickle.load(fh) == m_len
     finally:
         shutil.rmtree(home, ignore_errors=True)
+
+
+def test_builder_refuses_a_cut_off_genome_file(tmp_path):
+    """A genome download cut short (truncated .fna.gz) must fail the chunk, as gzip.open + SeqIO.parse does in the reference
+    (EOFError), not become a shorter genome in the database."""
+    from monica_b200 import _lib, database
+    rng = np.random.default_rng(9)
+    good = str(tmp_path / "GCF_good.fna.gz")
+    _write_genome(good, rng, 40)
+    raw = open(good, "rb").read()
+    cut = str(tmp_path / "GCF_cut.fna.gz")
+    with open(cut, "wb") as fh:
+        fh.write(raw[:len(raw) // 2])
+    out = tmp_path / "db"
+    out.mkdir()
+    lens = database.builder([(good, ("Species_0", "GCF_good.1"))], str(out), ["database", ".fna.gz"], 0)
+    assert lens["GCF_good.1"] > 0
+    with pytest.raises(_lib.MonicaB200Error) as ei:
+        database.builder([(good, ("Species_0", "GCF_good.1")), (cut, ("Species_1", "GCF_cut.1"))], str(out), ["database", ".fna.gz"], 1)
+    assert ei.value.code == -3 and "GCF_cut" in str(ei.value)
