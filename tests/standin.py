@@ -63,6 +63,7 @@ class OracleAligner:
                 return
             self._idx = O.Index(names, seqs)
             self.seq_names = list(names)
+            self._names_seqs = (list(names), list(seqs))
         except OSError:
             self._idx = None
 

@@ -117,7 +117,7 @@ def test_best_hit_equals_reference(ref_aligner):
     assert mine.best_hit([("a", 10, 100), ("b", 10, 100), ("c", 5, 100)]) == ("c", 5, 100)
 
 
-def _run(mod, names, seqs, reads, mode, two, focus, patch_mine):
+def _run(mod, names, seqs, reads, mode, two, focus, patch_mine, mta=None):
     sys.path.insert(0, GOLDEN)
     import make_golden
     wd = tempfile.mkdtemp(prefix="cmp_run_")
@@ -125,6 +125,8 @@ def _run(mod, names, seqs, reads, mode, two, focus, patch_mine):
         kw = {}
         if patch_mine:
             kw = {"indexer": {"genomes_path": os.path.join(wd, "markers")}}
+        if mta:
+            kw["mta"] = dict(mta)
         return make_golden.run_aligner(mod, wd, names, seqs, reads, mode, two, focus, kw)
     finally:
         shutil.rmtree(wd, ignore_errors=True)
@@ -491,3 +493,108 @@ def test_native_fastq_loader_large_file_with_one_odd_record(tmp_path):
     recs, written = got
     assert recs == [(r.id, r.description, str(r.seq)) for r in want] and recs[777][1] == "read777 ch=265"
     assert written.decode() == "".join(r.format_fastq() for r in want)
+
+
+def _twin_batch_aligner_class():
+    """tests/standin.OracleAligner plus the two batch calls of monica_b200.mappy_shim.Aligner that aligner()'s whole-file
+    route uses (map_batch, count), served by the oracle behind the C ABI (oracle/mm2o_abi.c) -- so the host logic of that
+    route (native FASTQ ingest, vectorised tally, native routed writers) runs on the CPU."""
+    import ctypes as C
+    import standin
+    from test_shard_cpu import _TwinAligner
+
+    class Hits:
+        pass
+
+    class TwinBatchAligner(standin.OracleAligner):
+        calls = 0
+
+        def __init__(self, *a, **kw):
+            super().__init__(*a, **kw)
+            self._twin = None
+            if self._idx is not None:
+                names, seqs = self._names_seqs
+                self._twin = _TwinAligner(names, [np.frombuffer(s if isinstance(s, bytes) else bytes(s), np.uint8) if not isinstance(s, np.ndarray) else s
+                                                  for s in seqs])
+
+        def map_batch(self, reads=None, cat=None, off=None, cigars=True):
+            type(self).calls += 1
+            L = self._twin.L
+            if reads is not None:      # the shim's other input form: a list of sequences
+                arrs = [np.frombuffer(r.encode() if isinstance(r, str) else bytes(r), np.uint8) for r in reads]
+                off = np.concatenate([[0], np.cumsum([len(a) for a in arrs])]).astype(np.int64)
+                cat = np.concatenate(arrs) if arrs else np.zeros(0, np.uint8)
+            h = self._twin.map_batch(cat=cat, off=off, cigars=cigars)
+            out = Hits()
+            out.h, out.n_reads = h, len(off) - 1
+            nh = L.mb_hits_n(h)
+            for f in ("read_idx", "rid", "mapq", "mlen", "nm", "is_primary"):
+                ptr = L.mb_hits_field(h, f.encode())
+                setattr(out, f, np.ctypeslib.as_array(ptr, shape=(nh,)).copy() if nh else np.zeros(0, np.int32))
+            return out
+
+        def count(self, hits, mapq_min, mode):
+            L = self._twin.L
+            m = {"basic": 0, "query_length": 1, "matching": 2}.get(mode, -1)
+            counts, ncls = np.zeros(self._twin.n_seq, np.int64), np.zeros(3, np.int64)
+            rcls, rbest = np.zeros(max(hits.n_reads, 1), np.int8), np.zeros(max(hits.n_reads, 1), np.int64)
+            assert L.mb_count(self._twin.idx, hits.h, mapq_min, m, counts.ctypes.data_as(C.c_void_p), ncls.ctypes.data_as(C.c_void_p),
+                              rcls.ctypes.data_as(C.c_void_p), rbest.ctypes.data_as(C.c_void_p)) == 0
+            return counts, ncls, rcls[:hits.n_reads], rbest[:hits.n_reads]
+
+    return TwinBatchAligner
+
+
+@pytest.mark.parametrize("mode,focus,overnight", [("basic", [], False), ("query_length", ["Species_1"], False), ("matching", ["Species_0"], True), (None, [], False)])
+def test_whole_file_route_equals_unmodified_reference(ref_aligner, small_case, monkeypatch, mode, focus, overnight):
+    """aligner()'s whole-file route (one native FASTQ load, one map_batch, mb_count's classes, vectorised tally, native routed
+    writers -- the route every single-index run takes on the GPU) against the UNMODIFIED reference's per-record loop: same
+    alignment dict, same bytes in every routed file.  The batch calls are served by the oracle twin of the C ABI."""
+    from monica_b200 import aligner as mine
+    names, seqs, reads = small_case
+    cls = _twin_batch_aligner_class()
+    fake = types.ModuleType("mappy")
+    fake.Aligner = cls
+    monkeypatch.setattr(mine, "mappy", fake)
+    monkeypatch.setattr(mine, "LAST_BREAKDOWN", None)
+    got = _run(mine, names, seqs, reads, mode, False, focus, True, mta={"overnight": overnight})
+    assert cls.calls >= 1 and mine.LAST_BREAKDOWN is not None, "the whole-file route was not taken"
+    want = _run(ref_aligner, names, seqs, reads, mode, False, focus, False, mta={"overnight": overnight})
+    assert got == want
+    if mode is not None:
+        assert any(v for v in got["alignment"].values())
+
+
+def test_duplicate_read_ids_leave_the_whole_file_route(ref_aligner, small_case, tmp_path, monkeypatch):
+    """Two records with one id share an entry of the reference's per-read dict (their hits are merged before best_hit): the
+    whole-file route must notice (mb_fastq_ids_unique) and hand the file to the per-record path, whose output equals the
+    unmodified reference's."""
+    import standin
+    from monica_b200 import aligner as mine
+    names, seqs, reads = small_case
+    cls = _twin_batch_aligner_class()
+    picked = reads[20:28]
+    outs = []
+    for mod, idx in ((mine, cls(names=names, seqs=[s.tobytes() for s in seqs])),
+                     (ref_aligner, standin.OracleAligner(names=names, seqs=[s.tobytes() for s in seqs]))):
+        d = tmp_path / mod.__name__.replace(".", "_")
+        for sub in ("hits", "mapped", "unmapped", "ambiguous", "focus"):
+            (d / sub).mkdir(parents=True)
+        with open(d / "s.fastq", "wb") as fh:
+            for i, r in enumerate(picked):
+                fh.write(b"@dup%d\n" % (i // 2) + r.tobytes() + b"\n+\n" + b"I" * len(r) + b"\n")     # every id twice
+        monkeypatch.setattr(mine, "LAST_BREAKDOWN", None)
+        cwd = os.getcwd()
+        os.chdir(d)
+        try:
+            res = mod.aligner("s.fastq", "s", idx, mode="query_length", hits_folder=str(d / "hits"), mapping_quality=60,
+                              focus_species=["Species_1"], mapped_folder=str(d / "mapped"), unmapped_folder=str(d / "unmapped"),
+                              ambiguous_folder=str(d / "ambiguous"), focus_folder=str(d / "focus"), last_index=True)
+        finally:
+            os.chdir(cwd)
+        files = {sub: (d / sub / "s.fastq").read_bytes() if (d / sub / "s.fastq").exists() else None for sub in ("mapped", "unmapped", "ambiguous", "focus")}
+        outs.append(({t: dict(c) for t, c in res[0].items()}, res[1], files, sorted(os.listdir(d / "hits")), (d / "s.fastq").exists()))
+        if mod is mine:
+            assert mine.LAST_BREAKDOWN is None, "a file with repeated ids went through the whole-file route"
+    assert outs[0] == outs[1]
+    assert outs[0][0], "nothing was counted"
