@@ -598,3 +598,21 @@ def test_duplicate_read_ids_leave_the_whole_file_route(ref_aligner, small_case, 
             assert mine.LAST_BREAKDOWN is None, "a file with repeated ids went through the whole-file route"
     assert outs[0] == outs[1]
     assert outs[0][0], "nothing was counted"
+
+
+@pytest.mark.parametrize("mode", ["query_length", "matching"])
+def test_two_index_carry_over_with_batch_calls_equals_unmodified_reference(ref_aligner, small_case, monkeypatch, mode):
+    """Two sequential indexes (aligner.py:184-188,196-203,218-223): the first index's kept hits travel in hits/<sample>_hits.pkl,
+    the per-record path gets each index's hits from ONE map_batch call (the branch every GPU run takes); outputs equal the
+    unmodified reference's per-read loop."""
+    from monica_b200 import aligner as mine
+    names, seqs, reads = small_case
+    cls = _twin_batch_aligner_class()
+    fake = types.ModuleType("mappy")
+    fake.Aligner = cls
+    monkeypatch.setattr(mine, "mappy", fake)
+    got = _run(mine, names, seqs, reads, mode, True, ["Species_1"], True)
+    assert cls.calls >= 4          # two samples x two indexes
+    want = _run(ref_aligner, names, seqs, reads, mode, True, ["Species_1"], False)
+    assert got == want and any(v for v in got["alignment"].values())
+    assert got["query_files_left"] == [] and got["hits_left"] == []
