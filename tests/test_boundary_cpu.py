@@ -616,3 +616,48 @@ def test_two_index_carry_over_with_batch_calls_equals_unmodified_reference(ref_a
     want = _run(ref_aligner, names, seqs, reads, mode, True, ["Species_1"], False)
     assert got == want and any(v for v in got["alignment"].values())
     assert got["query_files_left"] == [] and got["hits_left"] == []
+
+
+def test_fastq_packer_equals_read_packer(tmp_path):
+    """mb_fastq_pack (the packed batch straight from a natively loaded FASTQ, incl. multi-line and CRLF records and an empty
+    file) holds the words, runs and upload size mb_reads_pack makes from the same sequences, and both expand to nt4 codes."""
+    import ctypes as C
+    from monica_b200 import _lib, fastx
+    L = _lib.lib()
+    rng = np.random.default_rng(17)
+    tab = _nt4_table()
+    for name, n_rec in (("some", 37), ("none", 0)):
+        p = tmp_path / f"{name}.fastq"
+        with open(p, "w", newline="") as fh:
+            for i in range(n_rec):
+                n = int(rng.integers(1, 900))
+                s = "".join(rng.choice(list("ACGTACGTACGTACGTacgtNnRU"), n))
+                if i % 6 == 0:
+                    s = s[:n // 3] + "N" * (n // 3) + s[2 * (n // 3):]
+                nl = "\r\n" if i % 5 == 3 else "\n"
+                if i % 4 == 1 and n > 100:
+                    fh.write(f"@r{i} c{nl}{s[:50]}{nl}{s[50:]}{nl}+{nl}{'I' * 50}{nl}{'I' * (len(s) - 50)}{nl}")
+                else:
+                    fh.write(f"@r{i}{nl}{s}{nl}+{nl}{'I' * len(s)}{nl}")
+        want_seqs = [str(r.seq) for r in fastx.parse(str(p), "fastq")]
+        assert len(want_seqs) == n_rec
+        fq = C.c_void_p()
+        _lib.check(L.mb_fastq_load(os.fsencode(str(p)), C.byref(fq)))
+        pk_f, pk_r = C.c_void_p(), C.c_void_p()
+        try:
+            _lib.check(L.mb_fastq_pack(fq, 3, C.byref(pk_f)))
+            cat = np.frombuffer("".join(want_seqs).encode(), np.uint8).copy() if n_rec else np.zeros(1, np.uint8)
+            off = np.concatenate([[0], np.cumsum([len(s) for s in want_seqs])]).astype(np.int64)
+            total = int(off[-1])
+            _lib.check(L.mb_reads_pack(cat.ctypes.data, off.ctypes.data, n_rec, 2, C.byref(pk_r)))
+            codes_f, iv_f = _unpack_packed(L, pk_f, total)
+            codes_r, iv_r = _unpack_packed(L, pk_r, total)
+            assert np.array_equal(codes_f, codes_r) and np.array_equal(iv_f, iv_r)
+            assert np.array_equal(codes_f, tab[cat[:total]])
+            assert L.mb_packed_upload_bytes(pk_f) == L.mb_packed_upload_bytes(pk_r)
+        finally:
+            if pk_f:
+                L.mb_packed_free(pk_f)
+            if pk_r:
+                L.mb_packed_free(pk_r)
+            L.mb_fastq_free(fq)
