@@ -48,7 +48,8 @@ def test_null_handle_accessors_answer_like_the_oracle_twin():
     out-of-range answers (mb_index_seq_len: -1 as int64, not a wrapped uint32)."""
     import ctypes as C
     from monica_b200 import _lib
-    twin = C.CDLL(os.path.join(ROOT, "oracle", "_build", "libmonica_b200_oracle.so"))
+    import abi_harness
+    twin = abi_harness.oracle_library()        # builds oracle/_build on first use
     for L in (_lib.lib(), twin):
         L.mb_index_seq_len.argtypes = [C.c_void_p, C.c_int]
         L.mb_index_seq_len.restype = C.c_int64
