@@ -392,6 +392,7 @@ _ODD_FASTQ = {
     "tab_in_title": b"@r1\tx y\nACGT\n+\nIIII\n",
     "title_ends_in_blanks": b"@r1 d  \nACGT\n+\nIIII\n@r2\t\nAC\n+\nII\n",
     "lower_case_and_iupac": b"@r1\nacgtnRYKM\n+\nIIIIIIIII\n",
+    "blank_title": b"@   \nACGT\n+\nIIII\n@\nAC\n+\nII\n",
     "blank_lines_between": b"@r1\nACGT\n+\nIIII\n\n\n@r2\nAC\n+\nII\n",
     "long_title": b"@" + b"x" * 100000 + b" c\nACGT\n+\nIIII\n",
 }
