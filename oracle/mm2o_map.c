@@ -1156,9 +1156,9 @@ mm2o_result_t *mm2o_map(const mm2o_idx_t *mi, const mm2o_opt_t *opt, const char 
 	res->n_mini = mv.n, res->n_anchor = n_a, res->rep_len = rep_len;
 	if (trace && trace->enabled) {
 		trace->mini.n = trace->mini.m = mv.n;
-		trace->mini.a = (mm128_t*)malloc((mv.n + 1) * 16); memcpy(trace->mini.a, mv.a, mv.n * 16);
+		trace->mini.a = (mm128_t*)malloc((mv.n + 1) * 16); if (mv.n) memcpy(trace->mini.a, mv.a, mv.n * 16);
 		trace->anchors.n = trace->anchors.m = n_a;
-		trace->anchors.a = (mm128_t*)malloc((n_a + 1) * 16); memcpy(trace->anchors.a, a, n_a * 16);
+		trace->anchors.a = (mm128_t*)malloc((n_a + 1) * 16); if (n_a) memcpy(trace->anchors.a, a, n_a * 16);
 	}
 	free(mv.a);
 
@@ -1171,9 +1171,9 @@ mm2o_result_t *mm2o_map(const mm2o_idx_t *mi, const mm2o_opt_t *opt, const char 
 		int64_t tot = 0;
 		for (i = 0; i < n_regs0; ++i) tot += (int32_t)u[i];
 		trace->n_u = n_regs0;
-		trace->u = (uint64_t*)malloc((n_regs0 + 1) * 8); memcpy(trace->u, u, n_regs0 * 8);
+		trace->u = (uint64_t*)malloc((n_regs0 + 1) * 8); if (n_regs0) memcpy(trace->u, u, n_regs0 * 8);
 		trace->chained.n = trace->chained.m = tot;
-		trace->chained.a = (mm128_t*)malloc((tot + 1) * 16); memcpy(trace->chained.a, a, tot * 16);
+		trace->chained.a = (mm128_t*)malloc((tot + 1) * 16); if (tot) memcpy(trace->chained.a, a, tot * 16);
 	}
 
 	regs0 = mm_gen_regs(hash, qlen, n_regs0, u, a);
