@@ -2,11 +2,13 @@
 # The CPU oracle (the parity checker and the reference arm) under AddressSanitizer + UndefinedBehaviorSanitizer: a copy of
 # oracle/ is built with -fsanitize=address,undefined in a scratch directory and driven over the test reads (edge reads, empty /
 # sub-k / all-N / homopolymer reads), a hard-case bench-style batch, 50 kb reads at 15 % error and a tandem-repeat genome.
-# Any report goes to stderr; a clean run prints only the read / hit counts.  CPU only:  bash tools/oracle_sanitize.sh
+# Then the oracle's CPU test files run against the same build.  Any report goes to stderr / is counted; a clean run prints
+# the read / hit counts and "sanitizer reports in the test run: 0".  CPU only:  bash tools/oracle_sanitize.sh
 set -e
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
 W="$(mktemp -d /tmp/oracle_san.XXXXXX)"
-cp -r "$ROOT/oracle" "$ROOT/include" "$W/"
+(cd "$ROOT" && tar --exclude=.git --exclude=gpurun_out --exclude=profiles -cf - .) | (mkdir -p "$W/repo" && cd "$W/repo" && tar xf -)
+W="$W/repo"
 rm -rf "$W/oracle/_build"
 make -s -C "$W/oracle" CFLAGS="-O1 -g -std=gnu99 -fPIC -Wall -Wno-unused-function -ffp-contract=off -msse4.1 -fsanitize=address,undefined -fno-omit-frame-pointer"
 cat > "$W/run.py" <<PY
@@ -40,4 +42,12 @@ print("tandem-repeat reads, hits:", [len(i3.map(g[100:100 + L].copy())[0]) for L
 PY
 ASAN_OPTIONS=detect_leaks=0:halt_on_error=0 UBSAN_OPTIONS=print_stacktrace=1 \
 LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.so)" python "$W/run.py"
-rm -rf "$W"
+# the oracle's own CPU test files (known answers, the Python re-derivations, the C-ABI twin, gloo sharding) on the same build
+cd "$W"
+ASAN_OPTIONS=detect_leaks=0:halt_on_error=0 UBSAN_OPTIONS=print_stacktrace=1 \
+LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.so)" \
+python -m pytest tests/test_oracle_cpu.py tests/test_oracle_abi_cpu.py tests/test_shard_cpu.py -q -s -p no:cacheprovider > "$W/out.log" 2>&1 || true
+tail -1 "$W/out.log"
+echo "sanitizer reports in the test run: $(grep -c 'AddressSanitizer\|runtime error' "$W/out.log")"
+grep -n 'AddressSanitizer\|runtime error' "$W/out.log" | head -20
+rm -rf "$(dirname "$W")"
