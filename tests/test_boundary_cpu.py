@@ -467,9 +467,13 @@ def test_native_loaders_refuse_a_cut_off_gzip(tmp_path):
     good.write_bytes(whole)
     cut.write_bytes(whole[:len(whole) // 2])
     junk.write_bytes(b"hello world\nfoo\n")
-    fq = C.c_void_p()
-    assert L.mb_fastq_load(os.fsencode(str(good)), C.byref(fq)) == 0 and L.mb_fastq_n(fq) == 3000
-    L.mb_fastq_free(fq)
+    recs = [b"@r%d\nACGTACGTAC\n+\nIIIIIIIIII\n" % i for i in range(3000)]
+    multi = tmp_path / "multi.fastq.gz"      # bgzip-style: several members, an empty one at the end, zero padding behind it
+    multi.write_bytes(b"".join(gzip.compress(b"".join(recs[i:i + 500])) for i in range(0, 3000, 500)) + gzip.compress(b"") + b"\0" * 64)
+    for ok in (good, multi):
+        fq = C.c_void_p()
+        assert L.mb_fastq_load(os.fsencode(str(ok)), C.byref(fq)) == 0 and L.mb_fastq_n(fq) == 3000
+        L.mb_fastq_free(fq)
     for bad in (cut, junk):
         fq = C.c_void_p()
         assert L.mb_fastq_load(os.fsencode(str(bad)), C.byref(fq)) == -3          # MB_ERR_IO
