@@ -158,7 +158,12 @@ def _aligner_whole_file(sample, sample_name, index, mode, mapping_quality, overn
     L = _lib.lib()
     fq = C.c_void_p()
     t0 = time.perf_counter()
-    _lib.check(L.mb_fastq_load(os.fsencode(sample), C.byref(fq)))
+    rc = L.mb_fastq_load(os.fsencode(sample), C.byref(fq))
+    if rc != 0:
+        message = L.mb_last_error().decode(errors='replace')
+        if message.startswith('malformed FASTQ'):      # what SeqIO.parse raises at aligner.py:191,212 for such a file
+            raise ValueError(message)
+        raise _lib.MonicaB200Error(rc, message)
     try:
         if not L.mb_fastq_ids_unique(fq):
             return None

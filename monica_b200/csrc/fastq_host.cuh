@@ -228,7 +228,7 @@ static void fastq_parse_sequential(mb_fastq *fq, const char *path)
 	while (p < N) {
 		int64_t e = line_end(p), le = rstrip(p, e);
 		if (le == p) { p = e + 1; continue; }                          // blank line
-		if (s[p] != '@') throw mb_error(MB_ERR_IO, std::string("unexpected line in FASTQ input: ") + path);
+		if (s[p] != '@') throw mb_error(MB_ERR_IO, std::string("malformed FASTQ: records should start with '@': ") + path);
 		const int64_t rec_begin = p;
 		const int64_t hb = p + 1;
 		int64_t hl = le - hb;
@@ -252,7 +252,10 @@ static void fastq_parse_sequential(mb_fastq *fq, const char *path)
 			p = e + 1;
 		}
 		if (n_seq_lines != 1) canonical = false;
-		if (p < N) { e = line_end(p); if (e != p + 1) canonical = false; p = e + 1; } else canonical = false;   // skip the '+' line
+		// Bio.SeqIO raises ValueError for a record without its '+' line or with unequal sequence / quality lengths (the
+		// reference's SeqIO.parse, aligner.py:191,212): a cut-off file must not be mapped as if it were whole
+		if (p >= N) throw mb_error(MB_ERR_IO, std::string("malformed FASTQ: end of file without quality information (record '") + std::string(s + hb, (size_t)std::min<int64_t>(hl, 80)) + "'): " + path);
+		e = line_end(p); if (e != p + 1) canonical = false; p = e + 1;   // skip the '+' line
 		// quality lines until as long as the sequence
 		int64_t qb = p, ql = 0; bool multi = false; size_t xb = fq->extra.size();
 		int n_lines = 0; int64_t last_e = p;
@@ -264,7 +267,8 @@ static void fastq_parse_sequential(mb_fastq *fq, const char *path)
 			ql += le - p; ++n_lines; last_e = e;
 			p = e + 1;
 		}
-		if (multi || n_lines != 1 || last_e >= N || ql != seq_len || (p - rec_begin) != (hl + 1 + 1) + (seq_len + 1) + 2 + (ql + 1)) canonical = false;
+		if (ql != seq_len) throw mb_error(MB_ERR_IO, std::string("malformed FASTQ: lengths of sequence and quality values differ for '") + std::string(s + hb, (size_t)std::min<int64_t>(hl, 80)) + "' (" + std::to_string(seq_len) + " and " + std::to_string(ql) + "): " + path);
+		if (multi || n_lines != 1 || last_e >= N || (p - rec_begin) != (hl + 1 + 1) + (seq_len + 1) + 2 + (ql + 1)) canonical = false;
 		fq->head.push_back(hb); fq->head_len.push_back(hl); fq->id_len.push_back(idl);
 		if (multi) { fq->qual.push_back((int64_t)xb); fq->qual_in_extra.push_back(1); }
 		else { fq->qual.push_back(qb); fq->qual_in_extra.push_back(0); }

@@ -58,12 +58,16 @@ def _iter_records(fn):
                 while plus and not plus.startswith("+"):
                     seq += plus.rstrip("\r\n")
                     plus = fh.readline()
+                if not plus:           # Bio.SeqIO.QualityIO.FastqGeneralIterator raises ValueError for both
+                    raise ValueError("End of file without quality information.")
                 qual = ""
                 while len(qual) < len(seq):
                     q = fh.readline()
                     if not q:
                         break
                     qual += q.rstrip("\r\n")
+                if len(qual) != len(seq):
+                    raise ValueError("Lengths of sequence and quality values differs for %s (%i and %i)." % (head.rstrip(), len(seq), len(qual)))
                 yield head, seq, qual
                 line = fh.readline()
             elif line[0] == ">":

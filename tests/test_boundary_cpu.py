@@ -383,10 +383,6 @@ _ODD_FASTQ = {
     "only_newlines": b"\n\n\n",
     "no_trailing_newline": b"@r1\nACGT\n+\nIIII",
     "crlf": b"@r1 d\r\nACGT\r\n+\r\nIIII\r\n@r2\r\nGG\r\n+\r\nII\r\n",
-    "cut_after_sequence": b"@r1\nACGT\n",
-    "cut_after_plus": b"@r1\nACGT\n+\n",
-    "quality_too_short": b"@r1\nACGT\n+\nII\n",
-    "header_only": b"@r1",
     "quality_starts_with_at": b"@r1\nACGT\n+\n@III\n@r2\nAC\n+\n@I\n",
     "empty_sequence": b"@r1\n\n+\n\n@r2\nAC\n+\nII\n",
     "tab_in_title": b"@r1\tx y\nACGT\n+\nIIII\n",
@@ -395,6 +391,17 @@ _ODD_FASTQ = {
     "blank_title": b"@   \nACGT\n+\nIIII\n@\nAC\n+\nII\n",
     "blank_lines_between": b"@r1\nACGT\n+\nIIII\n\n\n@r2\nAC\n+\nII\n",
     "long_title": b"@" + b"x" * 100000 + b" c\nACGT\n+\nIIII\n",
+}
+
+
+_MALFORMED_FASTQ = {
+    "cut_after_sequence": b"@r0\nAC\n+\nII\n@r1\nACGT\n",
+    "cut_after_plus": b"@r1\nACGT\n+\n",
+    "quality_too_short": b"@r1\nACGT\n+\nII\n",
+    "quality_too_long": b"@r1\nACGT\n+\nIIIIIIII\n@r2\nAC\n+\nII\n",
+    "header_only": b"@r1",
+    "missing_plus": b"@r1\nACGT\nIIII\n@r2\nAC\n+\nII\n",
+    "not_fastq": b"hello world\nfoo\n",
 }
 
 
@@ -437,8 +444,46 @@ def test_native_fastq_loader_on_odd_input_equals_the_seqio_mirror(tmp_path, case
     assert rc == 0
     recs, written = got
     assert recs == [(r.id, r.description, str(r.seq)) for r in want]
-    if all(len(r.qual) == len(r.seq) for r in want):
-        assert written.decode() == "".join(r.format_fastq() for r in want)
+    assert written.decode() == "".join(r.format_fastq() for r in want)
+
+
+@pytest.mark.parametrize("case", sorted(_MALFORMED_FASTQ))
+def test_malformed_fastq_fails_like_seqio(tmp_path, case):
+    """Bio.SeqIO (the reference's SeqIO.parse, aligner.py:191,212) raises ValueError for a record without its '+' line or with
+    unequal sequence / quality lengths -- what a cut-off file looks like.  The native loader answers MB_ERR_IO with a
+    'malformed FASTQ' message, the Python mirror raises ValueError, and aligner()'s whole-file route turns the former into
+    the latter."""
+    import ctypes as C
+    from monica_b200 import _lib, fastx, aligner as mine
+    p = tmp_path / "x.fastq"
+    p.write_bytes(_MALFORMED_FASTQ[case])
+    with pytest.raises(ValueError):
+        list(fastx.parse(str(p), "fastq"))
+    L = _lib.lib()
+    fq = C.c_void_p()
+    assert L.mb_fastq_load(os.fsencode(str(p)), C.byref(fq)) == -3
+    assert L.mb_last_error().decode().startswith("malformed FASTQ") and "x.fastq" in L.mb_last_error().decode()
+    for sub in ("hits", "mapped", "unmapped", "ambiguous"):
+        (tmp_path / sub).mkdir()
+
+    class NeverMapped:          # a batch-capable index: the whole-file route is taken and must fail before it maps anything
+        seq_names = []
+
+        def map_batch(self, *a, **k):
+            raise AssertionError("mapped a malformed file")
+
+        count = map_batch
+
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        with pytest.raises(ValueError):
+            mine.aligner("x.fastq", "x", NeverMapped(), mode="basic", hits_folder=str(tmp_path / "hits"), mapping_quality=60,
+                         mapped_folder=str(tmp_path / "mapped"), unmapped_folder=str(tmp_path / "unmapped"),
+                         ambiguous_folder=str(tmp_path / "ambiguous"), last_index=True)
+    finally:
+        os.chdir(cwd)
+    assert p.exists()           # the input is not consumed
 
 
 def test_fastx_title_rule_is_seqio_s():
@@ -463,10 +508,10 @@ def test_native_loaders_refuse_a_cut_off_gzip(tmp_path):
     from monica_b200 import _lib
     L = _lib.lib()
     whole = gzip.compress(b"".join(b"@r%d\nACGTACGTAC\n+\nIIIIIIIIII\n" % i for i in range(3000)))
-    good, cut, junk = tmp_path / "good.fastq.gz", tmp_path / "cut.fastq.gz", tmp_path / "junk.fastq"
+    good, cut, junk = tmp_path / "good.fastq.gz", tmp_path / "cut.fastq.gz", tmp_path / "junk.fastq.gz"
     good.write_bytes(whole)
     cut.write_bytes(whole[:len(whole) // 2])
-    junk.write_bytes(b"hello world\nfoo\n")
+    junk.write_bytes(b"\x1f\x8b" + b"\0" * 40)
     recs = [b"@r%d\nACGTACGTAC\n+\nIIIIIIIIII\n" % i for i in range(3000)]
     multi = tmp_path / "multi.fastq.gz"      # bgzip-style: several members, an empty one at the end, zero padding behind it
     multi.write_bytes(b"".join(gzip.compress(b"".join(recs[i:i + 500])) for i in range(0, 3000, 500)) + gzip.compress(b"") + b"\0" * 64)
