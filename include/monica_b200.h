@@ -173,6 +173,8 @@ int  mb_allreduce_counts(mb_index_t *idx, mb_comm_t *comm, int64_t *counts, int6
  * mb_fastq_route     SeqIO.write(seq_record, <mapped|unmapped|ambiguous|focus>) monica/genomes/aligner.py:232,236,243,265
  * The sequences come back in the concatenated layout mb_map_batch takes. */
 int  mb_fastq_load(const char *path, mb_fastq_t **out);              /* plain or gzip; multi-line records accepted */
+/* MB_ERR_IO with a message starting "malformed FASTQ" where Bio.SeqIO raises ValueError (no '+' line, unequal sequence and
+ * quality lengths, a record that does not start with '@'), and for a gzip stream that ends before its trailer. */
 int64_t mb_fastq_n(const mb_fastq_t *fq);
 const uint8_t *mb_fastq_seqs(const mb_fastq_t *fq, const int64_t **off);
 const char *mb_fastq_header(const mb_fastq_t *fq, int64_t i, int64_t *len, int32_t *id_len);
