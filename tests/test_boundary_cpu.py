@@ -712,3 +712,32 @@ def test_fastq_packer_equals_read_packer(tmp_path):
             if pk_r:
                 L.mb_packed_free(pk_r)
             L.mb_fastq_free(fq)
+
+
+def test_multi_threaded_aligner_propagates_a_malformed_file_like_the_reference(ref_aligner, small_case, tmp_path, monkeypatch):
+    """One cut-off FASTQ among the samples: pool.starmap re-raises the worker's ValueError in the reference
+    (aligner.py:96-103); the mirror does the same on its whole-file route."""
+    import standin
+    from monica_b200 import aligner as mine, synth
+    names, seqs, reads = small_case
+    cls = _twin_batch_aligner_class()
+    for mod, acls in ((mine, cls), (ref_aligner, standin.OracleAligner)):
+        d = tmp_path / mod.__name__.replace(".", "_")
+        (d / "q").mkdir(parents=True)
+        (d / "db").mkdir()
+        synth.write_fastq(str(d / "q" / "good.fastq"), reads[20:24])
+        with open(d / "q" / "cut.fastq", "wb") as fh:
+            fh.write(b"@r0\n" + reads[25].tobytes() + b"\n+\n" + b"I" * len(reads[25]) + b"\n@r1\n" + reads[26].tobytes()[:100] + b"\n")
+        synth.write_fasta_gz(str(d / "db" / "database1.fna.gz"), names, seqs)
+        fake = types.ModuleType("mappy")
+        fake.Aligner = acls
+        monkeypatch.setattr(mod, "mappy", fake)
+        cwd = os.getcwd()
+        try:
+            kw = {"genomes_path": str(d / "markers")} if mod is mine else {}
+            idx = sorted(mod.indexer(str(d / "db"), str(d / "idx"), **kw) or [os.path.join(str(d / "idx"), f) for f in os.listdir(d / "idx") if f.endswith(".mmi")])
+            with pytest.raises(ValueError):
+                mod.multi_threaded_aligner(str(d / "q"), idx, mode="basic", n_threads=2, output_folder=str(d))
+        finally:
+            os.chdir(cwd)
+        assert (d / "q" / "cut.fastq").exists()
