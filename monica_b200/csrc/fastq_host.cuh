@@ -244,7 +244,7 @@ static void fastq_parse_sequential(mb_fastq *fq, const char *path)
 		for (;;) {
 			if (p >= N) break;
 			e = line_end(p);
-			if (s[p] == '+') break;
+			if (s[p] == '+' && n_seq_lines > 0) break;                  // the line after the title is sequence whatever it starts with (Bio.SeqIO)
 			le = rstrip(p, e);
 			cat.insert(cat.end(), (const uint8_t*)s + p, (const uint8_t*)s + le);
 			seq_len += le - p; ++n_seq_lines;

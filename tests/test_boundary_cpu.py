@@ -402,6 +402,7 @@ _MALFORMED_FASTQ = {
     "header_only": b"@r1",
     "missing_plus": b"@r1\nACGT\nIIII\n@r2\nAC\n+\nII\n",
     "not_fastq": b"hello world\nfoo\n",
+    "sequence_line_missing": b"@r0\n+\n\n",        # Bio.SeqIO: the line after the title is sequence whatever it starts with
 }
 
 
